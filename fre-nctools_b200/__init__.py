@@ -1,0 +1,324 @@
+"""fre-nctools_b200 — B200-native conservative regridding (fregrid's exchange-grid path).
+
+Host-side Python mirror of the reference's C interface for this path.  Everything here is a
+thin ctypes binding over ``libxgrid_b200.so`` (include/xgrid_b200.h); there is no Python or
+CPU implementation of the math — if the CUDA library or a GPU is missing the calls raise.
+
+Mirrored reference entry points (tools/libfrencutils/create_xgrid.h:39-80):
+    create_xgrid_2dx2d_order1 / create_xgrid_2dx2d_order2 / get_grid_area / get_maxxgrid
+Batched interface (what tools/fregrid/conserve_interp.c:42 setup_conserve_interp does per
+output tile, all source tiles at once, results left in HBM):
+    XgridPlan
+
+The directory name contains a hyphen, so import it with ``load_package()`` from
+``__graft_entry__`` (or importlib) rather than a plain ``import``.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+CONSERVE_ORDER1 = 1       # globals.h:46
+CONSERVE_ORDER2 = 2       # globals.h:47
+GREAT_CIRCLE = 4096       # globals.h:58
+MONOTONIC = 16384         # globals.h:60
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+class XgridError(RuntimeError):
+    pass
+
+
+class _View(C.Structure):
+    _fields_ = [("nxgrid", C.c_longlong),
+                ("t_in", C.c_void_p), ("i_in", C.c_void_p), ("j_in", C.c_void_p),
+                ("i_out", C.c_void_p), ("j_out", C.c_void_p),
+                ("area", C.c_void_p), ("di", C.c_void_p), ("dj", C.c_void_p),
+                ("xgrid_clon", C.c_void_p), ("xgrid_clat", C.c_void_p)]
+
+
+def lib():
+    """Load (building in-tree if stale and nvcc is present) the C-ABI library."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = os.path.join(_HERE, "libxgrid_b200.so")
+    if _build.needs_build():
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        if os.path.exists(nvcc):
+            _build.build()
+        elif not os.path.exists(path):
+            raise XgridError("libxgrid_b200.so is not built and nvcc is unavailable; there is no CPU fallback")
+    L = C.CDLL(path)
+    vp = C.c_void_p
+    L.xgb_last_error.restype = C.c_char_p
+    L.xgb_plan_create.restype = vp
+    L.xgb_plan_create.argtypes = [C.c_int]
+    L.xgb_plan_destroy.argtypes = [vp]
+    L.xgb_plan_stream.restype = vp
+    L.xgb_plan_stream.argtypes = [vp]
+    L.xgb_plan_sync.argtypes = [vp]
+    L.xgb_plan_set_dst.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int]
+    L.xgb_plan_set_src.argtypes = [vp, C.c_int, _ip, _ip, vp, vp, vp, C.c_int]
+    L.xgb_plan_set_src_window.argtypes = [vp, C.c_longlong, C.c_longlong]
+    L.xgb_plan_partition.argtypes = [vp, C.c_int, C.POINTER(C.c_longlong)]
+    L.xgb_plan_generate.restype = C.c_longlong
+    L.xgb_plan_generate.argtypes = [vp, C.c_uint]
+    L.xgb_plan_last_npairs.restype = C.c_longlong
+    L.xgb_plan_last_npairs.argtypes = [vp]
+    L.xgb_plan_result_device.argtypes = [vp, C.POINTER(_View)]
+    L.xgb_plan_result_host.argtypes = [vp] + [vp] * 8
+    L.xgb_plan_result_centroids_host.argtypes = [vp, vp, vp]
+    L.xgb_plan_src_area_host.argtypes = [vp, vp]
+    L.xgb_plan_dst_area_host.argtypes = [vp, vp]
+    L.xgb_cubed_sphere_grid.argtypes = [C.c_int, vp, vp, vp, vp]
+    L.xgb_latlon_grid.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp]
+    L.xgb_ref_trig_host.restype = None
+    L.xgb_ref_trig_host.argtypes = [C.c_longlong] + [vp] * 5
+    L.xgb_ref_trig_device.argtypes = [C.c_longlong] + [vp] * 5
+    L.get_maxxgrid.restype = C.c_int
+    for name in ("create_xgrid_2dx2d_order1", "create_xgrid_2dx2d_order2"):
+        getattr(L, name).restype = C.c_int
+    _LIB = L
+    return L
+
+
+def _err():
+    return lib().xgb_last_error().decode(errors="replace")
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _f64_ptr(a):
+    """-> (pointer int, on_device flag, keepalive) for a numpy array or a CUDA torch tensor."""
+    if a is None:
+        return None, 0, None
+    if _is_torch(a):
+        import torch
+        if a.dtype != torch.float64:
+            raise TypeError("expected float64 tensor")
+        a = a.contiguous()
+        return a.data_ptr(), (1 if a.is_cuda else 0), a
+    arr = np.ascontiguousarray(a, dtype=np.float64)
+    return arr.ctypes.data, 0, arr
+
+
+# ---------------------------------------------------------------------------------------------
+# grid synthesis (host side, input preparation only)
+# ---------------------------------------------------------------------------------------------
+def cubed_sphere_grid(ni, centers=False):
+    """make_hgrid 'gnomonic_ed' C<ni> grid as fregrid reads it: (lonc, latc) each [6, ni+1, ni+1] radians."""
+    lonc = np.empty((6, ni + 1, ni + 1)); latc = np.empty_like(lonc)
+    lont = np.empty((6, ni, ni)) if centers else None
+    latt = np.empty((6, ni, ni)) if centers else None
+    rc = lib().xgb_cubed_sphere_grid(ni, lonc.ctypes.data, latc.ctypes.data,
+                                     lont.ctypes.data if centers else None, latt.ctypes.data if centers else None)
+    if rc:
+        raise XgridError("xgb_cubed_sphere_grid failed")
+    return (lonc, latc, lont, latt) if centers else (lonc, latc)
+
+
+def latlon_grid(nlon, nlat, lonbegin=0.0, lonend=360.0, latbegin=-90.0, latend=90.0):
+    """fregrid --nlon/--nlat output grid (fregrid_util.c:588-603): (lonc, latc) each [nlat+1, nlon+1] radians."""
+    lonc = np.empty((nlat + 1, nlon + 1)); latc = np.empty_like(lonc)
+    if lib().xgb_latlon_grid(nlon, nlat, lonbegin, lonend, latbegin, latend, lonc.ctypes.data, latc.ctypes.data):
+        raise XgridError("xgb_latlon_grid failed")
+    return lonc, latc
+
+
+# ---------------------------------------------------------------------------------------------
+# batched plan
+# ---------------------------------------------------------------------------------------------
+class _CudaArray:
+    """Zero-copy device array descriptor (CUDA array interface v3) for torch.as_tensor."""
+
+    def __init__(self, ptr, n, typestr, owner):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
+        self._owner = owner
+
+
+class XgridPlan:
+    """Exchange-grid generation for one destination tile and a source mosaic on one GPU."""
+
+    def __init__(self, device=0):
+        self._L = lib()
+        self._p = self._L.xgb_plan_create(int(device))
+        if not self._p:
+            raise XgridError(_err())
+        self.device = int(device)
+        self.ncell_src = 0
+        self.nxgrid = -1
+        self.order = 0
+
+    def close(self):
+        if getattr(self, "_p", None):
+            self._L.xgb_plan_destroy(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise XgridError(_err())
+
+    @property
+    def stream(self):
+        return self._L.xgb_plan_stream(self._p)
+
+    def sync(self):
+        self._ck(self._L.xgb_plan_sync(self._p))
+
+    def set_dst(self, lon, lat):
+        """lon/lat: [ny+1, nx+1] vertex arrays (numpy, or float64 CUDA tensors)."""
+        ny, nx = lon.shape[0] - 1, lon.shape[1] - 1
+        pl, dl, kl = _f64_ptr(lon); pa, da, ka = _f64_ptr(lat)
+        if dl != da:
+            raise TypeError("lon and lat must live on the same side")
+        self._ck(self._L.xgb_plan_set_dst(self._p, nx, ny, pl, pa, dl))
+        self.nx_dst, self.ny_dst = nx, ny
+
+    def set_src(self, lons, lats, mask=None):
+        """lons/lats: list of per-tile [ny+1, nx+1] arrays, or one [ntiles, ny+1, nx+1] array."""
+        if not isinstance(lons, (list, tuple)):
+            lons = [lons[t] for t in range(lons.shape[0])] if lons.ndim == 3 else [lons]
+            lats = [lats[t] for t in range(lats.shape[0])] if lats.ndim == 3 else [lats]
+        nx = (C.c_int * len(lons))(*[int(a.shape[1] - 1) for a in lons])
+        ny = (C.c_int * len(lons))(*[int(a.shape[0] - 1) for a in lons])
+        if _is_torch(lons[0]):
+            import torch
+            lon = torch.cat([a.reshape(-1) for a in lons]); lat = torch.cat([a.reshape(-1) for a in lats])
+        else:
+            lon = np.concatenate([np.asarray(a, dtype=np.float64).ravel() for a in lons])
+            lat = np.concatenate([np.asarray(a, dtype=np.float64).ravel() for a in lats])
+        pl, dl, kl = _f64_ptr(lon); pa, da, ka = _f64_ptr(lat)
+        pm, dm, km = _f64_ptr(mask)
+        if dl != da or (mask is not None and dm != dl):
+            raise TypeError("lon, lat and mask must live on the same side")
+        self._ck(self._L.xgb_plan_set_src(self._p, len(lons), nx, ny, pl, pa, pm, dl))
+        self.tiles = [(int(nx[t]), int(ny[t])) for t in range(len(lons))]
+        self.ncell_src = sum(a * b for a, b in self.tiles)
+
+    def set_src_window(self, begin, end):
+        self._ck(self._L.xgb_plan_set_src_window(self._p, int(begin), int(end)))
+
+    def partition(self, nparts):
+        b = (C.c_longlong * (nparts + 1))()
+        self._ck(self._L.xgb_plan_partition(self._p, nparts, b))
+        return [int(v) for v in b]
+
+    def generate(self, opcode):
+        n = self._L.xgb_plan_generate(self._p, int(opcode))
+        if n < 0:
+            raise XgridError(_err())
+        self.nxgrid = int(n)
+        self.order = 2 if (opcode & CONSERVE_ORDER2) else 1
+        return self.nxgrid
+
+    @property
+    def npairs(self):
+        return int(self._L.xgb_plan_last_npairs(self._p))
+
+    def result_host(self):
+        n = self.nxgrid
+        out = {k: np.empty(n, np.int32) for k in ("t_in", "i_in", "j_in", "i_out", "j_out")}
+        out["area"] = np.empty(n)
+        if self.order == 2:
+            out["di"] = np.empty(n); out["dj"] = np.empty(n)
+        args = [out[k].ctypes.data for k in ("t_in", "i_in", "j_in", "i_out", "j_out", "area")]
+        args += [out["di"].ctypes.data, out["dj"].ctypes.data] if self.order == 2 else [None, None]
+        self._ck(self._L.xgb_plan_result_host(self._p, *args))
+        if self.order == 2:
+            out["xgrid_clon"] = np.empty(n); out["xgrid_clat"] = np.empty(n)
+            self._ck(self._L.xgb_plan_result_centroids_host(self._p, out["xgrid_clon"].ctypes.data, out["xgrid_clat"].ctypes.data))
+        return out
+
+    def result_device(self):
+        """Zero-copy torch views of the device-resident result (valid until the next generate)."""
+        import torch
+        v = _View()
+        self._ck(self._L.xgb_plan_result_device(self._p, C.byref(v)))
+        n = int(v.nxgrid)
+        dev = torch.device("cuda", self.device)
+        out = {}
+        for k in ("t_in", "i_in", "j_in", "i_out", "j_out"):
+            out[k] = torch.as_tensor(_CudaArray(getattr(v, k), n, "<i4", self), device=dev) if n else torch.empty(0, dtype=torch.int32, device=dev)
+        for k in ("area", "di", "dj", "xgrid_clon", "xgrid_clat"):
+            ptr = getattr(v, k)
+            if ptr:
+                out[k] = torch.as_tensor(_CudaArray(ptr, n, "<f8", self), device=dev) if n else torch.empty(0, dtype=torch.float64, device=dev)
+        return out
+
+    def src_area(self):
+        a = np.empty(self.ncell_src)
+        self._ck(self._L.xgb_plan_src_area_host(self._p, a.ctypes.data))
+        return a
+
+    def dst_area(self):
+        a = np.empty(self.nx_dst * self.ny_dst)
+        self._ck(self._L.xgb_plan_dst_area_host(self._p, a.ctypes.data))
+        return a
+
+
+# ---------------------------------------------------------------------------------------------
+# reference-signature calls (host buffers in, host buffers out), as fregrid makes them
+# (conserve_interp.c:186-200): outputs are allocated at get_maxxgrid() like the reference's callers.
+# ---------------------------------------------------------------------------------------------
+def get_maxxgrid():
+    return int(lib().get_maxxgrid())
+
+
+def _create_xgrid(order, lon_in, lat_in, lon_out, lat_out, mask_in=None, capacity=None):
+    L = lib()
+    lon_in = np.ascontiguousarray(lon_in, np.float64); lat_in = np.ascontiguousarray(lat_in, np.float64)
+    lon_out = np.ascontiguousarray(lon_out, np.float64); lat_out = np.ascontiguousarray(lat_out, np.float64)
+    nlat_in, nlon_in = lon_in.shape[0] - 1, lon_in.shape[1] - 1
+    nlat_out, nlon_out = lon_out.shape[0] - 1, lon_out.shape[1] - 1
+    if mask_in is None:
+        mask_in = np.ones(nlon_in * nlat_in)
+    mask_in = np.ascontiguousarray(mask_in, np.float64)
+    cap = int(capacity or get_maxxgrid())
+    ii, ji, io, jo = (np.empty(cap, np.int32) for _ in range(4))
+    xa = np.empty(cap)
+    ci = lambda v: C.byref(C.c_int(v))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    if order == 1:
+        n = L.create_xgrid_2dx2d_order1(ci(nlon_in), ci(nlat_in), ci(nlon_out), ci(nlat_out), p(lon_in), p(lat_in),
+                                        p(lon_out), p(lat_out), p(mask_in), p(ii), p(ji), p(io), p(jo), p(xa))
+        return n, ii[:n], ji[:n], io[:n], jo[:n], xa[:n]
+    xc = np.empty(cap); yc = np.empty(cap)
+    n = L.create_xgrid_2dx2d_order2(ci(nlon_in), ci(nlat_in), ci(nlon_out), ci(nlat_out), p(lon_in), p(lat_in),
+                                    p(lon_out), p(lat_out), p(mask_in), p(ii), p(ji), p(io), p(jo), p(xa), p(xc), p(yc))
+    return n, ii[:n], ji[:n], io[:n], jo[:n], xa[:n], xc[:n], yc[:n]
+
+
+def create_xgrid_2dx2d_order1(lon_in, lat_in, lon_out, lat_out, mask_in=None):
+    """create_xgrid.c:621 — returns (nxgrid, i_in, j_in, i_out, j_out, xgrid_area)."""
+    return _create_xgrid(1, lon_in, lat_in, lon_out, lat_out, mask_in)
+
+
+def create_xgrid_2dx2d_order2(lon_in, lat_in, lon_out, lat_out, mask_in=None):
+    """create_xgrid.c:893 — returns (nxgrid, i_in, j_in, i_out, j_out, xgrid_area, xgrid_clon, xgrid_clat)."""
+    return _create_xgrid(2, lon_in, lat_in, lon_out, lat_out, mask_in)
+
+
+def get_grid_area(lon, lat):
+    """create_xgrid.c:66 — cell areas [ny, nx] in m^2."""
+    lon = np.ascontiguousarray(lon, np.float64); lat = np.ascontiguousarray(lat, np.float64)
+    ny, nx = lon.shape[0] - 1, lon.shape[1] - 1
+    area = np.empty((ny, nx))
+    lib().get_grid_area(C.byref(C.c_int(nx)), C.byref(C.c_int(ny)), lon.ctypes.data_as(C.c_void_p),
+                        lat.ctypes.data_as(C.c_void_p), area.ctypes.data_as(C.c_void_p))
+    return area

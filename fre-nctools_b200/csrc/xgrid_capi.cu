@@ -1,0 +1,518 @@
+// C-ABI layer of libxgrid_b200 (see include/xgrid_b200.h).
+// Plan management, host<->device staging, and the reference-signature entry points.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "../../include/xgrid_b200.h"
+#include "xgrid_internal.h"
+#include "xgrid_plan.h"
+
+using namespace xgb;
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void xgb_set_error(const char* fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* xgb_last_error(void) { return g_err; }
+
+// The reference's error_handler (mosaic_util.c:57-65): message on stderr, exit(1).
+[[noreturn]] static void fatal(const char* msg)
+{
+  fprintf(stderr, "FATAL Error: %s\n", msg);
+  exit(1);
+}
+
+#define CU_OK(call)                                                                         \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      xgb_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return 1;                                                                             \
+    }                                                                                       \
+  } while (0)
+
+int DevBuf::reserve(size_t bytes)
+{
+  if (bytes <= cap) return 0;
+  if (p) { cudaFree(p); p = nullptr; cap = 0; }
+  // grow geometrically so repeated generates with slowly varying sizes do not re-allocate
+  size_t want = bytes + bytes / 8 + 256;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    xgb_set_error("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+    p = nullptr; cap = 0;
+    return 1;
+  }
+  cap = want;
+  return 0;
+}
+void DevBuf::release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+
+extern "C" int xgb_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------------
+extern "C" xgb_plan* xgb_plan_create(int device)
+{
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    xgb_set_error("no CUDA device available (%s); libxgrid_b200 has no CPU path", cudaGetErrorString(e));
+    return nullptr;
+  }
+  if (device < 0 || device >= ndev) { xgb_set_error("device %d out of range (have %d)", device, ndev); return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess) { xgb_set_error("cudaSetDevice(%d) failed", device); return nullptr; }
+  xgb_plan* p = new xgb_plan();
+  p->device = device;
+  if (cudaStreamCreateWithFlags(&p->st, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMalloc(&p->err_dev, sizeof(int)) != cudaSuccess ||
+      cudaMalloc(&p->total_dev, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMallocHost(&p->total_host, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMallocHost(&p->err_host, sizeof(int)) != cudaSuccess) {
+    xgb_set_error("plan resource allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete p;
+    return nullptr;
+  }
+  cudaMemsetAsync(p->err_dev, 0, sizeof(int), p->st);
+  return p;
+}
+
+extern "C" void xgb_plan_destroy(xgb_plan* p)
+{
+  if (!p) return;
+  cudaSetDevice(p->device);
+  cudaStreamSynchronize(p->st);
+  DevBuf* bufs[] = {&p->dst_lon, &p->dst_lat, &p->dst_store, &p->pyr_store, &p->src_lon, &p->src_lat, &p->mask,
+                    &p->src_store, &p->tiles_dev, &p->cnt, &p->pair_off, &p->out_off, &p->pairs, &p->parea,
+                    &p->pclon, &p->pclat, &p->scan_tmp, &p->t_in, &p->i_in, &p->j_in, &p->i_out, &p->j_out,
+                    &p->area, &p->clon, &p->clat, &p->di, &p->dj, &p->bounds_dev,
+                    &p->gc_src_xyz, &p->gc_dst_xyz};
+  for (DevBuf* b : bufs) b->release();
+  xgb_apply_release(p);
+  if (p->err_dev) cudaFree(p->err_dev);
+  if (p->total_dev) cudaFree(p->total_dev);
+  if (p->total_host) cudaFreeHost(p->total_host);
+  if (p->err_host) cudaFreeHost(p->err_host);
+  if (p->st) cudaStreamDestroy(p->st);
+  delete p;
+}
+
+extern "C" void* xgb_plan_stream(xgb_plan* p) { return p ? (void*)p->st : nullptr; }
+
+extern "C" int xgb_plan_sync(xgb_plan* p)
+{
+  if (!p) { xgb_set_error("null plan"); return 1; }
+  CU_OK(cudaSetDevice(p->device));
+  CU_OK(cudaStreamSynchronize(p->st));
+  return 0;
+}
+
+static int carve_cellset(DevBuf& store, long long ncell, CellSet* cs)
+{
+  const size_t nd = (size_t)ncell;
+  const size_t bytes = nd * sizeof(double) * (6 + 2 * kMaxV) + nd + 64;
+  if (store.reserve(bytes)) return 1;
+  double* b = (double*)store.p;
+  cs->ncell = ncell;
+  cs->ymin = b; b += nd; cs->ymax = b; b += nd;
+  cs->xmin = b; b += nd; cs->xmax = b; b += nd;
+  cs->xavg = b; b += nd; cs->area = b; b += nd;
+  cs->vx = b; b += nd * kMaxV;
+  cs->vy = b; b += nd * kMaxV;
+  cs->nv = (unsigned char*)b;
+  return 0;
+}
+
+static int upload(DevBuf& dst, const double* src, size_t n, int on_device, cudaStream_t st)
+{
+  if (dst.reserve(n * sizeof(double))) return 1;
+  CU_OK(cudaMemcpyAsync(dst.p, src, n * sizeof(double), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
+static int check_kernel_errors(xgb_plan* p, bool fatal_like_reference)
+{
+  CU_OK(cudaMemcpyAsync(p->err_host, p->err_dev, sizeof(int), cudaMemcpyDeviceToHost, p->st));
+  CU_OK(cudaStreamSynchronize(p->st));
+  CU_OK(cudaGetLastError());
+  const int e = *p->err_host;
+  if (e == 0) return 0;
+  cudaMemsetAsync(p->err_dev, 0, sizeof(int), p->st);
+  const char* msg = "internal kernel error";
+  if (e & kErrTooManyVertices) msg = "create_xgrid.c: n2_in is greater than MAX_V";
+  else if (e & kErrParallelEdges)
+    msg = "the line between <x1_0,y1_0> and  <x1_1,y1_1> should not parallel to the line between <x2_0,y2_0> and  <x2_1,y2_1>";
+  else if (e & kErrClipOverflow) msg = "clip_2dx2d: clipped polygon has more than MV vertices";
+  else if (e & kErrStackOverflow) msg = "candidate search: traversal stack exhausted";
+  else if (e & kErrGcNotConvex) msg = "create_xgrid.c(clip_2dx2d_great_circle): grid box is not convex";
+  else if (e & kErrGcWalk) msg = "clip_2dx2d_great_circle: polygon walk did not return to the first intersection";
+  else if (e & kErrGcNodePool) msg = "getNext: curListPos >= MAXNODELIST";
+  if (fatal_like_reference) fatal(msg);
+  xgb_set_error("%s (kernel error bits 0x%x)", msg, e);
+  return 1;
+}
+
+extern "C" int xgb_plan_set_dst(xgb_plan* p, int nx, int ny, const double* lon, const double* lat, int on_device)
+{
+  if (!p || nx <= 0 || ny <= 0 || !lon || !lat) { xgb_set_error("xgb_plan_set_dst: bad arguments"); return 1; }
+  CU_OK(cudaSetDevice(p->device));
+  const size_t nv = (size_t)(nx + 1) * (ny + 1);
+  const long long nc = (long long)nx * ny;
+  if (nc >= (1ll << 31)) { xgb_set_error("destination tile too large for 32-bit cell indices"); return 1; }
+  if (upload(p->dst_lon, lon, nv, on_device, p->st) || upload(p->dst_lat, lat, nv, on_device, p->st)) return 1;
+  if (carve_cellset(p->dst_store, nc, &p->dst)) return 1;
+  p->nx2 = nx; p->ny2 = ny;
+  TileDesc td{nx, ny, 0, 0};
+  launch_cell_precompute(td, (const double*)p->dst_lon.p, (const double*)p->dst_lat.p, p->dst, p->err_dev, p->st);
+
+  // pyramid: level 0 aliases the cell arrays, upper levels live in pyr_store
+  Pyramid& P = p->pyr;
+  P.nlev = 1;
+  P.lev[0] = PyrLevel{nx, ny, p->dst.ymin, p->dst.ymax, p->dst.xmin, p->dst.xmax};
+  size_t upper = 0;
+  {
+    int lx = nx, ly = ny;
+    while ((long long)lx * ly > 32 && P.nlev < kMaxLevels) {
+      lx = (lx + 1) / 2; ly = (ly + 1) / 2;
+      upper += (size_t)lx * ly;
+      P.lev[P.nlev].nx = lx; P.lev[P.nlev].ny = ly;
+      ++P.nlev;
+    }
+  }
+  if (p->pyr_store.reserve(upper * 4 * sizeof(double) + 64)) return 1;
+  double* b = (double*)p->pyr_store.p;
+  for (int l = 1; l < P.nlev; ++l) {
+    const size_t n = (size_t)P.lev[l].nx * P.lev[l].ny;
+    double *a0 = b, *a1 = b + n, *a2 = b + 2 * n, *a3 = b + 3 * n;
+    b += 4 * n;
+    launch_pyramid_level(P.lev[l - 1], a0, a1, a2, a3, P.lev[l].nx, P.lev[l].ny, p->st);
+    P.lev[l].ymin = a0; P.lev[l].ymax = a1; P.lev[l].xmin = a2; P.lev[l].xmax = a3;
+  }
+  p->have_dst = true;
+  p->gc_dst_ready = false;
+  return check_kernel_errors(p, false);
+}
+
+extern "C" int xgb_plan_set_src(xgb_plan* p, int ntiles, const int* nx, const int* ny,
+                                const double* lon, const double* lat, const double* mask, int on_device)
+{
+  if (!p || ntiles <= 0 || !nx || !ny || !lon || !lat) { xgb_set_error("xgb_plan_set_src: bad arguments"); return 1; }
+  CU_OK(cudaSetDevice(p->device));
+  p->tiles.clear();
+  long long coff = 0, voff = 0;
+  for (int n = 0; n < ntiles; ++n) {
+    if (nx[n] <= 0 || ny[n] <= 0) { xgb_set_error("xgb_plan_set_src: empty tile %d", n); return 1; }
+    p->tiles.push_back(TileDesc{nx[n], ny[n], coff, voff});
+    coff += (long long)nx[n] * ny[n];
+    voff += (long long)(nx[n] + 1) * (ny[n] + 1);
+  }
+  if (coff >= (1ll << 31)) { xgb_set_error("source mosaic too large for 32-bit cell indices"); return 1; }
+  if (upload(p->src_lon, lon, (size_t)voff, on_device, p->st) || upload(p->src_lat, lat, (size_t)voff, on_device, p->st)) return 1;
+  p->has_mask = (mask != nullptr);
+  if (mask && upload(p->mask, mask, (size_t)coff, on_device, p->st)) return 1;
+  if (p->tiles_dev.reserve(sizeof(TileDesc) * ntiles)) return 1;
+  CU_OK(cudaMemcpyAsync(p->tiles_dev.p, p->tiles.data(), sizeof(TileDesc) * ntiles, cudaMemcpyHostToDevice, p->st));
+  if (carve_cellset(p->src_store, coff, &p->src)) return 1;
+  for (int n = 0; n < ntiles; ++n)
+    launch_cell_precompute(p->tiles[n], (const double*)p->src_lon.p, (const double*)p->src_lat.p, p->src, p->err_dev, p->st);
+  p->s0 = 0; p->ns = coff;
+  p->have_src = true;
+  p->gc_src_ready = false;
+  // the tile table was copied from pageable host memory: make sure it has landed before `tiles` can change
+  return check_kernel_errors(p, false);
+}
+
+extern "C" int xgb_plan_set_src_window(xgb_plan* p, long long begin, long long end)
+{
+  if (!p || !p->have_src) { xgb_set_error("xgb_plan_set_src_window: no source grid"); return 1; }
+  if (begin < 0 || end < begin || end > p->src.ncell) { xgb_set_error("xgb_plan_set_src_window: bad window"); return 1; }
+  p->s0 = begin; p->ns = end - begin;
+  return 0;
+}
+
+// count pass + scan over [s0, s0+ns); leaves pair_off (ns+1 entries) and the total on the host
+static int count_candidates(xgb_plan* p, long long s0, long long ns, unsigned long long* total)
+{
+  if (p->cnt.reserve((size_t)(ns + 1) * sizeof(uint32_t)) || p->pair_off.reserve((size_t)(ns + 1) * sizeof(uint32_t)) ||
+      p->scan_tmp.reserve(scan_tmp_bytes(ns)))
+    return 1;
+  launch_candidates(false, p->src, s0, ns, p->has_mask ? (const double*)p->mask.p : nullptr, p->pyr, p->dst,
+                    nullptr, (uint32_t*)p->cnt.p, nullptr, p->err_dev, p->st);
+  launch_exclusive_scan((const uint32_t*)p->cnt.p, (uint32_t*)p->pair_off.p, ns, p->total_dev, p->scan_tmp.p, p->st);
+  CU_OK(cudaMemcpyAsync(p->total_host, p->total_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->st));
+  CU_OK(cudaStreamSynchronize(p->st));
+  *total = p->total_host[0];
+  if (*total >= (1ull << 32)) { xgb_set_error("more than 2^32 candidate pairs in one window; shard the source cells"); return 1; }
+  return 0;
+}
+
+extern "C" int xgb_plan_partition(xgb_plan* p, int nparts, long long* bounds)
+{
+  if (!p || !p->have_src || !p->have_dst || nparts <= 0 || !bounds) { xgb_set_error("xgb_plan_partition: bad arguments"); return 1; }
+  CU_OK(cudaSetDevice(p->device));
+  unsigned long long total = 0;
+  const long long nc = p->src.ncell;
+  if (count_candidates(p, 0, nc, &total)) return 1;
+  if (p->bounds_dev.reserve((size_t)(nparts + 1) * sizeof(long long))) return 1;
+  launch_partition((const uint32_t*)p->pair_off.p, nc, total, nparts, (long long*)p->bounds_dev.p, p->st);
+  CU_OK(cudaMemcpyAsync(bounds, p->bounds_dev.p, (size_t)(nparts + 1) * sizeof(long long), cudaMemcpyDeviceToHost, p->st));
+  CU_OK(cudaStreamSynchronize(p->st));
+  return 0;
+}
+
+extern "C" long long xgb_plan_generate(xgb_plan* p, unsigned int opcode)
+{
+  if (!p || !p->have_src || !p->have_dst) { xgb_set_error("xgb_plan_generate: set source and destination grids first"); return -1; }
+  const int order = (opcode & XGB_CONSERVE_ORDER2) ? 2 : 1;
+  if (!(opcode & (XGB_CONSERVE_ORDER1 | XGB_CONSERVE_ORDER2))) {
+    xgb_set_error("conserve_interp: interp_method should be CONSERVE_ORDER1 or CONSERVE_ORDER2");   // conserve_interp.c:230
+    return -1;
+  }
+  if (cudaSetDevice(p->device) != cudaSuccess) { xgb_set_error("cudaSetDevice failed"); return -1; }
+  if (opcode & XGB_GREAT_CIRCLE) return xgb_generate_great_circle(p, order);
+
+  const long long s0 = p->s0, ns = p->ns;
+  const double* mask = p->has_mask ? (const double*)p->mask.p : nullptr;
+  unsigned long long npairs = 0;
+  if (count_candidates(p, s0, ns, &npairs)) return -1;
+  p->npairs = npairs;
+
+  if (p->pairs.reserve((size_t)npairs * sizeof(int2) + 16) || p->parea.reserve((size_t)npairs * sizeof(double) + 16) ||
+      p->out_off.reserve((size_t)(ns + 1) * sizeof(uint32_t)))
+    return -1;
+  if (order == 2 && (p->pclon.reserve((size_t)npairs * sizeof(double) + 16) || p->pclat.reserve((size_t)npairs * sizeof(double) + 16)))
+    return -1;
+
+  launch_candidates(true, p->src, s0, ns, mask, p->pyr, p->dst, (const uint32_t*)p->pair_off.p,
+                    nullptr, (int2*)p->pairs.p, p->err_dev, p->st);
+  cudaMemsetAsync(p->cnt.p, 0, (size_t)(ns + 1) * sizeof(uint32_t), p->st);
+  launch_clip(order, p->src, p->dst, mask, (const int2*)p->pairs.p, npairs, s0,
+              (double*)p->parea.p, (double*)p->pclon.p, (double*)p->pclat.p, (uint32_t*)p->cnt.p, p->err_dev, p->st);
+  launch_exclusive_scan((const uint32_t*)p->cnt.p, (uint32_t*)p->out_off.p, ns, p->total_dev + 1, p->scan_tmp.p, p->st);
+  if (cudaMemcpyAsync(p->total_host + 1, p->total_dev + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->st) != cudaSuccess ||
+      cudaStreamSynchronize(p->st) != cudaSuccess) {
+    xgb_set_error("xgrid generation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return -1;
+  }
+  const unsigned long long nx = p->total_host[1];
+  p->nxgrid = (long long)nx;
+  p->order = order;
+
+  const size_t ni = (size_t)nx * sizeof(int) + 16, nd = (size_t)nx * sizeof(double) + 16;
+  if (p->t_in.reserve(ni) || p->i_in.reserve(ni) || p->j_in.reserve(ni) || p->i_out.reserve(ni) || p->j_out.reserve(ni) ||
+      p->area.reserve(nd))
+    return -1;
+  if (order == 2 && (p->clon.reserve(nd) || p->clat.reserve(nd) || p->di.reserve(nd) || p->dj.reserve(nd))) return -1;
+
+  launch_scatter(order, (const int2*)p->pairs.p, npairs, (const double*)p->parea.p, (const double*)p->pclon.p,
+                 (const double*)p->pclat.p, (const uint32_t*)p->pair_off.p, (const uint32_t*)p->out_off.p,
+                 (const TileDesc*)p->tiles_dev.p, (int)p->tiles.size(), s0, p->nx2,
+                 (int*)p->t_in.p, (int*)p->i_in.p, (int*)p->j_in.p, (int*)p->i_out.p, (int*)p->j_out.p,
+                 (double*)p->area.p, (double*)p->clon.p, (double*)p->clat.p, p->st);
+  if (order == 2)
+    launch_order2_finalize(p->src, s0, ns, (const uint32_t*)p->out_off.p, (const double*)p->area.p,
+                           (const double*)p->clon.p, (const double*)p->clat.p, (double*)p->di.p, (double*)p->dj.p, p->st);
+  if (check_kernel_errors(p, false)) return -1;
+  return p->nxgrid;
+}
+
+extern "C" long long xgb_plan_last_npairs(xgb_plan* p) { return p ? (long long)p->npairs : -1; }
+
+extern "C" int xgb_plan_result_device(xgb_plan* p, xgb_xgrid_view* v)
+{
+  if (!p || !v || p->nxgrid < 0) { xgb_set_error("xgb_plan_result_device: no result"); return 1; }
+  v->nxgrid = p->nxgrid;
+  v->t_in = (int*)p->t_in.p; v->i_in = (int*)p->i_in.p; v->j_in = (int*)p->j_in.p;
+  v->i_out = (int*)p->i_out.p; v->j_out = (int*)p->j_out.p;
+  v->area = (double*)p->area.p;
+  const bool o2 = (p->order == 2);
+  v->di = o2 ? (double*)p->di.p : nullptr; v->dj = o2 ? (double*)p->dj.p : nullptr;
+  v->xgrid_clon = o2 ? (double*)p->clon.p : nullptr; v->xgrid_clat = o2 ? (double*)p->clat.p : nullptr;
+  return 0;
+}
+
+static int d2h(void* dst, const void* src, size_t bytes, cudaStream_t st)
+{
+  if (!dst || bytes == 0) return 0;
+  CU_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+extern "C" int xgb_plan_result_host(xgb_plan* p, int* t_in, int* i_in, int* j_in, int* i_out, int* j_out,
+                                    double* area, double* di, double* dj)
+{
+  if (!p || p->nxgrid < 0) { xgb_set_error("xgb_plan_result_host: no result"); return 1; }
+  CU_OK(cudaSetDevice(p->device));
+  const size_t n = (size_t)p->nxgrid;
+  if (d2h(t_in, p->t_in.p, n * sizeof(int), p->st) || d2h(i_in, p->i_in.p, n * sizeof(int), p->st) ||
+      d2h(j_in, p->j_in.p, n * sizeof(int), p->st) || d2h(i_out, p->i_out.p, n * sizeof(int), p->st) ||
+      d2h(j_out, p->j_out.p, n * sizeof(int), p->st) || d2h(area, p->area.p, n * sizeof(double), p->st))
+    return 1;
+  if (p->order == 2 && (d2h(di, p->di.p, n * sizeof(double), p->st) || d2h(dj, p->dj.p, n * sizeof(double), p->st))) return 1;
+  CU_OK(cudaStreamSynchronize(p->st));
+  return 0;
+}
+
+extern "C" int xgb_plan_result_centroids_host(xgb_plan* p, double* xclon, double* xclat)
+{
+  if (!p || p->nxgrid < 0 || p->order != 2) { xgb_set_error("xgb_plan_result_centroids_host: no order-2 result"); return 1; }
+  CU_OK(cudaSetDevice(p->device));
+  const size_t n = (size_t)p->nxgrid;
+  if (d2h(xclon, p->clon.p, n * sizeof(double), p->st) || d2h(xclat, p->clat.p, n * sizeof(double), p->st)) return 1;
+  CU_OK(cudaStreamSynchronize(p->st));
+  return 0;
+}
+
+extern "C" int xgb_plan_src_area_host(xgb_plan* p, double* area)
+{
+  if (!p || !p->have_src) { xgb_set_error("no source grid"); return 1; }
+  CU_OK(cudaSetDevice(p->device));
+  if (d2h(area, p->src.area, (size_t)p->src.ncell * sizeof(double), p->st)) return 1;
+  CU_OK(cudaStreamSynchronize(p->st));
+  return 0;
+}
+
+extern "C" int xgb_plan_dst_area_host(xgb_plan* p, double* area)
+{
+  if (!p || !p->have_dst) { xgb_set_error("no destination grid"); return 1; }
+  CU_OK(cudaSetDevice(p->device));
+  if (d2h(area, p->dst.area, (size_t)p->dst.ncell * sizeof(double), p->st)) return 1;
+  CU_OK(cudaStreamSynchronize(p->st));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Part 1: reference-signature entry points.  One process-wide plan on device XGB_DEVICE (default 0),
+// mirroring the reference's single-threaded, non-reentrant callers.
+// ---------------------------------------------------------------------------------------------
+static xgb_plan* default_plan()
+{
+  static xgb_plan* plan = nullptr;
+  if (!plan) {
+    const char* env = getenv("XGB_DEVICE");
+    plan = xgb_plan_create(env ? atoi(env) : 0);
+    if (!plan) fatal(xgb_last_error());
+  }
+  return plan;
+}
+
+#ifndef XGB_MAXXGRID
+#define XGB_MAXXGRID 5e6            /* create_xgrid.h:22-28, serial build */
+#endif
+
+extern "C" int get_maxxgrid(void) { return (int)XGB_MAXXGRID; }
+
+extern "C" void get_grid_area(const int* nlon, const int* nlat, const double* lon, const double* lat, double* area)
+{
+  xgb_plan* p = default_plan();
+  if (xgb_plan_set_dst(p, *nlon, *nlat, lon, lat, 0) || xgb_plan_dst_area_host(p, area)) fatal(xgb_last_error());
+}
+
+static int create_xgrid_2dx2d(int order, const int* nlon_in, const int* nlat_in, const int* nlon_out, const int* nlat_out,
+                              const double* lon_in, const double* lat_in, const double* lon_out, const double* lat_out,
+                              const double* mask_in, int* i_in, int* j_in, int* i_out, int* j_out,
+                              double* xgrid_area, double* xgrid_clon, double* xgrid_clat)
+{
+  xgb_plan* p = default_plan();
+  if (xgb_plan_set_dst(p, *nlon_out, *nlat_out, lon_out, lat_out, 0)) fatal(xgb_last_error());
+  if (xgb_plan_set_src(p, 1, nlon_in, nlat_in, lon_in, lat_in, mask_in, 0)) fatal(xgb_last_error());
+  // kernel-raised conditions that the reference treats as fatal are fatal here too
+  const long long n = xgb_plan_generate(p, order == 2 ? XGB_CONSERVE_ORDER2 : XGB_CONSERVE_ORDER1);
+  if (n < 0) fatal(xgb_last_error());
+  if (n >= (long long)XGB_MAXXGRID)                                     // create_xgrid.c:809-812
+    fatal("The xgrid size is too large for resources.\n"
+          " nxgrid is greater than MAXXGRID/nthreads; increase MAXXGRID,\n"
+          " decrease nthreads, or increase number of MPI ranks.");
+  if (xgb_plan_result_host(p, nullptr, i_in, j_in, i_out, j_out, xgrid_area, nullptr, nullptr)) fatal(xgb_last_error());
+  if (order == 2 && xgb_plan_result_centroids_host(p, xgrid_clon, xgrid_clat)) fatal(xgb_last_error());
+  return (int)n;
+}
+
+extern "C" int create_xgrid_2dx2d_order1(const int* nlon_in, const int* nlat_in, const int* nlon_out, const int* nlat_out,
+                                         const double* lon_in, const double* lat_in, const double* lon_out, const double* lat_out,
+                                         const double* mask_in, int* i_in, int* j_in, int* i_out, int* j_out, double* xgrid_area)
+{
+  return create_xgrid_2dx2d(1, nlon_in, nlat_in, nlon_out, nlat_out, lon_in, lat_in, lon_out, lat_out, mask_in,
+                            i_in, j_in, i_out, j_out, xgrid_area, nullptr, nullptr);
+}
+
+extern "C" int create_xgrid_2dx2d_order2(const int* nlon_in, const int* nlat_in, const int* nlon_out, const int* nlat_out,
+                                         const double* lon_in, const double* lat_in, const double* lon_out, const double* lat_out,
+                                         const double* mask_in, int* i_in, int* j_in, int* i_out, int* j_out,
+                                         double* xgrid_area, double* xgrid_clon, double* xgrid_clat)
+{
+  return create_xgrid_2dx2d(2, nlon_in, nlat_in, nlon_out, nlat_out, lon_in, lat_in, lon_out, lat_out, mask_in,
+                            i_in, j_in, i_out, j_out, xgrid_area, xgrid_clon, xgrid_clat);
+}
+
+extern "C" int create_xgrid_2dx2d_order1_(const int* a, const int* b, const int* c, const int* d, const double* e, const double* f,
+                                          const double* g, const double* h, const double* m, int* i1, int* j1, int* i2, int* j2,
+                                          double* xa)
+{
+  return create_xgrid_2dx2d_order1(a, b, c, d, e, f, g, h, m, i1, j1, i2, j2, xa);
+}
+
+extern "C" int create_xgrid_2dx2d_order2_(const int* a, const int* b, const int* c, const int* d, const double* e, const double* f,
+                                          const double* g, const double* h, const double* m, int* i1, int* j1, int* i2, int* j2,
+                                          double* xa, double* xc, double* yc)
+{
+  return create_xgrid_2dx2d_order2(a, b, c, d, e, f, g, h, m, i1, j1, i2, j2, xa, xc, yc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Self-check hooks for ref_trig.cuh (tests only): the host build and the device build of the same
+// source, so tests can pin both against the libm the reference links.
+// ---------------------------------------------------------------------------------------------
+extern "C" void xgb_ref_trig_host(long long n, const double* x, double* s, double* c, double* ss, double* sc)
+{
+  for (long long i = 0; i < n; ++i) {
+    s[i] = ref_sin(x[i]);
+    c[i] = ref_cos(x[i]);
+    ref_sincos(x[i], &ss[i], &sc[i]);
+  }
+}
+
+__global__ void ref_trig_kernel(long long n, const double* __restrict__ x, double* s, double* c, double* ss, double* sc)
+{
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  s[i] = ref_sin(x[i]);
+  c[i] = ref_cos(x[i]);
+  ref_sincos(x[i], &ss[i], &sc[i]);
+}
+
+extern "C" int xgb_ref_trig_device(long long n, const double* x, double* s, double* c, double* ss, double* sc)
+{
+  double* d = nullptr;
+  const size_t nb = (size_t)n * sizeof(double);
+  CU_OK(cudaMalloc(&d, 5 * nb));
+  CU_OK(cudaMemcpy(d, x, nb, cudaMemcpyHostToDevice));
+  ref_trig_kernel<<<(unsigned)((n + 255) / 256), 256>>>(n, d, d + n, d + 2 * n, d + 3 * n, d + 4 * n);
+  CU_OK(cudaGetLastError());
+  CU_OK(cudaMemcpy(s, d + n, nb, cudaMemcpyDeviceToHost));
+  CU_OK(cudaMemcpy(c, d + 2 * n, nb, cudaMemcpyDeviceToHost));
+  CU_OK(cudaMemcpy(ss, d + 3 * n, nb, cudaMemcpyDeviceToHost));
+  CU_OK(cudaMemcpy(sc, d + 4 * n, nb, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return 0;
+}

@@ -1,0 +1,205 @@
+// Device-side spherical polygon geometry for the exchange-grid kernels (sm_100a).
+//
+// Every routine states the arithmetic of the reference routine it replaces in the same
+// association order and is compiled with -fmad=false, because each accept/reject decision of
+// the exchange grid is a floating-point predicate (inside_edge <= 1e-12, area ratio > 1e-6,
+// pole tests in fix_lon) and the integer cell lists have to match the reference bit for bit.
+// Citations are relative to the reference tree (mlee03/FRE-NCtools).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include "ref_trig.cuh"
+
+namespace xgb {
+
+constexpr double kPi     = 3.14159265358979323846;
+constexpr double kTwoPi  = 2.0 * kPi;
+constexpr double kHalfPi = 0.5 * kPi;
+constexpr double kRadius = 6371000.0;          // constant.h:23
+constexpr double kSmall  = 1.e-10;             // mosaic_util.h:34 SMALL_VALUE
+constexpr double kPoleTol = 1.e-6;             // mosaic_util.c:35 TOLORENCE
+constexpr double kAreaRatioThresh = 1.e-6;     // create_xgrid.c:27
+constexpr double kMaskThresh = 0.5;            // create_xgrid.c:28
+constexpr int    kMaxV = 8;                    // create_xgrid.c:627 MAX_V (vertices of a fix_lon'd cell)
+constexpr int    kMaxClip = 16;                // capacity of a clipped polygon (<= n1 + n2 for convex cells)
+
+// ---------------------------------------------------------------------------------------------
+// fix_lon (mosaic_util.c:667-738) on a thread-private 4-vertex cell; returns the vertex count.
+// x/y must have room for kMaxV + 2 entries.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int vtx_remove(double* x, double* y, int n, int at) {
+  for (int k = at; k < n - 1; ++k) { x[k] = x[k + 1]; y[k] = y[k + 1]; }
+  return n - 1;
+}
+__device__ __forceinline__ int vtx_insert(double* x, double* y, int n, int at, double lon, double lat) {
+  for (int k = n - 1; k >= at; --k) { x[k + 1] = x[k]; y[k + 1] = y[k]; }
+  x[at] = lon; y[at] = lat;
+  return n + 1;
+}
+
+__device__ inline int fix_lon(double* x, double* y, int n, double tlon) {
+  const double near_pole = kHalfPi - kPoleTol;
+  int nn = n;
+  bool any_pole = false;
+  for (int i = 0; i < nn; ++i) any_pole |= (fabs(y[i]) >= near_pole);
+  if (any_pole) {
+    // pole vertices must come in pairs (mosaic_util.c:679-692)
+    for (int i = 0; i < nn; ++i) {
+      if (fabs(y[i]) >= near_pole) {
+        int prev = (i + nn - 1) % nn, next = (i + 1) % nn;
+        if (y[prev] == y[i] && y[next] == y[i]) { nn = vtx_remove(x, y, nn, i); --i; }
+        else if (y[prev] != y[i] && y[next] != y[i]) {
+          if (nn >= kMaxV + 2) return -1;
+          nn = vtx_insert(x, y, nn, i, x[i], y[i]); ++i;
+        }
+      }
+    }
+    // first/second of a pole pair take the neighbouring longitudes (:693-700)
+    for (int i = 0; i < nn; ++i) {
+      if (fabs(y[i]) >= near_pole) {
+        int prev = (i + nn - 1) % nn, next = (i + 1) % nn;
+        if (y[prev] != y[i]) x[i] = x[prev];
+        if (y[next] != y[i]) x[i] = x[next];
+      }
+    }
+  }
+  // a side through a pole gets twin pole vertices (:702-717)
+  for (int i = 0; i < nn; ++i) {
+    int prev = (i + nn - 1) % nn;
+    double d = x[i] - x[prev];
+    if (fabs(d + kPi) < kSmall || fabs(d - kPi) < kSmall) {
+      if (nn + 2 > kMaxV + 2) return -1;
+      double xa = x[prev], xb = x[i];
+      double yp = (y[i] < 0.0) ? -kHalfPi : kHalfPi;
+      nn = vtx_insert(x, y, nn, i, xb, yp);
+      nn = vtx_insert(x, y, nn, i, xa, yp);
+      break;
+    }
+  }
+  if (nn == 0) return 0;
+  // unwrap (:718-725)
+  double sum = x[0];
+  for (int i = 1; i < nn; ++i) {
+    double d = x[i] - x[i - 1];
+    if (d < -kPi) d = d + kTwoPi;
+    else if (d > kPi) d = d - kTwoPi;
+    x[i] = x[i - 1] + d;
+    sum += x[i];
+  }
+  // mean within pi of tlon (:727-729)
+  double shift = (sum / nn) - tlon;
+  if (shift < -kPi)      { for (int i = 0; i < nn; ++i) x[i] += kTwoPi; }
+  else if (shift > kPi)  { for (int i = 0; i < nn; ++i) x[i] -= kTwoPi; }
+  return nn;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Strided polygon view: vertex k lives at p[k * stride].  stride = blockDim.x for the
+// shared-memory staging used by the clip kernel (bank-conflict free), 1 for private arrays.
+// ---------------------------------------------------------------------------------------------
+struct PolyView {
+  const double* x; const double* y; int stride;
+  __device__ __forceinline__ double X(int k) const { return x[k * stride]; }
+  __device__ __forceinline__ double Y(int k) const { return y[k * stride]; }
+};
+
+// poly_area_main (mosaic_util.c:417-459) -> m^2
+__device__ __forceinline__ double poly_area(const PolyView& p, int n) {
+  double acc = 0.0;
+  double xi = p.X(0), yi = p.Y(0);
+  const double x0 = xi, y0 = yi;
+  for (int i = 0; i < n; ++i) {
+    double xn, yn;
+    if (i + 1 < n) { xn = p.X(i + 1); yn = p.Y(i + 1); } else { xn = x0; yn = y0; }
+    double dx = xn - xi;
+    double lat1 = yn, lat2 = yi;
+    if (dx > kPi)  dx = dx - 2.0 * kPi;
+    if (dx < -kPi) dx = dx + 2.0 * kPi;
+    if (fabs(dx + kPi) < kSmall || fabs(dx - kPi) < kSmall) {
+      acc += kPi;                                  // side through a pole (:434-437)
+    } else if (fabs(lat1 - lat2) < kSmall) {
+      acc -= dx * ref_sin(0.5 * (lat1 + lat2));
+    } else {
+      double dy = 0.5 * (lat1 - lat2);
+      double dat = ref_sin(dy) / dy;
+      acc -= dx * ref_sin(0.5 * (lat1 + lat2)) * dat;
+    }
+    xi = xn; yi = yn;
+  }
+  return (acc < 0) ? -acc * kRadius * kRadius : acc * kRadius * kRadius;
+}
+
+// poly_ctrlat (create_xgrid.c:2096-2121)
+__device__ __forceinline__ double poly_ctrlat(const PolyView& p, int n) {
+  double acc = 0.0;
+  double xi = p.X(0), yi = p.Y(0);
+  const double x0 = xi, y0 = yi;
+  for (int i = 0; i < n; ++i) {
+    double xn, yn;
+    if (i + 1 < n) { xn = p.X(i + 1); yn = p.Y(i + 1); } else { xn = x0; yn = y0; }
+    double dx = xn - xi;
+    double lat1 = yn, lat2 = yi;
+    double dy = lat2 - lat1;
+    double hdy = dy * 0.5;
+    double avg_y = (lat1 + lat2) * 0.5;
+    if (dx != 0.0) {
+      if (dx > kPi)   dx = dx - 2.0 * kPi;
+      if (dx <= -kPi) dx = dx + 2.0 * kPi;
+      // the reference binary evaluates cos(avg_y)/sin(avg_y) with one sincos() call, cos(lat1) and
+      // sin(hdy) with cos()/sin() (gcc -O2); ref_* reproduce exactly those entry points
+      double sa, ca;
+      ref_sincos(avg_y, &sa, &ca);
+      if (fabs(hdy) < kSmall)
+        acc -= dx * (2 * ca + lat2 * sa - ref_cos(lat1));
+      else
+        acc -= dx * ((ref_sin(hdy) / hdy) * (2 * ca + lat2 * sa) - ref_cos(lat1));
+    }
+    xi = xn; yi = yn;
+  }
+  return acc * kRadius * kRadius;
+}
+
+// poly_ctrlon (create_xgrid.c:2170-2217)
+__device__ __forceinline__ double poly_ctrlon(const PolyView& p, int n, double clon) {
+  double acc = 0.0;
+  double xi = p.X(0), yi = p.Y(0);
+  const double x0 = xi, y0 = yi;
+  for (int i = 0; i < n; ++i) {
+    double xn, yn;
+    if (i + 1 < n) { xn = p.X(i + 1); yn = p.Y(i + 1); } else { xn = x0; yn = y0; }
+    double phi1 = xn, phi2 = xi, lat1 = yn, lat2 = yi;
+    double dphi = phi1 - phi2;
+    if (dphi != 0.0) {
+      double s1, c1, s2, c2;
+      ref_sincos(lat1, &s1, &c1);
+      ref_sincos(lat2, &s2, &c2);
+      double f1 = 0.5 * (c1 * s1 + lat1);
+      double f2 = 0.5 * (c2 * s2 + lat2);
+      if (dphi > kPi)  dphi = dphi - 2.0 * kPi;
+      if (dphi < -kPi) dphi = dphi + 2.0 * kPi;
+      double dphi1 = phi1 - clon;
+      if (dphi1 > kPi)  dphi1 -= 2.0 * kPi;
+      if (dphi1 < -kPi) dphi1 += 2.0 * kPi;
+      double dphi2 = phi2 - clon;
+      if (dphi2 > kPi)  dphi2 -= 2.0 * kPi;
+      if (dphi2 < -kPi) dphi2 += 2.0 * kPi;
+      if (fabs(dphi2 - dphi1) < kPi) {
+        acc -= dphi * (dphi1 * f1 + dphi2 * f2) / 2.0;
+      } else {
+        double fac = (dphi1 > 0.0) ? kPi : -kPi;
+        double fint = f1 + (f2 - f1) * (fac - dphi1) / fabs(dphi);
+        acc -= 0.5 * dphi1 * (dphi1 - fac) * f1 - 0.5 * dphi2 * (dphi2 + fac) * f2 + 0.5 * fac * (dphi1 + dphi2) * fint;
+      }
+    }
+    xi = xn; yi = yn;
+  }
+  return acc * kRadius * kRadius;
+}
+
+// inside_edge (create_xgrid.c:2342-2350)
+__device__ __forceinline__ bool inside_edge(double x0, double y0, double x1, double y1, double x, double y) {
+  double product = (x - x0) * (y1 - y0) + (x0 - x1) * (y - y0);
+  return product <= 1.e-12;
+}
+
+}  // namespace xgb

@@ -1,0 +1,82 @@
+// Internal (C++) interface between the kernel TUs and the C-ABI layer.  Not installed.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "xgrid_geom.cuh"
+
+namespace xgb {
+
+// One structured tile of a mosaic: nx*ny cells, (nx+1)*(ny+1) vertices, row-major.
+struct TileDesc {
+  int nx, ny;
+  long long cell_off;   // first cell of this tile in the concatenated cell index space
+  long long vert_off;   // first vertex in the concatenated vertex arrays
+};
+
+// fix_lon'd cells of a whole mosaic, struct-of-arrays in HBM.  Vertex k of cell c is
+// vx[k*ncell + c]: a warp reading vertex k of 32 neighbouring cells reads 256 contiguous
+// bytes, and planes 4..7 (only pole cells use them) are never touched by ordinary cells.
+struct CellSet {
+  long long ncell;
+  double *ymin, *ymax;        // latitude range of the 4 raw corners  (create_xgrid.c:727-728)
+  double *xmin, *xmax, *xavg; // longitude range / mean after fix_lon (create_xgrid.c:731-733)
+  double *area;               // poly_area of the fix_lon'd cell       (create_xgrid.c:66-88)
+  unsigned char* nv;          // vertex count after fix_lon (3..8)
+  double *vx, *vy;            // [kMaxV][ncell]
+};
+
+// Min/max pyramid over the destination tile's index space: level 0 = cells, level l+1 node
+// (ix,iy) bounds level-l nodes (2ix..2ix+1, 2iy..2iy+1).  Upper levels only prune; the exact
+// reference predicates run at level 0.
+constexpr int kMaxLevels = 24;
+struct PyrLevel { int nx, ny; const double *ymin, *ymax, *xmin, *xmax; };
+struct Pyramid { int nlev; PyrLevel lev[kMaxLevels]; };
+
+// error bits raised by kernels (read back by the C-ABI layer, which turns them into the
+// reference's fatal errors)
+enum : int {
+  kErrTooManyVertices = 1,   // "n2_in is greater than MAX_V"        (create_xgrid.c:730)
+  kErrParallelEdges   = 2,   // clip_2dx2d determinant < EPSLN30      (create_xgrid.c:1314)
+  kErrClipOverflow    = 4,   // clipped polygon exceeded MV vertices
+  kErrStackOverflow   = 8,   // candidate traversal stack exhausted (internal)
+  kErrGcNotConvex     = 16,  // great-circle: grid box is not convex  (create_xgrid.c:1576-1579)
+  kErrGcWalk          = 32,  // great-circle: polygon walk failed     (create_xgrid.c:1795,1822,1825)
+  kErrGcNodePool      = 64,  // great-circle: node pool exhausted     (mosaic_util.c:1075)
+};
+
+// ---- launchers (xgrid_kernels.cu) ----------------------------------------------------------
+void launch_cell_precompute(const TileDesc& tile, const double* lon, const double* lat,
+                            CellSet cells, int* err, cudaStream_t st);
+void launch_pyramid_level(const PyrLevel& child, double* ymin, double* ymax, double* xmin, double* xmax,
+                          int nx, int ny, cudaStream_t st);
+void launch_candidates(bool fill, const CellSet& src, long long s0, long long ns, const double* mask,
+                       const Pyramid& pyr, const CellSet& dst, const uint32_t* pair_off,
+                       uint32_t* cnt, int2* pairs, int* err, cudaStream_t st);
+void launch_clip(int order, const CellSet& src, const CellSet& dst, const double* mask,
+                 const int2* pairs, unsigned long long npairs, long long s0,
+                 double* parea, double* pclon, double* pclat, uint32_t* cnt, int* err, cudaStream_t st);
+void launch_scatter(int order, const int2* pairs, unsigned long long npairs,
+                    const double* parea, const double* pclon, const double* pclat,
+                    const uint32_t* pair_off, const uint32_t* out_off,
+                    const TileDesc* tiles, int ntiles, long long s0, int nx2,
+                    int* t_in, int* i_in, int* j_in, int* i_out, int* j_out,
+                    double* area, double* clon, double* clat, cudaStream_t st);
+void launch_order2_finalize(const CellSet& src, long long s0, long long ns, const uint32_t* out_off,
+                            const double* area, const double* clon, const double* clat,
+                            double* di, double* dj, cudaStream_t st);
+// exclusive prefix sum of n uint32 counts; out has n+1 entries (out[n] = total, must fit 32 bits);
+// the 64-bit total is also written to *total_dev.  tmp must hold scan_tmp_bytes(n).
+size_t scan_tmp_bytes(long long n);
+void launch_exclusive_scan(const uint32_t* in, uint32_t* out, long long n, unsigned long long* total_dev,
+                           void* tmp, cudaStream_t st);
+
+// ---- great-circle path (xgrid_gc_kernels.cu) -----------------------------------------------
+void launch_gc_cell_precompute(const TileDesc& tile, const double* lon, const double* lat,
+                               double* x, double* y, double* z, long long nvert_total_unused,
+                               double* area, long long cell_off, int* err, cudaStream_t st);
+
+// ---- apply (apply_kernels.cu) --------------------------------------------------------------
+void launch_build_dst_csr_count(long long nxgrid, const int* i_out, const int* j_out, int nx2,
+                                uint32_t* cnt, cudaStream_t st);
+
+}  // namespace xgb

@@ -1,0 +1,614 @@
+// Exchange-grid ("xgrid") weight-generation kernels for sm_100a.
+//
+// Replaces create_xgrid_2dx2d_order1/order2 (reference create_xgrid.c:621-1152):
+//   cell_precompute  : per cell lat range, fix_lon, lon range/mean, poly_area   (:714-739, :757-768)
+//   pyramid_level    : 2x2 min/max reduction of destination cell boxes (replaces the O(N1*N2) scan)
+//   candidates<FILL> : per source cell, walk the pyramid; at level 0 apply the reference's exact
+//                      latitude / shifted-longitude box tests (:777-801); count, then fill pairs
+//   clip<ORDER>      : per candidate pair Sutherland-Hodgman clip + poly_area + area-ratio test
+//                      (+ poly_ctrlon / poly_ctrlat for order 2)  (:802-820, :1080-1097)
+//   scatter          : stable compaction into the reference's emission order
+//                      (source cell row-major, then destination index ascending)
+//   order2_finalize  : per source cell centroid correction -> tile1_distance (conserve_interp.c:319-358)
+//
+// FP64 throughout, compiled with -fmad=false (see xgrid_geom.cuh).
+#include "xgrid_internal.h"
+#include "xgrid_plan.h"
+
+namespace xgb {
+
+// =============================================================================================
+// cell precompute
+// =============================================================================================
+__global__ void __launch_bounds__(128)
+cell_precompute_kernel(TileDesc tile, const double* __restrict__ lon, const double* __restrict__ lat,
+                       CellSet cells, int* err)
+{
+  const long long ncell_tile = (long long)tile.nx * tile.ny;
+  const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (c >= ncell_tile) return;
+  const int i = (int)(c % tile.nx), j = (int)(c / tile.nx);
+  const int nxp = tile.nx + 1;
+  const double* lo = lon + tile.vert_off;
+  const double* la = lat + tile.vert_off;
+  const long long n0 = (long long)j * nxp + i, n3 = (long long)(j + 1) * nxp + i;
+
+  double x[kMaxV + 2], y[kMaxV + 2];
+  x[0] = lo[n0];     y[0] = la[n0];
+  x[1] = lo[n0 + 1]; y[1] = la[n0 + 1];
+  x[2] = lo[n3 + 1]; y[2] = la[n3 + 1];
+  x[3] = lo[n3];     y[3] = la[n3];
+
+  double ymin = y[0], ymax = y[0];
+#pragma unroll
+  for (int k = 1; k < 4; ++k) { if (y[k] < ymin) ymin = y[k]; if (y[k] > ymax) ymax = y[k]; }
+
+  int n = fix_lon(x, y, 4, kPi);
+  if (n < 0 || n > kMaxV) { atomicOr(err, kErrTooManyVertices); n = (n < 0) ? 4 : kMaxV; }
+
+  double xmin = x[0], xmax = x[0], sum = 0.0;
+  for (int k = 1; k < n; ++k) { if (x[k] < xmin) xmin = x[k]; if (x[k] > xmax) xmax = x[k]; }
+  for (int k = 0; k < n; ++k) sum += x[k];
+
+  const long long g = tile.cell_off + c;
+  cells.ymin[g] = ymin; cells.ymax[g] = ymax;
+  cells.xmin[g] = xmin; cells.xmax[g] = xmax;
+  cells.xavg[g] = sum / n;
+  cells.nv[g] = (unsigned char)n;
+  for (int k = 0; k < n; ++k) {
+    cells.vx[(long long)k * cells.ncell + g] = x[k];
+    cells.vy[(long long)k * cells.ncell + g] = y[k];
+  }
+  PolyView pv{x, y, 1};
+  cells.area[g] = poly_area(pv, n);
+}
+
+void launch_cell_precompute(const TileDesc& tile, const double* lon, const double* lat,
+                            CellSet cells, int* err, cudaStream_t st)
+{
+  const long long n = (long long)tile.nx * tile.ny;
+  if (n <= 0) return;
+  const int threads = 128;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  cell_precompute_kernel<<<blocks, threads, 0, st>>>(tile, lon, lat, cells, err);
+}
+
+// =============================================================================================
+// min/max pyramid
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+pyramid_level_kernel(PyrLevel child, double* __restrict__ ymin, double* __restrict__ ymax,
+                     double* __restrict__ xmin, double* __restrict__ xmax, int nx, int ny)
+{
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= (long long)nx * ny) return;
+  const int ix = (int)(t % nx), iy = (int)(t / nx);
+  double a = 1e300, b = -1e300, c = 1e300, d = -1e300;
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy) {
+    const int cy = 2 * iy + dy;
+    if (cy >= child.ny) continue;
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const int cx = 2 * ix + dx;
+      if (cx >= child.nx) continue;
+      const long long q = (long long)cy * child.nx + cx;
+      a = fmin(a, child.ymin[q]); b = fmax(b, child.ymax[q]);
+      c = fmin(c, child.xmin[q]); d = fmax(d, child.xmax[q]);
+    }
+  }
+  ymin[t] = a; ymax[t] = b; xmin[t] = c; xmax[t] = d;
+}
+
+void launch_pyramid_level(const PyrLevel& child, double* ymin, double* ymax, double* xmin, double* xmax,
+                          int nx, int ny, cudaStream_t st)
+{
+  const long long n = (long long)nx * ny;
+  const int threads = 256;
+  pyramid_level_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(child, ymin, ymax, xmin, xmax, nx, ny);
+}
+
+// =============================================================================================
+// candidate search
+// =============================================================================================
+constexpr int kStack = 3 * kMaxLevels + 8;
+
+struct SrcBox { double ymin, ymax, xmin, xmax, xavg; };
+
+// conservative node test: the node may contain a cell that passes the exact tests under one of
+// the three 2*pi shifts the reference can apply (create_xgrid.c:786-801).  Rounding of
+// (bound + 2pi) is monotone, so this never rejects a node holding a true candidate.
+__device__ __forceinline__ bool node_hit(const PyrLevel& L, long long q, const SrcBox& s)
+{
+  if (L.ymin[q] >= s.ymax || L.ymax[q] <= s.ymin) return false;
+  const double lo = L.xmin[q], hi = L.xmax[q];
+  if (!(lo >= s.xmax || hi <= s.xmin)) return true;
+  if (!(lo + kTwoPi >= s.xmax || hi + kTwoPi <= s.xmin)) return true;
+  if (!(lo - kTwoPi >= s.xmax || hi - kTwoPi <= s.xmin)) return true;
+  return false;
+}
+
+// exact reference predicates for one (source cell, destination cell) pair, create_xgrid.c:777-801
+__device__ __forceinline__ bool leaf_hit(const CellSet& dst, long long d, const SrcBox& s)
+{
+  if (dst.ymin[d] >= s.ymax || dst.ymax[d] <= s.ymin) return false;
+  double lo = dst.xmin[d], hi = dst.xmax[d];
+  const double dx = dst.xavg[d] - s.xavg;
+  if (dx < -kPi)     { lo += kTwoPi; hi += kTwoPi; }
+  else if (dx > kPi) { lo -= kTwoPi; hi -= kTwoPi; }
+  if (lo >= s.xmax || hi <= s.xmin) return false;
+  return true;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+candidate_kernel(CellSet src, long long s0, long long ns, const double* __restrict__ mask,
+                 Pyramid pyr, CellSet dst, const uint32_t* __restrict__ pair_off,
+                 uint32_t* __restrict__ cnt, int2* __restrict__ pairs, int* err)
+{
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= ns) return;
+  const long long s = s0 + t;
+  uint32_t n = 0;
+  const uint32_t base = FILL ? pair_off[t] : 0u;
+
+  if (mask == nullptr || mask[s] > kMaskThresh) {
+    SrcBox sb;
+    sb.ymin = src.ymin[s]; sb.ymax = src.ymax[s];
+    sb.xmin = src.xmin[s]; sb.xmax = src.xmax[s]; sb.xavg = src.xavg[s];
+
+    unsigned long long stack[kStack];
+    int sp = 0;
+    const int top = pyr.nlev - 1;
+    {
+      const PyrLevel& L = pyr.lev[top];
+      for (int iy = 0; iy < L.ny; ++iy)
+        for (int ix = 0; ix < L.nx; ++ix) {
+          const long long q = (long long)iy * L.nx + ix;
+          if (top == 0) {
+            if (leaf_hit(dst, q, sb)) { if (FILL) pairs[base + n] = make_int2((int)t, (int)q); ++n; }
+          } else if (node_hit(L, q, sb)) {
+            stack[sp++] = ((unsigned long long)top << 58) | ((unsigned long long)iy << 29) | (unsigned long long)ix;
+          }
+        }
+    }
+    while (sp > 0) {
+      const unsigned long long e = stack[--sp];
+      const int lev = (int)(e >> 58) - 1;                      // child level
+      const int py = (int)((e >> 29) & 0x1fffffffull), px = (int)(e & 0x1fffffffull);
+      const PyrLevel& L = pyr.lev[lev];
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const int cy = 2 * py + dy;
+        if (cy >= L.ny) continue;
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int cx = 2 * px + dx;
+          if (cx >= L.nx) continue;
+          const long long q = (long long)cy * L.nx + cx;
+          if (lev == 0) {
+            if (leaf_hit(dst, q, sb)) { if (FILL) pairs[base + n] = make_int2((int)t, (int)q); ++n; }
+          } else if (node_hit(L, q, sb)) {
+            if (sp < kStack) stack[sp++] = ((unsigned long long)lev << 58) | ((unsigned long long)cy << 29) | (unsigned long long)cx;
+            else atomicOr(err, kErrStackOverflow);
+          }
+        }
+      }
+    }
+  }
+  if (!FILL) cnt[t] = n;
+}
+
+void launch_candidates(bool fill, const CellSet& src, long long s0, long long ns, const double* mask,
+                       const Pyramid& pyr, const CellSet& dst, const uint32_t* pair_off,
+                       uint32_t* cnt, int2* pairs, int* err, cudaStream_t st)
+{
+  if (ns <= 0) return;
+  const int threads = 128;
+  const unsigned blocks = (unsigned)((ns + threads - 1) / threads);
+  if (fill) candidate_kernel<true><<<blocks, threads, 0, st>>>(src, s0, ns, mask, pyr, dst, pair_off, cnt, pairs, err);
+  else      candidate_kernel<false><<<blocks, threads, 0, st>>>(src, s0, ns, mask, pyr, dst, pair_off, cnt, pairs, err);
+}
+
+// =============================================================================================
+// clip
+// =============================================================================================
+constexpr int kClipThreads = 128;
+constexpr int kFastCap = 8;       // shared-memory polygon capacity per thread (quad x quad)
+constexpr int kSlowCap = 50;      // reference MV (create_xgrid.h:31), thread-local fallback
+
+__device__ __forceinline__ double dst_vertex_lon(const CellSet& dst, long long d, int k, int shift, bool wrap)
+{
+  double v = dst.vx[(long long)k * dst.ncell + d];
+  if (shift > 0) v += kTwoPi; else if (shift < 0) v -= kTwoPi;     // create_xgrid.c:787-796
+  if (wrap) { if (v < -kPi) v += kTwoPi; else if (v > kPi) v -= kTwoPi; }   // pimod, :1343-1349
+  return v;
+}
+
+// Sutherland-Hodgman of polygon A (n1 vertices in ax/ay, element k at [k*stride]) against every
+// edge of destination cell d (create_xgrid.c:1292-1340).  Ping-pongs between the A and B buffers
+// instead of copying back.  Returns the vertex count and the buffer holding the result, or -1
+// if a stage would exceed CAP vertices.
+template <int CAP>
+__device__ __forceinline__ int clip_cell(double* ax, double* ay, double* bx, double* by, int stride, int n1,
+                                         const CellSet& dst, long long d, int n2, int shift, bool wrap,
+                                         double** rx, double** ry, int* err)
+{
+  double *cx = ax, *cy = ay, *ox = bx, *oy = by;
+  int np = n1;
+  double ex0 = dst_vertex_lon(dst, d, n2 - 1, shift, wrap);
+  double ey0 = dst.vy[(long long)(n2 - 1) * dst.ncell + d];
+  for (int e = 0; e < n2; ++e) {
+    const double ex1 = dst_vertex_lon(dst, d, e, shift, wrap);
+    const double ey1 = dst.vy[(long long)e * dst.ncell + d];
+    const double edy = ey1 - ey0, endx = ex0 - ex1;            // (y1-y0), (x0-x1) of inside_edge
+    double px = cx[(np - 1) * stride], py = cy[(np - 1) * stride];
+    bool was_in = ((px - ex0) * edy + endx * (py - ey0)) <= 1.e-12;
+    int no = 0;
+    for (int k = 0; k < np; ++k) {
+      const double qx = cx[k * stride], qy = cy[k * stride];
+      const bool is_in = ((qx - ex0) * edy + endx * (qy - ey0)) <= 1.e-12;
+      if (is_in != was_in) {
+        if (no >= CAP) return -1;
+        const double dy1 = qy - py, dy2 = ey1 - ey0, dx1 = qx - px, dx2 = ex1 - ex0;
+        const double ds1 = py * qx - qy * px, ds2 = ey0 * ex1 - ey1 * ex0;
+        const double determ = dy2 * dx1 - dy1 * dx2;
+        if (fabs(determ) < 1.0e-30) atomicOr(err, kErrParallelEdges);
+        ox[no * stride] = (dx2 * ds1 - dx1 * ds2) / determ;
+        oy[no * stride] = (dy2 * ds1 - dy1 * ds2) / determ;
+        ++no;
+      }
+      if (is_in) {
+        if (no >= CAP) return -1;
+        ox[no * stride] = qx; oy[no * stride] = qy; ++no;
+      }
+      px = qx; py = qy; was_in = is_in;
+    }
+    np = no;
+    if (np == 0) { *rx = ox; *ry = oy; return 0; }
+    double* t;
+    t = cx; cx = ox; ox = t;
+    t = cy; cy = oy; oy = t;
+    ex0 = ex1; ey0 = ey1;
+  }
+  *rx = cx; *ry = cy;
+  return np;
+}
+
+// load the source polygon into a strided buffer, report whether pimod applies (create_xgrid.c:1279-1290)
+__device__ __forceinline__ bool load_src_poly(const CellSet& src, long long s, int n1, double* ax, double* ay, int stride)
+{
+  bool wrap = false;
+  for (int k = 0; k < n1; ++k) {
+    const double v = src.vx[(long long)k * src.ncell + s];
+    ax[k * stride] = v;
+    ay[k * stride] = src.vy[(long long)k * src.ncell + s];
+    if (v > kTwoPi || v < 0.0) wrap = true;
+  }
+  if (wrap) {
+    for (int k = 0; k < n1; ++k) {
+      double v = ax[k * stride];
+      if (v < -kPi) v += kTwoPi; else if (v > kPi) v -= kTwoPi;
+      ax[k * stride] = v;
+    }
+  }
+  return wrap;
+}
+
+template <int ORDER>
+__global__ void __launch_bounds__(kClipThreads)
+clip_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const int2* __restrict__ pairs,
+            unsigned long long npairs, long long s0,
+            double* __restrict__ parea, double* __restrict__ pclon, double* __restrict__ pclat,
+            uint32_t* __restrict__ cnt, int* err)
+{
+  __shared__ double sm[4 * kFastCap * kClipThreads];            // [buf][coord][vertex][thread]
+  const unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (p >= npairs) return;
+  const int2 pr = pairs[p];
+  const long long s = s0 + pr.x, d = pr.y;
+  const int n1 = src.nv[s], n2 = dst.nv[d];
+  const double s_xavg = src.xavg[s];
+  const double dxavg = dst.xavg[d] - s_xavg;
+  const int shift = (dxavg < -kPi) ? 1 : ((dxavg > kPi) ? -1 : 0);
+
+  const int stride = kClipThreads;
+  double* ax = sm + threadIdx.x;
+  double* ay = ax + kFastCap * kClipThreads;
+  double* bx = ay + kFastCap * kClipThreads;
+  double* by = bx + kFastCap * kClipThreads;
+
+  double *rx = nullptr, *ry = nullptr;
+  int rstride = stride;
+  int n_out;
+  double loc[4 * kSlowCap];                                       // only touched on the slow path
+  {
+    const bool wrap = load_src_poly(src, s, n1, ax, ay, stride);
+    n_out = clip_cell<kFastCap>(ax, ay, bx, by, stride, n1, dst, d, n2, shift, wrap, &rx, &ry, err);
+  }
+  if (n_out < 0) {
+    // rare: more than 8 vertices at some stage (pole cells, non-convex cells) -> reference-sized buffers
+    const bool wrap = load_src_poly(src, s, n1, loc, loc + kSlowCap, 1);
+    n_out = clip_cell<kSlowCap>(loc, loc + kSlowCap, loc + 2 * kSlowCap, loc + 3 * kSlowCap, 1, n1,
+                                dst, d, n2, shift, wrap, &rx, &ry, err);
+    rstride = 1;
+    if (n_out < 0) { atomicOr(err, kErrClipOverflow); n_out = 0; }
+  }
+
+  double xarea = 0.0;
+  bool keep = false;
+  PolyView pv{rx, ry, rstride};
+  if (n_out > 0) {
+    const double m = mask ? mask[s] : 1.0;
+    xarea = poly_area(pv, n_out) * m;                            // create_xgrid.c:805
+    const double a1 = src.area[s], a2 = dst.area[d];
+    const double min_area = (a1 < a2) ? a1 : a2;                 // :806
+    keep = (xarea / min_area > kAreaRatioThresh);                // :807
+  }
+  parea[p] = keep ? xarea : 0.0;
+  if (keep) {
+    if (ORDER == 2) {
+      pclon[p] = poly_ctrlon(pv, n_out, s_xavg);                 // :1091
+      pclat[p] = poly_ctrlat(pv, n_out);                         // :1092
+    }
+    atomicAdd(&cnt[pr.x], 1u);
+  }
+}
+
+void launch_clip(int order, const CellSet& src, const CellSet& dst, const double* mask,
+                 const int2* pairs, unsigned long long npairs, long long s0,
+                 double* parea, double* pclon, double* pclat, uint32_t* cnt, int* err, cudaStream_t st)
+{
+  if (npairs == 0) return;
+  const unsigned blocks = (unsigned)((npairs + kClipThreads - 1) / kClipThreads);
+  if (order == 2) clip_kernel<2><<<blocks, kClipThreads, 0, st>>>(src, dst, mask, pairs, npairs, s0, parea, pclon, pclat, cnt, err);
+  else            clip_kernel<1><<<blocks, kClipThreads, 0, st>>>(src, dst, mask, pairs, npairs, s0, parea, pclon, pclat, cnt, err);
+}
+
+// =============================================================================================
+// compaction into reference order
+// =============================================================================================
+__device__ __forceinline__ int find_tile(const TileDesc* tiles, int ntiles, long long s)
+{
+  int t = 0;
+  while (t + 1 < ntiles && s >= tiles[t + 1].cell_off) ++t;
+  return t;
+}
+
+template <int ORDER>
+__global__ void __launch_bounds__(256)
+scatter_kernel(const int2* __restrict__ pairs, unsigned long long npairs,
+               const double* __restrict__ parea, const double* __restrict__ pclon, const double* __restrict__ pclat,
+               const uint32_t* __restrict__ pair_off, const uint32_t* __restrict__ out_off,
+               const TileDesc* __restrict__ tiles, int ntiles, long long s0, int nx2,
+               int* __restrict__ t_in, int* __restrict__ i_in, int* __restrict__ j_in,
+               int* __restrict__ i_out, int* __restrict__ j_out,
+               double* __restrict__ area, double* __restrict__ clon, double* __restrict__ clat)
+{
+  const unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (p >= npairs) return;
+  const double a = parea[p];
+  if (!(a > 0.0)) return;
+  const int2 pr = pairs[p];
+  // rank among the accepted pairs of the same source cell by ascending destination index:
+  // the reference visits destination cells in ascending ij for each source cell (create_xgrid.c:769)
+  uint32_t rank = 0;
+  const uint32_t qb = pair_off[pr.x], qe = pair_off[pr.x + 1];
+  for (uint32_t q = qb; q < qe; ++q)
+    if (parea[q] > 0.0 && pairs[q].y < pr.y) ++rank;
+  const size_t o = (size_t)out_off[pr.x] + rank;
+  const long long s = s0 + pr.x;
+  const int tl = find_tile(tiles, ntiles, s);
+  const long long c = s - tiles[tl].cell_off;
+  t_in[o] = tl;
+  i_in[o] = (int)(c % tiles[tl].nx);
+  j_in[o] = (int)(c / tiles[tl].nx);
+  i_out[o] = pr.y % nx2;
+  j_out[o] = pr.y / nx2;
+  area[o] = a;
+  if (ORDER == 2) { clon[o] = pclon[p]; clat[o] = pclat[p]; }
+}
+
+void launch_scatter(int order, const int2* pairs, unsigned long long npairs,
+                    const double* parea, const double* pclon, const double* pclat,
+                    const uint32_t* pair_off, const uint32_t* out_off,
+                    const TileDesc* tiles, int ntiles, long long s0, int nx2,
+                    int* t_in, int* i_in, int* j_in, int* i_out, int* j_out,
+                    double* area, double* clon, double* clat, cudaStream_t st)
+{
+  if (npairs == 0) return;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((npairs + threads - 1) / threads);
+  if (order == 2)
+    scatter_kernel<2><<<blocks, threads, 0, st>>>(pairs, npairs, parea, pclon, pclat, pair_off, out_off, tiles, ntiles, s0, nx2,
+                                                  t_in, i_in, j_in, i_out, j_out, area, clon, clat);
+  else
+    scatter_kernel<1><<<blocks, threads, 0, st>>>(pairs, npairs, parea, pclon, pclat, pair_off, out_off, tiles, ntiles, s0, nx2,
+                                                  t_in, i_in, j_in, i_out, j_out, area, clon, clat);
+}
+
+// =============================================================================================
+// order-2 centroid correction (conserve_interp.c:216-221 and :319-358), one thread per source cell.
+// The cell's exchange cells are contiguous and in reference order, so the sequential sums below
+// add in exactly the order the reference's loop at :216-221 does.
+// clon/clat hold xgrid_clon/xgrid_clat on entry; di/dj receive tile1_distance.
+// =============================================================================================
+__global__ void __launch_bounds__(128)
+order2_finalize_kernel(CellSet src, long long s0, long long ns, const uint32_t* __restrict__ out_off,
+                       const double* __restrict__ area, const double* __restrict__ clon, const double* __restrict__ clat,
+                       double* __restrict__ di, double* __restrict__ dj)
+{
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= ns) return;
+  const uint32_t b = out_off[t], e = out_off[t + 1];
+  if (b == e) return;
+  double sa = 0.0, sx = 0.0, sy = 0.0;
+  for (uint32_t k = b; k < e; ++k) { sa += area[k]; sx += clon[k]; sy += clat[k]; }
+  double cx = 0.0, cy = 0.0;
+  if (sa > 0) {
+    const long long s = s0 + t;
+    const double cell_area = src.area[s];
+    if (fabs(sa - cell_area) / cell_area < 1.e-3) {              // AREA_RATIO, conserve_interp.c:35,:330
+      cx = sx / sa; cy = sy / sa;
+    } else {                                                     // :334-347 analytic centroid of the cell
+      double x[kMaxV], y[kMaxV];
+      const int n = src.nv[s];
+      for (int k = 0; k < n; ++k) { x[k] = src.vx[(long long)k * src.ncell + s]; y[k] = src.vy[(long long)k * src.ncell + s]; }
+      PolyView pv{x, y, 1};
+      cx = poly_ctrlon(pv, n, src.xavg[s]) / cell_area;
+      cy = poly_ctrlat(pv, n) / cell_area;
+    }
+  }
+  for (uint32_t k = b; k < e; ++k) {                             // :256-257 then :355-356
+    const double a = area[k];
+    double u = clon[k] / a, v = clat[k] / a;
+    u -= cx; v -= cy;
+    di[k] = u; dj[k] = v;
+  }
+}
+
+void launch_order2_finalize(const CellSet& src, long long s0, long long ns, const uint32_t* out_off,
+                            const double* area, const double* clon, const double* clat,
+                            double* di, double* dj, cudaStream_t st)
+{
+  if (ns <= 0) return;
+  const int threads = 128;
+  order2_finalize_kernel<<<(unsigned)((ns + threads - 1) / threads), threads, 0, st>>>(src, s0, ns, out_off, area, clon, clat, di, dj);
+}
+
+// =============================================================================================
+// exclusive scan (reduce-then-scan, three launches; counts are small so uint32 offsets suffice,
+// the 64-bit grand total is returned separately so the caller can detect overflow)
+// =============================================================================================
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanThreads * kScanItems;   // 4096 elements per block
+
+__device__ __forceinline__ unsigned long long block_reduce_u64(unsigned long long v, unsigned long long* sh)
+{
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    v = (lane < (blockDim.x >> 5)) ? sh[lane] : 0ull;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[0] = v;
+  }
+  __syncthreads();
+  return sh[0];
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_block_sums_kernel(const uint32_t* __restrict__ in, long long n, unsigned long long* __restrict__ bsum)
+{
+  __shared__ unsigned long long sh[32];
+  const long long base = (long long)blockIdx.x * kScanTile;
+  unsigned long long v = 0;
+  for (int k = 0; k < kScanItems; ++k) {
+    const long long i = base + (long long)k * kScanThreads + threadIdx.x;
+    if (i < n) v += in[i];
+  }
+  const unsigned long long tot = block_reduce_u64(v, sh);
+  if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+
+// single block: exclusive scan of nblk block sums in place; writes the grand total
+__global__ void __launch_bounds__(1024)
+scan_spine_kernel(unsigned long long* __restrict__ bsum, long long nblk, unsigned long long* __restrict__ total)
+{
+  __shared__ unsigned long long sh[1024];
+  __shared__ unsigned long long carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (long long base = 0; base < nblk; base += 1024) {
+    const long long i = base + threadIdx.x;
+    const unsigned long long v = (i < nblk) ? bsum[i] : 0ull;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {                         // Hillis-Steele inclusive scan
+      unsigned long long add = (threadIdx.x >= (unsigned)o) ? sh[threadIdx.x - o] : 0ull;
+      __syncthreads();
+      sh[threadIdx.x] += add;
+      __syncthreads();
+    }
+    const unsigned long long incl = sh[threadIdx.x];
+    if (i < nblk) bsum[i] = carry + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_final_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, long long n,
+                  const unsigned long long* __restrict__ bsum)
+{
+  __shared__ uint32_t sh[kScanThreads];
+  const long long base = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kScanItems;
+  uint32_t v[kScanItems];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) { const long long i = base + k; v[k] = (i < n) ? in[i] : 0u; sum += v[k]; }
+  sh[threadIdx.x] = sum;
+  __syncthreads();
+  for (int o = 1; o < kScanThreads; o <<= 1) {
+    uint32_t add = (threadIdx.x >= (unsigned)o) ? sh[threadIdx.x - o] : 0u;
+    __syncthreads();
+    sh[threadIdx.x] += add;
+    __syncthreads();
+  }
+  uint32_t run = (uint32_t)bsum[blockIdx.x] + sh[threadIdx.x] - sum;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) { const long long i = base + k; if (i < n) out[i] = run; run += v[k]; }
+  // out[n] = grand total, written by whichever thread owns element n-1
+  if (base <= n - 1 && n - 1 < base + kScanItems) out[n] = run;
+}
+
+size_t scan_tmp_bytes(long long n)
+{
+  const long long nblk = (n + kScanTile - 1) / kScanTile;
+  return (size_t)(nblk > 0 ? nblk : 1) * sizeof(unsigned long long);
+}
+
+void launch_exclusive_scan(const uint32_t* in, uint32_t* out, long long n, unsigned long long* total_dev,
+                           void* tmp, cudaStream_t st)
+{
+  if (n <= 0) { cudaMemsetAsync(out, 0, sizeof(uint32_t), st); cudaMemsetAsync(total_dev, 0, sizeof(unsigned long long), st); return; }
+  const long long nblk = (n + kScanTile - 1) / kScanTile;
+  unsigned long long* bsum = (unsigned long long*)tmp;
+  scan_block_sums_kernel<<<(unsigned)nblk, kScanThreads, 0, st>>>(in, n, bsum);
+  scan_spine_kernel<<<1, 1024, 0, st>>>(bsum, nblk, total_dev);
+  scan_final_kernel<<<(unsigned)nblk, kScanThreads, 0, st>>>(in, out, n, bsum);
+}
+
+}  // namespace xgb
+
+// =============================================================================================
+// balanced partition of the source cells by candidate-pair count (multi-GPU sharding):
+// bounds[k] = first cell whose exclusive pair offset reaches k*total/nparts.
+// =============================================================================================
+namespace xgb {
+__global__ void partition_kernel(const uint32_t* __restrict__ pair_off, long long ncell, unsigned long long total,
+                                 int nparts, long long* __restrict__ bounds)
+{
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > nparts) return;
+  if (k == 0) { bounds[0] = 0; return; }
+  if (k == nparts) { bounds[nparts] = ncell; return; }
+  const unsigned long long target = (total / (unsigned long long)nparts) * (unsigned long long)k;
+  long long lo = 0, hi = ncell;                 // first index with pair_off[idx] >= target
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if ((unsigned long long)pair_off[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  bounds[k] = lo;
+}
+
+void launch_partition(const uint32_t* pair_off, long long ncell, unsigned long long total, int nparts,
+                      long long* bounds, cudaStream_t st)
+{
+  partition_kernel<<<(nparts + 1 + 63) / 64, 64, 0, st>>>(pair_off, ncell, total, nparts, bounds);
+}
+}  // namespace xgb

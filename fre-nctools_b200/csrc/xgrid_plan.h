@@ -1,0 +1,64 @@
+// Plan object behind the opaque xgb_plan handle (include/xgrid_b200.h).  Internal.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <vector>
+#include "xgrid_internal.h"
+
+// grow-only device allocation
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes);   // 0 on success
+  void release();
+};
+
+struct xgb_apply_state;        // apply_capi.cu
+
+struct xgb_plan {
+  int device = 0;
+  cudaStream_t st = nullptr;
+
+  // destination tile
+  bool have_dst = false;
+  int nx2 = 0, ny2 = 0;
+  DevBuf dst_lon, dst_lat, dst_store, pyr_store;
+  xgb::CellSet dst{};
+  xgb::Pyramid pyr{};
+
+  // source mosaic
+  bool have_src = false, has_mask = false;
+  std::vector<xgb::TileDesc> tiles;
+  DevBuf tiles_dev, src_lon, src_lat, mask, src_store;
+  xgb::CellSet src{};
+  long long s0 = 0, ns = 0;          // active window of source cells
+
+  // great-circle extras (cartesian vertices, spherical-excess areas)
+  bool gc_src_ready = false, gc_dst_ready = false;
+  DevBuf gc_src_xyz, gc_dst_xyz;
+
+  // work space
+  DevBuf cnt, pair_off, out_off, pairs, parea, pclon, pclat, scan_tmp, bounds_dev;
+
+  // result (Interp_config layout)
+  DevBuf t_in, i_in, j_in, i_out, j_out, area, clon, clat, di, dj;
+  long long nxgrid = -1;
+  unsigned long long npairs = 0;
+  int order = 0;
+
+  int* err_dev = nullptr;
+  int* err_host = nullptr;                    // pinned
+  unsigned long long* total_dev = nullptr;    // [2]
+  unsigned long long* total_host = nullptr;   // pinned [2]
+
+  xgb_apply_state* apply = nullptr;
+};
+
+void xgb_set_error(const char* fmt, ...);
+long long xgb_generate_great_circle(xgb_plan* p, int order);   // xgrid_gc_capi.cu
+void xgb_apply_release(xgb_plan* p);                           // apply_capi.cu
+
+namespace xgb {
+void launch_partition(const uint32_t* pair_off, long long ncell, unsigned long long total, int nparts,
+                      long long* bounds, cudaStream_t st);
+}

@@ -655,3 +655,16 @@ void orc_conserve_apply(int order, long nxgrid, const int *t_in, const int *i_in
   }
   free(out_area); free(out_miss); free(doff); free(goff); free(moff);
 }
+
+/* the libm this oracle (and oracle/_ref) is linked against, exposed element-wise so tests can pin
+ * the product's ref_sin/ref_cos/ref_sincos (csrc/ref_trig.cuh) to it bit for bit */
+void sincos(double, double *, double *);
+void orc_libm_trig(long n, const double *x, double *s, double *c, double *ss, double *sc)
+{
+  long i;
+  for (i = 0; i < n; i++) {
+    s[i] = sin(x[i]);
+    c[i] = cos(x[i]);
+    sincos(x[i], &ss[i], &sc[i]);
+  }
+}

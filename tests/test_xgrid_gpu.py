@@ -1,0 +1,185 @@
+"""GPU parity tests of exchange-grid weight generation: CUDA path (through the C ABI) vs the CPU oracle.
+
+Bar (BASELINE.json north_star): integer cell lists bit-exact, xgrid_area within 1e-12 relative;
+tile1_distance (a difference of near-equal centroids) within 1e-11 rad absolute.
+"""
+import numpy as np
+import pytest
+
+import xgtest
+
+pytestmark = pytest.mark.gpu
+
+AREA_RTOL = 1e-12
+DIST_ATOL = 1e-9
+
+
+def test_ref_trig_device_equals_host_and_libm(pkg):
+    """csrc/ref_trig.cuh: device build == host build == the libm the reference links (bit for bit)."""
+    x = xgtest.trig_samples(300000)
+    host = [np.empty_like(x) for _ in range(4)]
+    dev = [np.empty_like(x) for _ in range(4)]
+    pkg.lib().xgb_ref_trig_host(x.size, *[a.ctypes.data for a in [x] + host])
+    assert pkg.lib().xgb_ref_trig_device(x.size, *[a.ctypes.data for a in [x] + dev]) == 0
+    for a, b in zip(host, dev):
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+    if xgtest.libm_matches_ref_trig():
+        for a, b in zip(dev, xgtest.libm_trig(x)):
+            assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+
+
+def _gen(pkg, lonc, latc, lon2, lat2, opcode, mask=None):
+    plan = pkg.XgridPlan(0)
+    plan.set_dst(lon2, lat2)
+    plan.set_src(lonc, latc, mask)
+    n = plan.generate(opcode)
+    got = plan.result_host()
+    got["nxgrid"] = n
+    got["npairs"] = plan.npairs
+    plan.close()
+    return got
+
+
+@pytest.mark.parametrize("ni,nlon,nlat", [(8, 36, 18), (16, 180, 90), (48, 360, 180)])
+@pytest.mark.parametrize("order", [1, 2])
+def test_cubed_sphere_to_latlon_matches_oracle(pkg, ni, nlon, nlat, order):
+    lonc, latc = pkg.cubed_sphere_grid(ni)
+    lon2, lat2 = pkg.latlon_grid(nlon, nlat)
+    got = _gen(pkg, lonc, latc, lon2, lat2, order)
+    ref = xgtest.oracle_setup(lonc, latc, lon2, lat2, order)
+    sc = xgtest.parent_scale(ref, lonc, latc, lon2, lat2)
+    xgtest.assert_xgrid_equal(got, ref, order, AREA_RTOL, DIST_ATOL, same_order=True, scale=sc)
+    # per-exchange-cell relative difference for cells that are not slivers (>= 1% of the parent cell)
+    big = ref["area"] >= 1e-2 * sc
+    assert np.max(np.abs(got["area"][big] - ref["area"][big]) / ref["area"][big]) <= 1e-10
+
+
+def test_c48_known_answer(pkg):
+    """SURVEY 8c sanity values: C48 -> 360x180 order-1 nxgrid 146032, sum(area)/4piR^2 = 0.9999999995881"""
+    lonc, latc = pkg.cubed_sphere_grid(48)
+    lon2, lat2 = pkg.latlon_grid(360, 180)
+    got = _gen(pkg, lonc, latc, lon2, lat2, 1)
+    assert got["nxgrid"] == 146032
+    frac = np.sum(got["area"]) / (4 * np.pi * xgtest.RADIUS ** 2)
+    assert abs(frac - 0.999999999588102) < 1e-12
+
+
+def test_c96_quarter_degree_order2_matches_oracle(pkg):
+    """BASELINE config 2 weights: C96 -> 1440x720 order 2 (nxgrid 1645856)."""
+    lonc, latc = pkg.cubed_sphere_grid(96)
+    lon2, lat2 = pkg.latlon_grid(1440, 720)
+    got = _gen(pkg, lonc, latc, lon2, lat2, 2)
+    assert got["nxgrid"] == 1645856
+    ref = xgtest.oracle_setup(lonc, latc, lon2, lat2, 2)
+    sc = xgtest.parent_scale(ref, lonc, latc, lon2, lat2)
+    xgtest.assert_xgrid_equal(got, ref, 2, AREA_RTOL, DIST_ATOL, same_order=True, scale=sc)
+
+
+def test_latlon_to_latlon_and_regional(pkg):
+    """lat-lon source (pole rows, cyclic seam) onto a shifted regional lat-lon window."""
+    lon1, lat1 = pkg.latlon_grid(72, 36)
+    lon2, lat2 = pkg.latlon_grid(50, 40, lonbegin=-30.0, lonend=95.0, latbegin=-63.0, latend=77.0)
+    for order in (1, 2):
+        got = _gen(pkg, [lon1], [lat1], lon2, lat2, order)
+        ref = xgtest.oracle_setup([lon1], [lat1], lon2, lat2, order)
+        sc = xgtest.parent_scale(ref, [lon1], [lat1], lon2, lat2)
+        xgtest.assert_xgrid_equal(got, ref, order, AREA_RTOL, DIST_ATOL, scale=sc)
+
+
+def test_cubed_sphere_to_cubed_sphere_tile(pkg):
+    """curvilinear destination (a rotated cube face incl. the pole tile): exercises the generic pyramid."""
+    lonc, latc = pkg.cubed_sphere_grid(24)
+    lond, latd = pkg.cubed_sphere_grid(20)
+    for tile in (0, 2, 5):
+        got = _gen(pkg, lonc, latc, lond[tile], latd[tile], 2)
+        ref = xgtest.oracle_setup(lonc, latc, lond[tile], latd[tile], 2)
+        sc = xgtest.parent_scale(ref, lonc, latc, lond[tile], latd[tile])
+        xgtest.assert_xgrid_equal(got, ref, 2, AREA_RTOL, DIST_ATOL, scale=sc)
+
+
+def test_mask_and_empty(pkg):
+    lonc, latc = pkg.cubed_sphere_grid(12)
+    lon2, lat2 = pkg.latlon_grid(60, 30)
+    rng = np.random.default_rng(7)
+    mask = (rng.random(6 * 12 * 12) > 0.4).astype(np.float64)
+    got = _gen(pkg, lonc, latc, lon2, lat2, 1, mask=mask)
+    # masked source cells emit nothing (create_xgrid.c:752)
+    src = (got["t_in"].astype(np.int64) * 144 + got["j_in"] * 12 + got["i_in"])
+    assert np.all(mask[src] > 0.5)
+    full = _gen(pkg, lonc, latc, lon2, lat2, 1)
+    srcf = (full["t_in"].astype(np.int64) * 144 + full["j_in"] * 12 + full["i_in"])
+    keep = mask[srcf] > 0.5
+    assert got["nxgrid"] == int(keep.sum())
+    assert np.array_equal(got["i_out"], full["i_out"][keep]) and np.array_equal(got["area"], full["area"][keep])
+    none = _gen(pkg, lonc, latc, lon2, lat2, 1, mask=np.zeros(6 * 144))
+    assert none["nxgrid"] == 0
+
+
+def test_reference_signature_entry_points(pkg):
+    """create_xgrid_2dx2d_order1/2 through the reference's own C signatures, per tile with the
+    latitude-trimmed slab exactly as conserve_interp.c:169-200 calls them."""
+    lonc, latc = pkg.cubed_sphere_grid(16)
+    lon2, lat2 = pkg.latlon_grid(90, 45)
+    O = xgtest.oracle_lib()
+    for tile in (0, 2):
+        n, ii, ji, io, jo, xa, xc, yc = pkg.create_xgrid_2dx2d_order2(lonc[tile], latc[tile], lon2, lat2)
+        cap = 200000
+        bi = [np.zeros(cap, np.int32) for _ in range(4)]
+        bd = [np.zeros(cap) for _ in range(3)]
+        m = O.orc_create_xgrid_2dx2d(2, 16, 16, 90, 45, np.ascontiguousarray(lonc[tile]).ravel(), np.ascontiguousarray(latc[tile]).ravel(),
+                                     lon2.ravel(), lat2.ravel(), np.ones(256), cap, *bi, bd[0], bd[1].ctypes.data, bd[2].ctypes.data)
+        assert n == m
+        for a, b in zip((ii, ji, io, jo), bi):
+            assert np.array_equal(a, b[:m])
+        if xgtest.libm_matches_ref_trig():
+            assert np.array_equal(xa, bd[0][:m]) and np.array_equal(xc, bd[1][:m]) and np.array_equal(yc, bd[2][:m])
+        else:
+            assert np.max(np.abs(xa - bd[0][:m]) / bd[0][:m]) <= 1e-10
+    area = pkg.get_grid_area(lon2, lat2)
+    oa = np.zeros(90 * 45)
+    O.orc_get_grid_area(90, 45, lon2.ravel(), lat2.ravel(), oa)
+    if xgtest.libm_matches_ref_trig():
+        assert np.array_equal(area.ravel(), oa)
+    assert np.max(np.abs(area.ravel() - oa) / oa) <= AREA_RTOL
+    assert pkg.get_maxxgrid() == 5000000
+
+
+def test_windows_concatenate_to_full_result(pkg):
+    """multi-GPU sharding unit: source-cell windows, concatenated in order, equal the single-window result."""
+    lonc, latc = pkg.cubed_sphere_grid(24)
+    lon2, lat2 = pkg.latlon_grid(120, 60)
+    plan = pkg.XgridPlan(0)
+    plan.set_dst(lon2, lat2)
+    plan.set_src(lonc, latc)
+    plan.generate(2)
+    full = plan.result_host()
+    bounds = plan.partition(5)
+    assert bounds[0] == 0 and bounds[-1] == 6 * 24 * 24 and all(a <= b for a, b in zip(bounds, bounds[1:]))
+    parts = []
+    for a, b in zip(bounds, bounds[1:]):
+        plan.set_src_window(a, b)
+        plan.generate(2)
+        parts.append(plan.result_host())
+    for k in full:
+        cat = np.concatenate([p[k] for p in parts])
+        assert np.array_equal(cat, full[k]), k
+
+
+def test_conservation_c192_half_degree(pkg):
+    """size-independent property at a size the oracle is not run at: exchange areas tile both grids."""
+    lonc, latc = pkg.cubed_sphere_grid(192)
+    lon2, lat2 = pkg.latlon_grid(720, 360)
+    plan = pkg.XgridPlan(0)
+    plan.set_dst(lon2, lat2)
+    plan.set_src(lonc, latc)
+    n = plan.generate(2)
+    r = plan.result_host()
+    a_src = plan.src_area(); a_dst = plan.dst_area()
+    s = np.bincount(r["t_in"].astype(np.int64) * 192 * 192 + r["j_in"] * 192 + r["i_in"], weights=r["area"], minlength=a_src.size)
+    d = np.bincount(r["j_out"].astype(np.int64) * 720 + r["i_out"], weights=r["area"], minlength=a_dst.size)
+    assert np.max(np.abs(s - a_src) / a_src) < 2e-4      # poly_area's straight-line sides vs great-circle cube edges
+    assert np.max(np.abs(d - a_dst) / a_dst) < 2e-4
+    assert abs(r["area"].sum() / (4 * np.pi * xgtest.RADIUS ** 2) - 1) < 1e-8
+    # sortedness: reference emission order
+    key = (r["t_in"].astype(np.int64) * 192 * 192 + r["j_in"] * 192 + r["i_in"]) * (720 * 360) + r["j_out"].astype(np.int64) * 720 + r["i_out"]
+    assert np.all(np.diff(key) > 0)

@@ -1,0 +1,276 @@
+"""Test-side helpers: ctypes access to the CPU oracle (oracle/liboracle_xgrid.so), to the compiled
+reference (oracle/_ref/libfrenc_ref.so, when present) and loading of the product package.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+dp = np.ctypeslib.ndpointer(np.float64, flags="C")
+ip = np.ctypeslib.ndpointer(np.int32, flags="C")
+vp = C.c_void_p
+
+ORDER1, ORDER2, GREAT_CIRCLE, MONOTONIC, LEGACY_CLIP = 1, 2, 4096, 16384, 2048
+RADIUS = 6371000.0
+
+_oracle = None
+_ref = None
+
+
+def package():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    return ge.load_package()
+
+
+def oracle_lib():
+    global _oracle
+    if _oracle is None:
+        path = os.path.join(ORACLE_DIR, "liboracle_xgrid.so")
+        srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.startswith("xgrid_oracle")]
+        if not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in srcs):
+            subprocess.run(["make", "-s", "-C", ORACLE_DIR, "oracle"], check=True)
+        L = C.CDLL(path)
+        L.orc_fix_lon.argtypes = [dp, dp, C.c_int, C.c_double]
+        L.orc_poly_area.restype = C.c_double
+        L.orc_poly_area.argtypes = [dp, dp, C.c_int]
+        L.orc_poly_ctrlon.restype = C.c_double
+        L.orc_poly_ctrlon.argtypes = [dp, dp, C.c_int, C.c_double]
+        L.orc_poly_ctrlat.restype = C.c_double
+        L.orc_poly_ctrlat.argtypes = [dp, dp, C.c_int]
+        L.orc_clip_2dx2d.argtypes = [dp, dp, C.c_int, dp, dp, C.c_int, dp, dp]
+        L.orc_get_grid_area.argtypes = [C.c_int, C.c_int, dp, dp, dp]
+        L.orc_create_xgrid_2dx2d.restype = C.c_long
+        L.orc_create_xgrid_2dx2d.argtypes = [C.c_int] * 5 + [dp] * 5 + [C.c_long] + [ip] * 4 + [dp, vp, vp]
+        L.orc_setup_conserve_interp.restype = C.c_long
+        L.orc_setup_conserve_interp.argtypes = [C.c_int, ip, ip, dp, dp, C.c_int, C.c_int, dp, dp, C.c_uint, C.c_long] + [ip] * 5 + [dp, vp, vp]
+        L.orc_conserve_apply.argtypes = [C.c_int, C.c_long] + [ip] * 5 + [dp, vp, vp, C.c_int, ip, ip, dp, vp, vp, vp,
+                                         C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, dp]
+        L.orc_libm_trig.argtypes = [C.c_long] + [dp] * 5
+        _oracle = L
+    return _oracle
+
+
+def trig_samples(n=200000, seed=99):
+    """arguments covering every branch of csrc/ref_trig.cuh: bulk (-2.42, 2.42), Taylor range, tiny, near pi/2"""
+    rng = np.random.default_rng(seed)
+    x = np.concatenate([rng.uniform(-2.42, 2.42, n), rng.uniform(-0.13, 0.13, n // 4), rng.uniform(-1e-3, 1e-3, n // 8),
+                        rng.uniform(-1e-8, 1e-8, n // 8), np.pi / 2 - rng.uniform(0, 1e-4, n // 8),
+                        -np.pi / 2 + rng.uniform(0, 1e-4, n // 8),
+                        np.array([0.0, -0.0, np.pi / 2, -np.pi / 2, 0.126, 0.855469, 0.85546875, 2.426265, 2.0 ** -26, 2.0 ** -27])])
+    return np.ascontiguousarray(x)
+
+
+def libm_trig(x):
+    L = oracle_lib()
+    out = [np.empty_like(x) for _ in range(4)]
+    L.orc_libm_trig(x.size, x, *out)
+    return out
+
+
+_libm_ok = None
+
+
+def libm_matches_ref_trig():
+    """True when the host libm rounds sin/cos/sincos exactly like csrc/ref_trig.cuh (glibc 2.39 x86-64 FMA build):
+    then the GPU results are expected to equal the oracle's bit for bit, areas and centroids included."""
+    global _libm_ok
+    if _libm_ok is None:
+        pk = package()
+        x = trig_samples(50000)
+        got = [np.empty_like(x) for _ in range(4)]
+        pk.lib().xgb_ref_trig_host(x.size, *[a.ctypes.data for a in [x] + got])
+        want = libm_trig(x)
+        _libm_ok = all(np.array_equal(a.view(np.uint64), b.view(np.uint64)) for a, b in zip(got, want))
+    return _libm_ok
+
+
+def ref_lib():
+    """The unmodified reference compiled by oracle/Makefile, or None when it was never built."""
+    global _ref
+    if _ref is None:
+        path = os.path.join(ORACLE_DIR, "_ref", "libfrenc_ref.so")
+        if os.path.isdir("/root/reference/tools/libfrencutils"):
+            subprocess.run(["make", "-s", "-C", ORACLE_DIR, "ref"], check=True)
+        if not os.path.exists(path):
+            return None
+        L = C.CDLL(path)
+        L.ref_cubed_sphere_grid.argtypes = [C.c_int, dp, dp, vp, vp]
+        L.ref_tripolar_grid.argtypes = [C.c_int, C.c_int] + [C.c_double] * 5 + [dp, dp]
+        L.ref_regrid_setup.restype = vp
+        L.ref_regrid_setup.argtypes = [C.c_int, ip, ip, dp, dp, vp, vp, C.c_int, C.c_int, dp, dp, C.c_int, C.c_int, C.c_uint]
+        L.ref_regrid_nxgrid.restype = C.c_long
+        L.ref_regrid_nxgrid.argtypes = [vp]
+        L.ref_regrid_get.argtypes = [vp] + [ip] * 5 + [dp, vp, vp]
+        L.ref_regrid_cell_area.argtypes = [vp, vp, vp]
+        L.ref_regrid_apply.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_uint, dp, vp, vp, vp, dp]
+        L.ref_regrid_free.argtypes = [vp]
+        L.ref_compute_extent.argtypes = [C.c_int, C.c_int, ip, ip]
+        L.fix_lon.argtypes = [dp, dp, C.c_int, C.c_double]
+        L.poly_area.restype = C.c_double
+        L.poly_area.argtypes = [dp, dp, C.c_int]
+        L.poly_ctrlon.restype = C.c_double
+        L.poly_ctrlon.argtypes = [dp, dp, C.c_int, C.c_double]
+        L.poly_ctrlat.restype = C.c_double
+        L.poly_ctrlat.argtypes = [dp, dp, C.c_int]
+        L.clip_2dx2d.argtypes = [dp, dp, C.c_int, dp, dp, C.c_int, dp, dp]
+        L.get_grid_area.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), dp, dp, dp]
+        _ref = L
+    return _ref
+
+
+def _tiles(lonc, latc):
+    """[ntiles, ny+1, nx+1] array or list of 2-D arrays -> (nx[], ny[], lon_cat, lat_cat)."""
+    if not isinstance(lonc, (list, tuple)):
+        lonc = [lonc[t] for t in range(lonc.shape[0])] if lonc.ndim == 3 else [lonc]
+        latc = [latc[t] for t in range(latc.shape[0])] if latc.ndim == 3 else [latc]
+    nx = np.array([a.shape[1] - 1 for a in lonc], np.int32)
+    ny = np.array([a.shape[0] - 1 for a in lonc], np.int32)
+    lon = np.ascontiguousarray(np.concatenate([np.asarray(a, np.float64).ravel() for a in lonc]))
+    lat = np.ascontiguousarray(np.concatenate([np.asarray(a, np.float64).ravel() for a in latc]))
+    return nx, ny, lon, lat
+
+
+def _alloc(cap, order):
+    out = {k: np.zeros(cap, np.int32) for k in ("t_in", "i_in", "j_in", "i_out", "j_out")}
+    out["area"] = np.zeros(cap)
+    if order == 2:
+        out["di"] = np.zeros(cap)
+        out["dj"] = np.zeros(cap)
+    return out
+
+
+def _trim(out, n):
+    res = {k: v[:n].copy() for k, v in out.items()}
+    res["nxgrid"] = int(n)
+    return res
+
+
+def oracle_setup(lonc, latc, lon2, lat2, opcode, cap=None):
+    """oracle restatement of setup_conserve_interp for a source mosaic and one destination tile."""
+    L = oracle_lib()
+    nx, ny, lon, lat = _tiles(lonc, latc)
+    lon2 = np.ascontiguousarray(lon2, np.float64); lat2 = np.ascontiguousarray(lat2, np.float64)
+    ny2, nx2 = lon2.shape[0] - 1, lon2.shape[1] - 1
+    order = 2 if opcode & ORDER2 else 1
+    if cap is None:
+        cap = int(12 * max(int((nx * ny).sum()), nx2 * ny2)) + 4096
+    out = _alloc(cap, order)
+    n = L.orc_setup_conserve_interp(len(nx), nx, ny, lon, lat, nx2, ny2, lon2.ravel(), lat2.ravel(), opcode, cap,
+                                    out["t_in"], out["i_in"], out["j_in"], out["i_out"], out["j_out"], out["area"],
+                                    out["di"].ctypes.data if order == 2 else None,
+                                    out["dj"].ctypes.data if order == 2 else None)
+    if n < 0:
+        raise RuntimeError("oracle capacity exceeded")
+    return _trim(out, n)
+
+
+def ref_setup(lonc, latc, lon2, lat2, opcode, jsc=None, jec=None, keep=False):
+    """the reference's own setup_conserve_interp (conserve_interp.c:42) through oracle/ref_driver.c"""
+    L = ref_lib()
+    nx, ny, lon, lat = _tiles(lonc, latc)
+    lon2 = np.ascontiguousarray(lon2, np.float64); lat2 = np.ascontiguousarray(lat2, np.float64)
+    ny2, nx2 = lon2.shape[0] - 1, lon2.shape[1] - 1
+    order = 2 if opcode & ORDER2 else 1
+    jsc = 0 if jsc is None else jsc
+    jec = ny2 - 1 if jec is None else jec
+    if not (opcode & GREAT_CIRCLE):
+        opcode |= LEGACY_CLIP
+    devnull = os.open(os.devnull, os.O_WRONLY); saved = os.dup(1); os.dup2(devnull, 1)   # reference prints a NOTE
+    try:
+        r = L.ref_regrid_setup(len(nx), nx, ny, lon, lat, None, None, nx2, ny2, lon2.ravel(), lat2.ravel(), jsc, jec, opcode)
+    finally:
+        os.dup2(saved, 1); os.close(saved); os.close(devnull)
+    n = L.ref_regrid_nxgrid(r)
+    out = _alloc(max(n, 1), order)
+    L.ref_regrid_get(r, out["t_in"], out["i_in"], out["j_in"], out["i_out"], out["j_out"], out["area"],
+                     out["di"].ctypes.data if order == 2 else None, out["dj"].ctypes.data if order == 2 else None)
+    res = _trim(out, n)
+    if keep:
+        res["handle"] = r
+    else:
+        L.ref_regrid_free(r)
+    return res
+
+
+def ref_cubed_sphere(ni, centers=False):
+    L = ref_lib()
+    lonc = np.zeros((6, ni + 1, ni + 1)); latc = np.zeros_like(lonc)
+    lont = np.zeros((6, ni, ni)); latt = np.zeros_like(lont)
+    rc = L.ref_cubed_sphere_grid(ni, lonc.reshape(-1), latc.reshape(-1),
+                                 lont.ctypes.data if centers else None, latt.ctypes.data if centers else None)
+    assert rc == 0
+    return (lonc, latc, lont, latt) if centers else (lonc, latc)
+
+
+def canonical_order(x):
+    """sort key of an exchange-grid list: (tile, j_in, i_in, j_out, i_out)"""
+    return np.lexsort((x["i_out"], x["j_out"], x["i_in"], x["j_in"], x["t_in"]))
+
+
+def parent_scale(x, lonc, latc, lon2, lat2):
+    """min(area of parent source cell, area of parent destination cell) per exchange cell: the
+    reference's own normalisation of xgrid_area in its accept test (create_xgrid.c:806-807)."""
+    L = oracle_lib()
+    nx, ny, lon, lat = _tiles(lonc, latc)
+    lon2 = np.ascontiguousarray(lon2, np.float64); lat2 = np.ascontiguousarray(lat2, np.float64)
+    ny2, nx2 = lon2.shape[0] - 1, lon2.shape[1] - 1
+    a_src, coff, voff, offs = [], 0, 0, []
+    for t in range(len(nx)):
+        nv = (nx[t] + 1) * (ny[t] + 1)
+        a = np.zeros(nx[t] * ny[t])
+        L.orc_get_grid_area(int(nx[t]), int(ny[t]), lon[voff:voff + nv].copy(), lat[voff:voff + nv].copy(), a)
+        a_src.append(a); offs.append(coff)
+        coff += nx[t] * ny[t]; voff += nv
+    a_src = np.concatenate(a_src); offs = np.array(offs, np.int64)
+    a_dst = np.zeros(nx2 * ny2)
+    L.orc_get_grid_area(nx2, ny2, lon2.ravel(), lat2.ravel(), a_dst)
+    s = offs[x["t_in"]] + x["j_in"].astype(np.int64) * nx[x["t_in"]] + x["i_in"]
+    d = x["j_out"].astype(np.int64) * nx2 + x["i_out"]
+    return np.minimum(a_src[s], a_dst[d])
+
+
+def assert_xgrid_equal(got, ref, order, area_tol=1e-12, dist_atol=1e-11, same_order=True, scale=None, exact=None):
+    """Integer lists bit-exact (optionally after canonical sort).
+    exact=True (default: whenever the host libm rounds like csrc/ref_trig.cuh): xgrid_area and
+    tile1_distance must equal the reference BIT FOR BIT as well.  Otherwise:
+    xgrid_area: |got - ref| <= area_tol * scale, where scale is the parent-cell area (parent_scale) when
+    given, else the reference value itself.  The line integral in poly_area cancels catastrophically for
+    sliver cells (terms ~ dlon*sin(lat) against a result ~ ratio*dlon*dlat*cos(lat)), so a 1-ulp libm
+    difference is amplified by up to 1/ratio >= 1e6 relative to the sliver's own area; relative to the
+    parent cell it stays at rounding level.  See DESIGN.md "Parity tolerances".
+    tile1_distance: dist_atol absolute (radians; a difference of near-equal centroids)."""
+    assert got["nxgrid"] == ref["nxgrid"], (got["nxgrid"], ref["nxgrid"])
+    if same_order:
+        pg = pr = slice(None)
+    else:
+        pg, pr = canonical_order(got), canonical_order(ref)
+    for k in ("t_in", "i_in", "j_in", "i_out", "j_out"):
+        assert np.array_equal(got[k][pg], ref[k][pr]), f"{k} differs"
+    a, b = got["area"][pg], ref["area"][pr]
+    if exact is None:
+        exact = libm_matches_ref_trig()
+    if exact:
+        assert np.array_equal(a, b), f"xgrid_area not bit-identical: max rel {np.max(np.abs(a - b) / b)}"
+        if order == 2:
+            for k in ("di", "dj"):
+                assert np.array_equal(got[k][pg], ref[k][pr]), f"{k} not bit-identical: max abs {np.max(np.abs(got[k][pg] - ref[k][pr]))}"
+        return 0.0
+    den = b if scale is None else scale[pr]
+    rel = float(np.max(np.abs(a - b) / den)) if len(b) else 0.0
+    assert rel <= area_tol, f"xgrid_area max scaled diff {rel}"
+    tot = abs(a.sum() - b.sum()) / b.sum() if len(b) else 0.0
+    assert tot <= 1e-13, f"sum(xgrid_area) rel diff {tot}"
+    if order == 2:
+        for k in ("di", "dj"):
+            d = np.max(np.abs(got[k][pg] - ref[k][pr])) if len(b) else 0.0
+            assert d <= dist_atol, f"{k} max abs diff {d}"
+    return rel
