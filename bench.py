@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py — exchange-grid weight generation throughput (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c768] [--impl reference]
+
+A "step" is one complete weight generation (candidate search, clip, area/centroids, ordered
+compaction, order-2 centroid correction) of the workload, sharded by source-cell windows over the
+N ranks.  `value` is whole-job exchange cells per second with the grids already resident in HBM;
+`e2e` is the same job through the C ABI with HOST buffers (grid upload and result download inside
+the timed region).  N > 1 is launched by torchrun (one rank per GPU, NCCL).
+
+--impl reference times the reference's own CPU implementation (oracle/_ref, the unmodified
+FRE-NCtools sources compiled by oracle/Makefile; the oracle port if that was never built) on all
+host cores, each step a bounded sample of destination row bands of the same workload.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "xgrid_cells_per_sec"
+UNIT = "xgrid cells/s"
+
+# name -> (cubed-sphere N, nlon, nlat, order)
+WORKLOADS = {
+    "c768": (768, 2880, 1440, 2),     # BASELINE.json configs[3]: C768 -> 1/8 degree, order 2 (the metric's config)
+    "c96": (96, 1440, 720, 2),        # configs[1] weights
+    "c48": (48, 360, 180, 1),         # configs[0]
+    "c384": (384, 1440, 720, 2),
+    "c3072": (3072, 11520, 5760, 2),  # configs[4] (sizing run)
+}
+
+# Algorithmic FP64 operations per emitted exchange cell (source-level + - * / compare fabs = 1, sin/cos = 1),
+# counted by the op-counting build of the oracle (oracle/count_ops.py, see DESIGN.md "Algorithmic work").
+OPS_PER_XCELL = {1: 4.6e2, 2: 6.5e2}
+# bytes the clip kernel must move per candidate pair (order 2): pair 8 + src/dst cell polygons 2*(8*8+1) ... see DESIGN.md
+CLIP_BYTES_PER_PAIR = {1: 8 + 8, 2: 8 + 24}
+
+
+def workload_label(name):
+    n, nlon, nlat, order = WORKLOADS[name]
+    return f"C{n} gnomonic_ed cubed sphere (6x{n}x{n}) -> {nlon}x{nlat} lat-lon, conserve_order{order} weight generation"
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU reference / oracle sample (bounded): destination row bands on all host cores
+# ---------------------------------------------------------------------------------------------
+_G = {}
+
+
+def _band_worker(args):
+    import xgtest
+    jsc, jec, order, use_ref = args
+    lonc, latc, lon2, lat2 = _G["grids"]
+    t0 = time.perf_counter()
+    if use_ref:
+        r = xgtest.ref_setup(lonc, latc, lon2, lat2, order, jsc=jsc, jec=jec)
+    else:
+        r = xgtest.oracle_setup(lonc, latc, lon2[jsc:jec + 2], lat2[jsc:jec + 2], order)
+    return r["nxgrid"], time.perf_counter() - t0
+
+
+def cpu_sample(name, rows_per_worker, cores, pool=None):
+    """One bounded sample: `cores` destination bands of rows_per_worker rows, evenly spread over the
+    latitudes, each run by one process exactly as a fregrid_parallel rank owning that band would
+    (fregrid_util.c:592-603 layout {1,npes}).  Returns (xcells, wall seconds, kind)."""
+    import xgtest
+    n, nlon, nlat, order = WORKLOADS[name]
+    use_ref = xgtest.ref_lib() is not None
+    rows_per_worker = max(1, min(rows_per_worker, nlat // cores))
+    starts = [int((k + 0.5) * nlat / cores) for k in range(cores)]
+    jobs = [(min(s, nlat - rows_per_worker), min(s, nlat - rows_per_worker) + rows_per_worker - 1, order, use_ref) for s in starts]
+    t0 = time.perf_counter()
+    res = pool.map(_band_worker, jobs, chunksize=1)
+    wall = time.perf_counter() - t0
+    return sum(r[0] for r in res), wall, ("reference" if use_ref else "port")
+
+
+def make_pool(name, cores):
+    import xgtest
+    pkg = xgtest.package()
+    n, nlon, nlat, order = WORKLOADS[name]
+    if xgtest.ref_lib() is not None:
+        lonc, latc = xgtest.ref_cubed_sphere(n)           # the reference's own generator
+    else:
+        lonc, latc = pkg.cubed_sphere_grid(n)
+    lon2, lat2 = pkg.latlon_grid(nlon, nlat)
+    _G["grids"] = (lonc, latc, lon2, lat2)
+    ctx = mp.get_context("fork")                          # grids are inherited copy-on-write
+    return ctx.Pool(cores)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = args.workload
+    cores = os.cpu_count() or 1
+    pool = make_pool(name, cores)
+    # calibrate one row per worker, then size the per-step sample to finish the whole run in a few minutes
+    x0, t0, kind = cpu_sample(name, 1, cores, pool)
+    budget = min(25.0, max(t0, 150.0 / (args.steps + args.warmup)))
+    rows = max(1, min(int(budget / max(t0, 1e-3)), WORKLOADS[name][2] // cores))
+    for _ in range(max(0, args.warmup - 1)):
+        cpu_sample(name, rows, cores, pool)
+    tot_x, tot_t = 0, 0.0
+    for _ in range(args.steps):
+        x, t, kind = cpu_sample(name, rows, cores, pool)
+        tot_x += x; tot_t += t
+    pool.close()
+    val = tot_x / tot_t
+    n, nlon, nlat, order = WORKLOADS[name]
+    sample = (f"{cores} destination row bands x {rows} rows of {nlat} (evenly spaced latitudes), all 6 source tiles, "
+              f"one process per band; {tot_x // max(args.steps, 1)} xcells per step")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_label(name), "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = ge.load_package()
+    name = args.workload
+    n, nlon, nlat, order = WORKLOADS[name]
+    opcode = pkg.CONSERVE_ORDER2 if order == 2 else pkg.CONSERVE_ORDER1
+
+    lonc, latc = pkg.cubed_sphere_grid(n)
+    lon2, lat2 = pkg.latlon_grid(nlon, nlat)
+    plan = pkg.XgridPlan(local)
+    plan.set_dst(lon2, lat2)
+    plan.set_src(lonc, latc)
+    bounds = plan.partition(world)            # equal candidate-pair counts per rank; static, part of the plan
+    plan.set_src_window(bounds[rank], bounds[rank + 1])
+    ext = torch.cuda.ExternalStream(plan.stream, device=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    mine = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def step():
+        nx = plan.generate(opcode)
+        if world > 1:                           # the path's one exchange: per-rank counts -> global offsets
+            with torch.cuda.stream(ext):
+                mine.fill_(nx)
+                dist.all_gather_into_tensor(counts, mine)
+        return nx
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    plan.reset_phase_ms()
+    launches0 = pkg.kernel_launches()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(ext):
+        e0.record()
+    nx = 0
+    for _ in range(args.steps):
+        nx = step()
+    with torch.cuda.stream(ext):
+        e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = pkg.kernel_launches() - launches0
+    _, phase_sum, ngen = plan.phase_ms()
+    npairs = plan.npairs
+
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([nx, npairs, launches], dtype=torch.int64, device=dev)
+    clip_ms = torch.tensor([phase_sum["clip"] / max(ngen, 1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        dist.all_reduce(clip_ms, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    nx_total, npairs_total, launches_total = (int(v) for v in tot.tolist())
+    value = nx_total / (ms * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers (pinned), every step: H2D grids, generate, D2H result
+    h_lon1 = torch.from_numpy(np.ascontiguousarray(lonc)).pin_memory(); h_lat1 = torch.from_numpy(np.ascontiguousarray(latc)).pin_memory()
+    h_lon2 = torch.from_numpy(lon2).pin_memory(); h_lat2 = torch.from_numpy(lat2).pin_memory()
+    cap = int(nx * 1.02) + 1024
+    hb = {k: torch.empty(cap, dtype=torch.int32).pin_memory() for k in ("t_in", "i_in", "j_in", "i_out", "j_out")}
+    hb.update({k: torch.empty(cap, dtype=torch.float64).pin_memory() for k in (("area", "di", "dj") if order == 2 else ("area",))})
+    nx1 = np.full(6, n, np.int32)
+
+    def e2e_step():
+        plan.set_dst(h_lon2.numpy(), h_lat2.numpy())
+        plan.set_src_flat(nx1, nx1, h_lon1.numpy().reshape(-1), h_lat1.numpy().reshape(-1))
+        plan.set_src_window(bounds[rank], bounds[rank + 1])
+        k = plan.generate(opcode)
+        plan.result_host_into(hb)
+        return k
+
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e_step()
+    barrier()
+    with torch.cuda.stream(ext):
+        e0.record()
+    for _ in range(e2e_steps):
+        k = e2e_step()
+    with torch.cuda.stream(ext):
+        e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    h2d = (h_lon1.numel() + h_lat1.numel() + h_lon2.numel() + h_lat2.numel()) * 8
+    d2h = k * (5 * 4 + (3 if order == 2 else 1) * 8)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (clip): FP64 pipe, measured DFMA peak
+    fp64_peak = pkg.fp64_peak_tflops(local)
+    clip_s = float(clip_ms.item()) * 1e-3
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    flops = OPS_PER_XCELL[order] * nx_total / max(world, 1)          # per launch (per rank)
+    achieved_tf = flops / clip_s * 1e-12 if clip_s > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "clip_traffic.json"))).get(name)
+    except Exception:
+        pass
+    roofline = {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": traffic,
+                "kernel": f"clip_kernel<{order}>", "kernel_ms": clip_s * 1e3, "kernel_share_of_step": clip_s * 1e3 / ms,
+                "peak_source": "DFMA microbenchmark measured live by bench.py (MEASURED_PEAKS.json has no FP64 entry)",
+                "algorithmic_flops_per_xcell": OPS_PER_XCELL[order],
+                "hbm": {"achieved_gbs": (npairs_total / world) * (CLIP_BYTES_PER_PAIR[order] + 0) / clip_s * 1e-9 if clip_s > 0 else None,
+                        "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+    phases = {kk: vv / max(ngen, 1) for kk, vv in phase_sum.items()}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        pool = make_pool(name, cores)
+        x, tsec, kind = cpu_sample(name, 2, cores, pool)
+        pool.close()
+        cpu = {"value": x / tsec, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"{cores} destination row bands x 2 rows of {nlat} (evenly spaced), all 6 source tiles, one process per band: {x} xcells in {tsec:.1f} s"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload_label(name), "nxgrid": nx_total, "candidate_pairs": npairs_total,
+                       "sharding": f"{world} source-cell windows of equal candidate-pair count" if world > 1 else "single window",
+                       "l2": "inputs larger than L2 (cell tables ~1.4 GB per rank are re-read every step)"},
+            "clocks": clocks, "gpu_launches": launches_total,
+            "e2e": {"value": nx_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms, "steps": e2e_steps},
+            "roofline": roofline, "phase_ms": phases, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c768", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

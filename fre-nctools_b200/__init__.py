@@ -80,6 +80,11 @@ def lib():
     L.xgb_plan_dst_area_host.argtypes = [vp, vp]
     L.xgb_cubed_sphere_grid.argtypes = [C.c_int, vp, vp, vp, vp]
     L.xgb_latlon_grid.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp]
+    L.xgb_plan_phase_ms.argtypes = [vp, vp, vp, vp]
+    L.xgb_plan_reset_phase_ms.restype = None
+    L.xgb_plan_reset_phase_ms.argtypes = [vp]
+    L.xgb_kernel_launches.restype = C.c_longlong
+    L.xgb_fp64_peak_tflops.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.xgb_ref_trig_host.restype = None
     L.xgb_ref_trig_host.argtypes = [C.c_longlong] + [vp] * 5
     L.xgb_ref_trig_device.argtypes = [C.c_longlong] + [vp] * 5
@@ -193,22 +198,31 @@ class XgridPlan:
     def set_src(self, lons, lats, mask=None):
         """lons/lats: list of per-tile [ny+1, nx+1] arrays, or one [ntiles, ny+1, nx+1] array."""
         if not isinstance(lons, (list, tuple)):
+            if lons.ndim == 3 and not _is_torch(lons) and lons.flags["C_CONTIGUOUS"] and lats.flags["C_CONTIGUOUS"]:
+                nt, nyp, nxp = lons.shape          # already concatenated in memory: no staging copy
+                return self.set_src_flat([nxp - 1] * nt, [nyp - 1] * nt, lons.reshape(-1), lats.reshape(-1), mask)
             lons = [lons[t] for t in range(lons.shape[0])] if lons.ndim == 3 else [lons]
             lats = [lats[t] for t in range(lats.shape[0])] if lats.ndim == 3 else [lats]
-        nx = (C.c_int * len(lons))(*[int(a.shape[1] - 1) for a in lons])
-        ny = (C.c_int * len(lons))(*[int(a.shape[0] - 1) for a in lons])
+        nx = [int(a.shape[1] - 1) for a in lons]
+        ny = [int(a.shape[0] - 1) for a in lons]
         if _is_torch(lons[0]):
             import torch
             lon = torch.cat([a.reshape(-1) for a in lons]); lat = torch.cat([a.reshape(-1) for a in lats])
         else:
             lon = np.concatenate([np.asarray(a, dtype=np.float64).ravel() for a in lons])
             lat = np.concatenate([np.asarray(a, dtype=np.float64).ravel() for a in lats])
+        return self.set_src_flat(nx, ny, lon, lat, mask)
+
+    def set_src_flat(self, nx, ny, lon, lat, mask=None):
+        """tiles already concatenated: lon/lat flat arrays of sum((nx+1)*(ny+1)) vertices (host numpy, pinned or not, or CUDA tensors)."""
+        nxa = (C.c_int * len(nx))(*[int(v) for v in nx])
+        nya = (C.c_int * len(ny))(*[int(v) for v in ny])
         pl, dl, kl = _f64_ptr(lon); pa, da, ka = _f64_ptr(lat)
         pm, dm, km = _f64_ptr(mask)
         if dl != da or (mask is not None and dm != dl):
             raise TypeError("lon, lat and mask must live on the same side")
-        self._ck(self._L.xgb_plan_set_src(self._p, len(lons), nx, ny, pl, pa, pm, dl))
-        self.tiles = [(int(nx[t]), int(ny[t])) for t in range(len(lons))]
+        self._ck(self._L.xgb_plan_set_src(self._p, len(nx), nxa, nya, pl, pa, pm, dl))
+        self.tiles = [(int(a), int(b)) for a, b in zip(nx, ny)]
         self.ncell_src = sum(a * b for a, b in self.tiles)
 
     def set_src_window(self, begin, end):
@@ -230,6 +244,27 @@ class XgridPlan:
     @property
     def npairs(self):
         return int(self._L.xgb_plan_last_npairs(self._p))
+
+    PHASES = ("candidate_count", "candidate_fill", "clip", "scan", "scatter_finalize")
+
+    def phase_ms(self):
+        """(last generate's per-phase ms, accumulated per-phase ms, number of generates accumulated)"""
+        last = (C.c_float * 5)(); acc = (C.c_double * 5)(); n = C.c_longlong(0)
+        self._ck(self._L.xgb_plan_phase_ms(self._p, last, acc, C.byref(n)))
+        return dict(zip(self.PHASES, list(last))), dict(zip(self.PHASES, list(acc))), int(n.value)
+
+    def reset_phase_ms(self):
+        self._L.xgb_plan_reset_phase_ms(self._p)
+
+    def result_host_into(self, bufs):
+        """D2H into caller-provided (e.g. pinned) buffers: dict of numpy arrays / torch CPU tensors keyed like result_host()."""
+        def ptr(k):
+            b = bufs.get(k)
+            if b is None:
+                return None
+            return b.data_ptr() if _is_torch(b) else b.ctypes.data
+        self._ck(self._L.xgb_plan_result_host(self._p, ptr("t_in"), ptr("i_in"), ptr("j_in"), ptr("i_out"), ptr("j_out"),
+                                              ptr("area"), ptr("di"), ptr("dj")))
 
     def result_host(self):
         n = self.nxgrid
@@ -270,6 +305,17 @@ class XgridPlan:
         a = np.empty(self.nx_dst * self.ny_dst)
         self._ck(self._L.xgb_plan_dst_area_host(self._p, a.ctypes.data))
         return a
+
+
+def kernel_launches():
+    return int(lib().xgb_kernel_launches())
+
+
+def fp64_peak_tflops(device=0):
+    v = C.c_double(0)
+    if lib().xgb_fp64_peak_tflops(int(device), C.byref(v)):
+        raise XgridError(_err())
+    return float(v.value)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -93,6 +93,7 @@ extern "C" xgb_plan* xgb_plan_create(int device)
     delete p;
     return nullptr;
   }
+  for (int k = 0; k < 6; ++k) cudaEventCreate(&p->ev[k]);
   cudaMemsetAsync(p->err_dev, 0, sizeof(int), p->st);
   return p;
 }
@@ -109,6 +110,7 @@ extern "C" void xgb_plan_destroy(xgb_plan* p)
                     &p->gc_src_xyz, &p->gc_dst_xyz};
   for (DevBuf* b : bufs) b->release();
   xgb_apply_release(p);
+  for (int k = 0; k < 6; ++k) if (p->ev[k]) cudaEventDestroy(p->ev[k]);
   if (p->err_dev) cudaFree(p->err_dev);
   if (p->total_dev) cudaFree(p->total_dev);
   if (p->total_host) cudaFreeHost(p->total_host);
@@ -294,8 +296,10 @@ extern "C" long long xgb_plan_generate(xgb_plan* p, unsigned int opcode)
   const long long s0 = p->s0, ns = p->ns;
   const double* mask = p->has_mask ? (const double*)p->mask.p : nullptr;
   unsigned long long npairs = 0;
+  cudaEventRecord(p->ev[0], p->st);
   if (count_candidates(p, s0, ns, &npairs)) return -1;
   p->npairs = npairs;
+  cudaEventRecord(p->ev[1], p->st);
 
   if (p->pairs.reserve((size_t)npairs * sizeof(int2) + 16) || p->parea.reserve((size_t)npairs * sizeof(double) + 16) ||
       p->out_off.reserve((size_t)(ns + 1) * sizeof(uint32_t)))
@@ -306,8 +310,10 @@ extern "C" long long xgb_plan_generate(xgb_plan* p, unsigned int opcode)
   launch_candidates(true, p->src, s0, ns, mask, p->pyr, p->dst, (const uint32_t*)p->pair_off.p,
                     nullptr, (int2*)p->pairs.p, p->err_dev, p->st);
   cudaMemsetAsync(p->cnt.p, 0, (size_t)(ns + 1) * sizeof(uint32_t), p->st);
+  cudaEventRecord(p->ev[2], p->st);
   launch_clip(order, p->src, p->dst, mask, (const int2*)p->pairs.p, npairs, s0,
               (double*)p->parea.p, (double*)p->pclon.p, (double*)p->pclat.p, (uint32_t*)p->cnt.p, p->err_dev, p->st);
+  cudaEventRecord(p->ev[3], p->st);
   launch_exclusive_scan((const uint32_t*)p->cnt.p, (uint32_t*)p->out_off.p, ns, p->total_dev + 1, p->scan_tmp.p, p->st);
   if (cudaMemcpyAsync(p->total_host + 1, p->total_dev + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->st) != cudaSuccess ||
       cudaStreamSynchronize(p->st) != cudaSuccess) {
@@ -324,6 +330,7 @@ extern "C" long long xgb_plan_generate(xgb_plan* p, unsigned int opcode)
     return -1;
   if (order == 2 && (p->clon.reserve(nd) || p->clat.reserve(nd) || p->di.reserve(nd) || p->dj.reserve(nd))) return -1;
 
+  cudaEventRecord(p->ev[4], p->st);
   launch_scatter(order, (const int2*)p->pairs.p, npairs, (const double*)p->parea.p, (const double*)p->pclon.p,
                  (const double*)p->pclat.p, (const uint32_t*)p->pair_off.p, (const uint32_t*)p->out_off.p,
                  (const TileDesc*)p->tiles_dev.p, (int)p->tiles.size(), s0, p->nx2,
@@ -332,11 +339,37 @@ extern "C" long long xgb_plan_generate(xgb_plan* p, unsigned int opcode)
   if (order == 2)
     launch_order2_finalize(p->src, s0, ns, (const uint32_t*)p->out_off.p, (const double*)p->area.p,
                            (const double*)p->clon.p, (const double*)p->clat.p, (double*)p->di.p, (double*)p->dj.p, p->st);
+  cudaEventRecord(p->ev[5], p->st);
   if (check_kernel_errors(p, false)) return -1;
+  for (int k = 0; k < 5; ++k) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, p->ev[k], p->ev[k + 1]);
+    p->phase_ms[k] = ms;
+    p->phase_ms_sum[k] += ms;
+  }
+  p->generates += 1;
   return p->nxgrid;
 }
 
 extern "C" long long xgb_plan_last_npairs(xgb_plan* p) { return p ? (long long)p->npairs : -1; }
+
+// phases: 0 candidate count+scan, 1 candidate fill, 2 clip, 3 scan of accepted counts, 4 scatter+finalize
+extern "C" int xgb_plan_phase_ms(xgb_plan* p, float* last5, double* sum5, long long* generates)
+{
+  if (!p) { xgb_set_error("null plan"); return 1; }
+  for (int k = 0; k < 5; ++k) { if (last5) last5[k] = p->phase_ms[k]; if (sum5) sum5[k] = p->phase_ms_sum[k]; }
+  if (generates) *generates = p->generates;
+  return 0;
+}
+
+extern "C" void xgb_plan_reset_phase_ms(xgb_plan* p)
+{
+  if (!p) return;
+  for (int k = 0; k < 5; ++k) p->phase_ms_sum[k] = 0.0;
+  p->generates = 0;
+}
+
+extern "C" long long xgb_kernel_launches(void) { return xgb::g_launches; }
 
 extern "C" int xgb_plan_result_device(xgb_plan* p, xgb_xgrid_view* v)
 {

@@ -17,6 +17,8 @@
 
 namespace xgb {
 
+long long g_launches = 0;
+
 // =============================================================================================
 // cell precompute
 // =============================================================================================
@@ -70,6 +72,7 @@ void launch_cell_precompute(const TileDesc& tile, const double* lon, const doubl
   if (n <= 0) return;
   const int threads = 128;
   const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  ++g_launches;
   cell_precompute_kernel<<<blocks, threads, 0, st>>>(tile, lon, lat, cells, err);
 }
 
@@ -105,6 +108,7 @@ void launch_pyramid_level(const PyrLevel& child, double* ymin, double* ymax, dou
 {
   const long long n = (long long)nx * ny;
   const int threads = 256;
+  ++g_launches;
   pyramid_level_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(child, ymin, ymax, xmin, xmax, nx, ny);
 }
 
@@ -206,6 +210,7 @@ void launch_candidates(bool fill, const CellSet& src, long long s0, long long ns
   if (ns <= 0) return;
   const int threads = 128;
   const unsigned blocks = (unsigned)((ns + threads - 1) / threads);
+  ++g_launches;
   if (fill) candidate_kernel<true><<<blocks, threads, 0, st>>>(src, s0, ns, mask, pyr, dst, pair_off, cnt, pairs, err);
   else      candidate_kernel<false><<<blocks, threads, 0, st>>>(src, s0, ns, mask, pyr, dst, pair_off, cnt, pairs, err);
 }
@@ -361,6 +366,7 @@ void launch_clip(int order, const CellSet& src, const CellSet& dst, const double
 {
   if (npairs == 0) return;
   const unsigned blocks = (unsigned)((npairs + kClipThreads - 1) / kClipThreads);
+  ++g_launches;
   if (order == 2) clip_kernel<2><<<blocks, kClipThreads, 0, st>>>(src, dst, mask, pairs, npairs, s0, parea, pclon, pclat, cnt, err);
   else            clip_kernel<1><<<blocks, kClipThreads, 0, st>>>(src, dst, mask, pairs, npairs, s0, parea, pclon, pclat, cnt, err);
 }
@@ -419,6 +425,7 @@ void launch_scatter(int order, const int2* pairs, unsigned long long npairs,
   if (npairs == 0) return;
   const int threads = 256;
   const unsigned blocks = (unsigned)((npairs + threads - 1) / threads);
+  ++g_launches;
   if (order == 2)
     scatter_kernel<2><<<blocks, threads, 0, st>>>(pairs, npairs, parea, pclon, pclat, pair_off, out_off, tiles, ntiles, s0, nx2,
                                                   t_in, i_in, j_in, i_out, j_out, area, clon, clat);
@@ -473,6 +480,7 @@ void launch_order2_finalize(const CellSet& src, long long s0, long long ns, cons
 {
   if (ns <= 0) return;
   const int threads = 128;
+  ++g_launches;
   order2_finalize_kernel<<<(unsigned)((ns + threads - 1) / threads), threads, 0, st>>>(src, s0, ns, out_off, area, clon, clat, di, dj);
 }
 
@@ -578,8 +586,11 @@ void launch_exclusive_scan(const uint32_t* in, uint32_t* out, long long n, unsig
   if (n <= 0) { cudaMemsetAsync(out, 0, sizeof(uint32_t), st); cudaMemsetAsync(total_dev, 0, sizeof(unsigned long long), st); return; }
   const long long nblk = (n + kScanTile - 1) / kScanTile;
   unsigned long long* bsum = (unsigned long long*)tmp;
+  ++g_launches;
   scan_block_sums_kernel<<<(unsigned)nblk, kScanThreads, 0, st>>>(in, n, bsum);
+  ++g_launches;
   scan_spine_kernel<<<1, 1024, 0, st>>>(bsum, nblk, total_dev);
+  ++g_launches;
   scan_final_kernel<<<(unsigned)nblk, kScanThreads, 0, st>>>(in, out, n, bsum);
 }
 
@@ -609,6 +620,7 @@ __global__ void partition_kernel(const uint32_t* __restrict__ pair_off, long lon
 void launch_partition(const uint32_t* pair_off, long long ncell, unsigned long long total, int nparts,
                       long long* bounds, cudaStream_t st)
 {
+  ++g_launches;
   partition_kernel<<<(nparts + 1 + 63) / 64, 64, 0, st>>>(pair_off, ncell, total, nparts, bounds);
 }
 }  // namespace xgb

@@ -51,6 +51,12 @@ struct xgb_plan {
   unsigned long long* total_dev = nullptr;    // [2]
   unsigned long long* total_host = nullptr;   // pinned [2]
 
+  // per-phase device timing of generate (CUDA events on the plan stream)
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  float phase_ms[5] = {0, 0, 0, 0, 0};
+  double phase_ms_sum[5] = {0, 0, 0, 0, 0};
+  long long generates = 0;
+
   xgb_apply_state* apply = nullptr;
 };
 
@@ -59,6 +65,7 @@ long long xgb_generate_great_circle(xgb_plan* p, int order);   // xgrid_gc_capi.
 void xgb_apply_release(xgb_plan* p);                           // apply_capi.cu
 
 namespace xgb {
+extern long long g_launches;     // kernels launched by this library since load (xgrid_kernels.cu)
 void launch_partition(const uint32_t* pair_off, long long ncell, unsigned long long total, int nparts,
                       long long* bounds, cudaStream_t st);
 }

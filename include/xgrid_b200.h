@@ -105,6 +105,19 @@ long long xgb_plan_generate(xgb_plan *p, unsigned int opcode);
 /* candidate pairs examined by the last generate (clip-kernel work items) */
 long long xgb_plan_last_npairs(xgb_plan *p);
 
+/* Device time of the phases of generate, measured with CUDA events on the plan's stream:
+ * [0] candidate count + scan, [1] candidate fill, [2] clip kernel, [3] scan of accepted counts,
+ * [4] scatter + order-2 finalize.  last5: the last generate (ms); sum5/generates: accumulated
+ * since xgb_plan_reset_phase_ms.  Any pointer may be NULL. */
+int  xgb_plan_phase_ms(xgb_plan *p, float *last5, double *sum5, long long *generates);
+void xgb_plan_reset_phase_ms(xgb_plan *p);
+
+/* kernels launched by this library since it was loaded (all plans) */
+long long xgb_kernel_launches(void);
+
+/* DFMA throughput of `device` measured now (TFLOP/s, 2 flops per DFMA): the FP64 roofline denominator */
+int xgb_fp64_peak_tflops(int device, double *tflops);
+
 /* Device pointers to the last result (valid until the next generate/destroy).  Layout =
  * Interp_config (globals.h:149-163): t_in,i_in,j_in,i_out,j_out int32[nxgrid]; area f64 (m^2);
  * di,dj f64 (order 2 only: tile1_distance, conserve_interp.c:351-358; NULL for order 1). */

@@ -26,6 +26,21 @@
 #define ORC_AREA_RATIO_THRESH 1.e-6           /* create_xgrid.c:27 */
 #define ORC_MASK_THRESH 0.5                   /* create_xgrid.c:28 */
 
+/* Optional event counters (build with -DORC_COUNT_OPS -> liboracle_xgrid_ops.so, see oracle/count_ops.py):
+ * they count how often each primitive step runs so that DESIGN.md can state the algorithmic FP64
+ * operations per exchange cell from the source-level operation count of each step. */
+enum { CNT_CLIP_CALLS, CNT_INSIDE_EDGE, CNT_INTERSECT, CNT_AREA_CALLS, CNT_AREA_EDGE_GEN, CNT_AREA_EDGE_FLAT,
+       CNT_AREA_EDGE_POLE, CNT_RATIO_TESTS, CNT_ACCEPTED, CNT_CTRLON_EDGE, CNT_CTRLAT_EDGE_GEN, CNT_CTRLAT_EDGE_FLAT,
+       CNT_CLIP_NONEMPTY, CNT_N };
+#ifdef ORC_COUNT_OPS
+static long orc_cnt[CNT_N];
+#define ORC_COUNT(k) (orc_cnt[k]++)
+void orc_counts_get(long *out) { int k; for (k = 0; k < CNT_N; k++) out[k] = orc_cnt[k]; }
+void orc_counts_reset(void) { int k; for (k = 0; k < CNT_N; k++) orc_cnt[k] = 0; }
+#else
+#define ORC_COUNT(k) ((void)0)
+#endif
+
 static void orc_die(const char *msg)
 {
   fprintf(stderr, "xgrid_oracle FATAL: %s\n", msg);
@@ -110,6 +125,7 @@ double orc_poly_area(const double x[], const double y[], int n)
 {
   double acc = 0.0;
   int i;
+  ORC_COUNT(CNT_AREA_CALLS);
   for (i = 0; i < n; i++) {
     int ip = (i+1)%n;
     double dx = x[ip] - x[i];
@@ -118,11 +134,14 @@ double orc_poly_area(const double x[], const double y[], int n)
     if (dx < -ORC_PI) dx = dx + 2.0*ORC_PI;
     if (fabs(dx + ORC_PI) < ORC_SMALL || fabs(dx - ORC_PI) < ORC_SMALL) {
       acc += ORC_PI;                       /* side through a pole (:434-437) */
+      ORC_COUNT(CNT_AREA_EDGE_POLE);
       continue;
     }
-    if (fabs(lat1 - lat2) < ORC_SMALL)
+    if (fabs(lat1 - lat2) < ORC_SMALL) {
+      ORC_COUNT(CNT_AREA_EDGE_FLAT);
       acc -= dx * sin(0.5*(lat1 + lat2));
-    else {
+    } else {
+      ORC_COUNT(CNT_AREA_EDGE_GEN);
       double dy = 0.5*(lat1 - lat2);
       double dat = sin(dy)/dy;
       acc -= dx * sin(0.5*(lat1 + lat2)) * dat;
@@ -147,10 +166,13 @@ double orc_poly_ctrlat(const double x[], const double y[], int n)
     if (dx == 0.0) continue;
     if (dx > ORC_PI)   dx = dx - 2.0*ORC_PI;
     if (dx <= -ORC_PI) dx = dx + 2.0*ORC_PI;
-    if (fabs(hdy) < ORC_SMALL)
+    if (fabs(hdy) < ORC_SMALL) {
+      ORC_COUNT(CNT_CTRLAT_EDGE_FLAT);
       acc -= dx*(2*cos(avg_y) + lat2*sin(avg_y) - cos(lat1));
-    else
+    } else {
+      ORC_COUNT(CNT_CTRLAT_EDGE_GEN);
       acc -= dx*((sin(hdy)/hdy)*(2*cos(avg_y) + lat2*sin(avg_y)) - cos(lat1));
+    }
   }
   return acc*ORC_RADIUS*ORC_RADIUS;
 }
@@ -165,6 +187,7 @@ double orc_poly_ctrlon(const double x[], const double y[], int n, double clon)
     double phi1 = x[ip], phi2 = x[i], lat1 = y[ip], lat2 = y[i];
     double dphi = phi1 - phi2, dphi1, dphi2, f1, f2;
     if (dphi == 0.0) continue;
+    ORC_COUNT(CNT_CTRLON_EDGE);
     f1 = 0.5*(cos(lat1)*sin(lat1) + lat1);
     f2 = 0.5*(cos(lat2)*sin(lat2) + lat2);
     if (dphi > ORC_PI)  dphi = dphi - 2.0*ORC_PI;
@@ -190,6 +213,7 @@ double orc_poly_ctrlon(const double x[], const double y[], int n, double clon)
 static int orc_inside_edge(double x0, double y0, double x1, double y1, double x, double y)
 {
   double product = (x - x0)*(y1 - y0) + (x0 - x1)*(y - y0);
+  ORC_COUNT(CNT_INSIDE_EDGE);
   return (product <= 1.e-12) ? 1 : 0;
 }
 
@@ -200,6 +224,7 @@ int orc_clip_2dx2d(const double lon1[], const double lat1[], int n1,
 {
   double px[ORC_MV], py[ORC_MV], qx[ORC_MV], qy[ORC_MV];
   int np = n1, k, e, wrap = 0;
+  ORC_COUNT(CNT_CLIP_CALLS);
 
   for (k = 0; k < n1; k++) {
     px[k] = lon1[k]; py[k] = lat1[k];
@@ -225,6 +250,7 @@ int orc_clip_2dx2d(const double lon1[], const double lat1[], int n1,
           double dy1 = by - ay, dy2 = ey1 - ey0, dx1 = bx - ax, dx2 = ex1 - ex0;
           double ds1 = ay*bx - by*ax, ds2 = ey0*ex1 - ey1*ex0;
           double determ = dy2*dx1 - dy1*dx2;
+          ORC_COUNT(CNT_INTERSECT);
           if (fabs(determ) < 1.0e-30) orc_die("clip_2dx2d: parallel edges");
           lon_out[no]   = (dx2*ds1 - dx1*ds2)/determ;
           lat_out[no++] = (dy2*ds1 - dy1*ds2)/determ;
@@ -378,11 +404,13 @@ long orc_create_xgrid_2dx2d(int order, int nlon_in, int nlat_in, int nlon_out, i
           if (xmin2 >= s_xmax || xmax2 <= s_xmin) continue;                  /* :801 */
           no = orc_clip_2dx2d(x1, y1, n1, x2, y2, n2, xo, yo);               /* :802 */
           if (no > 0) {
+            ORC_COUNT(CNT_CLIP_NONEMPTY); ORC_COUNT(CNT_RATIO_TESTS);
             double xa = orc_poly_area(xo, yo, no) * mask_in[(size_t)j1*nx1 + i1];
             double a1 = area_in[(size_t)j1*nx1 + i1], a2 = area_out[ij];
             double min_area = (a1 < a2) ? a1 : a2;
             if (xa/min_area > ORC_AREA_RATIO_THRESH) {                       /* :807 */
               if (nxgrid >= cap) { nxgrid = -1; goto done; }
+              ORC_COUNT(CNT_ACCEPTED);
               xarea[nxgrid] = xa;
               if (order == 2) {                                              /* :1091-1092 */
                 xclon[nxgrid] = orc_poly_ctrlon(xo, yo, no, s_xavg);
