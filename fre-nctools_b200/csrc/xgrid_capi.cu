@@ -107,6 +107,7 @@ extern "C" void xgb_plan_destroy(xgb_plan* p)
                     &p->src_store, &p->tiles_dev, &p->cnt, &p->pair_off, &p->out_off, &p->pairs, &p->parea,
                     &p->pclon, &p->pclat, &p->scan_tmp, &p->t_in, &p->i_in, &p->j_in, &p->i_out, &p->j_out,
                     &p->area, &p->clon, &p->clat, &p->di, &p->dj, &p->bounds_dev,
+                    &p->heavy_ctl, &p->heavy_flag, &p->heavy_list, &p->heavy_items, &p->heavy_pairs,
                     &p->gc_src_xyz, &p->gc_dst_xyz};
   for (DevBuf* b : bufs) b->release();
   xgb_apply_release(p);
@@ -136,8 +137,7 @@ static int carve_cellset(DevBuf& store, long long ncell, CellSet* cs)
   if (store.reserve(bytes)) return 1;
   double* b = (double*)store.p;
   cs->ncell = ncell;
-  cs->ymin = b; b += nd; cs->ymax = b; b += nd;
-  cs->xmin = b; b += nd; cs->xmax = b; b += nd;
+  cs->box = (Box*)b; b += 4 * nd;
   cs->xavg = b; b += nd; cs->area = b; b += nd;
   cs->vx = b; b += nd * kMaxV;
   cs->vy = b; b += nd * kMaxV;
@@ -169,6 +169,7 @@ static int check_kernel_errors(xgb_plan* p, bool fatal_like_reference)
   else if (e & kErrGcNotConvex) msg = "create_xgrid.c(clip_2dx2d_great_circle): grid box is not convex";
   else if (e & kErrGcWalk) msg = "clip_2dx2d_great_circle: polygon walk did not return to the first intersection";
   else if (e & kErrGcNodePool) msg = "getNext: curListPos >= MAXNODELIST";
+  else if (e & kErrHeavyOverflow) msg = "candidate search: heavy-cell work buffer exhausted; raise XGB_HEAVY_CAP";
   if (fatal_like_reference) fatal(msg);
   xgb_set_error("%s (kernel error bits 0x%x)", msg, e);
   return 1;
@@ -190,7 +191,7 @@ extern "C" int xgb_plan_set_dst(xgb_plan* p, int nx, int ny, const double* lon, 
   // pyramid: level 0 aliases the cell arrays, upper levels live in pyr_store
   Pyramid& P = p->pyr;
   P.nlev = 1;
-  P.lev[0] = PyrLevel{nx, ny, p->dst.ymin, p->dst.ymax, p->dst.xmin, p->dst.xmax};
+  P.lev[0] = PyrLevel{nx, ny, p->dst.box};
   size_t upper = 0;
   {
     int lx = nx, ly = ny;
@@ -201,14 +202,13 @@ extern "C" int xgb_plan_set_dst(xgb_plan* p, int nx, int ny, const double* lon, 
       ++P.nlev;
     }
   }
-  if (p->pyr_store.reserve(upper * 4 * sizeof(double) + 64)) return 1;
-  double* b = (double*)p->pyr_store.p;
+  if (p->pyr_store.reserve(upper * sizeof(Box) + 64)) return 1;
+  Box* b = (Box*)p->pyr_store.p;
   for (int l = 1; l < P.nlev; ++l) {
     const size_t n = (size_t)P.lev[l].nx * P.lev[l].ny;
-    double *a0 = b, *a1 = b + n, *a2 = b + 2 * n, *a3 = b + 3 * n;
-    b += 4 * n;
-    launch_pyramid_level(P.lev[l - 1], a0, a1, a2, a3, P.lev[l].nx, P.lev[l].ny, p->st);
-    P.lev[l].ymin = a0; P.lev[l].ymax = a1; P.lev[l].xmin = a2; P.lev[l].xmax = a3;
+    launch_pyramid_level(P.lev[l - 1], b, P.lev[l].nx, P.lev[l].ny, p->st);
+    P.lev[l].box = b;
+    b += n;
   }
   p->have_dst = true;
   p->gc_dst_ready = false;
@@ -253,13 +253,36 @@ extern "C" int xgb_plan_set_src_window(xgb_plan* p, long long begin, long long e
 }
 
 // count pass + scan over [s0, s0+ns); leaves pair_off (ns+1 entries) and the total on the host
+static int heavy_work(xgb_plan* p, long long ns, HeavyWork* hw)
+{
+  // capacity of the heavy-cell work lists; generous for pole caps, overridable for coarse-on-fine regridding
+  size_t cap = (size_t)1 << 20;
+  const size_t quarter = (size_t)(ns + p->dst.ncell) / 4;
+  if (quarter > cap) cap = quarter;
+  if (const char* env = getenv("XGB_HEAVY_CAP")) cap = (size_t)atoll(env);
+  if (p->heavy_ctl.reserve(sizeof(HeavyCtl)) || p->heavy_flag.reserve((size_t)ns + 16) ||
+      p->heavy_list.reserve((size_t)(ns + 1) * sizeof(int)) || p->heavy_items.reserve(2 * cap * sizeof(int2)) ||
+      p->heavy_pairs.reserve(cap * sizeof(int2)))
+    return 1;
+  hw->ctl = (HeavyCtl*)p->heavy_ctl.p;
+  hw->flag = (unsigned char*)p->heavy_flag.p;
+  hw->list = (int*)p->heavy_list.p;
+  hw->items[0] = (int2*)p->heavy_items.p;
+  hw->items[1] = hw->items[0] + cap;
+  hw->pairs = (int2*)p->heavy_pairs.p;
+  hw->cap = (unsigned)cap;
+  return 0;
+}
+
 static int count_candidates(xgb_plan* p, long long s0, long long ns, unsigned long long* total)
 {
   if (p->cnt.reserve((size_t)(ns + 1) * sizeof(uint32_t)) || p->pair_off.reserve((size_t)(ns + 1) * sizeof(uint32_t)) ||
       p->scan_tmp.reserve(scan_tmp_bytes(ns)))
     return 1;
+  HeavyWork hw;
+  if (heavy_work(p, ns, &hw)) return 1;
   launch_candidates(false, p->src, s0, ns, p->has_mask ? (const double*)p->mask.p : nullptr, p->pyr, p->dst,
-                    nullptr, (uint32_t*)p->cnt.p, nullptr, p->err_dev, p->st);
+                    nullptr, (uint32_t*)p->cnt.p, nullptr, hw, p->err_dev, p->st);
   launch_exclusive_scan((const uint32_t*)p->cnt.p, (uint32_t*)p->pair_off.p, ns, p->total_dev, p->scan_tmp.p, p->st);
   CU_OK(cudaMemcpyAsync(p->total_host, p->total_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->st));
   CU_OK(cudaStreamSynchronize(p->st));
@@ -307,8 +330,10 @@ extern "C" long long xgb_plan_generate(xgb_plan* p, unsigned int opcode)
   if (order == 2 && (p->pclon.reserve((size_t)npairs * sizeof(double) + 16) || p->pclat.reserve((size_t)npairs * sizeof(double) + 16)))
     return -1;
 
+  HeavyWork hw;
+  if (heavy_work(p, ns, &hw)) return -1;
   launch_candidates(true, p->src, s0, ns, mask, p->pyr, p->dst, (const uint32_t*)p->pair_off.p,
-                    nullptr, (int2*)p->pairs.p, p->err_dev, p->st);
+                    (uint32_t*)p->cnt.p, (int2*)p->pairs.p, hw, p->err_dev, p->st);
   cudaMemsetAsync(p->cnt.p, 0, (size_t)(ns + 1) * sizeof(uint32_t), p->st);
   cudaEventRecord(p->ev[2], p->st);
   launch_clip(order, p->src, p->dst, mask, (const int2*)p->pairs.p, npairs, s0,

@@ -196,6 +196,90 @@ __device__ __forceinline__ double poly_ctrlon(const PolyView& p, int n, double c
   return acc * kRadius * kRadius;
 }
 
+// ---------------------------------------------------------------------------------------------
+// poly_area, poly_ctrlon and poly_ctrlat of one polygon in a single pass over its edges.
+// Each of the three sums accumulates exactly the terms of its reference routine, in the same
+// order; what is shared is only trig that is provably the same number:
+//   * sincos(lat) of a vertex serves the edge before and the edge after it (the reference
+//     evaluates it twice) and doubles as poly_ctrlat's cos(lat1) (cos() and sincos() agree bit
+//     for bit: both are do_cos / do_sin of the same reduced argument, see ref_trig.cuh);
+//   * poly_area's sin(dy), dy = (lat1-lat2)/2, is -sin(hdy) of poly_ctrlat (odd function, exact), so
+//     sin(dy)/dy == sin(hdy)/hdy;
+//   * poly_area's sin((lat1+lat2)/2) equals the sin half of poly_ctrlat's sincos for |x| < 0.855469
+//     (both are do_sin(x, 0)); above that sin() takes another path and is evaluated separately.
+// ORDER == 1 evaluates poly_area only.
+// ---------------------------------------------------------------------------------------------
+template <int ORDER>
+__device__ __forceinline__ void poly_moments(const PolyView& p, int n, double clon,
+                                             double* area_out, double* ctrlon_out, double* ctrlat_out) {
+  double aacc = 0.0, lonacc = 0.0, latacc = 0.0;
+  double xi = p.X(0), yi = p.Y(0);
+  const double x0 = xi, y0 = yi;
+  double si = 0.0, ci = 0.0;
+  if (ORDER == 2) ref_sincos(yi, &si, &ci);
+  const double s0 = si, c0 = ci;
+  for (int i = 0; i < n; ++i) {
+    double xn, yn, sn = 0.0, cn = 0.0;
+    if (i + 1 < n) { xn = p.X(i + 1); yn = p.Y(i + 1); if (ORDER == 2) ref_sincos(yn, &sn, &cn); }
+    else { xn = x0; yn = y0; sn = s0; cn = c0; }
+    const double lat1 = yn, lat2 = yi;
+    const double dx_raw = xn - xi;                       // x[ip]-x[i] == phi1-phi2
+    double dxa = dx_raw;                                 // poly_area's wrapped dx (mosaic_util.c:429-432)
+    if (dxa > kPi)  dxa = dxa - 2.0 * kPi;
+    if (dxa < -kPi) dxa = dxa + 2.0 * kPi;
+    const bool pole_edge = (fabs(dxa + kPi) < kSmall || fabs(dxa - kPi) < kSmall);
+    const bool flat_area = (fabs(lat1 - lat2) < kSmall);
+    const double avg = 0.5 * (lat1 + lat2);
+    const double dy = 0.5 * (lat1 - lat2);               // hdy of poly_ctrlat is -dy
+    const bool moving = (ORDER == 2) && (dx_raw != 0.0); // poly_ctrlon / poly_ctrlat skip dx == 0 edges
+    const bool flat_lat = (fabs(dy) < kSmall);           // fabs(hdy) < SMALL_VALUE (create_xgrid.c:2114)
+
+    double s_avg = 0.0, c_avg = 0.0;
+    if (moving) ref_sincos(avg, &s_avg, &c_avg);
+    double dat = 0.0;
+    if ((!pole_edge && !flat_area) || (moving && !flat_lat)) dat = ref_sin(dy) / dy;
+
+    if (pole_edge) {
+      aacc += kPi;                                       // mosaic_util.c:434-437
+    } else {
+      const uint32_t hi = (uint32_t)(trig::bits(avg) >> 32) & 0x7fffffffu;
+      const double sin_avg = (moving && hi < 0x3feb6000u) ? s_avg : ref_sin(avg);
+      if (flat_area) aacc -= dxa * sin_avg;
+      else           aacc -= dxa * sin_avg * dat;
+    }
+    if (moving) {
+      // poly_ctrlat (create_xgrid.c:2100-2118)
+      double dxl = dx_raw;
+      if (dxl > kPi)   dxl = dxl - 2.0 * kPi;
+      if (dxl <= -kPi) dxl = dxl + 2.0 * kPi;
+      if (flat_lat) latacc -= dxl * (2 * c_avg + lat2 * s_avg - cn);
+      else          latacc -= dxl * (dat * (2 * c_avg + lat2 * s_avg) - cn);
+      // poly_ctrlon (create_xgrid.c:2176-2215)
+      const double f1 = 0.5 * (cn * sn + lat1);
+      const double f2 = 0.5 * (ci * si + lat2);
+      double dphi = dx_raw;
+      if (dphi > kPi)  dphi = dphi - 2.0 * kPi;
+      if (dphi < -kPi) dphi = dphi + 2.0 * kPi;
+      double dphi1 = xn - clon;
+      if (dphi1 > kPi)  dphi1 -= 2.0 * kPi;
+      if (dphi1 < -kPi) dphi1 += 2.0 * kPi;
+      double dphi2 = xi - clon;
+      if (dphi2 > kPi)  dphi2 -= 2.0 * kPi;
+      if (dphi2 < -kPi) dphi2 += 2.0 * kPi;
+      if (fabs(dphi2 - dphi1) < kPi) {
+        lonacc -= dphi * (dphi1 * f1 + dphi2 * f2) / 2.0;
+      } else {
+        const double fac = (dphi1 > 0.0) ? kPi : -kPi;
+        const double fint = f1 + (f2 - f1) * (fac - dphi1) / fabs(dphi);
+        lonacc -= 0.5 * dphi1 * (dphi1 - fac) * f1 - 0.5 * dphi2 * (dphi2 + fac) * f2 + 0.5 * fac * (dphi1 + dphi2) * fint;
+      }
+    }
+    xi = xn; yi = yn; si = sn; ci = cn;
+  }
+  *area_out = (aacc < 0) ? -aacc * kRadius * kRadius : aacc * kRadius * kRadius;
+  if (ORDER == 2) { *ctrlon_out = lonacc * kRadius * kRadius; *ctrlat_out = latacc * kRadius * kRadius; }
+}
+
 // inside_edge (create_xgrid.c:2342-2350)
 __device__ __forceinline__ bool inside_edge(double x0, double y0, double x1, double y1, double x, double y) {
   double product = (x - x0) * (y1 - y0) + (x0 - x1) * (y - y0);

@@ -16,11 +16,15 @@ struct TileDesc {
 // fix_lon'd cells of a whole mosaic, struct-of-arrays in HBM.  Vertex k of cell c is
 // vx[k*ncell + c]: a warp reading vertex k of 32 neighbouring cells reads 256 contiguous
 // bytes, and planes 4..7 (only pole cells use them) are never touched by ordinary cells.
+// latitude range of the 4 raw corners (create_xgrid.c:727-728) and longitude range after fix_lon
+// (:731-732): one 32-byte record so a box test costs two 16-byte loads
+struct __align__(16) Box { double ymin, ymax, xmin, xmax; };
+
 struct CellSet {
   long long ncell;
-  double *ymin, *ymax;        // latitude range of the 4 raw corners  (create_xgrid.c:727-728)
-  double *xmin, *xmax, *xavg; // longitude range / mean after fix_lon (create_xgrid.c:731-733)
-  double *area;               // poly_area of the fix_lon'd cell       (create_xgrid.c:66-88)
+  Box* box;                   // [ncell]
+  double* xavg;               // mean longitude after fix_lon          (create_xgrid.c:733)
+  double* area;               // poly_area of the fix_lon'd cell       (create_xgrid.c:66-88)
   unsigned char* nv;          // vertex count after fix_lon (3..8)
   double *vx, *vy;            // [kMaxV][ncell]
 };
@@ -29,7 +33,7 @@ struct CellSet {
 // (ix,iy) bounds level-l nodes (2ix..2ix+1, 2iy..2iy+1).  Upper levels only prune; the exact
 // reference predicates run at level 0.
 constexpr int kMaxLevels = 24;
-struct PyrLevel { int nx, ny; const double *ymin, *ymax, *xmin, *xmax; };
+struct PyrLevel { int nx, ny; const Box* box; };
 struct Pyramid { int nlev; PyrLevel lev[kMaxLevels]; };
 
 // error bits raised by kernels (read back by the C-ABI layer, which turns them into the
@@ -42,16 +46,27 @@ enum : int {
   kErrGcNotConvex     = 16,  // great-circle: grid box is not convex  (create_xgrid.c:1576-1579)
   kErrGcWalk          = 32,  // great-circle: polygon walk failed     (create_xgrid.c:1795,1822,1825)
   kErrGcNodePool      = 64,  // great-circle: node pool exhausted     (mosaic_util.c:1075)
+  kErrHeavyOverflow   = 128, // heavy-cell work buffer exhausted (internal capacity)
+};
+
+// device-side control block and work buffers of the level-synchronous "heavy cell" candidate path
+struct HeavyCtl { unsigned nheavy; unsigned npairs; unsigned nitems[kMaxLevels]; };
+struct HeavyWork {
+  HeavyCtl* ctl;
+  unsigned char* flag;   // [ns]
+  int* list;             // [ns] window-relative source cells handed to the heavy path
+  int2* items[2];        // ping-pong (heavy cell, node) work items, cap entries each
+  int2* pairs;           // (source cell, destination cell) candidates found by the heavy path, cap entries
+  unsigned cap;
 };
 
 // ---- launchers (xgrid_kernels.cu) ----------------------------------------------------------
 void launch_cell_precompute(const TileDesc& tile, const double* lon, const double* lat,
                             CellSet cells, int* err, cudaStream_t st);
-void launch_pyramid_level(const PyrLevel& child, double* ymin, double* ymax, double* xmin, double* xmax,
-                          int nx, int ny, cudaStream_t st);
+void launch_pyramid_level(const PyrLevel& child, Box* out, int nx, int ny, cudaStream_t st);
 void launch_candidates(bool fill, const CellSet& src, long long s0, long long ns, const double* mask,
                        const Pyramid& pyr, const CellSet& dst, const uint32_t* pair_off,
-                       uint32_t* cnt, int2* pairs, int* err, cudaStream_t st);
+                       uint32_t* cnt, int2* pairs, const HeavyWork& hw, int* err, cudaStream_t st);
 void launch_clip(int order, const CellSet& src, const CellSet& dst, const double* mask,
                  const int2* pairs, unsigned long long npairs, long long s0,
                  double* parea, double* pclon, double* pclat, uint32_t* cnt, int* err, cudaStream_t st);

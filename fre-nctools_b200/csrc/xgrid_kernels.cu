@@ -53,8 +53,7 @@ cell_precompute_kernel(TileDesc tile, const double* __restrict__ lon, const doub
   for (int k = 0; k < n; ++k) sum += x[k];
 
   const long long g = tile.cell_off + c;
-  cells.ymin[g] = ymin; cells.ymax[g] = ymax;
-  cells.xmin[g] = xmin; cells.xmax[g] = xmax;
+  cells.box[g] = Box{ymin, ymax, xmin, xmax};
   cells.xavg[g] = sum / n;
   cells.nv[g] = (unsigned char)n;
   for (int k = 0; k < n; ++k) {
@@ -79,14 +78,20 @@ void launch_cell_precompute(const TileDesc& tile, const double* lon, const doubl
 // =============================================================================================
 // min/max pyramid
 // =============================================================================================
+__device__ __forceinline__ Box load_box(const Box* p)
+{
+  const double2* q = reinterpret_cast<const double2*>(p);
+  const double2 a = __ldg(q), b = __ldg(q + 1);
+  return Box{a.x, a.y, b.x, b.y};
+}
+
 __global__ void __launch_bounds__(256)
-pyramid_level_kernel(PyrLevel child, double* __restrict__ ymin, double* __restrict__ ymax,
-                     double* __restrict__ xmin, double* __restrict__ xmax, int nx, int ny)
+pyramid_level_kernel(PyrLevel child, Box* __restrict__ out, int nx, int ny)
 {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= (long long)nx * ny) return;
   const int ix = (int)(t % nx), iy = (int)(t / nx);
-  double a = 1e300, b = -1e300, c = 1e300, d = -1e300;
+  Box r{1e300, -1e300, 1e300, -1e300};
 #pragma unroll
   for (int dy = 0; dy < 2; ++dy) {
     const int cy = 2 * iy + dy;
@@ -95,37 +100,38 @@ pyramid_level_kernel(PyrLevel child, double* __restrict__ ymin, double* __restri
     for (int dx = 0; dx < 2; ++dx) {
       const int cx = 2 * ix + dx;
       if (cx >= child.nx) continue;
-      const long long q = (long long)cy * child.nx + cx;
-      a = fmin(a, child.ymin[q]); b = fmax(b, child.ymax[q]);
-      c = fmin(c, child.xmin[q]); d = fmax(d, child.xmax[q]);
+      const Box b = load_box(child.box + (long long)cy * child.nx + cx);
+      r.ymin = fmin(r.ymin, b.ymin); r.ymax = fmax(r.ymax, b.ymax);
+      r.xmin = fmin(r.xmin, b.xmin); r.xmax = fmax(r.xmax, b.xmax);
     }
   }
-  ymin[t] = a; ymax[t] = b; xmin[t] = c; xmax[t] = d;
+  out[t] = r;
 }
 
-void launch_pyramid_level(const PyrLevel& child, double* ymin, double* ymax, double* xmin, double* xmax,
-                          int nx, int ny, cudaStream_t st)
+void launch_pyramid_level(const PyrLevel& child, Box* out, int nx, int ny, cudaStream_t st)
 {
   const long long n = (long long)nx * ny;
   const int threads = 256;
   ++g_launches;
-  pyramid_level_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(child, ymin, ymax, xmin, xmax, nx, ny);
+  pyramid_level_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(child, out, nx, ny);
 }
 
 // =============================================================================================
 // candidate search
 // =============================================================================================
 constexpr int kStack = 3 * kMaxLevels + 8;
+constexpr uint32_t kHeavyPairs = 128;     // a source cell with more candidates than this ...
+constexpr int kHeavySteps = 768;          // ... or more node expansions is handed to the level-synchronous path
 
 struct SrcBox { double ymin, ymax, xmin, xmax, xavg; };
 
 // conservative node test: the node may contain a cell that passes the exact tests under one of
 // the three 2*pi shifts the reference can apply (create_xgrid.c:786-801).  Rounding of
 // (bound + 2pi) is monotone, so this never rejects a node holding a true candidate.
-__device__ __forceinline__ bool node_hit(const PyrLevel& L, long long q, const SrcBox& s)
+__device__ __forceinline__ bool node_hit(const Box& b, const SrcBox& s)
 {
-  if (L.ymin[q] >= s.ymax || L.ymax[q] <= s.ymin) return false;
-  const double lo = L.xmin[q], hi = L.xmax[q];
+  if (b.ymin >= s.ymax || b.ymax <= s.ymin) return false;
+  const double lo = b.xmin, hi = b.xmax;
   if (!(lo >= s.xmax || hi <= s.xmin)) return true;
   if (!(lo + kTwoPi >= s.xmax || hi + kTwoPi <= s.xmin)) return true;
   if (!(lo - kTwoPi >= s.xmax || hi - kTwoPi <= s.xmin)) return true;
@@ -135,8 +141,9 @@ __device__ __forceinline__ bool node_hit(const PyrLevel& L, long long q, const S
 // exact reference predicates for one (source cell, destination cell) pair, create_xgrid.c:777-801
 __device__ __forceinline__ bool leaf_hit(const CellSet& dst, long long d, const SrcBox& s)
 {
-  if (dst.ymin[d] >= s.ymax || dst.ymax[d] <= s.ymin) return false;
-  double lo = dst.xmin[d], hi = dst.xmax[d];
+  const Box b = load_box(dst.box + d);
+  if (b.ymin >= s.ymax || b.ymax <= s.ymin) return false;
+  double lo = b.xmin, hi = b.xmax;
   const double dx = dst.xavg[d] - s.xavg;
   if (dx < -kPi)     { lo += kTwoPi; hi += kTwoPi; }
   else if (dx > kPi) { lo -= kTwoPi; hi -= kTwoPi; }
@@ -144,25 +151,49 @@ __device__ __forceinline__ bool leaf_hit(const CellSet& dst, long long d, const 
   return true;
 }
 
+__device__ __forceinline__ SrcBox load_src_box(const CellSet& src, long long s)
+{
+  const Box b = load_box(src.box + s);
+  return SrcBox{b.ymin, b.ymax, b.xmin, b.xmax, src.xavg[s]};
+}
+
+// one slot in a global append buffer, one atomic per warp
+__device__ __forceinline__ unsigned warp_append(unsigned* counter, bool pred)
+{
+  const unsigned active = __activemask();
+  const unsigned votes = __ballot_sync(active, pred);
+  if (!pred) return 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(votes) - 1;
+  unsigned base = 0;
+  if (lane == leader) base = atomicAdd(counter, (unsigned)__popc(votes));
+  base = __shfl_sync(votes, base, leader);
+  return base + (unsigned)__popc(votes & ((1u << lane) - 1u));
+}
+
+// Per source cell depth-first walk of the pyramid with a private stack.  COUNT pass (FILL == false):
+// writes cnt[t]; cells that turn out to be heavy (pole caps, coarse-on-fine) stop early, are flagged and
+// queued for the level-synchronous kernels below, which keep every thread busy instead of leaving one
+// thread to enumerate thousands of nodes.  FILL pass: writes the pairs of the non-heavy cells.
 template <bool FILL>
 __global__ void __launch_bounds__(128)
 candidate_kernel(CellSet src, long long s0, long long ns, const double* __restrict__ mask,
                  Pyramid pyr, CellSet dst, const uint32_t* __restrict__ pair_off,
-                 uint32_t* __restrict__ cnt, int2* __restrict__ pairs, int* err)
+                 uint32_t* __restrict__ cnt, int2* __restrict__ pairs,
+                 unsigned char* __restrict__ heavy_flag, int* __restrict__ heavy_list, HeavyCtl* ctl, int* err)
 {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= ns) return;
+  if (FILL && heavy_flag[t]) return;
   const long long s = s0 + t;
   uint32_t n = 0;
   const uint32_t base = FILL ? pair_off[t] : 0u;
+  bool heavy = false;
 
   if (mask == nullptr || mask[s] > kMaskThresh) {
-    SrcBox sb;
-    sb.ymin = src.ymin[s]; sb.ymax = src.ymax[s];
-    sb.xmin = src.xmin[s]; sb.xmax = src.xmax[s]; sb.xavg = src.xavg[s];
-
+    const SrcBox sb = load_src_box(src, s);
     unsigned long long stack[kStack];
-    int sp = 0;
+    int sp = 0, steps = 0;
     const int top = pyr.nlev - 1;
     {
       const PyrLevel& L = pyr.lev[top];
@@ -171,12 +202,13 @@ candidate_kernel(CellSet src, long long s0, long long ns, const double* __restri
           const long long q = (long long)iy * L.nx + ix;
           if (top == 0) {
             if (leaf_hit(dst, q, sb)) { if (FILL) pairs[base + n] = make_int2((int)t, (int)q); ++n; }
-          } else if (node_hit(L, q, sb)) {
+          } else if (node_hit(load_box(L.box + q), sb)) {
             stack[sp++] = ((unsigned long long)top << 58) | ((unsigned long long)iy << 29) | (unsigned long long)ix;
           }
         }
     }
     while (sp > 0) {
+      if (!FILL && top > 0 && (n > kHeavyPairs || ++steps > kHeavySteps)) { heavy = true; break; }
       const unsigned long long e = stack[--sp];
       const int lev = (int)(e >> 58) - 1;                      // child level
       const int py = (int)((e >> 29) & 0x1fffffffull), px = (int)(e & 0x1fffffffull);
@@ -192,7 +224,7 @@ candidate_kernel(CellSet src, long long s0, long long ns, const double* __restri
           const long long q = (long long)cy * L.nx + cx;
           if (lev == 0) {
             if (leaf_hit(dst, q, sb)) { if (FILL) pairs[base + n] = make_int2((int)t, (int)q); ++n; }
-          } else if (node_hit(L, q, sb)) {
+          } else if (node_hit(load_box(L.box + q), sb)) {
             if (sp < kStack) stack[sp++] = ((unsigned long long)lev << 58) | ((unsigned long long)cy << 29) | (unsigned long long)cx;
             else atomicOr(err, kErrStackOverflow);
           }
@@ -200,19 +232,129 @@ candidate_kernel(CellSet src, long long s0, long long ns, const double* __restri
       }
     }
   }
-  if (!FILL) cnt[t] = n;
+  if (!FILL) {
+    if (heavy) {
+      const unsigned slot = atomicAdd(&ctl->nheavy, 1u);
+      heavy_list[slot] = (int)t;                               // capacity ns: cannot overflow
+      n = 0;                                                   // the heavy kernels add this cell's count
+    }
+    heavy_flag[t] = heavy ? 1 : 0;
+    cnt[t] = n;
+  }
+}
+
+// ---- level-synchronous path for heavy source cells -----------------------------------------------
+// Work items are (heavy cell h, pyramid node q) pairs; one launch per pyramid level expands every item into
+// its (up to) four children, so the work of a pole cap is spread over the whole grid of threads.
+// Item counts live on the device (HeavyCtl), launches use a fixed grid with grid-stride loops: no host sync.
+constexpr int kHeavyBlocks = 148 * 2, kHeavyThreads = 128;
+
+__global__ void __launch_bounds__(kHeavyThreads)
+heavy_seed_kernel(CellSet src, long long s0, Pyramid pyr, const int* __restrict__ heavy_list, HeavyCtl* ctl,
+                  int2* __restrict__ items, unsigned cap, int* err)
+{
+  const int top = pyr.nlev - 1;
+  const PyrLevel& L = pyr.lev[top];
+  const unsigned ntop = (unsigned)(L.nx * L.ny);
+  const unsigned long long total = (unsigned long long)ctl->nheavy * ntop;
+  for (unsigned long long w = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; w < total;
+       w += (unsigned long long)gridDim.x * blockDim.x) {
+    const int h = (int)(w / ntop), q = (int)(w % ntop);
+    const SrcBox sb = load_src_box(src, s0 + heavy_list[h]);
+    const bool hit = node_hit(load_box(L.box + q), sb);
+    const unsigned slot = warp_append(&ctl->nitems[top], hit);
+    if (hit) { if (slot < cap) items[slot] = make_int2(h, q); else atomicOr(err, kErrHeavyOverflow); }
+  }
+}
+
+// expands the items of level `lev` (lev >= 1) into level lev-1
+__global__ void __launch_bounds__(kHeavyThreads)
+heavy_expand_kernel(CellSet src, long long s0, Pyramid pyr, CellSet dst, int lev, const int* __restrict__ heavy_list,
+                    HeavyCtl* ctl, const int2* __restrict__ in, int2* __restrict__ out, int2* __restrict__ hpairs,
+                    uint32_t* __restrict__ cnt, unsigned cap, int* err)
+{
+  const unsigned nin = min(ctl->nitems[lev], cap);
+  const PyrLevel& P = pyr.lev[lev];
+  const PyrLevel& L = pyr.lev[lev - 1];
+  const unsigned long long total = 4ull * nin;
+  // iterate in whole warps so that warp_append sees converged lanes
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  const unsigned long long rounds = (total + stride - 1) / stride;
+  for (unsigned long long r = 0; r < rounds; ++r) {
+    const unsigned long long w = r * stride + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    bool hit = false;
+    int h = 0, t = 0;
+    long long q = 0;
+    if (w < total) {
+      const int2 it = in[w >> 2];
+      h = it.x;
+      const int py = it.y / P.nx, px = it.y % P.nx;
+      const int cx = 2 * px + (int)(w & 1), cy = 2 * py + (int)((w >> 1) & 1);
+      if (cx < L.nx && cy < L.ny) {
+        t = heavy_list[h];
+        const SrcBox sb = load_src_box(src, s0 + t);
+        q = (long long)cy * L.nx + cx;
+        hit = (lev == 1) ? leaf_hit(dst, q, sb) : node_hit(load_box(L.box + q), sb);
+      }
+    }
+    if (lev == 1) {
+      const unsigned slot = warp_append(&ctl->npairs, hit);
+      if (hit) {
+        if (slot < cap) { hpairs[slot] = make_int2(t, (int)q); atomicAdd(&cnt[t], 1u); }
+        else atomicOr(err, kErrHeavyOverflow);
+      }
+    } else {
+      const unsigned slot = warp_append(&ctl->nitems[lev - 1], hit);
+      if (hit) { if (slot < cap) out[slot] = make_int2(h, (int)q); else atomicOr(err, kErrHeavyOverflow); }
+    }
+  }
+}
+
+// after the scan: drop the heavy cells' pairs into their segments (order inside a segment is irrelevant,
+// scatter ranks by destination index); cnt[t] counts down to zero
+__global__ void __launch_bounds__(kHeavyThreads)
+heavy_fill_kernel(HeavyCtl* ctl, const int2* __restrict__ hpairs, const uint32_t* __restrict__ pair_off,
+                  uint32_t* __restrict__ cnt, int2* __restrict__ pairs, unsigned cap)
+{
+  const unsigned n = min(ctl->npairs, cap);
+  for (unsigned w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
+    const int2 pr = hpairs[w];
+    const uint32_t k = atomicSub(&cnt[pr.x], 1u) - 1u;
+    pairs[pair_off[pr.x] + k] = pr;
+  }
 }
 
 void launch_candidates(bool fill, const CellSet& src, long long s0, long long ns, const double* mask,
                        const Pyramid& pyr, const CellSet& dst, const uint32_t* pair_off,
-                       uint32_t* cnt, int2* pairs, int* err, cudaStream_t st)
+                       uint32_t* cnt, int2* pairs, const HeavyWork& hw, int* err, cudaStream_t st)
 {
   if (ns <= 0) return;
   const int threads = 128;
   const unsigned blocks = (unsigned)((ns + threads - 1) / threads);
-  ++g_launches;
-  if (fill) candidate_kernel<true><<<blocks, threads, 0, st>>>(src, s0, ns, mask, pyr, dst, pair_off, cnt, pairs, err);
-  else      candidate_kernel<false><<<blocks, threads, 0, st>>>(src, s0, ns, mask, pyr, dst, pair_off, cnt, pairs, err);
+  if (!fill) {
+    cudaMemsetAsync(hw.ctl, 0, sizeof(HeavyCtl), st);
+    ++g_launches;
+    candidate_kernel<false><<<blocks, threads, 0, st>>>(src, s0, ns, mask, pyr, dst, pair_off, cnt, pairs,
+                                                        hw.flag, hw.list, hw.ctl, err);
+    if (pyr.nlev > 1) {
+      const int top = pyr.nlev - 1;
+      ++g_launches;
+      heavy_seed_kernel<<<kHeavyBlocks, kHeavyThreads, 0, st>>>(src, s0, pyr, hw.list, hw.ctl, hw.items[top & 1], hw.cap, err);
+      for (int lev = top; lev >= 1; --lev) {
+        ++g_launches;
+        heavy_expand_kernel<<<kHeavyBlocks, kHeavyThreads, 0, st>>>(src, s0, pyr, dst, lev, hw.list, hw.ctl, hw.items[lev & 1],
+                                                                    hw.items[(lev - 1) & 1], hw.pairs, cnt, hw.cap, err);
+      }
+    }
+  } else {
+    ++g_launches;
+    candidate_kernel<true><<<blocks, threads, 0, st>>>(src, s0, ns, mask, pyr, dst, pair_off, cnt, pairs,
+                                                       hw.flag, hw.list, hw.ctl, err);
+    if (pyr.nlev > 1) {
+      ++g_launches;
+      heavy_fill_kernel<<<kHeavyBlocks, kHeavyThreads, 0, st>>>(hw.ctl, hw.pairs, pair_off, cnt, pairs, hw.cap);
+    }
+  }
 }
 
 // =============================================================================================
@@ -280,6 +422,69 @@ __device__ __forceinline__ int clip_cell(double* ax, double* ay, double* bx, dou
   return np;
 }
 
+// Same algorithm, restructured for SIMT execution (shared-memory polygons of at most kFastCap vertices):
+// per clip edge (1) inside-flags of all vertices as a bit mask, (2) the two edge crossings computed by all
+// lanes together instead of inside the divergent vertex loop, (3) assembly of the output list in the
+// reference's order (crossing before vertex k, then vertex k if inside).  An edge that keeps every vertex
+// leaves the polygon untouched, so it is skipped without copying.  Every emitted number is produced by the
+// same operations as in clip_cell, so results are bit-identical.  Returns -1 (caller falls back to the
+// generic routine) when a stage has more than two crossings (non-convex input) or would exceed kFastCap.
+__device__ __forceinline__ int clip_cell_fast(double* ax, double* ay, double* bx, double* by, int n1,
+                                              const CellSet& dst, long long d, int n2, int shift, bool wrap,
+                                              double** rx, double** ry, int* err)
+{
+  constexpr int stride = kClipThreads;
+  double *cx = ax, *cy = ay, *ox = bx, *oy = by;
+  int np = n1;
+  double ex0 = dst_vertex_lon(dst, d, n2 - 1, shift, wrap);
+  double ey0 = dst.vy[(long long)(n2 - 1) * dst.ncell + d];
+  for (int e = 0; e < n2; ++e) {
+    const double ex1 = dst_vertex_lon(dst, d, e, shift, wrap);
+    const double ey1 = dst.vy[(long long)e * dst.ncell + d];
+    const double edy = ey1 - ey0, endx = ex0 - ex1;
+    unsigned in = 0;
+    for (int k = 0; k < np; ++k) {
+      const double qx = cx[k * stride], qy = cy[k * stride];
+      in |= (unsigned)(((qx - ex0) * edy + endx * (qy - ey0)) <= 1.e-12) << k;
+    }
+    const unsigned full = (1u << np) - 1u;
+    if (in == 0u) { *rx = ox; *ry = oy; return 0; }
+    if (in != full) {
+      const unsigned prev = ((in << 1) | (in >> (np - 1))) & full;      // inside flag of vertex k-1 (cyclic)
+      const unsigned cross = in ^ prev;
+      if (__popc(cross) != 2 || np + 1 > kFastCap) return -1;
+      const int k0 = __ffs(cross) - 1, k1 = 31 - __clz(cross);
+      double X[2], Y[2];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int k = c ? k1 : k0;
+        const int km = (k == 0) ? np - 1 : k - 1;
+        const double px = cx[km * stride], py = cy[km * stride];
+        const double qx = cx[k * stride], qy = cy[k * stride];
+        const double dy1 = qy - py, dy2 = ey1 - ey0, dx1 = qx - px, dx2 = ex1 - ex0;
+        const double ds1 = py * qx - qy * px, ds2 = ey0 * ex1 - ey1 * ex0;
+        const double determ = dy2 * dx1 - dy1 * dx2;
+        if (fabs(determ) < 1.0e-30) atomicOr(err, kErrParallelEdges);
+        X[c] = (dx2 * ds1 - dx1 * ds2) / determ;
+        Y[c] = (dy2 * ds1 - dy1 * ds2) / determ;
+      }
+      int no = 0;
+      for (int k = 0; k < np; ++k) {
+        if (k == k0)      { ox[no * stride] = X[0]; oy[no * stride] = Y[0]; ++no; }
+        else if (k == k1) { ox[no * stride] = X[1]; oy[no * stride] = Y[1]; ++no; }
+        if ((in >> k) & 1u) { ox[no * stride] = cx[k * stride]; oy[no * stride] = cy[k * stride]; ++no; }
+      }
+      np = no;
+      double* t;
+      t = cx; cx = ox; ox = t;
+      t = cy; cy = oy; oy = t;
+    }
+    ex0 = ex1; ey0 = ey1;
+  }
+  *rx = cx; *ry = cy;
+  return np;
+}
+
 // load the source polygon into a strided buffer, report whether pimod applies (create_xgrid.c:1279-1290)
 __device__ __forceinline__ bool load_src_poly(const CellSet& src, long long s, int n1, double* ax, double* ay, int stride)
 {
@@ -329,7 +534,7 @@ clip_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const int
   double loc[4 * kSlowCap];                                       // only touched on the slow path
   {
     const bool wrap = load_src_poly(src, s, n1, ax, ay, stride);
-    n_out = clip_cell<kFastCap>(ax, ay, bx, by, stride, n1, dst, d, n2, shift, wrap, &rx, &ry, err);
+    n_out = clip_cell_fast(ax, ay, bx, by, n1, dst, d, n2, shift, wrap, &rx, &ry, err);
   }
   if (n_out < 0) {
     // rare: more than 8 vertices at some stage (pole cells, non-convex cells) -> reference-sized buffers
@@ -340,22 +545,21 @@ clip_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const int
     if (n_out < 0) { atomicOr(err, kErrClipOverflow); n_out = 0; }
   }
 
-  double xarea = 0.0;
+  double xarea = 0.0, xclon = 0.0, xclat = 0.0;
   bool keep = false;
   PolyView pv{rx, ry, rstride};
   if (n_out > 0) {
     const double m = mask ? mask[s] : 1.0;
-    xarea = poly_area(pv, n_out) * m;                            // create_xgrid.c:805
+    double a;
+    poly_moments<ORDER>(pv, n_out, s_xavg, &a, &xclon, &xclat);  // poly_area :805, poly_ctrlon :1091, poly_ctrlat :1092
+    xarea = a * m;
     const double a1 = src.area[s], a2 = dst.area[d];
     const double min_area = (a1 < a2) ? a1 : a2;                 // :806
     keep = (xarea / min_area > kAreaRatioThresh);                // :807
   }
   parea[p] = keep ? xarea : 0.0;
   if (keep) {
-    if (ORDER == 2) {
-      pclon[p] = poly_ctrlon(pv, n_out, s_xavg);                 // :1091
-      pclat[p] = poly_ctrlat(pv, n_out);                         // :1092
-    }
+    if (ORDER == 2) { pclon[p] = xclon; pclat[p] = xclat; }
     atomicAdd(&cnt[pr.x], 1u);
   }
 }

@@ -39,6 +39,7 @@ struct xgb_plan {
 
   // work space
   DevBuf cnt, pair_off, out_off, pairs, parea, pclon, pclat, scan_tmp, bounds_dev;
+  DevBuf heavy_ctl, heavy_flag, heavy_list, heavy_items, heavy_pairs;
 
   // result (Interp_config layout)
   DevBuf t_in, i_in, j_in, i_out, j_out, area, clon, clat, di, dj;
