@@ -78,6 +78,16 @@ def lib():
     L.xgb_plan_result_centroids_host.argtypes = [vp, vp, vp]
     L.xgb_plan_src_area_host.argtypes = [vp, vp]
     L.xgb_plan_dst_area_host.argtypes = [vp, vp]
+    L.xgb_plan_apply_setup.argtypes = [vp]
+    L.xgb_plan_set_xgrid.argtypes = [vp, C.c_int, _ip, _ip, C.c_int, C.c_int, C.c_longlong] + [vp] * 8 + [C.c_int]
+    L.xgb_plan_apply_nxgrid.restype = C.c_longlong
+    L.xgb_plan_apply_nxgrid.argtypes = [vp]
+    L.xgb_plan_grad_setup.argtypes = [vp, vp, vp, C.c_int]
+    L.xgb_plan_grad_set_metrics.argtypes = [vp, C.c_int] + [vp] * 11 + [C.c_int]
+    L.xgb_plan_grad_get_metrics.argtypes = [vp, C.c_int] + [vp] * 11
+    L.xgb_plan_grad_c2l.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_double, C.c_int]
+    L.xgb_plan_apply.argtypes = [vp, C.c_uint, C.c_int, vp, vp, vp, vp, C.c_int, C.c_double, vp, C.c_int]
+    L.xgb_plan_regrid.argtypes = [vp, C.c_uint, C.c_int, vp, C.c_int, C.c_double, vp, C.c_int]
     L.xgb_cubed_sphere_grid.argtypes = [C.c_int, vp, vp, vp, vp]
     L.xgb_latlon_grid.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp]
     L.xgb_plan_phase_ms.argtypes = [vp, vp, vp, vp]
@@ -294,6 +304,110 @@ class XgridPlan:
             ptr = getattr(v, k)
             if ptr:
                 out[k] = torch.as_tensor(_CudaArray(ptr, n, "<f8", self), device=dev) if n else torch.empty(0, dtype=torch.float64, device=dev)
+        return out
+
+    # ---- conservative apply (do_scalar_conserve_interp / grad_c2l), batched over field-levels -------------
+    METRICS = ("dx", "dy", "area", "edge_w", "edge_e", "edge_s", "edge_n", "en_n", "en_e", "vlon", "vlat")
+
+    def apply_setup(self):
+        """regroup the last generate()'s exchange grid by destination cell (one-time)"""
+        self._ck(self._L.xgb_plan_apply_setup(self._p))
+        self._apply_tiles = list(self.tiles)
+        self._apply_dst = (self.nx_dst, self.ny_dst)
+
+    def set_xgrid(self, tiles, nx_out, ny_out, x):
+        """exchange-grid lists from elsewhere (remap file, other GPUs): tiles = [(nx, ny), ...]; x = dict with
+        t_in, i_in, j_in, i_out, j_out (int32), area and optionally di, dj (float64); numpy or CUDA tensors"""
+        nxa = (C.c_int * len(tiles))(*[int(t[0]) for t in tiles])
+        nya = (C.c_int * len(tiles))(*[int(t[1]) for t in tiles])
+        n = int(x["area"].shape[0])
+        dev = 1 if _is_torch(x["area"]) and x["area"].is_cuda else 0
+        keep, ptrs = [], []
+        for k in ("t_in", "i_in", "j_in", "i_out", "j_out", "area", "di", "dj"):
+            v = x.get(k)
+            if v is None:
+                ptrs.append(None)
+                continue
+            if _is_torch(v):
+                v = v.contiguous()
+                ptrs.append(v.data_ptr())
+            else:
+                v = np.ascontiguousarray(v, dtype=np.float64 if k in ("area", "di", "dj") else np.int32)
+                ptrs.append(v.ctypes.data)
+            keep.append(v)
+        self._ck(self._L.xgb_plan_set_xgrid(self._p, len(tiles), nxa, nya, int(nx_out), int(ny_out), n, *ptrs, dev))
+        self._apply_tiles = [(int(a), int(b)) for a, b in tiles]
+        self._apply_dst = (int(nx_out), int(ny_out))
+
+    def _field_sizes(self):
+        ncell = sum(a * b for a, b in self._apply_tiles)
+        nhalo = sum((a + 2) * (b + 2) for a, b in self._apply_tiles)
+        return ncell, nhalo, self._apply_dst[0] * self._apply_dst[1]
+
+    def grad_setup(self, lont, latt):
+        """calc_c2l_grid_info on the device; lont/latt: haloed cell centres, tiles concatenated (flat)"""
+        pl, dl, kl = _f64_ptr(lont); pa, da, ka = _f64_ptr(latt)
+        if not hasattr(self, "_apply_tiles"):
+            self._apply_tiles = list(self.tiles)
+        self._ck(self._L.xgb_plan_grad_setup(self._p, pl, pa, dl))
+
+    def grad_set_metrics(self, tile, m):
+        """the reference's own metrics for one tile: dict keyed like METRICS (host numpy arrays)"""
+        arrs = [np.ascontiguousarray(m[k], np.float64) for k in self.METRICS]
+        self._ck(self._L.xgb_plan_grad_set_metrics(self._p, int(tile), *[a.ctypes.data for a in arrs], 0))
+
+    def grad_get_metrics(self, tile):
+        nx, ny = self._apply_tiles[tile]
+        sizes = {"dx": nx * (ny + 1), "dy": (nx + 1) * ny, "area": nx * ny, "edge_w": ny + 1, "edge_e": ny + 1, "edge_s": nx + 1,
+                 "edge_n": nx + 1, "en_n": 3 * nx * (ny + 1), "en_e": 3 * (nx + 1) * ny, "vlon": 3 * nx * ny, "vlat": 3 * nx * ny}
+        out = {k: np.empty(sizes[k]) for k in self.METRICS}
+        self._ck(self._L.xgb_plan_grad_get_metrics(self._p, int(tile), *[out[k].ctypes.data for k in self.METRICS]))
+        return out
+
+    def _alloc_like(self, ref, n, dtype_np, dtype_t):
+        if _is_torch(ref) and ref.is_cuda:
+            import torch
+            return torch.empty(n, dtype=getattr(torch, dtype_t), device=ref.device)
+        return np.empty(n, dtype_np)
+
+    @staticmethod
+    def _ptr(a):
+        if a is None:
+            return None
+        return a.data_ptr() if _is_torch(a) else a.ctypes.data
+
+    def grad_c2l(self, data, nfields=1, has_missing=False, missing=0.0, with_mask=True):
+        """-> (grad_x, grad_y, grad_mask) for nfields haloed field-levels (flat, back to back)"""
+        ncell, nhalo, ndst = self._field_sizes()
+        pd, dev, kd = _f64_ptr(data)
+        gx = self._alloc_like(kd, nfields * ncell, np.float64, "float64")
+        gy = self._alloc_like(kd, nfields * ncell, np.float64, "float64")
+        gm = self._alloc_like(kd, nfields * ncell, np.int32, "int32") if with_mask else None
+        self._ck(self._L.xgb_plan_grad_c2l(self._p, int(nfields), pd, self._ptr(gx), self._ptr(gy), self._ptr(gm),
+                                           int(bool(has_missing)), float(missing), dev))
+        return gx, gy, gm
+
+    def apply(self, opcode, data, nfields=1, grad_x=None, grad_y=None, grad_mask=None, has_missing=False, missing=0.0, out=None):
+        """do_scalar_conserve_interp for nfields field-levels -> flat [nfields * nx_out * ny_out]"""
+        ncell, nhalo, ndst = self._field_sizes()
+        pd, dev, kd = _f64_ptr(data)
+        px, dx_, kx = _f64_ptr(grad_x); py, dy_, ky = _f64_ptr(grad_y)
+        if grad_mask is not None and not _is_torch(grad_mask):
+            grad_mask = np.ascontiguousarray(grad_mask, np.int32)
+        if out is None:
+            out = self._alloc_like(kd, nfields * ndst, np.float64, "float64")
+        self._ck(self._L.xgb_plan_apply(self._p, int(opcode), int(nfields), pd, px, py, self._ptr(grad_mask),
+                                        int(bool(has_missing)), float(missing), self._ptr(out), dev))
+        return out
+
+    def regrid(self, opcode, data, nfields=1, has_missing=False, missing=0.0, out=None):
+        """gradient (order 2) + apply in one call -> flat [nfields * nx_out * ny_out]"""
+        ncell, nhalo, ndst = self._field_sizes()
+        pd, dev, kd = _f64_ptr(data)
+        if out is None:
+            out = self._alloc_like(kd, nfields * ndst, np.float64, "float64")
+        self._ck(self._L.xgb_plan_regrid(self._p, int(opcode), int(nfields), pd, int(bool(has_missing)), float(missing),
+                                         self._ptr(out), dev))
         return out
 
     def src_area(self):

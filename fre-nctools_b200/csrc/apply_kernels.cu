@@ -1,0 +1,392 @@
+// Conservative apply path for sm_100a: do_scalar_conserve_interp (reference conserve_interp.c:507-910) and the
+// order-2 gradient terms grad_c2l / a2b_ord2 (gradient_c2l.c:58-195), batched over field-levels.
+//
+//   dst_count / dst_fill / dst_sort_gather : one-time regrouping of the exchange-grid list by destination cell
+//        (a CSR over destination cells).  Inside a destination cell the entries keep the order of the original
+//        list, so the per-cell sums below add in exactly the order of the reference's scatter loop
+//        (conserve_interp.c:563-614, :745-811) and the remapped fields are bit-identical to the reference.
+//   apply<ORDER, MISSING>  : one thread per destination cell, kApplyBT field-levels per thread; the weights of
+//        a cell are read once per kApplyBT fields; output written coalesced.  No atomics.
+//   grad_c2l               : one thread per source cell, kGradBT field-levels per thread: corner averages
+//        (a2b_ord2 with its edge/corner rules), edge fluxes, Green's theorem, projection on (lon, lat).
+//   monotone_*             : the conserve_order2_monotonic limiter (conserve_interp.c:617-742).
+//
+// FP64, -fmad=false, reference association order throughout.
+#include "apply_internal.h"
+
+namespace xgb {
+
+extern long long g_launches;
+
+// =============================================================================================
+// destination-major regrouping
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+dst_count_kernel(long long n, const int* __restrict__ i_out, const int* __restrict__ j_out, int nx2, uint32_t* __restrict__ cnt)
+{
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
+    atomicAdd(&cnt[(long long)j_out[k] * nx2 + i_out[k]], 1u);
+}
+
+__global__ void __launch_bounds__(256)
+dst_fill_kernel(long long n, const int* __restrict__ i_out, const int* __restrict__ j_out, int nx2,
+                const uint32_t* __restrict__ off, uint32_t* __restrict__ cursor, uint32_t* __restrict__ perm)
+{
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+    const long long d = (long long)j_out[k] * nx2 + i_out[k];
+    perm[off[d] + atomicAdd(&cursor[d], 1u)] = (uint32_t)k;
+  }
+}
+
+// per destination cell: restore list order inside the segment (the fill above is unordered), then gather the
+// per-entry data next to each other so the apply kernel streams it
+__global__ void __launch_bounds__(128)
+dst_sort_gather_kernel(long long ndst, const uint32_t* __restrict__ off, uint32_t* __restrict__ perm,
+                       const int* __restrict__ t_in, const int* __restrict__ i_in, const int* __restrict__ j_in,
+                       const double* __restrict__ area, const double* __restrict__ di, const double* __restrict__ dj,
+                       const ApplyTile* __restrict__ tiles, int ntiles,
+                       int* __restrict__ c_cell, int* __restrict__ c_hidx, double* __restrict__ c_area,
+                       double* __restrict__ c_di, double* __restrict__ c_dj, int* err)
+{
+  const long long d = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (d >= ndst) return;
+  const uint32_t b = off[d], e = off[d + 1];
+  for (uint32_t q = b + 1; q < e; ++q) {                 // insertion sort: segments are a handful of entries
+    const uint32_t v = perm[q];
+    uint32_t r = q;
+    while (r > b && perm[r - 1] > v) { perm[r] = perm[r - 1]; --r; }
+    perm[r] = v;
+  }
+  for (uint32_t q = b; q < e; ++q) {
+    const uint32_t n = perm[q];
+    const int t = t_in[n], i = i_in[n], j = j_in[n];
+    if (t < 0 || t >= ntiles || i < 0 || j < 0 || i >= tiles[t].nx || j >= tiles[t].ny) { atomicOr(err, kErrApplyIndex); continue; }
+    c_cell[q] = (int)(tiles[t].cell_off + (long long)j * tiles[t].nx + i);
+    c_hidx[q] = (int)(tiles[t].halo_off + (long long)(j + 1) * (tiles[t].nx + 2) + i + 1);
+    c_area[q] = area[n];
+    if (di) { c_di[q] = di[n]; c_dj[q] = dj[n]; }
+  }
+}
+
+void launch_dst_count(long long n, const int* i_out, const int* j_out, int nx2, uint32_t* cnt, cudaStream_t st)
+{
+  if (n <= 0) return;
+  ++g_launches;
+  dst_count_kernel<<<148 * 8, 256, 0, st>>>(n, i_out, j_out, nx2, cnt);
+}
+
+void launch_dst_fill(long long n, const int* i_out, const int* j_out, int nx2, const uint32_t* off, uint32_t* cursor,
+                     uint32_t* perm, cudaStream_t st)
+{
+  if (n <= 0) return;
+  ++g_launches;
+  dst_fill_kernel<<<148 * 8, 256, 0, st>>>(n, i_out, j_out, nx2, off, cursor, perm);
+}
+
+void launch_dst_sort_gather(long long ndst, const uint32_t* off, uint32_t* perm, const int* t_in, const int* i_in, const int* j_in,
+                            const double* area, const double* di, const double* dj, const ApplyTile* tiles, int ntiles,
+                            ApplyCsr csr, int* err, cudaStream_t st)
+{
+  if (ndst <= 0) return;
+  ++g_launches;
+  dst_sort_gather_kernel<<<(unsigned)((ndst + 127) / 128), 128, 0, st>>>(ndst, off, perm, t_in, i_in, j_in, area, di, dj, tiles, ntiles,
+                                                                         csr.cell, csr.hidx, csr.area, csr.di, csr.dj, err);
+}
+
+// =============================================================================================
+// apply
+// =============================================================================================
+// out[f][d] = sum_q (data + grad_x*di + grad_y*dj)*area / sum_q area        (conserve_interp.c:745-839)
+// Field f of the batch starts at data + f*data_stride (all source tiles concatenated; order 2: each tile with its
+// one-cell halo, (nx+2)*(ny+2)); gradients and grad_mask at + f*ncell_src; output at out + f*ndst.
+// XDATA: the per-entry values come from xdata[f][n] (monotone limiter output) instead of data/grad.
+template <int ORDER, bool MISSING, bool XDATA>
+__global__ void __launch_bounds__(128)
+apply_kernel(ApplyCsr csr, long long ndst, int nf, const double* __restrict__ data, long long data_stride,
+             const double* __restrict__ gx, const double* __restrict__ gy, const int* __restrict__ gmask, long long ncell_src,
+             const double* __restrict__ xdata, long long nxgrid, double missing, double* __restrict__ out)
+{
+  const long long d = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (d >= ndst) return;
+  const int f0 = blockIdx.y * kApplyBT;
+  const uint32_t b = csr.off[d], e = csr.off[d + 1];
+  double acc[kApplyBT], asum[kApplyBT];
+  bool seen[kApplyBT];
+#pragma unroll
+  for (int k = 0; k < kApplyBT; ++k) { acc[k] = 0.0; asum[k] = 0.0; seen[k] = false; }
+  double asum_all = 0.0;
+
+  for (uint32_t q = b; q < e; ++q) {
+    const double area = csr.area[q];
+    const int cell = csr.cell[q];
+    const int src = (ORDER == 2) ? csr.hidx[q] : cell;
+    double di = 0.0, dj = 0.0;
+    if (ORDER == 2 && !XDATA) { di = csr.di[q]; dj = csr.dj[q]; }
+    const uint32_t n = XDATA ? csr.perm[q] : 0u;
+    if (!MISSING) asum_all += area;
+#pragma unroll
+    for (int k = 0; k < kApplyBT; ++k) {
+      const int f = f0 + k;
+      if (f >= nf) break;
+      if (XDATA) {
+        const double v = xdata[(long long)f * nxgrid + n];
+        if (v == missing) continue;                                         // :729
+        acc[k] += v * area;                                                 // :738
+        asum[k] += area;
+        continue;
+      }
+      const double v = data[(long long)f * data_stride + src];
+      if (MISSING && v == missing) continue;                                // :575, :766
+      if (ORDER == 2) {
+        const long long g = (long long)f * ncell_src + cell;
+        if (MISSING && gmask[g]) acc[k] += v * area;                        // :779
+        else acc[k] += (v + gx[g] * di + gy[g] * dj) * area;                // :782, :806
+      } else {
+        acc[k] += v * area;                                                 // :586, :608
+      }
+      if (MISSING) { asum[k] += area; seen[k] = true; }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kApplyBT; ++k) {
+    const int f = f0 + k;
+    if (f >= nf) break;
+    const double a = (MISSING || XDATA) ? asum[k] : asum_all;
+    double r;
+    if (a > 0) r = acc[k] / a;                                              // :833-834
+    else if (MISSING && seen[k]) r = 0.0;                                   // :835-836
+    else r = missing;                                                       // :837-838
+    out[(long long)f * ndst + d] = r;
+  }
+}
+
+void launch_apply(int order, bool has_missing, bool from_xdata, const ApplyCsr& csr, long long ndst, int nf,
+                  const double* data, long long data_stride, const double* gx, const double* gy, const int* gmask,
+                  long long ncell_src, const double* xdata, long long nxgrid, double missing, double* out, cudaStream_t st)
+{
+  if (ndst <= 0 || nf <= 0) return;
+  dim3 grid((unsigned)((ndst + 127) / 128), (unsigned)((nf + kApplyBT - 1) / kApplyBT));
+  ++g_launches;
+#define XGB_APPLY(O, M, X) apply_kernel<O, M, X><<<grid, 128, 0, st>>>(csr, ndst, nf, data, data_stride, gx, gy, gmask, ncell_src, xdata, nxgrid, missing, out)
+  if (from_xdata) XGB_APPLY(2, true, true);
+  else if (order == 2) { if (has_missing) XGB_APPLY(2, true, false); else XGB_APPLY(2, false, false); }
+  else { if (has_missing) XGB_APPLY(1, true, false); else XGB_APPLY(1, false, false); }
+#undef XGB_APPLY
+}
+
+// =============================================================================================
+// grad_c2l
+// =============================================================================================
+// a2b_ord2 (gradient_c2l.c:124-195) at corner (ci, cj) of a tile, all four on_*_edge flags set as fregrid
+// passes them (fregrid_util.c:2197-2200).  q: the field with its one-cell halo, row length nx+2.
+__device__ __forceinline__ double corner_value(const double* __restrict__ q, int nx, int ny, int ci, int cj, const GradTile& g)
+{
+  const int w = nx + 2, nxp = nx + 1, nyp = ny + 1;
+  const double r3 = 1. / 3.;
+  const bool W = (ci == 0), E = (ci == nx), S = (cj == 0), N = (cj == ny);
+  if (W && S) return r3 * (q[1 * w + 1] + q[1 * w] + q[1]);                              // :169
+  if (E && S) return r3 * (q[1 * w + nx] + q[nx] + q[1 * w + nxp]);                       // :170
+  if (E && N) return r3 * (q[ny * w + nx] + q[ny * w + nxp] + q[nyp * w + nx]);           // :171
+  if (W && N) return r3 * (q[ny * w + 1] + q[ny * w] + q[nyp * w + 1]);                   // :172
+  if (W) {                                                                                // :175-178
+    const double a = 0.5 * (q[cj * w] + q[cj * w + 1]), b = 0.5 * (q[(cj + 1) * w] + q[(cj + 1) * w + 1]);
+    return g.edge_w[cj] * a + (1 - g.edge_w[cj]) * b;
+  }
+  if (E) {                                                                                // :181-184
+    const double a = 0.5 * (q[cj * w + nx] + q[cj * w + nxp]), b = 0.5 * (q[(cj + 1) * w + nx] + q[(cj + 1) * w + nxp]);
+    return g.edge_e[cj] * a + (1 - g.edge_e[cj]) * b;
+  }
+  if (S) {                                                                                // :187-190
+    const double a = 0.5 * (q[ci] + q[w + ci]), b = 0.5 * (q[ci + 1] + q[w + ci + 1]);
+    return g.edge_s[ci] * a + (1 - g.edge_s[ci]) * b;
+  }
+  if (N) {                                                                                // :193-196
+    const double a = 0.5 * (q[ny * w + ci] + q[nyp * w + ci]), b = 0.5 * (q[ny * w + ci + 1] + q[nyp * w + ci + 1]);
+    return g.edge_n[ci] * a + (1 - g.edge_n[ci]) * b;
+  }
+  return 0.25 * (q[cj * w + ci] + q[cj * w + ci + 1] + q[(cj + 1) * w + ci] + q[(cj + 1) * w + ci + 1]);   // :163-166
+}
+
+// one thread per source cell (concatenated index), kGradBT field-levels per thread
+template <bool MISSING>
+__global__ void __launch_bounds__(128)
+grad_c2l_kernel(const GradTile* __restrict__ tiles, int ntiles, long long ncell, int nf,
+                const double* __restrict__ data, long long data_stride,
+                double* __restrict__ gx, double* __restrict__ gy, int* __restrict__ gmask, double missing)
+{
+  const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  int t = 0;
+  while (t + 1 < ntiles && c >= tiles[t + 1].cell_off) ++t;
+  const GradTile g = tiles[t];
+  const int nx = g.nx, ny = g.ny, nxp = nx + 1;
+  const long long lc = c - g.cell_off;
+  const int i = (int)(lc % nx), j = (int)(lc / nx);
+  // metrics of this cell (gradient_c2l.c:58-118), read once for all fields of the batch
+  const double dx_s = g.dx[(long long)j * nx + i], dx_n = g.dx[(long long)(j + 1) * nx + i];
+  const double dy_w = g.dy[(long long)j * nxp + i], dy_e = g.dy[(long long)j * nxp + i + 1];
+  double en_s[3], en_nn[3], ee_w[3], ee_e[3], vlon[3], vlat[3];
+#pragma unroll
+  for (int n = 0; n < 3; ++n) {
+    en_s[n] = g.en_n[3 * ((long long)j * nx + i) + n];
+    en_nn[n] = g.en_n[3 * ((long long)(j + 1) * nx + i) + n];
+    ee_w[n] = g.en_e[3 * ((long long)j * nxp + i) + n];
+    ee_e[n] = g.en_e[3 * ((long long)j * nxp + i + 1) + n];
+    vlon[n] = g.vlon[3 * lc + n];
+    vlat[n] = g.vlat[3 * lc + n];
+  }
+  const double area = g.area[lc];
+  const int f0 = blockIdx.y * kGradBT;
+  for (int k = 0; k < kGradBT; ++k) {
+    const int f = f0 + k;
+    if (f >= nf) break;
+    const double* q = data + (long long)f * data_stride + g.halo_off;
+    const double p00 = corner_value(q, nx, ny, i, j, g), p10 = corner_value(q, nx, ny, i + 1, j, g);
+    const double p01 = corner_value(q, nx, ny, i, j + 1, g), p11 = corner_value(q, nx, ny, i + 1, j + 1, g);
+    double g3[3];
+#pragma unroll
+    for (int n = 0; n < 3; ++n) {
+      const double pdx_s = 0.5 * (p00 + p10) * dx_s * en_s[n];                // :86-92
+      const double pdx_n = 0.5 * (p01 + p11) * dx_n * en_nn[n];
+      const double pdy_w = 0.5 * (p00 + p01) * dy_w * ee_w[n];                // :94-99
+      const double pdy_e = 0.5 * (p10 + p11) * dy_e * ee_e[n];
+      g3[n] = pdx_n - pdx_s - pdy_w + pdy_e;                                  // :102-107
+    }
+    double vx = (vlon[0] * g3[0] + vlon[1] * g3[1] + vlon[2] * g3[2]) / area; // :110-117
+    vx *= kRadius;
+    double vy = (vlat[0] * g3[0] + vlat[1] * g3[1] + vlat[2] * g3[2]) / area;
+    vy *= kRadius;
+    const long long o = (long long)f * ncell + c;
+    gx[o] = vx; gy[o] = vy;
+    if (gmask) {
+      int m = 0;
+      if (MISSING) {                                                          // fregrid_util.c:2203-2216
+        const int w = nx + 2, ii = i + 1, jj = j + 1;
+        m = (q[(jj - 1) * w + ii - 1] == missing || q[(jj - 1) * w + ii] == missing || q[(jj - 1) * w + ii + 1] == missing ||
+             q[jj * w + ii - 1] == missing || q[jj * w + ii + 1] == missing || q[(jj + 1) * w + ii - 1] == missing ||
+             q[(jj + 1) * w + ii] == missing || q[(jj + 1) * w + ii + 1] == missing) ? 1 : 0;
+      }
+      gmask[o] = m;
+    }
+  }
+}
+
+void launch_grad_c2l(const GradTile* tiles, int ntiles, long long ncell, int nf, const double* data, long long data_stride,
+                     double* gx, double* gy, int* gmask, bool has_missing, double missing, cudaStream_t st)
+{
+  if (ncell <= 0 || nf <= 0) return;
+  dim3 grid((unsigned)((ncell + 127) / 128), (unsigned)((nf + kGradBT - 1) / kGradBT));
+  ++g_launches;
+  if (has_missing) grad_c2l_kernel<true><<<grid, 128, 0, st>>>(tiles, ntiles, ncell, nf, data, data_stride, gx, gy, gmask, missing);
+  else             grad_c2l_kernel<false><<<grid, 128, 0, st>>>(tiles, ntiles, ncell, nf, data, data_stride, gx, gy, gmask, missing);
+}
+
+// =============================================================================================
+// monotone limiter (conserve_interp.c:617-742): one field-level per launch set
+// =============================================================================================
+// order-preserving map double <-> uint64 so atomicMax/atomicMin on integers implement max/min of doubles
+__device__ __forceinline__ unsigned long long dkey(double v)
+{
+  const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dkey_inv(unsigned long long k)
+{
+  const unsigned long long u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)u);
+}
+
+// f_bar_max / f_bar_min over the 3x3 neighbourhood (:630-640); f_max / f_min keys initialised (:626-629)
+__global__ void __launch_bounds__(128)
+monotone_bounds_kernel(const ApplyTile* __restrict__ tiles, int ntiles, long long ncell, const double* __restrict__ data,
+                       double missing, double* __restrict__ fbmax, double* __restrict__ fbmin,
+                       unsigned long long* __restrict__ fmax_key, unsigned long long* __restrict__ fmin_key)
+{
+  const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  int t = 0;
+  while (t + 1 < ntiles && c >= tiles[t + 1].cell_off) ++t;
+  const int nx = tiles[t].nx, w = nx + 2;
+  const long long lc = c - tiles[t].cell_off;
+  const int i = (int)(lc % nx), j = (int)(lc / nx);
+  const double* q = data + tiles[t].halo_off;
+  double mx = -1.e20, mn = 1.e20;
+  for (int jj = j - 1; jj <= j + 1; ++jj)
+    for (int ii = i - 1; ii <= i + 1; ++ii) {
+      const double v = q[(long long)(jj + 1) * w + ii + 1];
+      if (v != missing) { if (v > mx) mx = v; if (v < mn) mn = v; }
+    }
+  fbmax[c] = mx; fbmin[c] = mn;
+  fmax_key[c] = dkey(-1.e20); fmin_key[c] = dkey(1.e20);
+}
+
+// xdata[n] = f + grad_x*di + grad_y*dj (or f where grad_mask), f_max / f_min per source cell (:647-669)
+__global__ void __launch_bounds__(256)
+monotone_xdata_kernel(long long nxgrid, const int* __restrict__ t_in, const int* __restrict__ i_in, const int* __restrict__ j_in,
+                      const double* __restrict__ di, const double* __restrict__ dj, const ApplyTile* __restrict__ tiles,
+                      const double* __restrict__ data, const double* __restrict__ gx, const double* __restrict__ gy,
+                      const int* __restrict__ gmask, double missing, double* __restrict__ xdata,
+                      unsigned long long* __restrict__ fmax_key, unsigned long long* __restrict__ fmin_key)
+{
+  const long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (n >= nxgrid) return;
+  const int t = t_in[n], nx = tiles[t].nx;
+  const long long c = tiles[t].cell_off + (long long)j_in[n] * nx + i_in[n];
+  const double f = data[tiles[t].halo_off + (long long)(j_in[n] + 1) * (nx + 2) + i_in[n] + 1];
+  double v = missing;
+  if (f != missing) {
+    v = gmask[c] ? f : f + gx[c] * di[n] + gy[c] * dj[n];
+    atomicMax(&fmax_key[c], dkey(v));
+    atomicMin(&fmin_key[c], dkey(v));
+  }
+  xdata[n] = v;
+}
+
+// rescale towards the cell mean so no exchange-cell value leaves the neighbourhood bounds (:680-714)
+__global__ void __launch_bounds__(256)
+monotone_adjust_kernel(long long nxgrid, const int* __restrict__ t_in, const int* __restrict__ i_in, const int* __restrict__ j_in,
+                       const ApplyTile* __restrict__ tiles, const double* __restrict__ data, double missing,
+                       const double* __restrict__ fbmax, const double* __restrict__ fbmin,
+                       const unsigned long long* __restrict__ fmax_key, const unsigned long long* __restrict__ fmin_key,
+                       double* __restrict__ xdata, int* err)
+{
+  const long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (n >= nxgrid) return;
+  double v = xdata[n];
+  if (v == missing) return;
+  const int t = t_in[n], nx = tiles[t].nx;
+  const long long c = tiles[t].cell_off + (long long)j_in[n] * nx + i_in[n];
+  const double f_bar = data[tiles[t].halo_off + (long long)(j_in[n] + 1) * (nx + 2) + i_in[n] + 1];
+  const double f_max = dkey_inv(fmax_key[c]), f_min = dkey_inv(fmin_key[c]);
+  const double bmax = fbmax[c], bmin = fbmin[c];
+  if (f_max > bmax) {
+    v = f_bar + ((v - f_bar) / (f_max - f_bar)) * (bmax - f_bar);
+    if (v > bmax) {
+      if (v - bmax < 1.e-10) v = bmax;                                       // TOLERANCE, conserve_interp.c:37
+      if (v > bmax) atomicOr(err, kErrMonotoneMax);
+    }
+  } else if (f_min < bmin) {
+    v = f_bar + ((v - f_bar) / (f_min - f_bar)) * (bmin - f_bar);
+    if (v < bmin) {
+      if (bmin - v < 1.e-10) v = bmin;
+      if (v < bmin) atomicOr(err, kErrMonotoneMin);
+    }
+  }
+  xdata[n] = v;
+}
+
+void launch_monotone(long long nxgrid, const int* t_in, const int* i_in, const int* j_in, const double* di, const double* dj,
+                     const ApplyTile* tiles, int ntiles, long long ncell, const double* data, const double* gx, const double* gy,
+                     const int* gmask, double missing, double* fbmax, double* fbmin, unsigned long long* fmax_key,
+                     unsigned long long* fmin_key, double* xdata, int* err, cudaStream_t st)
+{
+  if (ncell <= 0) return;
+  g_launches += 3;
+  monotone_bounds_kernel<<<(unsigned)((ncell + 127) / 128), 128, 0, st>>>(tiles, ntiles, ncell, data, missing, fbmax, fbmin, fmax_key, fmin_key);
+  if (nxgrid <= 0) return;
+  const unsigned blocks = (unsigned)((nxgrid + 255) / 256);
+  monotone_xdata_kernel<<<blocks, 256, 0, st>>>(nxgrid, t_in, i_in, j_in, di, dj, tiles, data, gx, gy, gmask, missing, xdata, fmax_key, fmin_key);
+  monotone_adjust_kernel<<<blocks, 256, 0, st>>>(nxgrid, t_in, i_in, j_in, tiles, data, missing, fbmax, fbmin, fmax_key, fmin_key, xdata, err);
+}
+
+}  // namespace xgb

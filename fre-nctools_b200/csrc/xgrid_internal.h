@@ -85,13 +85,4 @@ size_t scan_tmp_bytes(long long n);
 void launch_exclusive_scan(const uint32_t* in, uint32_t* out, long long n, unsigned long long* total_dev,
                            void* tmp, cudaStream_t st);
 
-// ---- great-circle path (xgrid_gc_kernels.cu) -----------------------------------------------
-void launch_gc_cell_precompute(const TileDesc& tile, const double* lon, const double* lat,
-                               double* x, double* y, double* z, long long nvert_total_unused,
-                               double* area, long long cell_off, int* err, cudaStream_t st);
-
-// ---- apply (apply_kernels.cu) --------------------------------------------------------------
-void launch_build_dst_csr_count(long long nxgrid, const int* i_out, const int* j_out, int nx2,
-                                uint32_t* cnt, cudaStream_t st);
-
 }  // namespace xgb

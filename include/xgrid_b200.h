@@ -139,6 +139,64 @@ int xgb_plan_src_area_host(xgb_plan *p, double *area);
 int xgb_plan_dst_area_host(xgb_plan *p, double *area);
 
 /* ------------------------------------------------------------------------------------------
+ * Part 2b — conservative apply (do_scalar_conserve_interp, conserve_interp.c:507-910) and the order-2
+ * gradient terms (grad_c2l, gradient_c2l.c:58-118; calc_c2l_grid_info :368-454), batched over field-levels.
+ *
+ * Field layout ("one field-level" = what one reference call with nz == 1 consumes):
+ *   order 1 : all source tiles concatenated, nx*ny each                         (Field_config.data, globals.h:104)
+ *   order 2 : all source tiles concatenated, each WITH its one-cell halo, (nx+2)*(ny+2), halo already filled
+ *             (fregrid_util.c:2166-2183 update_halo is the caller's job, as it is for the reference routine)
+ *   grad_x, grad_y (double), grad_mask (int): tiles concatenated, nx*ny each     (globals.h:106-108)
+ *   output  : nx_out*ny_out
+ * A batch of nfields field-levels is nfields such arrays back to back.  Every field-level of a batch is
+ * remapped exactly as one reference call would remap it: per destination cell the sums run in the order of the
+ * exchange-grid list, so results are bit-identical to the reference.  Supported variants: order 1 / order 2,
+ * missing values (conserve_interp.c:563-590, :745-789), conserve_order2_monotonic (:617-742, opcode |
+ * XGB_MONOTONIC); cell_methods "mean" only (no cell_measures / weight field / --target_grid).
+ * on_device != 0: every pointer argument is a device pointer on the plan's device, work is only enqueued on
+ * the plan's stream.  on_device == 0: host pointers; the call returns when the outputs are in host memory.
+ * ---------------------------------------------------------------------------------------- */
+
+/* Regroup the result of the last xgb_plan_generate by destination cell (one-time, device side). */
+int xgb_plan_apply_setup(xgb_plan *p);
+
+/* The same from exchange-grid lists the caller already has (the READ branch of setup_conserve_interp,
+ * conserve_interp.c:63-128, or lists all-gathered from other GPUs): 0-based indices, area in m^2,
+ * di/dj = tile1_distance (NULL for order 1).  No grids are needed for order-1 apply. */
+int xgb_plan_set_xgrid(xgb_plan *p, int ntiles, const int *nx, const int *ny, int nx_out, int ny_out, long long nxgrid,
+                       const int *t_in, const int *i_in, const int *j_in, const int *i_out, const int *j_out,
+                       const double *area, const double *di, const double *dj, int on_device);
+long long xgb_plan_apply_nxgrid(xgb_plan *p);
+
+/* calc_c2l_grid_info (gradient_c2l.c:368) for every source tile on the device.  lont/latt: cell centres with a
+ * one-cell halo, tiles concatenated, (nx+2)*(ny+2) each (Grid_config.lont/latt, fregrid_util.c:262-292); corners
+ * are the plan's source grid.  Metrics agree with the reference to rounding, not bit for bit (see
+ * csrc/c2l_grid_info.cu); use xgb_plan_grad_set_metrics to supply the reference's own. */
+int xgb_plan_grad_setup(xgb_plan *p, const double *lont, const double *latt, int on_device);
+/* Metrics of one tile in the reference's layouts (Grid_config.dx, dy, area, edge_w/e/s/n, en_n, en_e, vlon_t,
+ * vlat_t; globals.h:193-209, sizes gradient_c2l.c:30-47). */
+int xgb_plan_grad_set_metrics(xgb_plan *p, int tile, const double *dx, const double *dy, const double *area,
+                              const double *edge_w, const double *edge_e, const double *edge_s, const double *edge_n,
+                              const double *en_n, const double *en_e, const double *vlon, const double *vlat, int on_device);
+int xgb_plan_grad_get_metrics(xgb_plan *p, int tile, double *dx, double *dy, double *area, double *edge_w, double *edge_e,
+                              double *edge_s, double *edge_n, double *en_n, double *en_e, double *vlon, double *vlat);
+
+/* grad_c2l with all four on_*_edge flags set, as fregrid calls it (fregrid_util.c:2197-2200), for nfields
+ * field-levels; grad_mask (may be NULL) as fregrid_util.c:2203-2216. */
+int xgb_plan_grad_c2l(xgb_plan *p, int nfields, const double *data, double *grad_x, double *grad_y, int *grad_mask,
+                      int has_missing, double missing, int on_device);
+
+/* do_scalar_conserve_interp for nfields field-levels.  opcode: XGB_CONSERVE_ORDER1 | XGB_CONSERVE_ORDER2
+ * [| XGB_MONOTONIC].  grad_* may be NULL for order 1; grad_mask may be NULL for order 2 without missing values.
+ * Cells no exchange cell touches receive `missing` (-1e20 when has_missing == 0, conserve_interp.c:541). */
+int xgb_plan_apply(xgb_plan *p, unsigned int opcode, int nfields, const double *data, const double *grad_x,
+                   const double *grad_y, const int *grad_mask, int has_missing, double missing, double *out, int on_device);
+
+/* gradient (order 2) + apply in one call; gradients stay in HBM. */
+int xgb_plan_regrid(xgb_plan *p, unsigned int opcode, int nfields, const double *data, int has_missing, double missing,
+                    double *out, int on_device);
+
+/* ------------------------------------------------------------------------------------------
  * Part 3 — input synthesis and self-checks (host side; not on the timed path).
  * ---------------------------------------------------------------------------------------- */
 

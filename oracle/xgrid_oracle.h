@@ -80,6 +80,9 @@ void orc_grad_c2l(int nx, int ny, const double *pin, const double *dx, const dou
                   const double *edge_s, const double *edge_n, const double *en_n, const double *en_e,
                   const double *vlon, const double *vlat, double *grad_x, double *grad_y);
 
+void orc_grad_mask(int nx, int ny, const double *pin, double missing, int *mask);
+double orc_spherical_angle(const double v1[3], const double v2[3], const double v3[3]);
+
 /* host libm, element-wise (pins csrc/ref_trig.cuh) */
 void orc_libm_trig(long n, const double *x, double *s, double *c, double *ss, double *sc);
 

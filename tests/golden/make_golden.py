@@ -113,6 +113,47 @@ def make_xgrid(tag, lonc, latc, lon2, lat2, opcode):
     print(f"xgrid_{tag}.npz: nxgrid", r["nxgrid"])
 
 
+def make_apply(tag, ni, nlon, nlat):
+    """remapped fields of the reference's do_scalar_conserve_interp + grad_c2l + calc_c2l_grid_info on a small case:
+    C<ni> -> nlon x nlat, two field-levels (smooth, random), order 1 / order 2 / order 2 with 5 % missing / monotonic"""
+    lonc, latc, lont, latt = xgtest.ref_cubed_sphere(ni, centers=True)
+    lo, la = latlon(nlon, nlat)
+    hm = xgtest.cubed_sphere_halo_map(lonc, latc)
+    xt = xgtest.with_halo(lont.reshape(-1), hm); yt = xgtest.with_halo(latt.reshape(-1), hm)
+    nh = (ni + 2) ** 2; nc = ni * ni
+    metrics = [xgtest.c2l_metrics("ref", ni, ni, xt[t * nh:(t + 1) * nh], yt[t * nh:(t + 1) * nh], lonc[t], latc[t]) for t in range(6)]
+    rng = np.random.default_rng(1234)
+    fields = np.stack([xgtest.smooth_field(lont, latt, 3, 2), rng.uniform(0, 1, 6 * nc)])
+    miss = -999.0
+    holes = np.random.default_rng(4321).uniform(size=fields.shape) < 0.05
+    fields_m = np.where(holes, miss, fields)
+    d = {"ni": np.int32(ni), "nlon": np.int32(nlon), "nlat": np.int32(nlat), "fields": fields, "fields_missing": fields_m,
+         "missing": np.float64(miss), "xt": xt, "yt": yt}
+    for k in xgtest.METRICS:
+        d["m_" + k] = np.concatenate([m[k] for m in metrics])
+    r1 = xgtest.ref_setup(lonc, latc, lo, la, 1, keep=True)
+    d["out_o1"] = np.stack([xgtest.ref_apply(r1["handle"], 1, f, nlon * nlat) for f in fields])
+    d["out_o1_missing"] = np.stack([xgtest.ref_apply(r1["handle"], 1, f, nlon * nlat, has_missing=True, missing=miss) for f in fields_m])
+    r2 = xgtest.ref_setup(lonc, latc, lo, la, 2, keep=True)
+    for name, src, hm_flag in (("", fields, False), ("_missing", fields_m, True)):
+        outs, outs_mono, gxs, gys, gms = [], [], [], [], []
+        for f in src:
+            fh = xgtest.with_halo(f, hm, corner=0.0)
+            gx = np.zeros(6 * nc); gy = np.zeros(6 * nc); gm = np.zeros(6 * nc, np.int32)
+            for t in range(6):
+                a, b = xgtest.grad_c2l("ref", ni, ni, fh[t * nh:(t + 1) * nh], metrics[t])
+                gx[t * nc:(t + 1) * nc] = a; gy[t * nc:(t + 1) * nc] = b
+                if hm_flag:
+                    gm[t * nc:(t + 1) * nc] = xgtest.grad_mask(ni, ni, fh[t * nh:(t + 1) * nh], miss)
+            outs.append(xgtest.ref_apply(r2["handle"], 2, fh, nlon * nlat, gx, gy, gm, has_missing=hm_flag, missing=miss))
+            outs_mono.append(xgtest.ref_apply(r2["handle"], 2, fh, nlon * nlat, gx, gy, gm, has_missing=hm_flag, missing=miss, monotonic=True))
+            gxs.append(gx); gys.append(gy); gms.append(gm)
+        d["out_o2" + name] = np.stack(outs); d["out_o2_mono" + name] = np.stack(outs_mono)
+        d["grad_x" + name] = np.stack(gxs); d["grad_y" + name] = np.stack(gys); d["grad_mask" + name] = np.stack(gms)
+    np.savez_compressed(os.path.join(HERE, f"apply_{tag}.npz"), **d)
+    print(f"apply_{tag}.npz: nxgrid", r1["nxgrid"], r2["nxgrid"])
+
+
 def latlon(nlon, nlat, lon0=0.0, lon1=360.0, lat0=-90.0, lat1=90.0):
     lon = np.array([(lon0 + i * ((lon1 - lon0) / nlon)) * D2R for i in range(nlon + 1)])
     lat = np.array([(lat0 + j * ((lat1 - lat0) / nlat)) * D2R for j in range(nlat + 1)])
@@ -134,6 +175,7 @@ def main():
     make_xgrid("ll40x20_regional_o2", [l1[0]], [l1[1]], l2[0], l2[1], 2)
     c10 = xgtest.ref_cubed_sphere(10)
     make_xgrid("c12_to_c10tile3_o2", c12[0], c12[1], c10[0][2], c10[1][2], 2)
+    make_apply("c8_36x18", 8, 36, 18)
 
 
 if __name__ == "__main__":

@@ -55,6 +55,9 @@ def oracle_lib():
         L.orc_conserve_apply.argtypes = [C.c_int, C.c_long] + [ip] * 5 + [dp, vp, vp, C.c_int, ip, ip, dp, vp, vp, vp,
                                          C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, dp]
         L.orc_libm_trig.argtypes = [C.c_long] + [dp] * 5
+        L.orc_grad_c2l.argtypes = [C.c_int, C.c_int] + [dp] * 14
+        L.orc_grad_mask.argtypes = [C.c_int, C.c_int, dp, C.c_double, ip]
+        L.orc_calc_c2l_grid_info.argtypes = [C.c_int, C.c_int] + [dp] * 15
         _oracle = L
     return _oracle
 
@@ -123,6 +126,9 @@ def ref_lib():
         L.poly_ctrlat.argtypes = [dp, dp, C.c_int]
         L.clip_2dx2d.argtypes = [dp, dp, C.c_int, dp, dp, C.c_int, dp, dp]
         L.get_grid_area.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), dp, dp, dp]
+        pi_ = C.POINTER(C.c_int)
+        L.grad_c2l.argtypes = [pi_, pi_] + [dp] * 14 + [pi_] * 4
+        L.calc_c2l_grid_info.argtypes = [pi_, pi_] + [dp] * 15 + [pi_] * 4
         _ref = L
     return _ref
 
@@ -274,3 +280,124 @@ def assert_xgrid_equal(got, ref, order, area_tol=1e-12, dist_atol=1e-11, same_or
             d = np.max(np.abs(got[k][pg] - ref[k][pr])) if len(b) else 0.0
             assert d <= dist_atol, f"{k} max abs diff {d}"
     return rel
+
+
+# ---------------------------------------------------------------------------------------------
+# apply path helpers: fields, halos, gradient metrics, oracle / reference apply
+# ---------------------------------------------------------------------------------------------
+METRICS = ("dx", "dy", "area", "edge_w", "edge_e", "edge_s", "edge_n", "en_n", "en_e", "vlon", "vlat")
+
+
+def metric_sizes(nx, ny):
+    return {"dx": nx * (ny + 1), "dy": (nx + 1) * ny, "area": nx * ny, "edge_w": ny + 1, "edge_e": ny + 1, "edge_s": nx + 1,
+            "edge_n": nx + 1, "en_n": 3 * nx * (ny + 1), "en_e": 3 * (nx + 1) * ny, "vlon": 3 * nx * ny, "vlat": 3 * nx * ny}
+
+
+def cubed_sphere_halo_map(lonc, latc):
+    """Index map that fills the one-cell halo of every tile of a cubed sphere from the neighbouring tiles
+    (what fregrid's update_halo, fregrid_util.c:2614, does from the mosaic contact list): returns an int64
+    array [6, n+2, n+2] of indices into the flat [6*n*n] cell array, -1 at the four halo corners.
+    Neighbours are found geometrically: the cell across an edge is the one sharing its two corner vertices."""
+    nt, npt, _ = lonc.shape
+    n = npt - 1
+    xyz = np.stack([np.cos(latc) * np.cos(lonc), np.cos(latc) * np.sin(lonc), np.sin(latc)], -1)
+    key = lambda v: tuple(np.round(v, 9) + 0.0)
+    edges = {}
+
+    def add(t, i, j, a, b):
+        k = frozenset((key(xyz[t][a]), key(xyz[t][b])))
+        edges.setdefault(k, []).append((t, i, j))
+    for t in range(nt):
+        for k in range(n):
+            add(t, 0, k, (k, 0), (k + 1, 0)); add(t, n - 1, k, (k, n), (k + 1, n))
+            add(t, k, 0, (0, k), (0, k + 1)); add(t, k, n - 1, (n, k), (n, k + 1))
+    m = -np.ones((nt, n + 2, n + 2), np.int64)
+    for t in range(nt):
+        m[t, 1:-1, 1:-1] = t * n * n + np.arange(n * n).reshape(n, n)
+
+    def other(t, a, b):
+        k = frozenset((key(xyz[t][a]), key(xyz[t][b])))
+        c = [e for e in edges[k] if e[0] != t]
+        assert len(c) == 1, (t, a, b, edges[k])
+        tt, ii, jj = c[0]
+        return tt * n * n + jj * n + ii
+    for t in range(nt):
+        for k in range(n):
+            m[t, k + 1, 0] = other(t, (k, 0), (k + 1, 0))
+            m[t, k + 1, n + 1] = other(t, (k, n), (k + 1, n))
+            m[t, 0, k + 1] = other(t, (0, k), (0, k + 1))
+            m[t, n + 1, k + 1] = other(t, (n, k), (n, k + 1))
+    return m
+
+
+def with_halo(flat, hmap, corner=0.0):
+    """flat [..., ncell] -> [..., 6*(n+2)^2] using cubed_sphere_halo_map; halo corners get `corner`"""
+    src = np.concatenate([np.asarray(flat, np.float64), np.full(flat.shape[:-1] + (1,), corner)], -1)
+    idx = np.where(hmap < 0, src.shape[-1] - 1, hmap).reshape(-1)
+    return np.ascontiguousarray(src[..., idx])
+
+
+def smooth_field(lont, latt, k=0, t=0):
+    """f = 2 + cos^2(lat) cos(2 lon) + 0.01 k + 0.001 t at cell centres (flat)"""
+    return (2.0 + np.cos(latt) ** 2 * np.cos(2 * lont) + 0.01 * k + 0.001 * t).reshape(-1)
+
+
+def c2l_metrics(fn_kind, nx, ny, xt, yt, xc, yc):
+    """calc_c2l_grid_info through the oracle ('oracle') or the compiled reference ('ref') for one tile"""
+    sz = metric_sizes(nx, ny)
+    m = {k: np.zeros(sz[k]) for k in METRICS}
+    args = [np.ascontiguousarray(a, np.float64).reshape(-1) for a in (xt, yt, xc, yc)] + [m[k] for k in METRICS]
+    if fn_kind == "oracle":
+        oracle_lib().orc_calc_c2l_grid_info(nx, ny, *args)
+    else:
+        one = C.c_int(1)
+        ref_lib().calc_c2l_grid_info(C.byref(C.c_int(nx)), C.byref(C.c_int(ny)), *args, *[C.byref(one)] * 4)
+    return m
+
+
+def grad_c2l(fn_kind, nx, ny, pin, m):
+    gx = np.zeros(nx * ny); gy = np.zeros(nx * ny)
+    args = [np.ascontiguousarray(pin, np.float64).reshape(-1)] + [m[k] for k in METRICS] + [gx, gy]
+    if fn_kind == "oracle":
+        oracle_lib().orc_grad_c2l(nx, ny, *args)
+    else:
+        one = C.c_int(1)
+        ref_lib().grad_c2l(C.byref(C.c_int(nx)), C.byref(C.c_int(ny)), *args, *[C.byref(one)] * 4)
+    return gx, gy
+
+
+def grad_mask(nx, ny, pin, missing):
+    m = np.zeros(nx * ny, np.int32)
+    oracle_lib().orc_grad_mask(nx, ny, np.ascontiguousarray(pin, np.float64).reshape(-1), float(missing), m)
+    return m
+
+
+def oracle_apply(x, order, tiles, data, nx_out, ny_out, grad_x=None, grad_y=None, gmask=None, has_missing=False,
+                 missing=0.0, monotonic=False):
+    """orc_conserve_apply for ONE field-level (nz = 1); tiles = [(nx, ny), ...]"""
+    L = oracle_lib()
+    nx = np.array([t[0] for t in tiles], np.int32); ny = np.array([t[1] for t in tiles], np.int32)
+    out = np.zeros(nx_out * ny_out)
+    ptr = lambda a: None if a is None else a.ctypes.data
+    gx = None if grad_x is None else np.ascontiguousarray(grad_x, np.float64)
+    gy = None if grad_y is None else np.ascontiguousarray(grad_y, np.float64)
+    gm = None if gmask is None else np.ascontiguousarray(gmask, np.int32)
+    di = x.get("di"); dj = x.get("dj")
+    L.orc_conserve_apply(order, x["area"].size, x["t_in"], x["i_in"], x["j_in"], x["i_out"], x["j_out"], x["area"],
+                         ptr(di) if order == 2 else None, ptr(dj) if order == 2 else None, len(tiles), nx, ny,
+                         np.ascontiguousarray(data, np.float64), ptr(gx), ptr(gy), ptr(gm), int(has_missing), float(missing),
+                         int(monotonic), nx_out, ny_out, 1, out)
+    return out
+
+
+def ref_apply(handle, order, data, nout, grad_x=None, grad_y=None, gmask=None, has_missing=False, missing=0.0, monotonic=False):
+    """the reference's do_scalar_conserve_interp for ONE field-level through oracle/ref_driver.c"""
+    L = ref_lib()
+    out = np.zeros(nout)
+    ptr = lambda a: None if a is None else a.ctypes.data
+    gx = None if grad_x is None else np.ascontiguousarray(grad_x, np.float64)
+    gy = None if grad_y is None else np.ascontiguousarray(grad_y, np.float64)
+    gm = None if gmask is None else np.ascontiguousarray(gmask, np.int32)
+    L.ref_regrid_apply(handle, order, int(has_missing), float(missing), 0, 1, MONOTONIC if monotonic else 0,
+                       np.ascontiguousarray(data, np.float64), ptr(gx), ptr(gy), ptr(gm), out)
+    return out
