@@ -184,6 +184,88 @@ def run_reference_arm(args):
 
 
 # ---------------------------------------------------------------------------------------------
+# apply leg (BASELINE.json metric, second half: "apply GB/s"): configs[1] = C96 -> 1440x720 order 2, 33 levels x 12 times
+# ---------------------------------------------------------------------------------------------
+APPLY_CFG = {"ni": 96, "nlon": 1440, "nlat": 720, "levels": 33, "times": 12}
+
+
+def apply_leg(pkg, torch, dist, rank, world, local, steps, warmup):
+    """grad_c2l + do_scalar_conserve_interp for all 396 field-levels of configs[1] per step.  Field-levels are dealt
+    round-robin to the ranks (no data-path collective: every rank holds the whole exchange grid, 53 MB).
+    Algorithmic bytes per step: nxgrid*32 once + B*(Nsrc*8 data + Nsrc*16 gradients written + Nsrc*16
+    gradients read + Ndst*8 output)."""
+    import xgtest
+    ni, nlon, nlat = APPLY_CFG["ni"], APPLY_CFG["nlon"], APPLY_CFG["nlat"]
+    B = APPLY_CFG["levels"] * APPLY_CFG["times"]
+    mine = list(range(rank, B, world))
+    nb = len(mine)
+    lonc, latc, lont, latt = pkg.cubed_sphere_grid(ni, centers=True)
+    lon2, lat2 = pkg.latlon_grid(nlon, nlat)
+    hm = xgtest.cubed_sphere_halo_map(lonc, latc)
+    plan = pkg.XgridPlan(local)
+    plan.set_dst(lon2, lat2)
+    plan.set_src(lonc, latc)
+    nx = plan.generate(pkg.CONSERVE_ORDER2)
+    plan.apply_setup()
+    plan.grad_setup(xgtest.with_halo(lont.reshape(-1), hm), xgtest.with_halo(latt.reshape(-1), hm))
+    ncell, nhalo, ndst = 6 * ni * ni, 6 * (ni + 2) ** 2, nlon * nlat
+    rng = np.random.default_rng(1234 + rank)
+    base = xgtest.smooth_field(lont, latt)
+    f = np.stack([base + 0.01 * (b % 33) + 0.001 * (b // 33) if b % 2 == 0 else rng.uniform(0, 1, ncell) for b in mine])
+    h_in = torch.from_numpy(xgtest.with_halo(f, hm).reshape(-1)).pin_memory()
+    h_out = torch.empty(nb * ndst, dtype=torch.float64).pin_memory()
+    dev = torch.device("cuda", local)
+    d_in = h_in.to(dev)
+    d_out = torch.empty(nb * ndst, dtype=torch.float64, device=dev)
+    ext = torch.cuda.ExternalStream(plan.stream, device=dev)
+    opcode = pkg.CONSERVE_ORDER2
+    launches0 = pkg.kernel_launches()
+
+    def timed(fn, n):
+        for _ in range(max(warmup, 1)):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(ext):
+            e0.record()
+        for _ in range(n):
+            fn()
+        with torch.cuda.stream(ext):
+            e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / n], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms = timed(lambda: plan.regrid(opcode, d_in, nb, out=d_out), max(steps, 3))
+    launches = (pkg.kernel_launches() - launches0) // (max(steps, 3) + max(warmup, 1))
+    e2e_ms = timed(lambda: plan.regrid(opcode, h_in.numpy(), nb, out=h_out.numpy()), 3)
+    plan.close()
+    bytes_step = nx * 32 * world + B * (ncell * 8 + ncell * 16 * 2 + ndst * 8)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    gbs = bytes_step / (ms * 1e-3) * 1e-9
+    return {"workload": f"C{ni} -> {nlon}x{nlat} conserve_order2 remap (grad_c2l + apply) of {B} field-levels "
+                        f"({APPLY_CFG['levels']} levels x {APPLY_CFG['times']} times), nxgrid {nx}",
+            "metric": "apply_GB_per_sec", "value": gbs, "unit": "GB/s (algorithmic bytes)", "ms_per_step": ms,
+            "field_levels_per_sec": B / (ms * 1e-3), "algorithmic_bytes_per_step": int(bytes_step), "gpu_launches_per_step": int(launches),
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s", "kernel": "apply_kernel<2> + grad_c2l_kernel"},
+            "e2e": {"value": bytes_step / (e2e_ms * 1e-3) * 1e-9, "unit": "GB/s (algorithmic bytes)", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(h_in.numel() * 8 * world), "d2h_bytes_per_step": int(h_out.numel() * 8 * world)},
+            "sharding": f"{B} field-levels dealt round-robin to {world} rank(s); every rank holds the whole exchange grid"}
+
+
+# ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
 def run_gpu_arm(args):
@@ -296,6 +378,10 @@ def run_gpu_arm(args):
     h2d = (h_lon1.numel() + h_lat1.numel() + h_lon2.numel() + h_lat2.numel()) * 8
     d2h = k * (5 * 4 + (3 if order == 2 else 1) * 8)
 
+    apply = None
+    if not args.no_apply:
+        apply = apply_leg(pkg, torch, dist, rank, world, local, min(args.steps, 10), args.warmup)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -344,7 +430,7 @@ def run_gpu_arm(args):
             "clocks": clocks, "gpu_launches": launches_total,
             "e2e": {"value": nx_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms, "steps": e2e_steps},
-            "roofline": roofline, "phase_ms": phases, "cpu_baseline": cpu}
+            "roofline": roofline, "phase_ms": phases, "cpu_baseline": cpu, "apply": apply}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -358,6 +444,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c768", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-apply", action="store_true", help="skip the apply-GB/s leg (configs[1])")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
