@@ -10,8 +10,9 @@
 // (sysdeps/ieee754/dbl-64/s_sin.c: do_sin / do_cos / TAYLOR_SIN over a 1/128-spaced table), with the
 // multiply-add contractions of its FMA build (__sin_fma / __cos_fma / __sincos_fma, the variant the
 // dynamic linker selects on every FMA-capable x86-64 CPU) written out as explicit fma() calls.
-// Only |x| < 2.426265 is restated (all latitudes and half-differences the regridding path feeds to
-// trig); larger arguments fall back to the toolchain's sin/cos.
+// |x| < 2.426265 (all latitudes and half-differences the 2dx2d path feeds to trig) takes the table paths;
+// 2.426265 <= |x| < 105414350 (longitudes, great-circle path) takes reduce_sincos + do_sincos; beyond that the
+// toolchain's sin/cos is used (never reached by regridding inputs).
 //
 // The same code compiles for host and device; tests/test_trig_cpu.py checks the host build
 // bit-for-bit against libm on millions of arguments, and tests/test_xgrid_gpu.py checks the device
@@ -127,6 +128,37 @@ XGB_HD double do_cos(double x, double dx) {
   const double xr = reduce(fabs(x), &t) + dx;
   return cos_core(xr, t);
 }
+// reduce_sincos (s_sin.c): x = n*pi/2 + (a + da), |a| <= pi/4.  Only the y step is contracted in the FMA build
+// (checked against this image's libm on 4e8 arguments; contracting the pp4 step as well is indistinguishable).
+constexpr double hpinv = 0x1.45F306DC9C883p-1, toint = 0x1.8000000000000p52;
+constexpr double mp1 = 0x1.921FB58000000p0, mp2 = -0x1.DDE973C000000p-27;
+constexpr double pp3 = -0x1.CB3B398000000p-55, pp4 = -0x1.d747f23e32ed7p-83;
+
+XGB_HD int reduce_sincos(double x, double* a, double* da) {
+  const double t = x * hpinv + toint;
+  const double xn = t - toint;
+  const int n = (int)(bits(t) & 3u);
+  const double y = fma(-xn, mp2, fma(-xn, mp1, x));
+  double t1 = xn * pp3;
+  const double t2 = y - t1;
+  double db = (y - t2) - t1;
+  t1 = xn * pp4;
+  const double b = t2 - t1;
+  db += (t2 - b) - t1;
+  *a = b; *da = db;
+  return n;
+}
+
+XGB_HD double do_sincos(double a, double da, int n) {
+  double r;
+  if (n & 1) r = do_cos(a, da);
+  else {
+    const double xx = a * a;
+    if (xx < 0.01588) r = taylor_sin(a, da);
+    else r = mag_with_sign_of(do_sin(a, da), a);
+  }
+  return (n & 2) ? -r : r;
+}
 }  // namespace trig
 
 XGB_HD double ref_sin(double x) {
@@ -134,6 +166,7 @@ XGB_HD double ref_sin(double x) {
   if (k < 0x3e500000u) return x;
   if (k < 0x3feb6000u) return trig::do_sin(x, 0.0);
   if (k < 0x400368fdu) return trig::mag_with_sign_of(trig::do_cos(trig::hp0 - fabs(x), trig::hp1), x);
+  if (k < 0x419921FBu) { double a, da; const int n = trig::reduce_sincos(x, &a, &da); return trig::do_sincos(a, da, n); }
   return sin(x);
 }
 
@@ -147,6 +180,7 @@ XGB_HD double ref_cos(double x) {
     const double da = (y - a) + trig::hp1;
     return trig::do_sin(a, da);
   }
+  if (k < 0x419921FBu) { double a, da; const int n = trig::reduce_sincos(x, &a, &da); return trig::do_sincos(a, da, n + 1); }
   return cos(x);
 }
 
@@ -173,6 +207,12 @@ XGB_HD void ref_sincos(double x, double* sn, double* cs) {
     *sn = trig::mag_with_sign_of(trig::cos_core(xr0 + ((a < 0) ? -da : da), t), x);
     if (aa < 0.126) *cs = trig::taylor_sin(a, da);
     else *cs = trig::mag_with_sign_of(trig::sin_core(xr0, (a <= 0) ? -da : da, t), a);
+    return;
+  }
+  if (k < 0x419921FBu) {
+    double a, da;
+    const int n = trig::reduce_sincos(x, &a, &da);
+    *sn = trig::do_sincos(a, da, n); *cs = trig::do_sincos(a, da, n + 1);
     return;
   }
   *sn = sin(x); *cs = cos(x);

@@ -63,12 +63,15 @@ def oracle_lib():
 
 
 def trig_samples(n=200000, seed=99):
-    """arguments covering every branch of csrc/ref_trig.cuh: bulk (-2.42, 2.42), Taylor range, tiny, near pi/2"""
+    """arguments covering every branch of csrc/ref_trig.cuh: bulk (-2.42, 2.42), Taylor range, tiny, near pi/2, and the
+    large-argument range reduction"""
     rng = np.random.default_rng(seed)
     x = np.concatenate([rng.uniform(-2.42, 2.42, n), rng.uniform(-0.13, 0.13, n // 4), rng.uniform(-1e-3, 1e-3, n // 8),
                         rng.uniform(-1e-8, 1e-8, n // 8), np.pi / 2 - rng.uniform(0, 1e-4, n // 8),
                         -np.pi / 2 + rng.uniform(0, 1e-4, n // 8),
-                        np.array([0.0, -0.0, np.pi / 2, -np.pi / 2, 0.126, 0.855469, 0.85546875, 2.426265, 2.0 ** -26, 2.0 ** -27])])
+                        rng.uniform(-7.0, 7.0, n // 2), rng.uniform(-400.0, 400.0, n // 4),      # longitudes: reduce_sincos branch
+                        np.array([0.0, -0.0, np.pi / 2, -np.pi / 2, 0.126, 0.855469, 0.85546875, 2.426265, 2.0 ** -26, 2.0 ** -27,
+                                  np.pi, -np.pi, 2 * np.pi, 1.5 * np.pi, 3.0, 4.0, 5.0, 6.0])])
     return np.ascontiguousarray(x)
 
 
