@@ -88,6 +88,9 @@ def lib():
     L.xgb_plan_grad_c2l.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_double, C.c_int]
     L.xgb_plan_apply.argtypes = [vp, C.c_uint, C.c_int, vp, vp, vp, vp, C.c_int, C.c_double, vp, C.c_int]
     L.xgb_plan_regrid.argtypes = [vp, C.c_uint, C.c_int, vp, C.c_int, C.c_double, vp, C.c_int]
+    L.xgb_plan_great_circle_area_host.argtypes = [vp, C.c_int, vp]
+    L.xgb_gc_clip_host.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp]
+    L.create_xgrid_great_circle.restype = C.c_int
     L.xgb_cubed_sphere_grid.argtypes = [C.c_int, vp, vp, vp, vp]
     L.xgb_latlon_grid.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp]
     L.xgb_plan_phase_ms.argtypes = [vp, vp, vp, vp]
@@ -415,6 +418,12 @@ class XgridPlan:
         self._ck(self._L.xgb_plan_src_area_host(self._p, a.ctypes.data))
         return a
 
+    def great_circle_area(self, which="src"):
+        """get_grid_great_circle_area on the device (create_xgrid.c:98): 'src' (tiles concatenated) or 'dst'"""
+        a = np.empty(self.ncell_src if which == "src" else self.nx_dst * self.ny_dst)
+        self._ck(self._L.xgb_plan_great_circle_area_host(self._p, 0 if which == "src" else 1, a.ctypes.data))
+        return a
+
     def dst_area(self):
         a = np.empty(self.nx_dst * self.ny_dst)
         self._ck(self._L.xgb_plan_dst_area_host(self._p, a.ctypes.data))
@@ -472,6 +481,34 @@ def create_xgrid_2dx2d_order1(lon_in, lat_in, lon_out, lat_out, mask_in=None):
 def create_xgrid_2dx2d_order2(lon_in, lat_in, lon_out, lat_out, mask_in=None):
     """create_xgrid.c:893 — returns (nxgrid, i_in, j_in, i_out, j_out, xgrid_area, xgrid_clon, xgrid_clat)."""
     return _create_xgrid(2, lon_in, lat_in, lon_out, lat_out, mask_in)
+
+
+def create_xgrid_great_circle(lon_in, lat_in, lon_out, lat_out, mask_in=None):
+    """create_xgrid.c:1366 — returns (nxgrid, i_in, j_in, i_out, j_out, xgrid_area, xgrid_clon, xgrid_clat)."""
+    L = lib()
+    lon_in = np.ascontiguousarray(lon_in, np.float64); lat_in = np.ascontiguousarray(lat_in, np.float64)
+    lon_out = np.ascontiguousarray(lon_out, np.float64); lat_out = np.ascontiguousarray(lat_out, np.float64)
+    nlat_in, nlon_in = lon_in.shape[0] - 1, lon_in.shape[1] - 1
+    nlat_out, nlon_out = lon_out.shape[0] - 1, lon_out.shape[1] - 1
+    mask_in = np.ones(nlon_in * nlat_in) if mask_in is None else np.ascontiguousarray(mask_in, np.float64)
+    cap = get_maxxgrid()
+    ii, ji, io, jo = (np.empty(cap, np.int32) for _ in range(4))
+    xa = np.empty(cap); xc = np.empty(cap); yc = np.empty(cap)
+    ci = lambda v: C.byref(C.c_int(v))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    n = L.create_xgrid_great_circle(ci(nlon_in), ci(nlat_in), ci(nlon_out), ci(nlat_out), p(lon_in), p(lat_in), p(lon_out), p(lat_out),
+                                    p(mask_in), p(ii), p(ji), p(io), p(jo), p(xa), p(xc), p(yc))
+    return n, ii[:n], ji[:n], io[:n], jo[:n], xa[:n], xc[:n], yc[:n]
+
+
+def get_grid_great_circle_area(lon, lat):
+    """create_xgrid.c:98 — spherical-excess cell areas [ny, nx] in m^2."""
+    lon = np.ascontiguousarray(lon, np.float64); lat = np.ascontiguousarray(lat, np.float64)
+    ny, nx = lon.shape[0] - 1, lon.shape[1] - 1
+    area = np.empty((ny, nx))
+    lib().get_grid_great_circle_area(C.byref(C.c_int(nx)), C.byref(C.c_int(ny)), lon.ctypes.data_as(C.c_void_p),
+                                     lat.ctypes.data_as(C.c_void_p), area.ctypes.data_as(C.c_void_p))
+    return area
 
 
 def get_grid_area(lon, lat):

@@ -1,0 +1,377 @@
+// Great-circle polygon clipping and spherical-excess area for the exchange-grid kernels (sm_100a; the same code
+// also compiles for the host so tests can run it against the compiled reference on the CPU).
+//
+// Replaces clip_2dx2d_great_circle (reference create_xgrid.c:1479-1908), line_intersect_2D_3D (:1919-2081),
+// intersect_tri_with_line / invert_matrix_3x3 (mosaic_util.c:967-1043), insidePolygon (:1487-1530),
+// great_circle_area / spherical_angle (:763-838) and the list primitives addEnd / addIntersect / insertIntersect /
+// setInbound / getFirstInbound (:1095-1470).
+//
+// The reference walks singly linked lists carved from a global 100-node pool; here each thread keeps its four
+// lists as small fixed arrays in local memory (two vertex rings of at most kGcRing nodes, the intersection list, the
+// output polygon) and an "insert after" is an array insertion.  Every decision (EPSLN8 snapping of the edge
+// parameters, EPSLN10 point identity, exact-coordinate node identity, inbound/outbound bookkeeping, the walk
+// itself) is restated one for one: which vertex ends up where decides the integer cell lists.
+//
+// Two places cannot be bit-identical to an x86-64 build of the reference, which evaluates them in x87 extended
+// precision: the 3x3 solve of intersect_tri_with_line (long double) and acosl() in spherical_angle.  The solve is
+// done here in double-double arithmetic (106 bits, so the rounded result equals the x87 one except when the x87
+// result itself sits within 2^-11 ulp of a rounding boundary); acos uses gc_acos below.  Areas therefore agree with the
+// reference to a few 1e-16 steradian (absolute: the spherical excess is a difference of O(1) angles), the integer
+// lists exactly.
+#pragma once
+#include <math.h>
+#include "ref_trig.cuh"
+
+namespace xgb {
+namespace gc {
+
+constexpr double kRange = 0.05;     // RANGE_CHECK_CRITERIA, mosaic_util.h:26
+constexpr double kEps8 = 1.e-8, kEps10 = 1.e-10, kEps15 = 1.e-15, kEps30 = 1.e-30;
+constexpr double kPiD = 3.14159265358979323846;
+constexpr double kR = 6371000.0;
+constexpr int kRing = 16;           // vertices + inserted intersections of one cell
+constexpr int kInter = 16;
+constexpr int kPoly = 24;
+constexpr int kErrNotConvex = -1, kErrWalk = -2, kErrPool = -3;
+
+// ---- double-double helpers (explicit fma: the file is compiled with -fmad=false) --------------------------
+struct dd { double hi, lo; };
+XGB_HD dd two_sum(double a, double b) { const double s = a + b, bb = s - a; return dd{s, (a - (s - bb)) + (b - bb)}; }
+XGB_HD dd two_prod(double a, double b) { const double p = a * b; return dd{p, fma(a, b, -p)}; }
+XGB_HD dd dd_norm(double hi, double lo) { const double s = hi + lo; return dd{s, lo - (s - hi)}; }
+XGB_HD dd dd_add(dd a, dd b) {
+  dd s = two_sum(a.hi, b.hi);
+  const dd t = two_sum(a.lo, b.lo);
+  s.lo += t.hi;
+  s = dd_norm(s.hi, s.lo);
+  s.lo += t.lo;
+  return dd_norm(s.hi, s.lo);
+}
+XGB_HD dd dd_neg(dd a) { return dd{-a.hi, -a.lo}; }
+XGB_HD dd dd_sub(dd a, dd b) { return dd_add(a, dd_neg(b)); }
+XGB_HD dd dd_mul_d(dd a, double b) { dd p = two_prod(a.hi, b); p.lo = fma(a.lo, b, p.lo); return dd_norm(p.hi, p.lo); }
+XGB_HD dd dd_mul(dd a, dd b) { dd p = two_prod(a.hi, b.hi); p.lo += a.hi * b.lo + a.lo * b.hi; return dd_norm(p.hi, p.lo); }
+XGB_HD dd dd_div(dd a, dd b) {
+  const double q1 = a.hi / b.hi;
+  dd r = dd_sub(a, dd_mul_d(b, q1));
+  const double q2 = r.hi / b.hi;
+  r = dd_sub(r, dd_mul_d(b, q2));
+  const double q3 = r.hi / b.hi;
+  dd q = dd_norm(q1, q2);
+  return dd_add(q, dd{q3, 0.0});
+}
+// a*b - c*d with doubles, exact products
+XGB_HD dd det2(double a, double b, double c, double d) { return dd_sub(two_prod(a, b), two_prod(c, d)); }
+
+// acosl(x) rounded to double, as spherical_angle (mosaic_util.c:834) produces it
+XGB_HD double gc_acos(double x) { return acos(x); }
+
+struct V3 { double x, y, z; };
+
+XGB_HD bool same_point(double x1, double y1, double z1, double x2, double y2, double z2) {   // mosaic_util.c:1193
+  return !(fabs(x1 - x2) > kEps10 || fabs(y1 - y2) > kEps10 || fabs(z1 - z2) > kEps10);
+}
+
+XGB_HD V3 cross(const V3& a, const V3& b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+
+// spherical_angle (mosaic_util.c:800-838), plain double as an autotools build compiles it
+XGB_HD double spherical_angle(const V3& v1, const V3& v2, const V3& v3) {
+  const V3 p = cross(v1, v2), q = cross(v1, v3);
+  double ddd = (p.x * p.x + p.y * p.y + p.z * p.z) * (q.x * q.x + q.y * q.y + q.z * q.z);
+  if (ddd <= 0.0) return 0.;
+  ddd = (p.x * q.x + p.y * q.y + p.z * q.z) / sqrt(ddd);
+  if (fabs(ddd - 1) < kEps30) ddd = 1;
+  if (fabs(ddd + 1) < kEps30) ddd = -1;
+  if (ddd > 1. || ddd < -1.) return (ddd < 0.) ? kPiD : 0.;
+  return gc_acos(ddd);
+}
+
+// great_circle_area (mosaic_util.c:763-790) of n vertices v[0..n)
+template <class Get>
+XGB_HD double great_circle_area(int n, Get get) {
+  double sum = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const int i1 = (i + 1 < n) ? i + 1 : i + 1 - n;
+    const int i2 = (i + 2 < n) ? i + 2 : i + 2 - n;
+    sum += spherical_angle(get(i1), get(i2), get(i));
+  }
+  return (sum - (n - 2.) * kPiD) * kR * kR;
+}
+
+// vertex ring node / intersection node
+struct RNode { double x, y, z, u; int intersect, inbound, inside; };
+struct INode { double x, y, z, u, u_clip; int inbound, subj_index, clip_index; };
+struct Ring { RNode n[kRing]; int len; bool overflow; };
+
+XGB_HD void ring_append_unique(Ring& l, double x, double y, double z) {          // addEnd(list, x, y, z, 0, 0, 0, -1)
+  for (int k = 0; k < l.len; ++k) if (same_point(l.n[k].x, l.n[k].y, l.n[k].z, x, y, z)) return;
+  if (l.len >= kRing) { l.overflow = true; return; }
+  l.n[l.len++] = RNode{x, y, z, 0.0, 0, 0, -1};
+}
+
+XGB_HD bool inside_polygon(const RNode& q, const Ring& l) {                      // mosaic_util.c:1487-1530
+  double sum = 0;
+  const V3 p0{q.x, q.y, q.z};
+  for (int k = 0; k < l.len; ++k) {
+    const RNode& a = l.n[k];
+    const RNode& b = l.n[(k + 1 < l.len) ? k + 1 : 0];
+    if (same_point(p0.x, p0.y, p0.z, a.x, a.y, a.z)) return true;
+    sum += spherical_angle(p0, V3{b.x, b.y, b.z}, V3{a.x, a.y, a.z});
+  }
+  return fabs(sum - 2 * kPiD) < kEps8;
+}
+
+XGB_HD double ring_area(const Ring& l) {                                          // gridArea, mosaic_util.c:1364
+  return great_circle_area(l.len, [&](int k) { return V3{l.n[k].x, l.n[k].y, l.n[k].z}; });
+}
+
+// insertIntersect (mosaic_util.c:1291-1362); false if vertex v is not in the ring (the reference aborts)
+XGB_HD bool ring_insert(Ring& l, const V3& p, double u1, double u2, int inbound, const V3& v) {
+  int a = -1;
+  for (int k = 0; k < l.len; ++k) if (l.n[k].x == v.x && l.n[k].y == v.y && l.n[k].z == v.z) { a = k; break; }
+  if (a < 0) return false;
+  double ucur = u1;
+  if (u1 == 1) { ucur = 0; a = (a + 1 < l.len) ? a + 1 : 0; }
+  if (ucur == 0) {
+    RNode& t = l.n[a];
+    t.intersect = 2; t.inside = 1; t.u = ucur; t.x = p.x; t.y = p.y; t.z = p.z;
+    return true;
+  }
+  if (u2 != 0 && u2 != 1) {
+    if (inbound == 1) {
+      int b = (a + 1 < l.len) ? a + 1 : 0;
+      int guard = 0;
+      while (l.n[b].intersect && guard++ < kRing) b = (b + 1 < l.len) ? b + 1 : 0;
+      l.n[b].inside = 0;
+    } else if (inbound == 2) l.n[a].inside = 0;
+  }
+  int b = a + 1;
+  while (b < l.len) {
+    if (l.n[b].intersect == 1) { if (l.n[b].u > ucur) break; }
+    else break;
+    a = b; ++b;
+  }
+  if (l.len >= kRing) { l.overflow = true; return true; }
+  for (int k = l.len; k > a + 1; --k) l.n[k] = l.n[k - 1];
+  ++l.len;
+  l.n[a + 1] = RNode{p.x, p.y, p.z, ucur, 1, inbound, 1};
+  return true;
+}
+
+// parameter t where the line l1 + t (l2 - l1) meets the plane through a, b and the origin
+// (intersect_tri_with_line, mosaic_util.c:967-1008: M = [l1-l2 | b-a | 0-a], x = M^-1 (l1-a), t = x[0]); double-double
+XGB_HD bool plane_line_param(const V3& a, const V3& b, const V3& l1, const V3& l2, double* t) {
+  const double m0 = l1.x - l2.x, m1 = b.x - a.x, m2 = 0.0 - a.x;
+  const double m3 = l1.y - l2.y, m4 = b.y - a.y, m5 = 0.0 - a.y;
+  const double m6 = l1.z - l2.z, m7 = b.z - a.z, m8 = 0.0 - a.z;
+  const dd c0 = det2(m4, m8, m5, m7);                 // cofactors of the first column
+  const dd c1 = det2(m3, m8, m5, m6);
+  const dd c2 = det2(m3, m7, m4, m6);
+  const dd det = dd_add(dd_sub(dd_mul_d(c0, m0), dd_mul_d(c1, m1)), dd_mul_d(c2, m2));
+  if (fabs(det.hi) < kEps15) return false;
+  const dd r1 = det2(m2, m7, m1, m8), r2 = det2(m1, m5, m2, m4);   // first row of the adjugate: c0, r1, r2
+  const double v0 = l1.x - a.x, v1 = l1.y - a.y, v2 = l1.z - a.z;
+  const dd num = dd_add(dd_add(dd_mul_d(c0, v0), dd_mul_d(r1, v1)), dd_mul_d(r2, v2));
+  const dd q = dd_div(num, det);
+  *t = q.hi + q.lo;
+  return true;
+}
+
+// line_intersect_2D_3D (create_xgrid.c:1919-2081)
+XGB_HD bool line_intersect(const V3& a1, const V3& a2, const V3& q1, const V3& q2, const V3& q3,
+                           V3* p, double* ua, double* uq, int* inbound) {
+  *inbound = 0;
+  if (same_point(a1.x, a1.y, a1.z, q1.x, q1.y, q1.z)) { *ua = 0; *uq = 0; *p = a1; return true; }
+  if (same_point(a1.x, a1.y, a1.z, q2.x, q2.y, q2.z)) { *ua = 0; *uq = 1; *p = a1; return true; }
+  if (same_point(a2.x, a2.y, a2.z, q1.x, q1.y, q1.z)) { *ua = 1; *uq = 0; *p = a2; return true; }
+  if (same_point(a2.x, a2.y, a2.z, q2.x, q2.y, q2.z)) { *ua = 1; *uq = 1; *p = a2; return true; }
+  if (!plane_line_param(q1, q2, a1, a2, ua)) return false;
+  if (fabs(*ua) < kEps8) *ua = 0;
+  if (fabs(*ua - 1) < kEps8) *ua = 1;
+  if (*ua < 0 || *ua > 1) return false;
+  if (!plane_line_param(a1, a2, q1, q2, uq)) return false;
+  if (fabs(*uq) < kEps8) *uq = 0;
+  if (fabs(*uq - 1) < kEps8) *uq = 1;
+  if (*uq < 0 || *uq > 1) return false;
+  const double u = *ua;
+  const V3 c3 = cross(cross(a1, a2), cross(q1, q2));
+  if (fabs(sqrt(c3.x * c3.x + c3.y * c3.y + c3.z * c3.z)) < kEps30) return false;
+  V3 r{a1.x + u * (a2.x - a1.x), a1.y + u * (a2.y - a1.y), a1.z + u * (a2.z - a1.z)};
+  const double norm = sqrt(r.x * r.x + r.y * r.y + r.z * r.z);
+  r.x /= norm; r.y /= norm; r.z /= norm;
+  *p = r;
+  if (*uq != 0 && *uq != 1) {
+    const V3 d{a2.x - a1.x, a2.y - a1.y, a2.z - a1.z}, v1{q2.x - q1.x, q2.y - q1.y, q2.z - q1.z}, v2{q3.x - q2.x, q3.y - q2.y, q3.z - q2.z};
+    const V3 c1 = cross(v1, v2), c2 = cross(v1, d);
+    *inbound = (c1.x * c2.x + c1.y * c2.y + c1.z * c2.z > 0) ? 2 : 1;
+  }
+  return true;
+}
+
+XGB_HD int ring_find(const Ring& l, double x, double y, double z) {
+  for (int k = 0; k < l.len; ++k) if (l.n[k].x == x && l.n[k].y == y && l.n[k].z == z) return k;
+  return -1;
+}
+
+struct Poly { V3 v[kPoly]; int len; bool overflow; };
+XGB_HD void poly_append_unique(Poly& l, double x, double y, double z) {
+  for (int k = 0; k < l.len; ++k) if (same_point(l.v[k].x, l.v[k].y, l.v[k].z, x, y, z)) return;
+  if (l.len >= kPoly) { l.overflow = true; return; }
+  l.v[l.len++] = V3{x, y, z};
+}
+
+// clip_2dx2d_great_circle: vertices of cell 1 (subject) and cell 2 (clip) in the reference's clockwise order.
+// Returns the vertex count of the overlap polygon written to out (capacity kPoly), 0 if none, < 0 where the
+// reference would abort.
+XGB_HD int clip_great_circle(const V3* c1, int n1, const V3* c2, int n2, V3* out) {
+  {                                                              // six range rejections (:1508-1528)
+    double lo1[3], hi1[3], lo2[3], hi2[3];
+    lo1[0] = hi1[0] = c1[0].x; lo1[1] = hi1[1] = c1[0].y; lo1[2] = hi1[2] = c1[0].z;
+    for (int k = 1; k < n1; ++k) {
+      lo1[0] = fmin(lo1[0], c1[k].x); hi1[0] = fmax(hi1[0], c1[k].x);
+      lo1[1] = fmin(lo1[1], c1[k].y); hi1[1] = fmax(hi1[1], c1[k].y);
+      lo1[2] = fmin(lo1[2], c1[k].z); hi1[2] = fmax(hi1[2], c1[k].z);
+    }
+    lo2[0] = hi2[0] = c2[0].x; lo2[1] = hi2[1] = c2[0].y; lo2[2] = hi2[2] = c2[0].z;
+    for (int k = 1; k < n2; ++k) {
+      lo2[0] = fmin(lo2[0], c2[k].x); hi2[0] = fmax(hi2[0], c2[k].x);
+      lo2[1] = fmin(lo2[1], c2[k].y); hi2[1] = fmax(hi2[1], c2[k].y);
+      lo2[2] = fmin(lo2[2], c2[k].z); hi2[2] = fmax(hi2[2], c2[k].z);
+    }
+    for (int a = 0; a < 3; ++a)
+      if (lo1[a] >= hi2[a] + kRange || lo2[a] >= hi1[a] + kRange) return 0;
+  }
+  Ring g1, g2;
+  g1.len = g2.len = 0; g1.overflow = g2.overflow = false;
+  for (int k = 0; k < n1; ++k) ring_append_unique(g1, c1[k].x, c1[k].y, c1[k].z);
+  for (int k = 0; k < n2; ++k) ring_append_unique(g2, c2[k].x, c2[k].y, c2[k].z);
+  const int npts1 = g1.len, npts2 = g2.len;
+  for (int k = 0; k < g1.len; ++k) g1.n[k].inside = inside_polygon(g1.n[k], g2) ? 1 : 0;     // :1549-1568
+  for (int k = 0; k < g2.len; ++k) g2.n[k].inside = inside_polygon(g2.n[k], g1) ? 1 : 0;
+  if (ring_area(g1) <= 0 || ring_area(g2) <= 0) return kErrNotConvex;                       // :1575-1578
+
+  V3 pt1[kRing], pt2[kRing];
+  for (int k = 0; k < npts1; ++k) pt1[k] = V3{g1.n[k].x, g1.n[k].y, g1.n[k].z};
+  for (int k = 0; k < npts2; ++k) pt2[k] = V3{g2.n[k].x, g2.n[k].y, g2.n[k].z};
+  INode inter[kInter];
+  int ninter = 0;
+  bool inter_overflow = false;
+
+  for (int i1 = 0; i1 < npts1; ++i1) {                                                       // :1606-1670
+    const int i1p = (i1 + 1 < npts1) ? i1 + 1 : 0;
+    for (int i2 = 0; i2 < npts2; ++i2) {
+      const int i2p = (i2 + 1 < npts2) ? i2 + 1 : i2 + 1 - npts2;
+      const int i2p2 = (i2 + 2 < npts2) ? i2 + 2 : i2 + 2 - npts2;
+      V3 p;
+      double u1, u2;
+      int inbound;
+      if (!line_intersect(pt1[i1], pt1[i1p], pt2[i2], pt2[i2p], pt2[i2p2], &p, &u1, &u2, &inbound)) continue;
+      {                                                                                      // addIntersect :1133-1186
+        double u1c = u1, u2c = u2;
+        int s = i1, c = i2;
+        if (u1c == 1) { u1c = 0; s = i1p; }
+        if (u2c == 1) { u2c = 0; c = i2p; }
+        bool dup = false;
+        for (int k = 0; k < ninter; ++k)
+          if ((inter[k].u == u1c && inter[k].subj_index == s) || (inter[k].u_clip == u2c && inter[k].clip_index == c)) { dup = true; break; }
+        if (dup) continue;
+        if (ninter >= kInter) { inter_overflow = true; continue; }
+        inter[ninter++] = INode{p.x, p.y, p.z, u1c, u2c, inbound, s, c};
+      }
+      if (u1 == 1) { if (!ring_insert(g1, p, 0.0, u2, inbound, pt1[i1p])) return kErrWalk; }
+      else         { if (!ring_insert(g1, p, u1, u2, inbound, pt1[i1])) return kErrWalk; }
+      if (u1 == 1) pt1[i1p] = p; else if (u1 == 0) pt1[i1] = p;
+      if (u2 == 1) { if (!ring_insert(g2, p, 0.0, u1, 0, pt2[i2p])) return kErrWalk; }
+      else         { if (!ring_insert(g2, p, u2, u1, 0, pt2[i2])) return kErrWalk; }
+      if (u2 == 1) pt2[i2p] = p; else if (u2 == 0) pt2[i2] = p;
+    }
+  }
+  if (g1.overflow || g2.overflow || inter_overflow) return kErrPool;
+
+  int nint = ninter, first = -1;                                                             // :1676-1693
+  if (nint > 1) for (int k = 0; k < ninter; ++k) if (inter[k].inbound == 2) { first = k; break; }
+  if (first < 0 && nint > 1) {                                                               // setInbound :1437-1470
+    for (int k = 0; k < ninter; ++k) {
+      if (inter[k].inbound) continue;
+      const int a = ring_find(g1, inter[k].x, inter[k].y, inter[k].z);
+      if (a < 0) return kErrWalk;
+      const RNode& prev = g1.n[a > 0 ? a - 1 : g1.len - 1];
+      const RNode& next = g1.n[a + 1 < g1.len ? a + 1 : 0];
+      inter[k].inbound = (prev.inside == 0 && next.inside == 1) ? 2 : 1;
+    }
+    for (int k = 0; k < ninter; ++k) if (inter[k].inbound == 2) { first = k; break; }
+  }
+
+  int n_out = 0;
+  if (first >= 0) {                                                                          // :1697-1838
+    Poly poly;
+    poly.len = 0; poly.overflow = false;
+    const V3 f{inter[first].x, inter[first].y, inter[first].z};
+    if (ring_find(g1, f.x, f.y, f.z) < 0) return kErrWalk;
+    poly_append_unique(poly, f.x, f.y, f.z);
+    --nint;
+    V3 cur = f;
+    const int maxiter1 = ninter;
+    int iter1 = 0;
+    bool found1 = false, on2 = false;
+    while (iter1 < maxiter1) {
+      const Ring& cl = on2 ? g2 : g1;
+      const int a = ring_find(cl, cur.x, cur.y, cur.z);
+      if (a < 0) return kErrWalk;
+      int b = (a + 1 < cl.len) ? a + 1 : 0;
+      bool found2 = false;
+      for (int iter2 = 0; iter2 < cl.len; ++iter2) {
+        bool b_is_x = false;
+        const RNode& nb = cl.n[b];
+        if (nb.intersect) {
+          if (nb.x == f.x && nb.y == f.y && nb.z == f.z) { found1 = true; break; }
+          const RNode& nc = cl.n[(b + 1 < cl.len) ? b + 1 : 0];
+          found2 = true; b_is_x = true;
+          if (nc.intersect || nc.inside == 1) found2 = false;
+        }
+        if (found2) { cur = V3{nb.x, nb.y, nb.z}; break; }
+        poly_append_unique(poly, nb.x, nb.y, nb.z);
+        if (b_is_x) --nint;
+        b = (b + 1 < cl.len) ? b + 1 : 0;
+      }
+      if (found1) break;
+      if (!found2) return kErrWalk;
+      if (cur.x == f.x && cur.y == f.y && cur.z == f.z) { found1 = true; break; }
+      poly_append_unique(poly, cur.x, cur.y, cur.z);
+      --nint;
+      on2 = !on2;
+      ++iter1;
+    }
+    if (!found1 || nint > 0) return kErrWalk;
+    if (poly.overflow) return kErrPool;
+    for (int k = 0; k < poly.len; ++k) out[k] = poly.v[k];
+    n_out = poly.len;
+    if (n_out < 3) n_out = 0;
+  }
+  if (n_out == 0) {                                                                          // :1841-1871
+    int c = 0;
+    for (int k = 0; k < g1.len; ++k) if (g1.n[k].intersect != 1 && g1.n[k].inside == 1) ++c;
+    if (c == npts1) {
+      for (int k = 0; k < npts1; ++k) out[k] = V3{g1.n[k].x, g1.n[k].y, g1.n[k].z};
+      return npts1;
+    }
+  }
+  if (n_out == 0) {                                                                          // :1874-1904
+    int c = 0;
+    for (int k = 0; k < g2.len; ++k) if (g2.n[k].intersect != 1 && g2.n[k].inside == 1) ++c;
+    if (c == npts2) {
+      for (int k = 0; k < npts2; ++k) out[k] = V3{g2.n[k].x, g2.n[k].y, g2.n[k].z};
+      n_out = npts2;
+    }
+  }
+  return n_out;
+}
+
+// latlon2xyz (mosaic_util.c:212-222) with the sin/cos entry points the reference binary calls
+XGB_HD V3 ll2xyz(double lon, double lat) {
+  const double cl = ref_cos(lat);
+  return V3{cl * ref_cos(lon), cl * ref_sin(lon), ref_sin(lat)};
+}
+
+}  // namespace gc
+}  // namespace xgb

@@ -108,7 +108,7 @@ extern "C" void xgb_plan_destroy(xgb_plan* p)
                     &p->pclon, &p->pclat, &p->scan_tmp, &p->t_in, &p->i_in, &p->j_in, &p->i_out, &p->j_out,
                     &p->area, &p->clon, &p->clat, &p->di, &p->dj, &p->bounds_dev,
                     &p->heavy_ctl, &p->heavy_flag, &p->heavy_list, &p->heavy_items, &p->heavy_pairs,
-                    &p->gc_src_xyz, &p->gc_dst_xyz};
+                    &p->gc_src_xyz, &p->gc_dst_xyz, &p->gc_pyr_store};
   for (DevBuf* b : bufs) b->release();
   xgb_apply_release(p);
   for (int k = 0; k < 6; ++k) if (p->ev[k]) cudaEventDestroy(p->ev[k]);
@@ -152,7 +152,7 @@ static int upload(DevBuf& dst, const double* src, size_t n, int on_device, cudaS
   return 0;
 }
 
-static int check_kernel_errors(xgb_plan* p, bool fatal_like_reference)
+int xgb_check_kernel_errors(xgb_plan* p, bool fatal_like_reference)
 {
   CU_OK(cudaMemcpyAsync(p->err_host, p->err_dev, sizeof(int), cudaMemcpyDeviceToHost, p->st));
   CU_OK(cudaStreamSynchronize(p->st));
@@ -212,7 +212,7 @@ extern "C" int xgb_plan_set_dst(xgb_plan* p, int nx, int ny, const double* lon, 
   }
   p->have_dst = true;
   p->gc_dst_ready = false;
-  return check_kernel_errors(p, false);
+  return xgb_check_kernel_errors(p, false);
 }
 
 extern "C" int xgb_plan_set_src(xgb_plan* p, int ntiles, const int* nx, const int* ny,
@@ -241,7 +241,7 @@ extern "C" int xgb_plan_set_src(xgb_plan* p, int ntiles, const int* nx, const in
   p->have_src = true;
   p->gc_src_ready = false;
   // the tile table was copied from pageable host memory: make sure it has landed before `tiles` can change
-  return check_kernel_errors(p, false);
+  return xgb_check_kernel_errors(p, false);
 }
 
 extern "C" int xgb_plan_set_src_window(xgb_plan* p, long long begin, long long end)
@@ -365,7 +365,7 @@ extern "C" long long xgb_plan_generate(xgb_plan* p, unsigned int opcode)
     launch_order2_finalize(p->src, s0, ns, (const uint32_t*)p->out_off.p, (const double*)p->area.p,
                            (const double*)p->clon.p, (const double*)p->clat.p, (double*)p->di.p, (double*)p->dj.p, p->st);
   cudaEventRecord(p->ev[5], p->st);
-  if (check_kernel_errors(p, false)) return -1;
+  if (xgb_check_kernel_errors(p, false)) return -1;
   for (int k = 0; k < 5; ++k) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, p->ev[k], p->ev[k + 1]);
@@ -535,6 +535,37 @@ extern "C" int create_xgrid_2dx2d_order2_(const int* a, const int* b, const int*
                                           double* xa, double* xc, double* yc)
 {
   return create_xgrid_2dx2d_order2(a, b, c, d, e, f, g, h, m, i1, j1, i2, j2, xa, xc, yc);
+}
+
+// create_xgrid.h:41 / :78-80 (create_xgrid.c:98-137, :1366-1466)
+extern "C" void get_grid_great_circle_area(const int* nlon, const int* nlat, const double* lon, const double* lat, double* area)
+{
+  xgb_plan* p = default_plan();
+  p->have_src = false;                // only the destination side is needed for the areas
+  if (xgb_plan_set_dst(p, *nlon, *nlat, lon, lat, 0) || xgb_plan_great_circle_area_host(p, 1, area)) fatal(xgb_last_error());
+}
+
+extern "C" int create_xgrid_great_circle(const int* nlon_in, const int* nlat_in, const int* nlon_out, const int* nlat_out,
+                                         const double* lon_in, const double* lat_in, const double* lon_out, const double* lat_out,
+                                         const double* mask_in, int* i_in, int* j_in, int* i_out, int* j_out,
+                                         double* xgrid_area, double* xgrid_clon, double* xgrid_clat)
+{
+  xgb_plan* p = default_plan();
+  if (xgb_plan_set_dst(p, *nlon_out, *nlat_out, lon_out, lat_out, 0)) fatal(xgb_last_error());
+  if (xgb_plan_set_src(p, 1, nlon_in, nlat_in, lon_in, lat_in, mask_in, 0)) fatal(xgb_last_error());
+  const long long n = xgb_plan_generate(p, XGB_CONSERVE_ORDER1 | XGB_GREAT_CIRCLE);
+  if (n < 0) fatal(xgb_last_error());
+  if (n > (long long)XGB_MAXXGRID) fatal("nxgrid is greater than MAXXGRID, increase MAXXGRID");      // create_xgrid.c:1450
+  if (xgb_plan_result_host(p, nullptr, i_in, j_in, i_out, j_out, xgrid_area, nullptr, nullptr)) fatal(xgb_last_error());
+  for (long long k = 0; k < n; ++k) { xgrid_clon[k] = 0; xgrid_clat[k] = 0; }                            // :1444-1445
+  return (int)n;
+}
+
+extern "C" int create_xgrid_great_circle_(const int* a, const int* b, const int* c, const int* d, const double* e, const double* f,
+                                          const double* g, const double* h, const double* m, int* i1, int* j1, int* i2, int* j2,
+                                          double* xa, double* xc, double* yc)
+{
+  return create_xgrid_great_circle(a, b, c, d, e, f, g, h, m, i1, j1, i2, j2, xa, xc, yc);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,239 @@
+// Great-circle exchange-grid kernels for sm_100a: create_xgrid_great_circle (reference create_xgrid.c:1366-1466).
+//
+//   gc_cell_precompute : per cell the four corners as unit vectors (latlon2xyz, :1401-1402) in the reference's
+//                        clockwise order, a bounding box in xyz grown by the bulge of the cell's great-circle sides,
+//                        and the cell's spherical-excess area (get_grid_great_circle_area, :98-137)
+//   gc_pyramid_level   : 2x2 union of destination boxes
+//   gc_candidates<FILL>: per source cell depth-first walk of the box pyramid.  The reference tests every
+//                        (source, destination) pair and rejects on coordinate ranges widened by 0.05 (318 km); a pair
+//                        can only produce an exchange cell when the two cells overlap, and overlapping cells have
+//                        intersecting boxes, so the tighter box test enumerates a superset of the accepted pairs
+//                        and the emitted list is unchanged.
+//   gc_clip            : one thread per candidate pair: clip_2dx2d_great_circle + great_circle_area + the
+//                        area-ratio test (:1436-1452); counts accepted pairs per source cell
+// The ordered compaction is the 2dx2d path's scatter kernel (the emission order is the same: source cells row-major,
+// then destination index ascending).
+#include "gc_clip.cuh"
+#include "xgrid_gc.h"
+
+namespace xgb {
+
+extern long long g_launches;
+
+__global__ void __launch_bounds__(128)
+gc_cell_precompute_kernel(TileDesc tile, const double* __restrict__ lon, const double* __restrict__ lat, GcCells cells, int* err)
+{
+  const long long n = (long long)tile.nx * tile.ny;
+  const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const int i = (int)(c % tile.nx), j = (int)(c / tile.nx);
+  const int nxp = tile.nx + 1;
+  const double* lo = lon + tile.vert_off;
+  const double* la = lat + tile.vert_off;
+  const long long n0 = (long long)j * nxp + i, n1 = (long long)(j + 1) * nxp + i;
+  const long long idx[4] = {n0, n1, n1 + 1, n0 + 1};                     // clockwise, create_xgrid.c:1421-1427
+  gc::V3 v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = gc::ll2xyz(lo[idx[k]], la[idx[k]]);
+  const long long g = tile.cell_off + c;
+  double bl[3] = {v[0].x, v[0].y, v[0].z}, bh[3] = {v[0].x, v[0].y, v[0].z};
+  double chord2 = 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    cells.v[(long long)(3 * k + 0) * cells.ncell + g] = v[k].x;
+    cells.v[(long long)(3 * k + 1) * cells.ncell + g] = v[k].y;
+    cells.v[(long long)(3 * k + 2) * cells.ncell + g] = v[k].z;
+    bl[0] = fmin(bl[0], v[k].x); bh[0] = fmax(bh[0], v[k].x);
+    bl[1] = fmin(bl[1], v[k].y); bh[1] = fmax(bh[1], v[k].y);
+    bl[2] = fmin(bl[2], v[k].z); bh[2] = fmax(bh[2], v[k].z);
+    const gc::V3& w = v[(k + 1) & 3];
+    const double dx = w.x - v[k].x, dy = w.y - v[k].y, dz = w.z - v[k].z;
+    chord2 = fmax(chord2, dx * dx + dy * dy + dz * dz);
+  }
+  // Every point of the cell is a normalised convex combination q/|q| of its corners, |q| >= cos(phi/2) with phi the
+  // cell's angular diameter <= twice its longest side; its coordinates leave the corners' range by at most
+  // sec(phi/2) - 1 ~ phi^2/8 <= c^2/2 (c = longest chord).  0.75 c^2 covers the higher-order terms for c^2 < 1;
+  // larger cells get the whole sphere.
+  const double grow = (chord2 < 1.0) ? 0.75 * chord2 + 1e-13 : 2.0;
+  Box3 b;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) { b.lo[a] = bl[a] - grow; b.hi[a] = bh[a] + grow; }
+  cells.box[g] = b;
+  // gridArea of the ring after addEnd's duplicate suppression (pole cells of a lat-lon grid become triangles)
+  gc::Ring r;
+  r.len = 0; r.overflow = false;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) gc::ring_append_unique(r, v[k].x, v[k].y, v[k].z);
+  cells.area[g] = gc::ring_area(r);
+  (void)err;
+}
+
+void launch_gc_cell_precompute(const TileDesc& tile, const double* lon, const double* lat, GcCells cells, int* err, cudaStream_t st)
+{
+  const long long n = (long long)tile.nx * tile.ny;
+  if (n <= 0) return;
+  ++g_launches;
+  gc_cell_precompute_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(tile, lon, lat, cells, err);
+}
+
+__device__ __forceinline__ Box3 load_box3(const Box3* p)
+{
+  const double2* q = reinterpret_cast<const double2*>(p);
+  const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+  Box3 r;
+  r.lo[0] = a.x; r.lo[1] = a.y; r.lo[2] = b.x; r.hi[0] = b.y; r.hi[1] = c.x; r.hi[2] = c.y;
+  return r;
+}
+
+__global__ void __launch_bounds__(256)
+gc_pyramid_level_kernel(Pyr3Level child, Box3* __restrict__ out, int nx, int ny)
+{
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= (long long)nx * ny) return;
+  const int ix = (int)(t % nx), iy = (int)(t / nx);
+  Box3 r;
+  for (int a = 0; a < 3; ++a) { r.lo[a] = 1e300; r.hi[a] = -1e300; }
+  for (int dy = 0; dy < 2; ++dy) {
+    const int cy = 2 * iy + dy;
+    if (cy >= child.ny) continue;
+    for (int dx = 0; dx < 2; ++dx) {
+      const int cx = 2 * ix + dx;
+      if (cx >= child.nx) continue;
+      const Box3 b = load_box3(child.box + (long long)cy * child.nx + cx);
+      for (int a = 0; a < 3; ++a) { r.lo[a] = fmin(r.lo[a], b.lo[a]); r.hi[a] = fmax(r.hi[a], b.hi[a]); }
+    }
+  }
+  out[t] = r;
+}
+
+void launch_gc_pyramid_level(const Pyr3Level& child, Box3* out, int nx, int ny, cudaStream_t st)
+{
+  const long long n = (long long)nx * ny;
+  ++g_launches;
+  gc_pyramid_level_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(child, out, nx, ny);
+}
+
+__device__ __forceinline__ bool boxes_meet(const Box3& a, const Box3& b)
+{
+  return a.lo[0] <= b.hi[0] && b.lo[0] <= a.hi[0] && a.lo[1] <= b.hi[1] && b.lo[1] <= a.hi[1] &&
+         a.lo[2] <= b.hi[2] && b.lo[2] <= a.hi[2];
+}
+
+constexpr int kGcStack = 3 * kMaxLevels + 8;
+
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+gc_candidate_kernel(GcCells src, long long s0, long long ns, const double* __restrict__ mask, Pyramid3 pyr,
+                    const uint32_t* __restrict__ pair_off, uint32_t* __restrict__ cnt, int2* __restrict__ pairs, int* err)
+{
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= ns) return;
+  const long long s = s0 + t;
+  uint32_t n = 0;
+  const uint32_t base = FILL ? pair_off[t] : 0u;
+  if (mask == nullptr || mask[s] > kMaskThresh) {                          // create_xgrid.c:1419
+    const Box3 sb = load_box3(src.box + s);
+    unsigned long long stack[kGcStack];
+    int sp = 0;
+    const int top = pyr.nlev - 1;
+    {
+      const Pyr3Level& L = pyr.lev[top];
+      for (int iy = 0; iy < L.ny; ++iy)
+        for (int ix = 0; ix < L.nx; ++ix) {
+          const long long q = (long long)iy * L.nx + ix;
+          if (!boxes_meet(load_box3(L.box + q), sb)) continue;
+          if (top == 0) { if (FILL) pairs[base + n] = make_int2((int)t, (int)q); ++n; }
+          else stack[sp++] = ((unsigned long long)top << 58) | ((unsigned long long)iy << 29) | (unsigned long long)ix;
+        }
+    }
+    while (sp > 0) {
+      const unsigned long long e = stack[--sp];
+      const int lev = (int)(e >> 58) - 1;
+      const int py = (int)((e >> 29) & 0x1fffffffull), px = (int)(e & 0x1fffffffull);
+      const Pyr3Level& L = pyr.lev[lev];
+      for (int dy = 0; dy < 2; ++dy) {
+        const int cy = 2 * py + dy;
+        if (cy >= L.ny) continue;
+        for (int dx = 0; dx < 2; ++dx) {
+          const int cx = 2 * px + dx;
+          if (cx >= L.nx) continue;
+          const long long q = (long long)cy * L.nx + cx;
+          if (!boxes_meet(load_box3(L.box + q), sb)) continue;
+          if (lev == 0) { if (FILL) pairs[base + n] = make_int2((int)t, (int)q); ++n; }
+          else if (sp < kGcStack) stack[sp++] = ((unsigned long long)lev << 58) | ((unsigned long long)cy << 29) | (unsigned long long)cx;
+          else atomicOr(err, kErrStackOverflow);
+        }
+      }
+    }
+  }
+  if (!FILL) cnt[t] = n;
+}
+
+void launch_gc_candidates(bool fill, const GcCells& src, long long s0, long long ns, const double* mask, const Pyramid3& pyr,
+                          const uint32_t* pair_off, uint32_t* cnt, int2* pairs, int* err, cudaStream_t st)
+{
+  if (ns <= 0) return;
+  const unsigned blocks = (unsigned)((ns + 127) / 128);
+  ++g_launches;
+  if (fill) gc_candidate_kernel<true><<<blocks, 128, 0, st>>>(src, s0, ns, mask, pyr, pair_off, cnt, pairs, err);
+  else      gc_candidate_kernel<false><<<blocks, 128, 0, st>>>(src, s0, ns, mask, pyr, pair_off, cnt, pairs, err);
+}
+
+__device__ __forceinline__ void load_cell(const GcCells& c, long long g, gc::V3* v)
+{
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    v[k] = gc::V3{c.v[(long long)(3 * k + 0) * c.ncell + g], c.v[(long long)(3 * k + 1) * c.ncell + g], c.v[(long long)(3 * k + 2) * c.ncell + g]};
+}
+
+__global__ void __launch_bounds__(64)
+gc_clip_kernel(GcCells src, GcCells dst, const double* __restrict__ mask, const int2* __restrict__ pairs,
+               unsigned long long npairs, long long s0, double* __restrict__ parea, uint32_t* __restrict__ cnt, int* err)
+{
+  const unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (p >= npairs) return;
+  const int2 pr = pairs[p];
+  const long long s = s0 + pr.x, d = pr.y;
+  gc::V3 a[4], b[4], out[gc::kPoly];
+  load_cell(src, s, a);
+  load_cell(dst, d, b);
+  const int n_out = gc::clip_great_circle(a, 4, b, 4, out);
+  double keep = 0.0;
+  if (n_out < 0) {
+    atomicOr(err, n_out == gc::kErrNotConvex ? kErrGcNotConvex : (n_out == gc::kErrPool ? kErrGcNodePool : kErrGcWalk));
+  } else if (n_out > 0) {
+    const double m = mask ? mask[s] : 1.0;
+    const double xarea = gc::great_circle_area(n_out, [&](int k) { return out[k]; }) * m;      // :1438
+    const double a1 = src.area[s], a2 = dst.area[d];
+    const double min_area = (a1 < a2) ? a1 : a2;                                               // :1439
+    if (xarea / min_area > kAreaRatioThresh) keep = xarea;                                     // :1440
+  }
+  parea[p] = keep;
+  if (keep > 0.0) atomicAdd(&cnt[pr.x], 1u);
+}
+
+void launch_gc_clip(const GcCells& src, const GcCells& dst, const double* mask, const int2* pairs, unsigned long long npairs,
+                    long long s0, double* parea, uint32_t* cnt, int* err, cudaStream_t st)
+{
+  if (npairs == 0) return;
+  ++g_launches;
+  gc_clip_kernel<<<(unsigned)((npairs + 63) / 64), 64, 0, st>>>(src, dst, mask, pairs, npairs, s0, parea, cnt, err);
+}
+
+}  // namespace xgb
+
+// host build of the same clip, for CPU tests against the compiled reference (include/xgrid_b200.h, Part 3)
+extern "C" int xgb_gc_clip_host(const double* x1, const double* y1, const double* z1, int n1,
+                                const double* x2, const double* y2, const double* z2, int n2,
+                                double* xo, double* yo, double* zo, double* area)
+{
+  using namespace xgb;
+  if (n1 > gc::kRing || n2 > gc::kRing) return gc::kErrPool;
+  gc::V3 a[gc::kRing], b[gc::kRing], out[gc::kPoly];
+  for (int k = 0; k < n1; ++k) a[k] = gc::V3{x1[k], y1[k], z1[k]};
+  for (int k = 0; k < n2; ++k) b[k] = gc::V3{x2[k], y2[k], z2[k]};
+  const int n = gc::clip_great_circle(a, n1, b, n2, out);
+  for (int k = 0; k < n; ++k) { xo[k] = out[k].x; yo[k] = out[k].y; zo[k] = out[k].z; }
+  if (area) *area = (n > 0) ? gc::great_circle_area(n, [&](int k) { return out[k]; }) : 0.0;
+  return n;
+}

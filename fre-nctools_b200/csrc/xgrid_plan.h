@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <vector>
 #include "xgrid_internal.h"
+#include "xgrid_gc.h"
 
 // grow-only device allocation
 struct DevBuf {
@@ -35,7 +36,9 @@ struct xgb_plan {
 
   // great-circle extras (cartesian vertices, spherical-excess areas)
   bool gc_src_ready = false, gc_dst_ready = false;
-  DevBuf gc_src_xyz, gc_dst_xyz;
+  DevBuf gc_src_xyz, gc_dst_xyz, gc_pyr_store;
+  xgb::GcCells gc_src{}, gc_dst{};
+  xgb::Pyramid3 gc_pyr{};
 
   // work space
   DevBuf cnt, pair_off, out_off, pairs, parea, pclon, pclat, scan_tmp, bounds_dev;

@@ -41,6 +41,20 @@ int create_xgrid_2dx2d_order2(const int *nlon_in, const int *nlat_in, const int 
                               const double *mask_in, int *i_in, int *j_in, int *i_out, int *j_out,
                               double *xgrid_area, double *xgrid_clon, double *xgrid_clat);
 
+/* create_xgrid.h:41  (create_xgrid.c:98-137) — spherical-excess cell areas of the great-circle path */
+void get_grid_great_circle_area(const int *nlon, const int *nlat, const double *lon, const double *lat, double *area);
+
+/* create_xgrid.h:78-80  (create_xgrid.c:1366-1466) — great-circle clipping; xgrid_clon/clat are zero-filled as in the
+ * reference (:1444-1445) */
+int create_xgrid_great_circle(const int *nlon_in, const int *nlat_in, const int *nlon_out, const int *nlat_out,
+                              const double *lon_in, const double *lat_in, const double *lon_out, const double *lat_out,
+                              const double *mask_in, int *i_in, int *j_in, int *i_out, int *j_out,
+                              double *xgrid_area, double *xgrid_clon, double *xgrid_clat);
+int create_xgrid_great_circle_(const int *nlon_in, const int *nlat_in, const int *nlon_out, const int *nlat_out,
+                               const double *lon_in, const double *lat_in, const double *lon_out, const double *lat_out,
+                               const double *mask_in, int *i_in, int *j_in, int *i_out, int *j_out,
+                               double *xgrid_area, double *xgrid_clon, double *xgrid_clat);
+
 /* Fortran-callable twins (create_xgrid.c:608, :881) */
 int create_xgrid_2dx2d_order1_(const int *nlon_in, const int *nlat_in, const int *nlon_out, const int *nlat_out,
                                const double *lon_in, const double *lat_in, const double *lon_out, const double *lat_out,
@@ -134,6 +148,9 @@ int xgb_plan_result_host(xgb_plan *p, int *t_in, int *i_in, int *j_in, int *i_ou
                          double *area, double *di, double *dj);
 int xgb_plan_result_centroids_host(xgb_plan *p, double *xgrid_clon, double *xgrid_clat);
 
+/* get_grid_great_circle_area on the device: which = 0 source cells (concatenated), 1 destination cells */
+int xgb_plan_great_circle_area_host(xgb_plan *p, int which, double *area);
+
 /* Cell areas computed on the device (get_grid_area): source cells concatenated / destination cells. */
 int xgb_plan_src_area_host(xgb_plan *p, double *area);
 int xgb_plan_dst_area_host(xgb_plan *p, double *area);
@@ -206,6 +223,12 @@ int xgb_cubed_sphere_grid(int ni, double *lonc, double *latc, double *lont, doub
 /* fregrid --nlon/--nlat regular output grid (fregrid_util.c:588-603); degrees in, radians out. */
 int xgb_latlon_grid(int nlon, int nlat, double lonbegin, double lonend, double latbegin, double latend,
                     double *lonc, double *latc);
+/* host build of the device great-circle clip (csrc/gc_clip.cuh: clip_2dx2d_great_circle + great_circle_area), so
+ * CPU tests can run the product's algorithm against the compiled reference.  Returns the vertex count (< 0: the
+ * condition on which the reference aborts). */
+int xgb_gc_clip_host(const double *x1, const double *y1, const double *z1, int n1,
+                     const double *x2, const double *y2, const double *z2, int n2,
+                     double *xo, double *yo, double *zo, double *area);
 /* sin/cos/sincos of csrc/ref_trig.cuh evaluated by the host build and by a device kernel (host pointers). */
 void xgb_ref_trig_host(long long n, const double *x, double *s, double *c, double *ss, double *sc);
 int  xgb_ref_trig_device(long long n, const double *x, double *s, double *c, double *ss, double *sc);

@@ -154,6 +154,37 @@ def make_apply(tag, ni, nlon, nlat):
     print(f"apply_{tag}.npz: nxgrid", r1["nxgrid"], r2["nxgrid"])
 
 
+def make_gc():
+    """great-circle path: polygon pairs through the reference's clip_2dx2d_great_circle + great_circle_area, and whole
+    exchange grids (cubed sphere and a small tripolar ocean grid -> lat-lon) through create_xgrid_great_circle"""
+    cases = xgtest.gc_quad_cases(1000, seed=20260102)
+    n = len(cases)
+    d = {"p1": np.zeros((n, 3, 4)), "p2": np.zeros((n, 3, 4)), "n_out": np.zeros(n, np.int32), "out": np.zeros((n, 3, 10)),
+         "area": np.zeros(n)}
+    for k, (a, b) in enumerate(cases):
+        d["p1"][k] = np.stack(a); d["p2"][k] = np.stack(b)
+        o = [np.zeros(60) for _ in range(3)]
+        m = R.clip_2dx2d_great_circle(*a, 4, *b, 4, *o)
+        d["n_out"][k] = m
+        for c in range(3):
+            d["out"][k, c] = o[c][:10]
+        if m > 0:
+            d["area"][k] = R.great_circle_area(m, *o)
+    np.savez_compressed(os.path.join(HERE, "gc_polys.npz"), **d)
+    print("gc_polys.npz:", n, "cases;", int((d["n_out"] > 0).sum()), "non-empty; max n_out", d["n_out"].max())
+    GC = xgtest.GREAT_CIRCLE
+    c8 = xgtest.ref_cubed_sphere(8)
+    lo, la = latlon(36, 18)
+    make_xgrid("gc_c8_36x18", c8[0], c8[1], lo, la, 1 | GC)
+    tl, ta = xgtest.tripolar_grid(48, 36)
+    make_xgrid("gc_tripolar24x18_36x18", [tl], [ta], lo, la, 1 | GC)
+    a = np.zeros(24 * 18)
+    R.get_grid_great_circle_area(C.byref(C.c_int(24)), C.byref(C.c_int(18)), np.ascontiguousarray(tl).reshape(-1), np.ascontiguousarray(ta).reshape(-1), a)
+    b = np.zeros(36 * 18)
+    R.get_grid_great_circle_area(C.byref(C.c_int(36)), C.byref(C.c_int(18)), lo.reshape(-1), la.reshape(-1), b)
+    np.savez_compressed(os.path.join(HERE, "gc_areas.npz"), tripolar=a, latlon=b)
+
+
 def latlon(nlon, nlat, lon0=0.0, lon1=360.0, lat0=-90.0, lat1=90.0):
     lon = np.array([(lon0 + i * ((lon1 - lon0) / nlon)) * D2R for i in range(nlon + 1)])
     lat = np.array([(lat0 + j * ((lat1 - lat0) / nlat)) * D2R for j in range(nlat + 1)])
@@ -176,6 +207,7 @@ def main():
     c10 = xgtest.ref_cubed_sphere(10)
     make_xgrid("c12_to_c10tile3_o2", c12[0], c12[1], c10[0][2], c10[1][2], 2)
     make_apply("c8_36x18", 8, 36, 18)
+    make_gc()
 
 
 if __name__ == "__main__":

@@ -1,0 +1,110 @@
+"""GPU parity tests of the great-circle exchange-grid path (create_xgrid_great_circle through the C ABI) against the CPU
+oracle and the reference's golden vectors.  Bar: integer cell lists bit-exact in the reference's emission order;
+xgrid_area to 4e-15 steradian absolute — the spherical excess is a sum of O(1) angles minus (n-2)*pi, each angle an
+acosl() rounded to double in the reference (x87), so one ulp of one angle is 2e-16 sr whatever the size of the cell
+(see csrc/gc_clip.cuh); relative to the cell that is 1e-11 for a quarter-degree cell."""
+import os
+
+import numpy as np
+import pytest
+
+import xgtest
+
+pytestmark = pytest.mark.gpu
+
+R2 = 6371000.0 ** 2
+AREA_ATOL_SR = 4e-15
+GC = xgtest.GREAT_CIRCLE
+
+
+def _gen(pkg, lonc, latc, lon2, lat2, mask=None):
+    plan = pkg.XgridPlan(0)
+    plan.set_dst(lon2, lat2)
+    plan.set_src(lonc, latc, mask)
+    n = plan.generate(1 | GC)
+    got = plan.result_host()
+    got["nxgrid"] = n
+    got["npairs"] = plan.npairs
+    got["area_src"] = plan.great_circle_area("src"); got["area_dst"] = plan.great_circle_area("dst")
+    plan.close()
+    return got
+
+
+def _check(got, ref):
+    assert got["nxgrid"] == ref["nxgrid"], (got["nxgrid"], ref["nxgrid"])
+    for k in ("t_in", "i_in", "j_in", "i_out", "j_out"):
+        assert np.array_equal(got[k], ref[k]), k
+    d = np.abs(got["area"] - ref["area"]) / R2
+    assert d.max(initial=0.0) <= AREA_ATOL_SR, d.max()
+    return float(np.mean(got["area"] == ref["area"]))
+
+
+@pytest.mark.parametrize("tag", ["gc_c8_36x18", "gc_tripolar24x18_36x18"])
+def test_gc_matches_reference_golden(pkg, tag):
+    g = np.load(os.path.join(xgtest.GOLDEN_DIR, f"xgrid_{tag}.npz"))
+    nx, ny = g["nx"], g["ny"]
+    lons, lats, off = [], [], 0
+    for t in range(nx.size):
+        nv = (nx[t] + 1) * (ny[t] + 1)
+        lons.append(g["lon_in"][off:off + nv].reshape(ny[t] + 1, nx[t] + 1)); lats.append(g["lat_in"][off:off + nv].reshape(ny[t] + 1, nx[t] + 1))
+        off += nv
+    got = _gen(pkg, lons, lats, g["lon_out"], g["lat_out"])
+    ref = {k: g[k] for k in ("t_in", "i_in", "j_in", "i_out", "j_out", "area")}
+    ref["nxgrid"] = g["area"].size
+    _check(got, ref)
+    if tag.startswith("gc_tripolar"):
+        a = np.load(os.path.join(xgtest.GOLDEN_DIR, "gc_areas.npz"))
+        assert np.max(np.abs(got["area_src"] - a["tripolar"])) / R2 <= AREA_ATOL_SR
+        assert np.max(np.abs(got["area_dst"] - a["latlon"])) / R2 <= AREA_ATOL_SR
+
+
+@pytest.mark.parametrize("ni,nlon,nlat", [(16, 90, 45), (48, 360, 180)])
+def test_gc_cubed_sphere_matches_oracle(pkg, ni, nlon, nlat):
+    """C48 -> 1 degree: SURVEY 8c sanity value nxgrid 146016 for the great-circle algorithm"""
+    lonc, latc = pkg.cubed_sphere_grid(ni)
+    lon2, lat2 = pkg.latlon_grid(nlon, nlat)
+    got = _gen(pkg, lonc, latc, lon2, lat2)
+    ref = xgtest.oracle_setup(lonc, latc, lon2, lat2, 1 | GC)
+    same = _check(got, ref)
+    if ni == 48:
+        assert got["nxgrid"] == 146016
+    assert abs(got["area"].sum() / (4 * np.pi * R2) - 1) < 1e-11
+    assert same > 0.5                                   # most areas are bit-identical; the rest differ by an ulp of one angle
+
+
+def test_gc_latlon_to_latlon_shared_edges_and_mask(pkg):
+    """vertices of one grid lying exactly on the sides of the other (the fragile inside/outside decisions of insidePolygon),
+    pole triangles on both sides, and a source mask"""
+    lon1, lat1 = pkg.latlon_grid(40, 20)
+    lon2, lat2 = pkg.latlon_grid(60, 30)
+    rng = np.random.default_rng(3)
+    mask = (rng.uniform(size=40 * 20) > 0.2).astype(np.float64)
+    got = _gen(pkg, [lon1], [lat1], lon2, lat2, mask)
+    L = xgtest.oracle_lib()
+    cap = 40000
+    out = {k: np.zeros(cap, np.int32) for k in ("i_in", "j_in", "i_out", "j_out")}
+    area = np.zeros(cap)
+    n = L.orc_create_xgrid_great_circle(40, 20, 60, 30, lon1.reshape(-1), lat1.reshape(-1), lon2.reshape(-1), lat2.reshape(-1), mask, cap,
+                                        out["i_in"], out["j_in"], out["i_out"], out["j_out"], area, None, None)
+    assert n == got["nxgrid"], (n, got["nxgrid"])
+    for k in out:
+        assert np.array_equal(got[k], out[k][:n]), k
+    assert np.max(np.abs(got["area"] - area[:n])) / R2 <= AREA_ATOL_SR
+
+
+def test_gc_reference_signature_entry_points(pkg):
+    lonc, latc = pkg.cubed_sphere_grid(8)
+    lon2, lat2 = pkg.latlon_grid(36, 18)
+    r = pkg.create_xgrid_great_circle(lonc[2], latc[2], lon2, lat2)
+    ref = xgtest.oracle_setup([lonc[2]], [latc[2]], lon2, lat2, 1 | GC)
+    assert r[0] == ref["nxgrid"]
+    for a, k in zip(r[1:5], ("i_in", "j_in", "i_out", "j_out")):
+        assert np.array_equal(a, ref[k]), k
+    assert np.max(np.abs(r[5] - ref["area"])) / R2 <= AREA_ATOL_SR
+    assert not r[6].any() and not r[7].any()
+    a = pkg.get_grid_great_circle_area(lon2, lat2)
+    want = np.zeros(36 * 18)
+    xgtest.oracle_lib().orc_get_grid_great_circle_area(36, 18, lon2.reshape(-1), lat2.reshape(-1), want)
+    assert np.max(np.abs(a.reshape(-1) - want)) / R2 <= AREA_ATOL_SR
+    with pytest.raises(pkg.XgridError):                 # fregrid.c:763: great circle is first order only
+        p = pkg.XgridPlan(0); p.set_dst(lon2, lat2); p.set_src(lonc, latc); p.generate(2 | GC)

@@ -55,6 +55,12 @@ def oracle_lib():
         L.orc_conserve_apply.argtypes = [C.c_int, C.c_long] + [ip] * 5 + [dp, vp, vp, C.c_int, ip, ip, dp, vp, vp, vp,
                                          C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, dp]
         L.orc_libm_trig.argtypes = [C.c_long] + [dp] * 5
+        L.orc_clip_2dx2d_great_circle.argtypes = [dp, dp, dp, C.c_int, dp, dp, dp, C.c_int, dp, dp, dp]
+        L.orc_great_circle_area.restype = C.c_double
+        L.orc_great_circle_area.argtypes = [C.c_int, dp, dp, dp]
+        L.orc_create_xgrid_great_circle.restype = C.c_long
+        L.orc_create_xgrid_great_circle.argtypes = [C.c_int] * 4 + [dp] * 5 + [C.c_long] + [ip] * 4 + [dp, vp, vp]
+        L.orc_get_grid_great_circle_area.argtypes = [C.c_int, C.c_int, dp, dp, dp]
         L.orc_grad_c2l.argtypes = [C.c_int, C.c_int] + [dp] * 14
         L.orc_grad_mask.argtypes = [C.c_int, C.c_int, dp, C.c_double, ip]
         L.orc_calc_c2l_grid_info.argtypes = [C.c_int, C.c_int] + [dp] * 15
@@ -130,6 +136,10 @@ def ref_lib():
         L.clip_2dx2d.argtypes = [dp, dp, C.c_int, dp, dp, C.c_int, dp, dp]
         L.get_grid_area.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), dp, dp, dp]
         pi_ = C.POINTER(C.c_int)
+        L.clip_2dx2d_great_circle.argtypes = [dp, dp, dp, C.c_int, dp, dp, dp, C.c_int, dp, dp, dp]
+        L.great_circle_area.restype = C.c_double
+        L.great_circle_area.argtypes = [C.c_int, dp, dp, dp]
+        L.get_grid_great_circle_area.argtypes = [pi_, pi_, dp, dp, dp]
         L.grad_c2l.argtypes = [pi_, pi_] + [dp] * 14 + [pi_] * 4
         L.calc_c2l_grid_info.argtypes = [pi_, pi_] + [dp] * 15 + [pi_] * 4
         _ref = L
@@ -404,3 +414,47 @@ def ref_apply(handle, order, data, nout, grad_x=None, grad_y=None, gmask=None, h
     L.ref_regrid_apply(handle, order, int(has_missing), float(missing), 0, 1, MONOTONIC if monotonic else 0,
                        np.ascontiguousarray(data, np.float64), ptr(gx), ptr(gy), ptr(gm), out)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# great-circle path helpers
+# ---------------------------------------------------------------------------------------------
+def ll2xyz(lon, lat):
+    return (np.ascontiguousarray(np.cos(lat) * np.cos(lon)), np.ascontiguousarray(np.cos(lat) * np.sin(lon)),
+            np.ascontiguousarray(np.sin(lat)))
+
+
+def gc_quad_cases(n, seed=1):
+    """pairs of spherical quads in the reference's clockwise corner order: generic overlaps, shared edges with vertices
+    lying on the other cell's edges, nested cells sharing a corner, identical cells, pole triangles"""
+    rng = np.random.default_rng(seed)
+    d2r = np.pi / 180
+
+    def quad(lon0, lat0, dlon, dlat, jit):
+        lon = np.array([lon0, lon0, lon0 + dlon, lon0 + dlon]) + rng.normal(0, jit, 4)
+        lat = np.clip(np.array([lat0, lat0 + dlat, lat0 + dlat, lat0]) + rng.normal(0, jit, 4), -90, 90)
+        return lon * d2r, lat * d2r
+    out = []
+    for it in range(n):
+        lon0 = rng.uniform(0, 355); lat0 = rng.uniform(-88, 84); d = rng.uniform(0.1, 3)
+        kind = it % 5
+        if kind == 0:
+            a = quad(lon0, lat0, d, d, 0.05 * d)
+            b = quad(lon0 + rng.uniform(-d, d), lat0 + rng.uniform(-d, d), d * rng.uniform(.5, 2), d * rng.uniform(.5, 2), 0)
+        elif kind == 1:
+            a = quad(lon0, lat0, d, d, 0); b = quad(lon0 + d / 2, lat0, d, d, 0)
+        elif kind == 2:
+            a = quad(lon0, lat0, d, d, 0); b = quad(lon0, lat0, d / 2, d / 2, 0)
+        elif kind == 3:
+            a = quad(lon0, lat0, d, d, 0); b = quad(lon0, lat0, d, d, 0)
+        else:                                               # pole row of a lat-lon grid (two corners coincide) vs a polar quad
+            a = quad(lon0, 90 - d, 2 * d, d, 0); b = quad(lon0 + d / 3, 90 - 1.5 * d, d, d, 0.02 * d)
+        out.append((ll2xyz(*a), ll2xyz(*b)))
+    return out
+
+
+def tripolar_grid(nx_s, ny_s, lat_join=65.0):
+    """make_hgrid tripolar grid through the compiled reference: supergrid nx_s x ny_s -> (lonc, latc) [ny_s/2+1, nx_s/2+1]"""
+    lonc = np.zeros((ny_s // 2 + 1, nx_s // 2 + 1)); latc = np.zeros_like(lonc)
+    ref_lib().ref_tripolar_grid(nx_s, ny_s, -280.0, 80.0, -82.0, 90.0, lat_join, lonc.reshape(-1), latc.reshape(-1))
+    return lonc, latc
