@@ -209,19 +209,33 @@ __device__ __forceinline__ double poly_ctrlon(const PolyView& p, int n, double c
 //     (both are do_sin(x, 0)); above that sin() takes another path and is evaluated separately.
 // ORDER == 1 evaluates poly_area only.
 // ---------------------------------------------------------------------------------------------
-template <int ORDER>
+// WARP: called by all 32 lanes of a converged warp (lanes without a polygon pass n = 0).  The edge loop then runs to the
+// warp's largest vertex count and the lanes are re-converged explicitly after every data-dependent section (the
+// sin/cos routines branch on the argument range), which the compiler does not do on its own across the inlined code.
+template <int ORDER, bool WARP = false>
 __device__ __forceinline__ void poly_moments(const PolyView& p, int n, double clon,
                                              double* area_out, double* ctrlon_out, double* ctrlat_out) {
   double aacc = 0.0, lonacc = 0.0, latacc = 0.0;
-  double xi = p.X(0), yi = p.Y(0);
+  double xi = 0.0, yi = 0.0;
+  if (n > 0) { xi = p.X(0); yi = p.Y(0); }
   const double x0 = xi, y0 = yi;
   double si = 0.0, ci = 0.0;
-  if (ORDER == 2) ref_sincos(yi, &si, &ci);
+  if (ORDER == 2 && n > 0) ref_sincos(yi, &si, &ci);
+  int nloop = n;
+  if (WARP) {
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+    nloop = __reduce_max_sync(0xffffffffu, n);
+#endif
+  }
   const double s0 = si, c0 = ci;
-  for (int i = 0; i < n; ++i) {
-    double xn, yn, sn = 0.0, cn = 0.0;
-    if (i + 1 < n) { xn = p.X(i + 1); yn = p.Y(i + 1); if (ORDER == 2) ref_sincos(yn, &sn, &cn); }
-    else { xn = x0; yn = y0; sn = s0; cn = c0; }
+  for (int i = 0; i < nloop; ++i) {
+    const bool act = !WARP || i < n;
+    double xn = x0, yn = y0, sn = s0, cn = c0;
+    if (act && i + 1 < n) { xn = p.X(i + 1); yn = p.Y(i + 1); if (ORDER == 2) ref_sincos(yn, &sn, &cn); }
+#if defined(__CUDA_ARCH__)
+    if (WARP) __syncwarp();
+#endif
     const double lat1 = yn, lat2 = yi;
     const double dx_raw = xn - xi;                       // x[ip]-x[i] == phi1-phi2
     double dxa = dx_raw;                                 // poly_area's wrapped dx (mosaic_util.c:429-432)
@@ -235,46 +249,61 @@ __device__ __forceinline__ void poly_moments(const PolyView& p, int n, double cl
     const bool flat_lat = (fabs(dy) < kSmall);           // fabs(hdy) < SMALL_VALUE (create_xgrid.c:2114)
 
     double s_avg = 0.0, c_avg = 0.0;
-    if (moving) ref_sincos(avg, &s_avg, &c_avg);
+    if (act && moving) ref_sincos(avg, &s_avg, &c_avg);
+#if defined(__CUDA_ARCH__)
+    if (WARP) __syncwarp();
+#endif
     double dat = 0.0;
-    if ((!pole_edge && !flat_area) || (moving && !flat_lat)) dat = ref_sin(dy) / dy;
-
-    if (pole_edge) {
-      aacc += kPi;                                       // mosaic_util.c:434-437
-    } else {
-      const uint32_t hi = (uint32_t)(trig::bits(avg) >> 32) & 0x7fffffffu;
-      const double sin_avg = (moving && hi < 0x3feb6000u) ? s_avg : ref_sin(avg);
-      if (flat_area) aacc -= dxa * sin_avg;
-      else           aacc -= dxa * sin_avg * dat;
-    }
-    if (moving) {
-      // poly_ctrlat (create_xgrid.c:2100-2118)
-      double dxl = dx_raw;
-      if (dxl > kPi)   dxl = dxl - 2.0 * kPi;
-      if (dxl <= -kPi) dxl = dxl + 2.0 * kPi;
-      if (flat_lat) latacc -= dxl * (2 * c_avg + lat2 * s_avg - cn);
-      else          latacc -= dxl * (dat * (2 * c_avg + lat2 * s_avg) - cn);
-      // poly_ctrlon (create_xgrid.c:2176-2215)
-      const double f1 = 0.5 * (cn * sn + lat1);
-      const double f2 = 0.5 * (ci * si + lat2);
-      double dphi = dx_raw;
-      if (dphi > kPi)  dphi = dphi - 2.0 * kPi;
-      if (dphi < -kPi) dphi = dphi + 2.0 * kPi;
-      double dphi1 = xn - clon;
-      if (dphi1 > kPi)  dphi1 -= 2.0 * kPi;
-      if (dphi1 < -kPi) dphi1 += 2.0 * kPi;
-      double dphi2 = xi - clon;
-      if (dphi2 > kPi)  dphi2 -= 2.0 * kPi;
-      if (dphi2 < -kPi) dphi2 += 2.0 * kPi;
-      if (fabs(dphi2 - dphi1) < kPi) {
-        lonacc -= dphi * (dphi1 * f1 + dphi2 * f2) / 2.0;
+    if (act && ((!pole_edge && !flat_area) || (moving && !flat_lat))) dat = ref_sin(dy) / dy;
+#if defined(__CUDA_ARCH__)
+    if (WARP) __syncwarp();
+#endif
+    const uint32_t hi = (uint32_t)(trig::bits(avg) >> 32) & 0x7fffffffu;
+    const bool own_sin = act && !pole_edge && !(moving && hi < 0x3feb6000u);
+    double sin_avg = s_avg;
+    if (own_sin) sin_avg = ref_sin(avg);
+#if defined(__CUDA_ARCH__)
+    if (WARP) __syncwarp();
+#endif
+    if (act) {
+      if (pole_edge) {
+        aacc += kPi;                                     // mosaic_util.c:434-437
       } else {
-        const double fac = (dphi1 > 0.0) ? kPi : -kPi;
-        const double fint = f1 + (f2 - f1) * (fac - dphi1) / fabs(dphi);
-        lonacc -= 0.5 * dphi1 * (dphi1 - fac) * f1 - 0.5 * dphi2 * (dphi2 + fac) * f2 + 0.5 * fac * (dphi1 + dphi2) * fint;
+        if (flat_area) aacc -= dxa * sin_avg;
+        else           aacc -= dxa * sin_avg * dat;
       }
+      if (moving) {
+        // poly_ctrlat (create_xgrid.c:2100-2118)
+        double dxl = dx_raw;
+        if (dxl > kPi)   dxl = dxl - 2.0 * kPi;
+        if (dxl <= -kPi) dxl = dxl + 2.0 * kPi;
+        if (flat_lat) latacc -= dxl * (2 * c_avg + lat2 * s_avg - cn);
+        else          latacc -= dxl * (dat * (2 * c_avg + lat2 * s_avg) - cn);
+        // poly_ctrlon (create_xgrid.c:2176-2215)
+        const double f1 = 0.5 * (cn * sn + lat1);
+        const double f2 = 0.5 * (ci * si + lat2);
+        double dphi = dx_raw;
+        if (dphi > kPi)  dphi = dphi - 2.0 * kPi;
+        if (dphi < -kPi) dphi = dphi + 2.0 * kPi;
+        double dphi1 = xn - clon;
+        if (dphi1 > kPi)  dphi1 -= 2.0 * kPi;
+        if (dphi1 < -kPi) dphi1 += 2.0 * kPi;
+        double dphi2 = xi - clon;
+        if (dphi2 > kPi)  dphi2 -= 2.0 * kPi;
+        if (dphi2 < -kPi) dphi2 += 2.0 * kPi;
+        if (fabs(dphi2 - dphi1) < kPi) {
+          lonacc -= dphi * (dphi1 * f1 + dphi2 * f2) / 2.0;
+        } else {
+          const double fac = (dphi1 > 0.0) ? kPi : -kPi;
+          const double fint = f1 + (f2 - f1) * (fac - dphi1) / fabs(dphi);
+          lonacc -= 0.5 * dphi1 * (dphi1 - fac) * f1 - 0.5 * dphi2 * (dphi2 + fac) * f2 + 0.5 * fac * (dphi1 + dphi2) * fint;
+        }
+      }
+      xi = xn; yi = yn; si = sn; ci = cn;
     }
-    xi = xn; yi = yn; si = sn; ci = cn;
+#if defined(__CUDA_ARCH__)
+    if (WARP) __syncwarp();
+#endif
   }
   *area_out = (aacc < 0) ? -aacc * kRadius * kRadius : aacc * kRadius * kRadius;
   if (ORDER == 2) { *ctrlon_out = lonacc * kRadius * kRadius; *ctrlat_out = latacc * kRadius * kRadius; }

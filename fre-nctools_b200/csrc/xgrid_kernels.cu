@@ -422,64 +422,72 @@ __device__ __forceinline__ int clip_cell(double* ax, double* ay, double* bx, dou
   return np;
 }
 
-// Same algorithm, restructured for SIMT execution (shared-memory polygons of at most kFastCap vertices):
-// per clip edge (1) inside-flags of all vertices as a bit mask, (2) the two edge crossings computed by all
-// lanes together instead of inside the divergent vertex loop, (3) assembly of the output list in the
-// reference's order (crossing before vertex k, then vertex k if inside).  An edge that keeps every vertex
-// leaves the polygon untouched, so it is skipped without copying.  Every emitted number is produced by the
-// same operations as in clip_cell, so results are bit-identical.  Returns -1 (caller falls back to the
-// generic routine) when a stage has more than two crossings (non-convex input) or would exceed kFastCap.
-__device__ __forceinline__ int clip_cell_fast(double* ax, double* ay, double* bx, double* by, int n1,
-                                              const CellSet& dst, long long d, int n2, int shift, bool wrap,
+// Same algorithm, restructured for SIMT execution.  The polygon (at most kFastCap vertices) lives in shared memory and,
+// between cuts, in registers; the destination cell's vertices are staged in shared memory once.  Per destination edge:
+// (A) the inside flags of all vertices as a bit mask, straight-line predicated code; edges that keep every vertex leave
+// the polygon untouched and are skipped without copying, so a thread runs through them until it meets an edge that
+// cuts; (B) all threads of the warp that have a cut pending do it together: the two crossings, then every kept vertex
+// and the crossings are stored at their final position (rank among kept vertices + crossings emitted before), which
+// reproduces the reference's output order (crossing before vertex k, then vertex k if inside, create_xgrid.c:1306-1330).
+// Every emitted number is produced by the same operations as in clip_cell, so results are bit-identical.  Returns -1
+// (caller falls back to the generic routine) when a stage has more than two crossings (non-convex input) or would
+// exceed kFastCap vertices.
+__device__ __forceinline__ int clip_cell_fast(double* ax, double* ay, double* bx, double* by,
+                                              const double (&ex)[4], const double (&ey)[4], int n1, int n2,
                                               double** rx, double** ry, int* err)
 {
-  constexpr int stride = kClipThreads;
+  constexpr int S = kClipThreads;
   double *cx = ax, *cy = ay, *ox = bx, *oy = by;
-  int np = n1;
-  double ex0 = dst_vertex_lon(dst, d, n2 - 1, shift, wrap);
-  double ey0 = dst.vy[(long long)(n2 - 1) * dst.ncell + d];
-  for (int e = 0; e < n2; ++e) {
-    const double ex1 = dst_vertex_lon(dst, d, e, shift, wrap);
-    const double ey1 = dst.vy[(long long)e * dst.ncell + d];
-    const double edy = ey1 - ey0, endx = ex0 - ex1;
-    unsigned in = 0;
-    for (int k = 0; k < np; ++k) {
-      const double qx = cx[k * stride], qy = cy[k * stride];
-      in |= (unsigned)(((qx - ex0) * edy + endx * (qy - ey0)) <= 1.e-12) << k;
-    }
-    const unsigned full = (1u << np) - 1u;
-    if (in == 0u) { *rx = ox; *ry = oy; return 0; }
-    if (in != full) {
-      const unsigned prev = ((in << 1) | (in >> (np - 1))) & full;      // inside flag of vertex k-1 (cyclic)
-      const unsigned cross = in ^ prev;
-      if (__popc(cross) != 2 || np + 1 > kFastCap) return -1;
-      const int k0 = __ffs(cross) - 1, k1 = 31 - __clz(cross);
-      double X[2], Y[2];
+  int np = (n2 > 4) ? -1 : n1;                                    // pole-adjacent destination cells: generic routine
+  double ex0 = (n2 == 4) ? ex[3] : ex[2], ey0 = (n2 == 4) ? ey[3] : ey[2];
+  // single exit: np <= 0 (empty, or -1 = needs the generic routine) simply skips the remaining edges, so the warp
+  // leaves this function converged
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int k = c ? k1 : k0;
-        const int km = (k == 0) ? np - 1 : k - 1;
-        const double px = cx[km * stride], py = cy[km * stride];
-        const double qx = cx[k * stride], qy = cy[k * stride];
-        const double dy1 = qy - py, dy2 = ey1 - ey0, dx1 = qx - px, dx2 = ex1 - ex0;
-        const double ds1 = py * qx - qy * px, ds2 = ey0 * ex1 - ey1 * ex0;
-        const double determ = dy2 * dx1 - dy1 * dx2;
-        if (fabs(determ) < 1.0e-30) atomicOr(err, kErrParallelEdges);
-        X[c] = (dx2 * ds1 - dx1 * ds2) / determ;
-        Y[c] = (dy2 * ds1 - dy1 * ds2) / determ;
-      }
-      int no = 0;
+  for (int e = 0; e < 4; ++e) {
+    if (e < n2 && np > 0) {
+      const double ex1 = ex[e], ey1 = ey[e];
+      const double edy = ey1 - ey0, endx = ex0 - ex1;             // (y1-y0), (x0-x1) of inside_edge
+      unsigned in = 0;
       for (int k = 0; k < np; ++k) {
-        if (k == k0)      { ox[no * stride] = X[0]; oy[no * stride] = Y[0]; ++no; }
-        else if (k == k1) { ox[no * stride] = X[1]; oy[no * stride] = Y[1]; ++no; }
-        if ((in >> k) & 1u) { ox[no * stride] = cx[k * stride]; oy[no * stride] = cy[k * stride]; ++no; }
+        const double qx = cx[k * S], qy = cy[k * S];
+        in |= (unsigned)(((qx - ex0) * edy + endx * (qy - ey0)) <= 1.e-12) << k;
       }
-      np = no;
-      double* t;
-      t = cx; cx = ox; ox = t;
-      t = cy; cy = oy; oy = t;
+      const unsigned full = (1u << np) - 1u;
+      if (in == 0u) np = 0;
+      else if (in != full) {
+        const unsigned prev = ((in << 1) | (in >> (np - 1))) & full;  // inside flag of vertex k-1 (cyclic)
+        const unsigned cross = in ^ prev;
+        if (__popc(cross) != 2 || np + 1 > kFastCap) np = -1;
+        else {
+          const int k0 = __ffs(cross) - 1, k1 = 31 - __clz(cross);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int k = c ? k1 : k0;
+            const int km = (k == 0) ? np - 1 : k - 1;
+            const double px = cx[km * S], py = cy[km * S];
+            const double qx = cx[k * S], qy = cy[k * S];
+            const double dy1 = qy - py, dy2 = ey1 - ey0, dx1 = qx - px, dx2 = ex1 - ex0;
+            const double ds1 = py * qx - qy * px, ds2 = ey0 * ex1 - ey1 * ex0;
+            const double determ = dy2 * dx1 - dy1 * dx2;
+            if (fabs(determ) < 1.0e-30) atomicOr(err, kErrParallelEdges);
+            const int pc = __popc(in & ((1u << k) - 1u)) + c;     // after the kept vertices before k (+ crossing 0)
+            ox[pc * S] = (dx2 * ds1 - dx1 * ds2) / determ;
+            oy[pc * S] = (dy2 * ds1 - dy1 * ds2) / determ;
+          }
+          for (int k = 0; k < np; ++k) {
+            const double qx = cx[k * S], qy = cy[k * S];
+            const int pos = __popc(in & ((1u << k) - 1u)) + (k >= k0) + (k >= k1);
+            if ((in >> k) & 1u) { ox[pos * S] = qx; oy[pos * S] = qy; }
+          }
+          np = __popc(in) + 2;
+          double* t;
+          t = cx; cx = ox; ox = t;
+          t = cy; cy = oy; oy = t;
+        }
+      }
+      ex0 = ex1; ey0 = ey1;
     }
-    ex0 = ex1; ey0 = ey1;
+    __syncwarp();
   }
   *rx = cx; *ry = cy;
   return np;
@@ -512,30 +520,40 @@ clip_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const int
             double* __restrict__ parea, double* __restrict__ pclon, double* __restrict__ pclat,
             uint32_t* __restrict__ cnt, int* err)
 {
-  __shared__ double sm[4 * kFastCap * kClipThreads];            // [buf][coord][vertex][thread]
+  __shared__ double sm[4 * kFastCap * kClipThreads];            // [A.x A.y B.x B.y][vertex][thread]
   const unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-  if (p >= npairs) return;
-  const int2 pr = pairs[p];
+  const bool valid = p < npairs;                                  // no early exit: the warp reconverges explicitly below
+  const int2 pr = valid ? pairs[p] : make_int2(0, 0);
   const long long s = s0 + pr.x, d = pr.y;
-  const int n1 = src.nv[s], n2 = dst.nv[d];
-  const double s_xavg = src.xavg[s];
-  const double dxavg = dst.xavg[d] - s_xavg;
+  const int n1 = valid ? src.nv[s] : 0, n2 = valid ? dst.nv[d] : 0;
+  const double s_xavg = valid ? src.xavg[s] : 0.0;
+  const double dxavg = valid ? dst.xavg[d] - s_xavg : 0.0;
   const int shift = (dxavg < -kPi) ? 1 : ((dxavg > kPi) ? -1 : 0);
 
   const int stride = kClipThreads;
+  constexpr int plane = kFastCap * kClipThreads;
   double* ax = sm + threadIdx.x;
-  double* ay = ax + kFastCap * kClipThreads;
-  double* bx = ay + kFastCap * kClipThreads;
-  double* by = bx + kFastCap * kClipThreads;
+  double* ay = ax + plane;
+  double* bx = ay + plane;
+  double* by = bx + plane;
 
-  double *rx = nullptr, *ry = nullptr;
+  double *rx = ax, *ry = ay;
   int rstride = stride;
-  int n_out;
+  int n_out = 0;
   double loc[4 * kSlowCap];                                       // only touched on the slow path
-  {
+  double ex[4] = {0.0, 0.0, 0.0, 0.0}, ey[4] = {0.0, 0.0, 0.0, 0.0};   // destination vertices as clip_2dx2d sees them
+  if (valid) {
     const bool wrap = load_src_poly(src, s, n1, ax, ay, stride);
-    n_out = clip_cell_fast(ax, ay, bx, by, n1, dst, d, n2, shift, wrap, &rx, &ry, err);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int kk = (k < n2) ? k : 0;
+      ex[k] = dst_vertex_lon(dst, d, kk, shift, wrap);
+      ey[k] = dst.vy[(long long)kk * dst.ncell + d];
+    }
   }
+  __syncwarp();
+  n_out = clip_cell_fast(ax, ay, bx, by, ex, ey, n1, n2, &rx, &ry, err);   // all lanes; n2 == 0 does nothing
+  __syncwarp();
   if (n_out < 0) {
     // rare: more than 8 vertices at some stage (pole cells, non-convex cells) -> reference-sized buffers
     const bool wrap = load_src_poly(src, s, n1, loc, loc + kSlowCap, 1);
@@ -544,6 +562,7 @@ clip_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const int
     rstride = 1;
     if (n_out < 0) { atomicOr(err, kErrClipOverflow); n_out = 0; }
   }
+  __syncwarp();
 
   double xarea = 0.0, xclon = 0.0, xclat = 0.0;
   bool keep = false;
@@ -551,13 +570,15 @@ clip_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const int
   if (n_out > 0) {
     const double m = mask ? mask[s] : 1.0;
     double a;
+    // (the warp-synchronous variant poly_moments<ORDER, true> measured 5 % slower on C768 -> 1/8 degree: the lanes of a
+    // warp hold polygons of similar size, and waiting for the slowest lane after every sin/cos costs more than it saves)
     poly_moments<ORDER>(pv, n_out, s_xavg, &a, &xclon, &xclat);  // poly_area :805, poly_ctrlon :1091, poly_ctrlat :1092
     xarea = a * m;
     const double a1 = src.area[s], a2 = dst.area[d];
     const double min_area = (a1 < a2) ? a1 : a2;                 // :806
     keep = (xarea / min_area > kAreaRatioThresh);                // :807
   }
-  parea[p] = keep ? xarea : 0.0;
+  if (valid) parea[p] = keep ? xarea : 0.0;
   if (keep) {
     if (ORDER == 2) { pclon[p] = xclon; pclat[p] = xclat; }
     atomicAdd(&cnt[pr.x], 1u);

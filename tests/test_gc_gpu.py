@@ -68,7 +68,8 @@ def test_gc_cubed_sphere_matches_oracle(pkg, ni, nlon, nlat):
     same = _check(got, ref)
     if ni == 48:
         assert got["nxgrid"] == 146016
-    assert abs(got["area"].sum() / (4 * np.pi * R2) - 1) < 1e-11
+    assert abs(got["area"].sum() - ref["area"].sum()) / ref["area"].sum() < 1e-13
+    assert abs(got["area"].sum() / (4 * np.pi * R2) - 1) < 1e-8      # slivers below the 1e-6 area ratio are dropped
     assert same > 0.5                                   # most areas are bit-identical; the rest differ by an ulp of one angle
 
 
