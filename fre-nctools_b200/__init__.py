@@ -71,6 +71,8 @@ def lib():
     L.xgb_plan_partition.argtypes = [vp, C.c_int, C.POINTER(C.c_longlong)]
     L.xgb_plan_generate.restype = C.c_longlong
     L.xgb_plan_generate.argtypes = [vp, C.c_uint]
+    L.xgb_plan_generate_to_host.restype = C.c_longlong
+    L.xgb_plan_generate_to_host.argtypes = [vp, C.c_uint, C.c_int, C.c_longlong] + [vp] * 10
     L.xgb_plan_last_npairs.restype = C.c_longlong
     L.xgb_plan_last_npairs.argtypes = [vp]
     L.xgb_plan_result_device.argtypes = [vp, C.POINTER(_View)]
@@ -248,6 +250,24 @@ class XgridPlan:
 
     def generate(self, opcode):
         n = self._L.xgb_plan_generate(self._p, int(opcode))
+        if n < 0:
+            raise XgridError(_err())
+        self.nxgrid = int(n)
+        self.order = 2 if (opcode & CONSERVE_ORDER2) else 1
+        return self.nxgrid
+
+    def generate_to_host(self, opcode, bufs, nchunks=8):
+        """generate + download overlapped (xgb_plan_generate_to_host): bufs = dict of preallocated host arrays (numpy or
+        pinned torch CPU tensors) keyed t_in, i_in, j_in, i_out, j_out, area[, di, dj, xgrid_clon, xgrid_clat]; returns nxgrid"""
+        def ptr(k):
+            b = bufs.get(k)
+            if b is None:
+                return None
+            return b.data_ptr() if _is_torch(b) else b.ctypes.data
+        cap = min(int(bufs[k].shape[0]) for k in bufs if bufs[k] is not None)
+        n = self._L.xgb_plan_generate_to_host(self._p, int(opcode), int(nchunks), cap, ptr("t_in"), ptr("i_in"), ptr("j_in"),
+                                              ptr("i_out"), ptr("j_out"), ptr("area"), ptr("di"), ptr("dj"),
+                                              ptr("xgrid_clon"), ptr("xgrid_clat"))
         if n < 0:
             raise XgridError(_err())
         self.nxgrid = int(n)

@@ -116,6 +116,8 @@ extern "C" void xgb_plan_destroy(xgb_plan* p)
   if (p->total_dev) cudaFree(p->total_dev);
   if (p->total_host) cudaFreeHost(p->total_host);
   if (p->err_host) cudaFreeHost(p->err_host);
+  if (p->copy_ev) cudaEventDestroy(p->copy_ev);
+  if (p->copy_st) cudaStreamDestroy(p->copy_st);
   if (p->st) cudaStreamDestroy(p->st);
   delete p;
 }
@@ -305,18 +307,12 @@ extern "C" int xgb_plan_partition(xgb_plan* p, int nparts, long long* bounds)
   return 0;
 }
 
-extern "C" long long xgb_plan_generate(xgb_plan* p, unsigned int opcode)
+// One window [s0, s0+ns) of source cells: candidate search, clip, ordered compaction, order-2 correction.
+// Results are written at entries [base, base + n) of the plan's result arrays.  stream_cap == 0: the arrays are
+// (re)sized to hold base + n entries (only valid for base == 0); otherwise they were sized to stream_cap entries
+// beforehand and must not move (asynchronous copies of earlier windows may be in flight).
+static long long generate_window(xgb_plan* p, int order, long long s0, long long ns, size_t base, size_t stream_cap)
 {
-  if (!p || !p->have_src || !p->have_dst) { xgb_set_error("xgb_plan_generate: set source and destination grids first"); return -1; }
-  const int order = (opcode & XGB_CONSERVE_ORDER2) ? 2 : 1;
-  if (!(opcode & (XGB_CONSERVE_ORDER1 | XGB_CONSERVE_ORDER2))) {
-    xgb_set_error("conserve_interp: interp_method should be CONSERVE_ORDER1 or CONSERVE_ORDER2");   // conserve_interp.c:230
-    return -1;
-  }
-  if (cudaSetDevice(p->device) != cudaSuccess) { xgb_set_error("cudaSetDevice failed"); return -1; }
-  if (opcode & XGB_GREAT_CIRCLE) return xgb_generate_great_circle(p, order);
-
-  const long long s0 = p->s0, ns = p->ns;
   const double* mask = p->has_mask ? (const double*)p->mask.p : nullptr;
   unsigned long long npairs = 0;
   cudaEventRecord(p->ev[0], p->st);
@@ -346,24 +342,29 @@ extern "C" long long xgb_plan_generate(xgb_plan* p, unsigned int opcode)
     return -1;
   }
   const unsigned long long nx = p->total_host[1];
-  p->nxgrid = (long long)nx;
-  p->order = order;
 
-  const size_t ni = (size_t)nx * sizeof(int) + 16, nd = (size_t)nx * sizeof(double) + 16;
-  if (p->t_in.reserve(ni) || p->i_in.reserve(ni) || p->j_in.reserve(ni) || p->i_out.reserve(ni) || p->j_out.reserve(ni) ||
-      p->area.reserve(nd))
+  if (stream_cap == 0) {
+    const size_t ni = (size_t)(base + nx) * sizeof(int) + 16, nd = (size_t)(base + nx) * sizeof(double) + 16;
+    if (p->t_in.reserve(ni) || p->i_in.reserve(ni) || p->j_in.reserve(ni) || p->i_out.reserve(ni) || p->j_out.reserve(ni) ||
+        p->area.reserve(nd))
+      return -1;
+    if (order == 2 && (p->clon.reserve(nd) || p->clat.reserve(nd) || p->di.reserve(nd) || p->dj.reserve(nd))) return -1;
+  } else if (base + nx > stream_cap) {
+    xgb_set_error("The xgrid size is too large for resources: %llu exchange cells do not fit the %zu-entry output buffers",
+                  (unsigned long long)(base + nx), stream_cap);
     return -1;
-  if (order == 2 && (p->clon.reserve(nd) || p->clat.reserve(nd) || p->di.reserve(nd) || p->dj.reserve(nd))) return -1;
+  }
 
   cudaEventRecord(p->ev[4], p->st);
   launch_scatter(order, (const int2*)p->pairs.p, npairs, (const double*)p->parea.p, (const double*)p->pclon.p,
                  (const double*)p->pclat.p, (const uint32_t*)p->pair_off.p, (const uint32_t*)p->out_off.p,
                  (const TileDesc*)p->tiles_dev.p, (int)p->tiles.size(), s0, p->nx2,
-                 (int*)p->t_in.p, (int*)p->i_in.p, (int*)p->j_in.p, (int*)p->i_out.p, (int*)p->j_out.p,
-                 (double*)p->area.p, (double*)p->clon.p, (double*)p->clat.p, p->st);
+                 (int*)p->t_in.p + base, (int*)p->i_in.p + base, (int*)p->j_in.p + base, (int*)p->i_out.p + base, (int*)p->j_out.p + base,
+                 (double*)p->area.p + base, (double*)p->clon.p + (order == 2 ? base : 0), (double*)p->clat.p + (order == 2 ? base : 0), p->st);
   if (order == 2)
-    launch_order2_finalize(p->src, s0, ns, (const uint32_t*)p->out_off.p, (const double*)p->area.p,
-                           (const double*)p->clon.p, (const double*)p->clat.p, (double*)p->di.p, (double*)p->dj.p, p->st);
+    launch_order2_finalize(p->src, s0, ns, (const uint32_t*)p->out_off.p, (const double*)p->area.p + base,
+                           (const double*)p->clon.p + base, (const double*)p->clat.p + base, (double*)p->di.p + base,
+                           (double*)p->dj.p + base, p->st);
   cudaEventRecord(p->ev[5], p->st);
   if (xgb_check_kernel_errors(p, false)) return -1;
   for (int k = 0; k < 5; ++k) {
@@ -372,6 +373,79 @@ extern "C" long long xgb_plan_generate(xgb_plan* p, unsigned int opcode)
     p->phase_ms[k] = ms;
     p->phase_ms_sum[k] += ms;
   }
+  return (long long)nx;
+}
+
+extern "C" long long xgb_plan_generate(xgb_plan* p, unsigned int opcode)
+{
+  if (!p || !p->have_src || !p->have_dst) { xgb_set_error("xgb_plan_generate: set source and destination grids first"); return -1; }
+  const int order = (opcode & XGB_CONSERVE_ORDER2) ? 2 : 1;
+  if (!(opcode & (XGB_CONSERVE_ORDER1 | XGB_CONSERVE_ORDER2))) {
+    xgb_set_error("conserve_interp: interp_method should be CONSERVE_ORDER1 or CONSERVE_ORDER2");   // conserve_interp.c:230
+    return -1;
+  }
+  if (cudaSetDevice(p->device) != cudaSuccess) { xgb_set_error("cudaSetDevice failed"); return -1; }
+  if (opcode & XGB_GREAT_CIRCLE) return xgb_generate_great_circle(p, order);
+  const long long n = generate_window(p, order, p->s0, p->ns, 0, 0);
+  if (n < 0) return -1;
+  p->nxgrid = n;
+  p->order = order;
+  p->generates += 1;
+  return p->nxgrid;
+}
+
+// Generate the current window in `nchunks` consecutive pieces of source cells and copy every piece to the caller's
+// host arrays while the next one is being computed (second stream): the D2H transfer of the result, which is longer
+// than its computation on PCIe gen5, overlaps with it.  Host arrays hold `capacity` entries (any of di, dj,
+// xgrid_clon, xgrid_clat may be NULL); pinned memory gives real overlap.  The device copy of the result is complete
+// afterwards as well (xgb_plan_result_device, xgb_plan_apply_setup).
+extern "C" long long xgb_plan_generate_to_host(xgb_plan* p, unsigned int opcode, int nchunks, long long capacity,
+                                               int* t_in, int* i_in, int* j_in, int* i_out, int* j_out,
+                                               double* area, double* di, double* dj, double* xgrid_clon, double* xgrid_clat)
+{
+  if (!p || !p->have_src || !p->have_dst) { xgb_set_error("xgb_plan_generate_to_host: set source and destination grids first"); return -1; }
+  const int order = (opcode & XGB_CONSERVE_ORDER2) ? 2 : 1;
+  if (!(opcode & (XGB_CONSERVE_ORDER1 | XGB_CONSERVE_ORDER2)) || (opcode & XGB_GREAT_CIRCLE) || capacity <= 0 || nchunks <= 0) {
+    xgb_set_error("xgb_plan_generate_to_host: needs CONSERVE_ORDER1/2 (no great circle), capacity > 0, nchunks > 0");
+    return -1;
+  }
+  if (cudaSetDevice(p->device) != cudaSuccess) { xgb_set_error("cudaSetDevice failed"); return -1; }
+  if (!p->copy_st) {
+    if (cudaStreamCreateWithFlags(&p->copy_st, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&p->copy_ev, cudaEventDisableTiming) != cudaSuccess) {
+      xgb_set_error("xgb_plan_generate_to_host: cannot create the copy stream");
+      return -1;
+    }
+  }
+  const size_t cap = (size_t)capacity;
+  const size_t ni = cap * sizeof(int) + 16, nd = cap * sizeof(double) + 16;
+  cudaStreamSynchronize(p->copy_st);
+  if (p->t_in.reserve(ni) || p->i_in.reserve(ni) || p->j_in.reserve(ni) || p->i_out.reserve(ni) || p->j_out.reserve(ni) || p->area.reserve(nd))
+    return -1;
+  if (order == 2 && (p->clon.reserve(nd) || p->clat.reserve(nd) || p->di.reserve(nd) || p->dj.reserve(nd))) return -1;
+
+  const long long w0 = p->s0, wn = p->ns;
+  size_t base = 0;
+  for (int c = 0; c < nchunks; ++c) {
+    const long long b = w0 + wn * c / nchunks, e = w0 + wn * (c + 1) / nchunks;
+    if (e <= b) continue;
+    const long long n = generate_window(p, order, b, e - b, base, cap);
+    if (n < 0) { cudaStreamSynchronize(p->copy_st); return -1; }
+    // generate_window returned after synchronising p->st: the piece is complete; ship it
+    struct { void* dst; const void* src; size_t esz; } cp[] = {
+        {t_in, p->t_in.p, 4}, {i_in, p->i_in.p, 4}, {j_in, p->j_in.p, 4}, {i_out, p->i_out.p, 4}, {j_out, p->j_out.p, 4},
+        {area, p->area.p, 8}, {order == 2 ? di : nullptr, p->di.p, 8}, {order == 2 ? dj : nullptr, p->dj.p, 8},
+        {order == 2 ? xgrid_clon : nullptr, p->clon.p, 8}, {order == 2 ? xgrid_clat : nullptr, p->clat.p, 8}};
+    for (auto& x : cp)
+      if (x.dst && n > 0)
+        cudaMemcpyAsync((char*)x.dst + base * x.esz, (const char*)x.src + base * x.esz, (size_t)n * x.esz, cudaMemcpyDeviceToHost, p->copy_st);
+    base += (size_t)n;
+  }
+  if (cudaStreamSynchronize(p->copy_st) != cudaSuccess) {
+    xgb_set_error("xgb_plan_generate_to_host: result copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return -1;
+  }
+  p->nxgrid = (long long)base;
+  p->order = order;
   p->generates += 1;
   return p->nxgrid;
 }

@@ -19,6 +19,8 @@ struct xgb_apply_state;        // apply_capi.cu
 struct xgb_plan {
   int device = 0;
   cudaStream_t st = nullptr;
+  cudaStream_t copy_st = nullptr;             // result download overlapped with generation (xgb_plan_generate_to_host)
+  cudaEvent_t copy_ev = nullptr;
 
   // destination tile
   bool have_dst = false;

@@ -116,6 +116,15 @@ int xgb_plan_partition(xgb_plan *p, int nparts, long long *bounds);
  * Results stay in HBM, in the reference's emission order (tile, j_in, i_in, then j_out*nx+i_out). */
 long long xgb_plan_generate(xgb_plan *p, unsigned int opcode);
 
+/* The same for callers that want the result in HOST arrays (what setup_conserve_interp's callers need,
+ * conserve_interp.c:236-257): the window is generated in nchunks consecutive pieces of source cells and each piece is
+ * copied out on a second stream while the next is computed, so the PCIe transfer overlaps the kernels.  The arrays
+ * hold `capacity` entries (di, dj, xgrid_clon, xgrid_clat may be NULL; all are ignored for order 1 except area);
+ * use pinned memory for real overlap.  Not available with XGB_GREAT_CIRCLE.  Returns nxgrid or -1. */
+long long xgb_plan_generate_to_host(xgb_plan *p, unsigned int opcode, int nchunks, long long capacity,
+                                    int *t_in, int *i_in, int *j_in, int *i_out, int *j_out,
+                                    double *area, double *di, double *dj, double *xgrid_clon, double *xgrid_clat);
+
 /* candidate pairs examined by the last generate (clip-kernel work items) */
 long long xgb_plan_last_npairs(xgb_plan *p);
 

@@ -183,3 +183,38 @@ def test_conservation_c192_half_degree(pkg):
     # sortedness: reference emission order
     key = (r["t_in"].astype(np.int64) * 192 * 192 + r["j_in"] * 192 + r["i_in"]) * (720 * 360) + r["j_out"].astype(np.int64) * 720 + r["i_out"]
     assert np.all(np.diff(key) > 0)
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_generate_to_host_chunks_equal_one_shot(pkg, order):
+    """xgb_plan_generate_to_host: the window generated in pieces with the download overlapped; host arrays and the
+    device-resident copy must equal the one-shot result bit for bit, for any number of pieces"""
+    lonc, latc = pkg.cubed_sphere_grid(24)
+    lon2, lat2 = pkg.latlon_grid(144, 72)
+    want = _gen(pkg, lonc, latc, lon2, lat2, order)
+    n = want["nxgrid"]
+    keys_i = ("t_in", "i_in", "j_in", "i_out", "j_out")
+    keys_f = ("area", "di", "dj", "xgrid_clon", "xgrid_clat") if order == 2 else ("area",)
+    for nchunks in (1, 3, 8, 50):
+        plan = pkg.XgridPlan(0)
+        plan.set_dst(lon2, lat2)
+        plan.set_src(lonc, latc)
+        bufs = {k: np.full(n + 7, -1, np.int32) for k in keys_i}
+        bufs.update({k: np.full(n + 7, np.nan) for k in keys_f})
+        got_n = plan.generate_to_host(order, bufs, nchunks=nchunks)
+        assert got_n == n
+        for k in keys_i + keys_f:
+            assert np.array_equal(bufs[k][:n], want[k]), (nchunks, k)
+            assert np.all(bufs[k][n:] == -1) if k in keys_i else np.all(np.isnan(bufs[k][n:]))
+        dev = plan.result_host()
+        for k in keys_i + keys_f:
+            assert np.array_equal(dev[k], want[k]), (nchunks, k)
+        plan.close()
+    # too small a capacity is an error, not an overrun
+    plan = pkg.XgridPlan(0)
+    plan.set_dst(lon2, lat2); plan.set_src(lonc, latc)
+    small = {k: np.zeros(n // 2, np.int32) for k in keys_i}
+    small.update({k: np.zeros(n // 2) for k in keys_f})
+    with pytest.raises(pkg.XgridError):
+        plan.generate_to_host(order, small, nchunks=4)
+    plan.close()
