@@ -64,7 +64,7 @@ void xgb_apply_release(xgb_plan* p)
 
 static int kernel_errors(xgb_plan* p)
 {
-  CU_OK(cudaMemcpyAsync(p->err_host, p->err_dev, sizeof(int), cudaMemcpyDeviceToHost, p->st));
+  launch_publish(p->err_host, p->err_dev, 1, p->st);
   CU_OK(cudaStreamSynchronize(p->st));
   CU_OK(cudaGetLastError());
   const int e = *p->err_host;

@@ -156,7 +156,7 @@ static int upload(DevBuf& dst, const double* src, size_t n, int on_device, cudaS
 
 int xgb_check_kernel_errors(xgb_plan* p, bool fatal_like_reference)
 {
-  CU_OK(cudaMemcpyAsync(p->err_host, p->err_dev, sizeof(int), cudaMemcpyDeviceToHost, p->st));
+  launch_publish(p->err_host, p->err_dev, 1, p->st);
   CU_OK(cudaStreamSynchronize(p->st));
   CU_OK(cudaGetLastError());
   const int e = *p->err_host;
@@ -286,7 +286,7 @@ static int count_candidates(xgb_plan* p, long long s0, long long ns, unsigned lo
   launch_candidates(false, p->src, s0, ns, p->has_mask ? (const double*)p->mask.p : nullptr, p->pyr, p->dst,
                     nullptr, (uint32_t*)p->cnt.p, nullptr, hw, p->err_dev, p->st);
   launch_exclusive_scan((const uint32_t*)p->cnt.p, (uint32_t*)p->pair_off.p, ns, p->total_dev, p->scan_tmp.p, p->st);
-  CU_OK(cudaMemcpyAsync(p->total_host, p->total_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->st));
+  launch_publish(p->total_host, p->total_dev, 2, p->st);
   CU_OK(cudaStreamSynchronize(p->st));
   *total = p->total_host[0];
   if (*total >= (1ull << 32)) { xgb_set_error("more than 2^32 candidate pairs in one window; shard the source cells"); return 1; }
@@ -336,8 +336,8 @@ static long long generate_window(xgb_plan* p, int order, long long s0, long long
               (double*)p->parea.p, (double*)p->pclon.p, (double*)p->pclat.p, (uint32_t*)p->cnt.p, p->err_dev, p->st);
   cudaEventRecord(p->ev[3], p->st);
   launch_exclusive_scan((const uint32_t*)p->cnt.p, (uint32_t*)p->out_off.p, ns, p->total_dev + 1, p->scan_tmp.p, p->st);
-  if (cudaMemcpyAsync(p->total_host + 1, p->total_dev + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->st) != cudaSuccess ||
-      cudaStreamSynchronize(p->st) != cudaSuccess) {
+  launch_publish(p->total_host + 1, p->total_dev + 1, 2, p->st);
+  if (cudaStreamSynchronize(p->st) != cudaSuccess) {
     xgb_set_error("xgrid generation failed: %s", cudaGetErrorString(cudaGetLastError()));
     return -1;
   }

@@ -82,8 +82,8 @@ long long xgb_generate_great_circle(xgb_plan* p, int order)
   cudaEventRecord(p->ev[0], p->st);
   launch_gc_candidates(false, p->gc_src, s0, ns, mask, p->gc_pyr, nullptr, (uint32_t*)p->cnt.p, nullptr, p->err_dev, p->st);
   launch_exclusive_scan((const uint32_t*)p->cnt.p, (uint32_t*)p->pair_off.p, ns, p->total_dev, p->scan_tmp.p, p->st);
-  if (cudaMemcpyAsync(p->total_host, p->total_dev, 8, cudaMemcpyDeviceToHost, p->st) != cudaSuccess ||
-      cudaStreamSynchronize(p->st) != cudaSuccess) {
+  launch_publish(p->total_host, p->total_dev, 2, p->st);
+  if (cudaStreamSynchronize(p->st) != cudaSuccess) {
     xgb_set_error("great-circle candidate search failed: %s", cudaGetErrorString(cudaGetLastError()));
     return -1;
   }
@@ -100,8 +100,8 @@ long long xgb_generate_great_circle(xgb_plan* p, int order)
                  p->err_dev, p->st);
   cudaEventRecord(p->ev[3], p->st);
   launch_exclusive_scan((const uint32_t*)p->cnt.p, (uint32_t*)p->out_off.p, ns, p->total_dev + 1, p->scan_tmp.p, p->st);
-  if (cudaMemcpyAsync(p->total_host + 1, p->total_dev + 1, 8, cudaMemcpyDeviceToHost, p->st) != cudaSuccess ||
-      cudaStreamSynchronize(p->st) != cudaSuccess) {
+  launch_publish(p->total_host + 1, p->total_dev + 1, 2, p->st);
+  if (cudaStreamSynchronize(p->st) != cudaSuccess) {
     xgb_set_error("great-circle clip failed: %s", cudaGetErrorString(cudaGetLastError()));
     return -1;
   }

@@ -849,3 +849,23 @@ void launch_partition(const uint32_t* pair_off, long long ncell, unsigned long l
   partition_kernel<<<(nparts + 1 + 63) / 64, 64, 0, st>>>(pair_off, ncell, total, nparts, bounds);
 }
 }  // namespace xgb
+
+// =============================================================================================
+// Small device -> host results (totals, error bits) are written by a one-thread kernel straight into pinned,
+// device-visible host memory instead of a cudaMemcpyAsync: a D2H memcpy would queue behind the large result downloads
+// of xgb_plan_generate_to_host on the copy engine, and the host waits for these words before it can size the next
+// launch.
+// =============================================================================================
+namespace xgb {
+__global__ void publish_kernel(unsigned* __restrict__ host_dst, const unsigned* __restrict__ dev_src, int nwords)
+{
+  for (int k = threadIdx.x; k < nwords; k += blockDim.x) host_dst[k] = dev_src[k];
+  __threadfence_system();
+}
+
+void launch_publish(void* host_dst, const void* dev_src, int nwords, cudaStream_t st)
+{
+  ++g_launches;
+  publish_kernel<<<1, 32, 0, st>>>((unsigned*)host_dst, (const unsigned*)dev_src, nwords);
+}
+}  // namespace xgb
