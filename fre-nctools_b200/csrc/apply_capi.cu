@@ -397,18 +397,26 @@ extern "C" int xgb_plan_regrid(xgb_plan* p, unsigned int opcode, int nfields, co
   const size_t nd = (size_t)nfields * (order == 2 ? a->nhalo : a->ncell), ng = (size_t)nfields * a->ncell, no = (size_t)nfields * a->ndst;
   const double* d_data = nullptr;
   if (stage_in(a->s_data, data, nd, on_device, p->st, &d_data)) return 1;
-  double *d_gx = nullptr, *d_gy = nullptr;
-  int* d_gm = nullptr;
-  if (order == 2) {
-    const bool need_mask = has_missing || (opcode & XGB_MONOTONIC);
-    if (a->s_gx.reserve(ng * 8 + 16) || a->s_gy.reserve(ng * 8 + 16) || (need_mask && a->s_gmask.reserve(ng * 4 + 16))) return 1;
-    d_gx = (double*)a->s_gx.p; d_gy = (double*)a->s_gy.p; d_gm = need_mask ? (int*)a->s_gmask.p : nullptr;
-    launch_grad_c2l((const GradTile*)a->gtiles_dev.p, (int)a->gtiles.size(), a->ncell, nfields, d_data, a->nhalo, d_gx, d_gy, d_gm,
-                    has_missing != 0, missing, p->st);
-  }
   double* d_out = out;
   if (!on_device) { if (a->s_out.reserve(no * 8 + 16)) return 1; d_out = (double*)a->s_out.p; }
-  if (apply_device(p, a, opcode, nfields, d_data, d_gx, d_gy, d_gm, has_missing != 0, missing, d_out)) return 1;
+  if (order == 2 && !(opcode & XGB_MONOTONIC)) {
+    // packed path: one 32-byte record (value, grad_x, grad_y, grad_mask) per source cell and field-level
+    if (a->s_gx.reserve(ng * 32 + 32)) return 1;
+    launch_grad_c2l_packed((const GradTile*)a->gtiles_dev.p, (int)a->gtiles.size(), a->ncell, nfields, d_data, a->nhalo,
+                           (double*)a->s_gx.p, has_missing != 0, missing, p->st);
+    launch_apply_packed(has_missing != 0, a->csr, a->ndst, nfields, (const double*)a->s_gx.p, a->ncell,
+                        has_missing ? missing : -1.e20, d_out, p->st);
+  } else {
+    double *d_gx = nullptr, *d_gy = nullptr;
+    int* d_gm = nullptr;
+    if (order == 2) {
+      if (a->s_gx.reserve(ng * 8 + 16) || a->s_gy.reserve(ng * 8 + 16) || a->s_gmask.reserve(ng * 4 + 16)) return 1;
+      d_gx = (double*)a->s_gx.p; d_gy = (double*)a->s_gy.p; d_gm = (int*)a->s_gmask.p;
+      launch_grad_c2l((const GradTile*)a->gtiles_dev.p, (int)a->gtiles.size(), a->ncell, nfields, d_data, a->nhalo, d_gx, d_gy, d_gm,
+                      has_missing != 0, missing, p->st);
+    }
+    if (apply_device(p, a, opcode, nfields, d_data, d_gx, d_gy, d_gm, has_missing != 0, missing, d_out)) return 1;
+  }
   if (!on_device) {
     CU_OK(cudaMemcpyAsync(out, d_out, no * 8, cudaMemcpyDeviceToHost, p->st));
     CU_OK(cudaStreamSynchronize(p->st));

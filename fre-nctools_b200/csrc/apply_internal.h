@@ -7,7 +7,7 @@
 namespace xgb {
 
 constexpr int kApplyBT = 8;    // field-levels per thread in apply: weights are read once per kApplyBT fields
-constexpr int kGradBT = 8;     // field-levels per thread in grad_c2l: metrics are read once per kGradBT fields
+constexpr int kGradBT = 4;     // field-levels per thread in grad_c2l: metrics are read once per kGradBT fields
 
 enum : int {
   kErrApplyIndex  = 1 << 10,   // exchange-grid entry points outside the source mosaic
@@ -51,6 +51,11 @@ void launch_apply(int order, bool has_missing, bool from_xdata, const ApplyCsr& 
                   long long ncell_src, const double* xdata, long long nxgrid, double missing, double* out, cudaStream_t st);
 void launch_grad_c2l(const GradTile* tiles, int ntiles, long long ncell, int nf, const double* data, long long data_stride,
                      double* gx, double* gy, int* gmask, bool has_missing, double missing, cudaStream_t st);
+// fused path: gradient kernel writes (value, grad_x, grad_y, grad_mask) per cell as one double4, apply gathers it
+void launch_grad_c2l_packed(const GradTile* tiles, int ntiles, long long ncell, int nf, const double* data, long long data_stride,
+                            double* packed, bool has_missing, double missing, cudaStream_t st);
+void launch_apply_packed(bool has_missing, const ApplyCsr& csr, long long ndst, int nf, const double* packed, long long ncell_src,
+                         double missing, double* out, cudaStream_t st);
 void launch_monotone(long long nxgrid, const int* t_in, const int* i_in, const int* j_in, const double* di, const double* dj,
                      const ApplyTile* tiles, int ntiles, long long ncell, const double* data, const double* gx, const double* gy,
                      const int* gmask, double missing, double* fbmax, double* fbmin, unsigned long long* fmax_key,

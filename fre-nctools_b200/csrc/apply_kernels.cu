@@ -106,9 +106,13 @@ apply_kernel(ApplyCsr csr, long long ndst, int nf, const double* __restrict__ da
              const double* __restrict__ gx, const double* __restrict__ gy, const int* __restrict__ gmask, long long ncell_src,
              const double* __restrict__ xdata, long long nxgrid, double missing, double* __restrict__ out)
 {
-  const long long d = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  // field tile varies fastest over the blocks: the blocks resident at any moment cover a narrow band of destination
+  // cells for ALL field tiles, so a chunk of the weights is fetched from HBM once and re-read from L2 by the other
+  // field tiles (with destination fastest the 3.3 GB output stream evicted it between tiles: 3.3 GB of re-reads)
+  const int nft = (nf + kApplyBT - 1) / kApplyBT;
+  const long long d = (long long)(blockIdx.x / nft) * blockDim.x + threadIdx.x;
   if (d >= ndst) return;
-  const int f0 = blockIdx.y * kApplyBT;
+  const int f0 = (int)(blockIdx.x % nft) * kApplyBT;
   const uint32_t b = csr.off[d], e = csr.off[d + 1];
   double acc[kApplyBT], asum[kApplyBT];
   bool seen[kApplyBT];
@@ -165,13 +169,76 @@ void launch_apply(int order, bool has_missing, bool from_xdata, const ApplyCsr& 
                   long long ncell_src, const double* xdata, long long nxgrid, double missing, double* out, cudaStream_t st)
 {
   if (ndst <= 0 || nf <= 0) return;
-  dim3 grid((unsigned)((ndst + 127) / 128), (unsigned)((nf + kApplyBT - 1) / kApplyBT));
+  const long long nblk = ((ndst + 127) / 128) * ((nf + kApplyBT - 1) / kApplyBT);
+  if (nblk >= (1ll << 31)) return;                                 // callers batch fields; unreachable for sane batches
+  dim3 grid((unsigned)nblk);
   ++g_launches;
 #define XGB_APPLY(O, M, X) apply_kernel<O, M, X><<<grid, 128, 0, st>>>(csr, ndst, nf, data, data_stride, gx, gy, gmask, ncell_src, xdata, nxgrid, missing, out)
   if (from_xdata) XGB_APPLY(2, true, true);
   else if (order == 2) { if (has_missing) XGB_APPLY(2, true, false); else XGB_APPLY(2, false, false); }
   else { if (has_missing) XGB_APPLY(1, true, false); else XGB_APPLY(1, false, false); }
 #undef XGB_APPLY
+}
+
+// Fused-path variant: the gradient kernel leaves (value, grad_x, grad_y, grad_mask) of a source cell next to each other
+// (32 bytes, one sector), so an exchange-cell entry costs one gather per field instead of three.
+constexpr int kPackBT = kApplyBT;  // field-levels per thread (16 per thread and shared-memory staging of the entries
+                                   // both measured slower on configs[1]: the L1 footprint of the gathers grows)
+
+template <bool MISSING>
+__global__ void __launch_bounds__(128)
+apply_packed_kernel(ApplyCsr csr, long long ndst, int nf, const double4* __restrict__ packed, long long ncell_src,
+                    double missing, double* __restrict__ out)
+{
+  const int nft = (nf + kPackBT - 1) / kPackBT;
+  const long long d = (long long)(blockIdx.x / nft) * blockDim.x + threadIdx.x;
+  if (d >= ndst) return;
+  const int f0 = (int)(blockIdx.x % nft) * kPackBT;
+  const uint32_t b = csr.off[d], e = csr.off[d + 1];
+  double acc[kPackBT], asum[kPackBT];
+  bool seen[kPackBT];
+#pragma unroll
+  for (int k = 0; k < kPackBT; ++k) { acc[k] = 0.0; asum[k] = 0.0; seen[k] = false; }
+  double asum_all = 0.0;
+  for (uint32_t q = b; q < e; ++q) {
+    const double area = csr.area[q], di = csr.di[q], dj = csr.dj[q];
+    const int cell = csr.cell[q];
+    if (!MISSING) asum_all += area;
+#pragma unroll
+    for (int k = 0; k < kPackBT; ++k) {
+      const int f = f0 + k;
+      if (f >= nf) break;
+      const double2* pk = reinterpret_cast<const double2*>(&packed[(long long)f * ncell_src + cell]);
+      const double2 lo = __ldg(pk), hi = __ldg(pk + 1);
+      const double4 v = make_double4(lo.x, lo.y, hi.x, hi.y);
+      if (MISSING && v.x == missing) continue;                              // :766
+      if (MISSING && v.w != 0.0) acc[k] += v.x * area;                      // :779
+      else acc[k] += (v.x + v.y * di + v.z * dj) * area;                    // :782, :806
+      if (MISSING) { asum[k] += area; seen[k] = true; }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kPackBT; ++k) {
+    const int f = f0 + k;
+    if (f >= nf) break;
+    const double a = MISSING ? asum[k] : asum_all;
+    double r;
+    if (a > 0) r = acc[k] / a;
+    else if (MISSING && seen[k]) r = 0.0;
+    else r = missing;
+    out[(long long)f * ndst + d] = r;
+  }
+}
+
+void launch_apply_packed(bool has_missing, const ApplyCsr& csr, long long ndst, int nf, const double* packed, long long ncell_src,
+                         double missing, double* out, cudaStream_t st)
+{
+  if (ndst <= 0 || nf <= 0) return;
+  const long long nblk = ((ndst + 127) / 128) * ((nf + kPackBT - 1) / kPackBT);
+  if (nblk >= (1ll << 31)) return;
+  ++g_launches;
+  if (has_missing) apply_packed_kernel<true><<<(unsigned)nblk, 128, 0, st>>>(csr, ndst, nf, (const double4*)packed, ncell_src, missing, out);
+  else             apply_packed_kernel<false><<<(unsigned)nblk, 128, 0, st>>>(csr, ndst, nf, (const double4*)packed, ncell_src, missing, out);
 }
 
 // =============================================================================================
@@ -208,13 +275,15 @@ __device__ __forceinline__ double corner_value(const double* __restrict__ q, int
 }
 
 // one thread per source cell (concatenated index), kGradBT field-levels per thread
-template <bool MISSING>
-__global__ void __launch_bounds__(128)
+// PACKED: write (value, grad_x, grad_y, grad_mask) as one double4 per cell into gx (see apply_packed_kernel)
+template <bool MISSING, bool PACKED>
+__global__ void __launch_bounds__(128, 3)
 grad_c2l_kernel(const GradTile* __restrict__ tiles, int ntiles, long long ncell, int nf,
                 const double* __restrict__ data, long long data_stride,
                 double* __restrict__ gx, double* __restrict__ gy, int* __restrict__ gmask, double missing)
 {
-  const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int nft = (nf + kGradBT - 1) / kGradBT;
+  const long long c = (long long)(blockIdx.x / nft) * blockDim.x + threadIdx.x;
   if (c >= ncell) return;
   int t = 0;
   while (t + 1 < ntiles && c >= tiles[t + 1].cell_off) ++t;
@@ -236,7 +305,7 @@ grad_c2l_kernel(const GradTile* __restrict__ tiles, int ntiles, long long ncell,
     vlat[n] = g.vlat[3 * lc + n];
   }
   const double area = g.area[lc];
-  const int f0 = blockIdx.y * kGradBT;
+  const int f0 = (int)(blockIdx.x % nft) * kGradBT;
   for (int k = 0; k < kGradBT; ++k) {
     const int f = f0 + k;
     if (f >= nf) break;
@@ -257,16 +326,18 @@ grad_c2l_kernel(const GradTile* __restrict__ tiles, int ntiles, long long ncell,
     double vy = (vlat[0] * g3[0] + vlat[1] * g3[1] + vlat[2] * g3[2]) / area;
     vy *= kRadius;
     const long long o = (long long)f * ncell + c;
-    gx[o] = vx; gy[o] = vy;
-    if (gmask) {
-      int m = 0;
-      if (MISSING) {                                                          // fregrid_util.c:2203-2216
-        const int w = nx + 2, ii = i + 1, jj = j + 1;
-        m = (q[(jj - 1) * w + ii - 1] == missing || q[(jj - 1) * w + ii] == missing || q[(jj - 1) * w + ii + 1] == missing ||
-             q[jj * w + ii - 1] == missing || q[jj * w + ii + 1] == missing || q[(jj + 1) * w + ii - 1] == missing ||
-             q[(jj + 1) * w + ii] == missing || q[(jj + 1) * w + ii + 1] == missing) ? 1 : 0;
-      }
-      gmask[o] = m;
+    int m = 0;
+    if (MISSING && (PACKED || gmask)) {                                       // fregrid_util.c:2203-2216
+      const int w = nx + 2, ii = i + 1, jj = j + 1;
+      m = (q[(jj - 1) * w + ii - 1] == missing || q[(jj - 1) * w + ii] == missing || q[(jj - 1) * w + ii + 1] == missing ||
+           q[jj * w + ii - 1] == missing || q[jj * w + ii + 1] == missing || q[(jj + 1) * w + ii - 1] == missing ||
+           q[(jj + 1) * w + ii] == missing || q[(jj + 1) * w + ii + 1] == missing) ? 1 : 0;
+    }
+    if (PACKED) {
+      reinterpret_cast<double4*>(gx)[o] = make_double4(q[(long long)(j + 1) * (nx + 2) + i + 1], vx, vy, (double)m);
+    } else {
+      gx[o] = vx; gy[o] = vy;
+      if (gmask) gmask[o] = m;
     }
   }
 }
@@ -275,10 +346,24 @@ void launch_grad_c2l(const GradTile* tiles, int ntiles, long long ncell, int nf,
                      double* gx, double* gy, int* gmask, bool has_missing, double missing, cudaStream_t st)
 {
   if (ncell <= 0 || nf <= 0) return;
-  dim3 grid((unsigned)((ncell + 127) / 128), (unsigned)((nf + kGradBT - 1) / kGradBT));
+  const long long nblk = ((ncell + 127) / 128) * ((nf + kGradBT - 1) / kGradBT);
+  if (nblk >= (1ll << 31)) return;
+  dim3 grid((unsigned)nblk);
   ++g_launches;
-  if (has_missing) grad_c2l_kernel<true><<<grid, 128, 0, st>>>(tiles, ntiles, ncell, nf, data, data_stride, gx, gy, gmask, missing);
-  else             grad_c2l_kernel<false><<<grid, 128, 0, st>>>(tiles, ntiles, ncell, nf, data, data_stride, gx, gy, gmask, missing);
+  if (has_missing) grad_c2l_kernel<true, false><<<grid, 128, 0, st>>>(tiles, ntiles, ncell, nf, data, data_stride, gx, gy, gmask, missing);
+  else             grad_c2l_kernel<false, false><<<grid, 128, 0, st>>>(tiles, ntiles, ncell, nf, data, data_stride, gx, gy, gmask, missing);
+}
+
+void launch_grad_c2l_packed(const GradTile* tiles, int ntiles, long long ncell, int nf, const double* data, long long data_stride,
+                            double* packed, bool has_missing, double missing, cudaStream_t st)
+{
+  if (ncell <= 0 || nf <= 0) return;
+  const long long nblk = ((ncell + 127) / 128) * ((nf + kGradBT - 1) / kGradBT);
+  if (nblk >= (1ll << 31)) return;
+  dim3 grid((unsigned)nblk);
+  ++g_launches;
+  if (has_missing) grad_c2l_kernel<true, true><<<grid, 128, 0, st>>>(tiles, ntiles, ncell, nf, data, data_stride, packed, nullptr, nullptr, missing);
+  else             grad_c2l_kernel<false, true><<<grid, 128, 0, st>>>(tiles, ntiles, ncell, nf, data, data_stride, packed, nullptr, nullptr, missing);
 }
 
 // =============================================================================================
