@@ -64,6 +64,21 @@ int create_xgrid_2dx2d_order2_(const int *nlon_in, const int *nlat_in, const int
                                const double *mask_in, int *i_in, int *j_in, int *i_out, int *j_out,
                                double *xgrid_area, double *xgrid_clon, double *xgrid_clat);
 
+/* conserve_interp.h:25-32 — fregrid's own L3 entry points over its Grid_config / Interp_config / Field_config structs
+ * (globals.h:66-222; declared here with opaque struct tags: callers include the reference's headers, the library mirrors
+ * their layout in csrc/fregrid_abi.h and a test pins sizeof/offsetof against the compiled reference).
+ *   setup_conserve_interp (conserve_interp.c:42): the generate branch for all (output, input) tile pairs; interp[n].* are
+ *     malloc'ed like the reference does (:238-258).  READ / WRITE (remap-file I/O through netCDF) are refused loudly.
+ *   do_scalar_conserve_interp (conserve_interp.c:507): order 1 / order 2 / missing values / MONOTONIC, any nz;
+ *     cell_measures, cell_methods sum, weight fields and TARGET are refused loudly. */
+void setup_conserve_interp(int ntiles_in, const void *grid_in /* const Grid_config* */, int ntiles_out,
+                           void *grid_out /* Grid_config* */, void *interp /* Interp_config* */, unsigned int opcode);
+void do_scalar_conserve_interp(void *interp /* Interp_config* */, int varid, int ntiles_in, const void *grid_in,
+                               int ntiles_out, const void *grid_out, const void *field_in /* const Field_config* */,
+                               void *field_out /* Field_config* */, unsigned int opcode, int nz);
+/* sizeof/offsetof of the mirrored structs (test hook) */
+int xgb_abi_layout(size_t *out, int cap);
+
 /* ------------------------------------------------------------------------------------------
  * Part 2 — batched / device-resident interface.
  *

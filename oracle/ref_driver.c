@@ -300,3 +300,75 @@ void ref_compute_extent(int npts, int ndivs, int *ibegin, int *iend)
 {
   mpp_compute_extent(npts, ndivs, ibegin, iend);
 }
+
+
+/* ---- ABI checks of the product's reference-signature entry points ------------------------------------------ */
+#include <stddef.h>
+/* sizeof / offsetof of the REAL structs, in the order libxgrid_b200's xgb_abi_layout() reports its mirrors */
+int ref_abi_layout(size_t *out, int cap)
+{
+  const size_t v[] = {
+      sizeof(Var_config), offsetof(Var_config, missing), offsetof(Var_config, has_missing), offsetof(Var_config, interp_method),
+      offsetof(Var_config, cell_measures), offsetof(Var_config, cell_methods), offsetof(Var_config, use_volume),
+      sizeof(Field_config), offsetof(Field_config, data), offsetof(Field_config, grad_x), offsetof(Field_config, grad_y),
+      offsetof(Field_config, grad_mask), offsetof(Field_config, var),
+      sizeof(Interp_config), offsetof(Interp_config, nxgrid), offsetof(Interp_config, i_in), offsetof(Interp_config, t_in),
+      offsetof(Interp_config, di_in), offsetof(Interp_config, area), offsetof(Interp_config, file_exist),
+      sizeof(Grid_config), offsetof(Grid_config, nx), offsetof(Grid_config, ny), offsetof(Grid_config, nxc),
+      offsetof(Grid_config, nyc), offsetof(Grid_config, lonc), offsetof(Grid_config, latc), offsetof(Grid_config, cell_area),
+      offsetof(Grid_config, weight_exist), offsetof(Grid_config, domain)};
+  const int n = (int)(sizeof(v)/sizeof(v[0]));
+  int k;
+  for(k=0; k<n && k<cap; k++) out[k] = v[k];
+  return n;
+}
+
+typedef void (*setup_fn_t)(int, const Grid_config *, int, Grid_config *, Interp_config *, unsigned int);
+typedef void (*apply_fn_t)(Interp_config *, int, int, const Grid_config *, int, const Grid_config *, const Field_config *,
+                           Field_config *, unsigned int, int);
+
+/* Re-run the setup of an existing RefRegrid through ANOTHER implementation of setup_conserve_interp (a function pointer
+ * taken from libxgrid_b200.so), handing it the real Grid_config structs; returns a new handle sharing the grids. */
+RefRegrid *ref_regrid_setup_through(const RefRegrid *r, void *setup_fn)
+{
+  RefRegrid *q = (RefRegrid *)calloc(1, sizeof(RefRegrid));
+  *q = *r;
+  q->interp = (Interp_config *)calloc(1, sizeof(Interp_config));
+  ((setup_fn_t)setup_fn)(q->ntiles_in, q->gin, 1, q->gout, q->interp, q->opcode & ~(WRITE|READ|CHECK_CONSERVE|LEGACY_CLIP));
+  return q;
+}
+
+/* ref_regrid_apply, but through another implementation of do_scalar_conserve_interp */
+void ref_regrid_apply_through(RefRegrid *r, void *apply_fn, int interp_method, int has_missing, double missing,
+                              int nz, unsigned int extra_opcode,
+                              const double *data_in, const double *grad_x, const double *grad_y,
+                              const int *grad_mask, double *data_out)
+{
+  Field_config *fin  = (Field_config *)calloc(r->ntiles_in, sizeof(Field_config));
+  Field_config *fout = (Field_config *)calloc(1, sizeof(Field_config));
+  Var_config *var = (Var_config *)calloc(1, sizeof(Var_config));
+  size_t offd = 0, offg = 0, offm = 0;
+  int n, halo = (interp_method == CONSERVE_ORDER2) ? 1 : 0;
+  strcpy(var->name, "f");
+  var->interp_method = interp_method;
+  var->has_missing = has_missing;
+  var->missing = missing;
+  for(n=0; n<r->ntiles_in; n++) {
+    size_t nx = r->gin[n].nx, ny = r->gin[n].ny;
+    fin[n].var = var;
+    fin[n].data = (double *)(data_in + offd);
+    offd += (nx+2*halo)*(ny+2*halo)*nz;
+    if(halo) {
+      fin[n].grad_x = (double *)(grad_x + offg);
+      fin[n].grad_y = (double *)(grad_y + offg);
+      fin[n].grad_mask = (int *)(grad_mask + offm);
+      offg += nx*ny*nz;
+      offm += nx*ny;
+    }
+  }
+  fout[0].var = var;
+  fout[0].data = data_out;
+  ((apply_fn_t)apply_fn)(r->interp, 0, r->ntiles_in, r->gin, 1, r->gout, fin, fout,
+                         (r->opcode | extra_opcode) & ~(CHECK_CONSERVE|LEGACY_CLIP), nz);
+  free(fin); free(fout); free(var);
+}

@@ -195,3 +195,65 @@ def test_set_xgrid_from_host_lists_and_device_buffers(pkg):
     o1 = p.apply(1, f.reshape(-1), nf).reshape(nf, -1)
     for k in range(nf):
         assert np.array_equal(o1[k], xgtest.oracle_apply(x, 1, c.tiles, f[k], c.nlon, c.nlat)), k
+
+
+def test_reference_signature_setup_and_apply_through_real_structs(pkg):
+    """the drop-in claim end to end: the reference's own driver code (oracle/ref_driver.c, compiled against the real headers)
+    builds Grid_config / Field_config structs and calls libxgrid_b200's setup_conserve_interp and do_scalar_conserve_interp
+    through function pointers; lists and remapped fields equal the reference's own, bit for bit"""
+    import ctypes as C
+    R = xgtest.ref_lib()
+    if R is None:
+        pytest.skip("oracle/_ref not built")
+    L = pkg.lib()
+    setup_fn = C.cast(L.setup_conserve_interp, C.c_void_p)
+    apply_fn = C.cast(L.do_scalar_conserve_interp, C.c_void_p)
+    ni, nlon, nlat = 12, 48, 24
+    lonc, latc, lont, latt = pkg.cubed_sphere_grid(ni, centers=True)
+    lon2, lat2 = pkg.latlon_grid(nlon, nlat)
+    hm = xgtest.cubed_sphere_halo_map(lonc, latc)
+    nh, nc = (ni + 2) ** 2, ni * ni
+    rng = np.random.default_rng(17)
+    for order in (1, 2):
+        ref = xgtest.ref_setup(lonc, latc, lon2, lat2, order, keep=True)
+        devnull = os.open(os.devnull, os.O_WRONLY); saved = os.dup(1); os.dup2(devnull, 1)      # the NOTE line
+        try:
+            h = R.ref_regrid_setup_through(ref["handle"], setup_fn)
+        finally:
+            os.dup2(saved, 1); os.close(saved); os.close(devnull)
+        n = R.ref_regrid_nxgrid(h)
+        assert n == ref["nxgrid"]
+        out = xgtest._alloc(n, order)
+        R.ref_regrid_get(h, out["t_in"], out["i_in"], out["j_in"], out["i_out"], out["j_out"], out["area"],
+                         out["di"].ctypes.data if order == 2 else None, out["dj"].ctypes.data if order == 2 else None)
+        for k in out:
+            assert np.array_equal(out[k], ref[k]), (order, k)
+        # fields: two levels in one call (nz = 2), tile-major with the levels inside each tile like Field_config.data
+        f = rng.uniform(0, 1, (2, 6, nc))
+        if order == 1:
+            data = np.ascontiguousarray(f.transpose(1, 0, 2)).reshape(-1)
+            gx = gy = gm = None
+        else:
+            fh = np.stack([xgtest.with_halo(f[k].reshape(-1), hm).reshape(6, nh) for k in range(2)])
+            data = np.ascontiguousarray(fh.transpose(1, 0, 2)).reshape(-1)
+            gx = rng.normal(size=(6, 2, nc)).reshape(-1); gy = rng.normal(size=(6, 2, nc)).reshape(-1)
+            gm = np.zeros(6 * nc, np.int32)
+        want = np.zeros(2 * nlon * nlat); got = np.zeros(2 * nlon * nlat)
+        ptr = lambda a: None if a is None else a.ctypes.data
+        R.ref_regrid_apply(ref["handle"], order, 0, 0.0, 0, 2, 0, data, ptr(gx), ptr(gy), ptr(gm), want)
+        R.ref_regrid_apply_through(h, apply_fn, order, 0, 0.0, 2, 0, data, ptr(gx), ptr(gy), ptr(gm), got)
+        assert np.array_equal(got, want), order
+        # one level with missing values and the monotone limiter
+        if order == 2:
+            f1 = f[0].reshape(-1).copy(); f1[rng.uniform(size=f1.size) < 0.05] = -999.0
+            d1 = xgtest.with_halo(f1, hm)
+            p = pkg.XgridPlan(0)       # gradients from the library itself, reference metrics not needed for this comparison
+            g1x = rng.normal(size=6 * nc); g1y = rng.normal(size=6 * nc)
+            g1m = np.concatenate([xgtest.grad_mask(ni, ni, d1[t * nh:(t + 1) * nh], -999.0) for t in range(6)])
+            for extra in (0, xgtest.MONOTONIC):
+                want = np.zeros(nlon * nlat); got = np.zeros(nlon * nlat)
+                R.ref_regrid_apply(ref["handle"], 2, 1, -999.0, 0, 1, extra, d1, g1x.ctypes.data, g1y.ctypes.data, g1m.ctypes.data, want)
+                R.ref_regrid_apply_through(h, apply_fn, 2, 1, -999.0, 1, extra, d1, g1x.ctypes.data, g1y.ctypes.data, g1m.ctypes.data, got)
+                assert np.array_equal(got, want), extra
+            p.close()
+        R.ref_regrid_free(ref["handle"])

@@ -13,7 +13,7 @@ def _declared_symbols():
     text = open(os.path.join(xgtest.ROOT, "include", "xgrid_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     names = set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", text))
-    return sorted(n for n in names if n.startswith(("xgb_", "create_xgrid", "get_")) and n != "xgb_plan")
+    return sorted(n for n in names if n.startswith(("xgb_", "create_xgrid", "get_", "setup_conserve", "do_scalar_conserve")) and n != "xgb_plan")
 
 
 def test_all_declared_symbols_are_exported(pkg):
@@ -46,3 +46,14 @@ def test_host_side_grid_helpers(pkg):
     assert lonc.shape == (6, 5, 5)
     # tile 3 (index 2) holds the north pole at its centre vertex, tile 6 the south pole (create_gnomonic_cubic_grid.c:1691-1743)
     assert latc[2, 2, 2] == np.pi / 2 and latc[5, 2, 2] == -np.pi / 2
+
+
+def test_struct_layout_matches_reference(pkg, reflib):
+    """csrc/fregrid_abi.h mirrors Grid_config / Interp_config / Field_config / Var_config: sizeof and the offsets of every member
+    the library reads equal the compiled reference's (oracle/ref_driver.c ref_abi_layout, built from the real headers)"""
+    L = pkg.lib()
+    L.xgb_abi_layout.argtypes = [C.POINTER(C.c_size_t), C.c_int]
+    a = (C.c_size_t * 64)(); b = (C.c_size_t * 64)()
+    na = L.xgb_abi_layout(a, 64); nb = reflib.ref_abi_layout(b, 64)
+    assert na == nb and na >= 30
+    assert list(a)[:na] == list(b)[:nb]

@@ -126,6 +126,10 @@ def ref_lib():
         L.ref_regrid_apply.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_uint, dp, vp, vp, vp, dp]
         L.ref_regrid_free.argtypes = [vp]
         L.ref_compute_extent.argtypes = [C.c_int, C.c_int, ip, ip]
+        L.ref_abi_layout.argtypes = [C.POINTER(C.c_size_t), C.c_int]
+        L.ref_regrid_setup_through.restype = vp
+        L.ref_regrid_setup_through.argtypes = [vp, vp]
+        L.ref_regrid_apply_through.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint, dp, vp, vp, vp, dp]
         L.fix_lon.argtypes = [dp, dp, C.c_int, C.c_double]
         L.poly_area.restype = C.c_double
         L.poly_area.argtypes = [dp, dp, C.c_int]
