@@ -432,12 +432,15 @@ __device__ __forceinline__ int clip_cell(double* ax, double* ay, double* bx, dou
 // Every emitted number is produced by the same operations as in clip_cell, so results are bit-identical.  Returns -1
 // (caller falls back to the generic routine) when a stage has more than two crossings (non-convex input) or would
 // exceed kFastCap vertices.
-__device__ __forceinline__ int clip_cell_fast(double* ax, double* ay, double* bx, double* by,
-                                              const double (&ex)[4], const double (&ey)[4], int n1, int n2,
-                                              double** rx, double** ry, int* err)
+__device__ __forceinline__ int clip_cell_fast(double* sbase, const double (&ex)[4], const double (&ey)[4], int n1, int n2,
+                                              int* result_buf, int* err)
 {
+  // sbase = this thread's column of the block's polygon storage: buffer b, coordinate c, vertex k at
+  // sbase[((2*b + c)*kFastCap + k) * kClipThreads].  The current buffer is an integer, not a pair of pointers: the state
+  // carried across the (divergent) stages is cur, np and the previous destination vertex only.
   constexpr int S = kClipThreads;
-  double *cx = ax, *cy = ay, *ox = bx, *oy = by;
+  constexpr int P = kFastCap * kClipThreads;                     // one coordinate plane
+  int cur = 0;
   int np = (n2 > 4) ? -1 : n1;                                    // pole-adjacent destination cells: generic routine
   double ex0 = (n2 == 4) ? ex[3] : ex[2], ey0 = (n2 == 4) ? ey[3] : ey[2];
   // single exit: np <= 0 (empty, or -1 = needs the generic routine) simply skips the remaining edges, so the warp
@@ -447,6 +450,8 @@ __device__ __forceinline__ int clip_cell_fast(double* ax, double* ay, double* bx
     if (e < n2 && np > 0) {
       const double ex1 = ex[e], ey1 = ey[e];
       const double edy = ey1 - ey0, endx = ex0 - ex1;             // (y1-y0), (x0-x1) of inside_edge
+      const double* cx = sbase + (2 * cur) * P;
+      const double* cy = cx + P;
       unsigned in = 0;
       for (int k = 0; k < np; ++k) {
         const double qx = cx[k * S], qy = cy[k * S];
@@ -459,6 +464,8 @@ __device__ __forceinline__ int clip_cell_fast(double* ax, double* ay, double* bx
         const unsigned cross = in ^ prev;
         if (__popc(cross) != 2 || np + 1 > kFastCap) np = -1;
         else {
+          double* ox = sbase + (2 * (cur ^ 1)) * P;
+          double* oy = ox + P;
           const int k0 = __ffs(cross) - 1, k1 = 31 - __clz(cross);
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
@@ -480,16 +487,14 @@ __device__ __forceinline__ int clip_cell_fast(double* ax, double* ay, double* bx
             if ((in >> k) & 1u) { ox[pos * S] = qx; oy[pos * S] = qy; }
           }
           np = __popc(in) + 2;
-          double* t;
-          t = cx; cx = ox; ox = t;
-          t = cy; cy = oy; oy = t;
+          cur ^= 1;
         }
       }
       ex0 = ex1; ey0 = ey1;
     }
     __syncwarp();
   }
-  *rx = cx; *ry = cy;
+  *result_buf = cur;
   return np;
 }
 
@@ -552,7 +557,11 @@ clip_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const int
     }
   }
   __syncwarp();
-  n_out = clip_cell_fast(ax, ay, bx, by, ex, ey, n1, n2, &rx, &ry, err);   // all lanes; n2 == 0 does nothing
+  {
+    int buf = 0;
+    n_out = clip_cell_fast(ax, ex, ey, n1, n2, &buf, err);       // all lanes; n2 == 0 does nothing
+    rx = buf ? bx : ax; ry = buf ? by : ay;
+  }
   __syncwarp();
   if (n_out < 0) {
     // rare: more than 8 vertices at some stage (pole cells, non-convex cells) -> reference-sized buffers
