@@ -218,3 +218,89 @@ def test_generate_to_host_chunks_equal_one_shot(pkg, order):
     with pytest.raises(pkg.XgridError):
         plan.generate_to_host(order, small, nchunks=4)
     plan.close()
+
+
+def test_ragged_tiles_coarse_on_fine_and_fine_on_coarse(pkg):
+    """source tiles of different shapes in one mosaic; a very coarse source on a fine destination (every source cell is a
+    'heavy' cell of the candidate search and has hundreds of exchange cells) and the opposite"""
+    lon_a, lat_a = pkg.latlon_grid(7, 5, lonbegin=0.0, lonend=140.0, latbegin=-50.0, latend=20.0)
+    lon_b, lat_b = pkg.latlon_grid(13, 3, lonbegin=140.0, lonend=360.0, latbegin=-10.0, latend=80.0)
+    lon_c, lat_c = pkg.latlon_grid(4, 9, lonbegin=20.0, lonend=60.0, latbegin=20.0, latend=90.0)
+    srcs = ([lon_a, lon_b, lon_c], [lat_a, lat_b, lat_c])
+    for (nlon, nlat) in ((180, 90), (12, 6)):
+        lon2, lat2 = pkg.latlon_grid(nlon, nlat)
+        for order in (1, 2):
+            got = _gen(pkg, srcs[0], srcs[1], lon2, lat2, order)
+            ref = xgtest.oracle_setup(srcs[0], srcs[1], lon2, lat2, order)
+            sc = xgtest.parent_scale(ref, srcs[0], srcs[1], lon2, lat2)
+            xgtest.assert_xgrid_equal(got, ref, order, AREA_RTOL, DIST_ATOL, scale=sc)
+    # cubed sphere C4 on one degree: ~700 exchange cells per source cell
+    lonc, latc = pkg.cubed_sphere_grid(4)
+    lon2, lat2 = pkg.latlon_grid(360, 180)
+    got = _gen(pkg, lonc, latc, lon2, lat2, 2)
+    ref = xgtest.oracle_setup(lonc, latc, lon2, lat2, 2)
+    sc = xgtest.parent_scale(ref, lonc, latc, lon2, lat2)
+    xgtest.assert_xgrid_equal(got, ref, 2, AREA_RTOL, DIST_ATOL, scale=sc)
+    # and C96 on 10 degrees
+    lonc, latc = pkg.cubed_sphere_grid(96)
+    lon2, lat2 = pkg.latlon_grid(36, 18)
+    got = _gen(pkg, lonc, latc, lon2, lat2, 1)
+    ref = xgtest.oracle_setup(lonc, latc, lon2, lat2, 1)
+    xgtest.assert_xgrid_equal(got, ref, 1, AREA_RTOL, DIST_ATOL, scale=xgtest.parent_scale(ref, lonc, latc, lon2, lat2))
+
+
+def test_disjoint_grids_give_empty_list(pkg):
+    lon1, lat1 = pkg.latlon_grid(10, 10, lonbegin=10.0, lonend=50.0, latbegin=-40.0, latend=-5.0)
+    lon2, lat2 = pkg.latlon_grid(12, 8, lonbegin=100.0, lonend=160.0, latbegin=10.0, latend=60.0)
+    for opcode in (1, 2, 1 | xgtest.GREAT_CIRCLE):
+        plan = pkg.XgridPlan(0)
+        plan.set_dst(lon2, lat2)
+        plan.set_src([lon1], [lat1])
+        assert plan.generate(opcode) == 0
+        r = plan.result_host()
+        assert all(v.size == 0 for v in r.values())
+        plan.close()
+    assert xgtest.oracle_setup([lon1], [lat1], lon2, lat2, 1)["nxgrid"] == 0
+
+
+def test_c768_eighth_degree_full_size_properties(pkg):
+    """BASELINE configs[3] at full size (the bench workload): C768 -> 2880x1440 order 2.  The oracle needs minutes for it;
+    size-independent properties instead: known cell count, reference emission order without duplicates, exchange areas
+    tile the sphere and every destination cell, windows concatenate to the whole, tile1_distance is centred."""
+    n1, nlon, nlat = 768, 2880, 1440
+    lonc, latc = pkg.cubed_sphere_grid(n1)
+    lon2, lat2 = pkg.latlon_grid(nlon, nlat)
+    plan = pkg.XgridPlan(0)
+    plan.set_dst(lon2, lat2)
+    plan.set_src(lonc, latc)
+    n = plan.generate(2)
+    assert n == 16673872                                  # first measured with this library; equals bench.py's config.nxgrid
+    r = plan.result_host()
+    a_src = plan.src_area(); a_dst = plan.dst_area()
+    s = r["t_in"].astype(np.int64) * n1 * n1 + r["j_in"].astype(np.int64) * n1 + r["i_in"]
+    d = r["j_out"].astype(np.int64) * nlon + r["i_out"]
+    assert np.all(np.diff(s * (nlon * nlat) + d) > 0)
+    assert abs(r["area"].sum() / (4 * np.pi * xgtest.RADIUS ** 2) - 1) < 1e-9
+    per_dst = np.bincount(d, weights=r["area"], minlength=a_dst.size)
+    assert np.max(np.abs(per_dst - a_dst) / a_dst) < 2e-4
+    per_src = np.bincount(s, weights=r["area"], minlength=a_src.size)
+    assert np.max(np.abs(per_src - a_src) / a_src) < 2e-4
+    # tile1_distance: area-weighted mean over a source cell's exchange cells vanishes where the cell is fully covered
+    mx = np.bincount(s, weights=r["area"] * r["di"], minlength=a_src.size) / per_src
+    my = np.bincount(s, weights=r["area"] * r["dj"], minlength=a_src.size) / per_src
+    assert np.percentile(np.abs(mx), 99) < 1e-9 and np.percentile(np.abs(my), 99) < 1e-9
+    # a checksum of the integer lists that the 2-window run must reproduce
+    chk = int(np.bitwise_xor.reduce((s * 1315423911 + d * 2654435761) & 0xffffffffffff))
+    bounds = plan.partition(2)
+    parts = []
+    for a, b in zip(bounds, bounds[1:]):
+        plan.set_src_window(a, b)
+        plan.generate(2)
+        parts.append(plan.result_host())
+    plan.close()
+    assert sum(p["area"].size for p in parts) == n
+    s2 = np.concatenate([p["t_in"].astype(np.int64) * n1 * n1 + p["j_in"].astype(np.int64) * n1 + p["i_in"] for p in parts])
+    d2 = np.concatenate([p["j_out"].astype(np.int64) * nlon + p["i_out"] for p in parts])
+    assert int(np.bitwise_xor.reduce((s2 * 1315423911 + d2 * 2654435761) & 0xffffffffffff)) == chk
+    assert np.array_equal(np.concatenate([p["area"] for p in parts]), r["area"])
+    assert np.array_equal(np.concatenate([p["di"] for p in parts]), r["di"])
