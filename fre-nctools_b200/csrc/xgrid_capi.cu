@@ -104,7 +104,7 @@ extern "C" void xgb_plan_destroy(xgb_plan* p)
   cudaSetDevice(p->device);
   cudaStreamSynchronize(p->st);
   DevBuf* bufs[] = {&p->dst_lon, &p->dst_lat, &p->dst_store, &p->pyr_store, &p->src_lon, &p->src_lat, &p->mask,
-                    &p->src_store, &p->tiles_dev, &p->cnt, &p->pair_off, &p->out_off, &p->pairs, &p->parea,
+                    &p->src_store, &p->tiles_dev, &p->cnt, &p->pair_off, &p->pair_cnt, &p->out_off, &p->pairs, &p->parea,
                     &p->pclon, &p->pclat, &p->scan_tmp, &p->t_in, &p->i_in, &p->j_in, &p->i_out, &p->j_out,
                     &p->area, &p->clon, &p->clat, &p->di, &p->dj, &p->bounds_dev,
                     &p->heavy_ctl, &p->heavy_flag, &p->heavy_list, &p->heavy_items, &p->heavy_pairs,
@@ -257,11 +257,13 @@ extern "C" int xgb_plan_set_src_window(xgb_plan* p, long long begin, long long e
 // count pass + scan over [s0, s0+ns); leaves pair_off (ns+1 entries) and the total on the host
 static int heavy_work(xgb_plan* p, long long ns, HeavyWork* hw)
 {
-  // capacity of the heavy-cell work lists; generous for pole caps, overridable for coarse-on-fine regridding
+  // capacity of the heavy-cell work lists; grown automatically when a pass overflows (generate_window), XGB_HEAVY_CAP
+  // presets it
   size_t cap = (size_t)1 << 20;
   const size_t quarter = (size_t)(ns + p->dst.ncell) / 4;
   if (quarter > cap) cap = quarter;
-  if (const char* env = getenv("XGB_HEAVY_CAP")) cap = (size_t)atoll(env);
+  if (p->heavy_cap > cap) cap = p->heavy_cap;
+  if (const char* env = getenv("XGB_HEAVY_CAP")) { const size_t v = (size_t)atoll(env); if (v > cap) cap = v; }
   if (p->heavy_ctl.reserve(sizeof(HeavyCtl)) || p->heavy_flag.reserve((size_t)ns + 16) ||
       p->heavy_list.reserve((size_t)(ns + 1) * sizeof(int)) || p->heavy_items.reserve(2 * cap * sizeof(int2)) ||
       p->heavy_pairs.reserve(cap * sizeof(int2)))
@@ -283,11 +285,18 @@ static int count_candidates(xgb_plan* p, long long s0, long long ns, unsigned lo
     return 1;
   HeavyWork hw;
   if (heavy_work(p, ns, &hw)) return 1;
-  launch_candidates(false, p->src, s0, ns, p->has_mask ? (const double*)p->mask.p : nullptr, p->pyr, p->dst,
-                    nullptr, (uint32_t*)p->cnt.p, nullptr, hw, p->err_dev, p->st);
-  launch_exclusive_scan((const uint32_t*)p->cnt.p, (uint32_t*)p->pair_off.p, ns, p->total_dev, p->scan_tmp.p, p->st);
-  launch_publish(p->total_host, p->total_dev, 2, p->st);
-  CU_OK(cudaStreamSynchronize(p->st));
+  for (int attempt = 0;; ++attempt) {
+    launch_candidates_count(p->src, s0, ns, p->has_mask ? (const double*)p->mask.p : nullptr, p->pyr, p->dst,
+                            (uint32_t*)p->cnt.p, hw, p->err_dev, p->st);
+    launch_exclusive_scan((const uint32_t*)p->cnt.p, (uint32_t*)p->pair_off.p, ns, p->total_dev, p->scan_tmp.p, p->st);
+    launch_publish(p->total_host, p->total_dev, 2, p->st);
+    launch_publish(p->err_host, p->err_dev, 1, p->st);
+    CU_OK(cudaStreamSynchronize(p->st));
+    if (*p->err_host != kErrHeavyOverflow || attempt >= 8) break;
+    p->heavy_cap = (size_t)hw.cap * 2;                    // work lists too small (coarse source on fine destination)
+    cudaMemsetAsync(p->err_dev, 0, sizeof(int), p->st);
+    if (heavy_work(p, ns, &hw)) return 1;
+  }
   *total = p->total_host[0];
   if (*total >= (1ull << 32)) { xgb_set_error("more than 2^32 candidate pairs in one window; shard the source cells"); return 1; }
   return 0;
@@ -316,20 +325,46 @@ static long long generate_window(xgb_plan* p, int order, long long s0, long long
   const double* mask = p->has_mask ? (const double*)p->mask.p : nullptr;
   unsigned long long npairs = 0;
   cudaEventRecord(p->ev[0], p->st);
-  if (count_candidates(p, s0, ns, &npairs)) return -1;
-  p->npairs = npairs;
-  cudaEventRecord(p->ev[1], p->st);
-
-  if (p->pairs.reserve((size_t)npairs * sizeof(int2) + 16) || p->parea.reserve((size_t)npairs * sizeof(double) + 16) ||
-      p->out_off.reserve((size_t)(ns + 1) * sizeof(uint32_t)))
+  if (p->cnt.reserve((size_t)(ns + 1) * sizeof(uint32_t)) || p->pair_off.reserve((size_t)(ns + 1) * sizeof(uint32_t)) ||
+      p->pair_cnt.reserve((size_t)(ns + 1) * sizeof(uint32_t)) || p->out_off.reserve((size_t)(ns + 1) * sizeof(uint32_t)) ||
+      p->scan_tmp.reserve(scan_tmp_bytes(ns)))
     return -1;
-  if (order == 2 && (p->pclon.reserve((size_t)npairs * sizeof(double) + 16) || p->pclat.reserve((size_t)npairs * sizeof(double) + 16)))
-    return -1;
-
   HeavyWork hw;
   if (heavy_work(p, ns, &hw)) return -1;
-  launch_candidates(true, p->src, s0, ns, mask, p->pyr, p->dst, (const uint32_t*)p->pair_off.p,
-                    (uint32_t*)p->cnt.p, (int2*)p->pairs.p, hw, p->err_dev, p->st);
+  // single-pass candidate search into pair buffers sized from the last generate (first call: 8 pairs per source cell);
+  // the kernels drop what does not fit and report the true total, then the buffers grow and the pass is repeated
+  size_t cap = p->pairs_cap ? p->pairs_cap : (size_t)ns * 8 + (1u << 20);
+  for (int attempt = 0;; ++attempt) {
+    if (p->pairs.reserve(cap * sizeof(int2) + 16) || p->parea.reserve(cap * sizeof(double) + 16)) return -1;
+    if (order == 2 && (p->pclon.reserve(cap * sizeof(double) + 16) || p->pclat.reserve(cap * sizeof(double) + 16))) return -1;
+    cudaMemsetAsync(p->cnt.p, 0, (size_t)(ns + 1) * sizeof(uint32_t), p->st);
+    launch_candidates_single(p->src, s0, ns, mask, p->pyr, p->dst, (uint32_t*)p->pair_off.p, (uint32_t*)p->pair_cnt.p,
+                             (int2*)p->pairs.p, cap, (uint32_t*)p->cnt.p, hw, p->err_dev, p->st);
+    launch_publish(p->total_host, &hw.ctl->total, 4, p->st);          // total (2 words), nheavy, npairs of the heavy path
+    launch_publish(p->err_host, p->err_dev, 1, p->st);
+    if (cudaStreamSynchronize(p->st) != cudaSuccess) {
+      xgb_set_error("candidate search failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return -1;
+    }
+    if (*p->err_host == kErrHeavyOverflow && attempt < 8) {
+      // the level-synchronous work lists were too small (coarse source on a fine destination): grow and repeat
+      const unsigned heavy_pairs = ((const unsigned*)p->total_host)[3];
+      size_t want = (size_t)hw.cap * 2;
+      if ((size_t)heavy_pairs + heavy_pairs / 8 > want) want = (size_t)heavy_pairs + heavy_pairs / 8;
+      p->heavy_cap = want;
+      cudaMemsetAsync(p->err_dev, 0, sizeof(int), p->st);
+      if (heavy_work(p, ns, &hw)) return -1;
+      continue;
+    }
+    npairs = p->total_host[0];
+    if (npairs >= (1ull << 32)) { xgb_set_error("more than 2^32 candidate pairs in one window; shard the source cells"); return -1; }
+    if (npairs <= cap) break;
+    if (attempt > 9) { xgb_set_error("candidate search: pair buffers keep overflowing"); return -1; }
+    cap = (size_t)npairs + (size_t)npairs / 16 + 1024;
+  }
+  p->pairs_cap = cap;
+  p->npairs = npairs;
+  cudaEventRecord(p->ev[1], p->st);
   cudaMemsetAsync(p->cnt.p, 0, (size_t)(ns + 1) * sizeof(uint32_t), p->st);
   cudaEventRecord(p->ev[2], p->st);
   launch_clip(order, p->src, p->dst, mask, (const int2*)p->pairs.p, npairs, s0,
@@ -357,7 +392,7 @@ static long long generate_window(xgb_plan* p, int order, long long s0, long long
 
   cudaEventRecord(p->ev[4], p->st);
   launch_scatter(order, (const int2*)p->pairs.p, npairs, (const double*)p->parea.p, (const double*)p->pclon.p,
-                 (const double*)p->pclat.p, (const uint32_t*)p->pair_off.p, (const uint32_t*)p->out_off.p,
+                 (const double*)p->pclat.p, (const uint32_t*)p->pair_off.p, (const uint32_t*)p->pair_cnt.p, (const uint32_t*)p->out_off.p,
                  (const TileDesc*)p->tiles_dev.p, (int)p->tiles.size(), s0, p->nx2,
                  (int*)p->t_in.p + base, (int*)p->i_in.p + base, (int*)p->j_in.p + base, (int*)p->i_out.p + base, (int*)p->j_out.p + base,
                  (double*)p->area.p + base, (double*)p->clon.p + (order == 2 ? base : 0), (double*)p->clat.p + (order == 2 ? base : 0), p->st);

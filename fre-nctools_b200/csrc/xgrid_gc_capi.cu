@@ -76,12 +76,13 @@ long long xgb_generate_great_circle(xgb_plan* p, int order)
   if (gc_prepare(p)) return -1;
   const long long s0 = p->s0, ns = p->ns;
   const double* mask = p->has_mask ? (const double*)p->mask.p : nullptr;
-  if (p->cnt.reserve((size_t)(ns + 1) * 4) || p->pair_off.reserve((size_t)(ns + 1) * 4) || p->out_off.reserve((size_t)(ns + 1) * 4) ||
+  if (p->cnt.reserve((size_t)(ns + 1) * 4) || p->pair_off.reserve((size_t)(ns + 1) * 4) || p->pair_cnt.reserve((size_t)(ns + 1) * 4) ||
+      p->out_off.reserve((size_t)(ns + 1) * 4) ||
       p->scan_tmp.reserve(scan_tmp_bytes(ns)))
     return -1;
   cudaEventRecord(p->ev[0], p->st);
-  launch_gc_candidates(false, p->gc_src, s0, ns, mask, p->gc_pyr, nullptr, (uint32_t*)p->cnt.p, nullptr, p->err_dev, p->st);
-  launch_exclusive_scan((const uint32_t*)p->cnt.p, (uint32_t*)p->pair_off.p, ns, p->total_dev, p->scan_tmp.p, p->st);
+  launch_gc_candidates(false, p->gc_src, s0, ns, mask, p->gc_pyr, nullptr, (uint32_t*)p->pair_cnt.p, nullptr, p->err_dev, p->st);
+  launch_exclusive_scan((const uint32_t*)p->pair_cnt.p, (uint32_t*)p->pair_off.p, ns, p->total_dev, p->scan_tmp.p, p->st);
   launch_publish(p->total_host, p->total_dev, 2, p->st);
   if (cudaStreamSynchronize(p->st) != cudaSuccess) {
     xgb_set_error("great-circle candidate search failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -92,7 +93,7 @@ long long xgb_generate_great_circle(xgb_plan* p, int order)
   p->npairs = npairs;
   cudaEventRecord(p->ev[1], p->st);
   if (p->pairs.reserve((size_t)npairs * sizeof(int2) + 16) || p->parea.reserve((size_t)npairs * 8 + 16)) return -1;
-  launch_gc_candidates(true, p->gc_src, s0, ns, mask, p->gc_pyr, (const uint32_t*)p->pair_off.p, (uint32_t*)p->cnt.p,
+  launch_gc_candidates(true, p->gc_src, s0, ns, mask, p->gc_pyr, (const uint32_t*)p->pair_off.p, (uint32_t*)p->pair_cnt.p,
                        (int2*)p->pairs.p, p->err_dev, p->st);
   cudaMemsetAsync(p->cnt.p, 0, (size_t)(ns + 1) * 4, p->st);
   cudaEventRecord(p->ev[2], p->st);
@@ -113,7 +114,7 @@ long long xgb_generate_great_circle(xgb_plan* p, int order)
     return -1;
   cudaEventRecord(p->ev[4], p->st);
   launch_scatter(1, (const int2*)p->pairs.p, npairs, (const double*)p->parea.p, nullptr, nullptr, (const uint32_t*)p->pair_off.p,
-                 (const uint32_t*)p->out_off.p, (const TileDesc*)p->tiles_dev.p, (int)p->tiles.size(), s0, p->nx2,
+                 (const uint32_t*)p->pair_cnt.p, (const uint32_t*)p->out_off.p, (const TileDesc*)p->tiles_dev.p, (int)p->tiles.size(), s0, p->nx2,
                  (int*)p->t_in.p, (int*)p->i_in.p, (int*)p->j_in.p, (int*)p->i_out.p, (int*)p->j_out.p, (double*)p->area.p,
                  nullptr, nullptr, p->st);
   cudaEventRecord(p->ev[5], p->st);

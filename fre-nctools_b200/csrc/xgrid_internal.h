@@ -50,7 +50,7 @@ enum : int {
 };
 
 // device-side control block and work buffers of the level-synchronous "heavy cell" candidate path
-struct HeavyCtl { unsigned nheavy; unsigned npairs; unsigned nitems[kMaxLevels]; };
+struct HeavyCtl { unsigned long long total; unsigned nheavy; unsigned npairs; unsigned nitems[kMaxLevels]; };
 struct HeavyWork {
   HeavyCtl* ctl;
   unsigned char* flag;   // [ns]
@@ -64,15 +64,17 @@ struct HeavyWork {
 void launch_cell_precompute(const TileDesc& tile, const double* lon, const double* lat,
                             CellSet cells, int* err, cudaStream_t st);
 void launch_pyramid_level(const PyrLevel& child, Box* out, int nx, int ny, cudaStream_t st);
-void launch_candidates(bool fill, const CellSet& src, long long s0, long long ns, const double* mask,
-                       const Pyramid& pyr, const CellSet& dst, const uint32_t* pair_off,
-                       uint32_t* cnt, int2* pairs, const HeavyWork& hw, int* err, cudaStream_t st);
+void launch_candidates_count(const CellSet& src, long long s0, long long ns, const double* mask,
+                             const Pyramid& pyr, const CellSet& dst, uint32_t* cnt, const HeavyWork& hw, int* err, cudaStream_t st);
+void launch_candidates_single(const CellSet& src, long long s0, long long ns, const double* mask,
+                              const Pyramid& pyr, const CellSet& dst, uint32_t* pair_off, uint32_t* pair_cnt, int2* pairs,
+                              unsigned long long pair_cap, uint32_t* cursor, const HeavyWork& hw, int* err, cudaStream_t st);
 void launch_clip(int order, const CellSet& src, const CellSet& dst, const double* mask,
                  const int2* pairs, unsigned long long npairs, long long s0,
                  double* parea, double* pclon, double* pclat, uint32_t* cnt, int* err, cudaStream_t st);
 void launch_scatter(int order, const int2* pairs, unsigned long long npairs,
                     const double* parea, const double* pclon, const double* pclat,
-                    const uint32_t* pair_off, const uint32_t* out_off,
+                    const uint32_t* pair_off, const uint32_t* pair_cnt, const uint32_t* out_off,
                     const TileDesc* tiles, int ntiles, long long s0, int nx2,
                     int* t_in, int* i_in, int* j_in, int* i_out, int* j_out,
                     double* area, double* clon, double* clat, cudaStream_t st);

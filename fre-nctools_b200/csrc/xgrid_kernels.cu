@@ -243,6 +243,107 @@ candidate_kernel(CellSet src, long long s0, long long ns, const double* __restri
   }
 }
 
+// Single pass: the walk buffers a cell's candidates (a handful) in thread-local storage, the warp reserves space for all
+// its cells with one atomicAdd and writes them out; no second walk, no prefix sum.  pair_off[t] / pair_cnt[t] describe
+// the cell's segment (segments of different cells are in reservation order, which only affects locality).  Cells with
+// more than kSingleMax candidates, or too many node expansions, take the heavy path exactly as in the count pass.
+// Writes are dropped when the pair buffer (cap entries) is too small; the host sees ctl->total > cap and retries.
+constexpr int kSingleMax = 96;   // thread-local buffer; beyond it the cell goes to the heavy path
+
+__global__ void __launch_bounds__(128)
+candidate_single_kernel(CellSet src, long long s0, long long ns, const double* __restrict__ mask,
+                        Pyramid pyr, CellSet dst, uint32_t* __restrict__ pair_off, uint32_t* __restrict__ pair_cnt,
+                        int2* __restrict__ pairs, unsigned long long cap,
+                        unsigned char* __restrict__ heavy_flag, int* __restrict__ heavy_list, HeavyCtl* ctl, int* err)
+{
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const bool valid = t < ns;
+  const long long s = s0 + (valid ? t : 0);
+  int buf[kSingleMax];
+  uint32_t n = 0;
+  bool heavy = false;
+  if (valid && (mask == nullptr || mask[s] > kMaskThresh)) {
+    const SrcBox sb = load_src_box(src, s);
+    unsigned long long stack[kStack];
+    int sp = 0, steps = 0;
+    const int top = pyr.nlev - 1;
+    {
+      const PyrLevel& L = pyr.lev[top];
+      for (int iy = 0; iy < L.ny; ++iy)
+        for (int ix = 0; ix < L.nx; ++ix) {
+          const long long q = (long long)iy * L.nx + ix;
+          if (top == 0) {
+            if (leaf_hit(dst, q, sb)) { if (n < (uint32_t)kSingleMax) buf[n] = (int)q; ++n; }
+          } else if (node_hit(load_box(L.box + q), sb)) {
+            stack[sp++] = ((unsigned long long)top << 58) | ((unsigned long long)iy << 29) | (unsigned long long)ix;
+          }
+        }
+    }
+    while (sp > 0) {
+      if (top > 0 && (n > (uint32_t)kSingleMax || ++steps > kHeavySteps)) { heavy = true; break; }
+      const unsigned long long e = stack[--sp];
+      const int lev = (int)(e >> 58) - 1;                      // child level
+      const int py = (int)((e >> 29) & 0x1fffffffull), px = (int)(e & 0x1fffffffull);
+      const PyrLevel& L = pyr.lev[lev];
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const int cy = 2 * py + dy;
+        if (cy >= L.ny) continue;
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int cx = 2 * px + dx;
+          if (cx >= L.nx) continue;
+          const long long q = (long long)cy * L.nx + cx;
+          if (lev == 0) {
+            if (leaf_hit(dst, q, sb)) { if (n < (uint32_t)kSingleMax) buf[n] = (int)q; ++n; }
+          } else if (node_hit(load_box(L.box + q), sb)) {
+            if (sp < kStack) stack[sp++] = ((unsigned long long)lev << 58) | ((unsigned long long)cy << 29) | (unsigned long long)cx;
+            else atomicOr(err, kErrStackOverflow);
+          }
+        }
+      }
+    }
+    if (!heavy && n > (uint32_t)kSingleMax) {
+      if (top > 0) heavy = true;                               // the last expansion overflowed the buffer
+      else { atomicOr(err, kErrStackOverflow); n = kSingleMax; }   // no pyramid above tiny destination grids (<= 32 cells)
+    }
+  }
+  if (heavy) {
+    const unsigned slot = atomicAdd(&ctl->nheavy, 1u);
+    heavy_list[slot] = (int)t;
+    n = 0;                                                     // the heavy kernels count and place this cell's pairs
+  }
+  // one reservation per warp
+  __syncwarp();
+  const int lane = threadIdx.x & 31;
+  uint32_t incl = n;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  const uint32_t wsum = __shfl_sync(0xffffffffu, incl, 31);
+  unsigned long long wbase = 0;
+  if (lane == 31 && wsum > 0) wbase = atomicAdd(&ctl->total, (unsigned long long)wsum);
+  wbase = __shfl_sync(0xffffffffu, wbase, 31);
+  if (!valid) return;
+  const unsigned long long base = wbase + (incl - n);
+  heavy_flag[t] = heavy ? 1 : 0;
+  pair_off[t] = (uint32_t)base;
+  pair_cnt[t] = n;
+  if (base + n <= cap)
+    for (uint32_t k = 0; k < n; ++k) pairs[base + k] = make_int2((int)t, buf[k]);
+}
+
+// heavy cells: their counts are final after the last expand launch; reserve their segments
+__global__ void __launch_bounds__(128)
+heavy_reserve_kernel(HeavyCtl* ctl, const int* __restrict__ heavy_list, uint32_t* __restrict__ pair_off,
+                     const uint32_t* __restrict__ pair_cnt)
+{
+  const unsigned nh = ctl->nheavy;
+  for (unsigned h = blockIdx.x * blockDim.x + threadIdx.x; h < nh; h += gridDim.x * blockDim.x) {
+    const int t = heavy_list[h];
+    pair_off[t] = (uint32_t)atomicAdd(&ctl->total, (unsigned long long)pair_cnt[t]);
+  }
+}
+
 // ---- level-synchronous path for heavy source cells -----------------------------------------------
 // Work items are (heavy cell h, pyramid node q) pairs; one launch per pyramid level expands every item into
 // its (up to) four children, so the work of a pole cap is spread over the whole grid of threads.
@@ -310,50 +411,67 @@ heavy_expand_kernel(CellSet src, long long s0, Pyramid pyr, CellSet dst, int lev
   }
 }
 
-// after the scan: drop the heavy cells' pairs into their segments (order inside a segment is irrelevant,
-// scatter ranks by destination index); cnt[t] counts down to zero
+// drop the heavy cells' pairs into their segments (order inside a segment is irrelevant, scatter ranks by destination
+// index); cursor[t] counts up from zero (the caller zeroes it again afterwards)
 __global__ void __launch_bounds__(kHeavyThreads)
 heavy_fill_kernel(HeavyCtl* ctl, const int2* __restrict__ hpairs, const uint32_t* __restrict__ pair_off,
-                  uint32_t* __restrict__ cnt, int2* __restrict__ pairs, unsigned cap)
+                  uint32_t* __restrict__ cursor, int2* __restrict__ pairs, unsigned cap, unsigned long long pair_cap)
 {
   const unsigned n = min(ctl->npairs, cap);
   for (unsigned w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
     const int2 pr = hpairs[w];
-    const uint32_t k = atomicSub(&cnt[pr.x], 1u) - 1u;
-    pairs[pair_off[pr.x] + k] = pr;
+    const unsigned long long o = (unsigned long long)pair_off[pr.x] + atomicAdd(&cursor[pr.x], 1u);
+    if (o < pair_cap) pairs[o] = pr;
   }
 }
 
-void launch_candidates(bool fill, const CellSet& src, long long s0, long long ns, const double* mask,
-                       const Pyramid& pyr, const CellSet& dst, const uint32_t* pair_off,
-                       uint32_t* cnt, int2* pairs, const HeavyWork& hw, int* err, cudaStream_t st)
+// count pass only (xgb_plan_partition): cnt[t] = candidate pairs of source cell t, heavy cells included
+void launch_candidates_count(const CellSet& src, long long s0, long long ns, const double* mask,
+                             const Pyramid& pyr, const CellSet& dst, uint32_t* cnt, const HeavyWork& hw, int* err, cudaStream_t st)
 {
   if (ns <= 0) return;
   const int threads = 128;
   const unsigned blocks = (unsigned)((ns + threads - 1) / threads);
-  if (!fill) {
-    cudaMemsetAsync(hw.ctl, 0, sizeof(HeavyCtl), st);
+  cudaMemsetAsync(hw.ctl, 0, sizeof(HeavyCtl), st);
+  ++g_launches;
+  candidate_kernel<false><<<blocks, threads, 0, st>>>(src, s0, ns, mask, pyr, dst, nullptr, cnt, nullptr,
+                                                      hw.flag, hw.list, hw.ctl, err);
+  if (pyr.nlev > 1) {
+    const int top = pyr.nlev - 1;
     ++g_launches;
-    candidate_kernel<false><<<blocks, threads, 0, st>>>(src, s0, ns, mask, pyr, dst, pair_off, cnt, pairs,
-                                                        hw.flag, hw.list, hw.ctl, err);
-    if (pyr.nlev > 1) {
-      const int top = pyr.nlev - 1;
+    heavy_seed_kernel<<<kHeavyBlocks, kHeavyThreads, 0, st>>>(src, s0, pyr, hw.list, hw.ctl, hw.items[top & 1], hw.cap, err);
+    for (int lev = top; lev >= 1; --lev) {
       ++g_launches;
-      heavy_seed_kernel<<<kHeavyBlocks, kHeavyThreads, 0, st>>>(src, s0, pyr, hw.list, hw.ctl, hw.items[top & 1], hw.cap, err);
-      for (int lev = top; lev >= 1; --lev) {
-        ++g_launches;
-        heavy_expand_kernel<<<kHeavyBlocks, kHeavyThreads, 0, st>>>(src, s0, pyr, dst, lev, hw.list, hw.ctl, hw.items[lev & 1],
-                                                                    hw.items[(lev - 1) & 1], hw.pairs, cnt, hw.cap, err);
-      }
+      heavy_expand_kernel<<<kHeavyBlocks, kHeavyThreads, 0, st>>>(src, s0, pyr, dst, lev, hw.list, hw.ctl, hw.items[lev & 1],
+                                                                  hw.items[(lev - 1) & 1], hw.pairs, cnt, hw.cap, err);
     }
-  } else {
+  }
+}
+
+// single pass: pairs, pair_off, pair_cnt of every source cell of the window; ctl->total = number of pairs.
+// cursor: ns zeroed uint32 (left dirty).  Pairs beyond pair_cap are dropped (the caller compares ctl->total with it).
+void launch_candidates_single(const CellSet& src, long long s0, long long ns, const double* mask,
+                              const Pyramid& pyr, const CellSet& dst, uint32_t* pair_off, uint32_t* pair_cnt, int2* pairs,
+                              unsigned long long pair_cap, uint32_t* cursor, const HeavyWork& hw, int* err, cudaStream_t st)
+{
+  if (ns <= 0) return;
+  const unsigned blocks = (unsigned)((ns + 127) / 128);
+  cudaMemsetAsync(hw.ctl, 0, sizeof(HeavyCtl), st);
+  ++g_launches;
+  candidate_single_kernel<<<blocks, 128, 0, st>>>(src, s0, ns, mask, pyr, dst, pair_off, pair_cnt, pairs, pair_cap,
+                                                  hw.flag, hw.list, hw.ctl, err);
+  if (pyr.nlev > 1) {
+    const int top = pyr.nlev - 1;
     ++g_launches;
-    candidate_kernel<true><<<blocks, threads, 0, st>>>(src, s0, ns, mask, pyr, dst, pair_off, cnt, pairs,
-                                                       hw.flag, hw.list, hw.ctl, err);
-    if (pyr.nlev > 1) {
+    heavy_seed_kernel<<<kHeavyBlocks, kHeavyThreads, 0, st>>>(src, s0, pyr, hw.list, hw.ctl, hw.items[top & 1], hw.cap, err);
+    for (int lev = top; lev >= 1; --lev) {
       ++g_launches;
-      heavy_fill_kernel<<<kHeavyBlocks, kHeavyThreads, 0, st>>>(hw.ctl, hw.pairs, pair_off, cnt, pairs, hw.cap);
+      heavy_expand_kernel<<<kHeavyBlocks, kHeavyThreads, 0, st>>>(src, s0, pyr, dst, lev, hw.list, hw.ctl, hw.items[lev & 1],
+                                                                  hw.items[(lev - 1) & 1], hw.pairs, pair_cnt, hw.cap, err);
     }
+    g_launches += 2;
+    heavy_reserve_kernel<<<kHeavyBlocks, 128, 0, st>>>(hw.ctl, hw.list, pair_off, pair_cnt);
+    heavy_fill_kernel<<<kHeavyBlocks, kHeavyThreads, 0, st>>>(hw.ctl, hw.pairs, pair_off, cursor, pairs, hw.cap, pair_cap);
   }
 }
 
@@ -619,7 +737,7 @@ template <int ORDER>
 __global__ void __launch_bounds__(256)
 scatter_kernel(const int2* __restrict__ pairs, unsigned long long npairs,
                const double* __restrict__ parea, const double* __restrict__ pclon, const double* __restrict__ pclat,
-               const uint32_t* __restrict__ pair_off, const uint32_t* __restrict__ out_off,
+               const uint32_t* __restrict__ pair_off, const uint32_t* __restrict__ pair_cnt, const uint32_t* __restrict__ out_off,
                const TileDesc* __restrict__ tiles, int ntiles, long long s0, int nx2,
                int* __restrict__ t_in, int* __restrict__ i_in, int* __restrict__ j_in,
                int* __restrict__ i_out, int* __restrict__ j_out,
@@ -633,7 +751,7 @@ scatter_kernel(const int2* __restrict__ pairs, unsigned long long npairs,
   // rank among the accepted pairs of the same source cell by ascending destination index:
   // the reference visits destination cells in ascending ij for each source cell (create_xgrid.c:769)
   uint32_t rank = 0;
-  const uint32_t qb = pair_off[pr.x], qe = pair_off[pr.x + 1];
+  const uint32_t qb = pair_off[pr.x], qe = qb + pair_cnt[pr.x];
   for (uint32_t q = qb; q < qe; ++q)
     if (parea[q] > 0.0 && pairs[q].y < pr.y) ++rank;
   const size_t o = (size_t)out_off[pr.x] + rank;
@@ -651,7 +769,7 @@ scatter_kernel(const int2* __restrict__ pairs, unsigned long long npairs,
 
 void launch_scatter(int order, const int2* pairs, unsigned long long npairs,
                     const double* parea, const double* pclon, const double* pclat,
-                    const uint32_t* pair_off, const uint32_t* out_off,
+                    const uint32_t* pair_off, const uint32_t* pair_cnt, const uint32_t* out_off,
                     const TileDesc* tiles, int ntiles, long long s0, int nx2,
                     int* t_in, int* i_in, int* j_in, int* i_out, int* j_out,
                     double* area, double* clon, double* clat, cudaStream_t st)
@@ -661,10 +779,10 @@ void launch_scatter(int order, const int2* pairs, unsigned long long npairs,
   const unsigned blocks = (unsigned)((npairs + threads - 1) / threads);
   ++g_launches;
   if (order == 2)
-    scatter_kernel<2><<<blocks, threads, 0, st>>>(pairs, npairs, parea, pclon, pclat, pair_off, out_off, tiles, ntiles, s0, nx2,
+    scatter_kernel<2><<<blocks, threads, 0, st>>>(pairs, npairs, parea, pclon, pclat, pair_off, pair_cnt, out_off, tiles, ntiles, s0, nx2,
                                                   t_in, i_in, j_in, i_out, j_out, area, clon, clat);
   else
-    scatter_kernel<1><<<blocks, threads, 0, st>>>(pairs, npairs, parea, pclon, pclat, pair_off, out_off, tiles, ntiles, s0, nx2,
+    scatter_kernel<1><<<blocks, threads, 0, st>>>(pairs, npairs, parea, pclon, pclat, pair_off, pair_cnt, out_off, tiles, ntiles, s0, nx2,
                                                   t_in, i_in, j_in, i_out, j_out, area, clon, clat);
 }
 

@@ -43,7 +43,9 @@ struct xgb_plan {
   xgb::Pyramid3 gc_pyr{};
 
   // work space
-  DevBuf cnt, pair_off, out_off, pairs, parea, pclon, pclat, scan_tmp, bounds_dev;
+  DevBuf cnt, pair_off, pair_cnt, out_off, pairs, parea, pclon, pclat, scan_tmp, bounds_dev;
+  size_t heavy_cap = 0;              // entries of the heavy-cell work lists (grown on overflow)
+  size_t pairs_cap = 0;              // entries the pair buffers were last sized for (single-pass candidate search)
   DevBuf heavy_ctl, heavy_flag, heavy_list, heavy_items, heavy_pairs;
 
   // result (Interp_config layout)

@@ -304,3 +304,20 @@ def test_c768_eighth_degree_full_size_properties(pkg):
     assert int(np.bitwise_xor.reduce((s2 * 1315423911 + d2 * 2654435761) & 0xffffffffffff)) == chk
     assert np.array_equal(np.concatenate([p["area"] for p in parts]), r["area"])
     assert np.array_equal(np.concatenate([p["di"] for p in parts]), r["di"])
+
+
+def test_heavy_work_lists_grow_on_their_own(pkg):
+    """C24 on a 1/4 degree grid: every source cell has hundreds of candidates, far beyond the initial capacity of the
+    level-synchronous work lists; generation (and the partition's count pass) must grow them and still match the oracle"""
+    lonc, latc = pkg.cubed_sphere_grid(24)
+    lon2, lat2 = pkg.latlon_grid(1440, 720)
+    plan = pkg.XgridPlan(0)
+    plan.set_dst(lon2, lat2)
+    plan.set_src(lonc, latc)
+    b = plan.partition(3)
+    assert b[0] == 0 and b[-1] == 6 * 24 * 24
+    n = plan.generate(1)
+    got = plan.result_host(); got["nxgrid"] = n
+    plan.close()
+    ref = xgtest.oracle_setup(lonc, latc, lon2, lat2, 1)
+    xgtest.assert_xgrid_equal(got, ref, 1, AREA_RTOL, DIST_ATOL, scale=xgtest.parent_scale(ref, lonc, latc, lon2, lat2))
