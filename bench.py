@@ -341,6 +341,13 @@ def run_gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         dist.all_reduce(clip_ms, op=dist.ReduceOp.MAX)
+    per_rank = None
+    if world > 1:                                   # per-rank step time and phase sums, for load-balance diagnosis
+        mine_v = torch.tensor([e0.elapsed_time(e1) / args.steps, nx, npairs] + [phase_sum[k] / max(ngen, 1) for k in plan.PHASES],
+                              dtype=torch.float64, device=dev)
+        allv = torch.empty(world * mine_v.numel(), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allv, mine_v)
+        per_rank = [dict(zip(["ms", "nxgrid", "pairs"] + list(plan.PHASES), row)) for row in allv.view(world, -1).tolist()]
     ms = float(t.item())
     nx_total, npairs_total, launches_total = (int(v) for v in tot.tolist())
     value = nx_total / (ms * 1e-3)
@@ -430,7 +437,7 @@ def run_gpu_arm(args):
             "e2e": {"value": nx_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "api": f"set_dst + set_src (pinned host grids) + xgb_plan_generate_to_host in {args.e2e_chunks} pieces (pinned host result)"},
-            "roofline": roofline, "phase_ms": phases, "cpu_baseline": cpu, "apply": apply}
+            "roofline": roofline, "phase_ms": phases, "per_rank": per_rank, "cpu_baseline": cpu, "apply": apply}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -399,7 +399,7 @@ static long long generate_window(xgb_plan* p, int order, long long s0, long long
   if (order == 2)
     launch_order2_finalize(p->src, s0, ns, (const uint32_t*)p->out_off.p, (const double*)p->area.p + base,
                            (const double*)p->clon.p + base, (const double*)p->clat.p + base, (double*)p->di.p + base,
-                           (double*)p->dj.p + base, p->st);
+                           (double*)p->dj.p + base, hw.list, &hw.ctl->nheavy, p->st);   // heavy_list / counter are free again
   cudaEventRecord(p->ev[5], p->st);
   if (xgb_check_kernel_errors(p, false)) return -1;
   for (int k = 0; k < 5; ++k) {

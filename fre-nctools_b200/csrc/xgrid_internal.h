@@ -80,7 +80,7 @@ void launch_scatter(int order, const int2* pairs, unsigned long long npairs,
                     double* area, double* clon, double* clat, cudaStream_t st);
 void launch_order2_finalize(const CellSet& src, long long s0, long long ns, const uint32_t* out_off,
                             const double* area, const double* clon, const double* clat,
-                            double* di, double* dj, cudaStream_t st);
+                            double* di, double* dj, int* long_list /* ns ints */, unsigned* nlong, cudaStream_t st);
 // nwords 32-bit words from device memory to pinned host memory, by a kernel (not the copy engine)
 void launch_publish(void* host_dst, const void* dev_src, int nwords, cudaStream_t st);
 // exclusive prefix sum of n uint32 counts; out has n+1 entries (out[n] = total, must fit 32 bits);

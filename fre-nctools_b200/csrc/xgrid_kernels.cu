@@ -792,32 +792,40 @@ void launch_scatter(int order, const int2* pairs, unsigned long long npairs,
 // add in exactly the order the reference's loop at :216-221 does.
 // clon/clat hold xgrid_clon/xgrid_clat on entry; di/dj receive tile1_distance.
 // =============================================================================================
+constexpr uint32_t kLongSegment = 64;     // source cells with more exchange cells than this are summed by a whole warp
+
+// centroid of a source cell from the sums over its exchange cells (conserve_interp.c:326-348)
+__device__ __forceinline__ void cell_centroid(const CellSet& src, long long s, double sa, double sx, double sy, double* cx, double* cy)
+{
+  *cx = 0.0; *cy = 0.0;
+  if (!(sa > 0)) return;
+  const double cell_area = src.area[s];
+  if (fabs(sa - cell_area) / cell_area < 1.e-3) {              // AREA_RATIO, conserve_interp.c:35,:330
+    *cx = sx / sa; *cy = sy / sa;
+  } else {                                                     // :334-347 analytic centroid of the cell
+    double x[kMaxV], y[kMaxV];
+    const int n = src.nv[s];
+    for (int k = 0; k < n; ++k) { x[k] = src.vx[(long long)k * src.ncell + s]; y[k] = src.vy[(long long)k * src.ncell + s]; }
+    PolyView pv{x, y, 1};
+    *cx = poly_ctrlon(pv, n, src.xavg[s]) / cell_area;
+    *cy = poly_ctrlat(pv, n) / cell_area;
+  }
+}
+
 __global__ void __launch_bounds__(128)
 order2_finalize_kernel(CellSet src, long long s0, long long ns, const uint32_t* __restrict__ out_off,
                        const double* __restrict__ area, const double* __restrict__ clon, const double* __restrict__ clat,
-                       double* __restrict__ di, double* __restrict__ dj)
+                       double* __restrict__ di, double* __restrict__ dj, int* __restrict__ long_list, unsigned* __restrict__ nlong)
 {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= ns) return;
   const uint32_t b = out_off[t], e = out_off[t + 1];
   if (b == e) return;
+  if (e - b > kLongSegment) { long_list[atomicAdd(nlong, 1u)] = (int)t; return; }
   double sa = 0.0, sx = 0.0, sy = 0.0;
   for (uint32_t k = b; k < e; ++k) { sa += area[k]; sx += clon[k]; sy += clat[k]; }
-  double cx = 0.0, cy = 0.0;
-  if (sa > 0) {
-    const long long s = s0 + t;
-    const double cell_area = src.area[s];
-    if (fabs(sa - cell_area) / cell_area < 1.e-3) {              // AREA_RATIO, conserve_interp.c:35,:330
-      cx = sx / sa; cy = sy / sa;
-    } else {                                                     // :334-347 analytic centroid of the cell
-      double x[kMaxV], y[kMaxV];
-      const int n = src.nv[s];
-      for (int k = 0; k < n; ++k) { x[k] = src.vx[(long long)k * src.ncell + s]; y[k] = src.vy[(long long)k * src.ncell + s]; }
-      PolyView pv{x, y, 1};
-      cx = poly_ctrlon(pv, n, src.xavg[s]) / cell_area;
-      cy = poly_ctrlat(pv, n) / cell_area;
-    }
-  }
+  double cx, cy;
+  cell_centroid(src, s0 + t, sa, sx, sy, &cx, &cy);
   for (uint32_t k = b; k < e; ++k) {                             // :256-257 then :355-356
     const double a = area[k];
     double u = clon[k] / a, v = clat[k] / a;
@@ -826,14 +834,53 @@ order2_finalize_kernel(CellSet src, long long s0, long long ns, const uint32_t* 
   }
 }
 
+// Source cells with long segments (pole caps, coarse-on-fine): one warp per cell.  The sums must still be taken in list
+// order to be bit-identical with the reference's loop, so the additions stay sequential; what the warp buys is coalesced
+// loads (32 values at a time, handed round by shuffles) instead of one thread's dependent load chain, and a parallel
+// write-out.
+__global__ void __launch_bounds__(128)
+order2_finalize_long_kernel(CellSet src, long long s0, const uint32_t* __restrict__ out_off,
+                            const double* __restrict__ area, const double* __restrict__ clon, const double* __restrict__ clat,
+                            double* __restrict__ di, double* __restrict__ dj, const int* __restrict__ long_list,
+                            const unsigned* __restrict__ nlong)
+{
+  const int lane = threadIdx.x & 31;
+  const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < *nlong; w += nwarps) {
+    const long long t = long_list[w];
+    const uint32_t b = out_off[t], e = out_off[t + 1];
+    double sa = 0.0, sx = 0.0, sy = 0.0;
+    for (uint32_t base = b; base < e; base += 32) {
+      const uint32_t k = base + lane;
+      const double va = (k < e) ? area[k] : 0.0, vx = (k < e) ? clon[k] : 0.0, vy = (k < e) ? clat[k] : 0.0;
+      const int m = (e - base < 32u) ? (int)(e - base) : 32;
+      for (int j = 0; j < m; ++j) {
+        sa += __shfl_sync(0xffffffffu, va, j); sx += __shfl_sync(0xffffffffu, vx, j); sy += __shfl_sync(0xffffffffu, vy, j);
+      }
+    }
+    double cx, cy;
+    cell_centroid(src, s0 + t, sa, sx, sy, &cx, &cy);
+    for (uint32_t k = b + lane; k < e; k += 32) {
+      const double a = area[k];
+      double u = clon[k] / a, v = clat[k] / a;
+      u -= cx; v -= cy;
+      di[k] = u; dj[k] = v;
+    }
+    __syncwarp();
+  }
+}
+
 void launch_order2_finalize(const CellSet& src, long long s0, long long ns, const uint32_t* out_off,
                             const double* area, const double* clon, const double* clat,
-                            double* di, double* dj, cudaStream_t st)
+                            double* di, double* dj, int* long_list, unsigned* nlong, cudaStream_t st)
 {
   if (ns <= 0) return;
   const int threads = 128;
-  ++g_launches;
-  order2_finalize_kernel<<<(unsigned)((ns + threads - 1) / threads), threads, 0, st>>>(src, s0, ns, out_off, area, clon, clat, di, dj);
+  cudaMemsetAsync(nlong, 0, sizeof(unsigned), st);
+  g_launches += 2;
+  order2_finalize_kernel<<<(unsigned)((ns + threads - 1) / threads), threads, 0, st>>>(src, s0, ns, out_off, area, clon, clat, di, dj,
+                                                                                     long_list, nlong);
+  order2_finalize_long_kernel<<<148 * 2, 128, 0, st>>>(src, s0, out_off, area, clon, clat, di, dj, long_list, nlong);
 }
 
 // =============================================================================================
