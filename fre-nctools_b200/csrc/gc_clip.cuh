@@ -29,9 +29,10 @@ constexpr double kRange = 0.05;     // RANGE_CHECK_CRITERIA, mosaic_util.h:26
 constexpr double kEps8 = 1.e-8, kEps10 = 1.e-10, kEps15 = 1.e-15, kEps30 = 1.e-30;
 constexpr double kPiD = 3.14159265358979323846;
 constexpr double kR = 6371000.0;
-constexpr int kRing = 16;           // vertices + inserted intersections of one cell
-constexpr int kInter = 16;
-constexpr int kPoly = 24;
+constexpr int kRing = 12;           // vertices (<= 4) + inserted intersections (<= 8 between two convex quadrilaterals)
+constexpr int kInter = 12;
+constexpr int kPoly = 16;
+constexpr int kMaxIn = 4;           // corners of an input cell
 constexpr int kErrNotConvex = -1, kErrWalk = -2, kErrPool = -3;
 
 // ---- double-double helpers (explicit fma: the file is compiled with -fmad=false) --------------------------
@@ -224,6 +225,7 @@ XGB_HD void poly_append_unique(Poly& l, double x, double y, double z) {
 // Returns the vertex count of the overlap polygon written to out (capacity kPoly), 0 if none, < 0 where the
 // reference would abort.
 XGB_HD int clip_great_circle(const V3* c1, int n1, const V3* c2, int n2, V3* out) {
+  if (n1 > kMaxIn || n2 > kMaxIn) return kErrPool;
   {                                                              // six range rejections (:1508-1528)
     double lo1[3], hi1[3], lo2[3], hi2[3];
     lo1[0] = hi1[0] = c1[0].x; lo1[1] = hi1[1] = c1[0].y; lo1[2] = hi1[2] = c1[0].z;
@@ -250,7 +252,7 @@ XGB_HD int clip_great_circle(const V3* c1, int n1, const V3* c2, int n2, V3* out
   for (int k = 0; k < g2.len; ++k) g2.n[k].inside = inside_polygon(g2.n[k], g1) ? 1 : 0;
   if (ring_area(g1) <= 0 || ring_area(g2) <= 0) return kErrNotConvex;                       // :1575-1578
 
-  V3 pt1[kRing], pt2[kRing];
+  V3 pt1[kMaxIn], pt2[kMaxIn];
   for (int k = 0; k < npts1; ++k) pt1[k] = V3{g1.n[k].x, g1.n[k].y, g1.n[k].z};
   for (int k = 0; k < npts2; ++k) pt2[k] = V3{g2.n[k].x, g2.n[k].y, g2.n[k].z};
   INode inter[kInter];
@@ -365,6 +367,39 @@ XGB_HD int clip_great_circle(const V3* c1, int n1, const V3* c2, int n2, V3* out
     }
   }
   return n_out;
+}
+
+// Cheap proof that two cells cannot produce an exchange cell: some side of one cell has every corner of the other on its
+// outer side by more than kSepMargin (sine of the angular distance to the side's great circle; the inner side is where
+// the cell's own opposite corner lies, so the test does not depend on the orientation of the grid).  The spherical cap
+// n.x >= margin is convex, so it then holds the whole other cell; the cells are at least ~1e-5 rad apart, far beyond the
+// reference's tolerances (EPSLN8 on edge parameters, EPSLN10 on point identity, 1e-8 on insidePolygon's angle sum, whose
+// deficit for a point 1e-5 outside a side of length L is 8e-5/L), so the reference finds no intersection and no inside
+// vertex and returns 0 for such a pair.  Degenerate sides (pole triangles) have n = 0 and never separate.
+constexpr double kSepMargin = 1.e-5;
+XGB_HD bool separated_by_side(const V3* a, const V3* b) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const V3 n = cross(a[i], a[(i + 1) & 3]);
+    const V3& o2 = a[(i + 2) & 3];
+    const V3& o3 = a[(i + 3) & 3];
+    const double in2 = n.x * o2.x + n.y * o2.y + n.z * o2.z, in3 = n.x * o3.x + n.y * o3.y + n.z * o3.z;
+    const double inner = (fabs(in2) > fabs(in3)) ? in2 : in3;      // the cell's own far corner marks the inner side
+    const double len2 = n.x * n.x + n.y * n.y + n.z * n.z;
+    if (!(len2 > 1e-24)) continue;                                 // coincident corners (pole triangle)
+    const double lim = kSepMargin * sqrt(len2);
+    // a far corner within the margin of the side's circle (sliver cell), or the two far corners on opposite sides
+    // (twisted cell), give no reliable orientation: do not use this side
+    if (!(fabs(inner) > 10.0 * lim) || in2 * inner < -lim * fabs(inner) || in3 * inner < -lim * fabs(inner)) continue;
+    bool out = true;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double dk = n.x * b[k].x + n.y * b[k].y + n.z * b[k].z;
+      out = out && ((inner > 0.0) ? (dk < -lim) : (dk > lim));
+    }
+    if (out) return true;
+  }
+  return false;
 }
 
 // latlon2xyz (mosaic_util.c:212-222) with the sin/cos entry points the reference binary calls
