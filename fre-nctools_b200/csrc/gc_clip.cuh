@@ -165,6 +165,19 @@ XGB_HD bool plane_line_param(const V3& a, const V3& b, const V3& l1, const V3& l
   const double m0 = l1.x - l2.x, m1 = b.x - a.x, m2 = 0.0 - a.x;
   const double m3 = l1.y - l2.y, m4 = b.y - a.y, m5 = 0.0 - a.y;
   const double m6 = l1.z - l2.z, m7 = b.z - a.z, m8 = 0.0 - a.z;
+  {
+    // Plain-double estimate first.  The caller only asks whether t lies in [0, 1] (after snapping within 1e-8) unless it
+    // does; an estimate that is off by far less than 1e-4 settles the many side pairs that do not meet, and the
+    // double-double solve below is kept for those that (nearly) do and for ill-conditioned systems.
+    const double e0 = m4 * m8 - m5 * m7, e1 = m3 * m8 - m5 * m6, e2 = m3 * m7 - m4 * m6;
+    const double det_d = m0 * e0 - m1 * e1 + m2 * e2;
+    const double scale = fabs(m0 * e0) + fabs(m1 * e1) + fabs(m2 * e2);
+    if (fabs(det_d) > 1e-9 * scale && fabs(det_d) > 1e-12) {
+      const double w0 = l1.x - a.x, w1 = l1.y - a.y, w2 = l1.z - a.z;
+      const double t_d = (e0 * w0 + (m2 * m7 - m1 * m8) * w1 + (m1 * m5 - m2 * m4) * w2) / det_d;
+      if (t_d < -1e-4 || t_d > 1.0 + 1e-4) { *t = t_d; return true; }
+    }
+  }
   const dd c0 = det2(m4, m8, m5, m7);                 // cofactors of the first column
   const dd c1 = det2(m3, m8, m5, m6);
   const dd c2 = det2(m3, m7, m4, m6);
