@@ -90,6 +90,7 @@ def lib():
     L.xgb_plan_grad_c2l.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_double, C.c_int]
     L.xgb_plan_apply.argtypes = [vp, C.c_uint, C.c_int, vp, vp, vp, vp, C.c_int, C.c_double, vp, C.c_int]
     L.xgb_plan_regrid.argtypes = [vp, C.c_uint, C.c_int, vp, C.c_int, C.c_double, vp, C.c_int]
+    L.xgb_plan_apply_options.argtypes = [vp, C.c_int, vp, vp, vp, C.c_double, C.c_int, vp, C.c_int]
     L.xgb_plan_great_circle_area_host.argtypes = [vp, C.c_int, vp]
     L.xgb_gc_clip_host.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp]
     L.create_xgrid_great_circle.restype = C.c_int
@@ -422,6 +423,15 @@ class XgridPlan:
         self._ck(self._L.xgb_plan_apply(self._p, int(opcode), int(nfields), pd, px, py, self._ptr(grad_mask),
                                         int(bool(has_missing)), float(missing), self._ptr(out), dev))
         return out
+
+    def apply_options(self, cell_methods=0, weight=None, src_cell_area=None, field_area=None, area_missing=-1e20,
+                      target_grid=False, dst_cell_area=None):
+        """weight field / cell_methods sum / cell_measures / --target_grid for the following apply()/regrid() calls
+        (host numpy arrays, tiles concatenated); call without arguments to return to the plain mean"""
+        arrs = [None if a is None else np.ascontiguousarray(a, np.float64) for a in (weight, src_cell_area, field_area, dst_cell_area)]
+        ptr = [None if a is None else a.ctypes.data for a in arrs]
+        self._ck(self._L.xgb_plan_apply_options(self._p, int(cell_methods), ptr[0], ptr[1], ptr[2], float(area_missing),
+                                                int(bool(target_grid)), ptr[3], 0))
 
     def regrid(self, opcode, data, nfields=1, has_missing=False, missing=0.0, out=None):
         """gradient (order 2) + apply in one call -> flat [nfields * nx_out * ny_out]"""

@@ -41,6 +41,11 @@ struct xgb_apply_state {
   DevBuf gtiles_dev, metrics, centers;
   // staging for host-pointer calls, and scratch
   DevBuf s_data, s_gx, s_gy, s_gmask, s_out, s_xdata, s_fb, s_keys;
+  // per-source-cell factors (xgb_plan_apply_options)
+  int cell_methods = 0;
+  bool target_grid = false, opt_weight = false, opt_farea = false, opt_carea = false, opt_dcarea = false;
+  double area_missing = -1.e20;
+  DevBuf o_weight, o_carea, o_farea, o_dcarea, o_eff;
 };
 
 static xgb_apply_state* state(xgb_plan* p)
@@ -56,7 +61,7 @@ void xgb_apply_release(xgb_plan* p)
   DevBuf* bufs[] = {&a->tiles_dev, &a->l_t, &a->l_i, &a->l_j, &a->l_io, &a->l_jo, &a->l_area, &a->l_di, &a->l_dj,
                     &a->off, &a->cursor, &a->perm, &a->c_cell, &a->c_hidx, &a->c_area, &a->c_di, &a->c_dj, &a->scan_tmp,
                     &a->gtiles_dev, &a->metrics, &a->centers, &a->s_data, &a->s_gx, &a->s_gy, &a->s_gmask, &a->s_out,
-                    &a->s_xdata, &a->s_fb, &a->s_keys};
+                    &a->s_xdata, &a->s_fb, &a->s_keys, &a->o_weight, &a->o_carea, &a->o_farea, &a->o_dcarea, &a->o_eff};
   for (DevBuf* b : bufs) b->release();
   delete a;
   p->apply = nullptr;
@@ -74,6 +79,7 @@ static int kernel_errors(xgb_plan* p)
   if (e & kErrApplyIndex) msg = "conserve_interp: exchange-grid entry outside the source mosaic";
   else if (e & kErrMonotoneMax) msg = " xdata is greater than f_bar_max ";     // conserve_interp.c:693
   else if (e & kErrMonotoneMin) msg = " xdata is less than f_bar_min ";        // conserve_interp.c:707
+  else if (e & kErrAreaMissing) msg = "conserve_interp: data is not missing but area is missing";   // :578, :772
   xgb_set_error("%s (kernel error bits 0x%x)", msg, e);
   return 1;
 }
@@ -327,12 +333,88 @@ extern "C" int xgb_plan_grad_c2l(xgb_plan* p, int nfields, const double* data, d
   return 0;
 }
 
+extern "C" int xgb_plan_apply_options(xgb_plan* p, int cell_methods, const double* weight, const double* src_cell_area,
+                                      const double* field_area, double area_missing, int target_grid, const double* dst_cell_area,
+                                      int on_device)
+{
+  if (!p || !p->apply || !p->apply->have_csr) { xgb_set_error("xgb_plan_apply_options: call xgb_plan_apply_setup or xgb_plan_set_xgrid first"); return 1; }
+  xgb_apply_state* a = p->apply;
+  if (cell_methods != 0 && cell_methods != 1) { xgb_set_error("xgb_plan_apply_options: cell_methods must be 0 (mean) or 1 (sum)"); return 1; }
+  if ((cell_methods == 1 || field_area) && !src_cell_area && !p->have_src) { xgb_set_error("xgb_plan_apply_options: source cell areas needed"); return 1; }
+  if (target_grid && !dst_cell_area && !p->have_dst) { xgb_set_error("xgb_plan_apply_options: destination cell areas needed"); return 1; }
+  CU_OK(cudaSetDevice(p->device));
+  const cudaMemcpyKind k = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  auto put = [&](DevBuf& b, const double* src, size_t n, bool* flag) -> int {
+    *flag = (src != nullptr);
+    if (!src) return 0;
+    if (b.reserve(n * 8 + 16)) return 1;
+    return cudaMemcpyAsync(b.p, src, n * 8, k, p->st) != cudaSuccess;
+  };
+  if (put(a->o_weight, weight, (size_t)a->ncell, &a->opt_weight) || put(a->o_farea, field_area, (size_t)a->ncell, &a->opt_farea) ||
+      put(a->o_carea, src_cell_area, (size_t)a->ncell, &a->opt_carea) || put(a->o_dcarea, dst_cell_area, (size_t)a->ndst, &a->opt_dcarea)) {
+    xgb_set_error("xgb_plan_apply_options: copy failed");
+    return 1;
+  }
+  // cell areas default to the plan's own get_grid_area values (grid_in[].cell_area, fregrid_util.c:363-408)
+  if (!a->opt_carea && (cell_methods == 1 || field_area)) {
+    if (a->o_carea.reserve((size_t)a->ncell * 8 + 16)) return 1;
+    CU_OK(cudaMemcpyAsync(a->o_carea.p, p->src.area, (size_t)a->ncell * 8, cudaMemcpyDeviceToDevice, p->st));
+    a->opt_carea = true;
+  }
+  if (!a->opt_dcarea && target_grid) {
+    if (a->o_dcarea.reserve((size_t)a->ndst * 8 + 16)) return 1;
+    CU_OK(cudaMemcpyAsync(a->o_dcarea.p, p->dst.area, (size_t)a->ndst * 8, cudaMemcpyDeviceToDevice, p->st));
+    a->opt_dcarea = true;
+  }
+  CU_OK(cudaStreamSynchronize(p->st));
+  a->cell_methods = cell_methods;
+  a->target_grid = target_grid != 0;
+  a->area_missing = area_missing;
+  return 0;
+}
+
+// the CSR the kernels should use for this call: with weight / sum / cell_measures the per-entry area is replaced by the
+// effective area (conserve_interp.c:572-585)
+static int effective_csr(xgb_plan* p, xgb_apply_state* a, ApplyCsr* out)
+{
+  *out = a->csr;
+  if (!a->opt_weight && a->cell_methods == 0 && !a->opt_farea) return 0;
+  const size_t nn = (size_t)(a->nxgrid > 0 ? a->nxgrid : 1);
+  if (a->o_eff.reserve(nn * 8 + 16)) return 1;
+  launch_effective_area(a->csr, a->nxgrid, a->opt_weight ? (const double*)a->o_weight.p : nullptr, (const double*)a->o_carea.p,
+                        (a->cell_methods == 0 && a->opt_farea) ? (const double*)a->o_farea.p : nullptr, a->cell_methods,
+                        (double*)a->o_eff.p, p->st);
+  out->area = (double*)a->o_eff.p;
+  return 0;
+}
+
+static int check_variant_batch(xgb_apply_state* a, int nf, bool has_missing)
+{
+  // the reference refuses these for nz > 1 (conserve_interp.c:544-546); a batch of field-levels shares one field area
+  if (a->opt_farea && a->cell_methods == 0 && nf != 1) { xgb_set_error("conserve_interp: cell_measures should be false when nz > 1"); return 1; }
+  (void)has_missing;
+  return 0;
+}
+
+static void finish_variants(xgb_plan* p, xgb_apply_state* a, int order, int nf, const double* d_data, bool has_missing, double miss, double* d_out)
+{
+  if (a->opt_farea && a->cell_methods == 0 && has_missing)
+    launch_measure_check(a->csr, a->nxgrid, order, d_data, (const double*)a->o_farea.p, miss, a->area_missing, p->err_dev, p->st);
+  if (a->target_grid && a->cell_methods == 0)
+    launch_target_scale(a->csr, a->ndst, nf, a->opt_farea ? (const double*)a->o_farea.p : nullptr, (const double*)a->o_carea.p,
+                        (const double*)a->o_dcarea.p, miss, d_out, p->st);
+}
+
 // device-side body shared by xgb_plan_apply and xgb_plan_regrid; all pointers are device pointers
 static int apply_device(xgb_plan* p, xgb_apply_state* a, unsigned opcode, int nf, const double* d_data, const double* d_gx,
                         const double* d_gy, const int* d_gm, bool has_missing, double missing, double* d_out)
 {
   const int order = (opcode & XGB_CONSERVE_ORDER2) ? 2 : 1;
   const double miss = has_missing ? missing : -1.e20;                       // conserve_interp.c:541-542, MAXVAL :36
+  if (check_variant_batch(a, nf, has_missing)) return 1;
+  ApplyCsr csr;
+  if (effective_csr(p, a, &csr)) return 1;
+  const int sum_mode = a->cell_methods;
   if (order == 2 && (opcode & XGB_MONOTONIC)) {
     // the limiter couples all exchange cells of a source cell: one field-level at a time (conserve_interp.c:617-742)
     const size_t nn = (size_t)(a->nxgrid > 0 ? a->nxgrid : 1);
@@ -343,13 +425,16 @@ static int apply_device(xgb_plan* p, xgb_apply_state* a, unsigned opcode, int nf
       launch_monotone(a->nxgrid, a->t_in, a->i_in, a->j_in, a->di, a->dj, (const ApplyTile*)a->tiles_dev.p, (int)a->tiles.size(), a->ncell,
                       d_data + (size_t)f * a->nhalo, d_gx + (size_t)f * a->ncell, d_gy + (size_t)f * a->ncell, d_gm + (size_t)f * a->ncell,
                       miss, fb, fb + a->ncell, keys, keys + a->ncell, (double*)a->s_xdata.p, p->err_dev, p->st);
-      launch_apply(2, true, true, a->csr, a->ndst, 1, nullptr, 0, nullptr, nullptr, nullptr, a->ncell, (const double*)a->s_xdata.p,
-                   a->nxgrid, miss, d_out + (size_t)f * a->ndst, p->st);
+      launch_apply(2, true, true, csr, a->ndst, 1, nullptr, 0, nullptr, nullptr, nullptr, a->ncell, (const double*)a->s_xdata.p,
+                   a->nxgrid, miss, d_out + (size_t)f * a->ndst, p->st, sum_mode);
     }
+    finish_variants(p, a, order, nf, d_data, has_missing, miss, d_out);
     return kernel_errors(p);
   }
-  launch_apply(order, has_missing, false, a->csr, a->ndst, nf, d_data, order == 2 ? a->nhalo : a->ncell, d_gx, d_gy, d_gm, a->ncell,
-               nullptr, a->nxgrid, miss, d_out, p->st);
+  launch_apply(order, has_missing, false, csr, a->ndst, nf, d_data, order == 2 ? a->nhalo : a->ncell, d_gx, d_gy, d_gm, a->ncell,
+               nullptr, a->nxgrid, miss, d_out, p->st, sum_mode);
+  finish_variants(p, a, order, nf, d_data, has_missing, miss, d_out);
+  if (a->opt_farea && has_missing) return kernel_errors(p);
   return 0;
 }
 
@@ -404,8 +489,13 @@ extern "C" int xgb_plan_regrid(xgb_plan* p, unsigned int opcode, int nfields, co
     if (a->s_gx.reserve(ng * 32 + 32)) return 1;
     launch_grad_c2l_packed((const GradTile*)a->gtiles_dev.p, (int)a->gtiles.size(), a->ncell, nfields, d_data, a->nhalo,
                            (double*)a->s_gx.p, has_missing != 0, missing, p->st);
-    launch_apply_packed(has_missing != 0, a->csr, a->ndst, nfields, (const double*)a->s_gx.p, a->ncell,
-                        has_missing ? missing : -1.e20, d_out, p->st);
+    if (check_variant_batch(a, nfields, has_missing != 0)) return 1;
+    ApplyCsr csr;
+    if (effective_csr(p, a, &csr)) return 1;
+    const double miss = has_missing ? missing : -1.e20;
+    launch_apply_packed(has_missing != 0, csr, a->ndst, nfields, (const double*)a->s_gx.p, a->ncell, miss, d_out, p->st, a->cell_methods);
+    finish_variants(p, a, 2, nfields, d_data, has_missing != 0, miss, d_out);
+    if (a->opt_farea && has_missing && kernel_errors(p)) return 1;
   } else {
     double *d_gx = nullptr, *d_gy = nullptr;
     int* d_gm = nullptr;

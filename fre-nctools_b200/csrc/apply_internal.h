@@ -13,6 +13,7 @@ enum : int {
   kErrApplyIndex  = 1 << 10,   // exchange-grid entry points outside the source mosaic
   kErrMonotoneMax = 1 << 11,   // " xdata is greater than f_bar_max "   (conserve_interp.c:693)
   kErrMonotoneMin = 1 << 12,   // " xdata is less than f_bar_min "      (conserve_interp.c:707)
+  kErrAreaMissing = 1 << 13,   // "data is not missing but area is missing" (conserve_interp.c:578, :772)
 };
 
 // where a source tile's cells live in the concatenated field arrays
@@ -48,13 +49,20 @@ void launch_dst_sort_gather(long long ndst, const uint32_t* off, uint32_t* perm,
                             ApplyCsr csr, int* err, cudaStream_t st);
 void launch_apply(int order, bool has_missing, bool from_xdata, const ApplyCsr& csr, long long ndst, int nf,
                   const double* data, long long data_stride, const double* gx, const double* gy, const int* gmask,
-                  long long ncell_src, const double* xdata, long long nxgrid, double missing, double* out, cudaStream_t st);
+                  long long ncell_src, const double* xdata, long long nxgrid, double missing, double* out, cudaStream_t st,
+                  int sum_mode = 0);
 void launch_grad_c2l(const GradTile* tiles, int ntiles, long long ncell, int nf, const double* data, long long data_stride,
                      double* gx, double* gy, int* gmask, bool has_missing, double missing, cudaStream_t st);
 // fused path: gradient kernel writes (value, grad_x, grad_y, grad_mask) per cell as one double4, apply gathers it
 void launch_grad_c2l_packed(const GradTile* tiles, int ntiles, long long ncell, int nf, const double* data, long long data_stride,
                             double* packed, bool has_missing, double missing, cudaStream_t st);
 void launch_apply_packed(bool has_missing, const ApplyCsr& csr, long long ndst, int nf, const double* packed, long long ncell_src,
+                         double missing, double* out, cudaStream_t st, int sum_mode = 0);
+void launch_effective_area(const ApplyCsr& csr, long long n, const double* weight, const double* carea, const double* farea,
+                           int sum_mode, double* eff, cudaStream_t st);
+void launch_measure_check(const ApplyCsr& csr, long long n, int order, const double* data, const double* farea, double missing,
+                          double area_missing, int* err, cudaStream_t st);
+void launch_target_scale(const ApplyCsr& csr, long long ndst, int nf, const double* farea, const double* carea, const double* dst_carea,
                          double missing, double* out, cudaStream_t st);
 void launch_monotone(long long nxgrid, const int* t_in, const int* i_in, const int* j_in, const double* di, const double* dj,
                      const ApplyTile* tiles, int ntiles, long long ncell, const double* data, const double* gx, const double* gy,

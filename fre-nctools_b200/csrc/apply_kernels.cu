@@ -104,7 +104,7 @@ template <int ORDER, bool MISSING, bool XDATA>
 __global__ void __launch_bounds__(128)
 apply_kernel(ApplyCsr csr, long long ndst, int nf, const double* __restrict__ data, long long data_stride,
              const double* __restrict__ gx, const double* __restrict__ gy, const int* __restrict__ gmask, long long ncell_src,
-             const double* __restrict__ xdata, long long nxgrid, double missing, double* __restrict__ out)
+             const double* __restrict__ xdata, long long nxgrid, double missing, int sum_mode, double* __restrict__ out)
 {
   // field tile varies fastest over the blocks: the blocks resident at any moment cover a narrow band of destination
   // cells for ALL field tiles, so a chunk of the weights is fetched from HBM once and re-read from L2 by the other
@@ -156,9 +156,11 @@ apply_kernel(ApplyCsr csr, long long ndst, int nf, const double* __restrict__ da
     const int f = f0 + k;
     if (f >= nf) break;
     const double a = (MISSING || XDATA) ? asum[k] : asum_all;
+    const bool any = XDATA ? false : (MISSING ? seen[k] : (e > b));         // out_miss (not set by the limiter branch)
     double r;
-    if (a > 0) r = acc[k] / a;                                              // :833-834
-    else if (MISSING && seen[k]) r = 0.0;                                   // :835-836
+    if (sum_mode) r = (a == 0) ? (any ? 0.0 : missing) : acc[k];            // cell_methods "sum", :821-830
+    else if (a > 0) r = acc[k] / a;                                         // :833-834
+    else if (any) r = 0.0;                                                  // :835-836
     else r = missing;                                                       // :837-838
     out[(long long)f * ndst + d] = r;
   }
@@ -166,14 +168,14 @@ apply_kernel(ApplyCsr csr, long long ndst, int nf, const double* __restrict__ da
 
 void launch_apply(int order, bool has_missing, bool from_xdata, const ApplyCsr& csr, long long ndst, int nf,
                   const double* data, long long data_stride, const double* gx, const double* gy, const int* gmask,
-                  long long ncell_src, const double* xdata, long long nxgrid, double missing, double* out, cudaStream_t st)
+                  long long ncell_src, const double* xdata, long long nxgrid, double missing, double* out, cudaStream_t st, int sum_mode)
 {
   if (ndst <= 0 || nf <= 0) return;
   const long long nblk = ((ndst + 127) / 128) * ((nf + kApplyBT - 1) / kApplyBT);
   if (nblk >= (1ll << 31)) return;                                 // callers batch fields; unreachable for sane batches
   dim3 grid((unsigned)nblk);
   ++g_launches;
-#define XGB_APPLY(O, M, X) apply_kernel<O, M, X><<<grid, 128, 0, st>>>(csr, ndst, nf, data, data_stride, gx, gy, gmask, ncell_src, xdata, nxgrid, missing, out)
+#define XGB_APPLY(O, M, X) apply_kernel<O, M, X><<<grid, 128, 0, st>>>(csr, ndst, nf, data, data_stride, gx, gy, gmask, ncell_src, xdata, nxgrid, missing, sum_mode, out)
   if (from_xdata) XGB_APPLY(2, true, true);
   else if (order == 2) { if (has_missing) XGB_APPLY(2, true, false); else XGB_APPLY(2, false, false); }
   else { if (has_missing) XGB_APPLY(1, true, false); else XGB_APPLY(1, false, false); }
@@ -188,7 +190,7 @@ constexpr int kPackBT = kApplyBT;  // field-levels per thread (16 per thread and
 template <bool MISSING>
 __global__ void __launch_bounds__(128)
 apply_packed_kernel(ApplyCsr csr, long long ndst, int nf, const double4* __restrict__ packed, long long ncell_src,
-                    double missing, double* __restrict__ out)
+                    double missing, int sum_mode, double* __restrict__ out)
 {
   const int nft = (nf + kPackBT - 1) / kPackBT;
   const long long d = (long long)(blockIdx.x / nft) * blockDim.x + threadIdx.x;
@@ -222,23 +224,100 @@ apply_packed_kernel(ApplyCsr csr, long long ndst, int nf, const double4* __restr
     const int f = f0 + k;
     if (f >= nf) break;
     const double a = MISSING ? asum[k] : asum_all;
+    const bool any = MISSING ? seen[k] : (e > b);
     double r;
-    if (a > 0) r = acc[k] / a;
-    else if (MISSING && seen[k]) r = 0.0;
+    if (sum_mode) r = (a == 0) ? (any ? 0.0 : missing) : acc[k];
+    else if (a > 0) r = acc[k] / a;
+    else if (any) r = 0.0;
     else r = missing;
     out[(long long)f * ndst + d] = r;
   }
 }
 
 void launch_apply_packed(bool has_missing, const ApplyCsr& csr, long long ndst, int nf, const double* packed, long long ncell_src,
-                         double missing, double* out, cudaStream_t st)
+                         double missing, double* out, cudaStream_t st, int sum_mode)
 {
   if (ndst <= 0 || nf <= 0) return;
   const long long nblk = ((ndst + 127) / 128) * ((nf + kPackBT - 1) / kPackBT);
   if (nblk >= (1ll << 31)) return;
   ++g_launches;
-  if (has_missing) apply_packed_kernel<true><<<(unsigned)nblk, 128, 0, st>>>(csr, ndst, nf, (const double4*)packed, ncell_src, missing, out);
-  else             apply_packed_kernel<false><<<(unsigned)nblk, 128, 0, st>>>(csr, ndst, nf, (const double4*)packed, ncell_src, missing, out);
+  if (has_missing) apply_packed_kernel<true><<<(unsigned)nblk, 128, 0, st>>>(csr, ndst, nf, (const double4*)packed, ncell_src, missing, sum_mode, out);
+  else             apply_packed_kernel<false><<<(unsigned)nblk, 128, 0, st>>>(csr, ndst, nf, (const double4*)packed, ncell_src, missing, sum_mode, out);
+}
+
+// =============================================================================================
+// per-source-cell factors of do_scalar_conserve_interp: weight field, cell_methods "sum", cell_measures
+// (conserve_interp.c:572-585, :731-737, :767-777), folded into a per-entry effective area with the reference's operation
+// order; and the --target_grid rescale (:841-865)
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+effective_area_kernel(ApplyCsr csr, long long n, const double* __restrict__ weight, const double* __restrict__ carea,
+                      const double* __restrict__ farea, int sum_mode, double* __restrict__ eff)
+{
+  const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const int cell = csr.cell[q];
+  double a = csr.area[q];
+  if (weight) a *= weight[cell];
+  if (sum_mode) a /= carea[cell];
+  else if (farea) a *= (farea[cell] / carea[cell]);
+  eff[q] = a;
+}
+
+// "data is not missing but area is missing" (:576-579, :770-773): one field-level
+__global__ void __launch_bounds__(256)
+measure_check_kernel(ApplyCsr csr, long long n, int order, const double* __restrict__ data, const double* __restrict__ farea,
+                     double missing, double area_missing, int* err)
+{
+  const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const int cell = csr.cell[q];
+  const double v = data[order == 2 ? csr.hidx[q] : cell];
+  if (v != missing && farea[cell] == area_missing) atomicOr(err, kErrAreaMissing);
+}
+
+__global__ void __launch_bounds__(128)
+target_scale_kernel(ApplyCsr csr, long long ndst, int nf, const double* __restrict__ farea, const double* __restrict__ carea,
+                    const double* __restrict__ dst_carea, double missing, double* __restrict__ out)
+{
+  const long long d = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (d >= ndst) return;
+  double t = 0.0;
+  for (uint32_t q = csr.off[d], e = csr.off[d + 1]; q < e; ++q) {
+    const int cell = csr.cell[q];
+    if (farea) t += (csr.area[q] * farea[cell] / carea[cell]);     // :855-856
+    else t += csr.area[q];
+  }
+  const double s = t / dst_carea[d];
+  for (int f = 0; f < nf; ++f) {
+    const long long o = (long long)f * ndst + d;
+    const double v = out[o];
+    if (v != missing) out[o] = v * s;                                // :860-863
+  }
+}
+
+void launch_effective_area(const ApplyCsr& csr, long long n, const double* weight, const double* carea, const double* farea,
+                           int sum_mode, double* eff, cudaStream_t st)
+{
+  if (n <= 0) return;
+  ++g_launches;
+  effective_area_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(csr, n, weight, carea, farea, sum_mode, eff);
+}
+
+void launch_measure_check(const ApplyCsr& csr, long long n, int order, const double* data, const double* farea, double missing,
+                          double area_missing, int* err, cudaStream_t st)
+{
+  if (n <= 0) return;
+  ++g_launches;
+  measure_check_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(csr, n, order, data, farea, missing, area_missing, err);
+}
+
+void launch_target_scale(const ApplyCsr& csr, long long ndst, int nf, const double* farea, const double* carea, const double* dst_carea,
+                         double missing, double* out, cudaStream_t st)
+{
+  if (ndst <= 0) return;
+  ++g_launches;
+  target_scale_kernel<<<(unsigned)((ndst + 127) / 128), 128, 0, st>>>(csr, ndst, nf, farea, carea, dst_carea, missing, out);
 }
 
 // =============================================================================================

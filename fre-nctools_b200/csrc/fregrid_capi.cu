@@ -101,8 +101,9 @@ extern "C" void do_scalar_conserve_interp(void* interp_v, int varid, int ntiles_
   if (nz > 1 && has_missing) die("conserve_interp: has_missing should be false when nz > 1");                  // :544
   if (nz > 1 && v.cell_measures) die("conserve_interp: cell_measures should be false when nz > 1");            // :545
   if (nz > 1 && v.cell_methods == XGB_CELL_METHODS_SUM) die("conserve_interp: cell_methods should not be sum when nz > 1");
-  if (v.cell_measures || v.cell_methods == XGB_CELL_METHODS_SUM || grid_in[0].weight_exist || ((opcode & XGB_TARGET) && !v.use_volume))
-    die("libxgrid_b200: cell_measures / cell_methods sum / weight field / target_grid are not implemented on the GPU path yet");
+  const bool use_weight = grid_in[0].weight_exist != 0;                                            // :535
+  const bool use_sum = v.cell_methods == XGB_CELL_METHODS_SUM, use_meas = v.cell_measures != 0 && !use_sum;
+  const bool use_target = (opcode & XGB_TARGET) && !v.use_volume;                                  // :538-539
   xgb_plan* p = plan();
   std::vector<int> nx, ny;
   size_t ncell = 0, nhalo = 0;
@@ -130,6 +131,15 @@ extern "C" void do_scalar_conserve_interp(void* interp_v, int varid, int ntiles_
     }
     off += nt; offc += nc;
   }
+  std::vector<double> wgt, carea, farea;
+  if (use_weight || use_sum || use_meas) {
+    for (int m = 0; m < ntiles_in; ++m) {
+      const size_t nc = (size_t)grid_in[m].nx * grid_in[m].ny;
+      if (use_weight) wgt.insert(wgt.end(), grid_in[m].weight, grid_in[m].weight + nc);
+      if (use_sum || use_meas) carea.insert(carea.end(), grid_in[m].cell_area, grid_in[m].cell_area + nc);
+      if (use_meas) farea.insert(farea.end(), field_in[m].area, field_in[m].area + nc);
+    }
+  }
   for (int m = 0; m < ntiles_out; ++m) {
     const int nx2 = grid_out[m].nxc, ny2 = grid_out[m].nyc;
     if (interp[m].nxgrid == 0) {
@@ -144,6 +154,10 @@ extern "C" void do_scalar_conserve_interp(void* interp_v, int varid, int ntiles_
         die(xgb_last_error());
       g_csr_key = interp[m].i_in; g_csr_n = interp[m].nxgrid;
     }
+    if (xgb_plan_apply_options(p, use_sum ? 1 : 0, use_weight ? wgt.data() : nullptr, (use_sum || use_meas) ? carea.data() : nullptr,
+                               use_meas ? farea.data() : nullptr, v.area_missing, use_target ? 1 : 0,
+                               use_target ? grid_out[m].cell_area : nullptr, 0))
+      die(xgb_last_error());
     unsigned op = (order == 2) ? XGB_CONSERVE_ORDER2 : XGB_CONSERVE_ORDER1;
     if (order == 2 && (opcode & XGB_MONOTONIC)) op |= XGB_MONOTONIC;
     if (xgb_plan_apply(p, op, nz, data.data(), order == 2 ? gx.data() : nullptr, order == 2 ? gy.data() : nullptr,

@@ -193,7 +193,7 @@ int xgb_plan_dst_area_host(xgb_plan *p, double *area);
  * remapped exactly as one reference call would remap it: per destination cell the sums run in the order of the
  * exchange-grid list, so results are bit-identical to the reference.  Supported variants: order 1 / order 2,
  * missing values (conserve_interp.c:563-590, :745-789), conserve_order2_monotonic (:617-742, opcode |
- * XGB_MONOTONIC); cell_methods "mean" only (no cell_measures / weight field / --target_grid).
+ * XGB_MONOTONIC), and through xgb_plan_apply_options cell_methods "sum", cell_measures, a weight field and --target_grid.
  * on_device != 0: every pointer argument is a device pointer on the plan's device, work is only enqueued on
  * the plan's stream.  on_device == 0: host pointers; the call returns when the outputs are in host memory.
  * ---------------------------------------------------------------------------------------- */
@@ -232,6 +232,20 @@ int xgb_plan_grad_c2l(xgb_plan *p, int nfields, const double *data, double *grad
  * Cells no exchange cell touches receive `missing` (-1e20 when has_missing == 0, conserve_interp.c:541). */
 int xgb_plan_apply(xgb_plan *p, unsigned int opcode, int nfields, const double *data, const double *grad_x,
                    const double *grad_y, const int *grad_mask, int has_missing, double missing, double *out, int on_device);
+
+/* Per-source-cell factors of do_scalar_conserve_interp for the following apply / regrid calls (conserve_interp.c:572-585,
+ * :821-865), all optional:
+ *   cell_methods   0 = mean, 1 = sum (CELL_METHODS_SUM, globals.h:64): entries are weighted by area / cell_area and the
+ *                  destination value is the sum, not the mean
+ *   weight         grid_in[].weight (weight_exist): multiplies every entry's area
+ *   field_area     field_in[].area with cell_measures: entries are weighted by area * (field_area / cell_area); one
+ *                  field-level per call, like the reference (nz == 1); area_missing as Var_config.area_missing
+ *   src_cell_area  grid_in[].cell_area, tiles concatenated (NULL: the plan's own get_grid_area values)
+ *   target_grid    opcode TARGET: multiply the result by (sum of exchange areas) / dst_cell_area (NULL: the plan's own)
+ * Arrays are copied.  Call with (p, 0, NULL, NULL, NULL, 0, 0, NULL, 0) to return to the plain mean. */
+int xgb_plan_apply_options(xgb_plan *p, int cell_methods, const double *weight, const double *src_cell_area,
+                           const double *field_area, double area_missing, int target_grid, const double *dst_cell_area,
+                           int on_device);
 
 /* gradient (order 2) + apply in one call; gradients stay in HBM. */
 int xgb_plan_regrid(xgb_plan *p, unsigned int opcode, int nfields, const double *data, int has_missing, double missing,

@@ -372,3 +372,89 @@ void ref_regrid_apply_through(RefRegrid *r, void *apply_fn, int interp_method, i
                          (r->opcode | extra_opcode) & ~(CHECK_CONSERVE|LEGACY_CLIP), nz);
   free(fin); free(fout); free(var);
 }
+
+
+/* do_scalar_conserve_interp with the optional per-cell factors: weight (grid_in[].weight + weight_exist), cell_methods,
+ * cell_measures (field_in[].area, area_missing), TARGET (grid_out cell_area is already set by ref_regrid_setup).
+ * weight / farea: concatenated over tiles, NULL when unused.  nz == 1. */
+void ref_regrid_apply_ex(RefRegrid *r, int interp_method, int has_missing, double missing, int cell_methods,
+                         const double *weight, const double *farea, double area_missing, unsigned int extra_opcode,
+                         const double *data_in, const double *grad_x, const double *grad_y, const int *grad_mask,
+                         double *data_out)
+{
+  Field_config *fin  = (Field_config *)calloc(r->ntiles_in, sizeof(Field_config));
+  Field_config *fout = (Field_config *)calloc(1, sizeof(Field_config));
+  Var_config *var = (Var_config *)calloc(1, sizeof(Var_config));
+  size_t offd = 0, offc = 0;
+  int n, halo = (interp_method == CONSERVE_ORDER2) ? 1 : 0;
+  strcpy(var->name, "f");
+  var->interp_method = interp_method;
+  var->has_missing = has_missing;
+  var->missing = missing;
+  var->cell_methods = cell_methods;
+  var->cell_measures = farea ? 1 : 0;
+  var->area_missing = area_missing;
+  for(n=0; n<r->ntiles_in; n++) {
+    size_t nx = r->gin[n].nx, ny = r->gin[n].ny;
+    fin[n].var = var;
+    fin[n].data = (double *)(data_in + offd);
+    offd += (nx+2*halo)*(ny+2*halo);
+    if(halo) {
+      fin[n].grad_x = (double *)(grad_x + offc);
+      fin[n].grad_y = (double *)(grad_y + offc);
+      fin[n].grad_mask = (int *)(grad_mask + offc);
+    }
+    if(farea) fin[n].area = (double *)(farea + offc);
+    r->gin[n].weight = weight ? (double *)(weight + offc) : NULL;
+    r->gin[n].weight_exist = weight ? 1 : 0;
+    offc += nx*ny;
+  }
+  fout[0].var = var;
+  fout[0].data = data_out;
+  do_scalar_conserve_interp(r->interp, 0, r->ntiles_in, r->gin, 1, r->gout, fin, fout,
+                            (r->opcode | extra_opcode) & ~CHECK_CONSERVE, 1);
+  for(n=0; n<r->ntiles_in; n++) { r->gin[n].weight = NULL; r->gin[n].weight_exist = 0; }
+  free(fin); free(fout); free(var);
+}
+
+
+/* ref_regrid_apply_ex through another implementation of do_scalar_conserve_interp (function pointer) */
+void ref_regrid_apply_ex_through(RefRegrid *r, void *apply_fn, int interp_method, int has_missing, double missing, int cell_methods,
+                                 const double *weight, const double *farea, double area_missing, unsigned int extra_opcode,
+                                 const double *data_in, const double *grad_x, const double *grad_y, const int *grad_mask,
+                                 double *data_out)
+{
+  Field_config *fin  = (Field_config *)calloc(r->ntiles_in, sizeof(Field_config));
+  Field_config *fout = (Field_config *)calloc(1, sizeof(Field_config));
+  Var_config *var = (Var_config *)calloc(1, sizeof(Var_config));
+  size_t offd = 0, offc = 0;
+  int n, halo = (interp_method == CONSERVE_ORDER2) ? 1 : 0;
+  strcpy(var->name, "f");
+  var->interp_method = interp_method;
+  var->has_missing = has_missing;
+  var->missing = missing;
+  var->cell_methods = cell_methods;
+  var->cell_measures = farea ? 1 : 0;
+  var->area_missing = area_missing;
+  for(n=0; n<r->ntiles_in; n++) {
+    size_t nx = r->gin[n].nx, ny = r->gin[n].ny;
+    fin[n].var = var;
+    fin[n].data = (double *)(data_in + offd);
+    offd += (nx+2*halo)*(ny+2*halo);
+    if(halo) {
+      fin[n].grad_x = (double *)(grad_x + offc);
+      fin[n].grad_y = (double *)(grad_y + offc);
+      fin[n].grad_mask = (int *)(grad_mask + offc);
+    }
+    if(farea) fin[n].area = (double *)(farea + offc);
+    r->gin[n].weight = weight ? (double *)(weight + offc) : NULL;
+    r->gin[n].weight_exist = weight ? 1 : 0;
+    offc += nx*ny;
+  }
+  fout[0].var = var;
+  fout[0].data = data_out;
+  ((apply_fn_t)apply_fn)(r->interp, 0, r->ntiles_in, r->gin, 1, r->gout, fin, fout,
+                         (r->opcode | extra_opcode) & ~(CHECK_CONSERVE|LEGACY_CLIP), 1);
+  for(n=0; n<r->ntiles_in; n++) { r->gin[n].weight = NULL; r->gin[n].weight_exist = 0; }
+  free(fin); free(fout); free(var);
+}

@@ -684,6 +684,133 @@ void orc_conserve_apply(int order, long nxgrid, const int *t_in, const int *i_in
   free(out_area); free(out_miss); free(doff); free(goff); free(moff);
 }
 
+/* ------------------------------------------------------------------------------------------
+ * do_scalar_conserve_interp with the per-source-cell factors of conserve_interp.c:572-585 / :595-603 / :731-737 /
+ * :767-777 / :797-802 (weight field, cell_methods "sum", cell_measures) and the --target_grid rescale (:841-865), for one
+ * field-level (nz == 1).  weight / cell_area / farea: concatenated over tiles (nx*ny each), NULL when unused.
+ * ---------------------------------------------------------------------------------------- */
+static double orc_entry_area(double area, size_t g, const double *weight, int cell_methods, const double *cell_area,
+                             const double *farea)
+{
+  if (weight) area *= weight[g];
+  if (cell_methods == 1) area /= cell_area[g];
+  else if (farea) area *= (farea[g]/cell_area[g]);
+  return area;
+}
+
+void orc_conserve_apply_ex(int order, long nxgrid, const int *t_in, const int *i_in, const int *j_in,
+                           const int *i_out, const int *j_out, const double *area,
+                           const double *di, const double *dj,
+                           int ntiles_in, const int *nx_in, const int *ny_in,
+                           const double *data_in, const double *grad_x, const double *grad_y,
+                           const int *grad_mask, int has_missing, double missing_in, int monotonic,
+                           int cell_methods, const double *weight, const double *cell_area, const double *farea,
+                           int target_grid, const double *dst_cell_area,
+                           int nx_out, int ny_out, double *data_out)
+{
+  const int halo = (order == 2) ? 1 : 0;
+  const size_t nout = (size_t)nx_out*ny_out;
+  double missing = has_missing ? missing_in : -1.e20;
+  double *out_area = (double *)calloc(nout, sizeof(double));
+  int *out_miss = (int *)calloc(nout, sizeof(int));
+  size_t *doff = (size_t *)malloc((size_t)ntiles_in*sizeof(size_t));
+  size_t *moff = (size_t *)malloc((size_t)ntiles_in*sizeof(size_t));
+  double *xdata = NULL, *f_bar_max = NULL, *f_bar_min = NULL, *f_max = NULL, *f_min = NULL;
+  size_t a = 0, c = 0, q;
+  long n;
+  int m;
+  for (m = 0; m < ntiles_in; m++) {
+    doff[m] = a; moff[m] = c;
+    a += (size_t)(nx_in[m]+2*halo)*(ny_in[m]+2*halo);
+    c += (size_t)nx_in[m]*ny_in[m];
+  }
+  for (q = 0; q < nout; q++) data_out[q] = 0.0;
+  if (order == 2 && monotonic) {
+    f_bar_max = (double *)malloc(c*sizeof(double)); f_bar_min = (double *)malloc(c*sizeof(double));
+    f_max = (double *)malloc(c*sizeof(double)); f_min = (double *)malloc(c*sizeof(double));
+    xdata = (double *)malloc((size_t)(nxgrid > 0 ? nxgrid : 1)*sizeof(double));
+    for (m = 0; m < ntiles_in; m++) {
+      int nx1 = nx_in[m], ny1 = ny_in[m], i, j, ii, jj;
+      for (j = 0; j < ny1; j++) for (i = 0; i < nx1; i++) {
+        size_t g = moff[m] + (size_t)j*nx1 + i;
+        f_bar_max[g] = -1.e20; f_bar_min[g] = 1.e20; f_max[g] = -1.e20; f_min[g] = 1.e20;
+        for (jj = j-1; jj <= j+1; jj++) for (ii = i-1; ii <= i+1; ii++) {
+          double v = data_in[doff[m] + (size_t)(jj+1)*(nx1+2) + ii + 1];
+          if (v != missing) { if (v > f_bar_max[g]) f_bar_max[g] = v; if (v < f_bar_min[g]) f_bar_min[g] = v; }
+        }
+      }
+    }
+    for (n = 0; n < nxgrid; n++) {
+      int t = t_in[n], nx1 = nx_in[t];
+      size_t g = moff[t] + (size_t)j_in[n]*nx1 + i_in[n];
+      double f = data_in[doff[t] + (size_t)(j_in[n]+1)*(nx1+2) + i_in[n] + 1];
+      if (f != missing) {
+        xdata[n] = grad_mask[g] ? f : f + grad_x[g]*di[n] + grad_y[g]*dj[n];
+        if (xdata[n] > f_max[g]) f_max[g] = xdata[n];
+        if (xdata[n] < f_min[g]) f_min[g] = xdata[n];
+      } else xdata[n] = missing;
+    }
+    for (n = 0; n < nxgrid; n++) {
+      int t = t_in[n], nx1 = nx_in[t];
+      size_t g = moff[t] + (size_t)j_in[n]*nx1 + i_in[n];
+      double f_bar = data_in[doff[t] + (size_t)(j_in[n]+1)*(nx1+2) + i_in[n] + 1];
+      if (xdata[n] == missing) continue;
+      if (f_max[g] > f_bar_max[g]) {
+        xdata[n] = f_bar + ((xdata[n]-f_bar)/(f_max[g]-f_bar)) * (f_bar_max[g]-f_bar);
+        if (xdata[n] > f_bar_max[g] && xdata[n] - f_bar_max[g] < 1.e-10) xdata[n] = f_bar_max[g];
+      } else if (f_min[g] < f_bar_min[g]) {
+        xdata[n] = f_bar + ((xdata[n]-f_bar)/(f_min[g]-f_bar)) * (f_bar_min[g]-f_bar);
+        if (xdata[n] < f_bar_min[g] && f_bar_min[g] - xdata[n] < 1.e-10) xdata[n] = f_bar_min[g];
+      }
+    }
+  }
+  for (n = 0; n < nxgrid; n++) {
+    int t = t_in[n], nx1 = nx_in[t];
+    size_t g = moff[t] + (size_t)j_in[n]*nx1 + i_in[n];
+    size_t n0 = (size_t)j_out[n]*nx_out + i_out[n];
+    size_t nd = (order == 2) ? doff[t] + (size_t)(j_in[n]+1)*(nx1+2) + i_in[n] + 1 : g;
+    double ar = area[n];
+    if (order == 2 && monotonic) {
+      if (xdata[n] == missing) continue;
+      ar = orc_entry_area(ar, g, weight, cell_methods, cell_area, farea);
+      data_out[n0] += xdata[n]*ar;
+      out_area[n0] += ar;
+      continue;
+    }
+    if (weight) ar *= weight[g];                                              /* before the missing test, :572, :766 */
+    if (has_missing && data_in[nd] == missing) continue;
+    if (cell_methods == 1) ar /= cell_area[g];
+    else if (farea) ar *= (farea[g]/cell_area[g]);
+    if (order == 1) data_out[n0] += data_in[nd]*ar;
+    else if (has_missing && grad_mask[g]) data_out[n0] += data_in[nd]*ar;
+    else data_out[n0] += (data_in[nd] + grad_x[g]*di[n] + grad_y[g]*dj[n])*ar;
+    out_area[n0] += ar;
+    out_miss[n0] = 1;
+  }
+  if (cell_methods == 1) {                                                    /* :821-830 */
+    for (q = 0; q < nout; q++) if (out_area[q] == 0) data_out[q] = (out_miss[q] == 0) ? missing : 0.0;
+  } else {
+    for (q = 0; q < nout; q++) {                                              /* :832-839 */
+      if (out_area[q] > 0) data_out[q] /= out_area[q];
+      else if (out_miss[q] == 1) data_out[q] = 0.0;
+      else data_out[q] = missing;
+    }
+    if (target_grid) {                                                        /* :841-865 */
+      for (q = 0; q < nout; q++) out_area[q] = 0.0;
+      for (n = 0; n < nxgrid; n++) {
+        int t = t_in[n], nx1 = nx_in[t];
+        size_t g = moff[t] + (size_t)j_in[n]*nx1 + i_in[n];
+        size_t n0 = (size_t)j_out[n]*nx_out + i_out[n];
+        if (farea) out_area[n0] += (area[n]*farea[g]/cell_area[g]);
+        else out_area[n0] += area[n];
+      }
+      for (q = 0; q < nout; q++) if (data_out[q] != missing) data_out[q] *= (out_area[q]/dst_cell_area[q]);
+    }
+  }
+  free(out_area); free(out_miss); free(doff); free(moff);
+  free(xdata); free(f_bar_max); free(f_bar_min); free(f_max); free(f_min);
+}
+
 /* the libm this oracle (and oracle/_ref) is linked against, exposed element-wise so tests can pin
  * the product's ref_sin/ref_cos/ref_sincos (csrc/ref_trig.cuh) to it bit for bit */
 void sincos(double, double *, double *);

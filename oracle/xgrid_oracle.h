@@ -69,6 +69,17 @@ void orc_conserve_apply(int order, long nxgrid, const int *t_in, const int *i_in
                         const int *grad_mask, int has_missing, double missing, int monotonic,
                         int nx_out, int ny_out, int nz, double *data_out);
 
+/* the same with weight field / cell_methods sum / cell_measures / target-grid rescale, one field-level */
+void orc_conserve_apply_ex(int order, long nxgrid, const int *t_in, const int *i_in, const int *j_in,
+                           const int *i_out, const int *j_out, const double *area,
+                           const double *di, const double *dj,
+                           int ntiles_in, const int *nx_in, const int *ny_in,
+                           const double *data_in, const double *grad_x, const double *grad_y,
+                           const int *grad_mask, int has_missing, double missing, int monotonic,
+                           int cell_methods, const double *weight, const double *cell_area, const double *farea,
+                           int target_grid, const double *dst_cell_area,
+                           int nx_out, int ny_out, double *data_out);
+
 /* order-2 gradient terms */
 void orc_calc_c2l_grid_info(int nx, int ny, const double *xt, const double *yt,
                             const double *xc, const double *yc,

@@ -98,3 +98,40 @@ def test_oracle_apply_equals_compiled_reference(reflib, pkg):
             got = xgtest.oracle_apply(r, order, tiles, data, nlon, nlat, gx, gy, gm, has_missing=True, missing=1e20, monotonic=mono)
             assert np.array_equal(got, want), (order, mono)
         reflib.ref_regrid_free(r["handle"])
+
+
+def test_oracle_apply_variants_equal_compiled_reference(reflib, pkg):
+    """weight field / cell_methods sum / cell_measures / --target_grid x missing x monotone x order: orc_conserve_apply_ex
+    against the reference's do_scalar_conserve_interp, 60 combinations, bit for bit"""
+    import itertools
+    ni, nlon, nlat = 12, 40, 24
+    lonc, latc, lont, latt = xgtest.ref_cubed_sphere(ni, centers=True)
+    lon2, lat2 = pkg.latlon_grid(nlon, nlat)
+    hm = xgtest.cubed_sphere_halo_map(lonc, latc)
+    nc = ni * ni; nh = (ni + 2) ** 2
+    tiles = [(ni, ni)] * 6
+    rng = np.random.default_rng(5)
+    f = rng.uniform(0.5, 1.5, 6 * nc); fm = f.copy(); fm[rng.uniform(size=f.size) < 0.08] = -999.0
+    w = rng.uniform(0.2, 1.0, 6 * nc); fa = rng.uniform(1e9, 2e9, 6 * nc)
+    n = 0
+    for order in (1, 2):
+        r = xgtest.ref_setup(lonc, latc, lon2, lat2, order, keep=True)
+        ca = np.zeros(6 * nc); da = np.zeros(nlon * nlat)
+        reflib.ref_regrid_cell_area(r["handle"], ca.ctypes.data, da.ctypes.data)
+        for hmiss, cm, usew, usefa, tgt, mono in itertools.product((0, 1), repeat=6):
+            if (cm and (usefa or tgt)) or (mono and order == 1):
+                continue
+            src = fm if hmiss else f
+            data = src if order == 1 else xgtest.with_halo(src, hm)
+            gx = rng.normal(size=6 * nc) * 0.1; gy = rng.normal(size=6 * nc) * 0.1
+            gm = np.zeros(6 * nc, np.int32)
+            if order == 2 and hmiss:
+                gm = np.concatenate([xgtest.grad_mask(ni, ni, data[t * nh:(t + 1) * nh], -999.0) for t in range(6)])
+            want = xgtest.ref_apply_ex(r["handle"], order, data, nlon * nlat, gx, gy, gm, bool(hmiss), -999.0, bool(mono), cm,
+                                       w if usew else None, fa if usefa else None, -1e20, bool(tgt))
+            got = xgtest.oracle_apply_ex(r, order, tiles, data, nlon, nlat, gx, gy, gm, bool(hmiss), -999.0, bool(mono), cm,
+                                         w if usew else None, ca, fa if usefa else None, bool(tgt), da)
+            assert np.array_equal(got, want), (order, hmiss, cm, usew, usefa, tgt, mono)
+            n += 1
+        reflib.ref_regrid_free(r["handle"])
+    assert n == 60

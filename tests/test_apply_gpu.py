@@ -257,3 +257,67 @@ def test_reference_signature_setup_and_apply_through_real_structs(pkg):
                 assert np.array_equal(got, want), extra
             p.close()
         R.ref_regrid_free(ref["handle"])
+
+
+def test_apply_variants_sum_measures_weight_target(pkg):
+    """cell_methods sum, cell_measures, weight field, --target_grid and their combinations with missing values and the
+    monotone limiter (conserve_interp.c:572-585, :821-865): GPU == oracle bit for bit; and once more through the
+    reference-signature do_scalar_conserve_interp with the real structs"""
+    import itertools
+    ni, nlon, nlat = 12, 40, 24
+    c1 = Case(pkg, ni, nlon, nlat, 1)
+    c2 = Case(pkg, ni, nlon, nlat, 2)
+    nc, nh = c1.nc, c1.nh
+    rng = np.random.default_rng(5)
+    f = rng.uniform(0.5, 1.5, 6 * nc); fm = f.copy(); fm[rng.uniform(size=f.size) < 0.08] = -999.0
+    w = rng.uniform(0.2, 1.0, 6 * nc); fa = rng.uniform(1e9, 2e9, 6 * nc)
+    ncase = 0
+    for c in (c1, c2):
+        order = c.order
+        ca = c.plan.src_area(); da = c.plan.dst_area()
+        for hmiss, cm, usew, usefa, tgt, mono in itertools.product((0, 1), repeat=6):
+            if (cm and (usefa or tgt)) or (mono and order == 1):
+                continue
+            src = fm if hmiss else f
+            data = src if order == 1 else xgtest.with_halo(src, c.hm)
+            gx = rng.normal(size=6 * nc) * 0.1; gy = rng.normal(size=6 * nc) * 0.1
+            gm = np.zeros(6 * nc, np.int32)
+            if order == 2 and hmiss:
+                gm = np.concatenate([xgtest.grad_mask(ni, ni, data[t * nh:(t + 1) * nh], -999.0) for t in range(6)])
+            want = xgtest.oracle_apply_ex(c.x, order, c.tiles, data, nlon, nlat, gx, gy, gm, bool(hmiss), -999.0, bool(mono), cm,
+                                          w if usew else None, ca, fa if usefa else None, bool(tgt), da)
+            c.plan.apply_options(cm, w if usew else None, None, fa if usefa else None, -1e20, bool(tgt), None)
+            op = order | (xgtest.MONOTONIC if mono else 0)
+            got = c.plan.apply(op, data, 1, gx if order == 2 else None, gy if order == 2 else None, gm if order == 2 else None,
+                               has_missing=bool(hmiss), missing=-999.0)
+            assert np.array_equal(got, want), (order, hmiss, cm, usew, usefa, tgt, mono)
+            ncase += 1
+        c.plan.apply_options()
+        # back to the plain mean
+        data = f if order == 1 else xgtest.with_halo(f, c.hm)
+        plain = c.plan.apply(order, data, 1, np.zeros(6 * nc) if order == 2 else None, np.zeros(6 * nc) if order == 2 else None)
+        assert np.array_equal(plain, xgtest.oracle_apply(c.x, order, c.tiles, data, nlon, nlat, np.zeros(6 * nc), np.zeros(6 * nc)))
+    assert ncase == 60
+    # data present where the field area is missing is the reference's fatal error (:578): reported, not ignored
+    bad = fa.copy(); bad[7] = -1e20
+    c1.plan.apply_options(0, None, None, bad, -1e20, False, None)
+    with pytest.raises(pkg.XgridError, match="area is missing"):
+        c1.plan.apply(1, fm if fm[7] != -999.0 else f, 1, has_missing=True, missing=-999.0)
+    c1.plan.apply_options()
+    # reference signature with the real structs: sum + weight, and cell_measures + target
+    R = xgtest.ref_lib()
+    if R is not None:
+        import ctypes as C
+        L = pkg.lib()
+        apply_fn = C.cast(L.do_scalar_conserve_interp, C.c_void_p)
+        R.ref_regrid_apply_ex_through.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_double,
+                                                  C.c_uint, xgtest.dp, C.c_void_p, C.c_void_p, C.c_void_p, xgtest.dp]
+        ref = xgtest.ref_setup(c1.lonc, c1.latc, c1.lon2, c1.lat2, 1, keep=True)
+        for cm, usefa, tgt in ((1, 0, 0), (0, 1, 1)):
+            want = xgtest.ref_apply_ex(ref["handle"], 1, fm, nlon * nlat, has_missing=True, missing=-999.0, cell_methods=cm, weight=w,
+                                       farea=fa if usefa else None, target=bool(tgt))
+            got = np.zeros(nlon * nlat)
+            R.ref_regrid_apply_ex_through(ref["handle"], apply_fn, 1, 1, -999.0, cm, w.ctypes.data, fa.ctypes.data if usefa else None, -1e20,
+                                          xgtest.TARGET if tgt else 0, np.ascontiguousarray(fm), None, None, None, got)
+            assert np.array_equal(got, want), (cm, usefa, tgt)
+        R.ref_regrid_free(ref["handle"])

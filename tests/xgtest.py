@@ -55,6 +55,8 @@ def oracle_lib():
         L.orc_conserve_apply.argtypes = [C.c_int, C.c_long] + [ip] * 5 + [dp, vp, vp, C.c_int, ip, ip, dp, vp, vp, vp,
                                          C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, dp]
         L.orc_libm_trig.argtypes = [C.c_long] + [dp] * 5
+        L.orc_conserve_apply_ex.argtypes = [C.c_int, C.c_long] + [ip] * 5 + [dp, vp, vp, C.c_int, ip, ip, dp, vp, vp, vp, C.c_int, C.c_double, C.c_int,
+                                            C.c_int, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, dp]
         L.orc_clip_2dx2d_great_circle.argtypes = [dp, dp, dp, C.c_int, dp, dp, dp, C.c_int, dp, dp, dp]
         L.orc_great_circle_area.restype = C.c_double
         L.orc_great_circle_area.argtypes = [C.c_int, dp, dp, dp]
@@ -125,6 +127,7 @@ def ref_lib():
         L.ref_regrid_cell_area.argtypes = [vp, vp, vp]
         L.ref_regrid_apply.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_uint, dp, vp, vp, vp, dp]
         L.ref_regrid_free.argtypes = [vp]
+        L.ref_regrid_apply_ex.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, vp, vp, C.c_double, C.c_uint, dp, vp, vp, vp, dp]
         L.ref_compute_extent.argtypes = [C.c_int, C.c_int, ip, ip]
         L.ref_abi_layout.argtypes = [C.POINTER(C.c_size_t), C.c_int]
         L.ref_regrid_setup_through.restype = vp
@@ -462,3 +465,44 @@ def tripolar_grid(nx_s, ny_s, lat_join=65.0):
     lonc = np.zeros((ny_s // 2 + 1, nx_s // 2 + 1)); latc = np.zeros_like(lonc)
     ref_lib().ref_tripolar_grid(nx_s, ny_s, -280.0, 80.0, -82.0, 90.0, lat_join, lonc.reshape(-1), latc.reshape(-1))
     return lonc, latc
+
+
+TARGET = 16          # globals.h:50
+
+
+def oracle_apply_ex(x, order, tiles, data, nx_out, ny_out, grad_x=None, grad_y=None, gmask=None, has_missing=False, missing=0.0,
+                    monotonic=False, cell_methods=0, weight=None, cell_area=None, farea=None, target=False, dst_cell_area=None):
+    """orc_conserve_apply_ex for one field-level"""
+    L = oracle_lib()
+    nx = np.array([t[0] for t in tiles], np.int32); ny = np.array([t[1] for t in tiles], np.int32)
+    out = np.zeros(nx_out * ny_out)
+    keep = []
+
+    def ptr(a, dt=np.float64):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dt); keep.append(a)
+        return a.ctypes.data
+    L.orc_conserve_apply_ex(order, x["area"].size, x["t_in"], x["i_in"], x["j_in"], x["i_out"], x["j_out"], x["area"],
+                            ptr(x.get("di")) if order == 2 else None, ptr(x.get("dj")) if order == 2 else None, len(tiles), nx, ny,
+                            np.ascontiguousarray(data, np.float64), ptr(grad_x), ptr(grad_y), ptr(gmask, np.int32), int(has_missing),
+                            float(missing), int(monotonic), int(cell_methods), ptr(weight), ptr(cell_area), ptr(farea), int(target),
+                            ptr(dst_cell_area), nx_out, ny_out, out)
+    return out
+
+
+def ref_apply_ex(handle, order, data, nout, grad_x=None, grad_y=None, gmask=None, has_missing=False, missing=0.0, monotonic=False,
+                 cell_methods=0, weight=None, farea=None, area_missing=-1e20, target=False):
+    L = ref_lib()
+    out = np.zeros(nout)
+    keep = []
+
+    def ptr(a, dt=np.float64):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dt); keep.append(a)
+        return a.ctypes.data
+    extra = (MONOTONIC if monotonic else 0) | (TARGET if target else 0)
+    L.ref_regrid_apply_ex(handle, order, int(has_missing), float(missing), int(cell_methods), ptr(weight), ptr(farea), float(area_missing),
+                          extra, np.ascontiguousarray(data, np.float64), ptr(grad_x), ptr(grad_y), ptr(gmask, np.int32), out)
+    return out
