@@ -69,6 +69,8 @@ def lib():
     L.xgb_plan_set_src.argtypes = [vp, C.c_int, _ip, _ip, vp, vp, vp, C.c_int]
     L.xgb_plan_set_src_window.argtypes = [vp, C.c_longlong, C.c_longlong]
     L.xgb_plan_partition.argtypes = [vp, C.c_int, C.POINTER(C.c_longlong)]
+    L.xgb_plan_set_src_windows.argtypes = [vp, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    L.xgb_plan_window_counts.argtypes = [vp, C.POINTER(C.c_longlong)]
     L.xgb_plan_generate.restype = C.c_longlong
     L.xgb_plan_generate.argtypes = [vp, C.c_uint]
     L.xgb_plan_generate_to_host.restype = C.c_longlong
@@ -243,6 +245,21 @@ class XgridPlan:
 
     def set_src_window(self, begin, end):
         self._ck(self._L.xgb_plan_set_src_window(self._p, int(begin), int(end)))
+        self._nwin = 1
+
+    def set_src_windows(self, windows):
+        """several source-cell windows [(begin, end), ...] (at most 64), generated one after the other in one call"""
+        n = len(windows)
+        b = (C.c_longlong * n)(*[int(w[0]) for w in windows]); e = (C.c_longlong * n)(*[int(w[1]) for w in windows])
+        self._ck(self._L.xgb_plan_set_src_windows(self._p, n, b, e))
+        self._nwin = n
+
+    def window_counts(self):
+        """exchange cells each window of the last generate produced"""
+        n = getattr(self, "_nwin", 1)
+        c = (C.c_longlong * n)()
+        self._ck(self._L.xgb_plan_window_counts(self._p, c))
+        return [int(v) for v in c]
 
     def partition(self, nparts):
         b = (C.c_longlong * (nparts + 1))()

@@ -14,6 +14,9 @@
 
 using namespace xgb;
 
+static SrcMap single_window(long long begin, long long end);
+static SrcMap sub_map(const SrcMap& m, long long tb, long long te);
+
 // ---------------------------------------------------------------------------------------------
 // errors
 // ---------------------------------------------------------------------------------------------
@@ -88,7 +91,8 @@ extern "C" xgb_plan* xgb_plan_create(int device)
       cudaMalloc(&p->err_dev, sizeof(int)) != cudaSuccess ||
       cudaMalloc(&p->total_dev, 2 * sizeof(unsigned long long)) != cudaSuccess ||
       cudaMallocHost(&p->total_host, 2 * sizeof(unsigned long long)) != cudaSuccess ||
-      cudaMallocHost(&p->err_host, sizeof(int)) != cudaSuccess) {
+      cudaMallocHost(&p->err_host, sizeof(int)) != cudaSuccess ||
+      cudaMallocHost(&p->win_host, (kMaxWindows + 1) * sizeof(unsigned)) != cudaSuccess) {
     xgb_set_error("plan resource allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
     delete p;
     return nullptr;
@@ -116,6 +120,7 @@ extern "C" void xgb_plan_destroy(xgb_plan* p)
   if (p->total_dev) cudaFree(p->total_dev);
   if (p->total_host) cudaFreeHost(p->total_host);
   if (p->err_host) cudaFreeHost(p->err_host);
+  if (p->win_host) cudaFreeHost(p->win_host);
   if (p->copy_ev) cudaEventDestroy(p->copy_ev);
   if (p->copy_st) cudaStreamDestroy(p->copy_st);
   if (p->st) cudaStreamDestroy(p->st);
@@ -240,10 +245,59 @@ extern "C" int xgb_plan_set_src(xgb_plan* p, int ntiles, const int* nx, const in
   for (int n = 0; n < ntiles; ++n)
     launch_cell_precompute(p->tiles[n], (const double*)p->src_lon.p, (const double*)p->src_lat.p, p->src, p->err_dev, p->st);
   p->s0 = 0; p->ns = coff;
+  p->map = single_window(0, coff);
   p->have_src = true;
   p->gc_src_ready = false;
   // the tile table was copied from pageable host memory: make sure it has landed before `tiles` can change
   return xgb_check_kernel_errors(p, false);
+}
+
+static SrcMap single_window(long long begin, long long end)
+{
+  SrcMap m{};
+  m.nwin = 1; m.begin[0] = begin; m.cum[0] = 0; m.cum[1] = end - begin;
+  return m;
+}
+
+// the part [tb, te) of a map's window-relative index space as a map of its own
+static SrcMap sub_map(const SrcMap& m, long long tb, long long te)
+{
+  SrcMap r{};
+  r.nwin = 0; r.cum[0] = 0;
+  for (int w = 0; w < m.nwin; ++w) {
+    const long long lo = tb > m.cum[w] ? tb : m.cum[w], hi = te < m.cum[w + 1] ? te : m.cum[w + 1];
+    if (hi <= lo) continue;
+    r.begin[r.nwin] = m.begin[w] + (lo - m.cum[w]);
+    r.cum[r.nwin + 1] = r.cum[r.nwin] + (hi - lo);
+    ++r.nwin;
+  }
+  if (r.nwin == 0) { r.nwin = 1; r.begin[0] = 0; r.cum[1] = 0; }
+  return r;
+}
+
+extern "C" int xgb_plan_set_src_windows(xgb_plan* p, int nwin, const long long* begin, const long long* end)
+{
+  if (!p || !p->have_src) { xgb_set_error("xgb_plan_set_src_windows: no source grid"); return 1; }
+  if (nwin <= 0 || nwin > kMaxWindows || !begin || !end) { xgb_set_error("xgb_plan_set_src_windows: between 1 and %d windows", kMaxWindows); return 1; }
+  SrcMap m{};
+  m.nwin = nwin; m.cum[0] = 0;
+  for (int w = 0; w < nwin; ++w) {
+    if (begin[w] < 0 || end[w] < begin[w] || end[w] > p->src.ncell) { xgb_set_error("xgb_plan_set_src_windows: bad window %d", w); return 1; }
+    m.begin[w] = begin[w];
+    m.cum[w + 1] = m.cum[w] + (end[w] - begin[w]);
+  }
+  p->map = m;
+  p->s0 = begin[0]; p->ns = m.total();
+  return 0;
+}
+
+// exchange cells each window of the last generate produced (nwin values)
+extern "C" int xgb_plan_window_counts(xgb_plan* p, long long* counts)
+{
+  if (!p || p->nxgrid < 0 || !counts) { xgb_set_error("xgb_plan_window_counts: no result"); return 1; }
+  CU_OK(cudaSetDevice(p->device));
+  for (int w = 0; w < p->win_nx_n; ++w) counts[w] = p->win_nx[w];
+  return 0;
 }
 
 extern "C" int xgb_plan_set_src_window(xgb_plan* p, long long begin, long long end)
@@ -251,6 +305,7 @@ extern "C" int xgb_plan_set_src_window(xgb_plan* p, long long begin, long long e
   if (!p || !p->have_src) { xgb_set_error("xgb_plan_set_src_window: no source grid"); return 1; }
   if (begin < 0 || end < begin || end > p->src.ncell) { xgb_set_error("xgb_plan_set_src_window: bad window"); return 1; }
   p->s0 = begin; p->ns = end - begin;
+  p->map = single_window(begin, end);
   return 0;
 }
 
@@ -278,15 +333,16 @@ static int heavy_work(xgb_plan* p, long long ns, HeavyWork* hw)
   return 0;
 }
 
-static int count_candidates(xgb_plan* p, long long s0, long long ns, unsigned long long* total)
+static int count_candidates(xgb_plan* p, const SrcMap& sm, unsigned long long* total)
 {
+  const long long ns = sm.total();
   if (p->cnt.reserve((size_t)(ns + 1) * sizeof(uint32_t)) || p->pair_off.reserve((size_t)(ns + 1) * sizeof(uint32_t)) ||
       p->scan_tmp.reserve(scan_tmp_bytes(ns)))
     return 1;
   HeavyWork hw;
   if (heavy_work(p, ns, &hw)) return 1;
   for (int attempt = 0;; ++attempt) {
-    launch_candidates_count(p->src, s0, ns, p->has_mask ? (const double*)p->mask.p : nullptr, p->pyr, p->dst,
+    launch_candidates_count(p->src, sm, p->has_mask ? (const double*)p->mask.p : nullptr, p->pyr, p->dst,
                             (uint32_t*)p->cnt.p, hw, p->err_dev, p->st);
     launch_exclusive_scan((const uint32_t*)p->cnt.p, (uint32_t*)p->pair_off.p, ns, p->total_dev, p->scan_tmp.p, p->st);
     launch_publish(p->total_host, p->total_dev, 2, p->st);
@@ -308,7 +364,7 @@ extern "C" int xgb_plan_partition(xgb_plan* p, int nparts, long long* bounds)
   CU_OK(cudaSetDevice(p->device));
   unsigned long long total = 0;
   const long long nc = p->src.ncell;
-  if (count_candidates(p, 0, nc, &total)) return 1;
+  if (count_candidates(p, single_window(0, nc), &total)) return 1;
   if (p->bounds_dev.reserve((size_t)(nparts + 1) * sizeof(long long))) return 1;
   launch_partition((const uint32_t*)p->pair_off.p, nc, total, nparts, (long long*)p->bounds_dev.p, p->st);
   CU_OK(cudaMemcpyAsync(bounds, p->bounds_dev.p, (size_t)(nparts + 1) * sizeof(long long), cudaMemcpyDeviceToHost, p->st));
@@ -320,8 +376,9 @@ extern "C" int xgb_plan_partition(xgb_plan* p, int nparts, long long* bounds)
 // Results are written at entries [base, base + n) of the plan's result arrays.  stream_cap == 0: the arrays are
 // (re)sized to hold base + n entries (only valid for base == 0); otherwise they were sized to stream_cap entries
 // beforehand and must not move (asynchronous copies of earlier windows may be in flight).
-static long long generate_window(xgb_plan* p, int order, long long s0, long long ns, size_t base, size_t stream_cap)
+static long long generate_window(xgb_plan* p, int order, const SrcMap& sm, size_t base, size_t stream_cap)
 {
+  const long long ns = sm.total();
   const double* mask = p->has_mask ? (const double*)p->mask.p : nullptr;
   unsigned long long npairs = 0;
   cudaEventRecord(p->ev[0], p->st);
@@ -338,7 +395,7 @@ static long long generate_window(xgb_plan* p, int order, long long s0, long long
     if (p->pairs.reserve(cap * sizeof(int2) + 16) || p->parea.reserve(cap * sizeof(double) + 16)) return -1;
     if (order == 2 && (p->pclon.reserve(cap * sizeof(double) + 16) || p->pclat.reserve(cap * sizeof(double) + 16))) return -1;
     cudaMemsetAsync(p->cnt.p, 0, (size_t)(ns + 1) * sizeof(uint32_t), p->st);
-    launch_candidates_single(p->src, s0, ns, mask, p->pyr, p->dst, (uint32_t*)p->pair_off.p, (uint32_t*)p->pair_cnt.p,
+    launch_candidates_single(p->src, sm, mask, p->pyr, p->dst, (uint32_t*)p->pair_off.p, (uint32_t*)p->pair_cnt.p,
                              (int2*)p->pairs.p, cap, (uint32_t*)p->cnt.p, hw, p->err_dev, p->st);
     launch_publish(p->total_host, &hw.ctl->total, 4, p->st);          // total (2 words), nheavy, npairs of the heavy path
     launch_publish(p->err_host, p->err_dev, 1, p->st);
@@ -367,7 +424,7 @@ static long long generate_window(xgb_plan* p, int order, long long s0, long long
   cudaEventRecord(p->ev[1], p->st);
   cudaMemsetAsync(p->cnt.p, 0, (size_t)(ns + 1) * sizeof(uint32_t), p->st);
   cudaEventRecord(p->ev[2], p->st);
-  launch_clip(order, p->src, p->dst, mask, (const int2*)p->pairs.p, npairs, s0,
+  launch_clip(order, p->src, p->dst, mask, (const int2*)p->pairs.p, npairs, sm,
               (double*)p->parea.p, (double*)p->pclon.p, (double*)p->pclat.p, (uint32_t*)p->cnt.p, p->err_dev, p->st);
   cudaEventRecord(p->ev[3], p->st);
   launch_exclusive_scan((const uint32_t*)p->cnt.p, (uint32_t*)p->out_off.p, ns, p->total_dev + 1, p->scan_tmp.p, p->st);
@@ -393,15 +450,25 @@ static long long generate_window(xgb_plan* p, int order, long long s0, long long
   cudaEventRecord(p->ev[4], p->st);
   launch_scatter(order, (const int2*)p->pairs.p, npairs, (const double*)p->parea.p, (const double*)p->pclon.p,
                  (const double*)p->pclat.p, (const uint32_t*)p->pair_off.p, (const uint32_t*)p->pair_cnt.p, (const uint32_t*)p->out_off.p,
-                 (const TileDesc*)p->tiles_dev.p, (int)p->tiles.size(), s0, p->nx2,
+                 (const TileDesc*)p->tiles_dev.p, (int)p->tiles.size(), sm, p->nx2,
                  (int*)p->t_in.p + base, (int*)p->i_in.p + base, (int*)p->j_in.p + base, (int*)p->i_out.p + base, (int*)p->j_out.p + base,
                  (double*)p->area.p + base, (double*)p->clon.p + (order == 2 ? base : 0), (double*)p->clat.p + (order == 2 ? base : 0), p->st);
   if (order == 2)
-    launch_order2_finalize(p->src, s0, ns, (const uint32_t*)p->out_off.p, (const double*)p->area.p + base,
+    launch_order2_finalize(p->src, sm, (const uint32_t*)p->out_off.p, (const double*)p->area.p + base,
                            (const double*)p->clon.p + base, (const double*)p->clat.p + base, (double*)p->di.p + base,
                            (double*)p->dj.p + base, hw.list, &hw.ctl->nheavy, p->st);   // heavy_list / counter are free again
   cudaEventRecord(p->ev[5], p->st);
+  if (sm.nwin > 1 && stream_cap == 0) {                       // exchange cells per window, for the callers' global offsets
+    for (int w = 1; w < sm.nwin; ++w) launch_publish(p->win_host + w, (const uint32_t*)p->out_off.p + sm.cum[w], 1, p->st);
+  }
   if (xgb_check_kernel_errors(p, false)) return -1;
+  if (stream_cap == 0) {
+    p->win_nx_n = sm.nwin;
+    for (int w = 0; w < sm.nwin; ++w) {
+      const unsigned long long lo = (w == 0) ? 0ull : p->win_host[w], hi = (w + 1 == sm.nwin) ? nx : p->win_host[w + 1];
+      p->win_nx[w] = (long long)(hi - lo);
+    }
+  }
   for (int k = 0; k < 5; ++k) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, p->ev[k], p->ev[k + 1]);
@@ -421,7 +488,7 @@ extern "C" long long xgb_plan_generate(xgb_plan* p, unsigned int opcode)
   }
   if (cudaSetDevice(p->device) != cudaSuccess) { xgb_set_error("cudaSetDevice failed"); return -1; }
   if (opcode & XGB_GREAT_CIRCLE) return xgb_generate_great_circle(p, order);
-  const long long n = generate_window(p, order, p->s0, p->ns, 0, 0);
+  const long long n = generate_window(p, order, p->map, 0, 0);
   if (n < 0) return -1;
   p->nxgrid = n;
   p->order = order;
@@ -458,12 +525,12 @@ extern "C" long long xgb_plan_generate_to_host(xgb_plan* p, unsigned int opcode,
     return -1;
   if (order == 2 && (p->clon.reserve(nd) || p->clat.reserve(nd) || p->di.reserve(nd) || p->dj.reserve(nd))) return -1;
 
-  const long long w0 = p->s0, wn = p->ns;
+  const long long wn = p->map.total();
   size_t base = 0;
   for (int c = 0; c < nchunks; ++c) {
-    const long long b = w0 + wn * c / nchunks, e = w0 + wn * (c + 1) / nchunks;
+    const long long b = wn * c / nchunks, e = wn * (c + 1) / nchunks;
     if (e <= b) continue;
-    const long long n = generate_window(p, order, b, e - b, base, cap);
+    const long long n = generate_window(p, order, sub_map(p->map, b, e), base, cap);
     if (n < 0) { cudaStreamSynchronize(p->copy_st); return -1; }
     // generate_window returned after synchronising p->st: the piece is complete; ship it
     struct { void* dst; const void* src; size_t esz; } cp[] = {

@@ -74,7 +74,10 @@ long long xgb_generate_great_circle(xgb_plan* p, int order)
     return -1;
   }
   if (gc_prepare(p)) return -1;
+  if (p->map.nwin != 1) { xgb_set_error("great-circle generation takes a single source window"); return -1; }
   const long long s0 = p->s0, ns = p->ns;
+  SrcMap sm{};
+  sm.nwin = 1; sm.begin[0] = s0; sm.cum[0] = 0; sm.cum[1] = ns;
   const double* mask = p->has_mask ? (const double*)p->mask.p : nullptr;
   if (p->cnt.reserve((size_t)(ns + 1) * 4) || p->pair_off.reserve((size_t)(ns + 1) * 4) || p->pair_cnt.reserve((size_t)(ns + 1) * 4) ||
       p->out_off.reserve((size_t)(ns + 1) * 4) ||
@@ -109,12 +112,13 @@ long long xgb_generate_great_circle(xgb_plan* p, int order)
   const unsigned long long nx = p->total_host[1];
   p->nxgrid = (long long)nx;
   p->order = 1;
+  p->win_nx_n = 1; p->win_nx[0] = (long long)nx;
   const size_t ni = (size_t)nx * 4 + 16, nd = (size_t)nx * 8 + 16;
   if (p->t_in.reserve(ni) || p->i_in.reserve(ni) || p->j_in.reserve(ni) || p->i_out.reserve(ni) || p->j_out.reserve(ni) || p->area.reserve(nd))
     return -1;
   cudaEventRecord(p->ev[4], p->st);
   launch_scatter(1, (const int2*)p->pairs.p, npairs, (const double*)p->parea.p, nullptr, nullptr, (const uint32_t*)p->pair_off.p,
-                 (const uint32_t*)p->pair_cnt.p, (const uint32_t*)p->out_off.p, (const TileDesc*)p->tiles_dev.p, (int)p->tiles.size(), s0, p->nx2,
+                 (const uint32_t*)p->pair_cnt.p, (const uint32_t*)p->out_off.p, (const TileDesc*)p->tiles_dev.p, (int)p->tiles.size(), sm, p->nx2,
                  (int*)p->t_in.p, (int*)p->i_in.p, (int*)p->j_in.p, (int*)p->i_out.p, (int*)p->j_out.p, (double*)p->area.p,
                  nullptr, nullptr, p->st);
   cudaEventRecord(p->ev[5], p->st);

@@ -6,6 +6,24 @@
 
 namespace xgb {
 
+// The source cells one generate call works on: up to kMaxWindows contiguous ranges of the concatenated (tile-major,
+// row-major) cell index space, visited in the order given.  Kernels index them by a window-relative number t in
+// [0, total()); a single window is the common case.  Several windows let one GPU take an interleaved share of the
+// mosaic (polar and mid-latitude cells cost differently per pair), and let the host-download path work in pieces.
+constexpr int kMaxWindows = 64;
+struct SrcMap {
+  int nwin;
+  long long begin[kMaxWindows];      // first source cell of window w
+  long long cum[kMaxWindows + 1];    // window-relative index of the first cell of window w
+  __host__ __device__ long long total() const { return cum[nwin]; }
+  __host__ __device__ long long cell(long long t) const {
+    if (nwin == 1) return begin[0] + t;
+    int lo = 0, hi = nwin - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (cum[mid] <= t) lo = mid; else hi = mid - 1; }
+    return begin[lo] + (t - cum[lo]);
+  }
+};
+
 // One structured tile of a mosaic: nx*ny cells, (nx+1)*(ny+1) vertices, row-major.
 struct TileDesc {
   int nx, ny;
@@ -64,21 +82,21 @@ struct HeavyWork {
 void launch_cell_precompute(const TileDesc& tile, const double* lon, const double* lat,
                             CellSet cells, int* err, cudaStream_t st);
 void launch_pyramid_level(const PyrLevel& child, Box* out, int nx, int ny, cudaStream_t st);
-void launch_candidates_count(const CellSet& src, long long s0, long long ns, const double* mask,
+void launch_candidates_count(const CellSet& src, const SrcMap& sm, const double* mask,
                              const Pyramid& pyr, const CellSet& dst, uint32_t* cnt, const HeavyWork& hw, int* err, cudaStream_t st);
-void launch_candidates_single(const CellSet& src, long long s0, long long ns, const double* mask,
+void launch_candidates_single(const CellSet& src, const SrcMap& sm, const double* mask,
                               const Pyramid& pyr, const CellSet& dst, uint32_t* pair_off, uint32_t* pair_cnt, int2* pairs,
                               unsigned long long pair_cap, uint32_t* cursor, const HeavyWork& hw, int* err, cudaStream_t st);
 void launch_clip(int order, const CellSet& src, const CellSet& dst, const double* mask,
-                 const int2* pairs, unsigned long long npairs, long long s0,
+                 const int2* pairs, unsigned long long npairs, const SrcMap& sm,
                  double* parea, double* pclon, double* pclat, uint32_t* cnt, int* err, cudaStream_t st);
 void launch_scatter(int order, const int2* pairs, unsigned long long npairs,
                     const double* parea, const double* pclon, const double* pclat,
                     const uint32_t* pair_off, const uint32_t* pair_cnt, const uint32_t* out_off,
-                    const TileDesc* tiles, int ntiles, long long s0, int nx2,
+                    const TileDesc* tiles, int ntiles, const SrcMap& sm, int nx2,
                     int* t_in, int* i_in, int* j_in, int* i_out, int* j_out,
                     double* area, double* clon, double* clat, cudaStream_t st);
-void launch_order2_finalize(const CellSet& src, long long s0, long long ns, const uint32_t* out_off,
+void launch_order2_finalize(const CellSet& src, const SrcMap& sm, const uint32_t* out_off,
                             const double* area, const double* clon, const double* clat,
                             double* di, double* dj, int* long_list /* ns ints */, unsigned* nlong, cudaStream_t st);
 // nwords 32-bit words from device memory to pinned host memory, by a kernel (not the copy engine)

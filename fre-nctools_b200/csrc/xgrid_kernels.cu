@@ -177,15 +177,15 @@ __device__ __forceinline__ unsigned warp_append(unsigned* counter, bool pred)
 // thread to enumerate thousands of nodes.  FILL pass: writes the pairs of the non-heavy cells.
 template <bool FILL>
 __global__ void __launch_bounds__(128)
-candidate_kernel(CellSet src, long long s0, long long ns, const double* __restrict__ mask,
+candidate_kernel(CellSet src, SrcMap sm, const double* __restrict__ mask,
                  Pyramid pyr, CellSet dst, const uint32_t* __restrict__ pair_off,
                  uint32_t* __restrict__ cnt, int2* __restrict__ pairs,
                  unsigned char* __restrict__ heavy_flag, int* __restrict__ heavy_list, HeavyCtl* ctl, int* err)
 {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (t >= ns) return;
+  if (t >= sm.total()) return;
   if (FILL && heavy_flag[t]) return;
-  const long long s = s0 + t;
+  const long long s = sm.cell(t);
   uint32_t n = 0;
   const uint32_t base = FILL ? pair_off[t] : 0u;
   bool heavy = false;
@@ -251,14 +251,14 @@ candidate_kernel(CellSet src, long long s0, long long ns, const double* __restri
 constexpr int kSingleMax = 96;   // thread-local buffer; beyond it the cell goes to the heavy path
 
 __global__ void __launch_bounds__(128)
-candidate_single_kernel(CellSet src, long long s0, long long ns, const double* __restrict__ mask,
+candidate_single_kernel(CellSet src, SrcMap sm, const double* __restrict__ mask,
                         Pyramid pyr, CellSet dst, uint32_t* __restrict__ pair_off, uint32_t* __restrict__ pair_cnt,
                         int2* __restrict__ pairs, unsigned long long cap,
                         unsigned char* __restrict__ heavy_flag, int* __restrict__ heavy_list, HeavyCtl* ctl, int* err)
 {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const bool valid = t < ns;
-  const long long s = s0 + (valid ? t : 0);
+  const bool valid = t < sm.total();
+  const long long s = sm.cell(valid ? t : 0);
   int buf[kSingleMax];
   uint32_t n = 0;
   bool heavy = false;
@@ -351,7 +351,7 @@ heavy_reserve_kernel(HeavyCtl* ctl, const int* __restrict__ heavy_list, uint32_t
 constexpr int kHeavyBlocks = 148 * 2, kHeavyThreads = 128;
 
 __global__ void __launch_bounds__(kHeavyThreads)
-heavy_seed_kernel(CellSet src, long long s0, Pyramid pyr, const int* __restrict__ heavy_list, HeavyCtl* ctl,
+heavy_seed_kernel(CellSet src, SrcMap sm, Pyramid pyr, const int* __restrict__ heavy_list, HeavyCtl* ctl,
                   int2* __restrict__ items, unsigned cap, int* err)
 {
   const int top = pyr.nlev - 1;
@@ -361,7 +361,7 @@ heavy_seed_kernel(CellSet src, long long s0, Pyramid pyr, const int* __restrict_
   for (unsigned long long w = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; w < total;
        w += (unsigned long long)gridDim.x * blockDim.x) {
     const int h = (int)(w / ntop), q = (int)(w % ntop);
-    const SrcBox sb = load_src_box(src, s0 + heavy_list[h]);
+    const SrcBox sb = load_src_box(src, sm.cell(heavy_list[h]));
     const bool hit = node_hit(load_box(L.box + q), sb);
     const unsigned slot = warp_append(&ctl->nitems[top], hit);
     if (hit) { if (slot < cap) items[slot] = make_int2(h, q); else atomicOr(err, kErrHeavyOverflow); }
@@ -370,7 +370,7 @@ heavy_seed_kernel(CellSet src, long long s0, Pyramid pyr, const int* __restrict_
 
 // expands the items of level `lev` (lev >= 1) into level lev-1
 __global__ void __launch_bounds__(kHeavyThreads)
-heavy_expand_kernel(CellSet src, long long s0, Pyramid pyr, CellSet dst, int lev, const int* __restrict__ heavy_list,
+heavy_expand_kernel(CellSet src, SrcMap sm, Pyramid pyr, CellSet dst, int lev, const int* __restrict__ heavy_list,
                     HeavyCtl* ctl, const int2* __restrict__ in, int2* __restrict__ out, int2* __restrict__ hpairs,
                     uint32_t* __restrict__ cnt, unsigned cap, int* err)
 {
@@ -393,7 +393,7 @@ heavy_expand_kernel(CellSet src, long long s0, Pyramid pyr, CellSet dst, int lev
       const int cx = 2 * px + (int)(w & 1), cy = 2 * py + (int)((w >> 1) & 1);
       if (cx < L.nx && cy < L.ny) {
         t = heavy_list[h];
-        const SrcBox sb = load_src_box(src, s0 + t);
+        const SrcBox sb = load_src_box(src, sm.cell(t));
         q = (long long)cy * L.nx + cx;
         hit = (lev == 1) ? leaf_hit(dst, q, sb) : node_hit(load_box(L.box + q), sb);
       }
@@ -426,23 +426,24 @@ heavy_fill_kernel(HeavyCtl* ctl, const int2* __restrict__ hpairs, const uint32_t
 }
 
 // count pass only (xgb_plan_partition): cnt[t] = candidate pairs of source cell t, heavy cells included
-void launch_candidates_count(const CellSet& src, long long s0, long long ns, const double* mask,
+void launch_candidates_count(const CellSet& src, const SrcMap& sm, const double* mask,
                              const Pyramid& pyr, const CellSet& dst, uint32_t* cnt, const HeavyWork& hw, int* err, cudaStream_t st)
 {
+  const long long ns = sm.total();
   if (ns <= 0) return;
   const int threads = 128;
   const unsigned blocks = (unsigned)((ns + threads - 1) / threads);
   cudaMemsetAsync(hw.ctl, 0, sizeof(HeavyCtl), st);
   ++g_launches;
-  candidate_kernel<false><<<blocks, threads, 0, st>>>(src, s0, ns, mask, pyr, dst, nullptr, cnt, nullptr,
+  candidate_kernel<false><<<blocks, threads, 0, st>>>(src, sm, mask, pyr, dst, nullptr, cnt, nullptr,
                                                       hw.flag, hw.list, hw.ctl, err);
   if (pyr.nlev > 1) {
     const int top = pyr.nlev - 1;
     ++g_launches;
-    heavy_seed_kernel<<<kHeavyBlocks, kHeavyThreads, 0, st>>>(src, s0, pyr, hw.list, hw.ctl, hw.items[top & 1], hw.cap, err);
+    heavy_seed_kernel<<<kHeavyBlocks, kHeavyThreads, 0, st>>>(src, sm, pyr, hw.list, hw.ctl, hw.items[top & 1], hw.cap, err);
     for (int lev = top; lev >= 1; --lev) {
       ++g_launches;
-      heavy_expand_kernel<<<kHeavyBlocks, kHeavyThreads, 0, st>>>(src, s0, pyr, dst, lev, hw.list, hw.ctl, hw.items[lev & 1],
+      heavy_expand_kernel<<<kHeavyBlocks, kHeavyThreads, 0, st>>>(src, sm, pyr, dst, lev, hw.list, hw.ctl, hw.items[lev & 1],
                                                                   hw.items[(lev - 1) & 1], hw.pairs, cnt, hw.cap, err);
     }
   }
@@ -450,23 +451,24 @@ void launch_candidates_count(const CellSet& src, long long s0, long long ns, con
 
 // single pass: pairs, pair_off, pair_cnt of every source cell of the window; ctl->total = number of pairs.
 // cursor: ns zeroed uint32 (left dirty).  Pairs beyond pair_cap are dropped (the caller compares ctl->total with it).
-void launch_candidates_single(const CellSet& src, long long s0, long long ns, const double* mask,
+void launch_candidates_single(const CellSet& src, const SrcMap& sm, const double* mask,
                               const Pyramid& pyr, const CellSet& dst, uint32_t* pair_off, uint32_t* pair_cnt, int2* pairs,
                               unsigned long long pair_cap, uint32_t* cursor, const HeavyWork& hw, int* err, cudaStream_t st)
 {
+  const long long ns = sm.total();
   if (ns <= 0) return;
   const unsigned blocks = (unsigned)((ns + 127) / 128);
   cudaMemsetAsync(hw.ctl, 0, sizeof(HeavyCtl), st);
   ++g_launches;
-  candidate_single_kernel<<<blocks, 128, 0, st>>>(src, s0, ns, mask, pyr, dst, pair_off, pair_cnt, pairs, pair_cap,
+  candidate_single_kernel<<<blocks, 128, 0, st>>>(src, sm, mask, pyr, dst, pair_off, pair_cnt, pairs, pair_cap,
                                                   hw.flag, hw.list, hw.ctl, err);
   if (pyr.nlev > 1) {
     const int top = pyr.nlev - 1;
     ++g_launches;
-    heavy_seed_kernel<<<kHeavyBlocks, kHeavyThreads, 0, st>>>(src, s0, pyr, hw.list, hw.ctl, hw.items[top & 1], hw.cap, err);
+    heavy_seed_kernel<<<kHeavyBlocks, kHeavyThreads, 0, st>>>(src, sm, pyr, hw.list, hw.ctl, hw.items[top & 1], hw.cap, err);
     for (int lev = top; lev >= 1; --lev) {
       ++g_launches;
-      heavy_expand_kernel<<<kHeavyBlocks, kHeavyThreads, 0, st>>>(src, s0, pyr, dst, lev, hw.list, hw.ctl, hw.items[lev & 1],
+      heavy_expand_kernel<<<kHeavyBlocks, kHeavyThreads, 0, st>>>(src, sm, pyr, dst, lev, hw.list, hw.ctl, hw.items[lev & 1],
                                                                   hw.items[(lev - 1) & 1], hw.pairs, pair_cnt, hw.cap, err);
     }
     g_launches += 2;
@@ -639,7 +641,7 @@ __device__ __forceinline__ bool load_src_poly(const CellSet& src, long long s, i
 template <int ORDER>
 __global__ void __launch_bounds__(kClipThreads, 5)   // 96 registers: 5 blocks/SM measured 7 % faster than 4 (120 regs) or 6 (80, spills)
 clip_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const int2* __restrict__ pairs,
-            unsigned long long npairs, long long s0,
+            unsigned long long npairs, SrcMap smap,
             double* __restrict__ parea, double* __restrict__ pclon, double* __restrict__ pclat,
             uint32_t* __restrict__ cnt, int* err)
 {
@@ -647,7 +649,7 @@ clip_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const int
   const unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
   const bool valid = p < npairs;                                  // no early exit: the warp reconverges explicitly below
   const int2 pr = valid ? pairs[p] : make_int2(0, 0);
-  const long long s = s0 + pr.x, d = pr.y;
+  const long long s = smap.cell(pr.x), d = pr.y;
   const int n1 = valid ? src.nv[s] : 0, n2 = valid ? dst.nv[d] : 0;
   const double s_xavg = valid ? src.xavg[s] : 0.0;
   const double dxavg = valid ? dst.xavg[d] - s_xavg : 0.0;
@@ -713,14 +715,14 @@ clip_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const int
 }
 
 void launch_clip(int order, const CellSet& src, const CellSet& dst, const double* mask,
-                 const int2* pairs, unsigned long long npairs, long long s0,
+                 const int2* pairs, unsigned long long npairs, const SrcMap& sm,
                  double* parea, double* pclon, double* pclat, uint32_t* cnt, int* err, cudaStream_t st)
 {
   if (npairs == 0) return;
   const unsigned blocks = (unsigned)((npairs + kClipThreads - 1) / kClipThreads);
   ++g_launches;
-  if (order == 2) clip_kernel<2><<<blocks, kClipThreads, 0, st>>>(src, dst, mask, pairs, npairs, s0, parea, pclon, pclat, cnt, err);
-  else            clip_kernel<1><<<blocks, kClipThreads, 0, st>>>(src, dst, mask, pairs, npairs, s0, parea, pclon, pclat, cnt, err);
+  if (order == 2) clip_kernel<2><<<blocks, kClipThreads, 0, st>>>(src, dst, mask, pairs, npairs, sm, parea, pclon, pclat, cnt, err);
+  else            clip_kernel<1><<<blocks, kClipThreads, 0, st>>>(src, dst, mask, pairs, npairs, sm, parea, pclon, pclat, cnt, err);
 }
 
 // =============================================================================================
@@ -738,7 +740,7 @@ __global__ void __launch_bounds__(256)
 scatter_kernel(const int2* __restrict__ pairs, unsigned long long npairs,
                const double* __restrict__ parea, const double* __restrict__ pclon, const double* __restrict__ pclat,
                const uint32_t* __restrict__ pair_off, const uint32_t* __restrict__ pair_cnt, const uint32_t* __restrict__ out_off,
-               const TileDesc* __restrict__ tiles, int ntiles, long long s0, int nx2,
+               const TileDesc* __restrict__ tiles, int ntiles, SrcMap sm, int nx2,
                int* __restrict__ t_in, int* __restrict__ i_in, int* __restrict__ j_in,
                int* __restrict__ i_out, int* __restrict__ j_out,
                double* __restrict__ area, double* __restrict__ clon, double* __restrict__ clat)
@@ -755,7 +757,7 @@ scatter_kernel(const int2* __restrict__ pairs, unsigned long long npairs,
   for (uint32_t q = qb; q < qe; ++q)
     if (parea[q] > 0.0 && pairs[q].y < pr.y) ++rank;
   const size_t o = (size_t)out_off[pr.x] + rank;
-  const long long s = s0 + pr.x;
+  const long long s = sm.cell(pr.x);
   const int tl = find_tile(tiles, ntiles, s);
   const long long c = s - tiles[tl].cell_off;
   t_in[o] = tl;
@@ -770,7 +772,7 @@ scatter_kernel(const int2* __restrict__ pairs, unsigned long long npairs,
 void launch_scatter(int order, const int2* pairs, unsigned long long npairs,
                     const double* parea, const double* pclon, const double* pclat,
                     const uint32_t* pair_off, const uint32_t* pair_cnt, const uint32_t* out_off,
-                    const TileDesc* tiles, int ntiles, long long s0, int nx2,
+                    const TileDesc* tiles, int ntiles, const SrcMap& sm, int nx2,
                     int* t_in, int* i_in, int* j_in, int* i_out, int* j_out,
                     double* area, double* clon, double* clat, cudaStream_t st)
 {
@@ -779,10 +781,10 @@ void launch_scatter(int order, const int2* pairs, unsigned long long npairs,
   const unsigned blocks = (unsigned)((npairs + threads - 1) / threads);
   ++g_launches;
   if (order == 2)
-    scatter_kernel<2><<<blocks, threads, 0, st>>>(pairs, npairs, parea, pclon, pclat, pair_off, pair_cnt, out_off, tiles, ntiles, s0, nx2,
+    scatter_kernel<2><<<blocks, threads, 0, st>>>(pairs, npairs, parea, pclon, pclat, pair_off, pair_cnt, out_off, tiles, ntiles, sm, nx2,
                                                   t_in, i_in, j_in, i_out, j_out, area, clon, clat);
   else
-    scatter_kernel<1><<<blocks, threads, 0, st>>>(pairs, npairs, parea, pclon, pclat, pair_off, pair_cnt, out_off, tiles, ntiles, s0, nx2,
+    scatter_kernel<1><<<blocks, threads, 0, st>>>(pairs, npairs, parea, pclon, pclat, pair_off, pair_cnt, out_off, tiles, ntiles, sm, nx2,
                                                   t_in, i_in, j_in, i_out, j_out, area, clon, clat);
 }
 
@@ -813,19 +815,19 @@ __device__ __forceinline__ void cell_centroid(const CellSet& src, long long s, d
 }
 
 __global__ void __launch_bounds__(128)
-order2_finalize_kernel(CellSet src, long long s0, long long ns, const uint32_t* __restrict__ out_off,
+order2_finalize_kernel(CellSet src, SrcMap sm, const uint32_t* __restrict__ out_off,
                        const double* __restrict__ area, const double* __restrict__ clon, const double* __restrict__ clat,
                        double* __restrict__ di, double* __restrict__ dj, int* __restrict__ long_list, unsigned* __restrict__ nlong)
 {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (t >= ns) return;
+  if (t >= sm.total()) return;
   const uint32_t b = out_off[t], e = out_off[t + 1];
   if (b == e) return;
   if (e - b > kLongSegment) { long_list[atomicAdd(nlong, 1u)] = (int)t; return; }
   double sa = 0.0, sx = 0.0, sy = 0.0;
   for (uint32_t k = b; k < e; ++k) { sa += area[k]; sx += clon[k]; sy += clat[k]; }
   double cx, cy;
-  cell_centroid(src, s0 + t, sa, sx, sy, &cx, &cy);
+  cell_centroid(src, sm.cell(t), sa, sx, sy, &cx, &cy);
   for (uint32_t k = b; k < e; ++k) {                             // :256-257 then :355-356
     const double a = area[k];
     double u = clon[k] / a, v = clat[k] / a;
@@ -839,7 +841,7 @@ order2_finalize_kernel(CellSet src, long long s0, long long ns, const uint32_t* 
 // loads (32 values at a time, handed round by shuffles) instead of one thread's dependent load chain, and a parallel
 // write-out.
 __global__ void __launch_bounds__(128)
-order2_finalize_long_kernel(CellSet src, long long s0, const uint32_t* __restrict__ out_off,
+order2_finalize_long_kernel(CellSet src, SrcMap sm, const uint32_t* __restrict__ out_off,
                             const double* __restrict__ area, const double* __restrict__ clon, const double* __restrict__ clat,
                             double* __restrict__ di, double* __restrict__ dj, const int* __restrict__ long_list,
                             const unsigned* __restrict__ nlong)
@@ -859,7 +861,7 @@ order2_finalize_long_kernel(CellSet src, long long s0, const uint32_t* __restric
       }
     }
     double cx, cy;
-    cell_centroid(src, s0 + t, sa, sx, sy, &cx, &cy);
+    cell_centroid(src, sm.cell(t), sa, sx, sy, &cx, &cy);
     for (uint32_t k = b + lane; k < e; k += 32) {
       const double a = area[k];
       double u = clon[k] / a, v = clat[k] / a;
@@ -870,17 +872,18 @@ order2_finalize_long_kernel(CellSet src, long long s0, const uint32_t* __restric
   }
 }
 
-void launch_order2_finalize(const CellSet& src, long long s0, long long ns, const uint32_t* out_off,
+void launch_order2_finalize(const CellSet& src, const SrcMap& sm, const uint32_t* out_off,
                             const double* area, const double* clon, const double* clat,
                             double* di, double* dj, int* long_list, unsigned* nlong, cudaStream_t st)
 {
+  const long long ns = sm.total();
   if (ns <= 0) return;
   const int threads = 128;
   cudaMemsetAsync(nlong, 0, sizeof(unsigned), st);
   g_launches += 2;
-  order2_finalize_kernel<<<(unsigned)((ns + threads - 1) / threads), threads, 0, st>>>(src, s0, ns, out_off, area, clon, clat, di, dj,
+  order2_finalize_kernel<<<(unsigned)((ns + threads - 1) / threads), threads, 0, st>>>(src, sm, out_off, area, clon, clat, di, dj,
                                                                                      long_list, nlong);
-  order2_finalize_long_kernel<<<148 * 2, 128, 0, st>>>(src, s0, out_off, area, clon, clat, di, dj, long_list, nlong);
+  order2_finalize_long_kernel<<<148 * 2, 128, 0, st>>>(src, sm, out_off, area, clon, clat, di, dj, long_list, nlong);
 }
 
 // =============================================================================================

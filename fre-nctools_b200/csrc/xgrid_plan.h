@@ -34,7 +34,8 @@ struct xgb_plan {
   std::vector<xgb::TileDesc> tiles;
   DevBuf tiles_dev, src_lon, src_lat, mask, src_store;
   xgb::CellSet src{};
-  long long s0 = 0, ns = 0;          // active window of source cells
+  long long s0 = 0, ns = 0;          // active window of source cells (first window, total count)
+  xgb::SrcMap map{};                 // all active windows
 
   // great-circle extras (cartesian vertices, spherical-excess areas)
   bool gc_src_ready = false, gc_dst_ready = false;
@@ -56,6 +57,9 @@ struct xgb_plan {
 
   int* err_dev = nullptr;
   int* err_host = nullptr;                    // pinned
+  unsigned* win_host = nullptr;               // pinned: out_off at window boundaries
+  long long win_nx[xgb::kMaxWindows] = {0};   // exchange cells per window of the last generate
+  int win_nx_n = 0;
   unsigned long long* total_dev = nullptr;    // [2]
   unsigned long long* total_host = nullptr;   // pinned [2]
 

@@ -122,6 +122,12 @@ int xgb_plan_set_src(xgb_plan *p, int ntiles, const int *nx, const int *ny,
  * cell index space — the unit of multi-GPU sharding.  Default: all cells. */
 int xgb_plan_set_src_window(xgb_plan *p, long long begin, long long end);
 
+/* Several windows at once (at most 64), visited in the order given: one GPU's interleaved share of the mosaic.  The
+ * result lists the windows' exchange cells one window after the other; xgb_plan_window_counts returns how many each
+ * window produced (for global offsets when the pieces of several GPUs are put back into the serial order). */
+int xgb_plan_set_src_windows(xgb_plan *p, int nwin, const long long *begin, const long long *end);
+int xgb_plan_window_counts(xgb_plan *p, long long *counts);
+
 /* Split the source cells into nparts contiguous windows of (nearly) equal candidate-pair count.
  * bounds receives nparts+1 cell indices (bounds[0] = 0, bounds[nparts] = ncells). */
 int xgb_plan_partition(xgb_plan *p, int nparts, long long *bounds);

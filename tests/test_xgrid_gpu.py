@@ -321,3 +321,42 @@ def test_heavy_work_lists_grow_on_their_own(pkg):
     plan.close()
     ref = xgtest.oracle_setup(lonc, latc, lon2, lat2, 1)
     xgtest.assert_xgrid_equal(got, ref, 1, AREA_RTOL, DIST_ATOL, scale=xgtest.parent_scale(ref, lonc, latc, lon2, lat2))
+
+
+def test_interleaved_windows_reassemble_to_serial_list(pkg):
+    """xgb_plan_set_src_windows: two 'GPUs' take alternating windows of a 12-way partition; putting the windows' pieces back
+    in window order gives the serial list bit for bit (this is how bench.py shards for N > 1)"""
+    lonc, latc = pkg.cubed_sphere_grid(24)
+    lon2, lat2 = pkg.latlon_grid(120, 60)
+    plan = pkg.XgridPlan(0)
+    plan.set_dst(lon2, lat2)
+    plan.set_src(lonc, latc)
+    plan.generate(2)
+    full = plan.result_host()
+    nparts, world = 12, 2
+    b = plan.partition(nparts)
+    pieces = {}
+    for rank in range(world):
+        wins = [(b[w], b[w + 1]) for w in range(rank, nparts, world)]
+        plan.set_src_windows(wins)
+        n = plan.generate(2)
+        r = plan.result_host()
+        counts = plan.window_counts()
+        assert sum(counts) == n and len(counts) == len(wins)
+        off = 0
+        for k, w in enumerate(range(rank, nparts, world)):
+            pieces[w] = {key: v[off:off + counts[k]] for key, v in r.items()}
+            off += counts[k]
+    for key in full:
+        cat = np.concatenate([pieces[w][key] for w in range(nparts)])
+        assert np.array_equal(cat, full[key]), key
+    # the host-download path works on several windows too
+    wins = [(b[w], b[w + 1]) for w in range(0, nparts, 2)]
+    plan.set_src_windows(wins)
+    n = plan.generate(2)
+    want = plan.result_host()
+    bufs = {k: np.zeros(n + 3, v.dtype) for k, v in want.items()}
+    assert plan.generate_to_host(2, bufs, nchunks=5) == n
+    for k in want:
+        assert np.array_equal(bufs[k][:n], want[k]), k
+    plan.close()
