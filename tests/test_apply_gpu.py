@@ -91,8 +91,10 @@ def test_apply_order1(pkg, ni, nlon, nlat):
             assert np.array_equal(out[k], want), (holes, k)
 
 
-@pytest.mark.parametrize("ni,nlon,nlat", [(8, 36, 18), (24, 144, 72)])
+@pytest.mark.parametrize("ni,nlon,nlat", [(8, 36, 18), (24, 144, 72), (24, 18, 9), (16, 250, 130)])
 def test_apply_order2_variants(pkg, ni, nlon, nlat):
+    """(24, 18, 9): destination far coarser than the source, every 32x8 destination patch references more source cells than
+    the tiled kernel stages (direct-gather patches); (16, 250, 130): patch grid with ragged right/top edges"""
     c = Case(pkg, ni, nlon, nlat, 2)
     p = c.plan
     for t, m in enumerate(c.oracle_metrics()):
