@@ -50,7 +50,10 @@ def lib():
     if _LIB is not None:
         return _LIB
     path = os.path.join(_HERE, "libxgrid_b200.so")
-    if _build.needs_build():
+    dev = os.environ.get("XGRID_B200_LIB")        # developer override: a kernel-variant build (scripts/clip_variants.py)
+    if dev:
+        path = dev
+    elif _build.needs_build():
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
         if os.path.exists(nvcc):
             _build.build()
@@ -106,6 +109,16 @@ def lib():
     L.xgb_ref_trig_host.restype = None
     L.xgb_ref_trig_host.argtypes = [C.c_longlong] + [vp] * 5
     L.xgb_ref_trig_device.argtypes = [C.c_longlong] + [vp] * 5
+    L.xgb_ref_trig_site_host.restype = None
+    L.xgb_ref_trig_site_host.argtypes = [C.c_longlong] + [vp] * 5
+    L.xgb_ref_trig_site_device.argtypes = [C.c_longlong] + [vp] * 5
+    L.xgb_set_nc_format.argtypes = [C.c_char_p]
+    L.xgb_remap_write.argtypes = [C.c_char_p, C.c_int, C.c_longlong] + [vp] * 5 + [C.c_int, C.c_int] + [vp] * 3
+    L.xgb_remap_size.restype = C.c_longlong
+    L.xgb_remap_size.argtypes = [C.c_char_p]
+    L.xgb_remap_read.argtypes = [C.c_char_p, C.c_int, C.c_longlong] + [vp] * 8
+    L.xgb_poly_moments_site_host.restype = None
+    L.xgb_poly_moments_site_host.argtypes = [C.c_int, C.c_int, vp, vp, C.c_double, vp]
     L.get_maxxgrid.restype = C.c_int
     for name in ("create_xgrid_2dx2d_order1", "create_xgrid_2dx2d_order2"):
         getattr(L, name).restype = C.c_int

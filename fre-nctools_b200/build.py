@@ -27,16 +27,19 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, defines=()):
+    """out / defines: developer builds of kernel variants next to the product library (scripts/clip_variants.py)."""
+    if out is None and not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", OUT] + [os.path.join(CSRC, s) for s in sources()] + ["-lcudart"]
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", out or OUT] + [os.path.join(CSRC, s) for s in sources()] + ["-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building libxgrid_b200.so")
+    if out is not None:
+        return out
     with open(os.path.join(HERE, "build_ptxas.log"), "w") as f:
         f.write(r.stdout + r.stderr)
     return OUT

@@ -51,12 +51,44 @@ extern "C" void setup_conserve_interp(int ntiles_in, const void* grid_in_v, int 
   const xgb_Grid_config* grid_in = (const xgb_Grid_config*)grid_in_v;
   xgb_Grid_config* grid_out = (xgb_Grid_config*)grid_out_v;
   xgb_Interp_config* interp = (xgb_Interp_config*)interp_v;
-  if (opcode & XGB_READ)
-    die("libxgrid_b200: setup_conserve_interp cannot read remap files (no netCDF in this library); read the lists with "
-        "the reference's read_mosaic_xgrid_order1/2 and hand them to xgb_plan_set_xgrid");
-  if (opcode & XGB_WRITE)
-    die("libxgrid_b200: setup_conserve_interp cannot write remap files (no netCDF in this library); clear WRITE and write "
-        "interp[n] with the reference's writer, the list order is the serial reference order");
+  const bool o2 = (opcode & XGB_CONSERVE_ORDER2) != 0;
+  if (opcode & XGB_READ) {
+    // conserve_interp.c:62-125: every output tile whose remap file exists is read instead of computed
+    for (int n = 0; n < ntiles_out; ++n) {
+      if (!interp[n].file_exist) continue;
+      const long long nall = xgb_remap_size(interp[n].remap_file);
+      if (nall < 0) die(xgb_last_error());
+      const size_t k = (size_t)(nall > 0 ? nall : 1);
+      std::vector<int> t(k), i1(k), j1(k), i2(k), j2(k);
+      std::vector<double> a(k), di, dj;
+      if (o2) { di.resize(k); dj.resize(k); }
+      if (xgb_remap_read(interp[n].remap_file, o2 ? 2 : 1, nall, t.data(), i1.data(), j1.data(), i2.data(), j2.data(), a.data(),
+                         o2 ? di.data() : nullptr, o2 ? dj.data() : nullptr))
+        die(xgb_last_error());
+      // keep the cells of this process's part of the output tile (:93-98), indices relative to it (:107-115)
+      const xgb_Grid_config& g = grid_out[n];
+      std::vector<size_t> ind;
+      for (size_t q = 0; q < (size_t)nall; ++q)
+        if (i2[q] <= g.iec && i2[q] >= g.isc && j2[q] <= g.jec && j2[q] >= g.jsc) ind.push_back(q);
+      const size_t m = ind.size();
+      interp[n].nxgrid = m;
+      const size_t mm = m ? m : 1;
+      interp[n].i_in = (int*)malloc(mm * sizeof(int));   interp[n].j_in = (int*)malloc(mm * sizeof(int));
+      interp[n].i_out = (int*)malloc(mm * sizeof(int));  interp[n].j_out = (int*)malloc(mm * sizeof(int));
+      interp[n].t_in = (int*)malloc(mm * sizeof(int));   interp[n].area = (double*)malloc(mm * sizeof(double));
+      if (o2) { interp[n].di_in = (double*)malloc(mm * sizeof(double)); interp[n].dj_in = (double*)malloc(mm * sizeof(double)); }
+      for (size_t q = 0; q < m; ++q) {
+        const size_t s = ind[q];
+        interp[n].i_in[q] = i1[s]; interp[n].j_in[q] = j1[s]; interp[n].t_in[q] = t[s];
+        interp[n].i_out[q] = i2[s] - g.isc; interp[n].j_out[q] = j2[s] - g.jsc;
+        interp[n].area[q] = a[s];
+        if (o2) { interp[n].di_in[q] = di[s]; interp[n].dj_in[q] = dj[s]; }
+      }
+    }
+    g_csr_key = nullptr;
+    printf("NOTE: Finish reading index and weight for conservative interpolation from file.\n");   // :125
+    return;
+  }
   if (!(opcode & (XGB_CONSERVE_ORDER1 | XGB_CONSERVE_ORDER2)))
     die("conserve_interp: interp_method should be CONSERVE_ORDER1 or CONSERVE_ORDER2");     // conserve_interp.c:230
   xgb_plan* p = plan();
@@ -64,7 +96,6 @@ extern "C" void setup_conserve_interp(int ntiles_in, const void* grid_in_v, int 
   std::vector<double> lon, lat;
   concat_grids(ntiles_in, grid_in, nx, ny, lon, lat);
   const unsigned op = opcode & (XGB_CONSERVE_ORDER1 | XGB_CONSERVE_ORDER2 | XGB_GREAT_CIRCLE);
-  const bool o2 = (opcode & XGB_CONSERVE_ORDER2) != 0;
   for (int n = 0; n < ntiles_out; ++n) {
     if (xgb_plan_set_dst(p, grid_out[n].nxc, grid_out[n].nyc, grid_out[n].lonc, grid_out[n].latc, 0)) die(xgb_last_error());
     if (xgb_plan_set_src(p, ntiles_in, nx.data(), ny.data(), lon.data(), lat.data(), nullptr, 0)) die(xgb_last_error());
@@ -80,6 +111,12 @@ extern "C" void setup_conserve_interp(int ntiles_in, const void* grid_in_v, int 
     if (xgb_plan_result_host(p, interp[n].t_in, interp[n].i_in, interp[n].j_in, interp[n].i_out, interp[n].j_out, interp[n].area,
                              o2 ? interp[n].di_in : nullptr, o2 ? interp[n].dj_in : nullptr))
       die(xgb_last_error());
+    if (opcode & XGB_WRITE) {                                                    // conserve_interp.c:368-443
+      if (xgb_remap_write(interp[n].remap_file, o2 ? 2 : 1, nxg, interp[n].t_in, interp[n].i_in, interp[n].j_in, interp[n].i_out,
+                          interp[n].j_out, grid_out[n].isc, grid_out[n].jsc, interp[n].area, o2 ? interp[n].di_in : nullptr,
+                          o2 ? interp[n].dj_in : nullptr))
+        die(xgb_last_error());
+    }
   }
   g_csr_key = nullptr;
   if (opcode & XGB_GREAT_CIRCLE) return;

@@ -32,7 +32,7 @@
 namespace xgb {
 
 #if defined(__CUDACC__)
-static __device__ const double kSinCosTabDev[440] = {
+static __device__ __align__(16) const double kSinCosTabDev[440] = {
 #include "sincostab.inc"
 };
 #endif
@@ -216,6 +216,90 @@ XGB_HD void ref_sincos(double x, double* sn, double* cs) {
     return;
   }
   *sn = sin(x); *cs = cos(x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// One evaluation site for everything the clip kernel asks of trig (the kernel is instruction-fetch bound: five inlined
+// copies of the three range paths cost more than the arithmetic).  T is the 440-entry table (shared-memory copy in the
+// kernel, host table in the CPU tests).
+//   sin_only == false: (*sn, *cs) = ref_sincos(x)
+//   sin_only == true : *sn = ref_sin(x), *cs unspecified
+// Both table ranges reduce to "sin-type" and "cos-type" evaluations of one reduced argument (a, da):
+//   |x| < 0.855469        a = x, da = 0:                  sin = sin-type, cos = cos-type           (ref_sin == ref_sincos.sin)
+//   0.855469 <= |x| < 2.426265   y = pi/2 - |x|:          sin = +-cos-type, cos = sin-type, with
+//        ref_sincos: a = y + hp1, da = (y - a) + hp1;     ref_sin: a = y, da = hp1  (do_cos(y, hp1))
+// The operation order of every path is that of ref_sin / ref_sincos above; tests pin all three bit for bit against libm.
+// ---------------------------------------------------------------------------------------------
+namespace trig {
+XGB_HD double reduce_t(double ax, Tab* t, const double* T) {
+  const double u = ax + big;
+  const int k4 = (int)((uint32_t)bits(u) << 2);
+#if defined(__CUDA_ARCH__)
+  const double2 r0 = *reinterpret_cast<const double2*>(T + k4);       // rows are 32 bytes: two 16-byte loads
+  const double2 r1 = *reinterpret_cast<const double2*>(T + k4 + 2);
+  t->sn = r0.x; t->ssn = r0.y; t->cs = r1.x; t->ccs = r1.y;
+#else
+  t->sn = T[k4]; t->ssn = T[k4 + 1]; t->cs = T[k4 + 2]; t->ccs = T[k4 + 3];
+#endif
+  return ax - (u - big);
+}
+}  // namespace trig
+
+#if defined(__CUDACC__)
+static __device__ __noinline__ void ref_sincos_call(double x, double* sn, double* cs) { ref_sincos(x, sn, cs); }
+static __device__ __noinline__ double ref_sin_call(double x) { return ref_sin(x); }
+#endif
+
+XGB_HD void ref_trig_site(double x, bool sin_only, double* sn, double* cs, const double* T) {
+  const uint32_t k = (uint32_t)(trig::bits(x) >> 32) & 0x7fffffffu;
+  if (k < 0x3e400000u) { *sn = x; *cs = 1.0; return; }
+  if (k >= 0x400368fdu) {                       // never reached by latitudes
+#if defined(__CUDA_ARCH__)
+    if (sin_only) *sn = ref_sin_call(x); else ref_sincos_call(x, sn, cs);
+#else
+    if (sin_only) *sn = ref_sin(x); else ref_sincos(x, sn, cs);
+#endif
+    return;
+  }
+  const bool swap = (k >= 0x3feb6000u);
+  double a = x, da = 0.0;
+  if (swap) {
+    const double y = trig::hp0 - fabs(x);
+    if (sin_only) { a = y; da = trig::hp1; }
+    else { a = y + trig::hp1; da = (y - a) + trig::hp1; }
+  }
+  const double aa = fabs(a);
+  trig::Tab t;
+  const double xr0 = trig::reduce_t(aa, &t, T);
+  double S = 0.0, Cc = 0.0;
+  if (!(swap && sin_only)) {                    // sin-type of (a, da)
+    if (aa < 0.126) S = trig::taylor_sin(a, da);
+    else S = trig::mag_with_sign_of(trig::sin_core(xr0, (a <= 0) ? -da : da, t), a);
+  }
+  if (swap || !sin_only)                        // cos-type of (a, da)
+    Cc = trig::cos_core(xr0 + ((a < 0) ? -da : da), t);
+  if (swap) { *sn = trig::mag_with_sign_of(Cc, x); *cs = S; }
+  else      { *sn = S; *cs = Cc; }
+}
+
+// sin(x) for the half-differences of latitudes (|x| < 0.126 on any realistic grid): Taylor path inline, the rest by call
+XGB_HD double ref_sin_small(double x) {
+  const uint32_t k = (uint32_t)(trig::bits(x) >> 32) & 0x7fffffffu;
+  if (k < 0x3e500000u) return x;
+  if (fabs(x) < 0.126) return trig::taylor_sin(x, 0.0);
+#if defined(__CUDA_ARCH__)
+  return ref_sin_call(x);
+#else
+  return ref_sin(x);
+#endif
+}
+
+XGB_HD const double* ref_trig_table() {
+#if defined(__CUDA_ARCH__)
+  return kSinCosTabDev;
+#else
+  return kSinCosTabHost;
+#endif
 }
 
 }  // namespace xgb

@@ -31,6 +31,7 @@ void xgb_set_error(const char* fmt, ...)
 }
 
 extern "C" const char* xgb_last_error(void) { return g_err; }
+extern "C" void xgb_set_error_str(const char* s) { xgb_set_error("%s", s); }      // for the plain-C files (remap_file.c)
 
 // The reference's error_handler (mosaic_util.c:57-65): message on stderr, exit(1).
 [[noreturn]] static void fatal(const char* msg)
@@ -780,4 +781,55 @@ extern "C" int xgb_ref_trig_device(long long n, const double* x, double* s, doub
   CU_OK(cudaMemcpy(sc, d + 4 * n, nb, cudaMemcpyDeviceToHost));
   cudaFree(d);
   return 0;
+}
+
+// the single-site variant the clip kernel uses (ref_trig_site / ref_sin_small): s1 = sin-only mode, (ss, sc) = sincos mode,
+// sm = ref_sin_small; host build and device build (the device build reads the table from shared memory like the kernel)
+extern "C" void xgb_ref_trig_site_host(long long n, const double* x, double* s1, double* ss, double* sc, double* sm)
+{
+  const double* T = ref_trig_table();
+  for (long long i = 0; i < n; ++i) {
+    double dummy;
+    ref_trig_site(x[i], true, &s1[i], &dummy, T);
+    ref_trig_site(x[i], false, &ss[i], &sc[i], T);
+    sm[i] = ref_sin_small(x[i]);
+  }
+}
+
+__global__ void ref_trig_site_kernel(long long n, const double* __restrict__ x, double* s1, double* ss, double* sc, double* sm)
+{
+  __shared__ __align__(16) double T[440];
+  for (int k = threadIdx.x; k < 440; k += blockDim.x) T[k] = ref_trig_table()[k];
+  __syncthreads();
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double dummy;
+  ref_trig_site(x[i], true, &s1[i], &dummy, T);
+  ref_trig_site(x[i], false, &ss[i], &sc[i], T);
+  sm[i] = ref_sin_small(x[i]);
+}
+
+extern "C" int xgb_ref_trig_site_device(long long n, const double* x, double* s1, double* ss, double* sc, double* sm)
+{
+  double* d = nullptr;
+  const size_t nb = (size_t)n * sizeof(double);
+  CU_OK(cudaMalloc(&d, 5 * nb));
+  CU_OK(cudaMemcpy(d, x, nb, cudaMemcpyHostToDevice));
+  ref_trig_site_kernel<<<(unsigned)((n + 255) / 256), 256>>>(n, d, d + n, d + 2 * n, d + 3 * n, d + 4 * n);
+  CU_OK(cudaGetLastError());
+  CU_OK(cudaMemcpy(s1, d + n, nb, cudaMemcpyDeviceToHost));
+  CU_OK(cudaMemcpy(ss, d + 2 * n, nb, cudaMemcpyDeviceToHost));
+  CU_OK(cudaMemcpy(sc, d + 3 * n, nb, cudaMemcpyDeviceToHost));
+  CU_OK(cudaMemcpy(sm, d + 4 * n, nb, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return 0;
+}
+
+// host build of the clip kernel's moments routine (tests only): out = {area, ctrlon, ctrlat}
+extern "C" void xgb_poly_moments_site_host(int order, int n, const double* x, const double* y, double clon, double* out)
+{
+  PolyView pv{x, y, 1};
+  out[1] = out[2] = 0.0;
+  if (order == 2) poly_moments_site<2>(pv, n, clon, ref_trig_table(), &out[0], &out[1], &out[2]);
+  else            poly_moments_site<1>(pv, n, clon, ref_trig_table(), &out[0], &out[1], &out[2]);
 }

@@ -99,8 +99,8 @@ __device__ inline int fix_lon(double* x, double* y, int n, double tlon) {
 // ---------------------------------------------------------------------------------------------
 struct PolyView {
   const double* x; const double* y; int stride;
-  __device__ __forceinline__ double X(int k) const { return x[k * stride]; }
-  __device__ __forceinline__ double Y(int k) const { return y[k * stride]; }
+  XGB_HD double X(int k) const { return x[k * stride]; }
+  XGB_HD double Y(int k) const { return y[k * stride]; }
 };
 
 // poly_area_main (mosaic_util.c:417-459) -> m^2
@@ -304,6 +304,95 @@ __device__ __forceinline__ void poly_moments(const PolyView& p, int n, double cl
 #if defined(__CUDA_ARCH__)
     if (WARP) __syncwarp();
 #endif
+  }
+  *area_out = (aacc < 0) ? -aacc * kRadius * kRadius : aacc * kRadius * kRadius;
+  if (ORDER == 2) { *ctrlon_out = lonacc * kRadius * kRadius; *ctrlat_out = latacc * kRadius * kRadius; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same three sums with ONE trig evaluation site (ref_trig_site) and rolled loops: the clip kernel is bound by
+// instruction fetch, and poly_moments above inlines five copies of the trig range paths.  Edge i runs up to three
+// evaluations through the site: sincos(lat of the next vertex) [order 2], sincos(avg) [moving edges, order 2] and sin(avg)
+// with ref_sin's own reduction where poly_area's sin() differs from sincos's (see above).  Iteration -1 only evaluates
+// vertex 0.  Every accumulated term is the expression of poly_moments, so the results are bit-identical to it
+// (tests/test_capi_cpu.py pins this routine against the oracle's poly_area / poly_ctrlon / poly_ctrlat on the host).
+// T = the 440-entry sin/cos table (shared memory in the kernel).
+// ---------------------------------------------------------------------------------------------
+template <int ORDER>
+XGB_HD void poly_moments_site(const PolyView& p, int n, double clon, const double* T,
+                              double* area_out, double* ctrlon_out, double* ctrlat_out) {
+  double aacc = 0.0, lonacc = 0.0, latacc = 0.0;
+  double xi = 0.0, yi = 0.0, si = 0.0, ci = 0.0, s0 = 0.0, c0 = 0.0;
+#pragma unroll 1
+  for (int i = -1; i < n; ++i) {
+    const bool edge = (i >= 0);
+    const bool fresh = (i + 1 < n);                      // the next vertex is not vertex 0 again
+    const int kn = fresh ? i + 1 : 0;
+    const double xn = p.X(kn), yn = p.Y(kn);
+    const double lat1 = yn, lat2 = yi;
+    const double dx_raw = xn - xi;                       // x[ip]-x[i] == phi1-phi2
+    double dxa = dx_raw;                                 // poly_area's wrapped dx (mosaic_util.c:429-432)
+    if (dxa > kPi)  dxa = dxa - 2.0 * kPi;
+    if (dxa < -kPi) dxa = dxa + 2.0 * kPi;
+    const bool pole_edge = (fabs(dxa + kPi) < kSmall || fabs(dxa - kPi) < kSmall);
+    const bool flat_area = (fabs(lat1 - lat2) < kSmall);
+    const double avg = 0.5 * (lat1 + lat2);
+    const double dy = 0.5 * (lat1 - lat2);               // hdy of poly_ctrlat is -dy
+    const bool moving = (ORDER == 2) && edge && (dx_raw != 0.0);
+    const bool flat_lat = (fabs(dy) < kSmall);
+    const uint32_t hi = (uint32_t)(trig::bits(avg) >> 32) & 0x7fffffffu;
+    const bool own_sin = edge && !pole_edge && !(moving && hi < 0x3feb6000u);
+    double sn = s0, cn = c0, s_avg = 0.0, c_avg = 0.0, sin_avg = 0.0;
+#pragma unroll 1
+    for (int t = (ORDER == 2) ? 0 : 2; t < 3; ++t) {
+      const bool doit = (t == 0) ? ((ORDER == 2) && fresh) : (t == 1) ? moving : own_sin;
+      if (doit) {
+        double s_, c_;
+        ref_trig_site((t == 0) ? yn : avg, t == 2, &s_, &c_, T);
+        if (t == 0) { sn = s_; cn = c_; }
+        else if (t == 1) { s_avg = s_; c_avg = c_; }
+        else sin_avg = s_;
+      }
+    }
+    if (!own_sin) sin_avg = s_avg;
+    if (edge) {
+      double dat = 0.0;
+      if ((!pole_edge && !flat_area) || (moving && !flat_lat)) dat = ref_sin_small(dy) / dy;
+      if (pole_edge) {
+        aacc += kPi;                                     // mosaic_util.c:434-437
+      } else {
+        if (flat_area) aacc -= dxa * sin_avg;
+        else           aacc -= dxa * sin_avg * dat;
+      }
+      if (moving) {
+        // poly_ctrlat (create_xgrid.c:2100-2118)
+        double dxl = dx_raw;
+        if (dxl > kPi)   dxl = dxl - 2.0 * kPi;
+        if (dxl <= -kPi) dxl = dxl + 2.0 * kPi;
+        if (flat_lat) latacc -= dxl * (2 * c_avg + lat2 * s_avg - cn);
+        else          latacc -= dxl * (dat * (2 * c_avg + lat2 * s_avg) - cn);
+        // poly_ctrlon (create_xgrid.c:2176-2215)
+        const double f1 = 0.5 * (cn * sn + lat1);
+        const double f2 = 0.5 * (ci * si + lat2);
+        double dphi = dx_raw;
+        if (dphi > kPi)  dphi = dphi - 2.0 * kPi;
+        if (dphi < -kPi) dphi = dphi + 2.0 * kPi;
+        double dphi1 = xn - clon;
+        if (dphi1 > kPi)  dphi1 -= 2.0 * kPi;
+        if (dphi1 < -kPi) dphi1 += 2.0 * kPi;
+        double dphi2 = xi - clon;
+        if (dphi2 > kPi)  dphi2 -= 2.0 * kPi;
+        if (dphi2 < -kPi) dphi2 += 2.0 * kPi;
+        if (fabs(dphi2 - dphi1) < kPi) {
+          lonacc -= dphi * (dphi1 * f1 + dphi2 * f2) / 2.0;
+        } else {
+          const double fac = (dphi1 > 0.0) ? kPi : -kPi;
+          const double fint = f1 + (f2 - f1) * (fac - dphi1) / fabs(dphi);
+          lonacc -= 0.5 * dphi1 * (dphi1 - fac) * f1 - 0.5 * dphi2 * (dphi2 + fac) * f2 + 0.5 * fac * (dphi1 + dphi2) * fint;
+        }
+      }
+    } else { s0 = sn; c0 = cn; }
+    xi = xn; yi = yn; si = sn; ci = cn;
   }
   *area_out = (aacc < 0) ? -aacc * kRadius * kRadius : aacc * kRadius * kRadius;
   if (ORDER == 2) { *ctrlon_out = lonacc * kRadius * kRadius; *ctrlat_out = latacc * kRadius * kRadius; }

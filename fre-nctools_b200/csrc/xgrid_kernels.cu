@@ -480,7 +480,19 @@ void launch_candidates_single(const CellSet& src, const SrcMap& sm, const double
 // =============================================================================================
 // clip
 // =============================================================================================
-constexpr int kClipThreads = 128;
+#ifndef XGB_CLIP_VARIANT
+#define XGB_CLIP_VARIANT 0
+#endif
+#ifndef XGB_CLIP_THREADS
+#define XGB_CLIP_THREADS 128
+#endif
+#ifndef XGB_CLIP_BLOCKS
+#define XGB_CLIP_BLOCKS 5
+#endif
+#ifndef XGB_CLIP_BLOCKS1
+#define XGB_CLIP_BLOCKS1 XGB_CLIP_BLOCKS
+#endif
+constexpr int kClipThreads = XGB_CLIP_THREADS;
 constexpr int kFastCap = 8;       // shared-memory polygon capacity per thread (quad x quad)
 constexpr int kSlowCap = 50;      // reference MV (create_xgrid.h:31), thread-local fallback
 
@@ -565,10 +577,21 @@ __device__ __forceinline__ int clip_cell_fast(double* sbase, const double (&ex)[
   double ex0 = (n2 == 4) ? ex[3] : ex[2], ey0 = (n2 == 4) ? ey[3] : ey[2];
   // single exit: np <= 0 (empty, or -1 = needs the generic routine) simply skips the remaining edges, so the warp
   // leaves this function converged
+  // XGB_CLIP_VARIANT & 2: the destination-edge loop stays rolled (the vertices rotate through four register pairs) —
+  // a quarter of the code for a kernel that stalls on instruction fetch
+  double rxv[4] = {ex[0], ex[1], ex[2], ex[3]}, ryv[4] = {ey[0], ey[1], ey[2], ey[3]};
+#if (XGB_CLIP_VARIANT & 2)
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
   for (int e = 0; e < 4; ++e) {
     if (e < n2 && np > 0) {
+#if (XGB_CLIP_VARIANT & 2)
+      const double ex1 = rxv[0], ey1 = ryv[0];
+#else
       const double ex1 = ex[e], ey1 = ey[e];
+#endif
       const double edy = ey1 - ey0, endx = ex0 - ex1;             // (y1-y0), (x0-x1) of inside_edge
       const double* cx = sbase + (2 * cur) * P;
       const double* cy = cx + P;
@@ -612,6 +635,11 @@ __device__ __forceinline__ int clip_cell_fast(double* sbase, const double (&ex)[
       }
       ex0 = ex1; ey0 = ey1;
     }
+#if (XGB_CLIP_VARIANT & 2)
+    { const double tx = rxv[0], ty = ryv[0];
+      rxv[0] = rxv[1]; rxv[1] = rxv[2]; rxv[2] = rxv[3]; rxv[3] = tx;
+      ryv[0] = ryv[1]; ryv[1] = ryv[2]; ryv[2] = ryv[3]; ryv[3] = ty; }
+#endif
     __syncwarp();
   }
   *result_buf = cur;
@@ -639,13 +667,21 @@ __device__ __forceinline__ bool load_src_poly(const CellSet& src, long long s, i
 }
 
 template <int ORDER>
-__global__ void __launch_bounds__(kClipThreads, 5)   // 96 registers: 5 blocks/SM measured 7 % faster than 4 (120 regs) or 6 (80, spills)
+__global__ void __launch_bounds__(kClipThreads, (ORDER == 1) ? XGB_CLIP_BLOCKS1 : XGB_CLIP_BLOCKS)   // 96 registers: 5 blocks/SM measured 7 % faster than 4 (120 regs) or 6 (80, spills)
 clip_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const int2* __restrict__ pairs,
             unsigned long long npairs, SrcMap smap,
             double* __restrict__ parea, double* __restrict__ pclon, double* __restrict__ pclat,
             uint32_t* __restrict__ cnt, int* err)
 {
   __shared__ double sm[4 * kFastCap * kClipThreads];            // [A.x A.y B.x B.y][vertex][thread]
+#if (XGB_CLIP_VARIANT & 4)
+  __shared__ __align__(16) double s_tab[440];                    // sin/cos table of ref_trig.cuh: LDS instead of LDG
+  for (int k = threadIdx.x; k < 440; k += kClipThreads) s_tab[k] = ref_trig_table()[k];
+  __syncthreads();
+  const double* T = s_tab;
+#else
+  const double* T = ref_trig_table();
+#endif
   const unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
   const bool valid = p < npairs;                                  // no early exit: the warp reconverges explicitly below
   const int2 pr = valid ? pairs[p] : make_int2(0, 0);
@@ -701,7 +737,11 @@ clip_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const int
     double a;
     // (the warp-synchronous variant poly_moments<ORDER, true> measured 5 % slower on C768 -> 1/8 degree: the lanes of a
     // warp hold polygons of similar size, and waiting for the slowest lane after every sin/cos costs more than it saves)
+#if (XGB_CLIP_VARIANT & 1)
+    poly_moments_site<ORDER>(pv, n_out, s_xavg, T, &a, &xclon, &xclat);   // one trig site, rolled loops
+#else
     poly_moments<ORDER>(pv, n_out, s_xavg, &a, &xclon, &xclat);  // poly_area :805, poly_ctrlon :1091, poly_ctrlat :1092
+#endif
     xarea = a * m;
     const double a1 = src.area[s], a2 = dst.area[d];
     const double min_area = (a1 < a2) ? a1 : a2;                 // :806

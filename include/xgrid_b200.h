@@ -276,6 +276,32 @@ int xgb_gc_clip_host(const double *x1, const double *y1, const double *z1, int n
 /* sin/cos/sincos of csrc/ref_trig.cuh evaluated by the host build and by a device kernel (host pointers). */
 void xgb_ref_trig_host(long long n, const double *x, double *s, double *c, double *ss, double *sc);
 int  xgb_ref_trig_device(long long n, const double *x, double *s, double *c, double *ss, double *sc);
+/* the single-evaluation-site variant used inside the clip kernel (ref_trig_site / ref_sin_small): s1 = sin-only mode,
+   (ss, sc) = sincos mode, sm = ref_sin_small */
+void xgb_ref_trig_site_host(long long n, const double *x, double *s1, double *ss, double *sc, double *sm);
+int  xgb_ref_trig_site_device(long long n, const double *x, double *s1, double *ss, double *sc, double *sm);
+/* host build of the clip kernel's one-pass poly_area / poly_ctrlon / poly_ctrlat (csrc/xgrid_geom.cuh poly_moments_site):
+   out = {area, ctrlon, ctrlat} of the n-vertex polygon (order 1: area only) */
+void xgb_poly_moments_site_host(int order, int n, const double *x, const double *y, double clon, double *out);
+
+/* ------------------------------------------------------------------------------------------
+ * Part 4 — remap files (host side).  The file fregrid writes after weight generation and reads back with
+ * --remap_file (conserve_interp.c:382-438; read_mosaic.c:330-560), in the classic netCDF formats fregrid's
+ * --format option names (classic, 64bit_offset; mpp_io.c:1526-1540) plus CDF-5.  netCDF-4/HDF5 files are refused with a
+ * message.  Layout: dims string=255, ncells, two=2; int tile1(ncells), int tile1_cell(ncells,two),
+ * int tile2_cell(ncells,two), double xgrid_area(ncells) [m2], double tile1_distance(ncells,two) (order 2); 1-based on
+ * disk, 0-based in memory.  setup_conserve_interp honours READ / WRITE through these.
+ * ---------------------------------------------------------------------------------------- */
+/* "classic" | "64bit_offset" | "cdf5" for the files written from now on (set_in_format); nonzero + xgb_last_error otherwise */
+int xgb_set_nc_format(const char *name);
+int xgb_get_nc_format(void);                               /* 1, 2 or 5 */
+/* lists as setup_conserve_interp leaves them in Interp_config (0-based; i_out/j_out relative to isc/jsc) */
+int xgb_remap_write(const char *path, int order, long long nxgrid, const int *t_in, const int *i_in, const int *j_in,
+                    const int *i_out, const int *j_out, int isc, int jsc, const double *area, const double *di, const double *dj);
+long long xgb_remap_size(const char *path);                /* read_mosaic_xgrid_size; < 0 on error */
+/* read_mosaic_xgrid_order1/2 + the tile1 read and area rescale of conserve_interp.c:81-90: 0-based lists, area in m2 */
+int xgb_remap_read(const char *path, int order, long long cap, int *t_in, int *i_in, int *j_in, int *i_out, int *j_out,
+                   double *area, double *di, double *dj);
 
 #ifdef __cplusplus
 }

@@ -144,6 +144,15 @@ typedef struct {
  *   jsc_out/jec_out: destination row window [jsc,jec] owned by this "rank" (fregrid_util.c:592-603);
  *                    pass 0, ny_out-1 for the serial case.
  */
+/* the next ref_regrid_setup runs setup_conserve_interp with WRITE (mode 1) or READ (mode 2) on interp[0].remap_file = name */
+static unsigned int ref_remap_mode = 0;
+static char ref_remap_name[STRING];
+void ref_next_setup_remap(const char *name, int mode)
+{
+  strncpy(ref_remap_name, name, STRING-1);
+  ref_remap_mode = (mode == 1) ? WRITE : (mode == 2) ? READ : 0;
+}
+
 RefRegrid *ref_regrid_setup(int ntiles_in, const int *nx_in, const int *ny_in,
                             const double *lonc_in, const double *latc_in,
                             const double *lont_in, const double *latt_in,
@@ -204,6 +213,13 @@ RefRegrid *ref_regrid_setup(int ntiles_in, const int *nx_in, const int *ny_in,
     else                      get_grid_area(&g->nxc, &g->nyc, g->lonc, g->latc, g->cell_area);
   }
   r->interp[0].file_exist = 0;
+  if(ref_remap_mode) {   /* WRITE into / READ from the in-memory file store of shim/io_stubs.c */
+    strncpy(r->interp[0].remap_file, ref_remap_name, STRING-1);
+    r->interp[0].file_exist = (ref_remap_mode == READ);
+    setup_conserve_interp(ntiles_in, r->gin, 1, r->gout, r->interp, (opcode & ~(WRITE|READ|CHECK_CONSERVE)) | ref_remap_mode);
+    ref_remap_mode = 0;
+    return r;
+  }
   setup_conserve_interp(ntiles_in, r->gin, 1, r->gout, r->interp, opcode & ~(WRITE|READ|CHECK_CONSERVE));
   return r;
 }
@@ -335,6 +351,19 @@ RefRegrid *ref_regrid_setup_through(const RefRegrid *r, void *setup_fn)
   *q = *r;
   q->interp = (Interp_config *)calloc(1, sizeof(Interp_config));
   ((setup_fn_t)setup_fn)(q->ntiles_in, q->gin, 1, q->gout, q->interp, q->opcode & ~(WRITE|READ|CHECK_CONSERVE|LEGACY_CLIP));
+  return q;
+}
+
+/* the same, with WRITE (mode 1) or READ (mode 2) set and interp[0].remap_file = name: the product writes / reads a real file */
+RefRegrid *ref_regrid_setup_through_remap(const RefRegrid *r, void *setup_fn, const char *name, int mode)
+{
+  RefRegrid *q = (RefRegrid *)calloc(1, sizeof(RefRegrid));
+  *q = *r;
+  q->interp = (Interp_config *)calloc(1, sizeof(Interp_config));
+  strncpy(q->interp[0].remap_file, name, STRING-1);
+  q->interp[0].file_exist = (mode == 2);
+  ((setup_fn_t)setup_fn)(q->ntiles_in, q->gin, 1, q->gout, q->interp,
+                         (q->opcode & ~(WRITE|READ|CHECK_CONSERVE|LEGACY_CLIP)) | (mode == 1 ? WRITE : mode == 2 ? READ : 0));
   return q;
 }
 

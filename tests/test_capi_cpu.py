@@ -57,3 +57,45 @@ def test_struct_layout_matches_reference(pkg, reflib):
     na = L.xgb_abi_layout(a, 64); nb = reflib.ref_abi_layout(b, 64)
     assert na == nb and na >= 30
     assert list(a)[:na] == list(b)[:nb]
+
+
+def _moment_polygons(rng, count):
+    """convex-ish polygons of 3..8 vertices at every latitude, with the special edges the routines branch on: meridian edges
+    (dx == 0), parallels (dy == 0), a side through a pole (|dx| == pi), longitudes straddling +-pi of the centre"""
+    for c in range(count):
+        n = int(rng.integers(3, 9))
+        lat0 = rng.uniform(-1.55, 1.55)
+        lon0 = rng.uniform(-1.0, 7.0)
+        r = 10.0 ** rng.uniform(-4, -0.5)
+        ang = np.sort(rng.uniform(0, 2 * np.pi, n))
+        x = lon0 + r * np.cos(ang) / max(np.cos(lat0), 0.05)
+        y = np.clip(lat0 + r * np.sin(ang), -np.pi / 2, np.pi / 2)
+        kind = c % 8
+        if kind == 1:
+            x[1] = x[0]                      # meridian edge
+        elif kind == 2:
+            y[2 % n] = y[1]                  # parallel
+        elif kind == 3:
+            x[1] = x[0] + np.pi              # side through a pole
+        elif kind == 4:
+            x[n - 1] = x[0]; y[n - 1] = y[0] + 1e-11   # nearly flat, not moving
+        clon = lon0 + (rng.uniform(-4, 4) if kind == 5 else rng.uniform(-r, r))
+        yield n, np.ascontiguousarray(x), np.ascontiguousarray(y), clon
+
+
+def test_poly_moments_site_host_build_equals_oracle(pkg):
+    """csrc/xgrid_geom.cuh poly_moments_site (the clip kernel's one-pass area + centroid sums, host build) against the
+    oracle's poly_area / poly_ctrlon / poly_ctrlat: bit for bit"""
+    L = pkg.lib()
+    O = xgtest.oracle_lib()
+    rng = np.random.default_rng(2024)
+    out = np.zeros(3)
+    bad = 0
+    for n, x, y, clon in _moment_polygons(rng, 20000):
+        want = (O.orc_poly_area(x, y, n), O.orc_poly_ctrlon(x, y, n, clon), O.orc_poly_ctrlat(x, y, n))
+        for order in (1, 2):
+            L.xgb_poly_moments_site_host(order, n, x.ctypes.data, y.ctypes.data, clon, out.ctypes.data)
+            m = 3 if order == 2 else 1
+            if not all(np.float64(out[k]).view(np.uint64) == np.float64(want[k]).view(np.uint64) for k in range(m)):
+                bad += 1
+                assert bad < 1, (order, n, x, y, clon, out, want)

@@ -130,6 +130,19 @@ def ref_lib():
         L.ref_regrid_apply_ex.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, vp, vp, C.c_double, C.c_uint, dp, vp, vp, vp, dp]
         L.ref_compute_extent.argtypes = [C.c_int, C.c_int, ip, ip]
         L.ref_abi_layout.argtypes = [C.POINTER(C.c_size_t), C.c_int]
+        L.ref_next_setup_remap.argtypes = [C.c_char_p, C.c_int]
+        L.ref_regrid_setup_through_remap.restype = vp
+        L.ref_regrid_setup_through_remap.argtypes = [vp, vp, C.c_char_p, C.c_int]
+        for name in ("stub_dim_name", "stub_var_name", "stub_var_att_name", "stub_var_att_value"):
+            getattr(L, name).restype = C.c_char_p
+        L.stub_find.argtypes = [C.c_char_p]
+        L.stub_new_file.argtypes = [C.c_char_p]
+        L.stub_add_dim.argtypes = [C.c_int, C.c_char_p, C.c_long]
+        L.stub_add_var.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_int, ip]
+        L.stub_set_var_data.argtypes = [C.c_int, C.c_int, vp]
+        L.stub_var_data.restype = vp
+        L.stub_var_nelem.restype = C.c_long
+        L.stub_dim_size.restype = C.c_long
         L.ref_regrid_setup_through.restype = vp
         L.ref_regrid_setup_through.argtypes = [vp, vp]
         L.ref_regrid_apply_through.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint, dp, vp, vp, vp, dp]
@@ -199,7 +212,7 @@ def oracle_setup(lonc, latc, lon2, lat2, opcode, cap=None):
     return _trim(out, n)
 
 
-def ref_setup(lonc, latc, lon2, lat2, opcode, jsc=None, jec=None, keep=False):
+def ref_setup(lonc, latc, lon2, lat2, opcode, jsc=None, jec=None, keep=False, remap=None):
     """the reference's own setup_conserve_interp (conserve_interp.c:42) through oracle/ref_driver.c"""
     L = ref_lib()
     nx, ny, lon, lat = _tiles(lonc, latc)
@@ -211,6 +224,8 @@ def ref_setup(lonc, latc, lon2, lat2, opcode, jsc=None, jec=None, keep=False):
     if not (opcode & GREAT_CIRCLE):
         opcode |= LEGACY_CLIP
     devnull = os.open(os.devnull, os.O_WRONLY); saved = os.dup(1); os.dup2(devnull, 1)   # reference prints a NOTE
+    if remap is not None:      # (name, 1 = WRITE | 2 = READ) against the in-memory file store of oracle/shim/io_stubs.c
+        L.ref_next_setup_remap(remap[0].encode(), remap[1])
     try:
         r = L.ref_regrid_setup(len(nx), nx, ny, lon, lat, None, None, nx2, ny2, lon2.ravel(), lat2.ravel(), jsc, jec, opcode)
     finally:
@@ -506,3 +521,44 @@ def ref_apply_ex(handle, order, data, nout, grad_x=None, grad_y=None, gmask=None
     L.ref_regrid_apply_ex(handle, order, int(has_missing), float(missing), int(cell_methods), ptr(weight), ptr(farea), float(area_missing),
                           extra, np.ascontiguousarray(data, np.float64), ptr(grad_x), ptr(grad_y), ptr(gmask, np.int32), out)
     return out
+
+
+NC_TYPES = {1: "b", 2: "c", 3: "h", 4: "i", 5: "f", 6: "d"}
+
+
+def ref_store_file(name):
+    """what the reference handed its I/O layer for file `name` (oracle/shim/io_stubs.c): dims [(name, size)], vars
+    [(name, nc_type, dim indices, [(att, value)], data)] in definition order"""
+    L = ref_lib()
+    f = L.stub_find(name.encode())
+    assert f >= 0, name
+    dims = [(L.stub_dim_name(f, d).decode(), L.stub_dim_size(f, d)) for d in range(L.stub_ndims(f))]
+    out = []
+    for v in range(L.stub_nvars(f)):
+        t = L.stub_var_type(f, v)
+        dd = [L.stub_var_dim(f, v, k) for k in range(L.stub_var_ndim(f, v))]
+        atts = [(L.stub_var_att_name(f, v, a).decode(), L.stub_var_att_value(f, v, a).decode()) for a in range(L.stub_var_natts(f, v))]
+        n = L.stub_var_nelem(f, v)
+        dt = {4: np.int32, 6: np.float64}[t]
+        data = np.ctypeslib.as_array(C.cast(L.stub_var_data(f, v), C.POINTER(C.c_int if t == 4 else C.c_double)), shape=(n,)).astype(dt).copy()
+        out.append((L.stub_var_name(f, v).decode(), t, dd, atts, data.reshape([dims[k][1] for k in dd])))
+    return dims, out
+
+
+def ref_store_load(name, path):
+    """put the contents of a classic netCDF file (read with scipy, an implementation independent of csrc/nc3.c) into the
+    reference's in-memory file store under `name`, so that its READ branch can be run on it"""
+    from scipy.io import netcdf_file
+    L = ref_lib()
+    g = netcdf_file(path, "r", mmap=False)
+    f = L.stub_new_file(name.encode())
+    dn = list(g.dimensions)
+    for d in dn:
+        L.stub_add_dim(f, d.encode(), g.dimensions[d])
+    for vn, var in g.variables.items():
+        t = {"i": 4, "d": 6}[var.typecode()]
+        dd = np.array([dn.index(d) for d in var.dimensions], np.int32)
+        v = L.stub_add_var(f, vn.encode(), t, len(dd), dd)
+        data = np.ascontiguousarray(var[:], np.int32 if t == 4 else np.float64)
+        L.stub_set_var_data(f, v, data.ctypes.data)
+    g.close()
