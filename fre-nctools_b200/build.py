@@ -6,6 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libxgrid_b200.so")
+CLI_SRC = os.path.join(HERE, "cli", "fregrid_b200.c")
+CLI_OUT = os.path.join(HERE, "bin", "fregrid_b200")
 # -fmad=false: the exchange grid's accept/reject predicates must round like the reference's
 # un-fused x86-64 arithmetic (see csrc/xgrid_geom.cuh).
 NVCC_FLAGS = [
@@ -23,7 +25,9 @@ def needs_build():
         return True
     t = os.path.getmtime(OUT)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    deps += [os.path.join(HERE, "..", "include", "xgrid_b200.h"), os.path.abspath(__file__)]
+    deps += [os.path.join(HERE, "..", "include", "xgrid_b200.h"), os.path.abspath(__file__), CLI_SRC]
+    if not os.path.exists(CLI_OUT):
+        return True
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
@@ -42,7 +46,20 @@ def build(force=False, verbose=False, out=None, defines=()):
         return out
     with open(os.path.join(HERE, "build_ptxas.log"), "w") as f:
         f.write(r.stdout + r.stderr)
+    build_cli()
     return OUT
+
+
+def build_cli():
+    """fregrid_b200: the host side of the fregrid command line in C, linked against libxgrid_b200.so next to it."""
+    os.makedirs(os.path.dirname(CLI_OUT), exist_ok=True)
+    cmd = [os.environ.get("CC", "gcc"), "-O2", "-std=gnu99", "-Wall", "-o", CLI_OUT, CLI_SRC, "-L" + HERE, "-lxgrid_b200",
+           "-Wl,-rpath,$ORIGIN/..", "-Wl,--allow-shlib-undefined", "-lm"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("gcc failed building fregrid_b200")
+    return CLI_OUT
 
 
 if __name__ == "__main__":

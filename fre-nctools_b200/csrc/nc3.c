@@ -626,6 +626,29 @@ int nc3_put_att_double(nc3_file *f, int varid, const char *name, int type, int n
   return 0;
 }
 
+int nc3_copy_att(const nc3_file *fin, int varid_in, const char *name, nc3_file *fout, int varid_out)
+{
+  const Att *a = find_att(fin, varid_in, name);
+  Att *b;
+  if (!a) return fail(fout, "nc3_copy_att: no attribute %s", name);
+  if (!fout->writing || !fout->defmode) return fail(fout, "nc3_copy_att: not in define mode");
+  b = new_att(fout, varid_out, name);
+  if (!b) return fail(fout, "nc3_copy_att: bad variable id");
+  b->type = a->type; b->n = a->n;
+  b->raw = (unsigned char *)malloc((size_t)a->n * tsize(a->type) + 1);
+  memcpy(b->raw, a->raw, (size_t)a->n * tsize(a->type));
+  return 0;
+}
+
+int nc3_copy_atts(const nc3_file *fin, int varid_in, nc3_file *fout, int varid_out)
+{
+  Att *a;
+  const int n = att_list(fin, varid_in, &a);
+  int i;
+  for (i = 0; i < n; ++i) if (nc3_copy_att(fin, varid_in, a[i].name, fout, varid_out)) return -1;
+  return 0;
+}
+
 /* header serialisation */
 typedef struct { unsigned char *p; size_t n, cap; int fmt; } Out;
 static void o_need(Out *o, size_t k) { if (o->n + k > o->cap) { o->cap = (o->n + k) * 2 + 256; o->p = (unsigned char *)realloc(o->p, o->cap); } }

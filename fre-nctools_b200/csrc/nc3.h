@@ -57,6 +57,9 @@ int nc3_def_dim(nc3_file *f, const char *name, long long len);                  
 int nc3_def_var(nc3_file *f, const char *name, int type, int ndims, const int *dimids); /* returns varid */
 int nc3_put_att_text(nc3_file *f, int varid, const char *name, const char *text);
 int nc3_put_att_double(nc3_file *f, int varid, const char *name, int type, int n, const double *vals);
+/* copy one attribute (any type) / every attribute of a variable from an open file into a file in define mode */
+int nc3_copy_att(const nc3_file *fin, int varid_in, const char *name, nc3_file *fout, int varid_out);
+int nc3_copy_atts(const nc3_file *fin, int varid_in, nc3_file *fout, int varid_out);
 int nc3_enddef(nc3_file *f);
 int nc3_put_vara_double(nc3_file *f, int varid, const size_t *start, const size_t *count, const double *in);
 int nc3_put_vara_int(nc3_file *f, int varid, const size_t *start, const size_t *count, const int *in);

@@ -1,0 +1,260 @@
+"""fregrid_b200 (fre-nctools_b200/cli/fregrid_b200.c) end to end on the GPU: mosaic + supergrid + field files in classic netCDF
+(written here with scipy, an implementation independent of csrc/nc3.c) -> remap file and remapped fields, checked against the
+oracle on the same grids.  Mirrors the reference's own CLI tests (t/Test20-fregrid.sh: run fregrid on a cubed-sphere mosaic,
+look at the files it leaves behind), with numbers instead of `ncdump` existence checks."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+from scipy.io import netcdf_file
+
+import xgtest
+
+pytestmark = pytest.mark.gpu
+
+D2R = np.pi / 180.0
+R2D = 180.0 / np.pi
+NI = 16
+MISSING = np.float32(-1.0e10)
+
+
+def _exe(pkg):
+    path = os.path.join(os.path.dirname(pkg.__file__), "bin", "fregrid_b200")
+    assert os.path.exists(path), "fregrid_b200 is not built (python __graft_entry__.py)"
+    return path
+
+
+def _contacts(hmap, n):
+    """the mosaic's contact list from geometry (what make_solo_mosaic writes): for every pair of tiles sharing an edge, the
+    edge of each in supergrid indices, reversed on the second side when the two edges run in opposite directions"""
+    S = 2 * n
+    def side(t, which):
+        idx = {"W": hmap[t, 1:-1, 0], "E": hmap[t, 1:-1, n + 1], "S": hmap[t, 0, 1:-1], "N": hmap[t, n + 1, 1:-1]}[which]
+        tt = idx // (n * n); jj, ii = np.divmod(idx % (n * n), n)
+        assert np.all(tt == tt[0])
+        if np.all(ii == 0): other, along = "W", jj
+        elif np.all(ii == n - 1): other, along = "E", jj
+        elif np.all(jj == 0): other, along = "S", ii
+        else:
+            assert np.all(jj == n - 1); other, along = "N", ii
+        return int(tt[0]), other, bool(along[0] > along[-1])
+    def rng(which, rev):
+        a = f"{S}:1" if rev else f"1:{S}"
+        return {"W": f"1:1,{a}", "E": f"{S}:{S},{a}", "S": f"{a},1:1", "N": f"{a},{S}:{S}"}[which]
+    names, index, seen = [], [], set()
+    for t in range(6):
+        for which in "WESN":
+            tt, other, rev = side(t, which)
+            if (tt, other, t, which) in seen:
+                continue
+            seen.add((t, which, tt, other))
+            names.append(f"C{n}_mosaic:tile{t + 1}::C{n}_mosaic:tile{tt + 1}")
+            index.append(f"{rng(which, False)}::{rng(other, rev)}")
+    assert len(names) == 12
+    return names, index
+
+
+def _strings(g, name, dim, values):
+    v = g.createVariable(name, "c", (dim, "string"))
+    for k, s in enumerate(values):
+        v[k] = np.frombuffer(s.encode().ljust(255, b"\0"), "S1")
+
+
+@pytest.fixture(scope="module")
+def dataset(pkg, tmp_path_factory):
+    d = str(tmp_path_factory.mktemp("cli"))
+    n = NI
+    lonc, latc, lont, latt = pkg.cubed_sphere_grid(n, centers=True)
+    hmap = xgtest.cubed_sphere_halo_map(lonc, latc)
+    names, index = _contacts(hmap, n)
+    g = netcdf_file(os.path.join(d, f"C{n}_mosaic.nc"), "w", version=2)
+    g.createDimension("ntiles", 6); g.createDimension("ncontact", 12); g.createDimension("string", 255)
+    m = g.createVariable("mosaic", "c", ("string",)); m[:] = np.frombuffer(f"C{n}_mosaic".encode().ljust(255, b"\0"), "S1")
+    _strings(g, "gridfiles", "ntiles", [f"C{n}_grid.tile{t + 1}.nc" for t in range(6)])
+    _strings(g, "gridtiles", "ntiles", [f"tile{t + 1}" for t in range(6)])
+    _strings(g, "contacts", "ncontact", names)
+    _strings(g, "contact_index", "ncontact", index)
+    g.close()
+    xdeg = np.zeros((6, 2 * n + 1, 2 * n + 1)); ydeg = np.zeros_like(xdeg)
+    xdeg[:, ::2, ::2] = lonc * R2D; ydeg[:, ::2, ::2] = latc * R2D
+    xdeg[:, 1::2, 1::2] = lont * R2D; ydeg[:, 1::2, 1::2] = latt * R2D
+    for t in range(6):
+        g = netcdf_file(os.path.join(d, f"C{n}_grid.tile{t + 1}.nc"), "w", version=2)
+        g.createDimension("nx", 2 * n); g.createDimension("ny", 2 * n); g.createDimension("nxp", 2 * n + 1); g.createDimension("nyp", 2 * n + 1)
+        x = g.createVariable("x", "d", ("nyp", "nxp")); y = g.createVariable("y", "d", ("nyp", "nxp"))
+        x[:] = xdeg[t]; y[:] = ydeg[t]
+        g.close()
+    # what the tool sees after degrees -> radians (fregrid_util.c:227-241)
+    lonc_r = xdeg[:, ::2, ::2] * D2R; latc_r = ydeg[:, ::2, ::2] * D2R
+    lont_r = xdeg[:, 1::2, 1::2] * D2R; latt_r = ydeg[:, 1::2, 1::2] * D2R
+    nt, nz = 2, 3
+    rng = np.random.default_rng(7)
+    temp = np.stack([[xgtest.smooth_field(lont_r, latt_r, k, t).reshape(6, n, n) for k in range(nz)] for t in range(nt)]).astype(np.float32)
+    hole = rng.uniform(size=temp.shape) < 0.05
+    temp[hole] = MISSING
+    ps = np.stack([xgtest.smooth_field(lont_r, latt_r, 0, t).reshape(6, n, n) * 1000.0 for t in range(nt)])
+    orog = rng.uniform(0, 3000, (6, n, n))
+    for t in range(6):
+        g = netcdf_file(os.path.join(d, f"atmos.tile{t + 1}.nc"), "w", version=2)
+        g.createDimension("time", None); g.createDimension("pfull", nz); g.createDimension("grid_yt", n); g.createDimension("grid_xt", n)
+        g.title = "synthetic"
+        v = g.createVariable("time", "d", ("time",)); v.units = "days since 2000-01-01"; v.cartesian_axis = "T"
+        p = g.createVariable("pfull", "d", ("pfull",)); p.units = "mb"; p.cartesian_axis = "Z"; p[:] = [100.0, 500.0, 900.0]
+        yy = g.createVariable("grid_yt", "d", ("grid_yt",)); yy.cartesian_axis = "Y"; yy.units = "degrees_N"; yy[:] = np.arange(1.0, n + 1)
+        xx = g.createVariable("grid_xt", "d", ("grid_xt",)); xx.cartesian_axis = "X"; xx.units = "degrees_E"; xx[:] = np.arange(1.0, n + 1)
+        a = g.createVariable("temp", "f", ("time", "pfull", "grid_yt", "grid_xt")); a.missing_value = MISSING; a.units = "K"; a.long_name = "temperature"
+        b = g.createVariable("ps", "d", ("time", "grid_yt", "grid_xt")); b.units = "Pa"
+        c = g.createVariable("orog", "d", ("grid_yt", "grid_xt")); c.units = "m"
+        c[:] = orog[t]
+        for k in range(nt):
+            v[k] = 10.0 + k; a[k] = temp[k, :, t]; b[k] = ps[k, t]
+        g.close()
+    return dict(dir=d, n=n, lonc=lonc_r, latc=latc_r, lont=lont_r, latt=latt_r, hmap=hmap, temp=temp, ps=ps, orog=orog, nt=nt, nz=nz)
+
+
+def _run(pkg, ds, *args, ok=True):
+    r = subprocess.run([_exe(pkg)] + list(args), cwd=ds["dir"], capture_output=True, text=True, timeout=600)
+    assert (r.returncode == 0) == ok, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
+    return r
+
+
+def _remap_lists(pkg, path, order):
+    from test_remap_cpu import _read
+    return _read(pkg, path, order)
+
+
+def test_weights_only_writes_the_reference_remap_file(pkg, dataset):
+    """configs[0]: cubed sphere -> lat-lon, order-1 conservative, remap file written"""
+    ds = dataset
+    r = _run(pkg, ds, "--input_mosaic", f"C{ds['n']}_mosaic.nc", "--nlon", "60", "--nlat", "30", "--remap_file", "remap_o1", "--check_conserve")
+    assert "only weight information is calculated" in r.stdout and "****remap_o1.nc" in r.stdout
+    assert "The maximum ratio change" in r.stdout
+    lon2, lat2 = pkg.latlon_grid(60, 30)
+    want = xgtest.oracle_setup(ds["lonc"], ds["latc"], lon2, lat2, xgtest.ORDER1)
+    got = _remap_lists(pkg, os.path.join(ds["dir"], "remap_o1.nc"), 1)
+    xgtest.assert_xgrid_equal(got, want, 1, area_tol=1e-12)
+    for k in ("t_in", "i_in", "j_in", "i_out", "j_out"):
+        assert np.array_equal(got[k], want[k])
+    g = netcdf_file(os.path.join(ds["dir"], "remap_o1.nc"), "r", mmap=False)
+    assert list(g.variables) == ["tile1", "tile1_cell", "tile2_cell", "xgrid_area"] and g.version_byte == 2
+    g.close()
+
+
+def _expected(pkg, ds, order, nlon, nlat):
+    lon2, lat2 = pkg.latlon_grid(nlon, nlat)
+    x = xgtest.oracle_setup(ds["lonc"], ds["latc"], lon2, lat2, xgtest.ORDER2 if order == 2 else xgtest.ORDER1)
+    n = ds["n"]; tiles = [(n, n)] * 6
+    metrics = None
+    if order == 2:
+        nh = (n + 2) ** 2
+        xt = xgtest.with_halo(ds["lont"].reshape(-1), ds["hmap"]); yt = xgtest.with_halo(ds["latt"].reshape(-1), ds["hmap"])
+        metrics = [xgtest.c2l_metrics("oracle", n, n, xt[t * nh:(t + 1) * nh], yt[t * nh:(t + 1) * nh], ds["lonc"][t], ds["latc"][t]) for t in range(6)]
+
+    def remap(field, has_missing, missing):
+        flat = np.asarray(field, np.float64).reshape(-1)
+        if order == 1:
+            return xgtest.oracle_apply(x, 1, tiles, flat, nlon, nlat, has_missing=has_missing, missing=missing)
+        nc, nh = n * n, (n + 2) ** 2
+        fh = xgtest.with_halo(flat, ds["hmap"])
+        gx = np.zeros(6 * nc); gy = np.zeros(6 * nc); gm = np.zeros(6 * nc, np.int32)
+        for t in range(6):
+            gx[t * nc:(t + 1) * nc], gy[t * nc:(t + 1) * nc] = xgtest.grad_c2l("oracle", n, n, fh[t * nh:(t + 1) * nh], metrics[t])
+            if has_missing:
+                gm[t * nc:(t + 1) * nc] = xgtest.grad_mask(n, n, fh[t * nh:(t + 1) * nh], missing)
+        return xgtest.oracle_apply(x, 2, tiles, fh, nlon, nlat, grad_x=gx, grad_y=gy, gmask=gm, has_missing=has_missing, missing=missing)
+    return remap
+
+
+def test_order1_fields_written_then_remap_file_read_back(pkg, dataset):
+    ds = dataset
+    nlon, nlat = 48, 24
+    args = ["--input_mosaic", f"C{ds['n']}_mosaic.nc", "--nlon", str(nlon), "--nlat", str(nlat), "--input_file", "atmos",
+            "--scalar_field", "temp,ps,orog", "--output_file", "out1.nc", "--remap_file", "remap_f1.nc"]
+    r1 = _run(pkg, ds, *args)
+    assert "done calculating index and weight" in r1.stdout and "****out1.nc" in r1.stdout
+    out = os.path.join(ds["dir"], "out1.nc")
+    g = netcdf_file(out, "r", mmap=False)
+    assert g.dimensions["grid_xt"] == nlon and g.dimensions["grid_yt"] == nlat and g.dimensions["pfull"] == ds["nz"] and g.dimensions["bnds"] == 2
+    assert g.variables["time"].shape == (ds["nt"],) and np.array_equal(g.variables["time"][:], [10.0, 11.0])
+    assert np.allclose(g.variables["grid_xt"][:], (np.arange(nlon) + 0.5) * 360.0 / nlon, rtol=0, atol=1e-12)
+    assert np.allclose(g.variables["grid_yt"][:], -90 + (np.arange(nlat) + 0.5) * 180.0 / nlat, rtol=0, atol=1e-12)
+    assert g.variables["grid_xt"].bounds == b"grid_xt_bnds" and np.allclose(g.variables["grid_xt_bnds"][:, 1], (np.arange(nlon) + 1) * 360.0 / nlon, atol=1e-12)
+    assert g.variables["temp"].interp_method == b"conserve_order1" and g.variables["temp"].units == b"K" and g.title == b"synthetic"
+    assert b"--scalar_field temp,ps,orog" in g.history
+    remap = _expected(pkg, ds, 1, nlon, nlat)
+    for t in range(ds["nt"]):
+        want = remap(ds["ps"][t], False, 0.0)
+        assert np.array_equal(g.variables["ps"][t].reshape(-1), want)                     # double field: bit for bit
+        for k in range(ds["nz"]):
+            want = remap(ds["temp"][t, k].astype(np.float64), True, float(MISSING))
+            assert np.array_equal(g.variables["temp"][t, k].reshape(-1), want.astype(np.float32))
+    assert np.array_equal(g.variables["orog"][:].reshape(-1), remap(ds["orog"], False, 0.0))
+    ps_first = g.variables["ps"][:].copy(); temp_first = g.variables["temp"][:].copy()
+    g.close()
+    size_first = os.path.getsize(out)
+    r2 = _run(pkg, ds, *args)                                  # the remap file exists now: READ branch
+    assert "Finish reading index and weight" in r2.stdout
+    g = netcdf_file(out, "r", mmap=False)
+    # (areas read back are (a / 4 pi R^2) * 4 pi R^2 like the reference's, so values agree to rounding, not bit for bit)
+    assert np.allclose(g.variables["ps"][:], ps_first, rtol=1e-14, atol=0)
+    assert np.allclose(g.variables["temp"][:], temp_first, rtol=2e-7, atol=0)
+    g.close()
+    assert size_first == os.path.getsize(out)
+
+
+def test_order2_fields_with_missing_values(pkg, dataset):
+    """configs[1] in small: order-2 remap with gradient terms of a 3-D field over levels and times; halos come from the mosaic
+    contacts, gradient metrics from the device (rounding-level differences from the oracle's)"""
+    ds = dataset
+    nlon, nlat = 64, 32
+    _run(pkg, ds, "--input_mosaic", f"C{ds['n']}_mosaic.nc", "--nlon", str(nlon), "--nlat", str(nlat), "--input_file", "atmos.nc",
+         "--scalar_field", "ps,temp", "--output_file", "out2", "--interp_method", "conserve_order2", "--format", "classic")
+    g = netcdf_file(os.path.join(ds["dir"], "out2.nc"), "r", mmap=False)
+    assert g.version_byte == 1 and g.variables["ps"].interp_method == b"conserve_order2"
+    remap = _expected(pkg, ds, 2, nlon, nlat)
+    for t in range(ds["nt"]):
+        want = remap(ds["ps"][t], False, 0.0)
+        got = g.variables["ps"][t].reshape(-1)
+        assert np.allclose(got, want, rtol=1e-11, atol=0), np.abs(got / want - 1).max()
+        for k in range(ds["nz"]):
+            want = remap(ds["temp"][t, k].astype(np.float64), True, float(MISSING))
+            got = g.variables["temp"][t, k].reshape(-1).astype(np.float64)
+            same_holes = (got == float(MISSING)) == (want == float(MISSING))
+            assert same_holes.all()
+            ok = want != float(MISSING)
+            assert np.allclose(got[ok], want[ok], rtol=3e-7, atol=0)        # float output
+    g.close()
+
+
+def test_klevel_lstep_windows_and_standard_dimension(pkg, dataset):
+    ds = dataset
+    _run(pkg, ds, "--input_mosaic", f"C{ds['n']}_mosaic.nc", "--nlon", "36", "--nlat", "18", "--input_file", "atmos", "--scalar_field", "temp",
+         "--output_file", "out3", "--KlevelBegin", "2", "--KlevelEnd", "3", "--LstepBegin", "2", "--LstepEnd", "2", "--standard_dimension")
+    g = netcdf_file(os.path.join(ds["dir"], "out3.nc"), "r", mmap=False)
+    assert g.dimensions["lon"] == 36 and g.dimensions["lat"] == 18 and g.dimensions["pfull"] == 2
+    assert g.variables["lon"].units == b"degrees_E" and g.variables["lon"].bounds == b"lon_bnds" and g.variables["lat_bnds"].shape == (18, 2)
+    assert np.array_equal(g.variables["pfull"][:], [500.0, 900.0]) and np.array_equal(g.variables["time"][:], [11.0])
+    remap = _expected(pkg, ds, 1, 36, 18)
+    want = remap(ds["temp"][1, 2].astype(np.float64), True, float(MISSING))
+    assert np.array_equal(g.variables["temp"][0, 1].reshape(-1), want.astype(np.float32))
+    g.close()
+
+
+def test_reference_error_messages(pkg, dataset):
+    ds = dataset
+    mosaic = f"C{ds['n']}_mosaic.nc"
+    cases = [
+        (["--nlon", "10", "--nlat", "5"], "input_mosaic is not specified"),
+        (["--input_mosaic", mosaic], "nlon and nlat should be specified"),
+        (["--input_mosaic", mosaic, "--nlon", "10", "--nlat", "5"], "remap_file must be specified to save weight information"),
+        (["--input_mosaic", mosaic, "--nlon", "10", "--nlat", "5", "--remap_file", "r", "--interp_method", "nearest"], "interp_method must be"),
+        (["--input_mosaic", mosaic, "--nlon", "10", "--nlat", "5", "--input_file", "atmos"], "both scalar_field and vector_field are not specified"),
+        (["--input_mosaic", mosaic, "--nlon", "10", "--nlat", "5", "--input_file", "atmos", "--scalar_field", "nope"], "variable nope"),
+        (["--input_mosaic", mosaic, "--nlon", "10", "--nlat", "5", "--remap_file", "r", "--format", "netcdf4"], "HDF5"),
+        (["--input_mosaic", mosaic, "--nlon", "10", "--nlat", "5", "--input_file", "atmos", "--u_field", "u", "--v_field", "v"],
+         "conservative interpolation of vector fields is not supported"),
+    ]
+    for args, msg in cases:
+        r = _run(pkg, ds, *args, ok=False)
+        assert r.returncode == 1 and "FATAL Error" in r.stderr and msg in r.stderr, (args, r.stderr)
