@@ -212,15 +212,30 @@ __device__ __forceinline__ double poly_ctrlon(const PolyView& p, int n, double c
 // WARP: called by all 32 lanes of a converged warp (lanes without a polygon pass n = 0).  The edge loop then runs to the
 // warp's largest vertex count and the lanes are re-converged explicitly after every data-dependent section (the
 // sin/cos routines branch on the argument range), which the compiler does not do on its own across the inlined code.
-template <int ORDER, bool WARP = false>
+// LEAN: the trig goes through ref_trig_site / ref_sin_small (ref_trig.cuh): one reduction and one sin-type + one cos-type
+// evaluation serve both table ranges, the large-argument reduction (never taken by latitudes) becomes a call, and sin of
+// the half-difference takes its Taylor path inline — same bits, about a third of the instructions per site.  The clip
+// kernel is bound by instruction fetch (profiles/r01*), so this is worth more than the arithmetic it saves.
+template <int ORDER, bool WARP = false, bool LEAN = false>
 __device__ __forceinline__ void poly_moments(const PolyView& p, int n, double clon,
-                                             double* area_out, double* ctrlon_out, double* ctrlat_out) {
+                                             double* area_out, double* ctrlon_out, double* ctrlat_out,
+                                             const double* T = nullptr) {
+  auto sincos_ = [&](double a, double* s, double* c) {
+    if (LEAN) ref_trig_site(a, false, s, c, T); else ref_sincos(a, s, c);
+  };
+  auto sin_half_ = [&](double a) { return LEAN ? ref_sin_small(a) : ref_sin(a); };
+  auto sin_own_ = [&](double a) {
+    if (!LEAN) return ref_sin(a);
+    double s, c;
+    ref_trig_site(a, true, &s, &c, T);
+    return s;
+  };
   double aacc = 0.0, lonacc = 0.0, latacc = 0.0;
   double xi = 0.0, yi = 0.0;
   if (n > 0) { xi = p.X(0); yi = p.Y(0); }
   const double x0 = xi, y0 = yi;
   double si = 0.0, ci = 0.0;
-  if (ORDER == 2 && n > 0) ref_sincos(yi, &si, &ci);
+  if (ORDER == 2 && n > 0) sincos_(yi, &si, &ci);
   int nloop = n;
   if (WARP) {
 #if defined(__CUDA_ARCH__)
@@ -232,7 +247,7 @@ __device__ __forceinline__ void poly_moments(const PolyView& p, int n, double cl
   for (int i = 0; i < nloop; ++i) {
     const bool act = !WARP || i < n;
     double xn = x0, yn = y0, sn = s0, cn = c0;
-    if (act && i + 1 < n) { xn = p.X(i + 1); yn = p.Y(i + 1); if (ORDER == 2) ref_sincos(yn, &sn, &cn); }
+    if (act && i + 1 < n) { xn = p.X(i + 1); yn = p.Y(i + 1); if (ORDER == 2) sincos_(yn, &sn, &cn); }
 #if defined(__CUDA_ARCH__)
     if (WARP) __syncwarp();
 #endif
@@ -249,19 +264,19 @@ __device__ __forceinline__ void poly_moments(const PolyView& p, int n, double cl
     const bool flat_lat = (fabs(dy) < kSmall);           // fabs(hdy) < SMALL_VALUE (create_xgrid.c:2114)
 
     double s_avg = 0.0, c_avg = 0.0;
-    if (act && moving) ref_sincos(avg, &s_avg, &c_avg);
+    if (act && moving) sincos_(avg, &s_avg, &c_avg);
 #if defined(__CUDA_ARCH__)
     if (WARP) __syncwarp();
 #endif
     double dat = 0.0;
-    if (act && ((!pole_edge && !flat_area) || (moving && !flat_lat))) dat = ref_sin(dy) / dy;
+    if (act && ((!pole_edge && !flat_area) || (moving && !flat_lat))) dat = sin_half_(dy) / dy;
 #if defined(__CUDA_ARCH__)
     if (WARP) __syncwarp();
 #endif
     const uint32_t hi = (uint32_t)(trig::bits(avg) >> 32) & 0x7fffffffu;
     const bool own_sin = act && !pole_edge && !(moving && hi < 0x3feb6000u);
     double sin_avg = s_avg;
-    if (own_sin) sin_avg = ref_sin(avg);
+    if (own_sin) sin_avg = sin_own_(avg);
 #if defined(__CUDA_ARCH__)
     if (WARP) __syncwarp();
 #endif

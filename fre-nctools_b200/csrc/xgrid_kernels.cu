@@ -480,8 +480,15 @@ void launch_candidates_single(const CellSet& src, const SrcMap& sm, const double
 // =============================================================================================
 // clip
 // =============================================================================================
+// Compile-time switches of the clip kernel, kept because each was measured on C768 -> 1/8 degree (scripts/clip_variants.py,
+// profiles/r01q_clip_variants.txt); every combination produces bit-identical results:
+//   XGB_CLIP_VARIANT bit 1 (2): rolled destination-edge loop                       3.78 -> 3.32 ms (order 2)   ON
+//                    bit 0 (1): one-site moments (poly_moments_site)               +0.33 ms                    off
+//                    bit 2 (4): sin/cos table in shared memory (with bit 0 or 6)   +0.06 ms                    off
+//                    bit 6 (64): lean trig sites inside poly_moments               +0.13 ms                    off
+//   XGB_CLIP_BLOCKS / XGB_CLIP_BLOCKS1: resident blocks per SM for order 2 / order 1: 5 / 6 (order 1: 2.32 -> 2.19 ms)
 #ifndef XGB_CLIP_VARIANT
-#define XGB_CLIP_VARIANT 0
+#define XGB_CLIP_VARIANT 2
 #endif
 #ifndef XGB_CLIP_THREADS
 #define XGB_CLIP_THREADS 128
@@ -490,7 +497,7 @@ void launch_candidates_single(const CellSet& src, const SrcMap& sm, const double
 #define XGB_CLIP_BLOCKS 5
 #endif
 #ifndef XGB_CLIP_BLOCKS1
-#define XGB_CLIP_BLOCKS1 XGB_CLIP_BLOCKS
+#define XGB_CLIP_BLOCKS1 6
 #endif
 constexpr int kClipThreads = XGB_CLIP_THREADS;
 constexpr int kFastCap = 8;       // shared-memory polygon capacity per thread (quad x quad)
@@ -699,8 +706,8 @@ clip_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const int
   double* by = bx + plane;
 
   double *rx = ax, *ry = ay;
-  int rstride = stride;
   int n_out = 0;
+  int rstride = stride;
   double loc[4 * kSlowCap];                                       // only touched on the slow path
   double ex[4] = {0.0, 0.0, 0.0, 0.0}, ey[4] = {0.0, 0.0, 0.0, 0.0};   // destination vertices as clip_2dx2d sees them
   if (valid) {
@@ -739,6 +746,8 @@ clip_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const int
     // warp hold polygons of similar size, and waiting for the slowest lane after every sin/cos costs more than it saves)
 #if (XGB_CLIP_VARIANT & 1)
     poly_moments_site<ORDER>(pv, n_out, s_xavg, T, &a, &xclon, &xclat);   // one trig site, rolled loops
+#elif (XGB_CLIP_VARIANT & 64)
+    poly_moments<ORDER, false, true>(pv, n_out, s_xavg, &a, &xclon, &xclat, T);   // lean trig sites, same bits
 #else
     poly_moments<ORDER>(pv, n_out, s_xavg, &a, &xclon, &xclat);  // poly_area :805, poly_ctrlon :1091, poly_ctrlat :1092
 #endif
