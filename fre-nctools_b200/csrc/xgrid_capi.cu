@@ -218,6 +218,19 @@ extern "C" int xgb_plan_set_dst(xgb_plan* p, int nx, int ny, const double* lon, 
     P.lev[l].box = b;
     b += n;
   }
+  // separable tile (regular lat-lon): 1-D row / column boxes for the candidate search; XGB_NO_RECT=1 keeps the pyramid walk
+  p->rect.valid = 0;
+  const char* no_rect = getenv("XGB_NO_RECT");
+  if (!(no_rect && no_rect[0] == '1')) {
+    if (p->rect_store.reserve((size_t)(2 * ny + 3 * nx) * sizeof(double) + 64) || p->rect_rows.reserve((size_t)ny + 64) ||
+        p->rect_invalid.reserve(64))
+      return 1;
+    launch_rect_setup(p->dst, nx, ny, (double*)p->rect_store.p, (unsigned char*)p->rect_rows.p, (int*)p->rect_invalid.p, &p->rect, p->st);
+    int invalid = 1;
+    CU_OK(cudaMemcpyAsync(&invalid, p->rect_invalid.p, sizeof(int), cudaMemcpyDeviceToHost, p->st));
+    CU_OK(cudaStreamSynchronize(p->st));
+    if (invalid) p->rect.valid = 0;
+  }
   p->have_dst = true;
   p->gc_dst_ready = false;
   return xgb_check_kernel_errors(p, false);
@@ -396,7 +409,7 @@ static long long generate_window(xgb_plan* p, int order, const SrcMap& sm, size_
     if (p->pairs.reserve(cap * sizeof(int2) + 16) || p->parea.reserve(cap * sizeof(double) + 16)) return -1;
     if (order == 2 && (p->pclon.reserve(cap * sizeof(double) + 16) || p->pclat.reserve(cap * sizeof(double) + 16))) return -1;
     cudaMemsetAsync(p->cnt.p, 0, (size_t)(ns + 1) * sizeof(uint32_t), p->st);
-    launch_candidates_single(p->src, sm, mask, p->pyr, p->dst, (uint32_t*)p->pair_off.p, (uint32_t*)p->pair_cnt.p,
+    launch_candidates_single(p->src, sm, mask, p->pyr, p->rect, p->dst, (uint32_t*)p->pair_off.p, (uint32_t*)p->pair_cnt.p,
                              (int2*)p->pairs.p, cap, (uint32_t*)p->cnt.p, hw, p->err_dev, p->st);
     launch_publish(p->total_host, &hw.ctl->total, 4, p->st);          // total (2 words), nheavy, npairs of the heavy path
     launch_publish(p->err_host, p->err_dev, 1, p->st);
@@ -453,14 +466,14 @@ static long long generate_window(xgb_plan* p, int order, const SrcMap& sm, size_
                  (const double*)p->pclat.p, (const uint32_t*)p->pair_off.p, (const uint32_t*)p->pair_cnt.p, (const uint32_t*)p->out_off.p,
                  (const TileDesc*)p->tiles_dev.p, (int)p->tiles.size(), sm, p->nx2,
                  (int*)p->t_in.p + base, (int*)p->i_in.p + base, (int*)p->j_in.p + base, (int*)p->i_out.p + base, (int*)p->j_out.p + base,
-                 (double*)p->area.p + base, (double*)p->clon.p + (order == 2 ? base : 0), (double*)p->clat.p + (order == 2 ? base : 0), p->st);
+                 (double*)p->area.p + base, (double*)p->clon.p + (order == 2 ? base : 0), (double*)p->clat.p + (order == 2 ? base : 0), &hw, p->st);
   if (order == 2)
     launch_order2_finalize(p->src, sm, (const uint32_t*)p->out_off.p, (const double*)p->area.p + base,
                            (const double*)p->clon.p + base, (const double*)p->clat.p + base, (double*)p->di.p + base,
                            (double*)p->dj.p + base, hw.list, &hw.ctl->nheavy, p->st);   // heavy_list / counter are free again
   cudaEventRecord(p->ev[5], p->st);
   if (sm.nwin > 1 && stream_cap == 0) {                       // exchange cells per window, for the callers' global offsets
-    for (int w = 1; w < sm.nwin; ++w) launch_publish(p->win_host + w, (const uint32_t*)p->out_off.p + sm.cum[w], 1, p->st);
+    launch_publish_windows(p->win_host, p->out_off.p, sm, p->st);
   }
   if (xgb_check_kernel_errors(p, false)) return -1;
   if (stream_cap == 0) {

@@ -68,6 +68,17 @@ enum : int {
 };
 
 // device-side control block and work buffers of the level-synchronous "heavy cell" candidate path
+// Separable destination tile (every regular lat-lon grid): the latitude range of a cell depends on its row only, the
+// longitude range and mean longitude on its column only.  Checked cell by cell, bit for bit, when the destination is set
+// (rect_* kernels); the candidate search then needs two 1-D searches instead of a walk of the 2-D pyramid.
+struct RectDst {
+  int valid;                       // 0: use the pyramid
+  int nx, ny;
+  const double *ymin, *ymax;       // [ny], non-decreasing
+  const double *xmin, *xmax, *xavg;   // [nx], strictly increasing by more than kRectMinStep
+  const unsigned char* row_ok;     // [ny] 0: some cell of the row departs from the column values (next to a pole): pyramid
+};
+
 struct HeavyCtl { unsigned long long total; unsigned nheavy; unsigned npairs; unsigned nitems[kMaxLevels]; };
 struct HeavyWork {
   HeavyCtl* ctl;
@@ -85,7 +96,7 @@ void launch_pyramid_level(const PyrLevel& child, Box* out, int nx, int ny, cudaS
 void launch_candidates_count(const CellSet& src, const SrcMap& sm, const double* mask,
                              const Pyramid& pyr, const CellSet& dst, uint32_t* cnt, const HeavyWork& hw, int* err, cudaStream_t st);
 void launch_candidates_single(const CellSet& src, const SrcMap& sm, const double* mask,
-                              const Pyramid& pyr, const CellSet& dst, uint32_t* pair_off, uint32_t* pair_cnt, int2* pairs,
+                              const Pyramid& pyr, const RectDst& rect, const CellSet& dst, uint32_t* pair_off, uint32_t* pair_cnt, int2* pairs,
                               unsigned long long pair_cap, uint32_t* cursor, const HeavyWork& hw, int* err, cudaStream_t st);
 void launch_clip(int order, const CellSet& src, const CellSet& dst, const double* mask,
                  const int2* pairs, unsigned long long npairs, const SrcMap& sm,
@@ -95,12 +106,14 @@ void launch_scatter(int order, const int2* pairs, unsigned long long npairs,
                     const uint32_t* pair_off, const uint32_t* pair_cnt, const uint32_t* out_off,
                     const TileDesc* tiles, int ntiles, const SrcMap& sm, int nx2,
                     int* t_in, int* i_in, int* j_in, int* i_out, int* j_out,
-                    double* area, double* clon, double* clat, cudaStream_t st);
+                    double* area, double* clon, double* clat, const HeavyWork* hw, cudaStream_t st);
 void launch_order2_finalize(const CellSet& src, const SrcMap& sm, const uint32_t* out_off,
                             const double* area, const double* clon, const double* clat,
                             double* di, double* dj, int* long_list /* ns ints */, unsigned* nlong, cudaStream_t st);
 // nwords 32-bit words from device memory to pinned host memory, by a kernel (not the copy engine)
 void launch_publish(void* host_dst, const void* dev_src, int nwords, cudaStream_t st);
+void launch_rect_setup(const CellSet& dst, int nx, int ny, double* store, unsigned char* row_ok, int* invalid, RectDst* out, cudaStream_t st);
+void launch_publish_windows(void* host_dst, const void* out_off, const SrcMap& sm, cudaStream_t st);
 // exclusive prefix sum of n uint32 counts; out has n+1 entries (out[n] = total, must fit 32 bits);
 // the 64-bit total is also written to *total_dev.  tmp must hold scan_tmp_bytes(n).
 size_t scan_tmp_bytes(long long n);

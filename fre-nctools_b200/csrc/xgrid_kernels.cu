@@ -121,7 +121,10 @@ void launch_pyramid_level(const PyrLevel& child, Box* out, int nx, int ny, cudaS
 // =============================================================================================
 constexpr int kStack = 3 * kMaxLevels + 8;
 constexpr uint32_t kHeavyPairs = 128;     // a source cell with more candidates than this ...
-constexpr int kHeavySteps = 768;          // ... or more node expansions is handed to the level-synchronous path
+#ifndef XGB_HEAVY_STEPS
+#define XGB_HEAVY_STEPS 128
+#endif
+constexpr int kHeavySteps = XGB_HEAVY_STEPS;          // ... or more node expansions is handed to the level-synchronous path
 
 struct SrcBox { double ymin, ymax, xmin, xmax, xavg; };
 
@@ -243,16 +246,82 @@ candidate_kernel(CellSet src, SrcMap sm, const double* __restrict__ mask,
   }
 }
 
+// ---- separable destination tile (RectDst) ----------------------------------------------------------------------
+// Every box test of the reference (create_xgrid.c:777-801) is "latitude ranges overlap" AND "longitude ranges overlap after
+// the 2*pi shift chosen from the mean longitudes".  When the destination's latitude range depends on the row only and its
+// longitude range / mean longitude on the column only — checked bit for bit over all cells below — the candidates of a
+// source cell are (rows j0..j1) x (columns passing the exact longitude test), found with searches in five 1-D arrays that
+// stay in L1 instead of ~60 dependent box loads from L2 per source cell.
+constexpr double kRectMinStep = 1.e-9;    // columns must be further apart than any rounding of (bound +- 2*pi)
+
+__global__ void rect_extract_kernel(CellSet dst, int nx, int ny, double* ymin, double* ymax, double* xmin, double* xmax,
+                                    double* xavg, unsigned char* row_ok)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < ny) { const Box b = load_box(dst.box + (long long)t * nx); ymin[t] = b.ymin; ymax[t] = b.ymax; row_ok[t] = 1; }
+  if (t < nx) {
+    const long long c = (long long)(ny / 2) * nx + t;
+    const Box b = load_box(dst.box + c);
+    xmin[t] = b.xmin; xmax[t] = b.xmax; xavg[t] = dst.xavg[c];
+  }
+}
+
+__global__ void rect_check_kernel(CellSet dst, int nx, int ny, const double* __restrict__ ymin, const double* __restrict__ ymax,
+                                  const double* __restrict__ xmin, const double* __restrict__ xmax, const double* __restrict__ xavg,
+                                  unsigned char* row_ok, int* invalid)
+{
+  const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (c >= (long long)nx * ny) return;
+  const int i = (int)(c % nx), j = (int)(c / nx);
+  const Box b = load_box(dst.box + c);
+  if (b.ymin != ymin[j] || b.ymax != ymax[j]) *invalid = 1;
+  if (b.xmin != xmin[i] || b.xmax != xmax[i] || dst.xavg[c] != xavg[i]) row_ok[j] = 0;
+  if (j == 0 && i + 1 < nx)
+    if (!(xmin[i + 1] - xmin[i] > kRectMinStep) || !(xmax[i + 1] - xmax[i] > kRectMinStep) || !(xavg[i + 1] > xavg[i])) *invalid = 1;
+  if (i == 0 && j + 1 < ny)
+    if (!(ymin[j + 1] >= ymin[j]) || !(ymax[j + 1] >= ymax[j])) *invalid = 1;
+}
+
+// store: 2*ny + 3*nx doubles.  *out is filled on the host; out->valid still has to be cleared when *invalid comes back set.
+void launch_rect_setup(const CellSet& dst, int nx, int ny, double* store, unsigned char* row_ok, int* invalid, RectDst* out, cudaStream_t st)
+{
+  double* ymin = store; double* ymax = ymin + ny; double* xmin = ymax + ny; double* xmax = xmin + nx; double* xavg = xmax + nx;
+  cudaMemsetAsync(invalid, 0, sizeof(int), st);
+  const int m = nx > ny ? nx : ny;
+  g_launches += 2;
+  rect_extract_kernel<<<(m + 127) / 128, 128, 0, st>>>(dst, nx, ny, ymin, ymax, xmin, xmax, xavg, row_ok);
+  const long long nc = (long long)nx * ny;
+  rect_check_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(dst, nx, ny, ymin, ymax, xmin, xmax, xavg, row_ok, invalid);
+  *out = RectDst{1, nx, ny, ymin, ymax, xmin, xmax, xavg, row_ok};
+}
+
+__device__ __forceinline__ int first_greater(const double* __restrict__ a, int n, double v)   // first k with a[k] > v, n if none
+{
+  int lo = 0, hi = n;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] > v) hi = mid; else lo = mid + 1; }
+  return lo;
+}
+__device__ __forceinline__ int last_less(const double* __restrict__ a, int n, double v)       // last k with a[k] < v, -1 if none
+{
+  int lo = 0, hi = n;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < v) lo = mid + 1; else hi = mid; }
+  return lo - 1;
+}
+
 // Single pass: the walk buffers a cell's candidates (a handful) in thread-local storage, the warp reserves space for all
 // its cells with one atomicAdd and writes them out; no second walk, no prefix sum.  pair_off[t] / pair_cnt[t] describe
 // the cell's segment (segments of different cells are in reservation order, which only affects locality).  Cells with
 // more than kSingleMax candidates, or too many node expansions, take the heavy path exactly as in the count pass.
 // Writes are dropped when the pair buffer (cap entries) is too small; the host sees ctl->total > cap and retries.
-constexpr int kSingleMax = 96;   // thread-local buffer; beyond it the cell goes to the heavy path
+#ifndef XGB_SINGLE_MAX
+#define XGB_SINGLE_MAX 32
+#endif
+constexpr int kSingleMax = XGB_SINGLE_MAX;   // thread-local buffer; beyond it the cell goes to the heavy path
 
+template <bool RECT>
 __global__ void __launch_bounds__(128)
 candidate_single_kernel(CellSet src, SrcMap sm, const double* __restrict__ mask,
-                        Pyramid pyr, CellSet dst, uint32_t* __restrict__ pair_off, uint32_t* __restrict__ pair_cnt,
+                        Pyramid pyr, RectDst R, CellSet dst, uint32_t* __restrict__ pair_off, uint32_t* __restrict__ pair_cnt,
                         int2* __restrict__ pairs, unsigned long long cap,
                         unsigned char* __restrict__ heavy_flag, int* __restrict__ heavy_list, HeavyCtl* ctl, int* err)
 {
@@ -262,7 +331,47 @@ candidate_single_kernel(CellSet src, SrcMap sm, const double* __restrict__ mask,
   int buf[kSingleMax];
   uint32_t n = 0;
   bool heavy = false;
-  if (valid && (mask == nullptr || mask[s] > kMaskThresh)) {
+  if (RECT && valid && (mask == nullptr || mask[s] > kMaskThresh)) {
+    const SrcBox sb = load_src_box(src, s);
+    const int j0 = first_greater(R.ymax, R.ny, sb.ymin);         // rows with ymax <= ymin(source) fail the latitude test
+    const int j1 = last_less(R.ymin, R.ny, sb.ymax);             // rows with ymin >= ymax(source) fail it
+    if (j0 <= j1) {
+      if (j1 - j0 + 1 > kSingleMax) heavy = true;
+      for (int j = j0; j <= j1 && !heavy; ++j) if (!R.row_ok[j]) heavy = true;
+      if (!heavy) {
+        // column brackets for the three shifts the reference can apply, each widened by one column: the exact test below
+        // decides, the brackets only have to contain every column that passes (columns are > 1e-9 apart, roundings 1e-15)
+        int a[3], b[3], m = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double sh = (k == 0) ? 0.0 : (k == 1 ? kTwoPi : -kTwoPi);     // added to the destination longitudes
+          if (k == 1 && !(sb.xmax - kTwoPi > R.xmin[0] - 1.e-6)) continue;
+          if (k == 2 && !(sb.xmin + kTwoPi < R.xmax[R.nx - 1] + 1.e-6)) continue;
+          int lo = first_greater(R.xmax, R.nx, sb.xmin - sh) - 1, hi = last_less(R.xmin, R.nx, sb.xmax - sh) + 1;
+          if (lo < 0) lo = 0;
+          if (hi > R.nx - 1) hi = R.nx - 1;
+          if (lo <= hi) { a[m] = lo; b[m] = hi; ++m; }
+        }
+        for (int u = 0; u < m; ++u)                              // disjoint in ascending order
+          for (int w = u + 1; w < m; ++w)
+            if (a[w] < a[u]) { const int ta = a[u], tb = b[u]; a[u] = a[w]; b[u] = b[w]; a[w] = ta; b[w] = tb; }
+        int done = -1;                                           // last column already examined
+        for (int u = 0; u < m && !heavy; ++u) {
+          for (int i = (a[u] > done + 1) ? a[u] : done + 1; i <= b[u]; ++i) {
+            double lo = R.xmin[i], hi = R.xmax[i];
+            const double dx = R.xavg[i] - sb.xavg;               // create_xgrid.c:786-801, as in leaf_hit
+            if (dx < -kPi)     { lo += kTwoPi; hi += kTwoPi; }
+            else if (dx > kPi) { lo -= kTwoPi; hi -= kTwoPi; }
+            if (lo >= sb.xmax || hi <= sb.xmin) continue;
+            for (int j = j0; j <= j1; ++j) { if (n < (uint32_t)kSingleMax) buf[n] = j * R.nx + i; ++n; }
+            if (n > (uint32_t)kSingleMax) { heavy = true; break; }
+          }
+          if (b[u] > done) done = b[u];
+        }
+      }
+    }
+  }
+  if (!RECT && valid && (mask == nullptr || mask[s] > kMaskThresh)) {
     const SrcBox sb = load_src_box(src, s);
     unsigned long long stack[kStack];
     int sp = 0, steps = 0;
@@ -452,7 +561,7 @@ void launch_candidates_count(const CellSet& src, const SrcMap& sm, const double*
 // single pass: pairs, pair_off, pair_cnt of every source cell of the window; ctl->total = number of pairs.
 // cursor: ns zeroed uint32 (left dirty).  Pairs beyond pair_cap are dropped (the caller compares ctl->total with it).
 void launch_candidates_single(const CellSet& src, const SrcMap& sm, const double* mask,
-                              const Pyramid& pyr, const CellSet& dst, uint32_t* pair_off, uint32_t* pair_cnt, int2* pairs,
+                              const Pyramid& pyr, const RectDst& rect, const CellSet& dst, uint32_t* pair_off, uint32_t* pair_cnt, int2* pairs,
                               unsigned long long pair_cap, uint32_t* cursor, const HeavyWork& hw, int* err, cudaStream_t st)
 {
   const long long ns = sm.total();
@@ -460,8 +569,12 @@ void launch_candidates_single(const CellSet& src, const SrcMap& sm, const double
   const unsigned blocks = (unsigned)((ns + 127) / 128);
   cudaMemsetAsync(hw.ctl, 0, sizeof(HeavyCtl), st);
   ++g_launches;
-  candidate_single_kernel<<<blocks, 128, 0, st>>>(src, sm, mask, pyr, dst, pair_off, pair_cnt, pairs, pair_cap,
-                                                  hw.flag, hw.list, hw.ctl, err);
+  if (rect.valid && pyr.nlev > 1)
+    candidate_single_kernel<true><<<blocks, 128, 0, st>>>(src, sm, mask, pyr, rect, dst, pair_off, pair_cnt, pairs, pair_cap,
+                                                          hw.flag, hw.list, hw.ctl, err);
+  else
+    candidate_single_kernel<false><<<blocks, 128, 0, st>>>(src, sm, mask, pyr, rect, dst, pair_off, pair_cnt, pairs, pair_cap,
+                                                           hw.flag, hw.list, hw.ctl, err);
   if (pyr.nlev > 1) {
     const int top = pyr.nlev - 1;
     ++g_launches;
@@ -792,13 +905,15 @@ scatter_kernel(const int2* __restrict__ pairs, unsigned long long npairs,
                const TileDesc* __restrict__ tiles, int ntiles, SrcMap sm, int nx2,
                int* __restrict__ t_in, int* __restrict__ i_in, int* __restrict__ j_in,
                int* __restrict__ i_out, int* __restrict__ j_out,
-               double* __restrict__ area, double* __restrict__ clon, double* __restrict__ clat)
+               double* __restrict__ area, double* __restrict__ clon, double* __restrict__ clat,
+               const unsigned char* __restrict__ heavy_flag)
 {
   const unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
   if (p >= npairs) return;
   const double a = parea[p];
   if (!(a > 0.0)) return;
   const int2 pr = pairs[p];
+  if (heavy_flag && heavy_flag[pr.x]) return;                    // pole caps, coarse-on-fine: scatter_long_kernel
   // rank among the accepted pairs of the same source cell by ascending destination index:
   // the reference visits destination cells in ascending ij for each source cell (create_xgrid.c:769)
   uint32_t rank = 0;
@@ -818,23 +933,112 @@ scatter_kernel(const int2* __restrict__ pairs, unsigned long long npairs,
   if (ORDER == 2) { clon[o] = pclon[p]; clat[o] = pclat[p]; }
 }
 
+// Source cells the candidate search handed to the heavy path (a pole cap holds thousands of pairs): the rank loop above is
+// quadratic in the cell's pair count and ran on a handful of blocks (0.2 ms extra on the rank that owns a pole).  One block
+// per such cell: the accepted destination indices go into a shared-memory bitmap over the cell's index range, an exclusive
+// prefix popcount gives every pair its rank in O(n + range / 32).  Ranges beyond the bitmap fall back to the quadratic loop.
+constexpr int kRankWords = 6080;          // 2 x 23.75 KB of shared memory: destination index ranges up to 194 560 cells
+
+template <int ORDER>
+__global__ void __launch_bounds__(256)
+scatter_long_kernel(const int2* __restrict__ pairs, const double* __restrict__ parea, const double* __restrict__ pclon,
+                    const double* __restrict__ pclat, const uint32_t* __restrict__ pair_off, const uint32_t* __restrict__ pair_cnt,
+                    const uint32_t* __restrict__ out_off, const TileDesc* __restrict__ tiles, int ntiles, SrcMap sm, int nx2,
+                    int* __restrict__ t_in, int* __restrict__ i_in, int* __restrict__ j_in, int* __restrict__ i_out,
+                    int* __restrict__ j_out, double* __restrict__ area, double* __restrict__ clon, double* __restrict__ clat,
+                    const int* __restrict__ heavy_list, const unsigned* __restrict__ nheavy)
+{
+  __shared__ unsigned bits[kRankWords];
+  __shared__ unsigned pre[kRankWords];
+  __shared__ unsigned wsum[8];
+  __shared__ int s_lo, s_hi;
+  __shared__ unsigned s_carry;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned nh = *nheavy;
+  for (unsigned h = blockIdx.x; h < nh; h += gridDim.x) {
+    const int t = heavy_list[h];
+    const uint32_t qb = pair_off[t], n = pair_cnt[t];
+    if (threadIdx.x == 0) { s_lo = 0x7fffffff; s_hi = -1; s_carry = 0; }
+    __syncthreads();
+    int lo = 0x7fffffff, hi = -1;
+    for (uint32_t q = threadIdx.x; q < n; q += blockDim.x)
+      if (parea[qb + q] > 0.0) { const int d = pairs[qb + q].y; lo = min(lo, d); hi = max(hi, d); }
+    for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+    if (lane == 0 && hi >= 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
+    __syncthreads();
+    const int dlo = s_lo & ~31, dhi = s_hi;
+    if (dhi >= 0) {                                              // uniform across the block
+      const long long s = sm.cell(t);
+      const int tl = find_tile(tiles, ntiles, s);
+      const long long c = s - tiles[tl].cell_off;
+      const int ci = (int)(c % tiles[tl].nx), cj = (int)(c / tiles[tl].nx);
+      const size_t obase = out_off[t];
+      const unsigned words = (unsigned)((dhi - dlo) >> 5) + 1u;
+      const bool bitmap = words <= (unsigned)kRankWords;
+      if (bitmap) {
+        for (unsigned w = threadIdx.x; w < words; w += blockDim.x) bits[w] = 0u;
+        __syncthreads();
+        for (uint32_t q = threadIdx.x; q < n; q += blockDim.x)
+          if (parea[qb + q] > 0.0) { const unsigned k = (unsigned)(pairs[qb + q].y - dlo); atomicOr(&bits[k >> 5], 1u << (k & 31u)); }
+        __syncthreads();
+        for (unsigned w0 = 0; w0 < words; w0 += blockDim.x) {   // exclusive prefix popcount, blockDim words at a time
+          const unsigned w = w0 + threadIdx.x;
+          const unsigned cnt = (w < words) ? (unsigned)__popc(bits[w]) : 0u;
+          unsigned incl = cnt;
+          for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+          if (lane == 31) wsum[wid] = incl;
+          __syncthreads();
+          unsigned before = s_carry;
+          for (int k = 0; k < wid; ++k) before += wsum[k];
+          if (w < words) pre[w] = before + incl - cnt;
+          __syncthreads();
+          if (threadIdx.x == blockDim.x - 1) s_carry = before + incl;
+          __syncthreads();
+        }
+      }
+      for (uint32_t q = threadIdx.x; q < n; q += blockDim.x) {
+        const double a = parea[qb + q];
+        if (!(a > 0.0)) continue;
+        const int d = pairs[qb + q].y;
+        uint32_t rank = 0;
+        if (bitmap) { const unsigned k = (unsigned)(d - dlo); rank = pre[k >> 5] + (unsigned)__popc(bits[k >> 5] & ((1u << (k & 31u)) - 1u)); }
+        else for (uint32_t r = 0; r < n; ++r) if (parea[qb + r] > 0.0 && pairs[qb + r].y < d) ++rank;
+        const size_t o = obase + rank;
+        t_in[o] = tl; i_in[o] = ci; j_in[o] = cj;
+        i_out[o] = d % nx2; j_out[o] = d / nx2;
+        area[o] = a;
+        if (ORDER == 2) { clon[o] = pclon[qb + q]; clat[o] = pclat[qb + q]; }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 void launch_scatter(int order, const int2* pairs, unsigned long long npairs,
                     const double* parea, const double* pclon, const double* pclat,
                     const uint32_t* pair_off, const uint32_t* pair_cnt, const uint32_t* out_off,
                     const TileDesc* tiles, int ntiles, const SrcMap& sm, int nx2,
                     int* t_in, int* i_in, int* j_in, int* i_out, int* j_out,
-                    double* area, double* clon, double* clat, cudaStream_t st)
+                    double* area, double* clon, double* clat, const HeavyWork* hw, cudaStream_t st)
 {
   if (npairs == 0) return;
   const int threads = 256;
   const unsigned blocks = (unsigned)((npairs + threads - 1) / threads);
-  ++g_launches;
-  if (order == 2)
+  const unsigned char* flag = hw ? hw->flag : nullptr;            // no heavy path (great-circle generator): one kernel
+  g_launches += hw ? 2 : 1;
+  if (order == 2) {
     scatter_kernel<2><<<blocks, threads, 0, st>>>(pairs, npairs, parea, pclon, pclat, pair_off, pair_cnt, out_off, tiles, ntiles, sm, nx2,
-                                                  t_in, i_in, j_in, i_out, j_out, area, clon, clat);
-  else
+                                                  t_in, i_in, j_in, i_out, j_out, area, clon, clat, flag);
+    if (hw)
+      scatter_long_kernel<2><<<148 * 2, 256, 0, st>>>(pairs, parea, pclon, pclat, pair_off, pair_cnt, out_off, tiles, ntiles, sm, nx2,
+                                                      t_in, i_in, j_in, i_out, j_out, area, clon, clat, hw->list, &hw->ctl->nheavy);
+  } else {
     scatter_kernel<1><<<blocks, threads, 0, st>>>(pairs, npairs, parea, pclon, pclat, pair_off, pair_cnt, out_off, tiles, ntiles, sm, nx2,
-                                                  t_in, i_in, j_in, i_out, j_out, area, clon, clat);
+                                                  t_in, i_in, j_in, i_out, j_out, area, clon, clat, flag);
+    if (hw)
+      scatter_long_kernel<1><<<148 * 2, 256, 0, st>>>(pairs, parea, pclon, pclat, pair_off, pair_cnt, out_off, tiles, ntiles, sm, nx2,
+                                                      t_in, i_in, j_in, i_out, j_out, area, clon, clat, hw->list, &hw->ctl->nheavy);
+  }
 }
 
 // =============================================================================================
@@ -1087,6 +1291,19 @@ __global__ void publish_kernel(unsigned* __restrict__ host_dst, const unsigned* 
 {
   for (int k = threadIdx.x; k < nwords; k += blockDim.x) host_dst[k] = dev_src[k];
   __threadfence_system();
+}
+
+// out_off at the first cell of every window but the first, in one launch (the per-window exchange-cell counts follow)
+__global__ void publish_windows_kernel(unsigned* __restrict__ host_dst, const unsigned* __restrict__ out_off, SrcMap sm)
+{
+  for (int w = 1 + threadIdx.x; w < sm.nwin; w += blockDim.x) host_dst[w] = out_off[sm.cum[w]];
+  __threadfence_system();
+}
+
+void launch_publish_windows(void* host_dst, const void* out_off, const SrcMap& sm, cudaStream_t st)
+{
+  ++g_launches;
+  publish_windows_kernel<<<1, 64, 0, st>>>((unsigned*)host_dst, (const unsigned*)out_off, sm);
 }
 
 void launch_publish(void* host_dst, const void* dev_src, int nwords, cudaStream_t st)

@@ -28,6 +28,8 @@ struct xgb_plan {
   DevBuf dst_lon, dst_lat, dst_store, pyr_store;
   xgb::CellSet dst{};
   xgb::Pyramid pyr{};
+  DevBuf rect_store, rect_rows, rect_invalid;  // separable destination tile: 1-D row / column boxes (xgrid_internal.h RectDst)
+  xgb::RectDst rect{};
 
   // source mosaic
   bool have_src = false, has_mask = false;

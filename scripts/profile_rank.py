@@ -19,7 +19,7 @@ lon2, lat2 = pkg.latlon_grid(2880, 1440)
 plan = pkg.XgridPlan(0)
 plan.set_dst(lon2, lat2)
 plan.set_src(lonc, latc)
-WPR = 8
+WPR = int(os.environ.get('XGB_WPR', '8'))
 bounds = plan.partition(world * WPR)
 wins = [(bounds[w], bounds[w + 1]) for w in range(rank, world * WPR, world)]
 plan.set_src_windows(wins)
@@ -36,5 +36,5 @@ with torch.cuda.stream(st):
     e1.record()
 torch.cuda.synchronize()
 _, ph, ngen = plan.phase_ms()
-print(json.dumps({"rank": rank, "world": world, "nxgrid": int(n), "ms_per_step": e0.elapsed_time(e1) / steps,
+print(json.dumps({"rank": rank, "world": world, "wpr": WPR, "nxgrid": int(n), "ms_per_step": e0.elapsed_time(e1) / steps,
                   "phase_ms": {k: round(v / max(ngen, 1), 4) for k, v in ph.items()}}))
