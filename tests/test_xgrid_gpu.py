@@ -3,6 +3,7 @@
 Bar (BASELINE.json north_star): integer cell lists bit-exact, xgrid_area within 1e-12 relative;
 tile1_distance (a difference of near-equal centroids) within 1e-11 rad absolute.
 """
+import os
 import numpy as np
 import pytest
 
@@ -360,3 +361,47 @@ def test_interleaved_windows_reassemble_to_serial_list(pkg):
     for k in want:
         assert np.array_equal(bufs[k][:n], want[k]), k
     plan.close()
+
+
+def _generate(pkg, lonc, latc, lon2, lat2, order, no_rect):
+    os.environ["XGB_NO_RECT"] = "1" if no_rect else "0"       # read by xgb_plan_set_dst
+    try:
+        plan = pkg.XgridPlan(0)
+        plan.set_dst(lon2, lat2)
+        plan.set_src(lonc, latc)
+        n = plan.generate(pkg.CONSERVE_ORDER2 if order == 2 else pkg.CONSERVE_ORDER1)
+        out = plan.result_host()
+        out["nxgrid"] = n
+        plan.close()
+        return out
+    finally:
+        os.environ.pop("XGB_NO_RECT", None)
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_separable_destination_search_equals_pyramid_walk_and_oracle(pkg, order):
+    """the 1-D row / column candidate search used for separable (lat-lon) destinations against the pyramid walk and the oracle:
+    global grids, a window of negative longitudes, a window that wraps past 360 degrees (the 2*pi shifts of create_xgrid.c:786-
+    801), unevenly spaced rows and columns, a coarse source on a fine destination (heavy cells) and a destination that is not
+    separable at all (one displaced vertex: the check must fall back to the pyramid)"""
+    lonc, latc = pkg.cubed_sphere_grid(24)
+    rng = np.random.default_rng(5)
+    cases = [pkg.latlon_grid(144, 72), pkg.latlon_grid(90, 40, -180.0, 180.0, -80.0, 80.0), pkg.latlon_grid(120, 30, 100.0, 460.0, -30.0, 60.0),
+             pkg.latlon_grid(720, 360)]
+    xs = np.sort(rng.uniform(0.0, 2 * np.pi, 100)); ys = np.sort(rng.uniform(-0.5 * np.pi, 0.5 * np.pi, 50))
+    xs[0], xs[-1], ys[0], ys[-1] = 0.0, 2 * np.pi, -0.5 * np.pi, 0.5 * np.pi
+    cases.append(tuple(np.ascontiguousarray(a) for a in np.meshgrid(xs, ys)))
+    bent = [a.copy() for a in pkg.latlon_grid(72, 36)]
+    bent[0][10, 20] += 1e-3; bent[1][10, 20] += 2e-3
+    cases.append(tuple(bent))
+    for k, (lon2, lat2) in enumerate(cases):
+        a = _generate(pkg, lonc, latc, lon2, lat2, order, no_rect=False)
+        b = _generate(pkg, lonc, latc, lon2, lat2, order, no_rect=True)
+        assert a["nxgrid"] == b["nxgrid"] and a["nxgrid"] > 0, k
+        for key in a:
+            if key != "nxgrid":
+                assert np.array_equal(a[key], b[key]), (k, key)
+        if k in (1, 2, 4):
+            want = xgtest.oracle_setup(lonc, latc, lon2, lat2, xgtest.ORDER2 if order == 2 else xgtest.ORDER1)
+            sc = xgtest.parent_scale(want, lonc, latc, lon2, lat2)
+            xgtest.assert_xgrid_equal(a, want, order, area_tol=1e-12, dist_atol=1e-9, scale=sc)
