@@ -308,6 +308,40 @@ __device__ __forceinline__ int last_less(const double* __restrict__ a, int n, do
   return lo - 1;
 }
 
+// Column brackets of a source box for the three 2*pi shifts the reference can apply (create_xgrid.c:786-801), each widened
+// by one column, sorted by first column and made disjoint: the exact test (rect_column_hit) decides, the brackets only have
+// to contain every column that passes (columns are > 1e-9 apart, the roundings of bound +- 2*pi are 1e-15).
+__device__ __forceinline__ int rect_column_brackets(const RectDst& R, const SrcBox& sb, int* a, int* b)
+{
+  int m = 0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double sh = (k == 0) ? 0.0 : (k == 1 ? kTwoPi : -kTwoPi);     // added to the destination longitudes
+    if (k == 1 && !(sb.xmax - kTwoPi > R.xmin[0] - 1.e-6)) continue;
+    if (k == 2 && !(sb.xmin + kTwoPi < R.xmax[R.nx - 1] + 1.e-6)) continue;
+    int lo = first_greater(R.xmax, R.nx, sb.xmin - sh) - 1, hi = last_less(R.xmin, R.nx, sb.xmax - sh) + 1;
+    if (lo < 0) lo = 0;
+    if (hi > R.nx - 1) hi = R.nx - 1;
+    if (lo <= hi) { a[m] = lo; b[m] = hi; ++m; }
+  }
+  for (int u = 0; u < m; ++u)
+    for (int w = u + 1; w < m; ++w)
+      if (a[w] < a[u]) { const int ta = a[u], tb = b[u]; a[u] = a[w]; b[u] = b[w]; a[w] = ta; b[w] = tb; }
+  int done = -1;
+  for (int u = 0; u < m; ++u) { if (a[u] <= done) a[u] = done + 1; if (b[u] > done) done = b[u]; }
+  return m;
+}
+
+// the longitude half of leaf_hit on the column arrays
+__device__ __forceinline__ bool rect_column_hit(const RectDst& R, int i, const SrcBox& sb)
+{
+  double lo = R.xmin[i], hi = R.xmax[i];
+  const double dx = R.xavg[i] - sb.xavg;
+  if (dx < -kPi)     { lo += kTwoPi; hi += kTwoPi; }
+  else if (dx > kPi) { lo -= kTwoPi; hi -= kTwoPi; }
+  return !(lo >= sb.xmax || hi <= sb.xmin);
+}
+
 // Single pass: the walk buffers a cell's candidates (a handful) in thread-local storage, the warp reserves space for all
 // its cells with one atomicAdd and writes them out; no second walk, no prefix sum.  pair_off[t] / pair_cnt[t] describe
 // the cell's segment (segments of different cells are in reservation order, which only affects locality).  Cells with
@@ -339,35 +373,14 @@ candidate_single_kernel(CellSet src, SrcMap sm, const double* __restrict__ mask,
       if (j1 - j0 + 1 > kSingleMax) heavy = true;
       for (int j = j0; j <= j1 && !heavy; ++j) if (!R.row_ok[j]) heavy = true;
       if (!heavy) {
-        // column brackets for the three shifts the reference can apply, each widened by one column: the exact test below
-        // decides, the brackets only have to contain every column that passes (columns are > 1e-9 apart, roundings 1e-15)
-        int a[3], b[3], m = 0;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const double sh = (k == 0) ? 0.0 : (k == 1 ? kTwoPi : -kTwoPi);     // added to the destination longitudes
-          if (k == 1 && !(sb.xmax - kTwoPi > R.xmin[0] - 1.e-6)) continue;
-          if (k == 2 && !(sb.xmin + kTwoPi < R.xmax[R.nx - 1] + 1.e-6)) continue;
-          int lo = first_greater(R.xmax, R.nx, sb.xmin - sh) - 1, hi = last_less(R.xmin, R.nx, sb.xmax - sh) + 1;
-          if (lo < 0) lo = 0;
-          if (hi > R.nx - 1) hi = R.nx - 1;
-          if (lo <= hi) { a[m] = lo; b[m] = hi; ++m; }
-        }
-        for (int u = 0; u < m; ++u)                              // disjoint in ascending order
-          for (int w = u + 1; w < m; ++w)
-            if (a[w] < a[u]) { const int ta = a[u], tb = b[u]; a[u] = a[w]; b[u] = b[w]; a[w] = ta; b[w] = tb; }
-        int done = -1;                                           // last column already examined
-        for (int u = 0; u < m && !heavy; ++u) {
-          for (int i = (a[u] > done + 1) ? a[u] : done + 1; i <= b[u]; ++i) {
-            double lo = R.xmin[i], hi = R.xmax[i];
-            const double dx = R.xavg[i] - sb.xavg;               // create_xgrid.c:786-801, as in leaf_hit
-            if (dx < -kPi)     { lo += kTwoPi; hi += kTwoPi; }
-            else if (dx > kPi) { lo -= kTwoPi; hi -= kTwoPi; }
-            if (lo >= sb.xmax || hi <= sb.xmin) continue;
+        int a[3], b[3];
+        const int m = rect_column_brackets(R, sb, a, b);
+        for (int u = 0; u < m && !heavy; ++u)
+          for (int i = a[u]; i <= b[u]; ++i) {
+            if (!rect_column_hit(R, i, sb)) continue;
             for (int j = j0; j <= j1; ++j) { if (n < (uint32_t)kSingleMax) buf[n] = j * R.nx + i; ++n; }
             if (n > (uint32_t)kSingleMax) { heavy = true; break; }
           }
-          if (b[u] > done) done = b[u];
-        }
       }
     }
   }
@@ -534,6 +547,74 @@ heavy_fill_kernel(HeavyCtl* ctl, const int2* __restrict__ hpairs, const uint32_t
   }
 }
 
+// Heavy source cells on a separable destination, one warp each: the candidate set is (regular rows j0..j1) x (columns
+// passing the exact longitude test) plus, for the rows that opted out of the column arrays, every cell passing leaf_hit.
+// Counted, reserved with one atomicAdd and written by the same warp: one launch instead of the level-synchronous pyramid
+// expansion (seed + one launch per level + reserve + fill).  The order of a cell's pairs is irrelevant (scatter ranks them).
+__global__ void __launch_bounds__(256)
+heavy_rect_kernel(CellSet src, SrcMap sm, RectDst R, CellSet dst, const int* __restrict__ heavy_list, HeavyCtl* ctl,
+                  uint32_t* __restrict__ pair_off, uint32_t* __restrict__ pair_cnt, int2* __restrict__ pairs,
+                  unsigned long long pair_cap)
+{
+  const int lane = threadIdx.x & 31;
+  const unsigned below = (1u << lane) - 1u;
+  const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+  const unsigned nh = ctl->nheavy;
+  for (unsigned h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; h < nh; h += nwarps) {
+    const int t = heavy_list[h];
+    const SrcBox sb = load_src_box(src, sm.cell(t));
+    const int j0 = first_greater(R.ymax, R.ny, sb.ymin), j1 = last_less(R.ymin, R.ny, sb.ymax);
+    int a[3], b[3];
+    const int m = (j0 <= j1) ? rect_column_brackets(R, sb, a, b) : 0;
+    unsigned nreg = 0;
+    for (int j = j0 + lane; j <= j1; j += 32) nreg += R.row_ok[j] ? 1u : 0u;
+    for (int o = 16; o > 0; o >>= 1) nreg += __shfl_xor_sync(0xffffffffu, nreg, o);
+    const bool irregular = (j0 <= j1) && nreg != (unsigned)(j1 - j0 + 1);
+    unsigned long long base = 0;
+    unsigned total = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      unsigned cursor = 0;                                       // warp-uniform
+      if (nreg > 0)
+        for (int u = 0; u < m; ++u)
+          for (int i0 = a[u]; i0 <= b[u]; i0 += 32) {
+            const int i = i0 + lane;
+            const bool hit = (i <= b[u]) && rect_column_hit(R, i, sb);
+            const unsigned votes = __ballot_sync(0xffffffffu, hit);
+            if (pass == 1 && hit) {
+              unsigned long long o = base + cursor + (unsigned)__popc(votes & below) * nreg;
+              for (int j = j0; j <= j1; ++j)
+                if (R.row_ok[j]) { if (o < pair_cap) pairs[o] = make_int2(t, j * R.nx + i); ++o; }
+            }
+            cursor += (unsigned)__popc(votes) * nreg;
+          }
+      if (irregular)
+        for (int j = j0; j <= j1; ++j) {
+          if (R.row_ok[j]) continue;
+          for (int i0 = 0; i0 < R.nx; i0 += 32) {
+            const int i = i0 + lane;
+            const long long q = (long long)j * R.nx + i;
+            const bool hit = (i < R.nx) && leaf_hit(dst, q, sb);
+            const unsigned votes = __ballot_sync(0xffffffffu, hit);
+            if (pass == 1 && hit) {
+              const unsigned long long o = base + cursor + (unsigned)__popc(votes & below);
+              if (o < pair_cap) pairs[o] = make_int2(t, (int)q);
+            }
+            cursor += (unsigned)__popc(votes);
+          }
+        }
+      if (pass == 0) {
+        total = cursor;
+        if (lane == 0) {
+          base = atomicAdd(&ctl->total, (unsigned long long)total);
+          pair_off[t] = (uint32_t)base;
+          pair_cnt[t] = total;
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+      }
+    }
+  }
+}
+
 // count pass only (xgb_plan_partition): cnt[t] = candidate pairs of source cell t, heavy cells included
 void launch_candidates_count(const CellSet& src, const SrcMap& sm, const double* mask,
                              const Pyramid& pyr, const CellSet& dst, uint32_t* cnt, const HeavyWork& hw, int* err, cudaStream_t st)
@@ -575,7 +656,10 @@ void launch_candidates_single(const CellSet& src, const SrcMap& sm, const double
   else
     candidate_single_kernel<false><<<blocks, 128, 0, st>>>(src, sm, mask, pyr, rect, dst, pair_off, pair_cnt, pairs, pair_cap,
                                                            hw.flag, hw.list, hw.ctl, err);
-  if (pyr.nlev > 1) {
+  if (rect.valid && pyr.nlev > 1) {
+    ++g_launches;
+    heavy_rect_kernel<<<kHeavyBlocks, 256, 0, st>>>(src, sm, rect, dst, hw.list, hw.ctl, pair_off, pair_cnt, pairs, pair_cap);
+  } else if (pyr.nlev > 1) {
     const int top = pyr.nlev - 1;
     ++g_launches;
     heavy_seed_kernel<<<kHeavyBlocks, kHeavyThreads, 0, st>>>(src, sm, pyr, hw.list, hw.ctl, hw.items[top & 1], hw.cap, err);
@@ -897,6 +981,8 @@ __device__ __forceinline__ int find_tile(const TileDesc* tiles, int ntiles, long
   return t;
 }
 
+constexpr uint32_t kLongPairs = 256;      // heavy cells with at most this many pairs stay with the per-pair rank loop
+
 template <int ORDER>
 __global__ void __launch_bounds__(256)
 scatter_kernel(const int2* __restrict__ pairs, unsigned long long npairs,
@@ -913,7 +999,7 @@ scatter_kernel(const int2* __restrict__ pairs, unsigned long long npairs,
   const double a = parea[p];
   if (!(a > 0.0)) return;
   const int2 pr = pairs[p];
-  if (heavy_flag && heavy_flag[pr.x]) return;                    // pole caps, coarse-on-fine: scatter_long_kernel
+  if (heavy_flag && heavy_flag[pr.x] && pair_cnt[pr.x] > kLongPairs) return;   // pole caps, coarse-on-fine: scatter_long_kernel
   // rank among the accepted pairs of the same source cell by ascending destination index:
   // the reference visits destination cells in ascending ij for each source cell (create_xgrid.c:769)
   uint32_t rank = 0;
@@ -958,6 +1044,7 @@ scatter_long_kernel(const int2* __restrict__ pairs, const double* __restrict__ p
   for (unsigned h = blockIdx.x; h < nh; h += gridDim.x) {
     const int t = heavy_list[h];
     const uint32_t qb = pair_off[t], n = pair_cnt[t];
+    if (n <= kLongPairs) continue;                               // uniform: scatter_kernel ranked these
     if (threadIdx.x == 0) { s_lo = 0x7fffffff; s_hi = -1; s_carry = 0; }
     __syncthreads();
     int lo = 0x7fffffff, hi = -1;
