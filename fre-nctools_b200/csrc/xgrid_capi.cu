@@ -99,6 +99,13 @@ extern "C" xgb_plan* xgb_plan_create(int device)
     return nullptr;
   }
   for (int k = 0; k < 6; ++k) cudaEventCreate(&p->ev[k]);
+  if (cudaStreamCreateWithFlags(&p->aux_st, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&p->fork_ev, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&p->join_ev, cudaEventDisableTiming) != cudaSuccess) {
+    xgb_set_error("cannot create the auxiliary stream: %s", cudaGetErrorString(cudaGetLastError()));
+    xgb_plan_destroy(p);
+    return nullptr;
+  }
   cudaMemsetAsync(p->err_dev, 0, sizeof(int), p->st);
   return p;
 }
@@ -122,6 +129,9 @@ extern "C" void xgb_plan_destroy(xgb_plan* p)
   if (p->total_host) cudaFreeHost(p->total_host);
   if (p->err_host) cudaFreeHost(p->err_host);
   if (p->win_host) cudaFreeHost(p->win_host);
+  if (p->fork_ev) cudaEventDestroy(p->fork_ev);
+  if (p->join_ev) cudaEventDestroy(p->join_ev);
+  if (p->aux_st) cudaStreamDestroy(p->aux_st);
   if (p->copy_ev) cudaEventDestroy(p->copy_ev);
   if (p->copy_st) cudaStreamDestroy(p->copy_st);
   if (p->st) cudaStreamDestroy(p->st);
@@ -466,11 +476,12 @@ static long long generate_window(xgb_plan* p, int order, const SrcMap& sm, size_
                  (const double*)p->pclat.p, (const uint32_t*)p->pair_off.p, (const uint32_t*)p->pair_cnt.p, (const uint32_t*)p->out_off.p,
                  (const TileDesc*)p->tiles_dev.p, (int)p->tiles.size(), sm, p->nx2,
                  (int*)p->t_in.p + base, (int*)p->i_in.p + base, (int*)p->j_in.p + base, (int*)p->i_out.p + base, (int*)p->j_out.p + base,
-                 (double*)p->area.p + base, (double*)p->clon.p + (order == 2 ? base : 0), (double*)p->clat.p + (order == 2 ? base : 0), &hw, p->st);
+                 (double*)p->area.p + base, (double*)p->clon.p + (order == 2 ? base : 0), (double*)p->clat.p + (order == 2 ? base : 0), &hw, p->st,
+                 p->aux_st, p->fork_ev, p->join_ev);
   if (order == 2)
     launch_order2_finalize(p->src, sm, (const uint32_t*)p->out_off.p, (const double*)p->area.p + base,
                            (const double*)p->clon.p + base, (const double*)p->clat.p + base, (double*)p->di.p + base,
-                           (double*)p->dj.p + base, hw.list, &hw.ctl->nheavy, p->st);   // heavy_list / counter are free again
+                           (double*)p->dj.p + base, hw.list, &hw.ctl->nheavy, p->st, p->aux_st, p->fork_ev, p->join_ev);
   cudaEventRecord(p->ev[5], p->st);
   if (sm.nwin > 1 && stream_cap == 0) {                       // exchange cells per window, for the callers' global offsets
     launch_publish_windows(p->win_host, p->out_off.p, sm, p->st);

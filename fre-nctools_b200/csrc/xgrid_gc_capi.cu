@@ -120,7 +120,7 @@ long long xgb_generate_great_circle(xgb_plan* p, int order)
   launch_scatter(1, (const int2*)p->pairs.p, npairs, (const double*)p->parea.p, nullptr, nullptr, (const uint32_t*)p->pair_off.p,
                  (const uint32_t*)p->pair_cnt.p, (const uint32_t*)p->out_off.p, (const TileDesc*)p->tiles_dev.p, (int)p->tiles.size(), sm, p->nx2,
                  (int*)p->t_in.p, (int*)p->i_in.p, (int*)p->j_in.p, (int*)p->i_out.p, (int*)p->j_out.p, (double*)p->area.p,
-                 nullptr, nullptr, nullptr, p->st);
+                 nullptr, nullptr, nullptr, p->st, nullptr, nullptr, nullptr);
   cudaEventRecord(p->ev[5], p->st);
   if (xgb_check_kernel_errors(p, false)) return -1;
   for (int k = 0; k < 5; ++k) {

@@ -106,10 +106,12 @@ void launch_scatter(int order, const int2* pairs, unsigned long long npairs,
                     const uint32_t* pair_off, const uint32_t* pair_cnt, const uint32_t* out_off,
                     const TileDesc* tiles, int ntiles, const SrcMap& sm, int nx2,
                     int* t_in, int* i_in, int* j_in, int* i_out, int* j_out,
-                    double* area, double* clon, double* clat, const HeavyWork* hw, cudaStream_t st);
+                    double* area, double* clon, double* clat, const HeavyWork* hw, cudaStream_t st,
+                    cudaStream_t aux, cudaEvent_t fork, cudaEvent_t join);
 void launch_order2_finalize(const CellSet& src, const SrcMap& sm, const uint32_t* out_off,
                             const double* area, const double* clon, const double* clat,
-                            double* di, double* dj, int* long_list /* ns ints */, unsigned* nlong, cudaStream_t st);
+                            double* di, double* dj, const int* heavy_list, const unsigned* nheavy,
+                            cudaStream_t st, cudaStream_t aux, cudaEvent_t fork, cudaEvent_t join);
 // nwords 32-bit words from device memory to pinned host memory, by a kernel (not the copy engine)
 void launch_publish(void* host_dst, const void* dev_src, int nwords, cudaStream_t st);
 void launch_rect_setup(const CellSet& dst, int nx, int ny, double* store, unsigned char* row_ok, int* invalid, RectDst* out, cudaStream_t st);

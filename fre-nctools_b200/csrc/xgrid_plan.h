@@ -21,6 +21,8 @@ struct xgb_plan {
   cudaStream_t st = nullptr;
   cudaStream_t copy_st = nullptr;             // result download overlapped with generation (xgb_plan_generate_to_host)
   cudaEvent_t copy_ev = nullptr;
+  cudaStream_t aux_st = nullptr;              // heavy-cell kernels beside the bulk scatter / finalize kernels
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
 
   // destination tile
   bool have_dst = false;
