@@ -69,6 +69,7 @@ def lib():
     L.xgb_plan_stream.argtypes = [vp]
     L.xgb_plan_sync.argtypes = [vp]
     L.xgb_plan_set_dst.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int]
+    L.xgb_plan_set_dst_latlon.argtypes = [vp, C.c_int, C.c_int] + [C.c_double] * 4
     L.xgb_plan_set_src.argtypes = [vp, C.c_int, _ip, _ip, vp, vp, vp, C.c_int]
     L.xgb_plan_set_src_window.argtypes = [vp, C.c_longlong, C.c_longlong]
     L.xgb_plan_partition.argtypes = [vp, C.c_int, C.POINTER(C.c_longlong)]
@@ -225,6 +226,11 @@ class XgridPlan:
             raise TypeError("lon and lat must live on the same side")
         self._ck(self._L.xgb_plan_set_dst(self._p, nx, ny, pl, pa, dl))
         self.nx_dst, self.ny_dst = nx, ny
+
+    def set_dst_latlon(self, nlon, nlat, lonbegin=0.0, lonend=360.0, latbegin=-90.0, latend=90.0):
+        """fregrid's --nlon/--nlat output grid, built on the device (no upload); degrees."""
+        self._ck(self._L.xgb_plan_set_dst_latlon(self._p, int(nlon), int(nlat), float(lonbegin), float(lonend), float(latbegin), float(latend)))
+        self.nx_dst, self.ny_dst = int(nlon), int(nlat)
 
     def set_src(self, lons, lats, mask=None):
         """lons/lats: list of per-tile [ny+1, nx+1] arrays, or one [ntiles, ny+1, nx+1] array."""

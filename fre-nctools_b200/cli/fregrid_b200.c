@@ -319,6 +319,15 @@ static void update_halo(const Tile *grid, int n, double *const *tiles, const Bou
   }
 }
 
+/* the destination tile on the device: the --nlon/--nlat grid is built there (get_output_grid_by_size's arithmetic, nothing to
+   upload), a mosaic tile is uploaded */
+static int set_dst_tile(xgb_plan *plan, const Tile *g, int by_size, int nlon, int nlat, double lonbegin, double lonend,
+                        double latbegin, double latend)
+{
+  if (by_size) return xgb_plan_set_dst_latlon(plan, nlon, nlat, lonbegin, lonend, latbegin, latend);
+  return xgb_plan_set_dst(plan, g->nx, g->ny, g->lonc, g->latc, 0);
+}
+
 /* ------------------------------------------------------------------------------------------------------------- */
 /* exchange grid of one output tile, host lists */
 typedef struct {
@@ -591,7 +600,7 @@ int main(int argc, char **argv)
       XGB(xgb_remap_read(xg[m].remap_file, order, n, xg[m].t_in, xg[m].i_in, xg[m].j_in, xg[m].i_out, xg[m].j_out, xg[m].area, xg[m].di, xg[m].dj));
       continue;
     }
-    XGB(xgb_plan_set_dst(plan, gout[m].nx, gout[m].ny, gout[m].lonc, gout[m].latc, 0));
+    XGB(set_dst_tile(plan, &gout[m], !mosaic_out, nlon, nlat, lonbegin, lonend, latbegin, latend));
     const long long n = xgb_plan_generate(plan, opcode & (XGB_CONSERVE_ORDER1 | XGB_CONSERVE_ORDER2 | XGB_GREAT_CIRCLE));
     if (n < 0) die("%s", xgb_last_error());
     xgrid_alloc(&xg[m], n, order);
@@ -608,7 +617,7 @@ int main(int argc, char **argv)
     for (int m = 0; m < ntiles_out; ++m) {
       const int nx1 = gout[m].nx, ny1 = gout[m].ny;
       double *area2 = xmalloc((size_t)nx1 * ny1 * sizeof(double)), *cell_area = xmalloc((size_t)nx1 * ny1 * sizeof(double));
-      XGB(xgb_plan_set_dst(plan, nx1, ny1, gout[m].lonc, gout[m].latc, 0));
+      XGB(set_dst_tile(plan, &gout[m], !mosaic_out, nlon, nlat, lonbegin, lonend, latbegin, latend));
       XGB(xgb_plan_dst_area_host(plan, cell_area));
       for (size_t i = 0; i < (size_t)nx1 * ny1; ++i) area2[i] = 0;
       for (long long i = 0; i < xg[m].n; ++i) area2[(size_t)xg[m].j_out[i] * nx1 + xg[m].i_out[i]] += xg[m].area[i];
@@ -925,7 +934,7 @@ int main(int argc, char **argv)
 
     double *dst_area = NULL;
     if (target_grid) { dst_area = xmalloc((size_t)nx2 * ny2 * sizeof(double));
-      XGB(xgb_plan_set_dst(plan, nx2, ny2, gout[m].lonc, gout[m].latc, 0)); XGB(xgb_plan_dst_area_host(plan, dst_area)); }
+      XGB(set_dst_tile(plan, &gout[m], !mosaic_out, nlon, nlat, lonbegin, lonend, latbegin, latend)); XGB(xgb_plan_dst_area_host(plan, dst_area)); }
     /* the exchange grid of this output tile on the device */
     if (xg[m].n > 0) {
       XGB(xgb_plan_set_xgrid(plan, ntiles_in, nxs, nys, nx2, ny2, xg[m].n, xg[m].t_in, xg[m].i_in, xg[m].j_in, xg[m].i_out, xg[m].j_out,

@@ -193,6 +193,8 @@ int xgb_check_kernel_errors(xgb_plan* p, bool fatal_like_reference)
   return 1;
 }
 
+static int finish_set_dst(xgb_plan* p, int nx, int ny);
+
 extern "C" int xgb_plan_set_dst(xgb_plan* p, int nx, int ny, const double* lon, const double* lat, int on_device)
 {
   if (!p || nx <= 0 || ny <= 0 || !lon || !lat) { xgb_set_error("xgb_plan_set_dst: bad arguments"); return 1; }
@@ -201,6 +203,25 @@ extern "C" int xgb_plan_set_dst(xgb_plan* p, int nx, int ny, const double* lon, 
   const long long nc = (long long)nx * ny;
   if (nc >= (1ll << 31)) { xgb_set_error("destination tile too large for 32-bit cell indices"); return 1; }
   if (upload(p->dst_lon, lon, nv, on_device, p->st) || upload(p->dst_lat, lat, nv, on_device, p->st)) return 1;
+  return finish_set_dst(p, nx, ny);
+}
+
+// fregrid's --nlon/--nlat output grid (get_output_grid_by_size, fregrid_util.c:588-603) built on the device with the
+// reference's arithmetic, so the caller does not upload (nlon+1)*(nlat+1) vertices it never had as data.
+extern "C" int xgb_plan_set_dst_latlon(xgb_plan* p, int nlon, int nlat, double lonbegin, double lonend, double latbegin, double latend)
+{
+  if (!p || nlon <= 0 || nlat <= 0 || !(lonend > lonbegin) || !(latend > latbegin)) { xgb_set_error("xgb_plan_set_dst_latlon: bad arguments"); return 1; }
+  CU_OK(cudaSetDevice(p->device));
+  const size_t nv = (size_t)(nlon + 1) * (nlat + 1);
+  if ((long long)nlon * nlat >= (1ll << 31)) { xgb_set_error("destination tile too large for 32-bit cell indices"); return 1; }
+  if (p->dst_lon.reserve(nv * sizeof(double)) || p->dst_lat.reserve(nv * sizeof(double))) return 1;
+  launch_latlon_fill(nlon, nlat, lonbegin, lonend, latbegin, latend, (double*)p->dst_lon.p, (double*)p->dst_lat.p, p->st);
+  return finish_set_dst(p, nlon, nlat);
+}
+
+static int finish_set_dst(xgb_plan* p, int nx, int ny)
+{
+  const long long nc = (long long)nx * ny;
   if (carve_cellset(p->dst_store, nc, &p->dst)) return 1;
   p->nx2 = nx; p->ny2 = ny;
   TileDesc td{nx, ny, 0, 0};

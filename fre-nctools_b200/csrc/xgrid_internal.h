@@ -114,6 +114,8 @@ void launch_order2_finalize(const CellSet& src, const SrcMap& sm, const uint32_t
                             cudaStream_t st, cudaStream_t aux, cudaEvent_t fork, cudaEvent_t join);
 // nwords 32-bit words from device memory to pinned host memory, by a kernel (not the copy engine)
 void launch_publish(void* host_dst, const void* dev_src, int nwords, cudaStream_t st);
+void launch_latlon_fill(int nlon, int nlat, double lonbegin, double lonend, double latbegin, double latend, double* lon, double* lat,
+                        cudaStream_t st);
 void launch_rect_setup(const CellSet& dst, int nx, int ny, double* store, unsigned char* row_ok, int* invalid, RectDst* out, cudaStream_t st);
 void launch_publish_windows(void* host_dst, const void* out_off, const SrcMap& sm, cudaStream_t st);
 // exclusive prefix sum of n uint32 counts; out has n+1 entries (out[n] = total, must fit 32 bits);

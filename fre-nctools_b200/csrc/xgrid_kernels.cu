@@ -246,6 +246,28 @@ candidate_kernel(CellSet src, SrcMap sm, const double* __restrict__ mask,
   }
 }
 
+// fregrid's regular output grid (fregrid_util.c:588-603: lonc1D[i] = (lonbegin + i*dlon)*D2R, latc1D[j] = (latbegin + j*dlat)*D2R,
+// copied to every row / column), same operations in the same order, so the vertices are bit-identical to the host's
+__global__ void latlon_fill_kernel(int nlon, int nlat, double lonbegin, double dlon, double latbegin, double dlat,
+                                   double* __restrict__ lon, double* __restrict__ lat)
+{
+  const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (v >= (long long)(nlon + 1) * (nlat + 1)) return;
+  const int i = (int)(v % (nlon + 1)), j = (int)(v / (nlon + 1));
+  const double d2r = kPi / 180;
+  lon[v] = (lonbegin + i * dlon) * d2r;
+  lat[v] = (latbegin + j * dlat) * d2r;
+}
+
+void launch_latlon_fill(int nlon, int nlat, double lonbegin, double lonend, double latbegin, double latend, double* lon, double* lat,
+                        cudaStream_t st)
+{
+  const long long nv = (long long)(nlon + 1) * (nlat + 1);
+  ++g_launches;
+  latlon_fill_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>(nlon, nlat, lonbegin, (lonend - lonbegin) / nlon, latbegin,
+                                                                  (latend - latbegin) / nlat, lon, lat);
+}
+
 // ---- separable destination tile (RectDst) ----------------------------------------------------------------------
 // Every box test of the reference (create_xgrid.c:777-801) is "latitude ranges overlap" AND "longitude ranges overlap after
 // the 2*pi shift chosen from the mean longitudes".  When the destination's latitude range depends on the row only and its

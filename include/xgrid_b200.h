@@ -112,6 +112,10 @@ int          xgb_plan_sync(xgb_plan *p);
 /* Destination tile: (nx+1)*(ny+1) vertex longitudes/latitudes, radians, row-major
  * (Grid_config.lonc/latc, globals.h:188-189).  on_device != 0: pointers are device pointers. */
 int xgb_plan_set_dst(xgb_plan *p, int nx, int ny, const double *lon, const double *lat, int on_device);
+/* The same for fregrid's --nlon/--nlat/--lonBegin... regular output grid (get_output_grid_by_size, fregrid_util.c:588-603):
+ * the vertices are computed on the device with the reference's arithmetic (bit-identical to xgb_latlon_grid), nothing is
+ * uploaded.  Degrees. */
+int xgb_plan_set_dst_latlon(xgb_plan *p, int nlon, int nlat, double lonbegin, double lonend, double latbegin, double latend);
 
 /* Source mosaic: ntiles tiles concatenated, tile n has (nx[n]+1)*(ny[n]+1) vertices.
  * mask: per source cell (concatenated), NULL = all 1.0 (conserve_interp.c:160-161). */

@@ -405,3 +405,21 @@ def test_separable_destination_search_equals_pyramid_walk_and_oracle(pkg, order)
             want = xgtest.oracle_setup(lonc, latc, lon2, lat2, xgtest.ORDER2 if order == 2 else xgtest.ORDER1)
             sc = xgtest.parent_scale(want, lonc, latc, lon2, lat2)
             xgtest.assert_xgrid_equal(a, want, order, area_tol=1e-12, dist_atol=1e-9, scale=sc)
+
+
+def test_destination_grid_built_on_the_device_equals_the_uploaded_one(pkg):
+    """xgb_plan_set_dst_latlon (fregrid's --nlon/--nlat grid, get_output_grid_by_size) against the same grid uploaded from the
+    host: identical exchange grids, bit for bit"""
+    lonc, latc = pkg.cubed_sphere_grid(24)
+    for args in ((96, 48, 0.0, 360.0, -90.0, 90.0), (50, 40, -30.0, 95.0, -63.0, 77.0)):
+        lon2, lat2 = pkg.latlon_grid(*args)
+        want = _generate(pkg, lonc, latc, lon2, lat2, 2, no_rect=False)
+        plan = pkg.XgridPlan(0)
+        plan.set_dst_latlon(*args)
+        plan.set_src(lonc, latc)
+        n = plan.generate(pkg.CONSERVE_ORDER2)
+        got = plan.result_host()
+        plan.close()
+        assert n == want["nxgrid"] and n > 0
+        for key in got:
+            assert np.array_equal(got[key], want[key]), key
