@@ -121,9 +121,10 @@ typedef struct {
 
 static void tokenize_str(const char *s, const char *seps, char out[][STRING], int maxn, int *n)
 {
-  char buf[1024];
+  static char buf[40960];                                      /* fregrid.c MAXSTRING-sized entries */
   char *save = NULL, *t;
-  strncpy(buf, s, sizeof buf - 1); buf[sizeof buf - 1] = 0;
+  if (strlen(s) >= sizeof buf) die("fregrid: the entry '%.40s...' is too long", s);
+  strcpy(buf, s);
   *n = 0;
   for (t = strtok_r(buf, seps, &save); t; t = strtok_r(NULL, seps, &save)) {
     if (*n >= maxn) die("fregrid: too many tokens in '%s'", s);

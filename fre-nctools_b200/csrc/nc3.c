@@ -22,6 +22,7 @@
 #include <unistd.h>
 
 enum { TAG_DIM = 0x0A, TAG_VAR = 0x0B, TAG_ATT = 0x0C };
+#define NC3_MAX_LIST 65536u            /* dimensions / variables / attributes per list: a larger count is a corrupt header */
 
 typedef struct { char *name; long long len; } Dim;
 typedef struct { char *name; int type; long long n; unsigned char *raw; /* big-endian, as on disk, unpadded */ } Att;
@@ -149,6 +150,7 @@ static int rd_atts(Cur *c, int *natts, Att **atts)
   if (c->short_read) return 0;
   if (tag == 0 && n == 0) return 0;
   if (tag != TAG_ATT) return -1;
+  if (n > NC3_MAX_LIST) return -5;
   *atts = (Att *)calloc(n ? n : 1, sizeof(Att));
   for (i = 0; i < n; ++i) {
     Att *a = &(*atts)[i];
@@ -200,6 +202,7 @@ static int parse_header(nc3_file *f, const unsigned char *buf, size_t n)
   if (c.short_read) return 1;
   if (!(tag == 0 && cnt == 0)) {
     if (tag != TAG_DIM) return -1;
+    if (cnt > NC3_MAX_LIST) return -5;
     f->dims = (Dim *)calloc(cnt ? cnt : 1, sizeof(Dim));
     for (i = 0; i < cnt; ++i) {
       f->dims[i].name = rd_name(&c);
@@ -216,6 +219,7 @@ static int parse_header(nc3_file *f, const unsigned char *buf, size_t n)
   if (c.short_read) return 1;
   if (!(tag == 0 && cnt == 0)) {
     if (tag != TAG_VAR) return -1;
+    if (cnt > NC3_MAX_LIST) return -5;
     f->vars = (Var *)calloc(cnt ? cnt : 1, sizeof(Var));
     for (i = 0; i < cnt; ++i) {
       Var *v = &f->vars[i];

@@ -145,3 +145,25 @@ def test_netcdf4_is_refused_by_name(L, tmp_path):
     open(os.path.join(d,'h.nc'),'wb').write(b'\x89HDF\r\n\x1a\n'+b'\0'*100)
     assert not L.nc3_open(os.path.join(d, 'h.nc').encode(), err, 256)
     assert b'netCDF-4/HDF5' in err.value
+
+
+def test_corrupt_headers_are_refused(L, tmp_path):
+    """truncated files, absurd list counts and unknown types end in an error message, not in a crash"""
+    import struct
+    err = C.create_string_buffer(256)
+    good = str(tmp_path / "good.nc")
+    g = netcdf_file(good, "w", version=1); g.createDimension("n", 3); v = g.createVariable("v", "d", ("n",)); v[:] = [1.0, 2.0, 3.0]; g.close()
+    raw = open(good, "rb").read()
+    cases = {"short": raw[:20], "dims": raw[:8] + struct.pack(">ii", 0x0A, 0x7fffffff) + raw[16:],
+             "magic": b"CDF\x07" + raw[4:], "empty": b""}
+    for name, blob in cases.items():
+        p = str(tmp_path / (name + ".nc"))
+        open(p, "wb").write(blob)
+        assert not L.nc3_open(p.encode(), err, 256), name
+        assert err.value, name
+    f = L.nc3_open(good.encode(), err, 256)
+    assert f
+    out = np.zeros(3)
+    assert L.nc3_get_var_double(f, L.nc3_var_id(f, b"v"), out.ctypes.data) == 0 and out.tolist() == [1.0, 2.0, 3.0]
+    assert L.nc3_get_vara_double(f, 0, arr(2), arr(5), out.ctypes.data) != 0 and b"exceeds" in L.nc3_strerror(f)
+    L.nc3_close(f)
