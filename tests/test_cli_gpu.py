@@ -61,10 +61,8 @@ def _strings(g, name, dim, values):
         v[k] = np.frombuffer(s.encode().ljust(255, b"\0"), "S1")
 
 
-@pytest.fixture(scope="module")
-def dataset(pkg, tmp_path_factory):
-    d = str(tmp_path_factory.mktemp("cli"))
-    n = NI
+def _write_mosaic(pkg, d, n):
+    """C<n>_mosaic.nc + C<n>_grid.tile[1-6].nc as make_hgrid / make_solo_mosaic leave them; returns what fregrid sees"""
     lonc, latc, lont, latt = pkg.cubed_sphere_grid(n, centers=True)
     hmap = xgtest.cubed_sphere_halo_map(lonc, latc)
     names, index = _contacts(hmap, n)
@@ -86,8 +84,17 @@ def dataset(pkg, tmp_path_factory):
         x[:] = xdeg[t]; y[:] = ydeg[t]
         g.close()
     # what the tool sees after degrees -> radians (fregrid_util.c:227-241)
-    lonc_r = xdeg[:, ::2, ::2] * D2R; latc_r = ydeg[:, ::2, ::2] * D2R
-    lont_r = xdeg[:, 1::2, 1::2] * D2R; latt_r = ydeg[:, 1::2, 1::2] * D2R
+    return dict(lonc=xdeg[:, ::2, ::2] * D2R, latc=ydeg[:, ::2, ::2] * D2R, lont=xdeg[:, 1::2, 1::2] * D2R,
+                latt=ydeg[:, 1::2, 1::2] * D2R, hmap=hmap)
+
+
+@pytest.fixture(scope="module")
+def dataset(pkg, tmp_path_factory):
+    d = str(tmp_path_factory.mktemp("cli"))
+    n = NI
+    grid = _write_mosaic(pkg, d, n)
+    hmap = grid["hmap"]
+    lonc_r, latc_r, lont_r, latt_r = grid["lonc"], grid["latc"], grid["lont"], grid["latt"]
     nt, nz = 2, 3
     rng = np.random.default_rng(7)
     temp = np.stack([[xgtest.smooth_field(lont_r, latt_r, k, t).reshape(6, n, n) for k in range(nz)] for t in range(nt)]).astype(np.float32)
@@ -258,3 +265,30 @@ def test_reference_error_messages(pkg, dataset):
     for args, msg in cases:
         r = _run(pkg, ds, *args, ok=False)
         assert r.returncode == 1 and "FATAL Error" in r.stderr and msg in r.stderr, (args, r.stderr)
+
+
+def test_output_mosaic_with_several_tiles(pkg, dataset):
+    """--output_mosaic: cubed sphere onto another cubed sphere; one remap file and one output file per destination tile, named
+    after the mosaic's gridtiles (set_remap_file, set_mosaic_data_file); a curvilinear destination takes the pyramid search"""
+    ds = dataset
+    m = 10
+    out = _write_mosaic(pkg, ds["dir"], m)
+    args = ["--input_mosaic", f"C{ds['n']}_mosaic.nc", "--output_mosaic", f"C{m}_mosaic.nc", "--input_file", "atmos", "--scalar_field", "ps",
+            "--output_file", "cs_out", "--remap_file", "cs_remap"]
+    r = _run(pkg, ds, *args)
+    for t in range(6):
+        assert f"****cs_out.tile{t + 1}.nc" in r.stdout
+    n = ds["n"]; tiles = [(n, n)] * 6
+    for t in (0, 2, 5):
+        x = xgtest.oracle_setup(ds["lonc"], ds["latc"], out["lonc"][t], out["latc"][t], xgtest.ORDER1)
+        got = _remap_lists(pkg, os.path.join(ds["dir"], f"cs_remap.tile{t + 1}.nc"), 1)
+        for k in ("t_in", "i_in", "j_in", "i_out", "j_out"):
+            assert np.array_equal(got[k], x[k]), (t, k)
+        g = netcdf_file(os.path.join(ds["dir"], f"cs_out.tile{t + 1}.nc"), "r", mmap=False)
+        assert g.dimensions["grid_xt"] == m and g.dimensions["grid_yt"] == m and "grid_xt_bnds" not in g.variables
+        for k in range(ds["nt"]):
+            want = xgtest.oracle_apply(x, 1, tiles, ds["ps"][k].reshape(-1), m, m)
+            assert np.array_equal(g.variables["ps"][k].reshape(-1), want), (t, k)
+        g.close()
+    r2 = _run(pkg, ds, *args)                                  # all six remap files exist now: READ
+    assert "Finish reading index and weight" in r2.stdout
