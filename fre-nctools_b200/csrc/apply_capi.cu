@@ -493,7 +493,7 @@ extern "C" int xgb_plan_regrid(xgb_plan* p, unsigned int opcode, int nfields, co
     ApplyCsr csr;
     if (effective_csr(p, a, &csr)) return 1;
     const double miss = has_missing ? missing : -1.e20;
-    launch_apply_packed(has_missing != 0, csr, a->ndst, nfields, (const double*)a->s_gx.p, a->ncell, miss, d_out, p->st, a->cell_methods);
+    launch_apply_packed(has_missing != 0, csr, a->ndst, nfields, (const double*)a->s_gx.p, a->ncell, miss, d_out, p->st, a->cell_methods, a->nx2);
     finish_variants(p, a, 2, nfields, d_data, has_missing != 0, miss, d_out);
     if (a->opt_farea && has_missing && kernel_errors(p)) return 1;
   } else {

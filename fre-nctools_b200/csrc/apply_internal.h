@@ -57,7 +57,7 @@ void launch_grad_c2l(const GradTile* tiles, int ntiles, long long ncell, int nf,
 void launch_grad_c2l_packed(const GradTile* tiles, int ntiles, long long ncell, int nf, const double* data, long long data_stride,
                             double* packed, bool has_missing, double missing, cudaStream_t st);
 void launch_apply_packed(bool has_missing, const ApplyCsr& csr, long long ndst, int nf, const double* packed, long long ncell_src,
-                         double missing, double* out, cudaStream_t st, int sum_mode = 0);
+                         double missing, double* out, cudaStream_t st, int sum_mode, int nx_out);
 void launch_effective_area(const ApplyCsr& csr, long long n, const double* weight, const double* carea, const double* farea,
                            int sum_mode, double* eff, cudaStream_t st);
 void launch_measure_check(const ApplyCsr& csr, long long n, int order, const double* data, const double* farea, double missing,

@@ -184,17 +184,34 @@ void launch_apply(int order, bool has_missing, bool from_xdata, const ApplyCsr& 
 
 // Fused-path variant: the gradient kernel leaves (value, grad_x, grad_y, grad_mask) of a source cell next to each other
 // (32 bytes, one sector), so an exchange-cell entry costs one gather per field instead of three.
-constexpr int kPackBT = kApplyBT;  // field-levels per thread (16 per thread and shared-memory staging of the entries
-                                   // both measured slower on configs[1]: the L1 footprint of the gathers grows)
+#ifndef XGB_PACK_BT
+#define XGB_PACK_BT 8
+#endif
+#ifndef XGB_APPLY_PATCH_ROWS
+#define XGB_APPLY_PATCH_ROWS 0     // 0: a block takes 128 consecutive destination cells; R: a 32-wide, R-row patch (128 / R... see kernel)
+#endif
+constexpr int kPackBT = XGB_PACK_BT;  // field-levels per thread (16 per thread and shared-memory staging of the entries
+                                      // both measured slower on configs[1]: the L1 footprint of the gathers grows)
 
 template <bool MISSING>
 __global__ void __launch_bounds__(128)
 apply_packed_kernel(ApplyCsr csr, long long ndst, int nf, const double4* __restrict__ packed, long long ncell_src,
-                    double missing, int sum_mode, double* __restrict__ out)
+                    double missing, int sum_mode, double* __restrict__ out, int nx_out)
 {
   const int nft = (nf + kPackBT - 1) / kPackBT;
+#if XGB_APPLY_PATCH_ROWS > 0
+  // a block = a patch of 32 columns x 4 rows of the destination tile: its cells share far fewer source records than 128 cells
+  // of one row do, so the gathers of a block stay in L1
+  const int ny_out = (int)(ndst / nx_out);
+  const int npx = (nx_out + 31) / 32;
+  const long long patch = blockIdx.x / nft;
+  const int i = (int)(patch % npx) * 32 + (threadIdx.x & 31), j = (int)(patch / npx) * 4 + (threadIdx.x >> 5);
+  if (i >= nx_out || j >= ny_out) return;
+  const long long d = (long long)j * nx_out + i;
+#else
   const long long d = (long long)(blockIdx.x / nft) * blockDim.x + threadIdx.x;
   if (d >= ndst) return;
+#endif
   const int f0 = (int)(blockIdx.x % nft) * kPackBT;
   const uint32_t b = csr.off[d], e = csr.off[d + 1];
   double acc[kPackBT], asum[kPackBT];
@@ -235,14 +252,19 @@ apply_packed_kernel(ApplyCsr csr, long long ndst, int nf, const double4* __restr
 }
 
 void launch_apply_packed(bool has_missing, const ApplyCsr& csr, long long ndst, int nf, const double* packed, long long ncell_src,
-                         double missing, double* out, cudaStream_t st, int sum_mode)
+                         double missing, double* out, cudaStream_t st, int sum_mode, int nx_out)
 {
   if (ndst <= 0 || nf <= 0) return;
+#if XGB_APPLY_PATCH_ROWS > 0
+  const long long ny_out = ndst / nx_out;
+  const long long nblk = (long long)((nx_out + 31) / 32) * ((ny_out + 3) / 4) * ((nf + kPackBT - 1) / kPackBT);
+#else
   const long long nblk = ((ndst + 127) / 128) * ((nf + kPackBT - 1) / kPackBT);
+#endif
   if (nblk >= (1ll << 31)) return;
   ++g_launches;
-  if (has_missing) apply_packed_kernel<true><<<(unsigned)nblk, 128, 0, st>>>(csr, ndst, nf, (const double4*)packed, ncell_src, missing, sum_mode, out);
-  else             apply_packed_kernel<false><<<(unsigned)nblk, 128, 0, st>>>(csr, ndst, nf, (const double4*)packed, ncell_src, missing, sum_mode, out);
+  if (has_missing) apply_packed_kernel<true><<<(unsigned)nblk, 128, 0, st>>>(csr, ndst, nf, (const double4*)packed, ncell_src, missing, sum_mode, out, nx_out);
+  else             apply_packed_kernel<false><<<(unsigned)nblk, 128, 0, st>>>(csr, ndst, nf, (const double4*)packed, ncell_src, missing, sum_mode, out, nx_out);
 }
 
 // =============================================================================================
