@@ -292,3 +292,36 @@ def test_output_mosaic_with_several_tiles(pkg, dataset):
         g.close()
     r2 = _run(pkg, ds, *args)                                  # all six remap files exist now: READ
     assert "Finish reading index and weight" in r2.stdout
+
+
+def test_great_circle_grid_file_selects_the_great_circle_generator(pkg, reflib, tmp_path):
+    """configs[2] in small: a tripolar ocean grid whose grid file carries great_circle_algorithm = "TRUE" (get_great_circle_algorithm,
+    fregrid.c:757-765) onto a lat-lon grid: the remap file holds the great-circle exchange grid; order 2 is refused like the
+    reference does"""
+    d = str(tmp_path)
+    tl, ta = xgtest.tripolar_grid(120, 80)                     # model grid 60 x 40
+    ny, nx = tl.shape[0] - 1, tl.shape[1] - 1
+    g = netcdf_file(os.path.join(d, "ocean_mosaic.nc"), "w", version=1)
+    g.createDimension("ntiles", 1); g.createDimension("string", 255)
+    _strings(g, "gridfiles", "ntiles", ["ocean_hgrid.nc"]); _strings(g, "gridtiles", "ntiles", ["tile1"])
+    g.close()
+    xdeg = np.zeros((2 * ny + 1, 2 * nx + 1)); ydeg = np.zeros_like(xdeg)
+    xdeg[::2, ::2] = tl * R2D; ydeg[::2, ::2] = ta * R2D
+    g = netcdf_file(os.path.join(d, "ocean_hgrid.nc"), "w", version=1)
+    g.createDimension("nx", 2 * nx); g.createDimension("ny", 2 * ny); g.createDimension("nxp", 2 * nx + 1); g.createDimension("nyp", 2 * ny + 1)
+    g.great_circle_algorithm = "TRUE"
+    x = g.createVariable("x", "d", ("nyp", "nxp")); y = g.createVariable("y", "d", ("nyp", "nxp"))
+    x[:] = xdeg; y[:] = ydeg
+    g.close()
+    ds = {"dir": d}
+    _run(pkg, ds, "--input_mosaic", "ocean_mosaic.nc", "--nlon", "36", "--nlat", "18", "--remap_file", "gc_remap")
+    lon2, lat2 = pkg.latlon_grid(36, 18)
+    want = xgtest.oracle_setup([xdeg[::2, ::2] * D2R], [ydeg[::2, ::2] * D2R], lon2, lat2, xgtest.ORDER1 | xgtest.GREAT_CIRCLE)
+    got = _remap_lists(pkg, os.path.join(d, "gc_remap.nc"), 1)
+    assert got["nxgrid"] == want["nxgrid"] and want["nxgrid"] > 0
+    for k in ("t_in", "i_in", "j_in", "i_out", "j_out"):
+        assert np.array_equal(got[k], want[k]), k
+    assert np.allclose(got["area"], want["area"], rtol=0, atol=8e-15 * 6371000.0 ** 2)     # DESIGN.md section 2, great circle
+    r = _run(pkg, ds, "--input_mosaic", "ocean_mosaic.nc", "--nlon", "36", "--nlat", "18", "--remap_file", "gc2", "--interp_method",
+             "conserve_order2", ok=False)
+    assert "can not be conserve_order2" in r.stderr
