@@ -99,7 +99,7 @@ void launch_candidates_single(const CellSet& src, const SrcMap& sm, const double
                               const Pyramid& pyr, const RectDst& rect, const CellSet& dst, uint32_t* pair_off, uint32_t* pair_cnt, int2* pairs,
                               unsigned long long pair_cap, uint32_t* cursor, const HeavyWork& hw, int* err, cudaStream_t st);
 void launch_clip(int order, const CellSet& src, const CellSet& dst, const double* mask,
-                 const int2* pairs, unsigned long long npairs, const SrcMap& sm,
+                 const int2* pairs, unsigned long long npairs, const unsigned long long* npairs_dev, const SrcMap& sm,
                  double* parea, double* pclon, double* pclat, uint32_t* cnt, int* err, cudaStream_t st);
 void launch_scatter(int order, const int2* pairs, unsigned long long npairs,
                     const double* parea, const double* pclon, const double* pclat,
@@ -107,7 +107,7 @@ void launch_scatter(int order, const int2* pairs, unsigned long long npairs,
                     const TileDesc* tiles, int ntiles, const SrcMap& sm, int nx2,
                     int* t_in, int* i_in, int* j_in, int* i_out, int* j_out,
                     double* area, double* clon, double* clat, const HeavyWork* hw, cudaStream_t st,
-                    cudaStream_t aux, cudaEvent_t fork, cudaEvent_t join);
+                    cudaStream_t aux, cudaEvent_t fork, cudaEvent_t join, const unsigned long long* npairs_dev = nullptr);
 void launch_order2_finalize(const CellSet& src, const SrcMap& sm, const uint32_t* out_off,
                             const double* area, const double* clon, const double* clat,
                             double* di, double* dj, const int* heavy_list, const unsigned* nheavy,

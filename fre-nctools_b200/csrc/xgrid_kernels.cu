@@ -897,7 +897,7 @@ __device__ __forceinline__ bool load_src_poly(const CellSet& src, long long s, i
 template <int ORDER>
 __global__ void __launch_bounds__(kClipThreads, (ORDER == 1) ? XGB_CLIP_BLOCKS1 : XGB_CLIP_BLOCKS)   // 96 registers: 5 blocks/SM measured 7 % faster than 4 (120 regs) or 6 (80, spills)
 clip_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const int2* __restrict__ pairs,
-            unsigned long long npairs, SrcMap smap,
+            unsigned long long npairs, const unsigned long long* __restrict__ npairs_dev, SrcMap smap,
             double* __restrict__ parea, double* __restrict__ pclon, double* __restrict__ pclat,
             uint32_t* __restrict__ cnt, int* err)
 {
@@ -911,7 +911,11 @@ clip_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const int
   const double* T = ref_trig_table();
 #endif
   const unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-  const bool valid = p < npairs;                                  // no early exit: the warp reconverges explicitly below
+  // npairs_dev: the candidate search's total, still unseen by the host (single-sync generate); npairs is then the capacity
+  // of the pair buffer and bounds the launch
+  if (npairs_dev) { const unsigned long long nd = *npairs_dev; if (nd < npairs) npairs = nd; }
+  if (blockIdx.x * (unsigned long long)blockDim.x >= npairs) return;   // whole block beyond the list (capacity-sized launch)
+  const bool valid = p < npairs;                                  // no per-thread exit: the warp reconverges explicitly below
   const int2 pr = valid ? pairs[p] : make_int2(0, 0);
   const long long s = smap.cell(pr.x), d = pr.y;
   const int n1 = valid ? src.nv[s] : 0, n2 = valid ? dst.nv[d] : 0;
@@ -1045,14 +1049,14 @@ clip_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const int
 }
 
 void launch_clip(int order, const CellSet& src, const CellSet& dst, const double* mask,
-                 const int2* pairs, unsigned long long npairs, const SrcMap& sm,
+                 const int2* pairs, unsigned long long npairs, const unsigned long long* npairs_dev, const SrcMap& sm,
                  double* parea, double* pclon, double* pclat, uint32_t* cnt, int* err, cudaStream_t st)
 {
   if (npairs == 0) return;
   const unsigned blocks = (unsigned)((npairs + kClipThreads - 1) / kClipThreads);
   ++g_launches;
-  if (order == 2) clip_kernel<2><<<blocks, kClipThreads, 0, st>>>(src, dst, mask, pairs, npairs, sm, parea, pclon, pclat, cnt, err);
-  else            clip_kernel<1><<<blocks, kClipThreads, 0, st>>>(src, dst, mask, pairs, npairs, sm, parea, pclon, pclat, cnt, err);
+  if (order == 2) clip_kernel<2><<<blocks, kClipThreads, 0, st>>>(src, dst, mask, pairs, npairs, npairs_dev, sm, parea, pclon, pclat, cnt, err);
+  else            clip_kernel<1><<<blocks, kClipThreads, 0, st>>>(src, dst, mask, pairs, npairs, npairs_dev, sm, parea, pclon, pclat, cnt, err);
 }
 
 // =============================================================================================
@@ -1076,9 +1080,14 @@ scatter_kernel(const int2* __restrict__ pairs, unsigned long long npairs,
                int* __restrict__ t_in, int* __restrict__ i_in, int* __restrict__ j_in,
                int* __restrict__ i_out, int* __restrict__ j_out,
                double* __restrict__ area, double* __restrict__ clon, double* __restrict__ clat,
-               const unsigned char* __restrict__ heavy_flag)
+               const unsigned char* __restrict__ heavy_flag, const unsigned long long* __restrict__ npairs_dev)
 {
   const unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (npairs_dev) {                                               // single-sync generate: npairs is the buffer capacity
+    const unsigned long long nd = *npairs_dev;
+    if (nd > npairs) return;                                      // overflow: the host repeats the window with larger buffers
+    npairs = nd;
+  }
   if (p >= npairs) return;
   const double a = parea[p];
   if (!(a > 0.0)) return;
@@ -1116,9 +1125,11 @@ scatter_long_kernel(const int2* __restrict__ pairs, const double* __restrict__ p
                     const uint32_t* __restrict__ out_off, const TileDesc* __restrict__ tiles, int ntiles, SrcMap sm, int nx2,
                     int* __restrict__ t_in, int* __restrict__ i_in, int* __restrict__ j_in, int* __restrict__ i_out,
                     int* __restrict__ j_out, double* __restrict__ area, double* __restrict__ clon, double* __restrict__ clat,
-                    const int* __restrict__ heavy_list, const unsigned* __restrict__ nheavy)
+                    const int* __restrict__ heavy_list, const unsigned* __restrict__ nheavy,
+                    unsigned long long pair_cap, const unsigned long long* __restrict__ npairs_dev)
 {
   __shared__ unsigned bits[kRankWords];
+  if (npairs_dev && *npairs_dev > pair_cap) return;               // pair buffer overflow: nothing here is complete
   __shared__ unsigned pre[kRankWords];
   __shared__ unsigned wsum[8];
   __shared__ int s_lo, s_hi;
@@ -1191,7 +1202,7 @@ void launch_scatter(int order, const int2* pairs, unsigned long long npairs,
                     const TileDesc* tiles, int ntiles, const SrcMap& sm, int nx2,
                     int* t_in, int* i_in, int* j_in, int* i_out, int* j_out,
                     double* area, double* clon, double* clat, const HeavyWork* hw, cudaStream_t st,
-                    cudaStream_t aux, cudaEvent_t fork, cudaEvent_t join)
+                    cudaStream_t aux, cudaEvent_t fork, cudaEvent_t join, const unsigned long long* npairs_dev)
 {
   if (npairs == 0) return;
   if (hw) { cudaEventRecord(fork, st); cudaStreamWaitEvent(aux, fork, 0); }      // the block-per-cell kernel runs beside the bulk one
@@ -1201,16 +1212,18 @@ void launch_scatter(int order, const int2* pairs, unsigned long long npairs,
   g_launches += hw ? 2 : 1;
   if (order == 2) {
     scatter_kernel<2><<<blocks, threads, 0, st>>>(pairs, npairs, parea, pclon, pclat, pair_off, pair_cnt, out_off, tiles, ntiles, sm, nx2,
-                                                  t_in, i_in, j_in, i_out, j_out, area, clon, clat, flag);
+                                                  t_in, i_in, j_in, i_out, j_out, area, clon, clat, flag, npairs_dev);
     if (hw)
       scatter_long_kernel<2><<<148 * 2, 256, 0, aux>>>(pairs, parea, pclon, pclat, pair_off, pair_cnt, out_off, tiles, ntiles, sm, nx2,
-                                                      t_in, i_in, j_in, i_out, j_out, area, clon, clat, hw->list, &hw->ctl->nheavy);
+                                                      t_in, i_in, j_in, i_out, j_out, area, clon, clat, hw->list, &hw->ctl->nheavy,
+                                                      npairs, npairs_dev);
   } else {
     scatter_kernel<1><<<blocks, threads, 0, st>>>(pairs, npairs, parea, pclon, pclat, pair_off, pair_cnt, out_off, tiles, ntiles, sm, nx2,
-                                                  t_in, i_in, j_in, i_out, j_out, area, clon, clat, flag);
+                                                  t_in, i_in, j_in, i_out, j_out, area, clon, clat, flag, npairs_dev);
     if (hw)
       scatter_long_kernel<1><<<148 * 2, 256, 0, aux>>>(pairs, parea, pclon, pclat, pair_off, pair_cnt, out_off, tiles, ntiles, sm, nx2,
-                                                      t_in, i_in, j_in, i_out, j_out, area, clon, clat, hw->list, &hw->ctl->nheavy);
+                                                      t_in, i_in, j_in, i_out, j_out, area, clon, clat, hw->list, &hw->ctl->nheavy,
+                                                      npairs, npairs_dev);
   }
   if (hw) { cudaEventRecord(join, aux); cudaStreamWaitEvent(st, join, 0); }
 }
