@@ -312,7 +312,21 @@ def run_gpu_arm(args):
     h_mine = torch.zeros(WPR, dtype=torch.int64).pin_memory()
     mine = torch.zeros(WPR, dtype=torch.int64, device=dev)
 
+    # An asynchronous step enqueues one generate on the plan's stream (xgb_plan_generate_async) and, for N > 1, the path's one exchange behind
+    # it: per-window counts taken on the device, all-gathered over NCCL -> global offsets of every piece.  Nothing waits for the
+    # host inside the timed region; the count comes back with generate_finish() after it.  Opt-in (--async-steps): the default
+    # step is the blocking xgb_plan_generate (one host synchronisation per step).
+    use_async = args.async_steps
+    plan.generate(opcode)                           # sizes the buffers for this rank's windows (untimed)
+
     def step():
+        if use_async:
+            plan.generate_async(opcode)
+            if world > 1:
+                plan.window_counts_device(mine)
+                with torch.cuda.stream(ext):
+                    dist.all_gather_into_tensor(counts, mine)
+            return None
         nx = plan.generate(opcode)
         if world > 1:                           # the path's one exchange: per-window counts -> global offsets of every piece
             h_mine.copy_(torch.tensor(plan.window_counts(), dtype=torch.int64))
@@ -328,6 +342,8 @@ def run_gpu_arm(args):
 
     for _ in range(args.warmup):
         step()
+    if use_async:
+        plan.generate_finish()
     plan.reset_phase_ms()
     launches0 = pkg.kernel_launches()
     sampler = ClockSampler(local)
@@ -343,6 +359,10 @@ def run_gpu_arm(args):
     with torch.cuda.stream(ext):
         e1.record()
     barrier()
+    if use_async:
+        nx = plan.generate_finish()                 # the stream has drained: checks the kernels' error word, returns the count
+        if world > 1:
+            assert int(counts.sum().item()) > 0 and plan.window_counts() == mine.tolist()
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1) / args.steps
     launches = pkg.kernel_launches() - launches0
@@ -435,6 +455,7 @@ def run_gpu_arm(args):
     roofline = {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": traffic,
                 "kernel": f"clip_kernel<{order}>", "kernel_ms": clip_s * 1e3, "kernel_share_of_step": clip_s * 1e3 / ms,
+                "kernel_ms_samples": int(ngen),
                 "peak_source": "DFMA microbenchmark measured live by bench.py (MEASURED_PEAKS.json has no FP64 entry)",
                 "algorithmic_flops_per_xcell": OPS_PER_XCELL[order],
                 "hbm": {"achieved_gbs": (npairs_total / world) * (CLIP_BYTES_PER_PAIR[order] + 0) / clip_s * 1e-9 if clip_s > 0 else None,
@@ -455,6 +476,8 @@ def run_gpu_arm(args):
             "data": "synthetic",
             "config": {"workload": workload_label(name), "nxgrid": nx_total, "candidate_pairs": npairs_total,
                        "sharding": f"{world * WPR} source-cell windows of equal candidate-pair count dealt round-robin to {world} ranks" if world > 1 else "single window",
+                       "step": ("xgb_plan_generate_async per step (+ device-side window counts and NCCL all-gather for N > 1), one "
+                                "xgb_plan_generate_finish after the timed region") if use_async else "blocking xgb_plan_generate per step",
                        "l2": "inputs larger than L2 (cell tables ~1.4 GB per rank are re-read every step)"},
             "clocks": clocks, "gpu_launches": launches_total,
             "e2e": {"value": nx_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -474,6 +497,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c768", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--async-steps", action="store_true",
+                    help="xgb_plan_generate_async per step + one generate_finish after the timed region instead of the blocking call")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="pieces of the end-to-end generate (download overlapped with compute)")
     ap.add_argument("--no-apply", action="store_true", help="skip the apply-GB/s leg (configs[1])")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (sizing runs: tens of GB of pinned memory)")

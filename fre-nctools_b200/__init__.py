@@ -75,6 +75,10 @@ def lib():
     L.xgb_plan_partition.argtypes = [vp, C.c_int, C.POINTER(C.c_longlong)]
     L.xgb_plan_set_src_windows.argtypes = [vp, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     L.xgb_plan_window_counts.argtypes = [vp, C.POINTER(C.c_longlong)]
+    L.xgb_plan_generate_async.argtypes = [vp, C.c_uint]
+    L.xgb_plan_generate_finish.restype = C.c_longlong
+    L.xgb_plan_generate_finish.argtypes = [vp]
+    L.xgb_plan_window_counts_device.argtypes = [vp, vp]
     L.xgb_plan_generate.restype = C.c_longlong
     L.xgb_plan_generate.argtypes = [vp, C.c_uint]
     L.xgb_plan_generate_to_host.restype = C.c_longlong
@@ -292,6 +296,23 @@ class XgridPlan:
         self.nxgrid = int(n)
         self.order = 2 if (opcode & CONSERVE_ORDER2) else 1
         return self.nxgrid
+
+    def generate_async(self, opcode):
+        """enqueue a generate on the plan's stream without waiting (buffers as sized by the last generate())"""
+        self._ck(self._L.xgb_plan_generate_async(self._p, int(opcode)))
+        self._pending_order = 2 if (opcode & CONSERVE_ORDER2) else 1
+
+    def generate_finish(self):
+        n = self._L.xgb_plan_generate_finish(self._p)
+        if n < 0:
+            raise XgridError(_err())
+        self.nxgrid = int(n)
+        self.order = self._pending_order
+        return self.nxgrid
+
+    def window_counts_device(self, counts):
+        """per-window exchange-cell counts of the window last enqueued -> int64 CUDA tensor (nwin entries), on the plan's stream"""
+        self._ck(self._L.xgb_plan_window_counts_device(self._p, counts.data_ptr()))
 
     def generate_to_host(self, opcode, bufs, nchunks=8):
         """generate + download overlapped (xgb_plan_generate_to_host): bufs = dict of preallocated host arrays (numpy or

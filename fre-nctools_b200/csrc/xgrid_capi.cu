@@ -432,8 +432,8 @@ extern "C" int xgb_plan_partition(xgb_plan* p, int nparts, long long* bounds)
 // clip and scatter are launched for the capacity of the pair buffer and read the true count there — and the result arrays
 // are sized for that capacity (nxgrid <= pairs).  Totals, window offsets and the error word come back through pinned memory
 // at the end; a buffer that turned out too small (first call, or a grid change) repeats the window with the sizes just
-// learnt.  Saves two stream drains per generate: ~0.05 ms, which is 5 % of an 8-GPU step.
-static long long generate_window_resident(xgb_plan* p, int order, const SrcMap& sm)
+// learnt.  Split in two so that xgb_plan_generate_async can enqueue a window without waiting for it.
+static int resident_enqueue(xgb_plan* p, int order, const SrcMap& sm, size_t cap, HeavyWork& hw)
 {
   const long long ns = sm.total();
   const double* mask = p->has_mask ? (const double*)p->mask.p : nullptr;
@@ -441,75 +441,69 @@ static long long generate_window_resident(xgb_plan* p, int order, const SrcMap& 
       p->pair_cnt.reserve((size_t)(ns + 1) * sizeof(uint32_t)) || p->out_off.reserve((size_t)(ns + 1) * sizeof(uint32_t)) ||
       p->scan_tmp.reserve(scan_tmp_bytes(ns)))
     return -1;
-  HeavyWork hw;
   if (heavy_work(p, ns, &hw)) return -1;
-  size_t cap = p->pairs_cap ? p->pairs_cap : (size_t)ns * 8 + (1u << 20);
-  unsigned long long npairs = 0, nx = 0;
-  for (int attempt = 0;; ++attempt) {
-    if (p->pairs.reserve(cap * sizeof(int2) + 16) || p->parea.reserve(cap * sizeof(double) + 16)) return -1;
-    if (order == 2 && (p->pclon.reserve(cap * sizeof(double) + 16) || p->pclat.reserve(cap * sizeof(double) + 16))) return -1;
-    const size_t ni = cap * sizeof(int) + 16, nd = cap * sizeof(double) + 16;
-    if (p->t_in.reserve(ni) || p->i_in.reserve(ni) || p->j_in.reserve(ni) || p->i_out.reserve(ni) || p->j_out.reserve(ni) ||
-        p->area.reserve(nd))
-      return -1;
-    if (order == 2 && (p->clon.reserve(nd) || p->clat.reserve(nd) || p->di.reserve(nd) || p->dj.reserve(nd))) return -1;
-    const unsigned long long* npairs_dev = &hw.ctl->total;
-    cudaEventRecord(p->ev[0], p->st);
-    cudaMemsetAsync(p->cnt.p, 0, (size_t)(ns + 1) * sizeof(uint32_t), p->st);
-    launch_candidates_single(p->src, sm, mask, p->pyr, p->rect, p->dst, (uint32_t*)p->pair_off.p, (uint32_t*)p->pair_cnt.p,
-                             (int2*)p->pairs.p, cap, (uint32_t*)p->cnt.p, hw, p->err_dev, p->st);
-    cudaEventRecord(p->ev[1], p->st);
-    cudaMemsetAsync(p->cnt.p, 0, (size_t)(ns + 1) * sizeof(uint32_t), p->st);
-    cudaEventRecord(p->ev[2], p->st);
-    launch_clip(order, p->src, p->dst, mask, (const int2*)p->pairs.p, cap, npairs_dev, sm,
-                (double*)p->parea.p, (double*)p->pclon.p, (double*)p->pclat.p, (uint32_t*)p->cnt.p, p->err_dev, p->st);
-    cudaEventRecord(p->ev[3], p->st);
-    launch_exclusive_scan((const uint32_t*)p->cnt.p, (uint32_t*)p->out_off.p, ns, p->total_dev + 1, p->scan_tmp.p, p->st);
-    cudaEventRecord(p->ev[4], p->st);
-    launch_scatter(order, (const int2*)p->pairs.p, cap, (const double*)p->parea.p, (const double*)p->pclon.p,
-                   (const double*)p->pclat.p, (const uint32_t*)p->pair_off.p, (const uint32_t*)p->pair_cnt.p, (const uint32_t*)p->out_off.p,
-                   (const TileDesc*)p->tiles_dev.p, (int)p->tiles.size(), sm, p->nx2,
-                   (int*)p->t_in.p, (int*)p->i_in.p, (int*)p->j_in.p, (int*)p->i_out.p, (int*)p->j_out.p,
-                   (double*)p->area.p, (double*)p->clon.p, (double*)p->clat.p, &hw, p->st, p->aux_st, p->fork_ev, p->join_ev, npairs_dev);
-    if (order == 2)
-      launch_order2_finalize(p->src, sm, (const uint32_t*)p->out_off.p, (const double*)p->area.p, (const double*)p->clon.p,
-                             (const double*)p->clat.p, (double*)p->di.p, (double*)p->dj.p, hw.list, &hw.ctl->nheavy, p->st,
-                             p->aux_st, p->fork_ev, p->join_ev);
-    cudaEventRecord(p->ev[5], p->st);
-    if (sm.nwin > 1) launch_publish_windows(p->win_host, p->out_off.p, sm, p->st);
-    launch_publish(p->total_host, &hw.ctl->total, 4, p->st);          // pair total (2 words), nheavy, pairs of the pyramid heavy path
-    launch_publish(p->total_host + 2, p->total_dev + 1, 2, p->st);    // exchange cells
-    launch_publish(p->err_host, p->err_dev, 1, p->st);
-    if (cudaStreamSynchronize(p->st) != cudaSuccess) {
-      xgb_set_error("xgrid generation failed: %s", cudaGetErrorString(cudaGetLastError()));
-      return -1;
-    }
-    const int e = *p->err_host;
-    if (e == kErrHeavyOverflow && attempt < 8) {
-      // the level-synchronous work lists were too small (coarse source on a fine curvilinear destination): grow and repeat
-      const unsigned heavy_pairs = ((const unsigned*)p->total_host)[3];
-      size_t want = (size_t)hw.cap * 2;
-      if ((size_t)heavy_pairs + heavy_pairs / 8 > want) want = (size_t)heavy_pairs + heavy_pairs / 8;
-      p->heavy_cap = want;
-      cudaMemsetAsync(p->err_dev, 0, sizeof(int), p->st);
-      if (heavy_work(p, ns, &hw)) return -1;
-      continue;
-    }
-    npairs = p->total_host[0];
-    if (npairs >= (1ull << 32)) { xgb_set_error("more than 2^32 candidate pairs in one window; shard the source cells"); return -1; }
-    if (npairs > cap) {
-      if (attempt > 9) { xgb_set_error("candidate search: pair buffers keep overflowing"); return -1; }
-      cap = (size_t)npairs + (size_t)npairs / 16 + 1024;
-      if (e) cudaMemsetAsync(p->err_dev, 0, sizeof(int), p->st);
-      continue;
-    }
-    if (e) { cudaMemsetAsync(p->err_dev, 0, sizeof(int), p->st); }
-    if (report_kernel_error(p, e, false)) return -1;
-    nx = p->total_host[2];
-    break;
+  if (p->pairs.reserve(cap * sizeof(int2) + 16) || p->parea.reserve(cap * sizeof(double) + 16)) return -1;
+  if (order == 2 && (p->pclon.reserve(cap * sizeof(double) + 16) || p->pclat.reserve(cap * sizeof(double) + 16))) return -1;
+  const size_t ni = cap * sizeof(int) + 16, nd = cap * sizeof(double) + 16;
+  if (p->t_in.reserve(ni) || p->i_in.reserve(ni) || p->j_in.reserve(ni) || p->i_out.reserve(ni) || p->j_out.reserve(ni) ||
+      p->area.reserve(nd))
+    return -1;
+  if (order == 2 && (p->clon.reserve(nd) || p->clat.reserve(nd) || p->di.reserve(nd) || p->dj.reserve(nd))) return -1;
+  const unsigned long long* npairs_dev = &hw.ctl->total;
+  cudaEventRecord(p->ev[0], p->st);
+  cudaMemsetAsync(p->cnt.p, 0, (size_t)(ns + 1) * sizeof(uint32_t), p->st);
+  launch_candidates_single(p->src, sm, mask, p->pyr, p->rect, p->dst, (uint32_t*)p->pair_off.p, (uint32_t*)p->pair_cnt.p,
+                           (int2*)p->pairs.p, cap, (uint32_t*)p->cnt.p, hw, p->err_dev, p->st);
+  cudaEventRecord(p->ev[1], p->st);
+  cudaMemsetAsync(p->cnt.p, 0, (size_t)(ns + 1) * sizeof(uint32_t), p->st);
+  cudaEventRecord(p->ev[2], p->st);
+  launch_clip(order, p->src, p->dst, mask, (const int2*)p->pairs.p, cap, npairs_dev, sm,
+              (double*)p->parea.p, (double*)p->pclon.p, (double*)p->pclat.p, (uint32_t*)p->cnt.p, p->err_dev, p->st);
+  cudaEventRecord(p->ev[3], p->st);
+  launch_exclusive_scan((const uint32_t*)p->cnt.p, (uint32_t*)p->out_off.p, ns, p->total_dev + 1, p->scan_tmp.p, p->st);
+  cudaEventRecord(p->ev[4], p->st);
+  launch_scatter(order, (const int2*)p->pairs.p, cap, (const double*)p->parea.p, (const double*)p->pclon.p,
+                 (const double*)p->pclat.p, (const uint32_t*)p->pair_off.p, (const uint32_t*)p->pair_cnt.p, (const uint32_t*)p->out_off.p,
+                 (const TileDesc*)p->tiles_dev.p, (int)p->tiles.size(), sm, p->nx2,
+                 (int*)p->t_in.p, (int*)p->i_in.p, (int*)p->j_in.p, (int*)p->i_out.p, (int*)p->j_out.p,
+                 (double*)p->area.p, (double*)p->clon.p, (double*)p->clat.p, &hw, p->st, p->aux_st, p->fork_ev, p->join_ev, npairs_dev);
+  if (order == 2)
+    launch_order2_finalize(p->src, sm, (const uint32_t*)p->out_off.p, (const double*)p->area.p, (const double*)p->clon.p,
+                           (const double*)p->clat.p, (double*)p->di.p, (double*)p->dj.p, hw.list, &hw.ctl->nheavy, p->st,
+                           p->aux_st, p->fork_ev, p->join_ev);
+  cudaEventRecord(p->ev[5], p->st);
+  if (sm.nwin > 1) launch_publish_windows(p->win_host, p->out_off.p, sm, p->st);
+  launch_publish(p->total_host, &hw.ctl->total, 4, p->st);          // pair total (2 words), nheavy, pairs of the pyramid heavy path
+  launch_publish(p->total_host + 2, p->total_dev + 1, 2, p->st);    // exchange cells
+  launch_publish(p->err_host, p->err_dev, 1, p->st);
+  return 0;
+}
+
+// after the stream has drained: 0 = the window is complete (*nx_out set, bookkeeping done), 1 = repeat with the grown
+// buffers (cap / heavy lists updated), -1 = error
+static int resident_evaluate(xgb_plan* p, const SrcMap& sm, size_t& cap, const HeavyWork& hw, int attempt, unsigned long long* nx_out)
+{
+  const int e = *p->err_host;
+  if (e) cudaMemsetAsync(p->err_dev, 0, sizeof(int), p->st);
+  if (e == kErrHeavyOverflow && attempt < 8) {
+    // the level-synchronous work lists were too small (coarse source on a fine curvilinear destination): grow and repeat
+    const unsigned heavy_pairs = ((const unsigned*)p->total_host)[3];
+    size_t want = (size_t)hw.cap * 2;
+    if ((size_t)heavy_pairs + heavy_pairs / 8 > want) want = (size_t)heavy_pairs + heavy_pairs / 8;
+    p->heavy_cap = want;
+    return 1;
   }
+  const unsigned long long npairs = p->total_host[0];
+  if (npairs >= (1ull << 32)) { xgb_set_error("more than 2^32 candidate pairs in one window; shard the source cells"); return -1; }
+  if (npairs > cap) {
+    if (attempt > 9) { xgb_set_error("candidate search: pair buffers keep overflowing"); return -1; }
+    cap = (size_t)npairs + (size_t)npairs / 16 + 1024;
+    return 1;
+  }
+  if (report_kernel_error(p, e, false)) return -1;
+  const unsigned long long nx = p->total_host[2];
   {                                  // later calls launch for this capacity: keep it close to what the window needs
-    const size_t tight = (size_t)npairs + (size_t)npairs / 16 + 1024;
+    const size_t tight = (size_t)npairs + (size_t)npairs / 64 + 1024;
     p->pairs_cap = tight < cap ? tight : cap;
   }
   p->npairs = npairs;
@@ -524,7 +518,25 @@ static long long generate_window_resident(xgb_plan* p, int order, const SrcMap& 
     p->phase_ms[k] = ms;
     p->phase_ms_sum[k] += ms;
   }
-  return (long long)nx;
+  *nx_out = nx;
+  return 0;
+}
+
+static long long generate_window_resident(xgb_plan* p, int order, const SrcMap& sm)
+{
+  size_t cap = p->pairs_cap ? p->pairs_cap : (size_t)sm.total() * 8 + (1u << 20);
+  for (int attempt = 0;; ++attempt) {
+    HeavyWork hw;
+    if (resident_enqueue(p, order, sm, cap, hw)) return -1;
+    if (cudaStreamSynchronize(p->st) != cudaSuccess) {
+      xgb_set_error("xgrid generation failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return -1;
+    }
+    unsigned long long nx = 0;
+    const int r = resident_evaluate(p, sm, cap, hw, attempt, &nx);
+    if (r < 0) return -1;
+    if (r == 0) return (long long)nx;
+  }
 }
 
 static long long generate_window(xgb_plan* p, int order, const SrcMap& sm, size_t base, size_t stream_cap)
@@ -647,6 +659,64 @@ extern "C" long long xgb_plan_generate(xgb_plan* p, unsigned int opcode)
   p->order = order;
   p->generates += 1;
   return p->nxgrid;
+}
+
+// xgb_plan_generate without the wait: the window is enqueued on the plan's stream with the buffer sizes the last completed
+// generate settled on (so one synchronous call has to come first), the result stays in HBM, per-window counts can be taken
+// on the device (xgb_plan_window_counts_device) and further work — the next window, a collective — queued behind it.
+// xgb_plan_generate_finish waits, checks what the kernels reported and returns the count; if a buffer turned out too small it
+// repeats the window synchronously, so the result is always complete afterwards.
+extern "C" int xgb_plan_generate_async(xgb_plan* p, unsigned int opcode)
+{
+  if (!p || !p->have_src || !p->have_dst) { xgb_set_error("xgb_plan_generate_async: set source and destination grids first"); return 1; }
+  if (!(opcode & (XGB_CONSERVE_ORDER1 | XGB_CONSERVE_ORDER2)) || (opcode & XGB_GREAT_CIRCLE)) {
+    xgb_set_error("xgb_plan_generate_async: needs CONSERVE_ORDER1/2 (no great circle)");
+    return 1;
+  }
+  if (p->pairs_cap == 0) { xgb_set_error("xgb_plan_generate_async: run xgb_plan_generate once first (it sizes the buffers)"); return 1; }
+  CU_OK(cudaSetDevice(p->device));
+  p->pending_order = (opcode & XGB_CONSERVE_ORDER2) ? 2 : 1;
+  p->pending_map = p->map;
+  p->pending_cap = p->pairs_cap;
+  if (resident_enqueue(p, p->pending_order, p->pending_map, p->pending_cap, p->pending_hw)) return 1;
+  p->pending = true;
+  return 0;
+}
+
+extern "C" long long xgb_plan_generate_finish(xgb_plan* p)
+{
+  if (!p || !p->pending) { xgb_set_error("xgb_plan_generate_finish: nothing pending"); return -1; }
+  if (cudaSetDevice(p->device) != cudaSuccess) { xgb_set_error("cudaSetDevice failed"); return -1; }
+  p->pending = false;
+  if (cudaStreamSynchronize(p->st) != cudaSuccess) {
+    xgb_set_error("xgrid generation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return -1;
+  }
+  unsigned long long nx = 0;
+  size_t cap = p->pending_cap;
+  const int r = resident_evaluate(p, p->pending_map, cap, p->pending_hw, 0, &nx);
+  if (r < 0) return -1;
+  long long n = (long long)nx;
+  if (r == 1) {                                  // a buffer was too small: repeat the window the synchronous way
+    p->pairs_cap = cap;
+    n = generate_window_resident(p, p->pending_order, p->pending_map);
+    if (n < 0) return -1;
+  }
+  p->nxgrid = n;
+  p->order = p->pending_order;
+  p->generates += 1;
+  return n;
+}
+
+// exchange cells per window of the window last enqueued, written to a device array on the plan's stream (nwin int64 values):
+// the one exchange of the multi-GPU path (all-gather of the counts) then needs no trip through the host
+extern "C" int xgb_plan_window_counts_device(xgb_plan* p, long long* counts_dev)
+{
+  if (!p || !counts_dev || !p->have_src) { xgb_set_error("xgb_plan_window_counts_device: bad arguments"); return 1; }
+  CU_OK(cudaSetDevice(p->device));
+  const SrcMap& sm = p->pending ? p->pending_map : p->map;
+  launch_window_counts((const uint32_t*)p->out_off.p, sm, p->total_dev + 1, counts_dev, p->st);
+  return 0;
 }
 
 // Generate the current window in `nchunks` consecutive pieces of source cells and copy every piece to the caller's

@@ -117,6 +117,7 @@ void launch_publish(void* host_dst, const void* dev_src, int nwords, cudaStream_
 void launch_latlon_fill(int nlon, int nlat, double lonbegin, double lonend, double latbegin, double latend, double* lon, double* lat,
                         cudaStream_t st);
 void launch_rect_setup(const CellSet& dst, int nx, int ny, double* store, unsigned char* row_ok, int* invalid, RectDst* out, cudaStream_t st);
+void launch_window_counts(const uint32_t* out_off, const SrcMap& sm, const unsigned long long* total, long long* counts, cudaStream_t st);
 void launch_publish_windows(void* host_dst, const void* out_off, const SrcMap& sm, cudaStream_t st);
 // exclusive prefix sum of n uint32 counts; out has n+1 entries (out[n] = total, must fit 32 bits);
 // the 64-bit total is also written to *total_dev.  tmp must hold scan_tmp_bytes(n).

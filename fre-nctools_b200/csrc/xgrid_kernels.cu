@@ -1500,6 +1500,23 @@ void launch_publish_windows(void* host_dst, const void* out_off, const SrcMap& s
   publish_windows_kernel<<<1, 64, 0, st>>>((unsigned*)host_dst, (const unsigned*)out_off, sm);
 }
 
+// exchange cells per window, on the device: differences of out_off at the window boundaries, the last one against the total
+__global__ void window_counts_kernel(const unsigned* __restrict__ out_off, SrcMap sm, const unsigned long long* __restrict__ total,
+                                     long long* __restrict__ counts)
+{
+  for (int w = threadIdx.x; w < sm.nwin; w += blockDim.x) {
+    const unsigned long long lo = (w == 0) ? 0ull : out_off[sm.cum[w]];
+    const unsigned long long hi = (w + 1 == sm.nwin) ? *total : out_off[sm.cum[w + 1]];
+    counts[w] = (long long)(hi - lo);
+  }
+}
+
+void launch_window_counts(const uint32_t* out_off, const SrcMap& sm, const unsigned long long* total, long long* counts, cudaStream_t st)
+{
+  ++g_launches;
+  window_counts_kernel<<<1, 64, 0, st>>>(out_off, sm, total, counts);
+}
+
 void launch_publish(void* host_dst, const void* dev_src, int nwords, cudaStream_t st)
 {
   ++g_launches;

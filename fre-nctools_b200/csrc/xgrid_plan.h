@@ -59,6 +59,13 @@ struct xgb_plan {
   unsigned long long npairs = 0;
   int order = 0;
 
+  // a window enqueued by xgb_plan_generate_async and not yet finished
+  bool pending = false;
+  int pending_order = 0;
+  size_t pending_cap = 0;
+  xgb::SrcMap pending_map{};
+  xgb::HeavyWork pending_hw{};
+
   int* err_dev = nullptr;
   int* err_host = nullptr;                    // pinned
   unsigned* win_host = nullptr;               // pinned: out_off at window boundaries

@@ -140,6 +140,15 @@ int xgb_plan_partition(xgb_plan *p, int nparts, long long *bounds);
  * XGB_CONSERVE_ORDER2, optionally | XGB_GREAT_CIRCLE.  Returns nxgrid (>= 0) or -1.
  * Results stay in HBM, in the reference's emission order (tile, j_in, i_in, then j_out*nx+i_out). */
 long long xgb_plan_generate(xgb_plan *p, unsigned int opcode);
+/* The same without the wait.  xgb_plan_generate_async enqueues the window on the plan's stream with the buffer sizes the
+ * last completed xgb_plan_generate settled on (one synchronous call has to come first); the result stays in HBM and more
+ * work can be queued behind it.  xgb_plan_generate_finish waits, checks what the kernels reported and returns the count
+ * (a buffer that turned out too small makes it repeat the window synchronously).  xgb_plan_window_counts_device writes the
+ * per-window exchange-cell counts of the window last enqueued to a device array (nwin int64) on the plan's stream, so the
+ * multi-GPU count all-gather needs no trip through the host. */
+int xgb_plan_generate_async(xgb_plan *p, unsigned int opcode);
+long long xgb_plan_generate_finish(xgb_plan *p);
+int xgb_plan_window_counts_device(xgb_plan *p, long long *counts_dev);
 
 /* The same for callers that want the result in HOST arrays (what setup_conserve_interp's callers need,
  * conserve_interp.c:236-257): the window is generated in nchunks consecutive pieces of source cells and each piece is

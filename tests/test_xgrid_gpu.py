@@ -423,3 +423,38 @@ def test_destination_grid_built_on_the_device_equals_the_uploaded_one(pkg):
         assert n == want["nxgrid"] and n > 0
         for key in got:
             assert np.array_equal(got[key], want[key]), key
+
+
+def test_generate_async_queues_windows_and_finish_returns_the_same_result(pkg):
+    """xgb_plan_generate_async / _finish: several windows queued back to back without a host wait leave the same result as the
+    blocking call; per-window counts taken on the device equal the host's; a call before any blocking generate is refused"""
+    import torch
+    lonc, latc = pkg.cubed_sphere_grid(32)
+    plan = pkg.XgridPlan(0)
+    plan.set_dst_latlon(180, 90)
+    plan.set_src(lonc, latc)
+    with pytest.raises(pkg.XgridError):
+        plan.generate_async(pkg.CONSERVE_ORDER2)
+    b = plan.partition(6)
+    wins = [(b[0], b[1]), (b[2], b[3]), (b[5], b[6])]
+    plan.set_src_windows(wins)
+    n = plan.generate(pkg.CONSERVE_ORDER2)
+    want = plan.result_host(); wc = plan.window_counts()
+    dev_counts = torch.zeros(len(wins), dtype=torch.int64, device="cuda:0")
+    for _ in range(4):
+        plan.generate_async(pkg.CONSERVE_ORDER2)
+        plan.window_counts_device(dev_counts)
+    assert plan.generate_finish() == n
+    got = plan.result_host()
+    torch.cuda.synchronize()
+    assert dev_counts.tolist() == wc == plan.window_counts() and sum(wc) == n
+    for k in want:
+        assert np.array_equal(got[k], want[k]), k
+    # a larger window after a small one: the buffers sized for the small one overflow, finish repeats the window by itself
+    plan.set_src_window(b[0], b[1])
+    small = plan.generate(pkg.CONSERVE_ORDER1)
+    plan.set_src_window(b[0], b[6])
+    plan.generate_async(pkg.CONSERVE_ORDER1)
+    full = plan.generate_finish()
+    assert full > small and full == plan.generate(pkg.CONSERVE_ORDER1)
+    plan.close()
