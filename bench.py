@@ -314,9 +314,9 @@ def run_gpu_arm(args):
 
     # An asynchronous step enqueues one generate on the plan's stream (xgb_plan_generate_async) and, for N > 1, the path's one exchange behind
     # it: per-window counts taken on the device, all-gathered over NCCL -> global offsets of every piece.  Nothing waits for the
-    # host inside the timed region; the count comes back with generate_finish() after it.  Opt-in (--async-steps): the default
-    # step is the blocking xgb_plan_generate (one host synchronisation per step).
-    use_async = args.async_steps
+    # host inside the timed region; the count comes back with generate_finish() after it.  Default for N > 1 (2.42 -> 2.32 ms at
+    # N = 2); at N = 1 the blocking xgb_plan_generate (one host synchronisation per step) measures the same and stays the default.
+    use_async = args.async_steps or (world > 1 and not args.sync_steps)
     plan.generate(opcode)                           # sizes the buffers for this rank's windows (untimed)
 
     def step():
@@ -499,6 +499,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--async-steps", action="store_true",
                     help="xgb_plan_generate_async per step + one generate_finish after the timed region instead of the blocking call")
+    ap.add_argument("--sync-steps", action="store_true", help="blocking xgb_plan_generate per step also for N > 1 (default there: asynchronous steps)")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="pieces of the end-to-end generate (download overlapped with compute)")
     ap.add_argument("--no-apply", action="store_true", help="skip the apply-GB/s leg (configs[1])")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (sizing runs: tens of GB of pinned memory)")
