@@ -913,10 +913,14 @@ clip_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const int
   const unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
   // npairs_dev: the candidate search's total, still unseen by the host (single-sync generate); npairs is then the capacity
   // of the pair buffer and bounds the launch
-  if (npairs_dev) { const unsigned long long nd = *npairs_dev; if (nd < npairs) npairs = nd; }
-  if (blockIdx.x * (unsigned long long)blockDim.x >= npairs) return;   // whole block beyond the list (capacity-sized launch)
-  const bool valid = p < npairs;                                  // no per-thread exit: the warp reconverges explicitly below
-  const int2 pr = valid ? pairs[p] : make_int2(0, 0);
+  // Single-sync generate (npairs_dev != nullptr): the launch covers the pair buffer's capacity and the entries past the true
+  // count hold the sentinel (-1, -1) written by pad_pairs_kernel, so no thread has to wait for the count before it can
+  // fetch its pair (a dependent load at the head of every block cost 0.06 ms).
+  const bool in_launch = p < npairs;
+  int2 pr = in_launch ? pairs[p] : make_int2(-1, -1);
+  const bool valid = in_launch && pr.x >= 0;                      // no per-thread exit: the warp reconverges explicitly below
+  if (!valid) pr = make_int2(0, 0);
+  (void)npairs_dev;
   const long long s = smap.cell(pr.x), d = pr.y;
   const int n1 = valid ? src.nv[s] : 0, n2 = valid ? dst.nv[d] : 0;
   const double s_xavg = valid ? src.xavg[s] : 0.0;
@@ -1048,6 +1052,16 @@ clip_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const int
   }
 }
 
+// sentinel pairs from the true count (on the device) to the end of the launch the clip kernel will get
+__global__ void pad_pairs_kernel(int2* __restrict__ pairs, const unsigned long long* __restrict__ npairs_dev, unsigned long long cap)
+{
+  unsigned long long n = *npairs_dev;
+  if (n > cap) n = 0;            // the buffer overflowed (segments straddling its end were dropped): blank everything, the host repeats
+  for (unsigned long long p = n + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p < cap;
+       p += (unsigned long long)gridDim.x * blockDim.x)
+    pairs[p] = make_int2(-1, -1);
+}
+
 void launch_clip(int order, const CellSet& src, const CellSet& dst, const double* mask,
                  const int2* pairs, unsigned long long npairs, const unsigned long long* npairs_dev, const SrcMap& sm,
                  double* parea, double* pclon, double* pclat, uint32_t* cnt, int* err, cudaStream_t st)
@@ -1055,6 +1069,7 @@ void launch_clip(int order, const CellSet& src, const CellSet& dst, const double
   if (npairs == 0) return;
   const unsigned blocks = (unsigned)((npairs + kClipThreads - 1) / kClipThreads);
   ++g_launches;
+  if (npairs_dev) { ++g_launches; pad_pairs_kernel<<<148, 256, 0, st>>>(const_cast<int2*>(pairs), npairs_dev, npairs); }
   if (order == 2) clip_kernel<2><<<blocks, kClipThreads, 0, st>>>(src, dst, mask, pairs, npairs, npairs_dev, sm, parea, pclon, pclat, cnt, err);
   else            clip_kernel<1><<<blocks, kClipThreads, 0, st>>>(src, dst, mask, pairs, npairs, npairs_dev, sm, parea, pclon, pclat, cnt, err);
 }
