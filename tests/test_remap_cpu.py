@@ -181,3 +181,27 @@ def test_scipy_reads_what_the_product_writes_and_errors_are_loud(pkg, reflib, tm
     open(h5, "wb").write(b"\x89HDF\r\n\x1a\n" + bytes(64))
     assert L.xgb_remap_size(h5.encode()) < 0 and b"netCDF-4/HDF5" in L.xgb_last_error()
     assert L.xgb_remap_size(str(tmp_path / "missing.nc").encode()) < 0 and b"cannot open" in L.xgb_last_error()
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_golden_remap_files_round_trip(pkg, order):
+    """tests/golden/remap_c8_20x10_order*.nc (the reference's WRITE branch, tests/golden/make_remap_golden.py; no reference needed
+    here): read with xgb_remap_read, written again with xgb_remap_write -> the same bytes; scipy reads the same values"""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"remap_c8_20x10_order{order}.nc")
+    gold = open(path, "rb").read()
+    L = pkg.lib()
+    x = _read(pkg, path, order)
+    g = netcdf_file(path, "r", mmap=False)
+    assert g.dimensions["ncells"] == x["nxgrid"] and np.array_equal(g.variables["tile1_cell"][:, 0], x["i_in"] + 1)
+    area_disk = np.ascontiguousarray(g.variables["xgrid_area"][:], dtype=np.float64)     # native byte order
+    g.close()
+    assert np.allclose(x["area"], area_disk, rtol=4e-16, atol=0)       # (a / 4 pi R^2) * 4 pi R^2 on read, like the reference
+    x["area"] = area_disk
+    assert L.xgb_set_nc_format(b"64bit_offset") == 0
+    out = path + ".tmp"
+    try:
+        _write(pkg, out, order, x)
+        assert open(out, "rb").read() == gold
+    finally:
+        if os.path.exists(out):
+            os.remove(out)
