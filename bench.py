@@ -113,41 +113,70 @@ _G = {}
 
 def _band_worker(args):
     import xgtest
-    jsc, jec, order, use_ref = args
+    jsc, jec, order, use_ref, keep = args
     lonc, latc, lon2, lat2 = _G["grids"]
     t0 = time.perf_counter()
     if use_ref:
         r = xgtest.ref_setup(lonc, latc, lon2, lat2, order, jsc=jsc, jec=jec)
     else:
         r = xgtest.oracle_setup(lonc, latc, lon2[jsc:jec + 2], lat2[jsc:jec + 2], order)
-    return r["nxgrid"], time.perf_counter() - t0
+    dt = time.perf_counter() - t0
+    lists = None
+    if keep:                      # the band's list, rows made global, for the parity check against the GPU's list
+        lists = {k: r[k] for k in ("t_in", "i_in", "j_in", "i_out", "area")}
+        lists["j_out"] = r["j_out"] + jsc
+    return r["nxgrid"], dt, lists
 
 
-def cpu_sample(name, rows_per_worker, cores, pool=None):
+def cpu_sample(name, rows_per_worker, cores, pool=None, keep=False):
     """One bounded sample: `cores` destination bands of rows_per_worker rows, evenly spread over the
     latitudes, each run by one process exactly as a fregrid_parallel rank owning that band would
-    (fregrid_util.c:592-603 layout {1,npes}).  Returns (xcells, wall seconds, kind)."""
+    (fregrid_util.c:592-603 layout {1,npes}).  Returns (xcells, wall seconds, kind[, per-band lists])."""
     import xgtest
     n, nlon, nlat, order = WORKLOADS[name]
     use_ref = xgtest.ref_lib() is not None
     rows_per_worker = max(1, min(rows_per_worker, nlat // cores))
     starts = [int((k + 0.5) * nlat / cores) for k in range(cores)]
-    jobs = [(min(s, nlat - rows_per_worker), min(s, nlat - rows_per_worker) + rows_per_worker - 1, order, use_ref) for s in starts]
+    jobs = [(min(s, nlat - rows_per_worker), min(s, nlat - rows_per_worker) + rows_per_worker - 1, order, use_ref, keep) for s in starts]
     t0 = time.perf_counter()
     res = pool.map(_band_worker, jobs, chunksize=1)
     wall = time.perf_counter() - t0
-    return sum(r[0] for r in res), wall, ("reference" if use_ref else "port")
+    out = (sum(r[0] for r in res), wall, ("reference" if use_ref else "port"))
+    return out + ([(j[0], j[1], r[2]) for j, r in zip(jobs, res)],) if keep else out
+
+
+def parity_check_bands(gpu, bands):
+    """the GPU's exchange-grid list (host dict) restricted to each band's destination rows must be the band's list the CPU
+    reference produced: same cells in the same order, areas bit-identical when the host libm is the reference's (else 1e-9).
+    tile1_distance of a band run is not comparable (its per-source-cell sums only see the band).  -> cells compared"""
+    import xgtest
+    exact = xgtest.libm_matches_ref_trig()
+    n = 0
+    for jsc, jec, b in bands:
+        m = (gpu["j_out"] >= jsc) & (gpu["j_out"] <= jec)
+        if int(m.sum()) != b["area"].size:
+            raise SystemExit(f"bench.py: PARITY FAILURE rows {jsc}..{jec}: GPU {int(m.sum())} cells, CPU reference {b['area'].size}")
+        for k in ("t_in", "i_in", "j_in", "i_out", "j_out"):
+            if not np.array_equal(gpu[k][m], b[k]):
+                raise SystemExit(f"bench.py: PARITY FAILURE rows {jsc}..{jec}: {k} differs from the CPU reference")
+        ok = np.array_equal(gpu["area"][m], b["area"]) if exact else bool(np.max(np.abs(gpu["area"][m] - b["area"]) / b["area"]) < 1e-9)
+        if not ok:
+            raise SystemExit(f"bench.py: PARITY FAILURE rows {jsc}..{jec}: xgrid_area differs from the CPU reference")
+        n += b["area"].size
+    return n
 
 
 def make_pool(name, cores):
+    """the CPU legs build their grids WITHOUT the product library: the reference's own cubed-sphere generator (oracle/_ref) and
+    get_output_grid_by_size restated in numpy (xgtest.latlon_grid_np).  Only when oracle/_ref was never built (then the CPU leg
+    runs the oracle port) does the source grid come from the product's host-side generator."""
     import xgtest
-    pkg = xgtest.package()
     n, nlon, nlat, order = WORKLOADS[name]
     if xgtest.ref_lib() is not None:
         lonc, latc = xgtest.ref_cubed_sphere(n)           # the reference's own generator
     else:
-        lonc, latc = pkg.cubed_sphere_grid(n)
-    lon2, lat2 = pkg.latlon_grid(nlon, nlat)
+        lonc, latc = xgtest.package().cubed_sphere_grid(n)
+    lon2, lat2 = xgtest.latlon_grid_np(nlon, nlat)
     _G["grids"] = (lonc, latc, lon2, lat2)
     ctx = mp.get_context("fork")                          # grids are inherited copy-on-write
     return ctx.Pool(cores)
@@ -254,13 +283,15 @@ def apply_leg(pkg, torch, dist, rank, world, local, steps, warmup):
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    gbs = bytes_step / (ms * 1e-3) * 1e-9
+    gbs = bytes_step / (ms * 1e-3) * 1e-9             # whole job, all ranks
+    gbs_gpu = gbs / world                              # what one GPU's memory system delivers: the roofline compares THIS with one GPU's peak
     return {"workload": f"C{ni} -> {nlon}x{nlat} conserve_order2 remap (grad_c2l + apply) of {B} field-levels "
                         f"({APPLY_CFG['levels']} levels x {APPLY_CFG['times']} times), nxgrid {nx}",
             "metric": "apply_GB_per_sec", "value": gbs, "unit": "GB/s (algorithmic bytes)", "ms_per_step": ms,
             "field_levels_per_sec": B / (ms * 1e-3), "algorithmic_bytes_per_step": int(bytes_step), "gpu_launches_per_step": int(launches),
-            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s", "kernel": "apply_kernel<2> + grad_c2l_kernel"},
+            "roofline": {"bound": "hbm", "achieved": gbs_gpu, "peak": hbm_peak, "unit": "GB/s per GPU", "frac": gbs_gpu / hbm_peak,
+                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s", "kernel": "apply_packed_kernel + grad_c2l_kernel",
+                         "note": "per GPU: whole-job algorithmic GB/s divided by the number of ranks, against ONE GPU's measured HBM peak"},
             "e2e": {"value": bytes_step / (e2e_ms * 1e-3) * 1e-9, "unit": "GB/s (algorithmic bytes)", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(h_in.numel() * 8 * world), "d2h_bytes_per_step": int(h_out.numel() * 8 * world)},
             "sharding": f"{B} field-levels dealt round-robin to {world} rank(s); every rank holds the whole exchange grid"}
@@ -269,6 +300,18 @@ def apply_leg(pkg, torch, dist, rank, world, local, steps, warmup):
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
+def list_checksum(torch, r, n, nlon, order):
+    """order-independent 64-bit sums over a device-resident exchange-grid list (plan.result_device()): count, cell-pair keys,
+    bit patterns of xgrid_area and tile1_distance.  The pieces of an N-GPU run must add up to the single-GPU list's sums."""
+    s = (r["t_in"].to(torch.int64) * (n * n) + r["j_in"].to(torch.int64) * n + r["i_in"].to(torch.int64))
+    d = r["j_out"].to(torch.int64) * nlon + r["i_out"].to(torch.int64)
+    out = [torch.tensor(s.numel(), dtype=torch.int64, device=s.device), (s * 1315423911 + d * 2654435761).sum(),
+           r["area"].view(torch.int64).sum()]
+    if order == 2:
+        out += [r["di"].view(torch.int64).sum(), r["dj"].view(torch.int64).sum()]
+    return torch.stack(out)
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -364,6 +407,26 @@ def run_gpu_arm(args):
         if world > 1:
             assert int(counts.sum().item()) > 0 and plan.window_counts() == mine.tolist()
     clocks = sampler.stop() if rank == 0 else None
+    # ---- N > 1: the ranks' pieces against the single-GPU list (untimed).  Every rank sums its piece; rank 0 then generates the
+    # WHOLE problem on its own GPU (one window) and the all-reduced sums of the pieces must equal its sums exactly: same cells,
+    # same areas, same tile1_distance, nothing lost or duplicated at the window boundaries.
+    multi_parity = None
+    if world > 1:
+        mine_sum = list_checksum(torch, plan.result_device(), n, nlon, order)
+        dist.all_reduce(mine_sum, op=dist.ReduceOp.SUM)
+        whole = torch.zeros_like(mine_sum)
+        if rank == 0:
+            plan.set_src_window(0, plan.ncell_src)
+            plan.generate(opcode)
+            whole = list_checksum(torch, plan.result_device(), n, nlon, order)
+            set_windows()
+            plan.generate(opcode)
+        dist.broadcast(whole, src=0)
+        if not torch.equal(whole, mine_sum):
+            raise SystemExit(f"bench.py: PARITY FAILURE: the {world} ranks' pieces do not add up to the single-GPU list "
+                             f"(pieces {mine_sum.tolist()} vs whole {whole.tolist()})")
+        multi_parity = {"checked_xcells": int(whole[0].item()), "against": "single-GPU list on rank 0: count, cell-pair keys, "
+                        "xgrid_area and tile1_distance bit patterns (64-bit sums)", "equal": True}
     ms = e0.elapsed_time(e1) / args.steps
     launches = pkg.kernel_launches() - launches0
     _, phase_sum, ngen = plan.phase_ms()
@@ -456,20 +519,26 @@ def run_gpu_arm(args):
                 "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": traffic,
                 "kernel": f"clip_kernel<{order}>", "kernel_ms": clip_s * 1e3, "kernel_share_of_step": clip_s * 1e3 / ms,
                 "kernel_ms_samples": int(ngen),
-                "peak_source": "DFMA microbenchmark measured live by bench.py (MEASURED_PEAKS.json has no FP64 entry)",
+                "peak_source": "builder-measured: register-resident DFMA microbenchmark run live by bench.py (csrc/peak_probe.cu); MEASURED_PEAKS.json "
+                               "has no FP64 entry and the profiling guide states no FP64 fallback.  The path is compiled -fmad=false (bit-exact "
+                               "predicates), so apart from the explicit fma() of the sin/cos routines no DFMA is issued: the reachable ceiling is about half this peak",
                 "algorithmic_flops_per_xcell": OPS_PER_XCELL[order],
                 "hbm": {"achieved_gbs": (npairs_total / world) * (CLIP_BYTES_PER_PAIR[order] + 0) / clip_s * 1e-9 if clip_s > 0 else None,
                         "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
     phases = {kk: vv / max(ngen, 1) for kk, vv in phase_sum.items()}
 
     cpu = None
+    parity_checked = 0
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         pool = make_pool(name, cores)
-        x, tsec, kind = cpu_sample(name, 2, cores, pool)
+        x, tsec, kind, bands = cpu_sample(name, 2, cores, pool, keep=True)
         pool.close()
         cpu = {"value": x / tsec, "unit": UNIT, "cores": cores, "kind": kind,
                "sample": f"{cores} destination row bands x 2 rows of {nlat} (evenly spaced), all 6 source tiles, one process per band: {x} xcells in {tsec:.1f} s"}
+        # the CPU sample is also the checker: the end-to-end host result restricted to the sampled rows must BE the CPU lists
+        gpu_host = {kk: hb[kk].numpy()[:k] for kk in ("t_in", "i_in", "j_in", "i_out", "j_out", "area")}
+        parity_checked = parity_check_bands(gpu_host, bands)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -483,7 +552,8 @@ def run_gpu_arm(args):
             "e2e": {"value": nx_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "api": f"set_dst + set_src (pinned host grids) + xgb_plan_generate_to_host in {args.e2e_chunks} pieces (pinned host result)"},
-            "roofline": roofline, "phase_ms": phases, "per_rank": per_rank, "cpu_baseline": cpu, "apply": apply}
+            "roofline": roofline, "phase_ms": phases, "per_rank": per_rank, "cpu_baseline": cpu, "apply": apply,
+            "parity_checked_xcells": parity_checked, "multi_gpu_parity": multi_parity}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

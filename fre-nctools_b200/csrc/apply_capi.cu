@@ -76,7 +76,7 @@ static int kernel_errors(xgb_plan* p)
   if (e == 0) return 0;
   cudaMemsetAsync(p->err_dev, 0, sizeof(int), p->st);
   const char* msg = "internal kernel error";
-  if (e & kErrApplyIndex) msg = "conserve_interp: exchange-grid entry outside the source mosaic";
+  if (e & kErrApplyIndex) msg = "conserve_interp: exchange-grid entry outside the source mosaic or the output tile (does the remap file belong to these grids?)";
   else if (e & kErrMonotoneMax) msg = " xdata is greater than f_bar_max ";     // conserve_interp.c:693
   else if (e & kErrMonotoneMin) msg = " xdata is less than f_bar_min ";        // conserve_interp.c:707
   else if (e & kErrAreaMissing) msg = "conserve_interp: data is not missing but area is missing";   // :578, :772
@@ -126,10 +126,10 @@ static int build_csr(xgb_plan* p, xgb_apply_state* a)
     return 1;
   if (a->has_dist && (a->c_di.reserve(nn * 8) || a->c_dj.reserve(nn * 8))) return 1;
   CU_OK(cudaMemsetAsync(a->cursor.p, 0, (size_t)(ndst + 1) * 4, p->st));
-  launch_dst_count(n, a->i_out, a->j_out, a->nx2, (uint32_t*)a->cursor.p, p->st);
+  launch_dst_count(n, a->i_out, a->j_out, a->nx2, a->ny2, (uint32_t*)a->cursor.p, p->err_dev, p->st);
   launch_exclusive_scan((const uint32_t*)a->cursor.p, (uint32_t*)a->off.p, ndst, p->total_dev, a->scan_tmp.p, p->st);
   CU_OK(cudaMemsetAsync(a->cursor.p, 0, (size_t)(ndst + 1) * 4, p->st));
-  launch_dst_fill(n, a->i_out, a->j_out, a->nx2, (const uint32_t*)a->off.p, (uint32_t*)a->cursor.p, (uint32_t*)a->perm.p, p->st);
+  launch_dst_fill(n, a->i_out, a->j_out, a->nx2, a->ny2, (const uint32_t*)a->off.p, (uint32_t*)a->cursor.p, (uint32_t*)a->perm.p, p->st);
   a->csr.off = (const uint32_t*)a->off.p;
   a->csr.perm = (const uint32_t*)a->perm.p;
   a->csr.cell = (int*)a->c_cell.p; a->csr.hidx = (int*)a->c_hidx.p; a->csr.area = (double*)a->c_area.p;

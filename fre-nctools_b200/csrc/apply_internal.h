@@ -41,8 +41,8 @@ struct GradTile {
   const double *dx, *dy, *area, *edge_w, *edge_e, *edge_s, *edge_n, *en_n, *en_e, *vlon, *vlat;
 };
 
-void launch_dst_count(long long n, const int* i_out, const int* j_out, int nx2, uint32_t* cnt, cudaStream_t st);
-void launch_dst_fill(long long n, const int* i_out, const int* j_out, int nx2, const uint32_t* off, uint32_t* cursor,
+void launch_dst_count(long long n, const int* i_out, const int* j_out, int nx2, int ny2, uint32_t* cnt, int* err, cudaStream_t st);
+void launch_dst_fill(long long n, const int* i_out, const int* j_out, int nx2, int ny2, const uint32_t* off, uint32_t* cursor,
                      uint32_t* perm, cudaStream_t st);
 void launch_dst_sort_gather(long long ndst, const uint32_t* off, uint32_t* perm, const int* t_in, const int* i_in, const int* j_in,
                             const double* area, const double* di, const double* dj, const ApplyTile* tiles, int ntiles,

@@ -21,19 +21,27 @@ extern long long g_launches;
 // =============================================================================================
 // destination-major regrouping
 // =============================================================================================
+// A list entry that names a destination cell outside the tile (a stale remap file written for another output grid) is
+// dropped and reported (kErrApplyIndex), never counted or written.
 __global__ void __launch_bounds__(256)
-dst_count_kernel(long long n, const int* __restrict__ i_out, const int* __restrict__ j_out, int nx2, uint32_t* __restrict__ cnt)
+dst_count_kernel(long long n, const int* __restrict__ i_out, const int* __restrict__ j_out, int nx2, int ny2, uint32_t* __restrict__ cnt,
+                 int* err)
 {
-  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
-    atomicAdd(&cnt[(long long)j_out[k] * nx2 + i_out[k]], 1u);
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+    const int i = i_out[k], j = j_out[k];
+    if (i < 0 || i >= nx2 || j < 0 || j >= ny2) { atomicOr(err, kErrApplyIndex); continue; }
+    atomicAdd(&cnt[(long long)j * nx2 + i], 1u);
+  }
 }
 
 __global__ void __launch_bounds__(256)
-dst_fill_kernel(long long n, const int* __restrict__ i_out, const int* __restrict__ j_out, int nx2,
+dst_fill_kernel(long long n, const int* __restrict__ i_out, const int* __restrict__ j_out, int nx2, int ny2,
                 const uint32_t* __restrict__ off, uint32_t* __restrict__ cursor, uint32_t* __restrict__ perm)
 {
   for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
-    const long long d = (long long)j_out[k] * nx2 + i_out[k];
+    const int i = i_out[k], j = j_out[k];
+    if (i < 0 || i >= nx2 || j < 0 || j >= ny2) continue;         // reported by dst_count_kernel
+    const long long d = (long long)j * nx2 + i;
     perm[off[d] + atomicAdd(&cursor[d], 1u)] = (uint32_t)k;
   }
 }
@@ -68,19 +76,19 @@ dst_sort_gather_kernel(long long ndst, const uint32_t* __restrict__ off, uint32_
   }
 }
 
-void launch_dst_count(long long n, const int* i_out, const int* j_out, int nx2, uint32_t* cnt, cudaStream_t st)
+void launch_dst_count(long long n, const int* i_out, const int* j_out, int nx2, int ny2, uint32_t* cnt, int* err, cudaStream_t st)
 {
   if (n <= 0) return;
   ++g_launches;
-  dst_count_kernel<<<148 * 8, 256, 0, st>>>(n, i_out, j_out, nx2, cnt);
+  dst_count_kernel<<<148 * 8, 256, 0, st>>>(n, i_out, j_out, nx2, ny2, cnt, err);
 }
 
-void launch_dst_fill(long long n, const int* i_out, const int* j_out, int nx2, const uint32_t* off, uint32_t* cursor,
+void launch_dst_fill(long long n, const int* i_out, const int* j_out, int nx2, int ny2, const uint32_t* off, uint32_t* cursor,
                      uint32_t* perm, cudaStream_t st)
 {
   if (n <= 0) return;
   ++g_launches;
-  dst_fill_kernel<<<148 * 8, 256, 0, st>>>(n, i_out, j_out, nx2, off, cursor, perm);
+  dst_fill_kernel<<<148 * 8, 256, 0, st>>>(n, i_out, j_out, nx2, ny2, off, cursor, perm);
 }
 
 void launch_dst_sort_gather(long long ndst, const uint32_t* off, uint32_t* perm, const int* t_in, const int* i_in, const int* j_in,

@@ -23,6 +23,7 @@
 static xgb_plan* g_plan = nullptr;                      // one process-wide plan, like the reference's global state
 static const void* g_csr_key = nullptr;                 // interp[m].i_in the apply CSR was built from
 static size_t g_csr_n = 0;
+static int g_csr_order = 0;                            // ... and whether it carries di/dj (order 2)
 
 static xgb_plan* plan()
 {
@@ -96,9 +97,15 @@ extern "C" void setup_conserve_interp(int ntiles_in, const void* grid_in_v, int 
   std::vector<double> lon, lat;
   concat_grids(ntiles_in, grid_in, nx, ny, lon, lat);
   const unsigned op = opcode & (XGB_CONSERVE_ORDER1 | XGB_CONSERVE_ORDER2 | XGB_GREAT_CIRCLE);
+  if (xgb_plan_set_src(p, ntiles_in, nx.data(), ny.data(), lon.data(), lat.data(), nullptr, 0)) die(xgb_last_error());
+  // Order 2 with several output tiles: the reference sums every output tile's exchange cells per source cell before the
+  // AREA_RATIO test and the centroid subtraction (conserve_interp.c:204-221, :319-358), so the distances can only be
+  // finished after the last tile; the per-cell sums stay on the device across the generate calls.
+  const bool multi = o2 && ntiles_out > 1 && !(opcode & XGB_GREAT_CIRCLE);
+  std::vector<std::vector<double>> rawlon(multi ? ntiles_out : 0), rawlat(multi ? ntiles_out : 0);
+  if (multi && xgb_plan_order2_begin(p)) die(xgb_last_error());
   for (int n = 0; n < ntiles_out; ++n) {
     if (xgb_plan_set_dst(p, grid_out[n].nxc, grid_out[n].nyc, grid_out[n].lonc, grid_out[n].latc, 0)) die(xgb_last_error());
-    if (xgb_plan_set_src(p, ntiles_in, nx.data(), ny.data(), lon.data(), lat.data(), nullptr, 0)) die(xgb_last_error());
     const long long nxg = xgb_plan_generate(p, op);
     if (nxg < 0) die(xgb_last_error());
     interp[n].nxgrid = (size_t)nxg;
@@ -109,15 +116,30 @@ extern "C" void setup_conserve_interp(int ntiles_in, const void* grid_in_v, int 
     interp[n].t_in = (int*)malloc(k * sizeof(int));   interp[n].area = (double*)malloc(k * sizeof(double));
     if (o2) { interp[n].di_in = (double*)malloc(k * sizeof(double)); interp[n].dj_in = (double*)malloc(k * sizeof(double)); }
     if (xgb_plan_result_host(p, interp[n].t_in, interp[n].i_in, interp[n].j_in, interp[n].i_out, interp[n].j_out, interp[n].area,
-                             o2 ? interp[n].di_in : nullptr, o2 ? interp[n].dj_in : nullptr))
+                             (o2 && !multi) ? interp[n].di_in : nullptr, (o2 && !multi) ? interp[n].dj_in : nullptr))
       die(xgb_last_error());
-    if (opcode & XGB_WRITE) {                                                    // conserve_interp.c:368-443
-      if (xgb_remap_write(interp[n].remap_file, o2 ? 2 : 1, nxg, interp[n].t_in, interp[n].i_in, interp[n].j_in, interp[n].i_out,
-                          interp[n].j_out, grid_out[n].isc, grid_out[n].jsc, interp[n].area, o2 ? interp[n].di_in : nullptr,
-                          o2 ? interp[n].dj_in : nullptr))
-        die(xgb_last_error());
+    if (multi) {
+      rawlon[n].resize(k); rawlat[n].resize(k);
+      if (xgb_plan_result_centroids_host(p, rawlon[n].data(), rawlat[n].data())) die(xgb_last_error());
     }
   }
+  if (multi) {
+    if (xgb_plan_order2_end(p)) die(xgb_last_error());
+    for (int n = 0; n < ntiles_out; ++n)
+      if (interp[n].nxgrid &&
+          xgb_plan_order2_distance(p, (long long)interp[n].nxgrid, interp[n].t_in, interp[n].i_in, interp[n].j_in, interp[n].area,
+                                   rawlon[n].data(), rawlat[n].data(), interp[n].di_in, interp[n].dj_in))
+        die(xgb_last_error());
+    xgb_plan_order2_reset(p);
+  }
+  if (opcode & XGB_WRITE)                                                        // conserve_interp.c:368-443
+    for (int n = 0; n < ntiles_out; ++n) {
+      if (interp[n].nxgrid == 0) continue;
+      if (xgb_remap_write(interp[n].remap_file, o2 ? 2 : 1, (long long)interp[n].nxgrid, interp[n].t_in, interp[n].i_in, interp[n].j_in,
+                          interp[n].i_out, interp[n].j_out, grid_out[n].isc, grid_out[n].jsc, interp[n].area,
+                          o2 ? interp[n].di_in : nullptr, o2 ? interp[n].dj_in : nullptr))
+        die(xgb_last_error());
+    }
   g_csr_key = nullptr;
   if (opcode & XGB_GREAT_CIRCLE) return;
   printf("NOTE: done calculating index and weight for conservative interpolation\n");   // conserve_interp.c:446
@@ -184,12 +206,12 @@ extern "C" void do_scalar_conserve_interp(void* interp_v, int varid, int ntiles_
       for (size_t q = 0; q < (size_t)nx2 * ny2 * nz; ++q) field_out[m].data[q] = miss;
       continue;
     }
-    if (g_csr_key != (const void*)interp[m].i_in || g_csr_n != interp[m].nxgrid) {
+    if (g_csr_key != (const void*)interp[m].i_in || g_csr_n != interp[m].nxgrid || g_csr_order != order) {
       if (xgb_plan_set_xgrid(p, ntiles_in, nx.data(), ny.data(), nx2, ny2, (long long)interp[m].nxgrid, interp[m].t_in, interp[m].i_in,
                              interp[m].j_in, interp[m].i_out, interp[m].j_out, interp[m].area,
                              order == 2 ? interp[m].di_in : nullptr, order == 2 ? interp[m].dj_in : nullptr, 0))
         die(xgb_last_error());
-      g_csr_key = interp[m].i_in; g_csr_n = interp[m].nxgrid;
+      g_csr_key = interp[m].i_in; g_csr_n = interp[m].nxgrid; g_csr_order = order;
     }
     if (xgb_plan_apply_options(p, use_sum ? 1 : 0, use_weight ? wgt.data() : nullptr, (use_sum || use_meas) ? carea.data() : nullptr,
                                use_meas ? farea.data() : nullptr, v.area_missing, use_target ? 1 : 0,

@@ -120,7 +120,9 @@ extern "C" void xgb_plan_destroy(xgb_plan* p)
                     &p->pclon, &p->pclat, &p->scan_tmp, &p->t_in, &p->i_in, &p->j_in, &p->i_out, &p->j_out,
                     &p->area, &p->clon, &p->clat, &p->di, &p->dj, &p->bounds_dev,
                     &p->heavy_ctl, &p->heavy_flag, &p->heavy_list, &p->heavy_items, &p->heavy_pairs,
-                    &p->gc_src_xyz, &p->gc_dst_xyz, &p->gc_pyr_store};
+                    &p->gc_src_xyz, &p->gc_dst_xyz, &p->gc_pyr_store,
+                    &p->rect_store, &p->rect_rows, &p->rect_invalid, &p->o2_acc, &p->o2_tmp,
+                    &p->clip_vx, &p->clip_vy, &p->clip_meta};
   for (DevBuf* b : bufs) b->release();
   xgb_apply_release(p);
   for (int k = 0; k < 6; ++k) if (p->ev[k]) cudaEventDestroy(p->ev[k]);
@@ -195,6 +197,7 @@ static int report_kernel_error(xgb_plan* p, int e, bool fatal_like_reference)
   else if (e & kErrGcWalk) msg = "clip_2dx2d_great_circle: polygon walk did not return to the first intersection";
   else if (e & kErrGcNodePool) msg = "getNext: curListPos >= MAXNODELIST";
   else if (e & kErrHeavyOverflow) msg = "candidate search: heavy-cell work buffer exhausted; raise XGB_HEAVY_CAP";
+  else if (e & kErrBadIndex) msg = "exchange-grid list names a cell outside its grid (does the remap file belong to these grids?)";
   if (fatal_like_reference) fatal(msg);
   xgb_set_error("%s (kernel error bits 0x%x)", msg, e);
   return 1;
@@ -300,6 +303,7 @@ extern "C" int xgb_plan_set_src(xgb_plan* p, int ntiles, const int* nx, const in
   p->map = single_window(0, coff);
   p->have_src = true;
   p->gc_src_ready = false;
+  p->o2_state = 0;
   // the tile table was copied from pageable host memory: make sure it has landed before `tiles` can change
   return xgb_check_kernel_errors(p, false);
 }
@@ -405,6 +409,7 @@ static int count_candidates(xgb_plan* p, const SrcMap& sm, unsigned long long* t
     cudaMemsetAsync(p->err_dev, 0, sizeof(int), p->st);
     if (heavy_work(p, ns, &hw)) return 1;
   }
+  if (report_kernel_error(p, *p->err_host, false)) return 1;      // still overflowing after 8 retries, or any other kernel error
   *total = p->total_host[0];
   if (*total >= (1ull << 32)) { xgb_set_error("more than 2^32 candidate pairs in one window; shard the source cells"); return 1; }
   return 0;
@@ -433,6 +438,14 @@ extern "C" int xgb_plan_partition(xgb_plan* p, int nparts, long long* bounds)
 // are sized for that capacity (nxgrid <= pairs).  Totals, window offsets and the error word come back through pinned memory
 // at the end; a buffer that turned out too small (first call, or a grid change) repeats the window with the sizes just
 // learnt.  Split in two so that xgb_plan_generate_async can enqueue a window without waiting for it.
+// scratch of the two-kernel clip for a launch over `pairs` candidate pairs
+static int reserve_clip_scratch(xgb_plan* p, size_t pairs)
+{
+  const size_t nv = clip_scratch_vertices(pairs);
+  return p->clip_vx.reserve(nv * sizeof(double) + 16) || p->clip_vy.reserve(nv * sizeof(double) + 16) ||
+         p->clip_meta.reserve(pairs * sizeof(unsigned short) + 16);
+}
+
 static int resident_enqueue(xgb_plan* p, int order, const SrcMap& sm, size_t cap, HeavyWork& hw)
 {
   const long long ns = sm.total();
@@ -444,6 +457,7 @@ static int resident_enqueue(xgb_plan* p, int order, const SrcMap& sm, size_t cap
   if (heavy_work(p, ns, &hw)) return -1;
   if (p->pairs.reserve(cap * sizeof(int2) + 16) || p->parea.reserve(cap * sizeof(double) + 16)) return -1;
   if (order == 2 && (p->pclon.reserve(cap * sizeof(double) + 16) || p->pclat.reserve(cap * sizeof(double) + 16))) return -1;
+  if (reserve_clip_scratch(p, cap)) return -1;
   const size_t ni = cap * sizeof(int) + 16, nd = cap * sizeof(double) + 16;
   if (p->t_in.reserve(ni) || p->i_in.reserve(ni) || p->j_in.reserve(ni) || p->i_out.reserve(ni) || p->j_out.reserve(ni) ||
       p->area.reserve(nd))
@@ -458,7 +472,8 @@ static int resident_enqueue(xgb_plan* p, int order, const SrcMap& sm, size_t cap
   cudaMemsetAsync(p->cnt.p, 0, (size_t)(ns + 1) * sizeof(uint32_t), p->st);
   cudaEventRecord(p->ev[2], p->st);
   launch_clip(order, p->src, p->dst, mask, (const int2*)p->pairs.p, cap, npairs_dev, sm,
-              (double*)p->parea.p, (double*)p->pclon.p, (double*)p->pclat.p, (uint32_t*)p->cnt.p, p->err_dev, p->st);
+              (double*)p->parea.p, (double*)p->pclon.p, (double*)p->pclat.p, (uint32_t*)p->cnt.p, p->err_dev, p->st,
+              (double*)p->clip_vx.p, (double*)p->clip_vy.p, (unsigned short*)p->clip_meta.p);
   cudaEventRecord(p->ev[3], p->st);
   launch_exclusive_scan((const uint32_t*)p->cnt.p, (uint32_t*)p->out_off.p, ns, p->total_dev + 1, p->scan_tmp.p, p->st);
   cudaEventRecord(p->ev[4], p->st);
@@ -467,7 +482,10 @@ static int resident_enqueue(xgb_plan* p, int order, const SrcMap& sm, size_t cap
                  (const TileDesc*)p->tiles_dev.p, (int)p->tiles.size(), sm, p->nx2,
                  (int*)p->t_in.p, (int*)p->i_in.p, (int*)p->j_in.p, (int*)p->i_out.p, (int*)p->j_out.p,
                  (double*)p->area.p, (double*)p->clon.p, (double*)p->clat.p, &hw, p->st, p->aux_st, p->fork_ev, p->join_ev, npairs_dev);
-  if (order == 2)
+  if (order == 2 && p->o2_state == 1)
+    launch_order2_accumulate(sm, (const uint32_t*)p->out_off.p, (const double*)p->area.p, (const double*)p->clon.p,
+                             (const double*)p->clat.p, (double*)p->o2_acc.p, p->src.ncell, p->st);
+  else if (order == 2)
     launch_order2_finalize(p->src, sm, (const uint32_t*)p->out_off.p, (const double*)p->area.p, (const double*)p->clon.p,
                            (const double*)p->clat.p, (double*)p->di.p, (double*)p->dj.p, hw.list, &hw.ctl->nheavy, p->st,
                            p->aux_st, p->fork_ev, p->join_ev);
@@ -588,8 +606,10 @@ static long long generate_window(xgb_plan* p, int order, const SrcMap& sm, size_
   cudaEventRecord(p->ev[1], p->st);
   cudaMemsetAsync(p->cnt.p, 0, (size_t)(ns + 1) * sizeof(uint32_t), p->st);
   cudaEventRecord(p->ev[2], p->st);
+  if (reserve_clip_scratch(p, (size_t)npairs)) return -1;
   launch_clip(order, p->src, p->dst, mask, (const int2*)p->pairs.p, npairs, nullptr, sm,
-              (double*)p->parea.p, (double*)p->pclon.p, (double*)p->pclat.p, (uint32_t*)p->cnt.p, p->err_dev, p->st);
+              (double*)p->parea.p, (double*)p->pclon.p, (double*)p->pclat.p, (uint32_t*)p->cnt.p, p->err_dev, p->st,
+              (double*)p->clip_vx.p, (double*)p->clip_vy.p, (unsigned short*)p->clip_meta.p);
   cudaEventRecord(p->ev[3], p->st);
   launch_exclusive_scan((const uint32_t*)p->cnt.p, (uint32_t*)p->out_off.p, ns, p->total_dev + 1, p->scan_tmp.p, p->st);
   launch_publish(p->total_host + 1, p->total_dev + 1, 2, p->st);
@@ -618,7 +638,10 @@ static long long generate_window(xgb_plan* p, int order, const SrcMap& sm, size_
                  (int*)p->t_in.p + base, (int*)p->i_in.p + base, (int*)p->j_in.p + base, (int*)p->i_out.p + base, (int*)p->j_out.p + base,
                  (double*)p->area.p + base, (double*)p->clon.p + (order == 2 ? base : 0), (double*)p->clat.p + (order == 2 ? base : 0), &hw, p->st,
                  p->aux_st, p->fork_ev, p->join_ev);
-  if (order == 2)
+  if (order == 2 && p->o2_state == 1)
+    launch_order2_accumulate(sm, (const uint32_t*)p->out_off.p, (const double*)p->area.p + base, (const double*)p->clon.p + base,
+                             (const double*)p->clat.p + base, (double*)p->o2_acc.p, p->src.ncell, p->st);
+  else if (order == 2)
     launch_order2_finalize(p->src, sm, (const uint32_t*)p->out_off.p, (const double*)p->area.p + base,
                            (const double*)p->clon.p + base, (const double*)p->clat.p + base, (double*)p->di.p + base,
                            (double*)p->dj.p + base, hw.list, &hw.ctl->nheavy, p->st, p->aux_st, p->fork_ev, p->join_ev);
@@ -774,6 +797,63 @@ extern "C" long long xgb_plan_generate_to_host(xgb_plan* p, unsigned int opcode,
   p->generates += 1;
   return p->nxgrid;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Order 2 with several output tiles (conserve_interp.c:148-227, :319-358).  Between _begin and _end every order-2 generate
+// adds its exchange cells to per-source-cell sums that persist across calls (output tiles in call order, list order inside
+// a call: the reference's order) and leaves di/dj unset; the caller keeps each tile's lists and raw xgrid_clon/xgrid_clat
+// (xgb_plan_result_centroids_host).  _end turns the sums into centroids; _distance then gives one tile's tile1_distance.
+// ---------------------------------------------------------------------------------------------
+extern "C" int xgb_plan_order2_begin(xgb_plan* p)
+{
+  if (!p || !p->have_src) { xgb_set_error("xgb_plan_order2_begin: set the source grid first"); return 1; }
+  CU_OK(cudaSetDevice(p->device));
+  const size_t bytes = 3 * (size_t)p->src.ncell * sizeof(double);
+  if (p->o2_acc.reserve(bytes)) return 1;
+  CU_OK(cudaMemsetAsync(p->o2_acc.p, 0, bytes, p->st));
+  p->o2_state = 1;
+  return 0;
+}
+
+extern "C" int xgb_plan_order2_end(xgb_plan* p)
+{
+  if (!p || p->o2_state != 1) { xgb_set_error("xgb_plan_order2_end: no accumulation in progress"); return 1; }
+  CU_OK(cudaSetDevice(p->device));
+  launch_order2_centroids(p->src, (double*)p->o2_acc.p, p->st);
+  p->o2_state = 2;
+  return xgb_check_kernel_errors(p, false);
+}
+
+extern "C" int xgb_plan_order2_distance(xgb_plan* p, long long n, const int* t_in, const int* i_in, const int* j_in,
+                                        const double* area, const double* xgrid_clon, const double* xgrid_clat, double* di, double* dj)
+{
+  if (!p || p->o2_state != 2) { xgb_set_error("xgb_plan_order2_distance: call xgb_plan_order2_end first"); return 1; }
+  if (n < 0 || (n > 0 && (!t_in || !i_in || !j_in || !area || !xgrid_clon || !xgrid_clat || !di || !dj))) {
+    xgb_set_error("xgb_plan_order2_distance: bad arguments");
+    return 1;
+  }
+  if (n == 0) return 0;
+  CU_OK(cudaSetDevice(p->device));
+  const size_t k = (size_t)n;
+  if (p->o2_tmp.reserve(k * (3 * sizeof(int) + 5 * sizeof(double)) + 64)) return 1;
+  double* d_area = (double*)p->o2_tmp.p;
+  double *d_clon = d_area + k, *d_clat = d_clon + k, *d_di = d_clat + k, *d_dj = d_di + k;
+  int* d_t = (int*)(d_dj + k);
+  int *d_i = d_t + k, *d_j = d_i + k;
+  CU_OK(cudaMemcpyAsync(d_area, area, k * sizeof(double), cudaMemcpyHostToDevice, p->st));
+  CU_OK(cudaMemcpyAsync(d_clon, xgrid_clon, k * sizeof(double), cudaMemcpyHostToDevice, p->st));
+  CU_OK(cudaMemcpyAsync(d_clat, xgrid_clat, k * sizeof(double), cudaMemcpyHostToDevice, p->st));
+  CU_OK(cudaMemcpyAsync(d_t, t_in, k * sizeof(int), cudaMemcpyHostToDevice, p->st));
+  CU_OK(cudaMemcpyAsync(d_i, i_in, k * sizeof(int), cudaMemcpyHostToDevice, p->st));
+  CU_OK(cudaMemcpyAsync(d_j, j_in, k * sizeof(int), cudaMemcpyHostToDevice, p->st));
+  launch_order2_distance(n, d_t, d_i, d_j, (const TileDesc*)p->tiles_dev.p, (int)p->tiles.size(), d_area, d_clon, d_clat,
+                         (const double*)p->o2_acc.p, p->src.ncell, d_di, d_dj, p->err_dev, p->st);
+  CU_OK(cudaMemcpyAsync(di, d_di, k * sizeof(double), cudaMemcpyDeviceToHost, p->st));
+  CU_OK(cudaMemcpyAsync(dj, d_dj, k * sizeof(double), cudaMemcpyDeviceToHost, p->st));
+  return xgb_check_kernel_errors(p, false);
+}
+
+extern "C" void xgb_plan_order2_reset(xgb_plan* p) { if (p) p->o2_state = 0; }
 
 extern "C" long long xgb_plan_last_npairs(xgb_plan* p) { return p ? (long long)p->npairs : -1; }
 

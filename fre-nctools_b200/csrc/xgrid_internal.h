@@ -65,6 +65,7 @@ enum : int {
   kErrGcWalk          = 32,  // great-circle: polygon walk failed     (create_xgrid.c:1795,1822,1825)
   kErrGcNodePool      = 64,  // great-circle: node pool exhausted     (mosaic_util.c:1075)
   kErrHeavyOverflow   = 128, // heavy-cell work buffer exhausted (internal capacity)
+  kErrBadIndex        = 256, // an exchange-grid list names a cell outside its grid
 };
 
 // device-side control block and work buffers of the level-synchronous "heavy cell" candidate path
@@ -100,7 +101,10 @@ void launch_candidates_single(const CellSet& src, const SrcMap& sm, const double
                               unsigned long long pair_cap, uint32_t* cursor, const HeavyWork& hw, int* err, cudaStream_t st);
 void launch_clip(int order, const CellSet& src, const CellSet& dst, const double* mask,
                  const int2* pairs, unsigned long long npairs, const unsigned long long* npairs_dev, const SrcMap& sm,
-                 double* parea, double* pclon, double* pclat, uint32_t* cnt, int* err, cudaStream_t st);
+                 double* parea, double* pclon, double* pclat, uint32_t* cnt, int* err, cudaStream_t st,
+                 double* gvx = nullptr, double* gvy = nullptr, unsigned short* gmeta = nullptr);
+// vertices of the scratch arrays gvx / gvy the two-kernel clip needs for a launch over npairs pairs (gmeta: npairs entries)
+size_t clip_scratch_vertices(unsigned long long npairs);
 void launch_scatter(int order, const int2* pairs, unsigned long long npairs,
                     const double* parea, const double* pclon, const double* pclat,
                     const uint32_t* pair_off, const uint32_t* pair_cnt, const uint32_t* out_off,
@@ -112,6 +116,13 @@ void launch_order2_finalize(const CellSet& src, const SrcMap& sm, const uint32_t
                             const double* area, const double* clon, const double* clat,
                             double* di, double* dj, const int* heavy_list, const unsigned* nheavy,
                             cudaStream_t st, cudaStream_t aux, cudaEvent_t fork, cudaEvent_t join);
+// order 2 over several output tiles (conserve_interp.c:204-221, :319-358); acc = [area | clon | clat] x ncell source cells
+void launch_order2_accumulate(const SrcMap& sm, const uint32_t* out_off, const double* area, const double* clon, const double* clat,
+                              double* acc, long long ncell, cudaStream_t st);
+void launch_order2_centroids(const CellSet& src, double* acc, cudaStream_t st);
+void launch_order2_distance(long long n, const int* t_in, const int* i_in, const int* j_in, const TileDesc* tiles, int ntiles,
+                            const double* area, const double* clon, const double* clat, const double* acc, long long ncell,
+                            double* di, double* dj, int* err, cudaStream_t st);
 // nwords 32-bit words from device memory to pinned host memory, by a kernel (not the copy engine)
 void launch_publish(void* host_dst, const void* dev_src, int nwords, cudaStream_t st);
 void launch_latlon_fill(int nlon, int nlat, double lonbegin, double lonend, double latbegin, double latend, double* lon, double* lat,

@@ -1052,6 +1052,844 @@ clip_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const int
   }
 }
 
+// =============================================================================================
+// clip, block-cooperative version (round 2; XGB_CLIP2, default on).  Same arithmetic, bit for bit, as clip_kernel above;
+// what changes is who does it.  ncu on clip_kernel (profiles/r01u_ncu_full_kernels.txt): 19.98 of 32 threads active per
+// instruction, FP64 pipe 37 % — the lanes of a warp hold pairs that are cut by different destination edges (every stage
+// runs its crossing code for the lanes that need it while the rest wait), 9 % of the pairs clip to nothing, and the
+// moments loop runs to the warp's largest vertex count.  Here
+//   (1) the block's 128 pairs are first dealt to the threads by the destination edges that can cut them (which sides of
+//       the destination cell's box the source cell's box sticks out of: a stable counting sort on a 4-bit key), so a warp
+//       holds pairs with (nearly) one cut pattern and skips the crossing code of the other stages altogether;
+//   (2) Sutherland-Hodgman runs one thread per pair as before (clip_cell_fast, polygons in shared memory);
+//   (3) the surviving polygons are flattened into block-wide vertex arrays (prefix sum of the vertex counts) and the
+//       moments become edge-parallel: one pass evaluates sincos(latitude) once per vertex, one pass evaluates every
+//       edge's three terms (poly_area / poly_ctrlon / poly_ctrlat), then each polygon's owner adds its terms up in edge
+//       order — the additions, and so the results, are the reference's (mosaic_util.c:417-459, create_xgrid.c:2096-2217).
+//       Lanes are dense (no empty pairs, no trip-count spread) and diverge only on the edge type.
+// A skipped term (dx == 0 edges of poly_ctrlon/ctrlat) is stored as +0.0: x - (+0.0) == x for every x, -0.0 included.
+// The pole-edge term of poly_area (acc += pi) is stored as -pi: x - (-pi) is the same IEEE operation as x + pi.
+// Polygons from the generic routine (more than 8 vertices at some stage) and the few that do not fit the block's
+// flattened arrays (kC2Cap vertices for 128 pairs; the mean is 3.6 per pair) take the per-thread routine as before.
+// =============================================================================================
+#ifndef XGB_CLIP2
+#define XGB_CLIP2 1
+#endif
+#ifndef XGB_CLIP2_SORT
+#define XGB_CLIP2_SORT 0
+#endif
+#ifndef XGB_CLIP2_BLOCKS
+#define XGB_CLIP2_BLOCKS 5
+#endif
+#ifndef XGB_CLIP2_CAP
+#define XGB_CLIP2_CAP 640
+#endif
+constexpr int kC2Cap = XGB_CLIP2_CAP;      // flattened vertices per block
+
+#ifndef XGB_CLIP2_IDX
+#define XGB_CLIP2_IDX 1
+#endif
+// XGB_CLIP2_CALLS: the sin / cos evaluations of the moments are CALLS of two routines (ref_sincos_call, ref_sin_call) instead
+// of four inlined copies — ncu: the kernel stalls on instruction fetch (no_instruction 12 % of the samples at 5 blocks/SM,
+// twice that at 7), its hot code is 70 KB of SASS.  XGB_CLIP2_ROLL: the destination-edge loop of the indexed clip stays rolled.
+#ifndef XGB_CLIP2_CALLS
+#define XGB_CLIP2_CALLS 0
+#endif
+#ifndef XGB_CLIP2_ROLL
+#define XGB_CLIP2_ROLL 1
+#endif
+#if XGB_CLIP2_CALLS
+#define C2_SINCOS(x, s, c) ref_sincos_call((x), (s), (c))
+#define C2_SIN(x) ref_sin_call(x)
+#define C2_SIN_SMALL(x) ref_sin_small(x)
+#else
+#define C2_SINCOS(x, s, c) ref_sincos((x), (s), (c))
+#define C2_SIN(x) ref_sin(x)
+#define C2_SIN_SMALL(x) ref_sin(x)
+#endif
+constexpr int kIdxSlots = 12;      // 4 source vertices + 2 crossings per destination edge
+
+// inside_edge (create_xgrid.c:2342-2350) of point (x, y) against the edge (x0, y0) -> (x1, y1)
+__device__ __forceinline__ unsigned in_bit(double x0, double y0, double x1, double y1, double x, double y)
+{
+  return (unsigned)(((x - x0) * (y1 - y0) + (x0 - x1) * (y - y0)) <= 1.e-12);
+}
+
+// Sutherland-Hodgman (clip_2dx2d, create_xgrid.c:1292-1340) on an INDEXED polygon.  ncu on clip_cell_fast: the loop that
+// copies the kept vertices to the other buffer is 10 % of the kernel's instructions at 9 of 32 lanes, the inside-flag loop
+// another 9 % (two shared-memory loads and a loop trip per vertex and stage).  Here a vertex never moves: the 4 source
+// vertices and the (at most 8) crossings sit in append-only slots of shared memory, the polygon is a list of slot numbers
+// packed in nibbles, and every vertex's inside flag for each destination edge is evaluated ONCE, in registers, when the
+// vertex is created (straight-line code) and kept as one bit per edge in list order.  A stage that does not cut is a mask
+// compare; a stage that cuts computes the two crossings (same operations as the reference), their flags for the edges
+// still to come, and splices list and masks with shifts.  The emitted vertex order is the reference's (crossing before
+// vertex k, then vertex k if inside).  Returns the vertex count, the list in *list_out; -1 = not a 3/4-gon pair, more than
+// two crossings (non-convex) or more than 8 vertices: the caller takes the generic routine.
+//   sx: this thread's column; slot j has x at sx[j * S], y at sx[(kIdxSlots + j) * S].  vx/vy: the source vertices (also
+//   stored in slots 0..n1-1 by the caller).  ex/ey: destination vertices as clip_2dx2d sees them.
+__device__ __forceinline__ int clip_cell_idx(double* sx, const double (&vx)[4], const double (&vy)[4], const double (&ex)[4],
+                                             const double (&ey)[4], int n1, int n2, unsigned long long* list_out, int* err)
+{
+  constexpr int S = kClipThreads;
+  double* sy = sx + kIdxSlots * S;
+  int np = ((n1 == 3 || n1 == 4) && (n2 == 3 || n2 == 4)) ? n1 : ((n1 == 0) ? 0 : -1);
+  const unsigned none3 = (n2 == 3) ? 0xffu : 0u;                  // a triangle has no fourth edge: everything is inside it
+  // edge e runs from destination vertex e-1 (the last one for e == 0) to vertex e
+  const double bx0 = (n2 == 4) ? ex[3] : ex[2], by0 = (n2 == 4) ? ey[3] : ey[2];
+  unsigned M[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const double x0 = (e == 0) ? bx0 : ex[e - 1], y0 = (e == 0) ? by0 : ey[e - 1];
+    unsigned m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m |= in_bit(x0, y0, ex[e], ey[e], vx[k], vy[k]) << k;
+    if (e == 3) m |= none3;
+    M[e] = m & ((n1 == 3) ? 7u : 15u);
+  }
+  unsigned long long L = (n1 == 3) ? 0x210ull : 0x3210ull;
+  int ns = 4;                                                      // next free slot
+#if XGB_CLIP2_ROLL
+  // rolled: the edge's end vertex, the following vertices and the masks rotate through registers (a quarter of the code)
+  double ax0 = bx0, ay0 = by0;                                     // start of the current edge
+  double r0x = ex[0], r0y = ey[0], r1x = ex[1], r1y = ey[1], r2x = ex[2], r2y = ey[2], r3x = ex[3], r3y = ey[3];
+  unsigned m0 = M[0], m1 = M[1], m2 = M[2], m3 = M[3];
+#pragma unroll 1
+  for (int e = 0; e < 4; ++e) {
+    if (np > 0) {
+      const unsigned full = (1u << np) - 1u;
+      const unsigned m = m0;
+      if (m == 0u) np = 0;
+      else if (m != full) {
+        const unsigned prev = ((m << 1) | (m >> (np - 1))) & full;   // inside flag of vertex k-1 (cyclic)
+        const unsigned cross = m ^ prev;
+        if (__popc(cross) != 2 || np + 1 > kFastCap) np = -1;
+        else {
+          const int k0 = __ffs(cross) - 1, k1 = 31 - __clz(cross);
+          const double ex0 = ax0, ey0 = ay0, ex1 = r0x, ey1 = r0y;
+          double cxv[2], cyv[2];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int k = c ? k1 : k0;
+            const int km = (k == 0) ? np - 1 : k - 1;
+            const int sa = (int)(L >> (4 * km)) & 15, sb = (int)(L >> (4 * k)) & 15;
+            const double px = sx[sa * S], py = sy[sa * S];
+            const double qx = sx[sb * S], qy = sy[sb * S];
+            const double dy1 = qy - py, dy2 = ey1 - ey0, dx1 = qx - px, dx2 = ex1 - ex0;
+            const double ds1 = py * qx - qy * px, ds2 = ey0 * ex1 - ey1 * ex0;
+            const double determ = dy2 * dx1 - dy1 * dx2;
+            if (fabs(determ) < 1.0e-30) atomicOr(err, kErrParallelEdges);
+            cxv[c] = (dx2 * ds1 - dx1 * ds2) / determ;
+            cyv[c] = (dy2 * ds1 - dy1 * ds2) / determ;
+            sx[(ns + c) * S] = cxv[c]; sy[(ns + c) * S] = cyv[c];
+          }
+          const bool run_inside = (m >> k0) & 1u;                  // vertex k0 is kept: the kept run is [k0, k1)
+          const int rl = k1 - k0;
+          if (run_inside)
+            L = (unsigned long long)ns | (((L >> (4 * k0)) & ((1ull << (4 * rl)) - 1ull)) << 4) | ((unsigned long long)(ns + 1) << (4 * (rl + 1)));
+          else
+            L = (L & ((1ull << (4 * k0)) - 1ull)) | ((unsigned long long)(ns | ((ns + 1) << 4)) << (4 * k0)) | ((L >> (4 * k1)) << (4 * (k0 + 2)));
+          auto splice = [&](unsigned Mf, unsigned b0, unsigned b1) -> unsigned {
+            return run_inside ? (b0 | (((Mf >> k0) & ((1u << rl) - 1u)) << 1) | (b1 << (rl + 1)))
+                              : ((Mf & ((1u << k0) - 1u)) | (b0 << k0) | (b1 << (k0 + 1)) | ((Mf >> k1) << (k0 + 2)));
+          };
+          // flags of the two crossings for the edges still to come (e is warp-uniform)
+          if (e < 3) {
+            const unsigned f3 = (e == 2) ? (none3 & 1u) : 0u;
+            m1 = splice(m1, in_bit(r0x, r0y, r1x, r1y, cxv[0], cyv[0]) | f3, in_bit(r0x, r0y, r1x, r1y, cxv[1], cyv[1]) | f3);
+          }
+          if (e < 2) {
+            const unsigned f3 = (e == 1) ? (none3 & 1u) : 0u;
+            m2 = splice(m2, in_bit(r1x, r1y, r2x, r2y, cxv[0], cyv[0]) | f3, in_bit(r1x, r1y, r2x, r2y, cxv[1], cyv[1]) | f3);
+          }
+          if (e < 1) {
+            const unsigned f3 = none3 & 1u;
+            m3 = splice(m3, in_bit(r2x, r2y, r3x, r3y, cxv[0], cyv[0]) | f3, in_bit(r2x, r2y, r3x, r3y, cxv[1], cyv[1]) | f3);
+          }
+          np = run_inside ? rl + 2 : k0 + 2 + np - k1;
+          ns += 2;
+        }
+      }
+    }
+    { // rotate
+      ax0 = r0x; ay0 = r0y;
+      const double tx = r0x, ty = r0y;
+      r0x = r1x; r0y = r1y; r1x = r2x; r1y = r2y; r2x = r3x; r2y = r3y; r3x = tx; r3y = ty;
+      m0 = m1; m1 = m2; m2 = m3;
+    }
+    __syncwarp();
+  }
+#else
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (np > 0) {
+      const unsigned full = (1u << np) - 1u;
+      const unsigned m = M[e];
+      if (m == 0u) np = 0;
+      else if (m != full) {
+        const unsigned prev = ((m << 1) | (m >> (np - 1))) & full;   // inside flag of vertex k-1 (cyclic)
+        const unsigned cross = m ^ prev;
+        if (__popc(cross) != 2 || np + 1 > kFastCap) np = -1;
+        else {
+          const int k0 = __ffs(cross) - 1, k1 = 31 - __clz(cross);
+          const double ex0 = (e == 0) ? bx0 : ex[e - 1], ey0 = (e == 0) ? by0 : ey[e - 1];
+          const double ex1 = ex[e], ey1 = ey[e];
+          double cxv[2], cyv[2];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int k = c ? k1 : k0;
+            const int km = (k == 0) ? np - 1 : k - 1;
+            const int sa = (int)(L >> (4 * km)) & 15, sb = (int)(L >> (4 * k)) & 15;
+            const double px = sx[sa * S], py = sy[sa * S];
+            const double qx = sx[sb * S], qy = sy[sb * S];
+            const double dy1 = qy - py, dy2 = ey1 - ey0, dx1 = qx - px, dx2 = ex1 - ex0;
+            const double ds1 = py * qx - qy * px, ds2 = ey0 * ex1 - ey1 * ex0;
+            const double determ = dy2 * dx1 - dy1 * dx2;
+            if (fabs(determ) < 1.0e-30) atomicOr(err, kErrParallelEdges);
+            cxv[c] = (dx2 * ds1 - dx1 * ds2) / determ;
+            cyv[c] = (dy2 * ds1 - dy1 * ds2) / determ;
+            sx[(ns + c) * S] = cxv[c]; sy[(ns + c) * S] = cyv[c];
+          }
+          const bool run_inside = (m >> k0) & 1u;                  // vertex k0 is kept: the kept run is [k0, k1)
+          const int rl = k1 - k0;
+          // splice the list: crossing at k0 -> slot ns, crossing at k1 -> slot ns + 1
+          if (run_inside)
+            L = (unsigned long long)ns | (((L >> (4 * k0)) & ((1ull << (4 * rl)) - 1ull)) << 4) | ((unsigned long long)(ns + 1) << (4 * (rl + 1)));
+          else
+            L = (L & ((1ull << (4 * k0)) - 1ull)) | ((unsigned long long)(ns | ((ns + 1) << 4)) << (4 * k0)) | ((L >> (4 * k1)) << (4 * (k0 + 2)));
+          // flags of the two crossings for the edges still to come, spliced into those edges' masks the same way
+#pragma unroll
+          for (int f = e + 1; f < 4; ++f) {
+            const double x0 = ex[f - 1], y0 = ey[f - 1];
+            unsigned b0 = in_bit(x0, y0, ex[f], ey[f], cxv[0], cyv[0]), b1 = in_bit(x0, y0, ex[f], ey[f], cxv[1], cyv[1]);
+            if (f == 3) { b0 |= none3 & 1u; b1 |= none3 & 1u; }
+            const unsigned Mf = M[f];
+            if (run_inside) M[f] = b0 | (((Mf >> k0) & ((1u << rl) - 1u)) << 1) | (b1 << (rl + 1));
+            else            M[f] = (Mf & ((1u << k0) - 1u)) | (b0 << k0) | (b1 << (k0 + 1)) | ((Mf >> k1) << (k0 + 2));
+          }
+          np = run_inside ? rl + 2 : k0 + 2 + np - k1;
+          ns += 2;
+        }
+      }
+    }
+    __syncwarp();
+  }
+#endif
+  *list_out = L;
+  return np;
+}
+
+// one edge of a clipped polygon: the terms poly_area_main / poly_ctrlon / poly_ctrlat accumulate for it
+// (the body of poly_moments' loop, xgrid_geom.cuh)
+template <int ORDER>
+__device__ __forceinline__ void edge_terms(double xi, double yi, double xn, double yn, double si, double ci, double sn, double cn,
+                                           double clon, double* ta, double* tlon, double* tlat)
+{
+  const double lat1 = yn, lat2 = yi;
+  const double dx_raw = xn - xi;                       // x[ip]-x[i] == phi1-phi2
+  double dxa = dx_raw;                                 // poly_area's wrapped dx (mosaic_util.c:429-432)
+  if (dxa > kPi)  dxa = dxa - 2.0 * kPi;
+  if (dxa < -kPi) dxa = dxa + 2.0 * kPi;
+  const bool pole_edge = (fabs(dxa + kPi) < kSmall || fabs(dxa - kPi) < kSmall);
+  const bool flat_area = (fabs(lat1 - lat2) < kSmall);
+  const double avg = 0.5 * (lat1 + lat2);
+  const double dy = 0.5 * (lat1 - lat2);               // hdy of poly_ctrlat is -dy
+  const bool moving = (ORDER == 2) && (dx_raw != 0.0); // poly_ctrlon / poly_ctrlat skip dx == 0 edges
+  const bool flat_lat = (fabs(dy) < kSmall);           // fabs(hdy) < SMALL_VALUE (create_xgrid.c:2114)
+  double s_avg = 0.0, c_avg = 0.0;
+  if (moving) C2_SINCOS(avg, &s_avg, &c_avg);
+  double dat = 0.0;
+  if ((!pole_edge && !flat_area) || (moving && !flat_lat)) dat = C2_SIN_SMALL(dy) / dy;
+  const uint32_t hi = (uint32_t)(trig::bits(avg) >> 32) & 0x7fffffffu;
+  const bool own_sin = !pole_edge && !(moving && hi < 0x3feb6000u);
+  double sin_avg = s_avg;
+  if (own_sin) sin_avg = C2_SIN(avg);
+  if (pole_edge) *ta = -kPi;                           // mosaic_util.c:434-437
+  else if (flat_area) *ta = dxa * sin_avg;
+  else *ta = dxa * sin_avg * dat;
+  if (ORDER == 2) {
+    double tl = 0.0, tt = 0.0;
+    if (moving) {
+      // poly_ctrlat (create_xgrid.c:2100-2118)
+      double dxl = dx_raw;
+      if (dxl > kPi)   dxl = dxl - 2.0 * kPi;
+      if (dxl <= -kPi) dxl = dxl + 2.0 * kPi;
+      if (flat_lat) tt = dxl * (2 * c_avg + lat2 * s_avg - cn);
+      else          tt = dxl * (dat * (2 * c_avg + lat2 * s_avg) - cn);
+      // poly_ctrlon (create_xgrid.c:2176-2215)
+      const double f1 = 0.5 * (cn * sn + lat1);
+      const double f2 = 0.5 * (ci * si + lat2);
+      double dphi = dx_raw;
+      if (dphi > kPi)  dphi = dphi - 2.0 * kPi;
+      if (dphi < -kPi) dphi = dphi + 2.0 * kPi;
+      double dphi1 = xn - clon;
+      if (dphi1 > kPi)  dphi1 -= 2.0 * kPi;
+      if (dphi1 < -kPi) dphi1 += 2.0 * kPi;
+      double dphi2 = xi - clon;
+      if (dphi2 > kPi)  dphi2 -= 2.0 * kPi;
+      if (dphi2 < -kPi) dphi2 += 2.0 * kPi;
+      if (fabs(dphi2 - dphi1) < kPi) {
+        tl = dphi * (dphi1 * f1 + dphi2 * f2) / 2.0;
+      } else {
+        const double fac = (dphi1 > 0.0) ? kPi : -kPi;
+        const double fint = f1 + (f2 - f1) * (fac - dphi1) / fabs(dphi);
+        tl = 0.5 * dphi1 * (dphi1 - fac) * f1 - 0.5 * dphi2 * (dphi2 + fac) * f2 + 0.5 * fac * (dphi1 + dphi2) * fint;
+      }
+    }
+    *tlon = tl; *tlat = tt;
+  }
+}
+
+template <int ORDER>
+__global__ void __launch_bounds__(kClipThreads, XGB_CLIP2_BLOCKS)
+clip2_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const int2* __restrict__ pairs,
+             unsigned long long npairs, SrcMap smap,
+             double* __restrict__ parea, double* __restrict__ pclon, double* __restrict__ pclat,
+             uint32_t* __restrict__ cnt, int* err)
+{
+  static_assert(kClipThreads == 128, "clip2_kernel is written for 128-thread blocks");
+  // flattened arrays FX FY [FS FC] — the edge terms overwrite them in place — plus each polygon's first vertex (P0: x y [sin cos])
+  constexpr int kArrays = (ORDER == 2) ? 4 : 2;
+  constexpr int kFlatDoubles = kArrays * kC2Cap + kArrays * kClipThreads;
+#if XGB_CLIP2_IDX
+  constexpr int kClipDoubles = 2 * kIdxSlots * kClipThreads;
+#else
+  constexpr int kClipDoubles = 4 * kFastCap * kClipThreads;
+#endif
+  constexpr int kSmDoubles = (kFlatDoubles > kClipDoubles) ? kFlatDoubles : kClipDoubles;
+  __shared__ double sm[kSmDoubles];              // clip phase: [A.x A.y B.x B.y][vertex][thread]; then the flattened arrays
+  __shared__ unsigned short s_own[kC2Cap];       // owner thread | edge number << 7 | vertex count << 10 of every flattened vertex
+  __shared__ double s_clon[(ORDER == 2) ? kClipThreads : 1];
+  __shared__ int s_wsum[4];
+#if XGB_CLIP2_SORT
+  __shared__ unsigned char s_perm[kClipThreads];
+  __shared__ unsigned short s_kcnt[4][16];
+#endif
+  __shared__ int s_end;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const unsigned long long p0 = blockIdx.x * (unsigned long long)kClipThreads;
+  if (tid == 0) s_end = kC2Cap;                                   // read after two block barriers
+
+#if XGB_CLIP2_SORT
+  // ---- (1) deal the block's pairs to the threads by cut pattern -------------------------------------------------
+  {
+    const unsigned long long pn = p0 + tid;
+    int key = 15;                                                  // beyond the list / sentinel: last
+    if (pn < npairs) {
+      const int2 q = pairs[pn];
+      if (q.x >= 0) {
+        const long long s = smap.cell(q.x), d = q.y;
+        const Box sb = load_box(src.box + s), db = load_box(dst.box + d);
+        const double dxavg = dst.xavg[d] - src.xavg[s];
+        const double sh = (dxavg < -kPi) ? kTwoPi : ((dxavg > kPi) ? -kTwoPi : 0.0);
+        // destination vertex order (i,j) (i+1,j) (i+1,j+1) (i,j+1): stage 0 cuts at the west side, 1 south, 2 east, 3 north
+        key = (int)(sb.xmin < db.xmin + sh) | ((int)(sb.ymin < db.ymin) << 1) | ((int)(sb.xmax > db.xmax + sh) << 2)
+              | ((int)(sb.ymax > db.ymax) << 3);
+      }
+    }
+    if (tid < 64) (&s_kcnt[0][0])[tid] = 0;
+    __syncthreads();
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int rank = __popc(peers & ((1u << lane) - 1u));
+    if (rank == 0) s_kcnt[wid][key] = (unsigned short)__popc(peers);
+    __syncthreads();
+    if (tid < 16) {
+      // counts -> first position of (warp, key): pairs with smaller keys in every warp, pairs with this key in the warps before
+      const int c0 = s_kcnt[0][tid], c1 = s_kcnt[1][tid], c2 = s_kcnt[2][tid], c3 = s_kcnt[3][tid];
+      int inc = c0 + c1 + c2 + c3;
+      const int tot = inc;
+#pragma unroll
+      for (int dlt = 1; dlt < 16; dlt <<= 1) { const int v = __shfl_up_sync(0xffffu, inc, dlt); if (tid >= dlt) inc += v; }
+      const int kb = inc - tot;
+      s_kcnt[0][tid] = (unsigned short)kb; s_kcnt[1][tid] = (unsigned short)(kb + c0);
+      s_kcnt[2][tid] = (unsigned short)(kb + c0 + c1); s_kcnt[3][tid] = (unsigned short)(kb + c0 + c1 + c2);
+    }
+    __syncthreads();
+    const int pos = s_kcnt[wid][key] + rank;
+    s_perm[pos] = (unsigned char)tid;
+    __syncthreads();
+  }
+  const unsigned long long p = p0 + s_perm[tid];
+#else
+  const unsigned long long p = p0 + tid;
+#endif
+  // Single-sync generate: the launch covers the pair buffer's capacity and the entries past the true count hold the
+  // sentinel (-1, -1) written by pad_pairs_kernel.
+  const bool in_launch = p < npairs;
+  int2 pr = in_launch ? pairs[p] : make_int2(-1, -1);
+  const bool valid = in_launch && pr.x >= 0;
+  if (!valid) pr = make_int2(0, 0);
+  const long long s = smap.cell(pr.x), d = pr.y;
+  const int n1 = valid ? src.nv[s] : 0, n2 = valid ? dst.nv[d] : 0;
+  const double s_xavg = valid ? src.xavg[s] : 0.0;
+  const double dxavg = valid ? dst.xavg[d] - s_xavg : 0.0;
+  const int shift = (dxavg < -kPi) ? 1 : ((dxavg > kPi) ? -1 : 0);
+
+  // ---- (2) Sutherland-Hodgman, one thread per pair --------------------------------------------------------------
+  constexpr int stride = kClipThreads;
+  int n_out = 0;
+  bool own_moments = false;                                       // this thread evaluates its polygon's moments itself
+  double loc[4 * kSlowCap];                                       // only touched on the slow path
+  double *rx = loc, *ry = loc + kSlowCap;
+  double ex[4] = {0.0, 0.0, 0.0, 0.0}, ey[4] = {0.0, 0.0, 0.0, 0.0};   // destination vertices as clip_2dx2d sees them
+#if XGB_CLIP2_IDX
+  double* slot_x = sm + tid;                                      // slot j: x at slot_x[j * stride], y at slot_y[j * stride]
+  double* slot_y = slot_x + kIdxSlots * stride;
+  unsigned long long plist = 0;
+  {
+    double sxv[4] = {0.0, 0.0, 0.0, 0.0}, syv[4] = {0.0, 0.0, 0.0, 0.0};
+    const bool small = valid && n1 <= 4;
+    bool wrap = false;
+    if (small) {
+      // the source cell as clip_2dx2d sees it (create_xgrid.c:1279-1290): pimod when any longitude is outside [0, 2 pi]
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int kk = (k < n1) ? k : 0;
+        sxv[k] = src.vx[(long long)kk * src.ncell + s];
+        syv[k] = src.vy[(long long)kk * src.ncell + s];
+        if (k < n1 && (sxv[k] > kTwoPi || sxv[k] < 0.0)) wrap = true;
+      }
+      if (wrap) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { if (sxv[k] < -kPi) sxv[k] += kTwoPi; else if (sxv[k] > kPi) sxv[k] -= kTwoPi; }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { slot_x[k * stride] = sxv[k]; slot_y[k * stride] = syv[k]; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int kk = (k < n2) ? k : 0;
+        ex[k] = dst_vertex_lon(dst, d, kk, shift, wrap);
+        ey[k] = dst.vy[(long long)kk * dst.ncell + d];
+      }
+    }
+    __syncwarp();
+    n_out = clip_cell_idx(slot_x, sxv, syv, ex, ey, small ? n1 : (valid ? 99 : 0), n2, &plist, err);   // all lanes
+  }
+  __syncwarp();
+  bool fast = true;
+#else
+  constexpr int plane = kFastCap * kClipThreads;
+  double* ax = sm + tid;
+  double* ay = ax + plane;
+  double* bx = ay + plane;
+  double* by = bx + plane;
+  rx = ax; ry = ay;
+  if (valid) {
+    const bool wrap = load_src_poly(src, s, n1, ax, ay, stride);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int kk = (k < n2) ? k : 0;
+      ex[k] = dst_vertex_lon(dst, d, kk, shift, wrap);
+      ey[k] = dst.vy[(long long)kk * dst.ncell + d];
+    }
+  }
+  __syncwarp();
+  {
+    int buf = 0;
+    n_out = clip_cell_fast(ax, ex, ey, n1, n2, &buf, err);       // all lanes; n2 == 0 does nothing
+    rx = buf ? bx : ax; ry = buf ? by : ay;
+  }
+  __syncwarp();
+  bool fast = true;
+#endif
+  int rstride = stride;
+  if (n_out < 0) {
+    // rare: pole cells (more than 4 vertices), non-convex cells, more than 8 vertices at some stage -> reference-sized buffers
+    const bool wrap = load_src_poly(src, s, n1, loc, loc + kSlowCap, 1);
+    n_out = clip_cell<kSlowCap>(loc, loc + kSlowCap, loc + 2 * kSlowCap, loc + 3 * kSlowCap, 1, n1,
+                                dst, d, n2, shift, wrap, &rx, &ry, err);
+    rstride = 1;
+    fast = false;
+    if (n_out < 0) { atomicOr(err, kErrClipOverflow); n_out = 0; }
+    own_moments = n_out > 0;
+  }
+
+  // ---- (3) flatten the block's polygons: exclusive prefix sum of the vertex counts ---------------------------------
+  int nfl = (n_out > 0 && fast) ? n_out : 0;
+  int off;
+  {
+    int inc = nfl;
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, dlt); if (lane >= dlt) inc += v; }
+    if (lane == 31) s_wsum[wid] = inc;
+    __syncthreads();
+    int base = 0;
+#pragma unroll
+    for (int w = 0; w < 3; ++w) if (w < wid) base += s_wsum[w];
+    off = base + inc - nfl;
+  }
+  // Polygons that do not fit the flattened arrays take the per-thread routine.  Offsets grow with the thread number, so the
+  // ones that fit are a prefix of the block's polygons and stay contiguous from slot 0; s_end = where they end.
+  const int tot_all = s_wsum[0] + s_wsum[1] + s_wsum[2] + s_wsum[3];
+  double vx[kFastCap], vy[kFastCap];
+#if XGB_CLIP2_IDX
+#pragma unroll
+  for (int k = 0; k < kFastCap; ++k) {
+    const int sl = (int)(plist >> (4 * k)) & 15;
+    vx[k] = (k < nfl) ? slot_x[sl * stride] : 0.0;
+    vy[k] = (k < nfl) ? slot_y[sl * stride] : 0.0;
+  }
+#else
+#pragma unroll
+  for (int k = 0; k < kFastCap; ++k) {
+    vx[k] = (k < nfl) ? rx[k * stride] : 0.0;
+    vy[k] = (k < nfl) ? ry[k * stride] : 0.0;
+  }
+#endif
+  const bool turned_away = nfl > 0 && off + nfl > kC2Cap;
+  if (turned_away) { atomicMin(&s_end, off); own_moments = true; }
+
+  double aacc = 0.0, lonacc = 0.0, latacc = 0.0;
+  double xarea = 0.0, xclon = 0.0, xclat = 0.0;
+  if (own_moments) {
+    if (turned_away) {                                             // does not fit the flattened arrays: thread-local copy
+#pragma unroll
+      for (int k = 0; k < kFastCap; ++k) { loc[k] = vx[k]; loc[kSlowCap + k] = vy[k]; }
+      rx = loc; ry = loc + kSlowCap; rstride = 1;
+      nfl = 0;
+    }
+    PolyView pv{rx, ry, rstride};
+    double a;
+    poly_moments<ORDER>(pv, n_out, s_xavg, &a, &xclon, &xclat);   // poly_area :805, poly_ctrlon :1091, poly_ctrlat :1092
+    xarea = a;
+  }
+  __syncthreads();                                                // every polygon is in registers: the clip buffers are free
+  double* FX = sm;
+  double* FY = sm + kC2Cap;
+  double* FS = sm + ((ORDER == 2) ? 2 : 0) * kC2Cap;
+  double* FC = sm + ((ORDER == 2) ? 3 : 0) * kC2Cap;
+  double* P0 = sm + kArrays * kC2Cap;                             // [x y sin cos][thread]: vertex 0 of the thread's polygon
+#pragma unroll
+  for (int k = 0; k < kFastCap; ++k)
+    if (k < nfl) {
+      FX[off + k] = vx[k]; FY[off + k] = vy[k];
+      s_own[off + k] = (unsigned short)(tid | (k << 7) | (nfl << 10));
+    }
+  if (nfl > 0) { P0[tid] = vx[0]; P0[kClipThreads + tid] = vy[0]; }
+  if (ORDER == 2) s_clon[tid] = s_xavg;
+  __syncthreads();
+  const int nvtx = min(tot_all, s_end);                           // flattened vertices [0, nvtx), all valid
+  if (ORDER == 2) {
+    for (int e = tid; e < nvtx; e += kClipThreads) {
+      double sv, cv;
+      C2_SINCOS(FY[e], &sv, &cv);
+      FS[e] = sv; FC[e] = cv;
+      const unsigned o = s_own[e];
+      if (((o >> 7) & 7) == 0) { P0[2 * kClipThreads + (o & 127)] = sv; P0[3 * kClipThreads + (o & 127)] = cv; }
+    }
+    __syncthreads();
+  }
+  // Edge pass, 128 edges at a time.  The three terms of edge e overwrite FX/FY/FS[e]: vertex e is read by edge e (this
+  // chunk) and by edge e-1 (this chunk or an earlier one), and a polygon's closing edge reads its first vertex from P0, so
+  // after the barrier nothing still needs what is overwritten.
+  for (int base = 0; base < nvtx; base += kClipThreads) {
+    const int e = base + tid;
+    const bool act = e < nvtx;
+    double xi = 0.0, yi = 0.0, xn = 0.0, yn = 0.0, si = 0.0, ci = 0.0, sn = 0.0, cn = 0.0, clon = 0.0;
+    if (act) {
+      const unsigned o = s_own[e];
+      const int k = (o >> 7) & 7, n = o >> 10, t = o & 127;
+      xi = FX[e]; yi = FY[e];
+      if (ORDER == 2) { si = FS[e]; ci = FC[e]; clon = s_clon[t]; }
+      if (k + 1 < n) {
+        xn = FX[e + 1]; yn = FY[e + 1];
+        if (ORDER == 2) { sn = FS[e + 1]; cn = FC[e + 1]; }
+      } else {
+        xn = P0[t]; yn = P0[kClipThreads + t];
+        if (ORDER == 2) { sn = P0[2 * kClipThreads + t]; cn = P0[3 * kClipThreads + t]; }
+      }
+    }
+    __syncthreads();
+    if (act) {
+      double ta, tl = 0.0, tt = 0.0;
+      edge_terms<ORDER>(xi, yi, xn, yn, si, ci, sn, cn, clon, &ta, &tl, &tt);
+      FX[e] = ta;
+      if (ORDER == 2) { FY[e] = tl; FS[e] = tt; }
+    }
+  }
+  __syncthreads();
+  if (nfl > 0) {
+    for (int k = 0; k < nfl; ++k) {
+      aacc -= FX[off + k];
+      if (ORDER == 2) { lonacc -= FY[off + k]; latacc -= FS[off + k]; }
+    }
+    xarea = (aacc < 0) ? -aacc * kRadius * kRadius : aacc * kRadius * kRadius;
+    if (ORDER == 2) { xclon = lonacc * kRadius * kRadius; xclat = latacc * kRadius * kRadius; }
+  }
+  bool keep = false;
+  if (n_out > 0) {
+    const double m = mask ? mask[s] : 1.0;
+    xarea = xarea * m;
+    const double a1 = src.area[s], a2 = dst.area[d];
+    const double min_area = (a1 < a2) ? a1 : a2;                 // :806
+    keep = (xarea / min_area > kAreaRatioThresh);                // :807
+  }
+  if (valid) parea[p] = keep ? xarea : 0.0;
+  if (keep) {
+    if (ORDER == 2) { pclon[p] = xclon; pclat[p] = xclat; }
+    atomicAdd(&cnt[pr.x], 1u);
+  }
+}
+
+// =============================================================================================
+// clip as TWO kernels (XGB_CLIP_SPLIT, default on): Sutherland-Hodgman | moments.  ncu on the fused clip2_kernel: 8 500 SASS
+// instructions, ~4 500 of them hot, 12 % of the warp samples stalled on instruction fetch at 5 blocks/SM and 24 % at 7 — more
+// resident warps bought nothing.  Each half alone is a small kernel with its own register budget:
+//   clip_sh_kernel   one thread per pair: indexed Sutherland-Hodgman (clip_cell_idx); the block's surviving polygons are
+//                    written back to back (prefix sum of the vertex counts) into the block's own 768-vertex region of a
+//                    global scratch array, plus a 16-bit (offset, count) word per pair.  Pairs that clip to nothing are
+//                    finished here; so are the rare polygons of the generic routine and those that overflow the region.
+//   clip_mom_kernel  the block loads its region (coalesced) and runs the edge-parallel moments of clip2_kernel: sincos per
+//                    vertex, three terms per edge (in place), ordered sums per polygon, area-ratio test, results.
+// The polygons cross HBM once (16 B per vertex written and read: ~2.1 GB per C768 step, hidden behind the arithmetic).
+// =============================================================================================
+#ifndef XGB_CLIP_SPLIT
+#define XGB_CLIP_SPLIT 1
+#endif
+#ifndef XGB_SPLIT_BLOCKS1
+#define XGB_SPLIT_BLOCKS1 6
+#endif
+#ifndef XGB_SPLIT_BLOCKS2
+#define XGB_SPLIT_BLOCKS2 7
+#endif
+constexpr int kWarpCap = 192;             // vertices per warp region (6 per pair; the mean is 3.6)
+constexpr int kSplitCap = 4 * kWarpCap;   // per block of 4 warps
+
+// the tail every pair goes through once its polygon's sums are known (create_xgrid.c:805-820, :1091-1097)
+template <int ORDER>
+__device__ __forceinline__ void clip_finish(const CellSet& src, const CellSet& dst, const double* mask, long long s, long long d,
+                                            unsigned long long p, int srel, double xarea, double xclon, double xclat,
+                                            double* parea, double* pclon, double* pclat, uint32_t* cnt)
+{
+  const double m = mask ? mask[s] : 1.0;
+  xarea = xarea * m;
+  const double a1 = src.area[s], a2 = dst.area[d];
+  const double min_area = (a1 < a2) ? a1 : a2;                   // :806
+  const bool keep = (xarea / min_area > kAreaRatioThresh);       // :807
+  parea[p] = keep ? xarea : 0.0;
+  if (keep) {
+    if (ORDER == 2) { pclon[p] = xclon; pclat[p] = xclat; }
+    atomicAdd(&cnt[srel], 1u);
+  }
+}
+
+template <int ORDER>
+__global__ void __launch_bounds__(kClipThreads, XGB_SPLIT_BLOCKS1)
+clip_sh_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const int2* __restrict__ pairs,
+               unsigned long long npairs, SrcMap smap,
+               double* __restrict__ parea, double* __restrict__ pclon, double* __restrict__ pclat,
+               uint32_t* __restrict__ cnt, double* __restrict__ gvx, double* __restrict__ gvy,
+               unsigned short* __restrict__ gmeta, int* err)
+{
+  static_assert(kClipThreads == 128, "written for 128-thread blocks");
+  // no block barrier anywhere: the slots are thread-private columns and the prefix sum is per warp, so warps run on their own
+  __shared__ double sm[2 * kIdxSlots * kClipThreads];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const unsigned long long p = blockIdx.x * (unsigned long long)kClipThreads + tid;
+  const bool in_launch = p < npairs;
+  int2 pr = in_launch ? pairs[p] : make_int2(-1, -1);
+  const bool valid = in_launch && pr.x >= 0;                      // past the true count: sentinel pairs (pad_pairs_kernel)
+  if (!valid) pr = make_int2(0, 0);
+  const long long s = smap.cell(pr.x), d = pr.y;
+  // everything that depends on (s, d) only is requested at once: one round trip to L2 instead of three
+  const int n1r = src.nv[s], n2r = dst.nv[d];
+  const double s_xavg = src.xavg[s], d_xavg = dst.xavg[d];
+  double sxv[4], syv[4], ex[4], ey[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    sxv[k] = src.vx[(long long)k * src.ncell + s]; syv[k] = src.vy[(long long)k * src.ncell + s];
+    ex[k] = dst.vx[(long long)k * dst.ncell + d];  ey[k] = dst.vy[(long long)k * dst.ncell + d];
+  }
+  const int n1 = valid ? n1r : 0, n2 = valid ? n2r : 0;
+  const double dxavg = valid ? d_xavg - s_xavg : 0.0;
+  const int shift = (dxavg < -kPi) ? 1 : ((dxavg > kPi) ? -1 : 0);
+  constexpr int stride = kClipThreads;
+  double* slot_x = sm + tid;
+  double* slot_y = slot_x + kIdxSlots * stride;
+  unsigned long long plist = 0;
+  int n_out = 0;
+  {
+    const bool small = valid && n1 <= 4;
+    if (n1 == 3) { sxv[3] = sxv[0]; syv[3] = syv[0]; }            // plane 3 of a triangle is not defined
+    if (n2 == 3) { ex[3] = ex[0]; ey[3] = ey[0]; }
+    // the source cell as clip_2dx2d sees it (create_xgrid.c:1279-1290): pimod when any longitude is outside [0, 2 pi]
+    bool wrap = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (sxv[k] > kTwoPi || sxv[k] < 0.0) wrap = true;
+    if (wrap) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { if (sxv[k] < -kPi) sxv[k] += kTwoPi; else if (sxv[k] > kPi) sxv[k] -= kTwoPi; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      slot_x[k * stride] = sxv[k]; slot_y[k * stride] = syv[k];
+      double v = ex[k];                                            // dst_vertex_lon: create_xgrid.c:787-796, then pimod
+      if (shift > 0) v += kTwoPi; else if (shift < 0) v -= kTwoPi;
+      if (wrap) { if (v < -kPi) v += kTwoPi; else if (v > kPi) v -= kTwoPi; }
+      ex[k] = v;
+    }
+    __syncwarp();
+    n_out = clip_cell_idx(slot_x, sxv, syv, ex, ey, small ? n1 : (valid ? 99 : 0), n2, &plist, err);   // all lanes
+  }
+  __syncwarp();
+  bool own = false;                                               // this thread finishes its pair itself
+  double loc[4 * kSlowCap];                                       // only touched on the rare paths
+  double *rx = loc, *ry = loc + kSlowCap;
+  if (n_out < 0) {
+    // rare: pole cells (more than 4 vertices), non-convex cells, more than 8 vertices at some stage -> reference-sized buffers
+    const bool wrap = load_src_poly(src, s, n1, loc, loc + kSlowCap, 1);
+    n_out = clip_cell<kSlowCap>(loc, loc + kSlowCap, loc + 2 * kSlowCap, loc + 3 * kSlowCap, 1, n1,
+                                dst, d, n2, shift, wrap, &rx, &ry, err);
+    if (n_out < 0) { atomicOr(err, kErrClipOverflow); n_out = 0; }
+    own = true;
+  }
+  int nfl = (n_out > 0 && !own) ? n_out : 0;
+  int off;
+  {
+    int inc = nfl;
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, dlt); if (lane >= dlt) inc += v; }
+    off = inc - nfl;
+  }
+  if (nfl > 0 && off + nfl > kWarpCap) {                          // does not fit the warp's region: thread-local copy
+    for (int k = 0; k < nfl; ++k) {
+      const int sl = (int)(plist >> (4 * k)) & 15;
+      loc[k] = slot_x[sl * stride]; loc[kSlowCap + k] = slot_y[sl * stride];
+    }
+    rx = loc; ry = loc + kSlowCap;
+    own = true; nfl = 0;
+  }
+  if (nfl > 0) {
+    const size_t region = ((size_t)blockIdx.x * 4 + wid) * kWarpCap + off;
+    double* ox = gvx + region;
+    double* oy = gvy + region;
+#pragma unroll
+    for (int k = 0; k < kFastCap; ++k)
+      if (k < nfl) {
+        const int sl = (int)(plist >> (4 * k)) & 15;
+        ox[k] = slot_x[sl * stride]; oy[k] = slot_y[sl * stride];
+      }
+  }
+  if (in_launch) gmeta[p] = (unsigned short)((nfl > 0) ? (off | (nfl << 8)) : 0);
+  if (valid && nfl == 0) {
+    if (n_out > 0) {
+      PolyView pv{rx, ry, 1};
+      double a, xclon = 0.0, xclat = 0.0;
+      poly_moments<ORDER>(pv, n_out, s_xavg, &a, &xclon, &xclat); // poly_area :805, poly_ctrlon :1091, poly_ctrlat :1092
+      clip_finish<ORDER>(src, dst, mask, s, d, p, pr.x, a, xclon, xclat, parea, pclon, pclat, cnt);
+    } else {
+      parea[p] = 0.0;
+    }
+  }
+}
+
+// Moments, one WARP per 32 pairs (no block barriers: a warp loads its region, works and stores while the others are at other
+// stages, which is what hides the load latency — ncu on the block-wide version: long-scoreboard 3.4 and barrier 1.4 warps
+// stalled per issued instruction).
+template <int ORDER>
+__global__ void __launch_bounds__(kClipThreads, XGB_SPLIT_BLOCKS2)
+clip_mom_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const int2* __restrict__ pairs,
+                unsigned long long npairs, SrcMap smap,
+                double* __restrict__ parea, double* __restrict__ pclon, double* __restrict__ pclat,
+                uint32_t* __restrict__ cnt, const double* __restrict__ gvx, const double* __restrict__ gvy,
+                const unsigned short* __restrict__ gmeta)
+{
+  constexpr int kArrays = (ORDER == 2) ? 4 : 2;
+  constexpr int kWarpDoubles = kArrays * kWarpCap + kArrays * 32 + ((ORDER == 2) ? 32 : 0);
+  __shared__ double sm_all[4 * kWarpDoubles];
+  __shared__ unsigned short s_own_all[4 * kWarpCap];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const unsigned long long p = blockIdx.x * (unsigned long long)kClipThreads + tid;
+  const unsigned meta = (p < npairs) ? gmeta[p] : 0u;
+  const int nfl = meta >> 8, off = meta & 255;
+  const int nvtx = __reduce_max_sync(0xffffffffu, off + nfl);
+  if (nvtx == 0) return;                                          // warp-uniform: nothing survived the clip here
+  double* sm = sm_all + wid * kWarpDoubles;
+  unsigned short* s_own = s_own_all + wid * kWarpCap;
+  double* FX = sm;
+  double* FY = sm + kWarpCap;
+  double* FS = sm + ((ORDER == 2) ? 2 : 0) * kWarpCap;
+  double* FC = sm + ((ORDER == 2) ? 3 : 0) * kWarpCap;
+  double* P0 = sm + kArrays * kWarpCap;                           // [x y sin cos][lane]: vertex 0 of the lane's polygon
+  double* s_clon = P0 + kArrays * 32;
+  const size_t region = ((size_t)blockIdx.x * 4 + wid) * kWarpCap;
+  for (int e = lane; e < nvtx; e += 32) { FX[e] = gvx[region + e]; FY[e] = gvy[region + e]; }
+  int2 pr = make_int2(0, 0);
+  long long s = 0;
+  double f_mask = 1.0, f_a1 = 1.0, f_a2 = 1.0;                    // the finishing loads, requested now, used at the very end
+  if (nfl > 0) {
+    pr = pairs[p];
+    s = smap.cell(pr.x);
+    if (ORDER == 2) s_clon[lane] = src.xavg[s];
+    f_mask = mask ? mask[s] : 1.0;
+    f_a1 = src.area[s]; f_a2 = dst.area[pr.y];
+#pragma unroll
+    for (int k = 0; k < kFastCap; ++k)
+      if (k < nfl) s_own[off + k] = (unsigned short)(lane | (k << 5) | (nfl << 8));
+  }
+  __syncwarp();
+  if (nfl > 0) { P0[lane] = FX[off]; P0[32 + lane] = FY[off]; }
+  if (ORDER == 2) {
+    for (int e = lane; e < nvtx; e += 32) {
+      double sv, cv;
+      ref_sincos(FY[e], &sv, &cv);
+      FS[e] = sv; FC[e] = cv;
+      const unsigned o = s_own[e];
+      if (((o >> 5) & 7) == 0) { P0[2 * 32 + (o & 31)] = sv; P0[3 * 32 + (o & 31)] = cv; }
+    }
+  }
+  __syncwarp();
+  // Edge pass, 32 edges at a time.  The three terms of edge e overwrite FX/FY/FS[e]: vertex e is read by edge e (this chunk)
+  // and by edge e-1 (this chunk or an earlier one), and a polygon's closing edge reads its first vertex from P0, so after the
+  // warp barrier nothing still needs what is overwritten.
+  for (int base = 0; base < nvtx; base += 32) {
+    const int e = base + lane;
+    const bool act = e < nvtx;
+    double xi = 0.0, yi = 0.0, xn = 0.0, yn = 0.0, si = 0.0, ci = 0.0, sn = 0.0, cn = 0.0, clon = 0.0;
+    if (act) {
+      const unsigned o = s_own[e];
+      const int k = (o >> 5) & 7, n = o >> 8, t = o & 31;
+      xi = FX[e]; yi = FY[e];
+      if (ORDER == 2) { si = FS[e]; ci = FC[e]; clon = s_clon[t]; }
+      if (k + 1 < n) {
+        xn = FX[e + 1]; yn = FY[e + 1];
+        if (ORDER == 2) { sn = FS[e + 1]; cn = FC[e + 1]; }
+      } else {
+        xn = P0[t]; yn = P0[32 + t];
+        if (ORDER == 2) { sn = P0[2 * 32 + t]; cn = P0[3 * 32 + t]; }
+      }
+    }
+    __syncwarp();
+    if (act) {
+      double ta, tl = 0.0, tt = 0.0;
+      edge_terms<ORDER>(xi, yi, xn, yn, si, ci, sn, cn, clon, &ta, &tl, &tt);
+      FX[e] = ta;
+      if (ORDER == 2) { FY[e] = tl; FS[e] = tt; }
+    }
+  }
+  __syncwarp();
+  if (nfl > 0) {
+    double aacc = 0.0, lonacc = 0.0, latacc = 0.0;
+    for (int k = 0; k < nfl; ++k) {
+      aacc -= FX[off + k];
+      if (ORDER == 2) { lonacc -= FY[off + k]; latacc -= FS[off + k]; }
+    }
+    double xarea = (aacc < 0) ? -aacc * kRadius * kRadius : aacc * kRadius * kRadius;
+    xarea = xarea * f_mask;
+    const double min_area = (f_a1 < f_a2) ? f_a1 : f_a2;          // :806
+    const bool keep = (xarea / min_area > kAreaRatioThresh);      // :807
+    parea[p] = keep ? xarea : 0.0;
+    if (keep) {
+      if (ORDER == 2) { pclon[p] = lonacc * kRadius * kRadius; pclat[p] = latacc * kRadius * kRadius; }
+      atomicAdd(&cnt[pr.x], 1u);
+    }
+  }
+}
+
+size_t clip_scratch_vertices(unsigned long long npairs)
+{
+  return (size_t)((npairs + kClipThreads - 1) / kClipThreads) * kSplitCap;
+}
+
 // sentinel pairs from the true count (on the device) to the end of the launch the clip kernel will get
 __global__ void pad_pairs_kernel(int2* __restrict__ pairs, const unsigned long long* __restrict__ npairs_dev, unsigned long long cap)
 {
@@ -1064,14 +1902,33 @@ __global__ void pad_pairs_kernel(int2* __restrict__ pairs, const unsigned long l
 
 void launch_clip(int order, const CellSet& src, const CellSet& dst, const double* mask,
                  const int2* pairs, unsigned long long npairs, const unsigned long long* npairs_dev, const SrcMap& sm,
-                 double* parea, double* pclon, double* pclat, uint32_t* cnt, int* err, cudaStream_t st)
+                 double* parea, double* pclon, double* pclat, uint32_t* cnt, int* err, cudaStream_t st,
+                 double* gvx, double* gvy, unsigned short* gmeta)
 {
   if (npairs == 0) return;
   const unsigned blocks = (unsigned)((npairs + kClipThreads - 1) / kClipThreads);
   ++g_launches;
   if (npairs_dev) { ++g_launches; pad_pairs_kernel<<<148, 256, 0, st>>>(const_cast<int2*>(pairs), npairs_dev, npairs); }
+#if XGB_CLIP_SPLIT
+  if (gvx && gvy && gmeta) {
+    ++g_launches;
+    if (order == 2) {
+      clip_sh_kernel<2><<<blocks, kClipThreads, 0, st>>>(src, dst, mask, pairs, npairs, sm, parea, pclon, pclat, cnt, gvx, gvy, gmeta, err);
+      clip_mom_kernel<2><<<blocks, kClipThreads, 0, st>>>(src, dst, mask, pairs, npairs, sm, parea, pclon, pclat, cnt, gvx, gvy, gmeta);
+    } else {
+      clip_sh_kernel<1><<<blocks, kClipThreads, 0, st>>>(src, dst, mask, pairs, npairs, sm, parea, pclon, pclat, cnt, gvx, gvy, gmeta, err);
+      clip_mom_kernel<1><<<blocks, kClipThreads, 0, st>>>(src, dst, mask, pairs, npairs, sm, parea, pclon, pclat, cnt, gvx, gvy, gmeta);
+    }
+    return;
+  }
+#endif
+#if XGB_CLIP2
+  if (order == 2) clip2_kernel<2><<<blocks, kClipThreads, 0, st>>>(src, dst, mask, pairs, npairs, sm, parea, pclon, pclat, cnt, err);
+  else            clip2_kernel<1><<<blocks, kClipThreads, 0, st>>>(src, dst, mask, pairs, npairs, sm, parea, pclon, pclat, cnt, err);
+#else
   if (order == 2) clip_kernel<2><<<blocks, kClipThreads, 0, st>>>(src, dst, mask, pairs, npairs, npairs_dev, sm, parea, pclon, pclat, cnt, err);
   else            clip_kernel<1><<<blocks, kClipThreads, 0, st>>>(src, dst, mask, pairs, npairs, npairs_dev, sm, parea, pclon, pclat, cnt, err);
+#endif
 }
 
 // =============================================================================================
@@ -1346,6 +2203,91 @@ void launch_order2_finalize(const CellSet& src, const SrcMap& sm, const uint32_t
   cudaEventRecord(join, aux);
   order2_finalize_kernel<<<(unsigned)((ns + threads - 1) / threads), threads, 0, st>>>(src, sm, out_off, area, clon, clat, di, dj);
   cudaStreamWaitEvent(st, join, 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Order 2 over SEVERAL output tiles (conserve_interp.c:148-227, :319-358): the reference adds every output tile's exchange
+// cells into one cell_in[m] record per source cell — output tiles in order, list order inside a tile — BEFORE the
+// AREA_RATIO test and the centroid subtraction, so a source cell that straddles two output tiles is judged on its whole
+// area.  order2_accumulate continues the per-cell sums across generate calls (acc = 3 arrays over all source cells,
+// zeroed by xgb_plan_order2_begin); order2_centroids turns the sums into centroids once; order2_distance subtracts them
+// from one tile's xgrid_clon/area, xgrid_clat/area.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+order2_accumulate_kernel(SrcMap sm, const uint32_t* __restrict__ out_off, const double* __restrict__ area,
+                         const double* __restrict__ clon, const double* __restrict__ clat,
+                         double* __restrict__ acc_a, double* __restrict__ acc_x, double* __restrict__ acc_y)
+{
+  // one warp per source cell: coalesced loads, additions in list order (as order2_finalize_long_kernel)
+  const int lane = threadIdx.x & 31;
+  const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (w >= sm.total()) return;
+  const uint32_t b = out_off[w], e = out_off[w + 1];
+  if (b == e) return;
+  const long long s = sm.cell(w);
+  double sa = acc_a[s], sx = acc_x[s], sy = acc_y[s];
+  for (uint32_t base = b; base < e; base += 32) {
+    const uint32_t k = base + lane;
+    const double va = (k < e) ? area[k] : 0.0, vx = (k < e) ? clon[k] : 0.0, vy = (k < e) ? clat[k] : 0.0;
+    const int m = (e - base < 32u) ? (int)(e - base) : 32;
+    for (int j = 0; j < m; ++j) {
+      sa += __shfl_sync(0xffffffffu, va, j); sx += __shfl_sync(0xffffffffu, vx, j); sy += __shfl_sync(0xffffffffu, vy, j);
+    }
+  }
+  if (lane == 0) { acc_a[s] = sa; acc_x[s] = sx; acc_y[s] = sy; }
+}
+
+__global__ void __launch_bounds__(128)
+order2_centroids_kernel(CellSet src, double* __restrict__ acc_a, double* __restrict__ acc_x, double* __restrict__ acc_y)
+{
+  const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (s >= src.ncell) return;
+  double cx, cy;
+  cell_centroid(src, s, acc_a[s], acc_x[s], acc_y[s], &cx, &cy);
+  acc_x[s] = cx; acc_y[s] = cy;
+}
+
+__global__ void __launch_bounds__(256)
+order2_distance_kernel(long long n, const int* __restrict__ t_in, const int* __restrict__ i_in, const int* __restrict__ j_in,
+                       const TileDesc* __restrict__ tiles, int ntiles, const double* __restrict__ area,
+                       const double* __restrict__ clon, const double* __restrict__ clat,
+                       const double* __restrict__ cen_x, const double* __restrict__ cen_y, double* __restrict__ di, double* __restrict__ dj,
+                       int* err)
+{
+  const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int t = t_in[k];
+  if (t < 0 || t >= ntiles || i_in[k] < 0 || i_in[k] >= tiles[t].nx || j_in[k] < 0 || j_in[k] >= tiles[t].ny) { atomicOr(err, kErrBadIndex); return; }
+  const long long s = tiles[t].cell_off + (long long)j_in[k] * tiles[t].nx + i_in[k];
+  const double a = area[k];
+  double u = clon[k] / a, v = clat[k] / a;                        // conserve_interp.c:256-257
+  u -= cen_x[s]; v -= cen_y[s];                                   // :355-356
+  di[k] = u; dj[k] = v;
+}
+
+void launch_order2_accumulate(const SrcMap& sm, const uint32_t* out_off, const double* area, const double* clon, const double* clat,
+                              double* acc, long long ncell, cudaStream_t st)
+{
+  const long long ns = sm.total();
+  if (ns <= 0) return;
+  ++g_launches;
+  order2_accumulate_kernel<<<(unsigned)((ns * 32 + 127) / 128), 128, 0, st>>>(sm, out_off, area, clon, clat, acc, acc + ncell, acc + 2 * ncell);
+}
+
+void launch_order2_centroids(const CellSet& src, double* acc, cudaStream_t st)
+{
+  ++g_launches;
+  order2_centroids_kernel<<<(unsigned)((src.ncell + 127) / 128), 128, 0, st>>>(src, acc, acc + src.ncell, acc + 2 * src.ncell);
+}
+
+void launch_order2_distance(long long n, const int* t_in, const int* i_in, const int* j_in, const TileDesc* tiles, int ntiles,
+                            const double* area, const double* clon, const double* clat, const double* acc, long long ncell,
+                            double* di, double* dj, int* err, cudaStream_t st)
+{
+  if (n <= 0) return;
+  ++g_launches;
+  order2_distance_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, t_in, i_in, j_in, tiles, ntiles, area, clon, clat,
+                                                                      acc + ncell, acc + 2 * ncell, di, dj, err);
 }
 
 // =============================================================================================

@@ -49,6 +49,7 @@ struct xgb_plan {
 
   // work space
   DevBuf cnt, pair_off, pair_cnt, out_off, pairs, parea, pclon, pclat, scan_tmp, bounds_dev;
+  DevBuf clip_vx, clip_vy, clip_meta;   // polygons between the two clip kernels (xgrid_kernels.cu clip_sh_kernel / clip_mom_kernel)
   size_t heavy_cap = 0;              // entries of the heavy-cell work lists (grown on overflow)
   size_t pairs_cap = 0;              // entries the pair buffers were last sized for (single-pass candidate search)
   DevBuf heavy_ctl, heavy_flag, heavy_list, heavy_items, heavy_pairs;
@@ -58,6 +59,9 @@ struct xgb_plan {
   long long nxgrid = -1;
   unsigned long long npairs = 0;
   int order = 0;
+  // order 2 over several output tiles: per-source-cell sums carried across generate calls (xgb_plan_order2_begin/_end)
+  DevBuf o2_acc, o2_tmp;
+  int o2_state = 0;                  // 0 off, 1 accumulating (generate leaves di/dj unset), 2 centroids ready
 
   // a window enqueued by xgb_plan_generate_async and not yet finished
   bool pending = false;

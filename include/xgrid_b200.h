@@ -68,9 +68,12 @@ int create_xgrid_2dx2d_order2_(const int *nlon_in, const int *nlat_in, const int
  * (globals.h:66-222; declared here with opaque struct tags: callers include the reference's headers, the library mirrors
  * their layout in csrc/fregrid_abi.h and a test pins sizeof/offsetof against the compiled reference).
  *   setup_conserve_interp (conserve_interp.c:42): the generate branch for all (output, input) tile pairs; interp[n].* are
- *     malloc'ed like the reference does (:238-258).  READ / WRITE (remap-file I/O through netCDF) are refused loudly.
- *   do_scalar_conserve_interp (conserve_interp.c:507): order 1 / order 2 / missing values / MONOTONIC, any nz;
- *     cell_measures, cell_methods sum, weight fields and TARGET are refused loudly. */
+ *     malloc'ed like the reference does (:238-258).  Order 2 with several output tiles sums the exchange cells of every
+ *     output tile per source cell before the centroid correction, like :204-221 / :319-358.  READ (:62-125) and WRITE
+ *     (:368-443) go through the classic-netCDF remap-file reader / writer of Part 4 (CDF-1/2/5; netCDF-4/HDF5 files are
+ *     recognised and refused by name).
+ *   do_scalar_conserve_interp (conserve_interp.c:507): order 1 / order 2 per variable (interp_method), missing values,
+ *     MONOTONIC, any nz; weight fields, cell_methods sum, cell_measures and TARGET as in :535-539, :572-585, :841-865. */
 void setup_conserve_interp(int ntiles_in, const void *grid_in /* const Grid_config* */, int ntiles_out,
                            void *grid_out /* Grid_config* */, void *interp /* Interp_config* */, unsigned int opcode);
 void do_scalar_conserve_interp(void *interp /* Interp_config* */, int varid, int ntiles_in, const void *grid_in,
@@ -190,6 +193,19 @@ int xgb_plan_result_device(xgb_plan *p, xgb_xgrid_view *view);
 int xgb_plan_result_host(xgb_plan *p, int *t_in, int *i_in, int *j_in, int *i_out, int *j_out,
                          double *area, double *di, double *dj);
 int xgb_plan_result_centroids_host(xgb_plan *p, double *xgrid_clon, double *xgrid_clat);
+
+/* Order 2 with SEVERAL output tiles (setup_conserve_interp, conserve_interp.c:148-227 and :319-358): the reference adds the
+ * exchange cells of every output tile into one (area, clon, clat) record per source cell — output tiles in order, list
+ * order inside a tile — before the AREA_RATIO test and the centroid subtraction.  Between _begin and _end every order-2
+ * xgb_plan_generate adds its cells to those sums (kept on the device) and leaves di/dj unset; the caller keeps each
+ * tile's lists, areas and raw centroids (xgb_plan_result_host with di = dj = NULL, xgb_plan_result_centroids_host).
+ * _end turns the sums into source-cell centroids; _distance then computes one tile's tile1_distance from its lists (host
+ * arrays, n entries); _reset returns the plan to the one-tile behaviour.  xgb_plan_set_src also resets. */
+int xgb_plan_order2_begin(xgb_plan *p);
+int xgb_plan_order2_end(xgb_plan *p);
+int xgb_plan_order2_distance(xgb_plan *p, long long n, const int *t_in, const int *i_in, const int *j_in, const double *area,
+                             const double *xgrid_clon, const double *xgrid_clat, double *di, double *dj);
+void xgb_plan_order2_reset(xgb_plan *p);
 
 /* get_grid_great_circle_area on the device: which = 0 source cells (concatenated), 1 destination cells */
 int xgb_plan_great_circle_area_host(xgb_plan *p, int which, double *area);

@@ -487,3 +487,96 @@ void ref_regrid_apply_ex_through(RefRegrid *r, void *apply_fn, int interp_method
   for(n=0; n<r->ntiles_in; n++) { r->gin[n].weight = NULL; r->gin[n].weight_exist = 0; }
   free(fin); free(fout); free(var);
 }
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Several OUTPUT tiles (conserve_interp.c:148-227, :319-358: order 2 sums every output tile's exchange cells per source
+ * cell before the centroid correction).  Builds Grid_config[ntiles_in] / Grid_config[ntiles_out] and runs
+ * setup_conserve_interp — the reference's own when setup_fn is NULL, otherwise the implementation behind the pointer
+ * (libxgrid_b200.so's export) on the very same structs.
+ *   lonc_out/latc_out: the output tiles' vertex arrays back to back, each (nx_out[n]+1)*(ny_out[n]+1).
+ * ------------------------------------------------------------------------------------------------------------------- */
+typedef struct { int ntiles_in, ntiles_out; unsigned int opcode; Grid_config *gin, *gout; Interp_config *interp; } RefMulti;
+
+RefMulti *ref_multi_setup(int ntiles_in, const int *nx_in, const int *ny_in, const double *lonc_in, const double *latc_in,
+                          int ntiles_out, const int *nx_out, const int *ny_out, const double *lonc_out, const double *latc_out,
+                          unsigned int opcode, void *setup_fn)
+{
+  RefMulti *r = (RefMulti *)calloc(1, sizeof(RefMulti));
+  size_t off = 0;
+  int n;
+  ref_init_once();
+  r->ntiles_in = ntiles_in; r->ntiles_out = ntiles_out; r->opcode = opcode;
+  r->gin = (Grid_config *)calloc(ntiles_in, sizeof(Grid_config));
+  r->gout = (Grid_config *)calloc(ntiles_out, sizeof(Grid_config));
+  r->interp = (Interp_config *)calloc(ntiles_out, sizeof(Interp_config));
+  for(n=0; n<ntiles_in; n++) {
+    Grid_config *g = r->gin + n;
+    size_t nv = (size_t)(nx_in[n]+1)*(ny_in[n]+1);
+    g->nx = g->nxc = nx_in[n]; g->ny = g->nyc = ny_in[n];
+    g->lonc = (double *)malloc(nv*sizeof(double)); g->latc = (double *)malloc(nv*sizeof(double));
+    memcpy(g->lonc, lonc_in+off, nv*sizeof(double)); memcpy(g->latc, latc_in+off, nv*sizeof(double));
+    off += nv;
+    g->cell_area = (double *)malloc((size_t)g->nx*g->ny*sizeof(double));
+    get_grid_area(&g->nx, &g->ny, g->lonc, g->latc, g->cell_area);
+  }
+  off = 0;
+  for(n=0; n<ntiles_out; n++) {
+    Grid_config *g = r->gout + n;
+    size_t nv = (size_t)(nx_out[n]+1)*(ny_out[n]+1);
+    g->nx = g->nxc = nx_out[n]; g->ny = g->nyc = ny_out[n];
+    g->isc = 0; g->iec = nx_out[n]-1; g->jsc = 0; g->jec = ny_out[n]-1;
+    g->lonc = (double *)malloc(nv*sizeof(double)); g->latc = (double *)malloc(nv*sizeof(double));
+    memcpy(g->lonc, lonc_out+off, nv*sizeof(double)); memcpy(g->latc, latc_out+off, nv*sizeof(double));
+    off += nv;
+    g->cell_area = (double *)malloc((size_t)g->nx*g->ny*sizeof(double));
+    get_grid_area(&g->nx, &g->ny, g->lonc, g->latc, g->cell_area);
+  }
+  if(setup_fn) ((setup_fn_t)setup_fn)(ntiles_in, r->gin, ntiles_out, r->gout, r->interp, opcode & ~(WRITE|READ|CHECK_CONSERVE|LEGACY_CLIP));
+  else setup_conserve_interp(ntiles_in, r->gin, ntiles_out, r->gout, r->interp, opcode & ~(WRITE|READ|CHECK_CONSERVE));
+  return r;
+}
+
+long ref_multi_nxgrid(const RefMulti *r, int n) { return (long)r->interp[n].nxgrid; }
+
+void ref_multi_get(const RefMulti *r, int n, int *t_in, int *i_in, int *j_in, int *i_out, int *j_out, double *area, double *di, double *dj)
+{
+  size_t k = r->interp[n].nxgrid;
+  memcpy(t_in, r->interp[n].t_in, k*sizeof(int));   memcpy(i_in, r->interp[n].i_in, k*sizeof(int));
+  memcpy(j_in, r->interp[n].j_in, k*sizeof(int));   memcpy(i_out, r->interp[n].i_out, k*sizeof(int));
+  memcpy(j_out, r->interp[n].j_out, k*sizeof(int)); memcpy(area, r->interp[n].area, k*sizeof(double));
+  if(di && (r->opcode & CONSERVE_ORDER2)) memcpy(di, r->interp[n].di_in, k*sizeof(double));
+  if(dj && (r->opcode & CONSERVE_ORDER2)) memcpy(dj, r->interp[n].dj_in, k*sizeof(double));
+}
+
+/* do_scalar_conserve_interp on a handle from ref_multi_setup: one variable (interp_method), nz = 1, no missing values;
+ * apply_fn NULL = the reference's.  data_in: source tiles back to back, (nx+2*halo)*(ny+2*halo) each (halo 1 for order 2);
+ * data_out: output tiles back to back. */
+void ref_multi_apply(RefMulti *r, void *apply_fn, int interp_method, const double *data_in, const double *grad_x, const double *grad_y,
+                     const int *grad_mask, double *data_out)
+{
+  Field_config *fin  = (Field_config *)calloc(r->ntiles_in, sizeof(Field_config));
+  Field_config *fout = (Field_config *)calloc(r->ntiles_out, sizeof(Field_config));
+  Var_config *var = (Var_config *)calloc(1, sizeof(Var_config));
+  size_t offd = 0, offg = 0, offo = 0;
+  int n, halo = (interp_method == CONSERVE_ORDER2) ? 1 : 0;
+  strcpy(var->name, "f");
+  var->interp_method = interp_method;
+  for(n=0; n<r->ntiles_in; n++) {
+    size_t nx = r->gin[n].nx, ny = r->gin[n].ny;
+    fin[n].var = var;
+    fin[n].data = (double *)(data_in + offd);
+    offd += (nx+2*halo)*(ny+2*halo);
+    if(halo) {
+      fin[n].grad_x = (double *)(grad_x + offg); fin[n].grad_y = (double *)(grad_y + offg); fin[n].grad_mask = (int *)(grad_mask + offg);
+      offg += nx*ny;
+    }
+  }
+  for(n=0; n<r->ntiles_out; n++) {
+    fout[n].var = var;
+    fout[n].data = data_out + offo;
+    offo += (size_t)r->gout[n].nxc*r->gout[n].nyc;
+  }
+  if(apply_fn) ((apply_fn_t)apply_fn)(r->interp, 0, r->ntiles_in, r->gin, r->ntiles_out, r->gout, fin, fout, r->opcode & ~(CHECK_CONSERVE|LEGACY_CLIP), 1);
+  else do_scalar_conserve_interp(r->interp, 0, r->ntiles_in, r->gin, r->ntiles_out, r->gout, fin, fout, r->opcode & ~CHECK_CONSERVE, 1);
+  free(fin); free(fout); free(var);
+}

@@ -434,12 +434,12 @@ done:
  * setup_conserve_interp — conserve_interp.c:127-367 (generate branch), single destination
  * tile, serial (npes == 1) so the mpp gathers at :204-215 are identities.
  * ---------------------------------------------------------------------------------------- */
-long orc_setup_conserve_interp(int ntiles_in, const int *nx_in, const int *ny_in,
-                               const double *lonc_in, const double *latc_in,
-                               int nx_out, int ny_out, const double *lonc_out, const double *latc_out,
-                               unsigned int opcode, long cap,
-                               int *t_in, int *i_in, int *j_in, int *i_out, int *j_out,
-                               double *area, double *di, double *dj)
+long orc_setup_conserve_interp_ex(int ntiles_in, const int *nx_in, const int *ny_in,
+                                  const double *lonc_in, const double *latc_in,
+                                  int nx_out, int ny_out, const double *lonc_out, const double *latc_out,
+                                  unsigned int opcode, long cap,
+                                  int *t_in, int *i_in, int *j_in, int *i_out, int *j_out,
+                                  double *area, double *di, double *dj, double *xclon_out, double *xclat_out)
 {
   const int order = (opcode & ORC_CONSERVE_ORDER2) ? 2 : 1;
   long total = 0;
@@ -550,8 +550,80 @@ long orc_setup_conserve_interp(int ntiles_in, const int *nx_in, const int *ny_in
     }
   }
 done:
+  if (order == 2 && total > 0) {                      /* the generators' raw xgrid_clon / xgrid_clat, for the checkers */
+    if (xclon_out) memcpy(xclon_out, xclon, (size_t)total*sizeof(double));
+    if (xclat_out) memcpy(xclat_out, xclat, (size_t)total*sizeof(double));
+  }
   free(cell_off); free(c_area); free(c_clon); free(c_clat); free(xclon); free(xclat);
   return total;
+}
+
+long orc_setup_conserve_interp(int ntiles_in, const int *nx_in, const int *ny_in,
+                               const double *lonc_in, const double *latc_in,
+                               int nx_out, int ny_out, const double *lonc_out, const double *latc_out,
+                               unsigned int opcode, long cap,
+                               int *t_in, int *i_in, int *j_in, int *i_out, int *j_out,
+                               double *area, double *di, double *dj)
+{
+  return orc_setup_conserve_interp_ex(ntiles_in, nx_in, ny_in, lonc_in, latc_in, nx_out, ny_out, lonc_out, latc_out, opcode, cap,
+                                      t_in, i_in, j_in, i_out, j_out, area, di, dj, NULL, NULL);
+}
+
+/* The order-2 centroid correction alone (conserve_interp.c:204-221, :256-257, :319-358) for a finished list of ONE output
+ * tile: per source cell the sums of area / xgrid_clon / xgrid_clat in list order, the AREA_RATIO test against the cell's
+ * own area, the analytic centroid otherwise, then di = xgrid_clon/area - centroid.  Lets a full-size list produced on the
+ * GPU (whose areas and raw centroids are checked against the reference on sampled destination bands) be checked for
+ * tile1_distance without running the whole reference generator. */
+void orc_order2_distance(int ntiles_in, const int *nx_in, const int *ny_in, const double *lonc_in, const double *latc_in,
+                         long n, const int *t_in, const int *i_in, const int *j_in,
+                         const double *area, const double *xclon, const double *xclat, double *di, double *dj)
+{
+  size_t ncell_tot = 0, off = 0, offc = 0;
+  size_t *cell_off = (size_t *)malloc((size_t)ntiles_in*sizeof(size_t));
+  double *c_area, *c_clon, *c_clat;
+  int m;
+  long k;
+  for (m = 0; m < ntiles_in; m++) { cell_off[m] = ncell_tot; ncell_tot += (size_t)nx_in[m]*ny_in[m]; }
+  c_area = (double *)calloc(ncell_tot, sizeof(double));
+  c_clon = (double *)calloc(ncell_tot, sizeof(double));
+  c_clat = (double *)calloc(ncell_tot, sizeof(double));
+  for (k = 0; k < n; k++) {                                                   /* :216-221 */
+    size_t ii = cell_off[t_in[k]] + (size_t)j_in[k]*nx_in[t_in[k]] + i_in[k];
+    c_area[ii] += area[k]; c_clon[ii] += xclon[k]; c_clat[ii] += xclat[k];
+    di[k] = xclon[k]/area[k];                                                 /* :256-257 */
+    dj[k] = xclat[k]/area[k];
+  }
+  for (m = 0; m < ntiles_in; m++) {                                           /* :319-349 */
+    const int nx = nx_in[m], ny = ny_in[m];
+    const double *lon = lonc_in + off, *lat = latc_in + off;
+    double *cell_area = (double *)malloc((size_t)nx*ny*sizeof(double));
+    int i, j;
+    orc_get_grid_area(nx, ny, lon, lat, cell_area);
+    for (j = 0; j < ny; j++) for (i = 0; i < nx; i++) {
+      size_t ii = (size_t)j*nx + i, g = offc + ii;
+      if (c_area[g] > 0) {
+        if (fabs(c_area[g] - cell_area[ii])/cell_area[ii] < 1.e-3) {
+          c_clon[g] /= c_area[g];
+          c_clat[g] /= c_area[g];
+        } else {
+          double x[ORC_MV], y[ORC_MV], lo, hi, avg;
+          int nv = orc_cell_poly(lon, lat, nx+1, i, j, x, y, NULL, NULL);
+          orc_minmaxavg(x, nv, &lo, &hi, &avg);
+          c_clon[g] = orc_poly_ctrlon(x, y, nv, avg)/cell_area[ii];
+          c_clat[g] = orc_poly_ctrlat(x, y, nv)/cell_area[ii];
+        }
+      }
+    }
+    free(cell_area);
+    off += (size_t)(nx+1)*(ny+1);
+    offc += (size_t)nx*ny;
+  }
+  for (k = 0; k < n; k++) {                                                   /* :351-358 */
+    size_t ii = cell_off[t_in[k]] + (size_t)j_in[k]*nx_in[t_in[k]] + i_in[k];
+    di[k] -= c_clon[ii];
+    dj[k] -= c_clat[ii];
+  }
+  free(cell_off); free(c_area); free(c_clon); free(c_clat);
 }
 
 /* ------------------------------------------------------------------------------------------

@@ -60,6 +60,18 @@ long orc_setup_conserve_interp(int ntiles_in, const int *nx_in, const int *ny_in
                                int *t_in, int *i_in, int *j_in, int *i_out, int *j_out,
                                double *area, double *di, double *dj);
 
+/* the same, also returning the generators' raw xgrid_clon / xgrid_clat (order 2; may be NULL) */
+long orc_setup_conserve_interp_ex(int ntiles_in, const int *nx_in, const int *ny_in,
+                                  const double *lonc_in, const double *latc_in,
+                                  int nx_out, int ny_out, const double *lonc_out, const double *latc_out,
+                                  unsigned int opcode, long cap,
+                                  int *t_in, int *i_in, int *j_in, int *i_out, int *j_out,
+                                  double *area, double *di, double *dj, double *xclon_out, double *xclat_out);
+/* the order-2 centroid correction alone (conserve_interp.c:204-221, :319-358) for a finished list of one output tile */
+void orc_order2_distance(int ntiles_in, const int *nx_in, const int *ny_in, const double *lonc_in, const double *latc_in,
+                         long n, const int *t_in, const int *i_in, const int *j_in,
+                         const double *area, const double *xclon, const double *xclat, double *di, double *dj);
+
 /* apply (do_scalar_conserve_interp, mean cell_methods, no cell_measures/weights/target) */
 void orc_conserve_apply(int order, long nxgrid, const int *t_in, const int *i_in, const int *j_in,
                         const int *i_out, const int *j_out, const double *area,

@@ -323,3 +323,87 @@ def test_apply_variants_sum_measures_weight_target(pkg):
                                           xgtest.TARGET if tgt else 0, np.ascontiguousarray(fm), None, None, None, got)
             assert np.array_equal(got, want), (cm, usefa, tgt)
         R.ref_regrid_free(ref["handle"])
+
+
+def test_order2_over_several_output_tiles_and_mixed_order_variables(pkg):
+    """(a) conserve_order2 onto a 6-tile output mosaic — the reference sums every output tile's exchange cells
+    per source cell before the AREA_RATIO test and the centroid subtraction (conserve_interp.c:204-221, :319-358), so
+    tile1_distance of a source cell that straddles two output tiles depends on all of them; (b) an order-1 variable
+    followed by an order-2 variable on the same Interp_config (interp_method is per variable, conserve_interp.c:528).
+    Both through the reference's own structs and libxgrid_b200's exported setup_conserve_interp /
+    do_scalar_conserve_interp, against the compiled reference, bit for bit."""
+    import ctypes as C
+    R = xgtest.ref_lib()
+    if R is None:
+        pytest.skip("oracle/_ref not built")
+    L = pkg.lib()
+    setup_fn = C.cast(L.setup_conserve_interp, C.c_void_p)
+    apply_fn = C.cast(L.do_scalar_conserve_interp, C.c_void_p)
+    ni, no = 12, 10
+    lonc, latc = pkg.cubed_sphere_grid(ni)
+    lono, lato = pkg.cubed_sphere_grid(no)
+    href, ref = xgtest.ref_multi_setup(lonc, latc, lono, lato, 2)
+    hgot, got = xgtest.ref_multi_setup(lonc, latc, lono, lato, 2, setup_fn)
+    straddlers = 0
+    for n in range(6):
+        assert got[n]["nxgrid"] == ref[n]["nxgrid"] > 0
+        for k in ("t_in", "i_in", "j_in", "i_out", "j_out", "area", "di", "dj"):
+            assert np.array_equal(got[n][k], ref[n][k]), (n, k)
+    cells = [set(zip(r["t_in"].tolist(), r["j_in"].tolist(), r["i_in"].tolist())) for r in ref]
+    for a in range(6):
+        for b in range(a + 1, 6):
+            straddlers += len(cells[a] & cells[b])
+    assert straddlers > 100                      # the case the per-tile correction got wrong is really exercised
+    # (b) mixed interp_method on one Interp_config
+    hm = xgtest.cubed_sphere_halo_map(lonc, latc)
+    nc = ni * ni
+    rng = np.random.default_rng(5)
+    f = rng.uniform(0, 1, 6 * nc)
+    fh = xgtest.with_halo(f, hm)
+    gx = rng.normal(size=6 * nc); gy = rng.normal(size=6 * nc); gm = np.zeros(6 * nc, np.int32)
+    nout = 6 * no * no
+    for order, data in ((1, f), (2, fh), (1, f), (2, fh)):
+        want = np.zeros(nout); out = np.zeros(nout)
+        a = (gx.ctypes.data, gy.ctypes.data, gm.ctypes.data) if order == 2 else (None, None, None)
+        R.ref_multi_apply(href, None, order, data, *a, want)
+        R.ref_multi_apply(hgot, apply_fn, order, data, *a, out)
+        assert np.array_equal(out, want), order
+
+
+def test_exchange_grid_naming_cells_outside_the_output_tile_is_refused(pkg):
+    """a stale remap file written for another output grid must raise, not write out of bounds"""
+    ni, nlon, nlat = 8, 36, 18
+    lonc, latc = pkg.cubed_sphere_grid(ni)
+    lon2, lat2 = pkg.latlon_grid(nlon, nlat)
+    x = xgtest.oracle_setup(lonc, latc, lon2, lat2, 1)
+    p = pkg.XgridPlan(0)
+    bad = dict(x); bad["j_out"] = x["j_out"].copy(); bad["j_out"][7] = nlat + 3
+    with pytest.raises(pkg.XgridError, match="outside"):
+        p.set_xgrid([(ni, ni)] * 6, nlon, nlat, bad)
+    bad = dict(x); bad["i_out"] = x["i_out"].copy(); bad["i_out"][11] = -1
+    with pytest.raises(pkg.XgridError, match="outside"):
+        p.set_xgrid([(ni, ni)] * 6, nlon, nlat, bad)
+    p.set_xgrid([(ni, ni)] * 6, nlon, nlat, x)          # the plan is still usable
+    p.close()
+
+
+def test_config1_full_size_396_field_levels_three_compared_with_the_oracle(pkg):
+    """BASELINE configs[1] at full size — C96 -> 1440x720 order 2 with gradient terms, 33 levels x 12 times in ONE batched
+    call (what bench.py's apply leg times): three of the 396 remapped field-levels (first, middle, last; a smooth and two
+    random ones) against the CPU oracle's grad_c2l + do_scalar_conserve_interp, bit for bit (oracle metrics handed in)."""
+    c = Case(pkg, 96, 1440, 720, 2)
+    p = c.plan
+    for t, m in enumerate(c.oracle_metrics()):
+        p.grad_set_metrics(t, m)
+    B = 33 * 12
+    rng = np.random.default_rng(1234)
+    base = xgtest.smooth_field(c.lont, c.latt)
+    f = np.stack([(base + 0.01 * (b % 33) + 0.001 * (b // 33)).reshape(-1) if b % 2 == 0 else rng.uniform(0, 1, 6 * c.nc) for b in range(B)])
+    fh = xgtest.with_halo(f, c.hm)
+    out = p.regrid(2, fh.reshape(-1), B).reshape(B, -1)
+    for k in (0, 197, B - 1):
+        ox, oy, om = c.oracle_grad(fh[k])
+        want = xgtest.oracle_apply(c.x, 2, c.tiles, fh[k], c.nlon, c.nlat, ox, oy, om)
+        assert np.array_equal(out[k], want), k
+    assert np.all(np.isfinite(out))
+    p.close()

@@ -159,6 +159,17 @@ def test_gc_tripolar_config3_full_size_properties(pkg):
     if dump:
         m = x["j_in"] >= (tl.shape[0] - 1) - 24
         np.savez_compressed(dump, **{k: x[k][m] for k in ("i_in", "j_in", "i_out", "j_out", "area")})
+    # against the CPU oracle on slabs of source rows (the oracle scans every destination cell per source cell, so a slab of the
+    # full-size problem takes seconds): five mid-latitude rows and the three northernmost rows of the bipolar cap, where the
+    # grid is least lat-lon like.  Same lists in the same order; areas to the great-circle tolerance.
+    ny1 = tl.shape[0] - 1
+    for ja, jb in ((500, 505), (ny1 - 3, ny1)):
+        ref = xgtest.oracle_setup([tl[ja:jb + 1]], [ta[ja:jb + 1]], lon2, lat2, 1 | GC)
+        m = (x["j_in"] >= ja) & (x["j_in"] < jb)
+        assert int(m.sum()) == ref["nxgrid"] > 0, (ja, int(m.sum()), ref["nxgrid"])
+        assert np.array_equal(x["i_in"][m], ref["i_in"]) and np.array_equal(x["j_in"][m], ref["j_in"] + ja)
+        assert np.array_equal(x["i_out"][m], ref["i_out"]) and np.array_equal(x["j_out"][m], ref["j_out"])
+        assert np.max(np.abs(x["area"][m] - ref["area"])) / R2 <= AREA_ATOL_SR
     # tolerances: one ulp of one angle is 2e-16 sr whatever the cell size (absolute term), and the reference's accept test
     # keeps slivers down to 1e-6 of the smaller parent and drops the rest (relative term)
     slack = 2e-5 * a_src + 1e-13 * R2

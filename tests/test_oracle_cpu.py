@@ -115,3 +115,96 @@ def test_row_band_decomposition_concatenates(reflib, pkg):
     cat = {k: np.concatenate([p[k] for p in parts]) for k in ("t_in", "i_in", "j_in", "i_out", "j_out", "area")}
     cat["nxgrid"] = cat["area"].size
     xgtest.assert_xgrid_equal(cat, full, 1, same_order=False, exact=True)
+
+
+def test_reference_embedded_polygon_cases_match_the_oracle():
+    """The 26 hand-built cases of the reference's own print-only harness (create_xgrid.c:2383-3010: poles, tripolar fold,
+    identical boxes, containment, sides through the south pole, twin pole vertices), recorded in full precision from the
+    unmodified reference by tests/golden/make_polycases_golden.py.  The oracle restatement reproduces every one bit for
+    bit: clip_2dx2d_great_circle (1-10), create_xgrid_great_circle (11-14), clip_2dx2d + fix_lon + poly_area (15-26), and the
+    2dx2d / great-circle generators on the quadrilateral pairs taken as 1x1 grids."""
+    O = xgtest.oracle_lib()
+    g = _load("ref_polycases.npz")
+    seen = 0
+    for n in range(1, 27):
+        k = f"c{n:02d}_"
+        x1, y1, x2, y2 = g[k + "lon1"], g[k + "lat1"], g[k + "lon2"], g[k + "lat2"]
+        n1, n2, nlon1, nlat1, nlon2, nlat2 = (int(v) for v in g[k + "dims"])
+        if n <= 10:
+            a, b = g[k + "xyz1"], g[k + "xyz2"]
+            o = [np.zeros(MV) for _ in range(3)]
+            no = O.orc_clip_2dx2d_great_circle(*[np.ascontiguousarray(v) for v in a], 4, *[np.ascontiguousarray(v) for v in b], n2, *o)
+            assert no == int(g[k + "gc_n"]), n
+            assert np.array_equal(np.stack([v[:no] for v in o]), g[k + "gc_xyz"]), n
+        elif n <= 14:
+            cap = 4096
+            bi = [np.zeros(cap, np.int32) for _ in range(4)]
+            xa = np.zeros(cap)
+            nx = O.orc_create_xgrid_great_circle(nlon1, nlat1, nlon2, nlat2, np.ascontiguousarray(x1), np.ascontiguousarray(y1),
+                                                 np.ascontiguousarray(x2), np.ascontiguousarray(y2), np.ones(max(nlon1 * nlat1, 1)), cap,
+                                                 *bi, xa, None, None)
+            assert nx == int(g[k + "gcx_n"]), n
+            assert np.array_equal(np.stack([v[:nx] for v in bi]), g[k + "gcx_idx"]), n
+            assert np.array_equal(xa[:nx], g[k + "gcx_area"]), n
+        else:
+            a1 = np.zeros(MV); b1 = np.zeros(MV); a2 = np.zeros(MV); b2 = np.zeros(MV)
+            a1[:n1] = x1; b1[:n1] = y1; a2[:n2] = x2; b2[:n2] = y2
+            lo = np.zeros(MV); la = np.zeros(MV)
+            no = O.orc_clip_2dx2d(a1, b1, n1, a2, b2, n2, lo, la)
+            assert no == int(g[k + "clip_n"]), n
+            assert np.array_equal(lo[:no], g[k + "clip_lon"]) and np.array_equal(la[:no], g[k + "clip_lat"]), n
+            f1 = O.orc_fix_lon(a1, b1, n1, np.pi); f2 = O.orc_fix_lon(a2, b2, n2, np.pi); fo = O.orc_fix_lon(lo, la, no, np.pi)
+            assert [f1, f2, fo] == g[k + "fix_n"].tolist(), n
+            assert np.array_equal(np.stack([a1[:f1], b1[:f1]]), g[k + "fix1"]) and np.array_equal(np.stack([lo[:fo], la[:fo]]), g[k + "fixo"]), n
+            areas = np.array([O.orc_poly_area(a1, b1, f1), O.orc_poly_area(a2, b2, f2), O.orc_poly_area(lo, la, fo)])
+            assert _close(areas, g[k + "areas"], np.maximum(np.abs(g[k + "areas"]), 1.0)), n
+        if k + "cell_o2" in g:
+            cell = lambda v: np.ascontiguousarray(np.array([v[0], v[1], v[3], v[2]]))
+            bi = [np.zeros(64, np.int32) for _ in range(4)]
+            xa = np.zeros(64); xc = np.zeros(64); yc = np.zeros(64)
+            nx = O.orc_create_xgrid_2dx2d(2, 1, 1, 1, 1, cell(x1), cell(y1), cell(x2), cell(y2), np.ones(1), 64, *bi, xa,
+                                          xc.ctypes.data, yc.ctypes.data)
+            want = g[k + "cell_o2"]
+            assert nx == int(want[0]), n
+            assert _close(np.concatenate([xa[:nx], xc[:nx], yc[:nx]]), want[1:], np.maximum(np.abs(want[1:]), 1.0)), n
+            nx = O.orc_create_xgrid_great_circle(1, 1, 1, 1, cell(x1), cell(y1), cell(x2), cell(y2), np.ones(1), 64, *bi, xa, None, None)
+            want = g[k + "cell_gc"]
+            assert nx == int(want[0]) and np.array_equal(xa[:nx], want[1:]), n
+            seen += 1
+    assert seen >= 14
+
+
+def test_reference_embedded_great_circle_cases_match_the_product_clip(pkg):
+    """cases 1-10 through the product's own great-circle clip (host build of csrc/gc_clip.cuh, the code the kernel runs):
+    same vertex counts; coordinates to one ulp (the reference solves a 3x3 system in x87 long double, the product in
+    double-double)"""
+    g = _load("ref_polycases.npz")
+    L = pkg.lib()
+    for n in range(1, 11):
+        k = f"c{n:02d}_"
+        a, b = g[k + "xyz1"], g[k + "xyz2"]
+        o = [np.zeros(MV) for _ in range(3)]
+        no = L.xgb_gc_clip_host(*[np.ascontiguousarray(v).ctypes.data for v in a], 4, *[np.ascontiguousarray(v).ctypes.data for v in b],
+                                int(g[k + "dims"][1]), *[v.ctypes.data for v in o], None)
+        assert no == int(g[k + "gc_n"]), n
+        if no:
+            assert np.max(np.abs(np.stack([v[:no] for v in o]) - g[k + "gc_xyz"])) <= 4.5e-16, n
+
+
+def test_order2_distance_restatement_equals_the_setup_restatement():
+    """oracle_order2_distance (the centroid correction alone, used to check full-size GPU lists) against the oracle's whole
+    setup_conserve_interp, which the golden vectors and the compiled reference pin"""
+    pkg = xgtest.package()
+    lonc, latc = pkg.cubed_sphere_grid(12)
+    lon2, lat2 = pkg.latlon_grid(72, 36)
+    full = xgtest.oracle_setup(lonc, latc, lon2, lat2, 2, raw=True)
+    di, dj = xgtest.oracle_order2_distance(lonc, latc, full)
+    assert np.array_equal(di, full["di"]) and np.array_equal(dj, full["dj"])
+    if xgtest.ref_lib() is not None:
+        ref = xgtest.ref_setup(lonc, latc, lon2, lat2, 2)
+        assert np.array_equal(full["di"], ref["di"]) and np.array_equal(full["dj"], ref["dj"])
+        for jsc, jec in ((0, 0), (17, 19), (35, 35)):
+            b = xgtest.ref_band_xgrid(lonc, latc, lon2, lat2, 2, jsc, jec)
+            m = (full["j_out"] >= jsc) & (full["j_out"] <= jec)
+            for key in ("t_in", "i_in", "j_in", "i_out", "j_out", "area", "xgrid_clon", "xgrid_clat"):
+                assert np.array_equal(b[key], full[key][m]), (jsc, key)

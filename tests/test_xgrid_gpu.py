@@ -264,6 +264,23 @@ def test_disjoint_grids_give_empty_list(pkg):
     assert xgtest.oracle_setup([lon1], [lat1], lon2, lat2, 1)["nxgrid"] == 0
 
 
+_BAND = {}
+
+
+def _band_job(args):
+    jsc, jec, order = args
+    lonc, latc, lon2, lat2 = _BAND["grids"]
+    return xgtest.ref_band_xgrid(lonc, latc, lon2, lat2, order, jsc, jec)
+
+
+def _ref_bands(lonc, latc, lon2, lat2, order, bands):
+    """the unmodified reference generator on destination row bands, one forked process per band"""
+    import multiprocessing as mp
+    _BAND["grids"] = (lonc, latc, lon2, lat2)
+    with mp.get_context("fork").Pool(min(len(bands), os.cpu_count() or 1)) as pool:
+        return pool.map(_band_job, [(a, b, order) for a, b in bands], chunksize=1)
+
+
 def test_c768_eighth_degree_full_size_properties(pkg):
     """BASELINE configs[3] at full size (the bench workload): C768 -> 2880x1440 order 2.  The oracle needs minutes for it;
     size-independent properties instead: known cell count, reference emission order without duplicates, exchange areas
@@ -275,7 +292,7 @@ def test_c768_eighth_degree_full_size_properties(pkg):
     plan.set_dst(lon2, lat2)
     plan.set_src(lonc, latc)
     n = plan.generate(2)
-    assert n == 16673872                                  # first measured with this library; equals bench.py's config.nxgrid
+    assert n == 16673872                                  # = the unmodified reference's whole-problem count (profiles/r02_cpu_whole_c768.json)
     r = plan.result_host()
     a_src = plan.src_area(); a_dst = plan.dst_area()
     s = r["t_in"].astype(np.int64) * n1 * n1 + r["j_in"].astype(np.int64) * n1 + r["i_in"]
@@ -290,6 +307,41 @@ def test_c768_eighth_degree_full_size_properties(pkg):
     mx = np.bincount(s, weights=r["area"] * r["di"], minlength=a_src.size) / per_src
     my = np.bincount(s, weights=r["area"] * r["dj"], minlength=a_src.size) / per_src
     assert np.percentile(np.abs(mx), 99) < 1e-9 and np.percentile(np.abs(my), 99) < 1e-9
+    # ---- against the compiled reference on destination row bands (the headline config had no oracle comparison):
+    # the unmodified create_xgrid_2dx2d_order2 on 16 evenly spaced rows plus the two polar rows, one process per band like
+    # a fregrid_parallel rank; the GPU list restricted to those rows must be the same list in the same order, areas and
+    # raw centroids bit for bit.  tile1_distance (whole-grid sums per source cell) is then checked for the WHOLE list with
+    # the centroid-correction restatement (pinned to the reference on small grids, tests/test_oracle_cpu.py).
+    if xgtest.ref_lib() is not None:
+        rows = sorted(set([0, nlat - 1] + [int((k + 0.5) * nlat / 16) for k in range(16)]))
+        bands = _ref_bands(lonc, latc, lon2, lat2, 2, [(j, j) for j in rows])
+        checked = 0
+        for j, b in zip(rows, bands):
+            m = r["j_out"] == j
+            assert int(m.sum()) == b["nxgrid"] > 0, (j, int(m.sum()), b["nxgrid"])
+            for k in ("t_in", "i_in", "j_in", "i_out", "j_out"):
+                assert np.array_equal(r[k][m], b[k]), (j, k)
+            if xgtest.libm_matches_ref_trig():
+                for k in ("area", "xgrid_clon", "xgrid_clat"):
+                    assert np.array_equal(r[k][m], b[k]), (j, k)
+            else:
+                assert np.max(np.abs(r["area"][m] - b["area"]) / b["area"]) < 1e-9
+            checked += b["nxgrid"]
+        assert checked > 150000
+        di, dj = xgtest.oracle_order2_distance(lonc, latc, r)
+        if xgtest.libm_matches_ref_trig():
+            assert np.array_equal(di, r["di"]) and np.array_equal(dj, r["dj"])
+        else:
+            assert np.max(np.abs(di - r["di"])) < 1e-9 and np.max(np.abs(dj - r["dj"])) < 1e-9
+    # ---- the WHOLE list against the unmodified reference's whole-problem run (scripts/cpu_whole_c768.py: every destination
+    # row on all host cores, 552 s on 8 cores; profiles/r02_cpu_whole_c768.json), row by row: count, cell pairs, and the bit
+    # patterns of xgrid_area / xgrid_clon / xgrid_clat as order-independent 64-bit sums per destination row
+    gold = np.load(os.path.join(xgtest.GOLDEN_DIR, "c768_rowhash.npz"))
+    assert int(gold["count"].sum()) == n
+    h = xgtest.row_hashes(r, nlat, n1, nlon)
+    assert np.array_equal(h[0], gold["count"]) and np.array_equal(h[1], gold["key"])
+    if xgtest.libm_matches_ref_trig():
+        assert np.array_equal(h[2], gold["area"]) and np.array_equal(h[3], gold["clon"]) and np.array_equal(h[4], gold["clat"])
     # a checksum of the integer lists that the 2-window run must reproduce
     chk = int(np.bitwise_xor.reduce((s * 1315423911 + d * 2654435761) & 0xffffffffffff))
     bounds = plan.partition(2)
@@ -458,3 +510,98 @@ def test_generate_async_queues_windows_and_finish_returns_the_same_result(pkg):
     full = plan.generate_finish()
     assert full > small and full == plan.generate(pkg.CONSERVE_ORDER1)
     plan.close()
+
+
+def test_c3072_thirtysecond_degree_source_slabs_against_the_compiled_reference(pkg):
+    """BASELINE configs[4] (the reference's one published figure: C3072 -> 11520x5760, conserve_order1; 2.7e8 exchange cells
+    for the whole job).  The whole mosaic and the destination are set up on the device at full size; four slabs of source
+    rows (mid-latitude face, rotated face, polar face, rotated face next to its edge) are generated as source windows —
+    the code path of a multi-GPU rank — and, on three destination rows each (first, middle and last row the slab reaches),
+    compared with the unmodified create_xgrid_2dx2d_order1 run on the same source rows and that destination row: same
+    lists, same order, bit-identical areas."""
+    if xgtest.ref_lib() is None:
+        pytest.skip("oracle/_ref not built")
+    import ctypes as C
+    n1, nlon, nlat = 3072, 11520, 5760
+    lonc, latc = pkg.cubed_sphere_grid(n1)
+    plan = pkg.XgridPlan(0)
+    plan.set_dst_latlon(nlon, nlat)                      # built on the device, bit-identical to latlon_grid (tested elsewhere)
+    plan.set_src(lonc, latc)
+    lon2, lat2 = pkg.latlon_grid(nlon, nlat)
+    R = xgtest.ref_lib()
+    R.create_xgrid_2dx2d_order1.restype = C.c_int
+    ci = lambda v: C.byref(C.c_int(v))
+    pv = lambda a: a.ctypes.data_as(C.c_void_p)
+    total = 0
+    for tile, j0, nrows in ((0, 1500, 3), (4, 777, 3), (2, 1530, 2), (5, 40, 3)):
+        begin = tile * n1 * n1 + j0 * n1
+        plan.set_src_window(begin, begin + nrows * n1)
+        n = plan.generate(1)
+        g = plan.result_host()
+        assert n > 0 and np.all(g["t_in"] == tile) and g["j_in"].min() >= j0 and g["j_in"].max() < j0 + nrows
+        lo1 = np.ascontiguousarray(lonc[tile, j0:j0 + nrows + 1]); la1 = np.ascontiguousarray(latc[tile, j0:j0 + nrows + 1])
+        ja, jb = int(g["j_out"].min()), int(g["j_out"].max())
+        mask = np.ones(n1 * nrows)
+        for j in sorted({ja, (ja + jb) // 2, jb}):
+            m = g["j_out"] == j
+            k = int(m.sum())
+            lo2 = np.ascontiguousarray(lon2[j:j + 2]); la2 = np.ascontiguousarray(lat2[j:j + 2])
+            cap = 4 * k + 65536
+            bi = [np.empty(cap, np.int32) for _ in range(4)]
+            xa = np.empty(cap)
+            nr = R.create_xgrid_2dx2d_order1(ci(n1), ci(nrows), ci(nlon), ci(1), pv(lo1), pv(la1), pv(lo2), pv(la2), pv(mask),
+                                             pv(bi[0]), pv(bi[1]), pv(bi[2]), pv(bi[3]), pv(xa))
+            assert nr == k > 0, (tile, j0, j, nr, k)
+            assert np.array_equal(g["i_in"][m], bi[0][:k]) and np.array_equal(g["j_in"][m], bi[1][:k] + j0)
+            assert np.array_equal(g["i_out"][m], bi[2][:k]) and np.all(bi[3][:k] == 0)
+            if xgtest.libm_matches_ref_trig():
+                assert np.array_equal(g["area"][m], xa[:k]), (tile, j0, j)
+            else:
+                assert np.max(np.abs(g["area"][m] - xa[:k]) / xa[:k]) < 1e-9
+            total += k
+        # rows beyond the slab's reach stay empty in the reference too
+        for j in (ja - 1, jb + 1):
+            if 0 <= j < nlat:
+                lo2 = np.ascontiguousarray(lon2[j:j + 2]); la2 = np.ascontiguousarray(lat2[j:j + 2])
+                bi = [np.empty(65536, np.int32) for _ in range(4)]
+                xa = np.empty(65536)
+                assert R.create_xgrid_2dx2d_order1(ci(n1), ci(nrows), ci(nlon), ci(1), pv(lo1), pv(la1), pv(lo2), pv(la2), pv(mask),
+                                                   pv(bi[0]), pv(bi[1]), pv(bi[2]), pv(bi[3]), pv(xa)) == 0
+    plan.close()
+    assert total > 2000
+
+
+def test_reference_embedded_polygon_cases_through_the_c_abi(pkg):
+    """The reference's own 26 hand-built polygon cases (create_xgrid.c:2383-3010; tests/golden/ref_polycases.npz, recorded from
+    the unmodified reference): every quadrilateral pair taken as two 1x1 grids through create_xgrid_2dx2d_order2 and
+    create_xgrid_great_circle of the C ABI, and the small-grid great-circle cases 11-13 — poles, sides through the south
+    pole, identical boxes, containment.  Counts and lists exact; 2dx2d areas / centroids bit-identical; great-circle areas
+    to the great-circle tolerance."""
+    g = np.load(os.path.join(xgtest.GOLDEN_DIR, "ref_polycases.npz"))
+    cell = lambda v: np.array([[v[0], v[1]], [v[3], v[2]]])
+    seen = 0
+    for n in range(1, 27):
+        k = f"c{n:02d}_"
+        x1, y1, x2, y2 = g[k + "lon1"], g[k + "lat1"], g[k + "lon2"], g[k + "lat2"]
+        if k + "cell_o2" in g:
+            want = g[k + "cell_o2"]
+            r = pkg.create_xgrid_2dx2d_order2(cell(x1), cell(y1), cell(x2), cell(y2))
+            assert r[0] == int(want[0]), n
+            got = np.concatenate([r[5], r[6], r[7]])
+            if xgtest.libm_matches_ref_trig():
+                assert np.array_equal(got, want[1:]), n
+            else:
+                assert np.allclose(got, want[1:], rtol=1e-9, atol=1.0), n
+            want = g[k + "cell_gc"]
+            r = pkg.create_xgrid_great_circle(cell(x1), cell(y1), cell(x2), cell(y2))
+            assert r[0] == int(want[0]), n
+            assert np.max(np.abs(r[5] - want[1:]), initial=0.0) / xgtest.RADIUS ** 2 <= 8e-15, n
+            seen += 1
+        if 11 <= n <= 13:
+            n1, n2, nlon1, nlat1, nlon2, nlat2 = (int(v) for v in g[k + "dims"])
+            r = pkg.create_xgrid_great_circle(x1.reshape(nlat1 + 1, nlon1 + 1), y1.reshape(nlat1 + 1, nlon1 + 1),
+                                              x2.reshape(nlat2 + 1, nlon2 + 1), y2.reshape(nlat2 + 1, nlon2 + 1))
+            assert r[0] == int(g[k + "gcx_n"]), n
+            assert np.array_equal(np.stack(r[1:5]), g[k + "gcx_idx"]), n
+            assert np.max(np.abs(r[5] - g[k + "gcx_area"]), initial=0.0) / xgtest.RADIUS ** 2 <= 8e-15, n
+    assert seen >= 14

@@ -52,6 +52,9 @@ def oracle_lib():
         L.orc_create_xgrid_2dx2d.argtypes = [C.c_int] * 5 + [dp] * 5 + [C.c_long] + [ip] * 4 + [dp, vp, vp]
         L.orc_setup_conserve_interp.restype = C.c_long
         L.orc_setup_conserve_interp.argtypes = [C.c_int, ip, ip, dp, dp, C.c_int, C.c_int, dp, dp, C.c_uint, C.c_long] + [ip] * 5 + [dp, vp, vp]
+        L.orc_setup_conserve_interp_ex.restype = C.c_long
+        L.orc_setup_conserve_interp_ex.argtypes = [C.c_int, ip, ip, dp, dp, C.c_int, C.c_int, dp, dp, C.c_uint, C.c_long] + [ip] * 5 + [dp, vp, vp, vp, vp]
+        L.orc_order2_distance.argtypes = [C.c_int, ip, ip, dp, dp, C.c_long, ip, ip, ip, dp, dp, dp, dp, dp]
         L.orc_conserve_apply.argtypes = [C.c_int, C.c_long] + [ip] * 5 + [dp, vp, vp, C.c_int, ip, ip, dp, vp, vp, vp,
                                          C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, dp]
         L.orc_libm_trig.argtypes = [C.c_long] + [dp] * 5
@@ -145,6 +148,12 @@ def ref_lib():
         L.stub_dim_size.restype = C.c_long
         L.ref_regrid_setup_through.restype = vp
         L.ref_regrid_setup_through.argtypes = [vp, vp]
+        L.ref_multi_setup.restype = vp
+        L.ref_multi_setup.argtypes = [C.c_int, ip, ip, dp, dp, C.c_int, ip, ip, dp, dp, C.c_uint, vp]
+        L.ref_multi_nxgrid.restype = C.c_long
+        L.ref_multi_nxgrid.argtypes = [vp, C.c_int]
+        L.ref_multi_get.argtypes = [vp, C.c_int] + [ip] * 5 + [dp, vp, vp]
+        L.ref_multi_apply.argtypes = [vp, vp, C.c_int, dp, vp, vp, vp, dp]
         L.ref_regrid_apply_through.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint, dp, vp, vp, vp, dp]
         L.fix_lon.argtypes = [dp, dp, C.c_int, C.c_double]
         L.poly_area.restype = C.c_double
@@ -193,8 +202,9 @@ def _trim(out, n):
     return res
 
 
-def oracle_setup(lonc, latc, lon2, lat2, opcode, cap=None):
-    """oracle restatement of setup_conserve_interp for a source mosaic and one destination tile."""
+def oracle_setup(lonc, latc, lon2, lat2, opcode, cap=None, raw=False):
+    """oracle restatement of setup_conserve_interp for a source mosaic and one destination tile.
+    raw=True (order 2): also the generators' raw xgrid_clon / xgrid_clat."""
     L = oracle_lib()
     nx, ny, lon, lat = _tiles(lonc, latc)
     lon2 = np.ascontiguousarray(lon2, np.float64); lat2 = np.ascontiguousarray(lat2, np.float64)
@@ -203,13 +213,81 @@ def oracle_setup(lonc, latc, lon2, lat2, opcode, cap=None):
     if cap is None:
         cap = int(12 * max(int((nx * ny).sum()), nx2 * ny2)) + 4096
     out = _alloc(cap, order)
-    n = L.orc_setup_conserve_interp(len(nx), nx, ny, lon, lat, nx2, ny2, lon2.ravel(), lat2.ravel(), opcode, cap,
-                                    out["t_in"], out["i_in"], out["j_in"], out["i_out"], out["j_out"], out["area"],
-                                    out["di"].ctypes.data if order == 2 else None,
-                                    out["dj"].ctypes.data if order == 2 else None)
+    if raw and order == 2:
+        out["xgrid_clon"] = np.empty(cap); out["xgrid_clat"] = np.empty(cap)
+    n = L.orc_setup_conserve_interp_ex(len(nx), nx, ny, lon, lat, nx2, ny2, lon2.ravel(), lat2.ravel(), opcode, cap,
+                                       out["t_in"], out["i_in"], out["j_in"], out["i_out"], out["j_out"], out["area"],
+                                       out["di"].ctypes.data if order == 2 else None,
+                                       out["dj"].ctypes.data if order == 2 else None,
+                                       out["xgrid_clon"].ctypes.data if "xgrid_clon" in out else None,
+                                       out["xgrid_clat"].ctypes.data if "xgrid_clat" in out else None)
     if n < 0:
         raise RuntimeError("oracle capacity exceeded")
     return _trim(out, n)
+
+
+def oracle_order2_distance(lonc, latc, x):
+    """tile1_distance (di, dj) of a finished one-output-tile list from its areas and raw centroids: the order-2 centroid
+    correction alone (conserve_interp.c:204-221, :319-358), oracle/xgrid_oracle.c orc_order2_distance"""
+    L = oracle_lib()
+    nx, ny, lon, lat = _tiles(lonc, latc)
+    n = int(x["area"].shape[0])
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    f64 = lambda a: np.ascontiguousarray(a, np.float64)
+    di = np.empty(n); dj = np.empty(n)
+    L.orc_order2_distance(len(nx), nx, ny, lon, lat, n, i32(x["t_in"]), i32(x["i_in"]), i32(x["j_in"]), f64(x["area"]),
+                          f64(x["xgrid_clon"]), f64(x["xgrid_clat"]), di, dj)
+    return di, dj
+
+
+def ref_band_xgrid(lonc, latc, lon2, lat2, order, jsc, jec):
+    """The UNMODIFIED reference generators create_xgrid_2dx2d_order1/2 (create_xgrid.c:621, :893) on destination rows
+    [jsc, jec] of a lat-lon grid, one call per source tile with setup_conserve_interp's latitude trim (conserve_interp.c:
+    169-200) — what a fregrid_parallel rank owning that band computes, but with the raw xgrid_clon / xgrid_clat kept
+    (setup_conserve_interp's own di/dj of a band differ from the whole-grid run: its per-cell sums only see the band).
+    -> dict t_in, i_in, j_in, i_out, j_out (GLOBAL row), area[, xgrid_clon, xgrid_clat]"""
+    R = ref_lib()
+    nxs, nys, _, _ = _tiles(lonc, latc)
+    lo2 = np.ascontiguousarray(lon2[jsc:jec + 2]); la2 = np.ascontiguousarray(lat2[jsc:jec + 2])
+    ny2, nx2 = lo2.shape[0] - 1, lo2.shape[1] - 1
+    y_min, y_max = la2.min(), la2.max()
+    cap = 64 * nx2 * ny2 + 65536
+    bufs = [np.empty(cap, np.int32) for _ in range(4)]
+    xa = np.empty(cap); xc = np.empty(cap); yc = np.empty(cap)
+    ci = lambda v: C.byref(C.c_int(v))
+    pv = lambda a: a.ctypes.data_as(C.c_void_p)
+    parts = {k: [] for k in ("t_in", "i_in", "j_in", "i_out", "j_out", "area", "xgrid_clon", "xgrid_clat")}
+    for m in range(len(nxs)):
+        lo1 = np.ascontiguousarray(lonc[m], np.float64); la1 = np.ascontiguousarray(latc[m], np.float64)
+        ny1, nx1 = lo1.shape[0] - 1, lo1.shape[1] - 1
+        rows_gt = np.nonzero((la1 > y_min).any(axis=1))[0]
+        rows_lt = np.nonzero((la1 < y_max).any(axis=1))[0]
+        jstart = max(0, (rows_gt.min() if rows_gt.size else ny1) - 1)
+        jend = min(ny1 - 1, (rows_lt.max() if rows_lt.size else -1) + 1)
+        ny_now = jend - jstart + 1
+        if ny_now <= 0:
+            continue
+        mask = np.ones(nx1 * ny_now)
+        a_lo = np.ascontiguousarray(lo1[jstart:jstart + ny_now + 1]); a_la = np.ascontiguousarray(la1[jstart:jstart + ny_now + 1])
+        if order == 2:
+            R.create_xgrid_2dx2d_order2.restype = C.c_int
+            n = R.create_xgrid_2dx2d_order2(ci(nx1), ci(ny_now), ci(nx2), ci(ny2), pv(a_lo), pv(a_la), pv(lo2), pv(la2), pv(mask),
+                                            pv(bufs[0]), pv(bufs[1]), pv(bufs[2]), pv(bufs[3]), pv(xa), pv(xc), pv(yc))
+        else:
+            R.create_xgrid_2dx2d_order1.restype = C.c_int
+            n = R.create_xgrid_2dx2d_order1(ci(nx1), ci(ny_now), ci(nx2), ci(ny2), pv(a_lo), pv(a_la), pv(lo2), pv(la2), pv(mask),
+                                            pv(bufs[0]), pv(bufs[1]), pv(bufs[2]), pv(bufs[3]), pv(xa))
+        assert 0 <= n <= cap
+        parts["t_in"].append(np.full(n, m, np.int32)); parts["i_in"].append(bufs[0][:n].copy())
+        parts["j_in"].append(bufs[1][:n] + jstart); parts["i_out"].append(bufs[2][:n].copy())
+        parts["j_out"].append(bufs[3][:n] + jsc); parts["area"].append(xa[:n].copy())
+        if order == 2:
+            parts["xgrid_clon"].append(xc[:n].copy()); parts["xgrid_clat"].append(yc[:n].copy())
+    out = {k: (np.concatenate(v) if v else np.empty(0)) for k, v in parts.items() if v or k in ("area",)}
+    for k in ("t_in", "i_in", "j_in", "i_out", "j_out"):
+        out[k] = out.get(k, np.empty(0, np.int32)).astype(np.int32)
+    out["nxgrid"] = int(out["area"].shape[0])
+    return out
 
 
 def ref_setup(lonc, latc, lon2, lat2, opcode, jsc=None, jec=None, keep=False, remap=None):
@@ -240,6 +318,60 @@ def ref_setup(lonc, latc, lon2, lat2, opcode, jsc=None, jec=None, keep=False, re
     else:
         L.ref_regrid_free(r)
     return res
+
+
+def ref_multi_setup(lonc, latc, lonc_out, latc_out, opcode, setup_fn=None):
+    """setup_conserve_interp over SEVERAL output tiles (oracle/ref_driver.c ref_multi_setup): the reference's own when
+    setup_fn is None, else the implementation behind the function pointer.  -> (handle, [per-output-tile dict])"""
+    L = ref_lib()
+    nx, ny, lon, lat = _tiles(lonc, latc)
+    nxo, nyo, lono, lato = _tiles(lonc_out, latc_out)
+    order = 2 if opcode & ORDER2 else 1
+    devnull = os.open(os.devnull, os.O_WRONLY); saved = os.dup(1); os.dup2(devnull, 1)   # the NOTE line
+    try:
+        h = L.ref_multi_setup(len(nx), nx, ny, lon, lat, len(nxo), nxo, nyo, lono, lato, opcode | LEGACY_CLIP, setup_fn)
+    finally:
+        os.dup2(saved, 1); os.close(saved); os.close(devnull)
+    res = []
+    for n in range(len(nxo)):
+        k = L.ref_multi_nxgrid(h, n)
+        out = _alloc(max(k, 1), order)
+        if k:
+            L.ref_multi_get(h, n, out["t_in"], out["i_in"], out["j_in"], out["i_out"], out["j_out"], out["area"],
+                            out["di"].ctypes.data if order == 2 else None, out["dj"].ctypes.data if order == 2 else None)
+        res.append(_trim(out, k))
+    return h, res
+
+
+def latlon_grid_np(nlon, nlat, lonbegin=0.0, lonend=360.0, latbegin=-90.0, latend=90.0):
+    """fregrid's --nlon/--nlat output grid (get_output_grid_by_size, fregrid_util.c:588-603) in plain Python/numpy — the
+    CPU legs (bench.py --impl reference, scripts/cpu_whole_c768.py) build their input without loading the product library;
+    bit-identical to pkg.latlon_grid (tests/test_capi_cpu.py)"""
+    d2r = np.pi / 180
+    dlon = (lonend - lonbegin) / nlon; dlat = (latend - latbegin) / nlat
+    lon1d = np.array([(lonbegin + i * dlon) * d2r for i in range(nlon + 1)])
+    lat1d = np.array([(latbegin + j * dlat) * d2r for j in range(nlat + 1)])
+    return (np.ascontiguousarray(np.broadcast_to(lon1d, (nlat + 1, nlon + 1))),
+            np.ascontiguousarray(np.broadcast_to(lat1d[:, None], (nlat + 1, nlon + 1))))
+
+
+def row_hashes(x, nlat, n1, nlon):
+    """per destination row of an exchange-grid list: count and order-independent 64-bit sums (wrapping) of the cell-pair
+    keys and of the bit patterns of xgrid_area / xgrid_clon / xgrid_clat -> uint64 [5, nlat].  Two lists with equal row hashes
+    hold the same cells with the same floating-point fields (tests/golden/c768_rowhash.npz: the unmodified reference's
+    whole C768 -> 1/8 degree list, scripts/cpu_whole_c768.py)."""
+    j = x["j_out"].astype(np.int64)
+    s = (x["t_in"].astype(np.uint64) * np.uint64(n1 * n1) + x["j_in"].astype(np.uint64) * np.uint64(n1) + x["i_in"].astype(np.uint64))
+    d = (x["j_out"].astype(np.uint64) * np.uint64(nlon) + x["i_out"].astype(np.uint64))
+    out = np.zeros((5, nlat), np.uint64)
+    with np.errstate(over="ignore"):
+        key = s * np.uint64(1315423911) + d * np.uint64(2654435761)
+        np.add.at(out[0], j, np.uint64(1))
+        np.add.at(out[1], j, key)
+        for r, k in ((2, "area"), (3, "xgrid_clon"), (4, "xgrid_clat")):
+            if k in x:
+                np.add.at(out[r], j, np.ascontiguousarray(x[k]).view(np.uint64))
+    return out
 
 
 def ref_cubed_sphere(ni, centers=False):
