@@ -460,16 +460,19 @@ def run_gpu_arm(args):
         return
     # ---- end to end through the C ABI with host buffers (pinned), every step: H2D grids, generate, D2H result
     h_lon1 = torch.from_numpy(np.ascontiguousarray(lonc)).pin_memory(); h_lat1 = torch.from_numpy(np.ascontiguousarray(latc)).pin_memory()
-    h_lon2 = torch.from_numpy(lon2).pin_memory(); h_lat2 = torch.from_numpy(lat2).pin_memory()
     cap = int(nx * 1.02) + 1024
     hb = {k: torch.empty(cap, dtype=torch.int32).pin_memory() for k in ("t_in", "i_in", "j_in", "i_out", "j_out")}
     hb.update({k: torch.empty(cap, dtype=torch.float64).pin_memory() for k in (("area", "di", "dj") if order == 2 else ("area",))})
     nx1 = np.full(6, n, np.int32)
 
+    e2e_windows = my_windows if world > 1 else [(bounds[0], bounds[1])]
+    h2d_box = [0]
+
     def e2e_step():
-        plan.set_dst(h_lon2.numpy(), h_lat2.numpy())
-        plan.set_src_flat(nx1, nx1, h_lon1.numpy().reshape(-1), h_lat1.numpy().reshape(-1))
-        set_windows()
+        # what a caller with host grids does every time: the --nlon/--nlat destination is built on the device (nothing to upload),
+        # the rank uploads and precomputes only the source rows of its own windows, the result comes back to pinned host memory
+        plan.set_dst_latlon(nlon, nlat)
+        h2d_box[0] = plan.set_src_sharded(nx1, nx1, h_lon1.numpy().reshape(-1), h_lat1.numpy().reshape(-1), e2e_windows)
         # generate in pieces; each piece is downloaded on a second stream while the next is computed
         return plan.generate_to_host(opcode, hb, nchunks=args.e2e_chunks)
 
@@ -487,8 +490,13 @@ def run_gpu_arm(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
-    h2d = (h_lon1.numel() + h_lat1.numel() + h_lon2.numel() + h_lat2.numel()) * 8
+    h2d = h2d_box[0]                                   # this rank's share of the source grid (the destination is built on the device)
+    h2d_t = torch.tensor([h2d, 0], dtype=torch.int64, device=dev)
     d2h = k * (5 * 4 + (3 if order == 2 else 1) * 8)
+    h2d_t[1] = d2h
+    if world > 1:
+        dist.all_reduce(h2d_t, op=dist.ReduceOp.SUM)
+    h2d, d2h = int(h2d_t[0].item()), int(h2d_t[1].item())          # whole job
 
     apply = None
     if not args.no_apply:
@@ -551,7 +559,8 @@ def run_gpu_arm(args):
             "clocks": clocks, "gpu_launches": launches_total,
             "e2e": {"value": nx_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms, "steps": e2e_steps,
-                    "api": f"set_dst + set_src (pinned host grids) + xgb_plan_generate_to_host in {args.e2e_chunks} pieces (pinned host result)"},
+                    "api": f"xgb_plan_set_dst_latlon + xgb_plan_set_src_sharded (pinned host source grid, each rank its own rows) + "
+                           f"xgb_plan_generate_to_host in {args.e2e_chunks} pieces (pinned host result); bytes are whole-job sums over the ranks"},
             "roofline": roofline, "phase_ms": phases, "per_rank": per_rank, "cpu_baseline": cpu, "apply": apply,
             "parity_checked_xcells": parity_checked, "multi_gpu_parity": multi_parity}
     print(json.dumps(line), flush=True)

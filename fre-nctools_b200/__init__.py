@@ -72,6 +72,7 @@ def lib():
     L.xgb_plan_set_dst_latlon.argtypes = [vp, C.c_int, C.c_int] + [C.c_double] * 4
     L.xgb_plan_set_src.argtypes = [vp, C.c_int, _ip, _ip, vp, vp, vp, C.c_int]
     L.xgb_plan_set_src_window.argtypes = [vp, C.c_longlong, C.c_longlong]
+    L.xgb_plan_set_src_sharded.argtypes = [vp, C.c_int, _ip, _ip, vp, vp, vp, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     L.xgb_plan_partition.argtypes = [vp, C.c_int, C.POINTER(C.c_longlong)]
     L.xgb_plan_set_src_windows.argtypes = [vp, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     L.xgb_plan_window_counts.argtypes = [vp, C.POINTER(C.c_longlong)]
@@ -125,7 +126,8 @@ def lib():
     L.xgb_poly_moments_site_host.restype = None
     L.xgb_poly_moments_site_host.argtypes = [C.c_int, C.c_int, vp, vp, C.c_double, vp]
     L.get_maxxgrid.restype = C.c_int
-    for name in ("create_xgrid_2dx2d_order1", "create_xgrid_2dx2d_order2"):
+    for name in ("create_xgrid_2dx2d_order1", "create_xgrid_2dx2d_order2", "create_xgrid_1dx2d_order1", "create_xgrid_1dx2d_order2",
+                 "create_xgrid_2dx1d_order1", "create_xgrid_2dx1d_order2"):
         getattr(L, name).restype = C.c_int
     _LIB = L
     return L
@@ -265,6 +267,29 @@ class XgridPlan:
         self._ck(self._L.xgb_plan_set_src(self._p, len(nx), nxa, nya, pl, pa, pm, dl))
         self.tiles = [(int(a), int(b)) for a, b in zip(nx, ny)]
         self.ncell_src = sum(a * b for a, b in self.tiles)
+
+    def set_src_sharded(self, nx, ny, lon, lat, windows, mask=None):
+        """the mosaic for a rank that only generates `windows` [(begin, end), ...]: uploads the vertex rows they touch and
+        precomputes their cells only (xgb_plan_set_src_sharded); lon/lat: flat host arrays of the WHOLE mosaic (pinned for
+        asynchronous copies).  -> bytes copied to the device"""
+        nxa = (C.c_int * len(nx))(*[int(v) for v in nx]); nya = (C.c_int * len(ny))(*[int(v) for v in ny])
+        pl, dl, kl = _f64_ptr(lon); pa, da, ka = _f64_ptr(lat); pm, dm, km = _f64_ptr(mask)
+        if dl or da or dm:
+            raise TypeError("xgb_plan_set_src_sharded takes host arrays")
+        n = len(windows)
+        b = (C.c_longlong * n)(*[int(w[0]) for w in windows]); e = (C.c_longlong * n)(*[int(w[1]) for w in windows])
+        self._ck(self._L.xgb_plan_set_src_sharded(self._p, len(nx), nxa, nya, pl, pa, pm, n, b, e))
+        self.tiles = [(int(a), int(c)) for a, c in zip(nx, ny)]
+        self.ncell_src = sum(a * c for a, c in self.tiles)
+        self._nwin = n
+        nbytes, off = 0, 0
+        for a, c in self.tiles:                          # what the call copied: vertex rows j0 .. j1+1 of every (window, tile) overlap
+            for wb, we in windows:
+                lo, hi = max(wb, off), min(we, off + a * c)
+                if hi > lo:
+                    nbytes += ((hi - 1 - off) // a - (lo - off) // a + 2) * (a + 1) * 16 + (8 * (hi - lo) if mask is not None else 0)
+            off += a * c
+        return nbytes
 
     def set_src_window(self, begin, end):
         self._ck(self._L.xgb_plan_set_src_window(self._p, int(begin), int(end)))
@@ -568,6 +593,52 @@ def create_xgrid_2dx2d_order1(lon_in, lat_in, lon_out, lat_out, mask_in=None):
 def create_xgrid_2dx2d_order2(lon_in, lat_in, lon_out, lat_out, mask_in=None):
     """create_xgrid.c:893 — returns (nxgrid, i_in, j_in, i_out, j_out, xgrid_area, xgrid_clon, xgrid_clat)."""
     return _create_xgrid(2, lon_in, lat_in, lon_out, lat_out, mask_in)
+
+
+def _create_xgrid_box(kind, order, lon_in, lat_in, lon_out, lat_out, mask_in=None, capacity=None):
+    """create_xgrid_1dx2d_* (kind "1dx2d": lon_in/lat_in are 1-D cell bounds, lon_out/lat_out 2-D vertex arrays) and
+    create_xgrid_2dx1d_* (kind "2dx1d": the other way round), create_xgrid.c:208-598"""
+    L = lib()
+    f64 = lambda a: np.ascontiguousarray(a, np.float64)
+    lon_in, lat_in, lon_out, lat_out = f64(lon_in), f64(lat_in), f64(lon_out), f64(lat_out)
+    if kind == "1dx2d":
+        nlon_in, nlat_in = lon_in.size - 1, lat_in.size - 1
+        nlat_out, nlon_out = lon_out.shape[0] - 1, lon_out.shape[1] - 1
+    else:
+        nlat_in, nlon_in = lon_in.shape[0] - 1, lon_in.shape[1] - 1
+        nlon_out, nlat_out = lon_out.size - 1, lat_out.size - 1
+    mask_in = np.ones(nlon_in * nlat_in) if mask_in is None else f64(mask_in)
+    cap = int(capacity or get_maxxgrid())
+    ii, ji, io, jo = (np.empty(cap, np.int32) for _ in range(4))
+    xa = np.empty(cap); xc = np.empty(cap); yc = np.empty(cap)
+    ci = lambda v: C.byref(C.c_int(v))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    fn = getattr(L, f"create_xgrid_{kind}_order{order}")
+    args = [ci(nlon_in), ci(nlat_in), ci(nlon_out), ci(nlat_out), p(lon_in), p(lat_in), p(lon_out), p(lat_out), p(mask_in),
+            p(ii), p(ji), p(io), p(jo), p(xa)] + ([p(xc), p(yc)] if order == 2 else [])
+    n = fn(*args)
+    out = (n, ii[:n], ji[:n], io[:n], jo[:n], xa[:n])
+    return out + (xc[:n], yc[:n]) if order == 2 else out
+
+
+def create_xgrid_1dx2d_order1(lon_in, lat_in, lon_out, lat_out, mask_in=None):
+    """create_xgrid.c:208 — 1-D input cell bounds x 2-D output grid -> (nxgrid, i_in, j_in, i_out, j_out, xgrid_area)"""
+    return _create_xgrid_box("1dx2d", 1, lon_in, lat_in, lon_out, lat_out, mask_in)
+
+
+def create_xgrid_1dx2d_order2(lon_in, lat_in, lon_out, lat_out, mask_in=None):
+    """create_xgrid.c:312 — ... + (xgrid_clon, xgrid_clat)"""
+    return _create_xgrid_box("1dx2d", 2, lon_in, lat_in, lon_out, lat_out, mask_in)
+
+
+def create_xgrid_2dx1d_order1(lon_in, lat_in, lon_out, lat_out, mask_in=None):
+    """create_xgrid.c:413 — 2-D input grid x 1-D output cell bounds"""
+    return _create_xgrid_box("2dx1d", 1, lon_in, lat_in, lon_out, lat_out, mask_in)
+
+
+def create_xgrid_2dx1d_order2(lon_in, lat_in, lon_out, lat_out, mask_in=None):
+    """create_xgrid.c:514"""
+    return _create_xgrid_box("2dx1d", 2, lon_in, lat_in, lon_out, lat_out, mask_in)
 
 
 def create_xgrid_great_circle(lon_in, lat_in, lon_out, lat_out, mask_in=None):

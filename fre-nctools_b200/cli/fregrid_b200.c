@@ -391,8 +391,9 @@ static const char *usage =
   "             [--remap_file file] [--interp_method conserve_order1|conserve_order2|conserve_order2_monotonic]\n"
   "             [--lonBegin #] [--lonEnd #] [--latBegin #] [--latEnd #] [--KlevelBegin #] [--KlevelEnd #]\n"
   "             [--LstepBegin #] [--LstepEnd #] [--check_conserve] [--target_grid] [--weight_file f --weight_field w]\n"
-  "             [--standard_dimension] [--format classic|64bit_offset|cdf5] [--debug]\n"
-  "Conservative remapping of scalar fields between mosaics (the conservative path of FRE-NCtools fregrid) on one B200.\n";
+  "             [--standard_dimension] [--format classic|64bit_offset|cdf5] [--debug] [--gpus N | --gpu_list d0,d1,...]\n"
+  "Conservative remapping of scalar fields between mosaics (the conservative path of FRE-NCtools fregrid) on B200 GPUs.\n"
+  "--gpus N: exchange-grid generation sharded over N devices of this box (one process; replaces mpirun fregrid_parallel).\n";
 
 int main(int argc, char **argv)
 {
@@ -402,6 +403,7 @@ int main(int argc, char **argv)
   char scalar_name[MAXVAR][STRING];
   int nscalar = 0, nfiles = 0, nfiles_out = 0, nlon = 0, nlat = 0, check_conserve = 0, debug = 0, target_grid = 0;
   int kbegin = 0, kend = -1, lbegin = 0, lend = -1, standard_dimension = 0;
+  int ngpus = 1, gpu_list[64], have_gpu_list = 0;
   double lonbegin = 0, lonend = 360, latbegin = -90, latend = 90;
   unsigned opcode = 0;
   int c, idx = 0, errflg = argc == 1;
@@ -426,6 +428,7 @@ int main(int argc, char **argv)
     {"debug", no_argument, NULL, 'P'}, {"nthreads", required_argument, NULL, 'Q'},
     {"associated_file_dir", required_argument, NULL, 'R'}, {"deflation", required_argument, NULL, 'S'},
     {"shuffle", required_argument, NULL, 'T'}, {"format", required_argument, NULL, 'U'}, {"help", no_argument, NULL, 'h'},
+    {"gpus", required_argument, NULL, 'V'}, {"gpu_list", required_argument, NULL, 'W'},
     {0, 0, 0, 0}};
   char tok[MAXVAR][STRING];
   int ntok;
@@ -460,6 +463,12 @@ int main(int argc, char **argv)
       case 'P': debug = 1; break;
       case 'Q': case 'S': case 'T': case 'R': case 'N': break;  /* threads / deflation / shuffle do not apply here */
       case 'U': format = optarg; break;
+      case 'V': ngpus = atoi(optarg); if (ngpus < 1 || ngpus > 64) die("fregrid_b200: --gpus must be between 1 and 64"); break;
+      case 'W': tokenize_str(optarg, ",", tok, MAXVAR, &ntok);
+                if (ntok < 1 || ntok > 64) die("fregrid_b200: --gpu_list takes 1 to 64 device numbers");
+                ngpus = ntok; have_gpu_list = 1;
+                for (int q = 0; q < ntok; ++q) gpu_list[q] = atoi(tok[q]);
+                break;
       case 'u': case 'v': case 'm':
         die("fregrid: conservative interpolation of vector fields is not supported. \n"
             "Use bilinear interpolation or regrid the vector components independently as scalars.");
@@ -592,6 +601,13 @@ int main(int argc, char **argv)
   for (int m = 0; m < ntiles_out; ++m) any_read |= xg[m].file_exist;
   struct timespec t0, t1;
   clock_gettime(CLOCK_MONOTONIC, &t0);
+  /* order 2 onto several output tiles: sums per source cell across the tiles (one device); several devices: one output tile at a time */
+  const int o2_multi = (order == 2 && ntiles_out > 1 && !(opcode & XGB_GREAT_CIRCLE) && !any_read);
+  const int multi_gpu = ((ngpus > 1 || have_gpu_list) && !(opcode & XGB_GREAT_CIRCLE) && !o2_multi);
+  double *raw_clon[MAXTILE] = {0}, *raw_clat[MAXTILE] = {0};
+  if (o2_multi) XGB(xgb_plan_order2_begin(plan));
+  if ((ngpus > 1 || have_gpu_list) && !multi_gpu && !any_read)
+    printf("NOTE: --gpus applies to conserve_order1/2 weight generation onto one output tile at a time; this run uses one device.\n");
   for (int m = 0; m < ntiles_out; ++m) {
     if (any_read) {                                         /* conserve_interp.c:62-125: READ reads, and only reads */
       if (!xg[m].file_exist) continue;
@@ -601,13 +617,53 @@ int main(int argc, char **argv)
       XGB(xgb_remap_read(xg[m].remap_file, order, n, xg[m].t_in, xg[m].i_in, xg[m].j_in, xg[m].i_out, xg[m].j_out, xg[m].area, xg[m].di, xg[m].dj));
       continue;
     }
+    if (multi_gpu) {
+      /* one process, ngpus devices: source-cell windows dealt to the devices, pieces put back in the serial order on the host
+         (csrc/multi_gpu.cu) — the reference's mpirun -n N fregrid_parallel (fregrid_util.c:489-492, conserve_interp.c:404-437) */
+      xgb_dst_spec ds;
+      memset(&ds, 0, sizeof ds);
+      if (!mosaic_out) { ds.by_size = 1; ds.nlon = nlon; ds.nlat = nlat; ds.lonbegin = lonbegin; ds.lonend = lonend; ds.latbegin = latbegin; ds.latend = latend; }
+      else { ds.nx = gout[m].nx; ds.ny = gout[m].ny; ds.lon = gout[m].lonc; ds.lat = gout[m].latc; }
+      xgb_host_xgrid hx;
+      XGB(xgb_generate_multi_gpu(ngpus, have_gpu_list ? gpu_list : NULL, opcode & (XGB_CONSERVE_ORDER1 | XGB_CONSERVE_ORDER2), &ds, ntiles_in, nxs, nys,
+                                 lon_cat, lat_cat, NULL, 0, &hx));
+      const long long n = hx.nxgrid;
+      xgrid_alloc(&xg[m], n, order);
+      if (n > 0) {
+        memcpy(xg[m].t_in, hx.t_in, n * sizeof(int)); memcpy(xg[m].i_in, hx.i_in, n * sizeof(int)); memcpy(xg[m].j_in, hx.j_in, n * sizeof(int));
+        memcpy(xg[m].i_out, hx.i_out, n * sizeof(int)); memcpy(xg[m].j_out, hx.j_out, n * sizeof(int)); memcpy(xg[m].area, hx.area, n * sizeof(double));
+        if (order == 2) { memcpy(xg[m].di, hx.di, n * sizeof(double)); memcpy(xg[m].dj, hx.dj, n * sizeof(double)); }
+      }
+      xgb_host_xgrid_free(&hx);
+      if (do_write && n > 0)
+        XGB(xgb_remap_write(xg[m].remap_file, order, n, xg[m].t_in, xg[m].i_in, xg[m].j_in, xg[m].i_out, xg[m].j_out, 0, 0, xg[m].area, xg[m].di, xg[m].dj));
+      continue;
+    }
     XGB(set_dst_tile(plan, &gout[m], !mosaic_out, nlon, nlat, lonbegin, lonend, latbegin, latend));
     const long long n = xgb_plan_generate(plan, opcode & (XGB_CONSERVE_ORDER1 | XGB_CONSERVE_ORDER2 | XGB_GREAT_CIRCLE));
     if (n < 0) die("%s", xgb_last_error());
     xgrid_alloc(&xg[m], n, order);
-    if (n > 0) XGB(xgb_plan_result_host(plan, xg[m].t_in, xg[m].i_in, xg[m].j_in, xg[m].i_out, xg[m].j_out, xg[m].area, xg[m].di, xg[m].dj));
-    if (do_write && n > 0)
+    if (n > 0) XGB(xgb_plan_result_host(plan, xg[m].t_in, xg[m].i_in, xg[m].j_in, xg[m].i_out, xg[m].j_out, xg[m].area,
+                                        o2_multi ? NULL : xg[m].di, o2_multi ? NULL : xg[m].dj));
+    if (o2_multi && n > 0) {                                /* raw centroids; the distances follow after the last output tile */
+      raw_clon[m] = xmalloc(n * sizeof(double)); raw_clat[m] = xmalloc(n * sizeof(double));
+      XGB(xgb_plan_result_centroids_host(plan, raw_clon[m], raw_clat[m]));
+    }
+    if (do_write && n > 0 && !o2_multi)
       XGB(xgb_remap_write(xg[m].remap_file, order, n, xg[m].t_in, xg[m].i_in, xg[m].j_in, xg[m].i_out, xg[m].j_out, 0, 0, xg[m].area, xg[m].di, xg[m].dj));
+  }
+  if (o2_multi && !any_read) {
+    /* conserve_interp.c:204-221, :319-358: the per-source-cell sums run over ALL output tiles before the AREA_RATIO test */
+    XGB(xgb_plan_order2_end(plan));
+    for (int m = 0; m < ntiles_out; ++m) {
+      if (xg[m].n > 0) {
+        XGB(xgb_plan_order2_distance(plan, xg[m].n, xg[m].t_in, xg[m].i_in, xg[m].j_in, xg[m].area, raw_clon[m], raw_clat[m], xg[m].di, xg[m].dj));
+        if (do_write)
+          XGB(xgb_remap_write(xg[m].remap_file, order, xg[m].n, xg[m].t_in, xg[m].i_in, xg[m].j_in, xg[m].i_out, xg[m].j_out, 0, 0, xg[m].area, xg[m].di, xg[m].dj));
+      }
+      free(raw_clon[m]); free(raw_clat[m]);
+    }
+    xgb_plan_order2_reset(plan);
   }
   clock_gettime(CLOCK_MONOTONIC, &t1);
   if (any_read) printf("NOTE: Finish reading index and weight for conservative interpolation from file.\n");

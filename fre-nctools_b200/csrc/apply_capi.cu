@@ -485,15 +485,24 @@ extern "C" int xgb_plan_regrid(xgb_plan* p, unsigned int opcode, int nfields, co
   double* d_out = out;
   if (!on_device) { if (a->s_out.reserve(no * 8 + 16)) return 1; d_out = (double*)a->s_out.p; }
   if (order == 2 && !(opcode & XGB_MONOTONIC)) {
-    // packed path: one 32-byte record (value, grad_x, grad_y, grad_mask) per source cell and field-level
-    if (a->s_gx.reserve(ng * 32 + 32)) return 1;
-    launch_grad_c2l_packed((const GradTile*)a->gtiles_dev.p, (int)a->gtiles.size(), a->ncell, nfields, d_data, a->nhalo,
-                           (double*)a->s_gx.p, has_missing != 0, missing, p->st);
     if (check_variant_batch(a, nfields, has_missing != 0)) return 1;
     ApplyCsr csr;
     if (effective_csr(p, a, &csr)) return 1;
     const double miss = has_missing ? missing : -1.e20;
-    launch_apply_packed(has_missing != 0, csr, a->ndst, nfields, (const double*)a->s_gx.p, a->ncell, miss, d_out, p->st, a->cell_methods, a->nx2);
+    static const bool use_packed = getenv("XGB_APPLY_PACKED") && getenv("XGB_APPLY_PACKED")[0] == '1';
+    if (!use_packed) {
+      // field-transposed path: per source cell the values / gradients of all field-levels side by side; a warp covers 32
+      // field-levels of one destination cell (apply_kernels.cu: grad_c2l_rec_kernel, apply_rec_kernel)
+      if (a->s_gx.reserve(apply_rec_doubles(a->ncell, nfields, has_missing != 0) * 8 + 64)) return 1;
+      launch_regrid_rec((const GradTile*)a->gtiles_dev.p, (int)a->gtiles.size(), a->ncell, nfields, d_data, a->nhalo, (double*)a->s_gx.p,
+                        has_missing != 0, missing, csr, a->ndst, miss, a->cell_methods, d_out, p->st);
+    } else {
+      // packed path (round 1): one 32-byte record (value, grad_x, grad_y, grad_mask) per source cell and field-level
+      if (a->s_gx.reserve(ng * 32 + 32)) return 1;
+      launch_grad_c2l_packed((const GradTile*)a->gtiles_dev.p, (int)a->gtiles.size(), a->ncell, nfields, d_data, a->nhalo,
+                             (double*)a->s_gx.p, has_missing != 0, missing, p->st);
+      launch_apply_packed(has_missing != 0, csr, a->ndst, nfields, (const double*)a->s_gx.p, a->ncell, miss, d_out, p->st, a->cell_methods, a->nx2);
+    }
     finish_variants(p, a, 2, nfields, d_data, has_missing != 0, miss, d_out);
     if (a->opt_farea && has_missing && kernel_errors(p)) return 1;
   } else {

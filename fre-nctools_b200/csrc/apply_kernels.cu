@@ -476,6 +476,179 @@ void launch_grad_c2l_packed(const GradTile* tiles, int ntiles, long long ncell, 
 }
 
 // =============================================================================================
+// Field-transposed order-2 path (xgb_plan_regrid, round 2).  ncu on apply_packed_kernel: 17 % of HBM, LSU wavefronts 59 % —
+// with field-major arrays every (exchange cell, field-level) is its own 32-byte gather.  Here the gradient kernel leaves, per
+// SOURCE CELL, the values / grad_x / grad_y (/ grad_mask) of all field-levels next to each other: rec[(cell * NC + comp) * nfp + f].
+// The apply kernel puts the 32 lanes of a warp on 32 consecutive field-levels of ONE destination cell: an exchange-cell entry
+// is three 256-byte coalesced loads for the whole warp, its weights are warp-uniform, every lane adds its field's terms in list
+// order (the reference's order, conserve_interp.c:785-812), and a block's 32 x 32 (destination, field) results go through
+// shared memory so the field-major output rows are written 256 bytes at a time.
+// =============================================================================================
+constexpr int kRecFields = 8;      // field-levels a gradient block transposes at a time
+
+template <bool MISSING>
+__global__ void __launch_bounds__(128)
+grad_c2l_rec_kernel(const GradTile* __restrict__ tiles, int ntiles, long long ncell, int nf, int nfp,
+                    const double* __restrict__ data, long long data_stride, double* __restrict__ rec, double missing)
+{
+  constexpr int NC = MISSING ? 4 : 3;
+  __shared__ double tile[NC][128][kRecFields + 1];
+  const long long c0 = (long long)blockIdx.x * 128;
+  const long long c = c0 + threadIdx.x;
+  const bool live = c < ncell;
+  GradTile g = tiles[0];
+  int i = 0, j = 0, nx = 1, ny = 1, nxp = 2;
+  long long lc = 0;
+  double dx_s = 0, dx_n = 0, dy_w = 0, dy_e = 0, area = 1;
+  double en_s[3], en_nn[3], ee_w[3], ee_e[3], vlon[3], vlat[3];
+  if (live) {
+    int t = 0;
+    while (t + 1 < ntiles && c >= tiles[t + 1].cell_off) ++t;
+    g = tiles[t];
+    nx = g.nx; ny = g.ny; nxp = nx + 1;
+    lc = c - g.cell_off;
+    i = (int)(lc % nx); j = (int)(lc / nx);
+    // metrics of this cell (gradient_c2l.c:58-118), read once for all field-levels
+    dx_s = g.dx[(long long)j * nx + i]; dx_n = g.dx[(long long)(j + 1) * nx + i];
+    dy_w = g.dy[(long long)j * nxp + i]; dy_e = g.dy[(long long)j * nxp + i + 1];
+#pragma unroll
+    for (int n = 0; n < 3; ++n) {
+      en_s[n] = g.en_n[3 * ((long long)j * nx + i) + n];
+      en_nn[n] = g.en_n[3 * ((long long)(j + 1) * nx + i) + n];
+      ee_w[n] = g.en_e[3 * ((long long)j * nxp + i) + n];
+      ee_e[n] = g.en_e[3 * ((long long)j * nxp + i + 1) + n];
+      vlon[n] = g.vlon[3 * lc + n];
+      vlat[n] = g.vlat[3 * lc + n];
+    }
+    area = g.area[lc];
+  }
+  for (int f0 = 0; f0 < nf; f0 += kRecFields) {
+    const int nk = (nf - f0 < kRecFields) ? nf - f0 : kRecFields;
+    if (live) {
+#pragma unroll 1
+      for (int k = 0; k < nk; ++k) {
+        const double* q = data + (long long)(f0 + k) * data_stride + g.halo_off;
+        const double p00 = corner_value(q, nx, ny, i, j, g), p10 = corner_value(q, nx, ny, i + 1, j, g);
+        const double p01 = corner_value(q, nx, ny, i, j + 1, g), p11 = corner_value(q, nx, ny, i + 1, j + 1, g);
+        double g3[3];
+#pragma unroll
+        for (int n = 0; n < 3; ++n) {
+          const double pdx_s = 0.5 * (p00 + p10) * dx_s * en_s[n];                // :86-92
+          const double pdx_n = 0.5 * (p01 + p11) * dx_n * en_nn[n];
+          const double pdy_w = 0.5 * (p00 + p01) * dy_w * ee_w[n];                // :94-99
+          const double pdy_e = 0.5 * (p10 + p11) * dy_e * ee_e[n];
+          g3[n] = pdx_n - pdx_s - pdy_w + pdy_e;                                  // :102-107
+        }
+        double vx = (vlon[0] * g3[0] + vlon[1] * g3[1] + vlon[2] * g3[2]) / area; // :110-117
+        vx *= kRadius;
+        double vy = (vlat[0] * g3[0] + vlat[1] * g3[1] + vlat[2] * g3[2]) / area;
+        vy *= kRadius;
+        const int w = nx + 2, ii = i + 1, jj = j + 1;
+        tile[0][threadIdx.x][k] = q[(long long)jj * w + ii];
+        tile[1][threadIdx.x][k] = vx;
+        tile[2][threadIdx.x][k] = vy;
+        if (MISSING) {                                                            // fregrid_util.c:2203-2216
+          const int m = (q[(jj - 1) * w + ii - 1] == missing || q[(jj - 1) * w + ii] == missing || q[(jj - 1) * w + ii + 1] == missing ||
+                         q[jj * w + ii - 1] == missing || q[jj * w + ii + 1] == missing || q[(jj + 1) * w + ii - 1] == missing ||
+                         q[(jj + 1) * w + ii] == missing || q[(jj + 1) * w + ii + 1] == missing) ? 1 : 0;
+          tile[NC - 1][threadIdx.x][k] = (double)m;
+        }
+      }
+    }
+    __syncthreads();
+    // transposed write-out: kRecFields consecutive field-levels of a cell are 64 contiguous bytes
+    for (int idx = threadIdx.x; idx < 128 * kRecFields; idx += 128) {
+      const int cl = idx / kRecFields, k = idx % kRecFields;
+      if (c0 + cl < ncell && k < nk) {
+#pragma unroll
+        for (int comp = 0; comp < NC; ++comp)
+          rec[((c0 + cl) * NC + comp) * nfp + f0 + k] = tile[comp][cl][k];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <bool MISSING>
+__global__ void __launch_bounds__(256)
+apply_rec_kernel(ApplyCsr csr, long long ndst, int nf, int nfp, const double* __restrict__ rec, double missing, int sum_mode,
+                 double* __restrict__ out)
+{
+  constexpr int NC = MISSING ? 4 : 3;
+  __shared__ double res[32][33];                                  // [field][destination cell]
+  const int nft = (nf + 31) / 32;
+  const long long d0 = (long long)(blockIdx.x / nft) * 32;       // field tile fastest: a destination tile's records stay in L1 / L2
+  const int f0 = (int)(blockIdx.x % nft) * 32;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int f = f0 + lane;
+  const bool fl = f < nf;
+#pragma unroll 1
+  for (int r = 0; r < 4; ++r) {
+    const int dl = wid * 4 + r;
+    const long long d = d0 + dl;
+    double result = missing;
+    if (d < ndst) {
+      const uint32_t b = csr.off[d], e = csr.off[d + 1];
+      double acc = 0.0, asum = 0.0;
+      bool seen = false;
+      for (uint32_t q = b; q < e; ++q) {
+        const double area = csr.area[q], di = csr.di[q], dj = csr.dj[q];     // warp-uniform
+        const double* rc = rec + (long long)csr.cell[q] * NC * nfp + f;
+        if (fl) {
+          const double v = rc[0], gx = rc[nfp], gy = rc[2 * nfp];
+          if (MISSING) {
+            if (v == missing) continue;                                     // :766
+            if (rc[3 * nfp] != 0.0) acc += v * area;                        // :779
+            else acc += (v + gx * di + gy * dj) * area;                     // :782, :806
+            asum += area; seen = true;
+          } else {
+            acc += (v + gx * di + gy * dj) * area;
+            asum += area;
+          }
+        }
+      }
+      const bool any = MISSING ? seen : (e > b);
+      if (sum_mode) result = (asum == 0) ? (any ? 0.0 : missing) : acc;    // cell_methods "sum", :821-830
+      else if (asum > 0) result = acc / asum;                              // :833-834
+      else if (any) result = 0.0;                                          // :835-836
+      else result = missing;                                               // :837-838
+    }
+    res[lane][dl] = result;
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int r = 0; r < 4; ++r) {
+    const int fr = wid * 4 + r;
+    if (f0 + fr < nf && d0 + lane < ndst) out[(long long)(f0 + fr) * ndst + d0 + lane] = res[fr][lane];
+  }
+}
+
+size_t apply_rec_doubles(long long ncell, int nf, bool has_missing)
+{
+  const int nfp = (nf + 3) & ~3;
+  return (size_t)ncell * (has_missing ? 4 : 3) * nfp;
+}
+
+void launch_regrid_rec(const GradTile* tiles, int ntiles, long long ncell, int nf, const double* data, long long data_stride, double* rec,
+                       bool has_missing, double missing, const ApplyCsr& csr, long long ndst, double apply_missing, int sum_mode,
+                       double* out, cudaStream_t st)
+{
+  if (ncell <= 0 || nf <= 0 || ndst <= 0) return;
+  const int nfp = (nf + 3) & ~3;
+  const unsigned gblk = (unsigned)((ncell + 127) / 128);
+  const long long ablk = ((ndst + 31) / 32) * ((nf + 31) / 32);
+  if (ablk >= (1ll << 31)) return;
+  g_launches += 2;
+  if (has_missing) {
+    grad_c2l_rec_kernel<true><<<gblk, 128, 0, st>>>(tiles, ntiles, ncell, nf, nfp, data, data_stride, rec, missing);
+    apply_rec_kernel<true><<<(unsigned)ablk, 256, 0, st>>>(csr, ndst, nf, nfp, rec, apply_missing, sum_mode, out);
+  } else {
+    grad_c2l_rec_kernel<false><<<gblk, 128, 0, st>>>(tiles, ntiles, ncell, nf, nfp, data, data_stride, rec, missing);
+    apply_rec_kernel<false><<<(unsigned)ablk, 256, 0, st>>>(csr, ndst, nf, nfp, rec, apply_missing, sum_mode, out);
+  }
+}
+
+// =============================================================================================
 // monotone limiter (conserve_interp.c:617-742): one field-level per launch set
 // =============================================================================================
 // order-preserving map double <-> uint64 so atomicMax/atomicMin on integers implement max/min of doubles

@@ -93,7 +93,8 @@ extern "C" xgb_plan* xgb_plan_create(int device)
       cudaMalloc(&p->total_dev, 2 * sizeof(unsigned long long)) != cudaSuccess ||
       cudaMallocHost(&p->total_host, 4 * sizeof(unsigned long long)) != cudaSuccess ||
       cudaMallocHost(&p->err_host, sizeof(int)) != cudaSuccess ||
-      cudaMallocHost(&p->win_host, (kMaxWindows + 1) * sizeof(unsigned)) != cudaSuccess) {
+      cudaMallocHost(&p->win_host, (kMaxWindows + 1) * sizeof(unsigned)) != cudaSuccess ||
+      cudaMallocHost(&p->rect_host, sizeof(int)) != cudaSuccess) {
     xgb_set_error("plan resource allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
     delete p;
     return nullptr;
@@ -131,6 +132,7 @@ extern "C" void xgb_plan_destroy(xgb_plan* p)
   if (p->total_host) cudaFreeHost(p->total_host);
   if (p->err_host) cudaFreeHost(p->err_host);
   if (p->win_host) cudaFreeHost(p->win_host);
+  if (p->rect_host) cudaFreeHost(p->rect_host);
   if (p->fork_ev) cudaEventDestroy(p->fork_ev);
   if (p->join_ev) cudaEventDestroy(p->join_ev);
   if (p->aux_st) cudaStreamDestroy(p->aux_st);
@@ -203,7 +205,7 @@ static int report_kernel_error(xgb_plan* p, int e, bool fatal_like_reference)
   return 1;
 }
 
-static int finish_set_dst(xgb_plan* p, int nx, int ny);
+static int finish_set_dst(xgb_plan* p, int nx, int ny, bool defer_checks = false);
 
 extern "C" int xgb_plan_set_dst(xgb_plan* p, int nx, int ny, const double* lon, const double* lat, int on_device)
 {
@@ -226,10 +228,12 @@ extern "C" int xgb_plan_set_dst_latlon(xgb_plan* p, int nlon, int nlat, double l
   if ((long long)nlon * nlat >= (1ll << 31)) { xgb_set_error("destination tile too large for 32-bit cell indices"); return 1; }
   if (p->dst_lon.reserve(nv * sizeof(double)) || p->dst_lat.reserve(nv * sizeof(double))) return 1;
   launch_latlon_fill(nlon, nlat, lonbegin, lonend, latbegin, latend, (double*)p->dst_lon.p, (double*)p->dst_lat.p, p->st);
-  return finish_set_dst(p, nlon, nlat);
+  // no host synchronisation here: a regular lat-lon grid is separable by construction; the check kernel's verdict and any kernel
+  // error are collected at the next generate's synchronisation (which repeats the window with the pyramid walk if needed)
+  return finish_set_dst(p, nlon, nlat, true);
 }
 
-static int finish_set_dst(xgb_plan* p, int nx, int ny)
+static int finish_set_dst(xgb_plan* p, int nx, int ny, bool defer_checks)
 {
   const long long nc = (long long)nx * ny;
   if (carve_cellset(p->dst_store, nc, &p->dst)) return 1;
@@ -267,14 +271,19 @@ static int finish_set_dst(xgb_plan* p, int nx, int ny)
         p->rect_invalid.reserve(64))
       return 1;
     launch_rect_setup(p->dst, nx, ny, (double*)p->rect_store.p, (unsigned char*)p->rect_rows.p, (int*)p->rect_invalid.p, &p->rect, p->st);
-    int invalid = 1;
-    CU_OK(cudaMemcpyAsync(&invalid, p->rect_invalid.p, sizeof(int), cudaMemcpyDeviceToHost, p->st));
-    CU_OK(cudaStreamSynchronize(p->st));
-    if (invalid) p->rect.valid = 0;
+    if (defer_checks) {
+      p->rect_pending = true;                  // p->rect.valid stays 1 (launch_rect_setup) until the verdict is read
+    } else {
+      int invalid = 1;
+      CU_OK(cudaMemcpyAsync(&invalid, p->rect_invalid.p, sizeof(int), cudaMemcpyDeviceToHost, p->st));
+      CU_OK(cudaStreamSynchronize(p->st));
+      if (invalid) p->rect.valid = 0;
+      p->rect_pending = false;
+    }
   }
   p->have_dst = true;
   p->gc_dst_ready = false;
-  return xgb_check_kernel_errors(p, false);
+  return defer_checks ? 0 : xgb_check_kernel_errors(p, false);
 }
 
 extern "C" int xgb_plan_set_src(xgb_plan* p, int ntiles, const int* nx, const int* ny,
@@ -306,6 +315,69 @@ extern "C" int xgb_plan_set_src(xgb_plan* p, int ntiles, const int* nx, const in
   p->o2_state = 0;
   // the tile table was copied from pageable host memory: make sure it has landed before `tiles` can change
   return xgb_check_kernel_errors(p, false);
+}
+
+// The source mosaic for a rank that only ever generates the given windows: the plan keeps the mosaic's full cell index space
+// (window bounds, t_in/i_in/j_in and emission order are those of the whole mosaic), but only the vertex rows the windows touch
+// are uploaded and only their cells are precomputed — host-to-device traffic and setup time scale with the rank's share.  No
+// host synchronisation: kernel errors surface at the next generate.  The windows become the active windows.
+extern "C" int xgb_plan_set_src_sharded(xgb_plan* p, int ntiles, const int* nx, const int* ny, const double* lon, const double* lat,
+                                        const double* mask, int nwin, const long long* begin, const long long* end)
+{
+  if (!p || ntiles <= 0 || !nx || !ny || !lon || !lat || nwin <= 0 || nwin > kMaxWindows || !begin || !end) {
+    xgb_set_error("xgb_plan_set_src_sharded: bad arguments");
+    return 1;
+  }
+  CU_OK(cudaSetDevice(p->device));
+  bool same = (int)p->tiles.size() == ntiles;
+  for (int n = 0; same && n < ntiles; ++n) same = p->tiles[n].nx == nx[n] && p->tiles[n].ny == ny[n];
+  long long coff = 0, voff = 0;
+  if (!same) {
+    p->tiles.clear();
+    for (int n = 0; n < ntiles; ++n) {
+      if (nx[n] <= 0 || ny[n] <= 0) { xgb_set_error("xgb_plan_set_src_sharded: empty tile %d", n); return 1; }
+      p->tiles.push_back(TileDesc{nx[n], ny[n], coff, voff});
+      coff += (long long)nx[n] * ny[n];
+      voff += (long long)(nx[n] + 1) * (ny[n] + 1);
+    }
+    if (coff >= (1ll << 31)) { xgb_set_error("source mosaic too large for 32-bit cell indices"); return 1; }
+    if (p->tiles_dev.reserve(sizeof(TileDesc) * ntiles)) return 1;
+    CU_OK(cudaMemcpyAsync(p->tiles_dev.p, p->tiles.data(), sizeof(TileDesc) * ntiles, cudaMemcpyHostToDevice, p->st));
+  } else {
+    coff = p->tiles.back().cell_off + (long long)p->tiles.back().nx * p->tiles.back().ny;
+    voff = p->tiles.back().vert_off + (long long)(p->tiles.back().nx + 1) * (p->tiles.back().ny + 1);
+  }
+  if (p->src_lon.reserve((size_t)voff * sizeof(double)) || p->src_lat.reserve((size_t)voff * sizeof(double))) return 1;
+  p->has_mask = (mask != nullptr);
+  if (mask && p->mask.reserve((size_t)coff * sizeof(double))) return 1;
+  if (carve_cellset(p->src_store, coff, &p->src)) return 1;
+  SrcMap m{};
+  m.nwin = nwin; m.cum[0] = 0;
+  for (int w = 0; w < nwin; ++w) {
+    if (begin[w] < 0 || end[w] < begin[w] || end[w] > coff) { xgb_set_error("xgb_plan_set_src_sharded: bad window %d", w); return 1; }
+    m.begin[w] = begin[w];
+    m.cum[w + 1] = m.cum[w] + (end[w] - begin[w]);
+    // the window's cells tile by tile: vertex rows j0 .. j1 + 1 of the tile, then the cells themselves
+    for (int t = 0; t < ntiles; ++t) {
+      const TileDesc& td = p->tiles[t];
+      const long long tb = td.cell_off, te = td.cell_off + (long long)td.nx * td.ny;
+      const long long lo = begin[w] > tb ? begin[w] : tb, hi = end[w] < te ? end[w] : te;
+      if (hi <= lo) continue;
+      const long long c0 = lo - tb, c1 = hi - tb;
+      const long long j0 = c0 / td.nx, j1 = (c1 - 1) / td.nx;
+      const size_t v0 = (size_t)td.vert_off + (size_t)j0 * (td.nx + 1), nv = (size_t)(j1 - j0 + 2) * (td.nx + 1);
+      CU_OK(cudaMemcpyAsync((double*)p->src_lon.p + v0, lon + v0, nv * sizeof(double), cudaMemcpyHostToDevice, p->st));
+      CU_OK(cudaMemcpyAsync((double*)p->src_lat.p + v0, lat + v0, nv * sizeof(double), cudaMemcpyHostToDevice, p->st));
+      if (mask) CU_OK(cudaMemcpyAsync((double*)p->mask.p + lo, mask + lo, (size_t)(hi - lo) * sizeof(double), cudaMemcpyHostToDevice, p->st));
+      launch_cell_precompute(td, (const double*)p->src_lon.p, (const double*)p->src_lat.p, p->src, p->err_dev, p->st, c0, c1);
+    }
+  }
+  p->map = m;
+  p->s0 = begin[0]; p->ns = m.total();
+  p->have_src = true;
+  p->gc_src_ready = false;
+  p->o2_state = 0;
+  return 0;
 }
 
 static SrcMap single_window(long long begin, long long end)
@@ -494,6 +566,7 @@ static int resident_enqueue(xgb_plan* p, int order, const SrcMap& sm, size_t cap
   launch_publish(p->total_host, &hw.ctl->total, 4, p->st);          // pair total (2 words), nheavy, pairs of the pyramid heavy path
   launch_publish(p->total_host + 2, p->total_dev + 1, 2, p->st);    // exchange cells
   launch_publish(p->err_host, p->err_dev, 1, p->st);
+  if (p->rect_pending) launch_publish(p->rect_host, p->rect_invalid.p, 1, p->st);
   return 0;
 }
 
@@ -503,6 +576,10 @@ static int resident_evaluate(xgb_plan* p, const SrcMap& sm, size_t& cap, const H
 {
   const int e = *p->err_host;
   if (e) cudaMemsetAsync(p->err_dev, 0, sizeof(int), p->st);
+  if (p->rect_pending) {                       // verdict of the separability check of xgb_plan_set_dst_latlon
+    p->rect_pending = false;
+    if (*p->rect_host) { p->rect.valid = 0; return 1; }          // not separable after all: repeat with the pyramid walk
+  }
   if (e == kErrHeavyOverflow && attempt < 8) {
     // the level-synchronous work lists were too small (coarse source on a fine curvilinear destination): grow and repeat
     const unsigned heavy_pairs = ((const unsigned*)p->total_host)[3];
@@ -581,9 +658,14 @@ static long long generate_window(xgb_plan* p, int order, const SrcMap& sm, size_
                              (int2*)p->pairs.p, cap, (uint32_t*)p->cnt.p, hw, p->err_dev, p->st);
     launch_publish(p->total_host, &hw.ctl->total, 4, p->st);          // total (2 words), nheavy, npairs of the heavy path
     launch_publish(p->err_host, p->err_dev, 1, p->st);
+    if (p->rect_pending) launch_publish(p->rect_host, p->rect_invalid.p, 1, p->st);
     if (cudaStreamSynchronize(p->st) != cudaSuccess) {
       xgb_set_error("candidate search failed: %s", cudaGetErrorString(cudaGetLastError()));
       return -1;
+    }
+    if (p->rect_pending) {
+      p->rect_pending = false;
+      if (*p->rect_host) { p->rect.valid = 0; continue; }             // not separable after all: repeat with the pyramid walk
     }
     if (*p->err_host == kErrHeavyOverflow && attempt < 8) {
       // the level-synchronous work lists were too small (coarse source on a fine destination): grow and repeat

@@ -37,9 +37,11 @@ __device__ __forceinline__ int vtx_insert(double* x, double* y, int n, int at, d
   return n + 1;
 }
 
-__device__ inline int fix_lon(double* x, double* y, int n, double tlon) {
+// everything of fix_lon that does not depend on tlon: pole vertices, twin poles, unwrap (mosaic_util.c:672-725); *sum_out = x_sum
+__device__ inline int fix_lon_unshifted(double* x, double* y, int n, double* sum_out) {
   const double near_pole = kHalfPi - kPoleTol;
   int nn = n;
+  *sum_out = 0.0;
   bool any_pole = false;
   for (int i = 0; i < nn; ++i) any_pole |= (fabs(y[i]) >= near_pole);
   if (any_pole) {
@@ -86,6 +88,14 @@ __device__ inline int fix_lon(double* x, double* y, int n, double tlon) {
     x[i] = x[i - 1] + d;
     sum += x[i];
   }
+  *sum_out = sum;
+  return nn;
+}
+
+__device__ inline int fix_lon(double* x, double* y, int n, double tlon) {
+  double sum;
+  const int nn = fix_lon_unshifted(x, y, n, &sum);
+  if (nn <= 0) return nn;
   // mean within pi of tlon (:727-729)
   double shift = (sum / nn) - tlon;
   if (shift < -kPi)      { for (int i = 0; i < nn; ++i) x[i] += kTwoPi; }

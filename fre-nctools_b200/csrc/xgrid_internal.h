@@ -91,8 +91,9 @@ struct HeavyWork {
 };
 
 // ---- launchers (xgrid_kernels.cu) ----------------------------------------------------------
+// cells [c0, c1) of the tile (default: all of it)
 void launch_cell_precompute(const TileDesc& tile, const double* lon, const double* lat,
-                            CellSet cells, int* err, cudaStream_t st);
+                            CellSet cells, int* err, cudaStream_t st, long long c0 = 0, long long c1 = -1);
 void launch_pyramid_level(const PyrLevel& child, Box* out, int nx, int ny, cudaStream_t st);
 void launch_candidates_count(const CellSet& src, const SrcMap& sm, const double* mask,
                              const Pyramid& pyr, const CellSet& dst, uint32_t* cnt, const HeavyWork& hw, int* err, cudaStream_t st);

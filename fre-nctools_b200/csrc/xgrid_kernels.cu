@@ -24,11 +24,10 @@ long long g_launches = 0;
 // =============================================================================================
 __global__ void __launch_bounds__(128)
 cell_precompute_kernel(TileDesc tile, const double* __restrict__ lon, const double* __restrict__ lat,
-                       CellSet cells, int* err)
+                       CellSet cells, int* err, long long c0, long long c1)
 {
-  const long long ncell_tile = (long long)tile.nx * tile.ny;
-  const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (c >= ncell_tile) return;
+  const long long c = c0 + blockIdx.x * (long long)blockDim.x + threadIdx.x;     // cells [c0, c1) of the tile
+  if (c >= c1) return;
   const int i = (int)(c % tile.nx), j = (int)(c / tile.nx);
   const int nxp = tile.nx + 1;
   const double* lo = lon + tile.vert_off;
@@ -65,14 +64,17 @@ cell_precompute_kernel(TileDesc tile, const double* __restrict__ lon, const doub
 }
 
 void launch_cell_precompute(const TileDesc& tile, const double* lon, const double* lat,
-                            CellSet cells, int* err, cudaStream_t st)
+                            CellSet cells, int* err, cudaStream_t st, long long c0, long long c1)
 {
-  const long long n = (long long)tile.nx * tile.ny;
+  const long long ncell_tile = (long long)tile.nx * tile.ny;
+  if (c1 < 0 || c1 > ncell_tile) c1 = ncell_tile;
+  if (c0 < 0) c0 = 0;
+  const long long n = c1 - c0;
   if (n <= 0) return;
   const int threads = 128;
   const unsigned blocks = (unsigned)((n + threads - 1) / threads);
   ++g_launches;
-  cell_precompute_kernel<<<blocks, threads, 0, st>>>(tile, lon, lat, cells, err);
+  cell_precompute_kernel<<<blocks, threads, 0, st>>>(tile, lon, lat, cells, err, c0, c1);
 }
 
 // =============================================================================================
@@ -1651,7 +1653,10 @@ clip2_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const in
 #ifndef XGB_SPLIT_BLOCKS2
 #define XGB_SPLIT_BLOCKS2 7
 #endif
-constexpr int kWarpCap = 192;             // vertices per warp region (6 per pair; the mean is 3.6)
+#ifndef XGB_WARP_CAP
+#define XGB_WARP_CAP 192
+#endif
+constexpr int kWarpCap = XGB_WARP_CAP;    // vertices per warp region (6 per pair; the mean is 3.6)
 constexpr int kSplitCap = 4 * kWarpCap;   // per block of 4 warps
 
 // the tail every pair goes through once its polygon's sums are known (create_xgrid.c:805-820, :1091-1097)
@@ -1799,10 +1804,30 @@ clip_mom_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const
   __shared__ unsigned short s_own_all[4 * kWarpCap];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const unsigned long long p = blockIdx.x * (unsigned long long)kClipThreads + tid;
+  // Everything this warp will need from global memory is requested in its first instructions, none of it behind another load:
+  // the (offset, count) words, the pairs, and the first 128 vertices of the region whether or not they are all used (the mean is
+  // 115; the region is allocated in full).  ncu on the previous version: 18 % of the warp samples sat in a load-store loop over
+  // the region, one DRAM round trip per trip.
+  const size_t region = ((size_t)blockIdx.x * 4 + wid) * kWarpCap;
+  double ax[kWarpCap / 32], ay[kWarpCap / 32];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { ax[c] = gvx[region + c * 32 + lane]; ay[c] = gvy[region + c * 32 + lane]; }
   const unsigned meta = (p < npairs) ? gmeta[p] : 0u;
+  int2 pr = (p < npairs) ? pairs[p] : make_int2(-1, -1);
   const int nfl = meta >> 8, off = meta & 255;
   const int nvtx = __reduce_max_sync(0xffffffffu, off + nfl);
   if (nvtx == 0) return;                                          // warp-uniform: nothing survived the clip here
+#pragma unroll
+  for (int c = 4; c < kWarpCap / 32; ++c) {
+    const bool in = c * 32 + lane < nvtx;
+    ax[c] = in ? gvx[region + c * 32 + lane] : 0.0; ay[c] = in ? gvy[region + c * 32 + lane] : 0.0;
+  }
+  if (pr.x < 0) pr = make_int2(0, 0);
+  const long long s = smap.cell(pr.x);
+  // the finishing values (used after the sums): into L1 now
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(src.area + s));
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(dst.area + pr.y));
+  if (mask) asm volatile("prefetch.global.L1 [%0];" ::"l"(mask + s));
   double* sm = sm_all + wid * kWarpDoubles;
   unsigned short* s_own = s_own_all + wid * kWarpCap;
   double* FX = sm;
@@ -1811,21 +1836,15 @@ clip_mom_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const
   double* FC = sm + ((ORDER == 2) ? 3 : 0) * kWarpCap;
   double* P0 = sm + kArrays * kWarpCap;                           // [x y sin cos][lane]: vertex 0 of the lane's polygon
   double* s_clon = P0 + kArrays * 32;
-  const size_t region = ((size_t)blockIdx.x * 4 + wid) * kWarpCap;
-  for (int e = lane; e < nvtx; e += 32) { FX[e] = gvx[region + e]; FY[e] = gvy[region + e]; }
-  int2 pr = make_int2(0, 0);
-  long long s = 0;
-  double f_mask = 1.0, f_a1 = 1.0, f_a2 = 1.0;                    // the finishing loads, requested now, used at the very end
   if (nfl > 0) {
-    pr = pairs[p];
-    s = smap.cell(pr.x);
     if (ORDER == 2) s_clon[lane] = src.xavg[s];
-    f_mask = mask ? mask[s] : 1.0;
-    f_a1 = src.area[s]; f_a2 = dst.area[pr.y];
 #pragma unroll
     for (int k = 0; k < kFastCap; ++k)
       if (k < nfl) s_own[off + k] = (unsigned short)(lane | (k << 5) | (nfl << 8));
   }
+#pragma unroll
+  for (int c = 0; c < kWarpCap / 32; ++c)
+    if (c * 32 + lane < nvtx) { FX[c * 32 + lane] = ax[c]; FY[c * 32 + lane] = ay[c]; }
   __syncwarp();
   if (nfl > 0) { P0[lane] = FX[off]; P0[32 + lane] = FY[off]; }
   if (ORDER == 2) {
@@ -1874,7 +1893,8 @@ clip_mom_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const
       if (ORDER == 2) { lonacc -= FY[off + k]; latacc -= FS[off + k]; }
     }
     double xarea = (aacc < 0) ? -aacc * kRadius * kRadius : aacc * kRadius * kRadius;
-    xarea = xarea * f_mask;
+    xarea = xarea * (mask ? mask[s] : 1.0);
+    const double f_a1 = src.area[s], f_a2 = dst.area[pr.y];
     const double min_area = (f_a1 < f_a2) ? f_a1 : f_a2;          // :806
     const bool keep = (xarea / min_area > kAreaRatioThresh);      // :807
     parea[p] = keep ? xarea : 0.0;

@@ -32,6 +32,8 @@ struct xgb_plan {
   xgb::Pyramid pyr{};
   DevBuf rect_store, rect_rows, rect_invalid;  // separable destination tile: 1-D row / column boxes (xgrid_internal.h RectDst)
   xgb::RectDst rect{};
+  bool rect_pending = false;                   // set_dst_latlon: the separability check's verdict is read at the next generate's sync
+  int* rect_host = nullptr;                    // pinned
 
   // source mosaic
   bool have_src = false, has_mask = false;

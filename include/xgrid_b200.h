@@ -64,6 +64,33 @@ int create_xgrid_2dx2d_order2_(const int *nlon_in, const int *nlat_in, const int
                                const double *mask_in, int *i_in, int *j_in, int *i_out, int *j_out,
                                double *xgrid_area, double *xgrid_clon, double *xgrid_clat);
 
+/* create_xgrid.h:47-64 — exchange grids between a regular grid given by its 1-D cell bounds and a 2-D grid (runoff_regrid.c:472,
+ * interp.c:277,329): lon_in/lat_in (1dx2d) resp. lon_out/lat_out (2dx1d) are nlon+1 / nlat+1 bounds, the other grid is 2-D vertex
+ * arrays; mask_in lives on the input grid.  Emission order of the reference (1-D cells row-major, then 2-D cells row-major). */
+int create_xgrid_1dx2d_order1(const int *nlon_in, const int *nlat_in, const int *nlon_out, const int *nlat_out,
+                              const double *lon_in, const double *lat_in, const double *lon_out, const double *lat_out,
+                              const double *mask_in, int *i_in, int *j_in, int *i_out, int *j_out, double *xgrid_area);
+int create_xgrid_1dx2d_order2(const int *nlon_in, const int *nlat_in, const int *nlon_out, const int *nlat_out,
+                              const double *lon_in, const double *lat_in, const double *lon_out, const double *lat_out,
+                              const double *mask_in, int *i_in, int *j_in, int *i_out, int *j_out,
+                              double *xgrid_area, double *xgrid_clon, double *xgrid_clat);
+int create_xgrid_2dx1d_order1(const int *nlon_in, const int *nlat_in, const int *nlon_out, const int *nlat_out,
+                              const double *lon_in, const double *lat_in, const double *lon_out, const double *lat_out,
+                              const double *mask_in, int *i_in, int *j_in, int *i_out, int *j_out, double *xgrid_area);
+int create_xgrid_2dx1d_order2(const int *nlon_in, const int *nlat_in, const int *nlon_out, const int *nlat_out,
+                              const double *lon_in, const double *lat_in, const double *lon_out, const double *lat_out,
+                              const double *mask_in, int *i_in, int *j_in, int *i_out, int *j_out,
+                              double *xgrid_area, double *xgrid_clon, double *xgrid_clat);
+/* Fortran twins (create_xgrid.c:196, :296, :404, :504) */
+int create_xgrid_1dx2d_order1_(const int *, const int *, const int *, const int *, const double *, const double *, const double *,
+                               const double *, const double *, int *, int *, int *, int *, double *);
+int create_xgrid_1dx2d_order2_(const int *, const int *, const int *, const int *, const double *, const double *, const double *,
+                               const double *, const double *, int *, int *, int *, int *, double *, double *, double *);
+int create_xgrid_2dx1d_order1_(const int *, const int *, const int *, const int *, const double *, const double *, const double *,
+                               const double *, const double *, int *, int *, int *, int *, double *);
+int create_xgrid_2dx1d_order2_(const int *, const int *, const int *, const int *, const double *, const double *, const double *,
+                               const double *, const double *, int *, int *, int *, int *, double *, double *, double *);
+
 /* conserve_interp.h:25-32 — fregrid's own L3 entry points over its Grid_config / Interp_config / Field_config structs
  * (globals.h:66-222; declared here with opaque struct tags: callers include the reference's headers, the library mirrors
  * their layout in csrc/fregrid_abi.h and a test pins sizeof/offsetof against the compiled reference).
@@ -128,6 +155,13 @@ int xgb_plan_set_src(xgb_plan *p, int ntiles, const int *nx, const int *ny,
 /* Restrict generation to source cells [begin, end) of the concatenated (tile-major, row-major)
  * cell index space — the unit of multi-GPU sharding.  Default: all cells. */
 int xgb_plan_set_src_window(xgb_plan *p, long long begin, long long end);
+
+/* The source mosaic for a process that only ever generates the given windows (one GPU of a multi-GPU run): same cell index
+ * space, window bounds and emission order as xgb_plan_set_src + xgb_plan_set_src_windows, but only the vertex rows the windows
+ * touch are copied to the device and only their cells are precomputed (host pointers; pinned memory gives asynchronous
+ * copies).  No host synchronisation; kernel-detected errors are reported by the next generate. */
+int xgb_plan_set_src_sharded(xgb_plan *p, int ntiles, const int *nx, const int *ny, const double *lon, const double *lat,
+                             const double *mask, int nwin, const long long *begin, const long long *end);
 
 /* Several windows at once (at most 64), visited in the order given: one GPU's interleaved share of the mosaic.  The
  * result lists the windows' exchange cells one window after the other; xgb_plan_window_counts returns how many each
@@ -213,6 +247,31 @@ int xgb_plan_great_circle_area_host(xgb_plan *p, int which, double *area);
 /* Cell areas computed on the device (get_grid_area): source cells concatenated / destination cells. */
 int xgb_plan_src_area_host(xgb_plan *p, double *area);
 int xgb_plan_dst_area_host(xgb_plan *p, double *area);
+
+/* ------------------------------------------------------------------------------------------
+ * Part 2a — one process, several GPUs (csrc/multi_gpu.cu).  Replaces the reference's MPI decomposition of
+ * setup_conserve_interp: destination row bands per rank (fregrid_util.c:489-492), the order-2 gather of every rank's list
+ * to every rank (conserve_interp.c:202-227) and the gather to the root for writing (:404-437).  The source cells are cut
+ * into ngpus * windows_per_gpu windows of equal candidate-pair count, dealt round-robin; the windows' results in window order
+ * are the serial list (same cells, same order, same bits as one GPU), written to pinned host arrays allocated here.
+ * devices: NULL = 0 .. ngpus-1 (a device may be named twice).  Great circle runs on one device (refused here).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int by_size;                       /* 1: regular lat-lon grid built on the device (fregrid --nlon/--nlat, degrees) */
+  int nlon, nlat;
+  double lonbegin, lonend, latbegin, latend;
+  int nx, ny;                        /* 0: vertex arrays [(ny+1)*(nx+1)], radians */
+  const double *lon, *lat;
+} xgb_dst_spec;
+typedef struct {
+  long long nxgrid;
+  int *t_in, *i_in, *j_in, *i_out, *j_out;
+  double *area, *di, *dj, *xgrid_clon, *xgrid_clat;     /* order 1: di .. xgrid_clat are NULL */
+} xgb_host_xgrid;
+int xgb_generate_multi_gpu(int ngpus, const int *devices, unsigned int opcode, const xgb_dst_spec *dst, int ntiles,
+                           const int *nx, const int *ny, const double *lon, const double *lat, const double *mask,
+                           int windows_per_gpu, xgb_host_xgrid *out);
+void xgb_host_xgrid_free(xgb_host_xgrid *x);
 
 /* ------------------------------------------------------------------------------------------
  * Part 2b — conservative apply (do_scalar_conserve_interp, conserve_interp.c:507-910) and the order-2

@@ -325,3 +325,49 @@ def test_great_circle_grid_file_selects_the_great_circle_generator(pkg, reflib, 
     r = _run(pkg, ds, "--input_mosaic", "ocean_mosaic.nc", "--nlon", "36", "--nlat", "18", "--remap_file", "gc2", "--interp_method",
              "conserve_order2", ok=False)
     assert "can not be conserve_order2" in r.stderr
+
+
+def test_gpus_option_writes_the_same_remap_file(pkg, dataset):
+    """fregrid_b200 --gpus / --gpu_list (one process, several devices, csrc/multi_gpu.cu; replaces mpirun fregrid_parallel):
+    the remap file is byte-identical to the one-device file, order 1 and order 2, lat-lon and mosaic destinations.  On a
+    one-GPU box the same device is named twice — two plans, two host threads, the whole window / offset / gather logic."""
+    import torch
+    ds = dataset
+    ndev = torch.cuda.device_count()
+    lists = ["0,0", "0,0,0"] + (["0,1"] if ndev > 1 else [])
+    for method, tag in (("conserve_order1", "o1"), ("conserve_order2", "o2")):
+        base = ["--input_mosaic", f"C{ds['n']}_mosaic.nc", "--nlon", "72", "--nlat", "36", "--interp_method", method]
+        _run(pkg, ds, *base, "--remap_file", f"one_{tag}")
+        want = open(os.path.join(ds["dir"], f"one_{tag}.nc"), "rb").read()
+        for k, gl in enumerate(lists):
+            _run(pkg, ds, *base, "--remap_file", f"multi_{tag}_{k}", "--gpu_list", gl)
+            assert open(os.path.join(ds["dir"], f"multi_{tag}_{k}.nc"), "rb").read() == want, (tag, gl)
+        if ndev > 1:
+            _run(pkg, ds, *base, "--remap_file", f"multi_{tag}_n", "--gpus", str(min(ndev, 8)))
+            assert open(os.path.join(ds["dir"], f"multi_{tag}_n.nc"), "rb").read() == want, tag
+    # a curvilinear destination tile by tile
+    m = 10
+    _write_mosaic(pkg, ds["dir"], m)
+    base = ["--input_mosaic", f"C{ds['n']}_mosaic.nc", "--output_mosaic", f"C{m}_mosaic.nc"]
+    _run(pkg, ds, *base, "--remap_file", "cs_one")
+    _run(pkg, ds, *base, "--remap_file", "cs_two", "--gpu_list", "0,0")
+    for t in range(6):
+        a = open(os.path.join(ds["dir"], f"cs_one.tile{t + 1}.nc"), "rb").read()
+        assert a == open(os.path.join(ds["dir"], f"cs_two.tile{t + 1}.nc"), "rb").read(), t
+
+
+def test_order2_onto_several_output_tiles_equals_the_reference(pkg, dataset):
+    """conserve_order2 with --output_mosaic: tile1_distance of every output tile's remap file equals the reference's
+    setup_conserve_interp over all six output tiles at once (per-source-cell sums across the tiles, conserve_interp.c:204-221)"""
+    if xgtest.ref_lib() is None:
+        pytest.skip("oracle/_ref not built")
+    ds = dataset
+    m = 10
+    out = _write_mosaic(pkg, ds["dir"], m)
+    _run(pkg, ds, "--input_mosaic", f"C{ds['n']}_mosaic.nc", "--output_mosaic", f"C{m}_mosaic.nc", "--remap_file", "cs2", "--interp_method", "conserve_order2")
+    h, ref = xgtest.ref_multi_setup(ds["lonc"], ds["latc"], out["lonc"], out["latc"], 2)
+    for t in range(6):
+        got = _remap_lists(pkg, os.path.join(ds["dir"], f"cs2.tile{t + 1}.nc"), 2)
+        for k in ("t_in", "i_in", "j_in", "i_out", "j_out", "di", "dj"):
+            assert np.array_equal(got[k], ref[t][k]), (t, k)
+        assert np.allclose(got["area"], ref[t]["area"], rtol=4e-16, atol=0), t     # the reader rescales: (a / 4 pi R^2) * 4 pi R^2

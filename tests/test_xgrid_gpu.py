@@ -605,3 +605,60 @@ def test_reference_embedded_polygon_cases_through_the_c_abi(pkg):
             assert np.array_equal(np.stack(r[1:5]), g[k + "gcx_idx"]), n
             assert np.max(np.abs(r[5] - g[k + "gcx_area"]), initial=0.0) / xgtest.RADIUS ** 2 <= 8e-15, n
     assert seen >= 14
+
+
+def test_1dx2d_and_2dx1d_generators_match_the_reference_golden(pkg):
+    """create_xgrid_1dx2d_order1/2 and create_xgrid_2dx1d_order1/2 (create_xgrid.c:208-598: runoff_regrid / interp.c's
+    generators between a regular grid given by 1-D bounds and a 2-D grid) through the reference-signature C ABI against
+    vectors recorded from the unmodified reference (tests/golden/make_box_golden.py): a pole inside a cube face, the date
+    line, a regional pair with masks, a one-column grid (get_grid_area_no_adjust branch) and a tripolar cap.  Lists in the
+    reference's emission order, areas and centroid integrals bit-identical."""
+    g = np.load(os.path.join(xgtest.GOLDEN_DIR, "xgrid_box.npz"))
+    exact = xgtest.libm_matches_ref_trig()
+    for key in g["names"]:
+        bname, gname = str(key).split("__")
+        lb, ab = g[f"box_{bname}_lon"], g[f"box_{bname}_lat"]
+        lg, ag = g[f"grid_{gname}_lon"], g[f"grid_{gname}_lat"]
+        for order in (1, 2):
+            for kind in ("1dx2d", "2dx1d"):
+                fn = getattr(pkg, f"create_xgrid_{kind}_order{order}")
+                if kind == "1dx2d":
+                    r = fn(lb, ab, lg, ag, g[f"{key}_mask_box"])
+                else:
+                    r = fn(lg, ag, lb, ab, g[f"{key}_mask_cell"])
+                pre = f"{key}_{kind}_o{order}_"
+                assert r[0] == int(g[pre + "n"]), (key, kind, order, r[0], int(g[pre + "n"]))
+                assert np.array_equal(np.stack(r[1:5]), g[pre + "idx"]), (key, kind, order)
+                fields = [("area", r[5])] + ([("clon", r[6]), ("clat", r[7])] if order == 2 else [])
+                for name, got in fields:
+                    want = g[pre + name]
+                    if exact:
+                        assert np.array_equal(got, want), (key, kind, order, name)
+                    else:
+                        assert np.allclose(got, want, rtol=1e-9, atol=1e-3), (key, kind, order, name)
+
+
+def test_sharded_source_upload_equals_the_whole_mosaic(pkg):
+    """xgb_plan_set_dst_latlon + xgb_plan_set_src_sharded (only the windows' vertex rows uploaded, only their cells precomputed,
+    no host synchronisation) generate exactly what xgb_plan_set_src + xgb_plan_set_src_windows generate"""
+    ni, nlon, nlat = 48, 360, 180
+    lonc, latc = pkg.cubed_sphere_grid(ni)
+    lon2, lat2 = pkg.latlon_grid(nlon, nlat)
+    full = pkg.XgridPlan(0)
+    full.set_dst(lon2, lat2); full.set_src(lonc, latc)
+    b = full.partition(6)
+    wins = [(b[1], b[2]), (b[4], b[5])]
+    full.set_src_windows(wins)
+    n = full.generate(2)
+    want = full.result_host(); wc = full.window_counts()
+    p = pkg.XgridPlan(0)
+    for _ in range(2):                                   # twice: the second call reuses the plan's buffers
+        p.set_dst_latlon(nlon, nlat)
+        nbytes = p.set_src_sharded([ni] * 6, [ni] * 6, lonc.reshape(-1), latc.reshape(-1), wins)
+        assert 0 < nbytes < lonc.size * 16
+        assert p.generate(2) == n
+        got = p.result_host()
+        assert p.window_counts() == wc
+        for k in want:
+            assert np.array_equal(got[k], want[k]), k
+    full.close(); p.close()
