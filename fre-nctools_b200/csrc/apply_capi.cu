@@ -524,4 +524,14 @@ extern "C" int xgb_plan_regrid(xgb_plan* p, unsigned int opcode, int nfields, co
   return 0;
 }
 
+// test hook: SharedDiv (csrc/shared_div.cuh) against the compiler's division on n host pairs; *nbad = quotients that differ
+extern "C" int xgb_shared_div_check(long long n, const double* a, const double* b, long long* nbad)
+{
+  unsigned long long bad = 0;
+  if (n <= 0 || !a || !b || !nbad) { xgb_set_error("xgb_shared_div_check: bad arguments"); return 1; }
+  if (shared_div_check(n, a, b, &bad)) { xgb_set_error("xgb_shared_div_check: device run failed"); return 1; }
+  *nbad = (long long)bad;
+  return 0;
+}
+
 extern "C" long long xgb_plan_apply_nxgrid(xgb_plan* p) { return (p && p->apply) ? p->apply->nxgrid : -1; }

@@ -59,6 +59,7 @@ void launch_grad_c2l_packed(const GradTile* tiles, int ntiles, long long ncell, 
 void launch_apply_packed(bool has_missing, const ApplyCsr& csr, long long ndst, int nf, const double* packed, long long ncell_src,
                          double missing, double* out, cudaStream_t st, int sum_mode, int nx_out);
 // field-transposed order-2 path: gradient + transpose into per-source-cell records, then the warp-per-destination-cell apply
+int shared_div_check(long long n, const double* a_host, const double* b_host, unsigned long long* nbad_host);
 size_t apply_rec_doubles(long long ncell, int nf, bool has_missing);
 void launch_regrid_rec(const GradTile* tiles, int ntiles, long long ncell, int nf, const double* data, long long data_stride, double* rec,
                        bool has_missing, double missing, const ApplyCsr& csr, long long ndst, double apply_missing, int sum_mode,

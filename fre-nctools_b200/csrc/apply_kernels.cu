@@ -13,6 +13,7 @@
 //
 // FP64, -fmad=false, reference association order throughout.
 #include "apply_internal.h"
+#include "shared_div.cuh"
 
 namespace xgb {
 
@@ -485,6 +486,7 @@ void launch_grad_c2l_packed(const GradTile* tiles, int ntiles, long long ncell, 
 // shared memory so the field-major output rows are written 256 bytes at a time.
 // =============================================================================================
 constexpr int kRecFields = 8;      // field-levels a gradient block transposes at a time
+constexpr int kRecChunk = 32;      // field-levels per gradient block
 
 template <bool MISSING>
 __global__ void __launch_bounds__(128)
@@ -522,8 +524,10 @@ grad_c2l_rec_kernel(const GradTile* __restrict__ tiles, int ntiles, long long nc
     }
     area = g.area[lc];
   }
-  for (int f0 = 0; f0 < nf; f0 += kRecFields) {
-    const int nk = (nf - f0 < kRecFields) ? nf - f0 : kRecFields;
+  // blockIdx.y: a chunk of kRecChunk field-levels (the metrics above are read once per chunk)
+  const int fbeg = blockIdx.y * kRecChunk, fend = (fbeg + kRecChunk < nf) ? fbeg + kRecChunk : nf;
+  for (int f0 = fbeg; f0 < fend; f0 += kRecFields) {
+    const int nk = (fend - f0 < kRecFields) ? fend - f0 : kRecFields;
     if (live) {
 #pragma unroll 1
       for (int k = 0; k < nk; ++k) {
@@ -569,58 +573,157 @@ grad_c2l_rec_kernel(const GradTile* __restrict__ tiles, int ntiles, long long nc
   }
 }
 
+// A block = a tile of kTileD consecutive destination cells x up to 256 field-levels; warp w owns 64 of the field-levels (two per
+// lane, 16-byte loads) and walks the tile's destination cells one after the other.  The tile's exchange-cell entries sit in
+// shared memory as 32-byte records (read once per block), so an entry costs a warp two broadcast 16-byte reads, three 512-byte
+// coalesced loads and twelve FP64 operations for 64 results.  Instruction counts per 64 results (ncu, configs[1]): first
+// version (one destination cell x 32 fields per warp, entries from global memory) 350; with staged entries 215, of which 44
+// were the both-ways select between staged and global entries and 40 the range checks of a shared-reciprocal division that
+// did not pay at two quotients per reciprocal (removed here; it stays in the gradient kernel, 64 quotients per reciprocal).
+#ifndef XGB_TILE_D
+#define XGB_TILE_D 8
+#endif
+constexpr int kTileD = XGB_TILE_D;
+constexpr int kTileE = 12 * XGB_TILE_D;   // entries staged per tile (mean 1.6 per destination cell on configs[1]); more: generic loop
+
+struct __align__(16) TileEntry { double area, di, dj; long long cell; };
+
+// a source cell's record for this lane's two field-levels
 template <bool MISSING>
-__global__ void __launch_bounds__(256)
+struct RecPair {
+  double2 v, gx, gy, gm;
+  __device__ __forceinline__ void load(const double* __restrict__ recf, long long cstride, int nfp, long long cell)
+  {
+    const double* rc = recf + cell * cstride;
+    v = *reinterpret_cast<const double2*>(rc);
+    gx = *reinterpret_cast<const double2*>(rc + nfp);
+    gy = *reinterpret_cast<const double2*>(rc + 2 * nfp);
+    if (MISSING) gm = *reinterpret_cast<const double2*>(rc + 3 * nfp);
+  }
+  __device__ __forceinline__ void add(double area, double di, double dj, double missing, double& acc0, double& acc1, double& as0,
+                                      double& as1, bool& seen0, bool& seen1) const
+  {
+    if (MISSING) {
+      if (v.x != missing) {                                               // :766
+        if (gm.x != 0.0) acc0 += v.x * area;                              // :779
+        else acc0 += (v.x + gx.x * di + gy.x * dj) * area;                // :782, :806
+        as0 += area; seen0 = true;
+      }
+      if (v.y != missing) {
+        if (gm.y != 0.0) acc1 += v.y * area;
+        else acc1 += (v.y + gx.y * di + gy.y * dj) * area;
+        as1 += area; seen1 = true;
+      }
+    } else {
+      acc0 += (v.x + gx.x * di + gy.x * dj) * area;
+      acc1 += (v.y + gx.y * di + gy.y * dj) * area;
+      as0 += area;
+    }
+  }
+};
+
+#ifndef XGB_APPLY_BLOCKS
+#define XGB_APPLY_BLOCKS 8
+#endif
+template <bool MISSING>
+__global__ void __launch_bounds__(128, XGB_APPLY_BLOCKS)
 apply_rec_kernel(ApplyCsr csr, long long ndst, int nf, int nfp, const double* __restrict__ rec, double missing, int sum_mode,
                  double* __restrict__ out)
 {
   constexpr int NC = MISSING ? 4 : 3;
-  __shared__ double res[32][33];                                  // [field][destination cell]
-  const int nft = (nf + 31) / 32;
-  const long long d0 = (long long)(blockIdx.x / nft) * 32;       // field tile fastest: a destination tile's records stay in L1 / L2
-  const int f0 = (int)(blockIdx.x % nft) * 32;
+  __shared__ double res[4][64][kTileD + 1];                       // [warp][field][destination cell]
+  __shared__ uint32_t s_off[kTileD + 1];
+  __shared__ TileEntry s_ent[kTileE];
+  const long long d0 = (long long)blockIdx.x * kTileD;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int f = f0 + lane;
-  const bool fl = f < nf;
-#pragma unroll 1
-  for (int r = 0; r < 4; ++r) {
-    const int dl = wid * 4 + r;
-    const long long d = d0 + dl;
-    double result = missing;
-    if (d < ndst) {
-      const uint32_t b = csr.off[d], e = csr.off[d + 1];
-      double acc = 0.0, asum = 0.0;
-      bool seen = false;
-      for (uint32_t q = b; q < e; ++q) {
-        const double area = csr.area[q], di = csr.di[q], dj = csr.dj[q];     // warp-uniform
-        const double* rc = rec + (long long)csr.cell[q] * NC * nfp + f;
-        if (fl) {
-          const double v = rc[0], gx = rc[nfp], gy = rc[2 * nfp];
-          if (MISSING) {
-            if (v == missing) continue;                                     // :766
-            if (rc[3 * nfp] != 0.0) acc += v * area;                        // :779
-            else acc += (v + gx * di + gy * dj) * area;                     // :782, :806
-            asum += area; seen = true;
-          } else {
-            acc += (v + gx * di + gy * dj) * area;
-            asum += area;
-          }
+  const int nd = (ndst - d0 < kTileD) ? (int)(ndst - d0) : kTileD;
+  if (threadIdx.x <= kTileD) s_off[threadIdx.x] = csr.off[d0 + (threadIdx.x < nd ? threadIdx.x : nd)];
+  __syncthreads();
+  const uint32_t q0 = s_off[0];
+  const int ne = (int)(s_off[nd] - q0);
+  const bool staged = ne <= kTileE;
+  if (staged)
+    for (int k = threadIdx.x; k < ne; k += 128)
+      s_ent[k] = TileEntry{csr.area[q0 + k], csr.di[q0 + k], csr.dj[q0 + k], (long long)csr.cell[q0 + k]};
+  __syncthreads();
+  const int fw = blockIdx.y * 256 + wid * 64;                    // this warp's 64 field-levels
+  if (fw >= nf) return;                                           // warp-uniform
+  const int f = fw + 2 * lane;                                    // this lane's two: f, f + 1
+  const bool l0 = f < nf;
+  const double* recf = rec + f;
+  const long long cstride = (long long)NC * nfp;
+  for (int dl = 0; dl < nd; ++dl) {
+    const int b = (int)(s_off[dl] - q0), e = (int)(s_off[dl + 1] - q0);
+    double acc0 = 0.0, acc1 = 0.0, as0 = 0.0, as1 = 0.0;
+    bool seen0 = false, seen1 = false;
+    if (l0) {
+      if (staged) {
+        // (tried: keeping the records of a destination cell's first two entries in registers while the next cells name the same
+        // source cells — two thirds of the record loads go away, L1 hit rate 49 -> 63 %, but the kernel got slower, 2.2 -> 2.9 ms)
+        for (int q = b; q < e; ++q) {
+          const double2 p0 = *reinterpret_cast<const double2*>(&s_ent[q].area);       // (area, di)
+          RecPair<MISSING> rr;
+          rr.load(recf, cstride, nfp, s_ent[q].cell);
+          rr.add(p0.x, p0.y, s_ent[q].dj, missing, acc0, acc1, as0, as1, seen0, seen1);
+        }
+      } else {
+        for (int q = b; q < e; ++q) {
+          RecPair<MISSING> rr;
+          rr.load(recf, cstride, nfp, (long long)csr.cell[q0 + q]);
+          rr.add(csr.area[q0 + q], csr.di[q0 + q], csr.dj[q0 + q], missing, acc0, acc1, as0, as1, seen0, seen1);
         }
       }
-      const bool any = MISSING ? seen : (e > b);
-      if (sum_mode) result = (asum == 0) ? (any ? 0.0 : missing) : acc;    // cell_methods "sum", :821-830
-      else if (asum > 0) result = acc / asum;                              // :833-834
-      else if (any) result = 0.0;                                          // :835-836
-      else result = missing;                                               // :837-838
     }
-    res[lane][dl] = result;
+    double r0, r1;
+    if (!MISSING) {
+      const bool any = e > b;
+      if (sum_mode) { r0 = (as0 == 0) ? (any ? 0.0 : missing) : acc0; r1 = (as0 == 0) ? (any ? 0.0 : missing) : acc1; }   // :821-830
+      else if (as0 > 0) { r0 = acc0 / as0; r1 = acc1 / as0; }                                                             // :833-834
+      else { r0 = r1 = any ? 0.0 : missing; }                                                                             // :835-838
+    } else if (sum_mode) {
+      r0 = (as0 == 0) ? (seen0 ? 0.0 : missing) : acc0; r1 = (as1 == 0) ? (seen1 ? 0.0 : missing) : acc1;
+    } else {
+      r0 = (as0 > 0) ? acc0 / as0 : (seen0 ? 0.0 : missing);
+      r1 = (as1 > 0) ? acc1 / as1 : (seen1 ? 0.0 : missing);
+    }
+    res[wid][2 * lane][dl] = r0; res[wid][2 * lane + 1][dl] = r1;
   }
-  __syncthreads();
-#pragma unroll 1
-  for (int r = 0; r < 4; ++r) {
-    const int fr = wid * 4 + r;
-    if (f0 + fr < nf && d0 + lane < ndst) out[(long long)(f0 + fr) * ndst + d0 + lane] = res[fr][lane];
+  __syncwarp();
+  // field-major rows: kTileD destination cells are contiguous; 32 / kTileD rows per pass
+  constexpr int kRowsPerPass = 32 / kTileD;
+  const int dl = lane % kTileD, sub = lane / kTileD;
+  double* o = out + (long long)(fw + sub) * ndst + d0 + dl;
+  const long long ostep = (long long)kRowsPerPass * ndst;
+  if (fw + 64 <= nf && nd == kTileD) {
+#pragma unroll 4
+    for (int fr = sub; fr < 64; fr += kRowsPerPass, o += ostep) *o = res[wid][fr][dl];
+  } else {
+    for (int fr = sub; fr < 64; fr += kRowsPerPass, o += ostep)
+      if (fw + fr < nf && dl < nd) *o = res[wid][fr][dl];
   }
+}
+
+// self-check of shared_div.cuh: quotients of a[i] / b[i] by SharedDiv against the compiler's division, bit for bit
+__global__ void shared_div_check_kernel(long long n, const double* __restrict__ a, const double* __restrict__ b, unsigned long long* nbad)
+{
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const SharedDiv sd(b[i]);
+  const double q = sd.div(a[i]), w = a[i] / b[i];
+  if (__double_as_longlong(q) != __double_as_longlong(w) && !(q != q && w != w)) atomicAdd(nbad, 1ull);
+}
+
+int shared_div_check(long long n, const double* a_host, const double* b_host, unsigned long long* nbad_host)
+{
+  double *a = nullptr, *b = nullptr;
+  unsigned long long* nbad = nullptr;
+  if (cudaMalloc(&a, n * 8) != cudaSuccess || cudaMalloc(&b, n * 8) != cudaSuccess || cudaMalloc(&nbad, 8) != cudaSuccess) return 1;
+  cudaMemcpy(a, a_host, n * 8, cudaMemcpyHostToDevice); cudaMemcpy(b, b_host, n * 8, cudaMemcpyHostToDevice);
+  cudaMemset(nbad, 0, 8);
+  shared_div_check_kernel<<<(unsigned)((n + 255) / 256), 256>>>(n, a, b, nbad);
+  const cudaError_t e = cudaMemcpy(nbad_host, nbad, 8, cudaMemcpyDeviceToHost);
+  cudaFree(a); cudaFree(b); cudaFree(nbad);
+  return e == cudaSuccess ? 0 : 1;
 }
 
 size_t apply_rec_doubles(long long ncell, int nf, bool has_missing)
@@ -635,16 +738,17 @@ void launch_regrid_rec(const GradTile* tiles, int ntiles, long long ncell, int n
 {
   if (ncell <= 0 || nf <= 0 || ndst <= 0) return;
   const int nfp = (nf + 3) & ~3;
-  const unsigned gblk = (unsigned)((ncell + 127) / 128);
-  const long long ablk = ((ndst + 31) / 32) * ((nf + 31) / 32);
-  if (ablk >= (1ll << 31)) return;
+  const dim3 gblk((unsigned)((ncell + 127) / 128), (unsigned)((nf + kRecChunk - 1) / kRecChunk));
+  const long long atiles = (ndst + kTileD - 1) / kTileD;
+  if (atiles >= (1ll << 31)) return;
+  const dim3 ablk((unsigned)atiles, (unsigned)((nf + 255) / 256));
   g_launches += 2;
   if (has_missing) {
     grad_c2l_rec_kernel<true><<<gblk, 128, 0, st>>>(tiles, ntiles, ncell, nf, nfp, data, data_stride, rec, missing);
-    apply_rec_kernel<true><<<(unsigned)ablk, 256, 0, st>>>(csr, ndst, nf, nfp, rec, apply_missing, sum_mode, out);
+    apply_rec_kernel<true><<<ablk, 128, 0, st>>>(csr, ndst, nf, nfp, rec, apply_missing, sum_mode, out);
   } else {
     grad_c2l_rec_kernel<false><<<gblk, 128, 0, st>>>(tiles, ntiles, ncell, nf, nfp, data, data_stride, rec, missing);
-    apply_rec_kernel<false><<<(unsigned)ablk, 256, 0, st>>>(csr, ndst, nf, nfp, rec, apply_missing, sum_mode, out);
+    apply_rec_kernel<false><<<ablk, 128, 0, st>>>(csr, ndst, nf, nfp, rec, apply_missing, sum_mode, out);
   }
 }
 

@@ -106,6 +106,8 @@ void setup_conserve_interp(int ntiles_in, const void *grid_in /* const Grid_conf
 void do_scalar_conserve_interp(void *interp /* Interp_config* */, int varid, int ntiles_in, const void *grid_in,
                                int ntiles_out, const void *grid_out, const void *field_in /* const Field_config* */,
                                void *field_out /* Field_config* */, unsigned int opcode, int nz);
+/* test hook: the shared-reciprocal division of the apply kernel (csrc/shared_div.cuh) against `/` on the device */
+int xgb_shared_div_check(long long n, const double *a, const double *b, long long *nbad);
 /* sizeof/offsetof of the mirrored structs (test hook) */
 int xgb_abi_layout(size_t *out, int cap);
 

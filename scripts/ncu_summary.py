@@ -71,7 +71,7 @@ def main():
         f.write(" | ".join(keys) + "\n")
         for d in out:
             f.write(" | ".join(("%.4g" % d[k]) if isinstance(d.get(k), float) else str(d.get(k, "")) for k in keys)
-                    + " (dram in %s)\n" % d.get("dram_read_unit", "?"))
+                    + " (dram_read in %s, dram_write in %s)\n" % (d.get("dram_read_unit", "?"), d.get("dram_write_unit", "?")))
     print(open(base + ".txt").read())
 
 

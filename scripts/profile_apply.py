@@ -1,18 +1,29 @@
-"""Run the apply leg of bench.py alone (configs[1]: C96 -> 1440x720 order 2, 396 field-levels), for ncu captures:
-    ncu --set full -k regex:apply_kernel\\|grad_c2l -o gpurun_out/apply python scripts/profile_apply.py"""
+#!/usr/bin/env python
+"""Developer tool: one batched order-2 regrid of BASELINE configs[1] (C96 -> 1440x720, 396 field-levels) for ncu."""
 import os
 import sys
 
+import numpy as np
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
+import xgtest  # noqa: E402
 
-import __graft_entry__ as ge  # noqa: E402
-import bench  # noqa: E402
-
-pkg = ge.load_package()
-torch.cuda.set_device(0)
-steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
-r = bench.apply_leg(pkg, torch, None, 0, 1, 0, steps, 1)
-print({k: r[k] for k in ("value", "ms_per_step", "field_levels_per_sec")}, r["e2e"])
+pkg = xgtest.package()
+ni, nlon, nlat, B = 96, 1440, 720, 396
+lonc, latc, lont, latt = pkg.cubed_sphere_grid(ni, centers=True)
+lon2, lat2 = pkg.latlon_grid(nlon, nlat)
+hm = xgtest.cubed_sphere_halo_map(lonc, latc)
+plan = pkg.XgridPlan(0)
+plan.set_dst(lon2, lat2); plan.set_src(lonc, latc)
+plan.generate(2); plan.apply_setup()
+plan.grad_setup(xgtest.with_halo(lont.reshape(-1), hm), xgtest.with_halo(latt.reshape(-1), hm))
+rng = np.random.default_rng(1)
+f = rng.uniform(0, 1, (B, 6 * ni * ni))
+d_in = torch.from_numpy(xgtest.with_halo(f, hm).reshape(-1)).cuda()
+d_out = torch.empty(B * nlon * nlat, dtype=torch.float64, device="cuda")
+for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
+    plan.regrid(2, d_in, B, out=d_out)
+torch.cuda.synchronize(); plan.sync()
+print("ok")

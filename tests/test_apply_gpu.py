@@ -407,3 +407,28 @@ def test_config1_full_size_396_field_levels_three_compared_with_the_oracle(pkg):
         assert np.array_equal(out[k], want), k
     assert np.all(np.isfinite(out))
     p.close()
+
+
+def test_shared_reciprocal_division_is_the_compilers_division(pkg):
+    """csrc/shared_div.cuh: out = sum / out_area for every field-level of a destination cell shares one reciprocal.  Each
+    quotient must be bit-identical to `a / b`: 2^24 pairs over the operand ranges the apply path sees (areas 1e3..1e13,
+    sums of either sign), wide random exponents, and the edges (tiny, huge, zero, equal, powers of two)."""
+    import ctypes as C
+    L = pkg.lib()
+    L.xgb_shared_div_check.argtypes = [C.c_longlong, C.c_void_p, C.c_void_p, C.POINTER(C.c_longlong)]
+    rng = np.random.default_rng(2024)
+    n = 1 << 22
+    sets = []
+    sets.append((rng.normal(0, 1, n) * 10.0 ** rng.uniform(0, 14, n), 10.0 ** rng.uniform(3, 13, n)))
+    sets.append((rng.normal(0, 1, n) * 2.0 ** rng.integers(-1000, 1000, n), rng.uniform(1, 2, n) * 2.0 ** rng.integers(-1000, 1000, n)))
+    m = rng.uniform(1, 2, n)
+    sets.append((m * rng.integers(1, 1000, n), m))                                            # exact and nearly exact quotients
+    edge = np.array([0.0, -0.0, 1.0, -1.0, 2.0 ** -1074, 2.0 ** -1022, 2.0 ** 1023, 1.7976931348623157e308, 3.0, 1.0 / 3.0, np.inf, np.nan, 5e-324])
+    ea, eb = np.meshgrid(edge, edge)
+    sets.append((ea.reshape(-1).copy(), eb.reshape(-1).copy()))
+    with np.errstate(all="ignore"):
+        for a, b in sets:
+            a = np.ascontiguousarray(a, np.float64); b = np.ascontiguousarray(b, np.float64)
+            bad = C.c_longlong(-1)
+            assert L.xgb_shared_div_check(a.size, a.ctypes.data, b.ctypes.data, C.byref(bad)) == 0
+            assert bad.value == 0, bad.value
