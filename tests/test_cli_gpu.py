@@ -371,3 +371,49 @@ def test_order2_onto_several_output_tiles_equals_the_reference(pkg, dataset):
         for k in ("t_in", "i_in", "j_in", "i_out", "j_out", "di", "dj"):
             assert np.array_equal(got[k], ref[t][k]), (t, k)
         assert np.allclose(got["area"], ref[t]["area"], rtol=1e-15, atol=0), t     # the reader rescales: (a / 4 pi R^2) * 4 pi R^2
+
+
+def test_fregrid_b200_against_the_unmodified_reference_fregrid(pkg, dataset):
+    """The drop-in claim at the command line: oracle/_ref/fregrid_ref — the reference's own fregrid (main, option parsing, mosaic
+    and field readers, mpp_io, conserve_interp, writers) compiled unmodified over the netCDF-C shim — and fregrid_b200 run with
+    the same arguments on the same files.  Remap files: same cells, same order, bit-identical areas and distances (byte-
+    identical when the container versions agree).  Output files: same variables, dimensions and attributes; order 1 values
+    identical; order 2 (the product computes the c2l metrics on the device) to 1e-11."""
+    ref = os.path.join(xgtest.ORACLE_DIR, "_ref", "fregrid_ref")
+    xgtest.ref_lib()
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/fregrid_ref not built")
+    ds = dataset
+    for method, order, tol in (("conserve_order1", 1, 0.0), ("conserve_order2", 2, 1e-11)):
+        common = ["--input_mosaic", f"C{ds['n']}_mosaic.nc", "--nlon", "48", "--nlat", "24", "--input_file", "atmos",
+                  "--scalar_field", "temp,ps,orog", "--interp_method", method]
+        r = subprocess.run([ref] + common + ["--output_file", f"cmp_ref_{order}.nc", "--remap_file", f"cmp_ref_remap_{order}.nc"],
+                           cwd=ds["dir"], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, (r.stdout[-1000:], r.stderr[-1000:])
+        _run(pkg, ds, *common, "--output_file", f"cmp_b200_{order}.nc", "--remap_file", f"cmp_b200_remap_{order}.nc")
+        a = open(os.path.join(ds["dir"], f"cmp_ref_remap_{order}.nc"), "rb").read()
+        b = open(os.path.join(ds["dir"], f"cmp_b200_remap_{order}.nc"), "rb").read()
+        if a[3] == b[3]:
+            assert a == b, f"remap files differ (order {order})"
+        else:
+            x = _remap_lists(pkg, os.path.join(ds["dir"], f"cmp_ref_remap_{order}.nc"), order)
+            y = _remap_lists(pkg, os.path.join(ds["dir"], f"cmp_b200_remap_{order}.nc"), order)
+            for k in x:
+                assert np.array_equal(x[k], y[k]), (order, k)
+        ga = netcdf_file(os.path.join(ds["dir"], f"cmp_ref_{order}.nc"), "r", mmap=False)
+        gb = netcdf_file(os.path.join(ds["dir"], f"cmp_b200_{order}.nc"), "r", mmap=False)
+        assert list(ga.variables) == list(gb.variables), (list(ga.variables), list(gb.variables))
+        assert dict(ga.dimensions) == dict(gb.dimensions)
+        for name, va in ga.variables.items():
+            vb = gb.variables[name]
+            assert va.dimensions == vb.dimensions and va.typecode() == vb.typecode(), name
+            assert {k: (v if not isinstance(v, np.ndarray) else v.tolist()) for k, v in va._attributes.items()} == \
+                   {k: (v if not isinstance(v, np.ndarray) else v.tolist()) for k, v in vb._attributes.items()}, name
+            xa, xb = np.asarray(va[:], np.float64), np.asarray(vb[:], np.float64)
+            if tol == 0.0 or name not in ("temp", "ps", "orog"):
+                assert np.array_equal(xa, xb), (order, name)
+            else:
+                m = (xa != MISSING) | (xb != MISSING)
+                assert np.array_equal(xa == MISSING, xb == MISSING), name
+                assert np.max(np.abs(xa[m] - xb[m]) / np.maximum(np.abs(xa[m]), 1e-30), initial=0.0) <= tol, (order, name)
+        ga.close(); gb.close()
