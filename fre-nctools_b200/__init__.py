@@ -677,3 +677,70 @@ def get_grid_area(lon, lat):
     lib().get_grid_area(C.byref(C.c_int(nx)), C.byref(C.c_int(ny)), lon.ctypes.data_as(C.c_void_p),
                         lat.ctypes.data_as(C.c_void_p), area.ctypes.data_as(C.c_void_p))
     return area
+
+
+# ---------------------------------------------------------------------------------------------
+# make_coupler_mosaic's exchange grids (csrc/coupler.cu, include/xgrid_b200.h Part 5)
+# ---------------------------------------------------------------------------------------------
+class _MosaicGrid(C.Structure):
+    _fields_ = [("ntiles", C.c_int), ("nx", C.c_void_p), ("ny", C.c_void_p), ("lon", C.c_void_p), ("lat", C.c_void_p)]
+
+
+class _CouplerList(C.Structure):
+    _fields_ = [("n", C.c_longlong)] + [(k, C.POINTER(C.c_int)) for k in ("t1", "i1", "j1", "t2", "i2", "j2")] + \
+               [(k, C.POINTER(C.c_double)) for k in ("area", "d1i", "d1j", "d2i", "d2j")]
+
+
+class _CouplerResult(C.Structure):
+    _fields_ = [("atmxlnd", _CouplerList), ("atmxocn", _CouplerList), ("lndxocn", _CouplerList),
+                ("ncell_atm", C.c_longlong), ("ncell_lnd", C.c_longlong), ("ncell_ocn", C.c_longlong)] + \
+               [(k, C.POINTER(C.c_double)) for k in ("area_atm", "area_lnd", "area_ocn", "lnd_xarea", "ocn_xarea")]
+
+
+def _mosaic_struct(tiles):
+    """tiles: list of (lon, lat) vertex arrays [ny+1, nx+1] in radians -> (_MosaicGrid, keepalive)"""
+    nx = np.array([t[0].shape[1] - 1 for t in tiles], np.int32)
+    ny = np.array([t[0].shape[0] - 1 for t in tiles], np.int32)
+    lon = np.concatenate([np.ascontiguousarray(t[0], np.float64).ravel() for t in tiles])
+    lat = np.concatenate([np.ascontiguousarray(t[1], np.float64).ravel() for t in tiles])
+    g = _MosaicGrid(len(tiles), nx.ctypes.data, ny.ctypes.data, lon.ctypes.data, lat.ctypes.data)
+    return g, (nx, ny, lon, lat)
+
+
+def make_coupler_xgrid(atm, ocn, omask, lnd=None, interp_order=2, area_ratio_thresh=1.0e-6, tile_nest=-1,
+                       ocn_same_as_atm=False, device=0):
+    """The exchange grids of make_coupler_mosaic (make_coupler_mosaic.c:1250-1720, :2556-2808) on the GPU.
+    atm / lnd / ocn: lists of (lon, lat) vertex arrays per tile, radians; lnd=None: the land model runs on the atmosphere mosaic.
+    omask: list of ocean-fraction arrays [ny, nx] per ocean tile.  Returns a dict of the three lists (numpy arrays, 0-based
+    parent cells) and the per-cell sums behind land_mask / ocean_mask."""
+    L = lib()
+    L.xgb_make_coupler_xgrid.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
+    L.xgb_coupler_result_free.argtypes = [C.c_void_p]
+    ga, ka = _mosaic_struct(atm)
+    go, ko = _mosaic_struct(ocn)
+    gl, kl = (_mosaic_struct(lnd) if lnd is not None else (None, None))
+    mask = np.concatenate([np.ascontiguousarray(m, np.float64).ravel() for m in omask])
+    if mask.size != int(sum((t[0].shape[0] - 1) * (t[0].shape[1] - 1) for t in ocn)):
+        raise ValueError("omask does not match the ocean mosaic")
+    res = _CouplerResult()
+    rc = L.xgb_make_coupler_xgrid(device, interp_order, area_ratio_thresh, tile_nest, 1 if lnd is None else 0,
+                                  1 if ocn_same_as_atm else 0, C.addressof(ga), C.addressof(gl) if gl is not None else None,
+                                  C.addressof(go), mask.ctypes.data, C.addressof(res))
+    if rc != 0:
+        raise XgridError(_err())
+    try:
+        def lst(l):
+            n = int(l.n)
+            d = {k: np.ctypeslib.as_array(getattr(l, k), (n,)).copy() if n else np.zeros(0, np.int32) for k in ("t1", "i1", "j1", "t2", "i2", "j2")}
+            d["area"] = np.ctypeslib.as_array(l.area, (n,)).copy() if n else np.zeros(0)
+            if interp_order == 2:
+                for k in ("d1i", "d1j", "d2i", "d2j"):
+                    d[k] = np.ctypeslib.as_array(getattr(l, k), (n,)).copy() if n else np.zeros(0)
+            return d
+        out = dict(atmxlnd=lst(res.atmxlnd), atmxocn=lst(res.atmxocn), lndxocn=lst(res.lndxocn))
+        for k, n in (("area_atm", res.ncell_atm), ("area_lnd", res.ncell_lnd), ("area_ocn", res.ncell_ocn),
+                     ("lnd_xarea", res.ncell_lnd), ("ocn_xarea", res.ncell_ocn)):
+            out[k] = np.ctypeslib.as_array(getattr(res, k), (int(n),)).copy()
+        return out
+    finally:
+        L.xgb_coupler_result_free(C.addressof(res))

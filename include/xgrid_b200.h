@@ -393,6 +393,47 @@ long long xgb_remap_size(const char *path);                /* read_mosaic_xgrid_
 int xgb_remap_read(const char *path, int order, long long cap, int *t_in, int *i_in, int *j_in, int *i_out, int *j_out,
                    double *area, double *di, double *dj);
 
+/* ============================================================================================
+ * Part 5 — make_coupler_mosaic's exchange grids (tools/make_coupler_mosaic/make_coupler_mosaic.c)
+ * ============================================================================================
+ * One call replaces the tool's exchange-grid loops and the sums behind its land_mask / ocean_mask files and its
+ * tile1_distance / tile2_distance variables: the per-atmosphere-cell loop (:1250-1720: atm x lnd polygons, atm x ocn cells
+ * scaled by ocn_frac, the land share 1 - ocn_frac of every ocean cell under an atm x lnd polygon), the land x ocean loop
+ * (:2556-2692) and the parent-cell sums (:1739-2030, :2694-2808).  Default clip method only (clip_2dx2d); the tool keeps
+ * reading the mosaics, deriving omask from the topography (:939-960), adding its artificial southern ocean row (:845-876) and
+ * writing the files (:2131-2480, :2810-2960).  Lists come back in the order the tool writes them: atmosphere (land) cell
+ * tile-major / row-major, then land / ocean cell tile-major / row-major; a file of the tool is the sub-list of one (tile1, tile2). */
+typedef struct {
+  int ntiles;
+  const int *nx, *ny;            /* cells per tile */
+  const double *lon, *lat;       /* radians; tile after tile, (ny+1) x (nx+1) vertices each, as get_global_grid returns them */
+} xgb_mosaic_grid;
+
+typedef struct {
+  long long n;
+  int *t1, *i1, *j1;             /* parent cell in the first mosaic: tile, i, j (0-based; the tool writes i+1, j+1) */
+  int *t2, *i2, *j2;             /* parent cell in the second mosaic */
+  double *area;                  /* xgrid_area, m^2 */
+  double *d1i, *d1j, *d2i, *d2j; /* interp_order 2: tile1_distance / tile2_distance (lon, lat); NULL for order 1 */
+} xgb_coupler_list;
+
+typedef struct {
+  xgb_coupler_list atmxlnd, atmxocn, lndxocn;      /* lndxocn is empty when lnd_same_as_atm */
+  long long ncell_atm, ncell_lnd, ncell_ocn;
+  double *area_atm, *area_lnd, *area_ocn;          /* get_grid_area of every cell (:277) */
+  double *lnd_xarea;                               /* per land cell: sum of its atm x lnd areas (land_mask = lnd_xarea / area_lnd, :2079) */
+  double *ocn_xarea;                               /* per ocean cell: sum of its atm x ocn areas (ocean_mask "areaX", :2037-2046) */
+} xgb_coupler_result;
+
+/* tile_nest: atmosphere tile left out of the parent sums (-1: none).  lnd_same_as_atm: the land model runs on the atmosphere
+ * mosaic (lnd may be NULL; an atmosphere cell then meets its own land cell only, :1474-1486).  ocn_same_as_atm: ocean tile n is
+ * searched for atmosphere tile n only (:1338-1345).  omask: ocean fraction of every ocean cell, tile after tile.  Results are
+ * malloc'ed; release them with xgb_coupler_result_free. */
+int  xgb_make_coupler_xgrid(int device, int interp_order, double area_ratio_thresh, int tile_nest, int lnd_same_as_atm,
+                            int ocn_same_as_atm, const xgb_mosaic_grid *atm, const xgb_mosaic_grid *lnd,
+                            const xgb_mosaic_grid *ocn, const double *omask, xgb_coupler_result *out);
+void xgb_coupler_result_free(xgb_coupler_result *r);
+
 #ifdef __cplusplus
 }
 #endif
