@@ -290,7 +290,7 @@ def apply_leg(pkg, torch, dist, rank, world, local, steps, warmup):
             "metric": "apply_GB_per_sec", "value": gbs, "unit": "GB/s (algorithmic bytes)", "ms_per_step": ms,
             "field_levels_per_sec": B / (ms * 1e-3), "algorithmic_bytes_per_step": int(bytes_step), "gpu_launches_per_step": int(launches),
             "roofline": {"bound": "hbm", "achieved": gbs_gpu, "peak": hbm_peak, "unit": "GB/s per GPU", "frac": gbs_gpu / hbm_peak,
-                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s", "kernel": "apply_packed_kernel + grad_c2l_kernel",
+                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s", "kernel": ("apply_packed_kernel + grad_c2l_kernel" if os.environ.get("XGB_APPLY_PACKED") == "1" else "apply_rec_kernel + grad_c2l_rec_kernel"),
                          "note": "per GPU: whole-job algorithmic GB/s divided by the number of ranks, against ONE GPU's measured HBM peak"},
             "e2e": {"value": bytes_step / (e2e_ms * 1e-3) * 1e-9, "unit": "GB/s (algorithmic bytes)", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(h_in.numel() * 8 * world), "d2h_bytes_per_step": int(h_out.numel() * 8 * world)},

@@ -479,12 +479,23 @@ void launch_grad_c2l_packed(const GradTile* tiles, int ntiles, long long ncell, 
 // =============================================================================================
 // Field-transposed order-2 path (xgb_plan_regrid, round 2).  ncu on apply_packed_kernel: 17 % of HBM, LSU wavefronts 59 % —
 // with field-major arrays every (exchange cell, field-level) is its own 32-byte gather.  Here the gradient kernel leaves, per
-// SOURCE CELL, the values / grad_x / grad_y (/ grad_mask) of all field-levels next to each other: rec[(cell * NC + comp) * nfp + f].
+// SOURCE CELL, the values / grad_x / grad_y (/ grad_mask) of all field-levels next to each other: see rec_index below.
 // The apply kernel puts the 32 lanes of a warp on 32 consecutive field-levels of ONE destination cell: an exchange-cell entry
 // is three 256-byte coalesced loads for the whole warp, its weights are warp-uniform, every lane adds its field's terms in list
 // order (the reference's order, conserve_interp.c:785-812), and a block's 32 x 32 (destination, field) results go through
 // shared memory so the field-major output rows are written 256 bytes at a time.
 // =============================================================================================
+// record layout: rec[cell][f / 64][comp][f % 64] — per source cell and per chunk of 64 field-levels (what one warp of the apply
+// kernel owns), the values, grad_x, grad_y (, grad_mask) are 512-byte rows one after the other.  A lane reaches everything it
+// needs of a source cell from ONE address with constant offsets (before: three addresses nfp apart, fourteen integer
+// instructions of 64-bit address arithmetic per entry), and every 16-byte-per-lane load of the warp is 512 contiguous bytes
+// (a layout with the components of a field-level PAIR adjacent was tried first: same instruction count, but each load then
+// touched 48 sectors for 16 sectors of data and the kernel stayed L1-bound at 2.14 ms).  nfp = nf rounded up to 64.
+constexpr int kRecLane = 64;
+__host__ __device__ __forceinline__ long long rec_index(long long cell, int f, int comp, int nc, int nfp)
+{
+  return ((cell * (nfp / kRecLane) + (f / kRecLane)) * nc + comp) * kRecLane + (f % kRecLane);
+}
 constexpr int kRecFields = 8;      // field-levels a gradient block transposes at a time
 constexpr int kRecChunk = 32;      // field-levels per gradient block
 
@@ -560,13 +571,13 @@ grad_c2l_rec_kernel(const GradTile* __restrict__ tiles, int ntiles, long long nc
       }
     }
     __syncthreads();
-    // transposed write-out: kRecFields consecutive field-levels of a cell are 64 contiguous bytes
+    // transposed write-out: kRecFields consecutive field-levels of a cell and a component are 64 contiguous bytes
     for (int idx = threadIdx.x; idx < 128 * kRecFields; idx += 128) {
       const int cl = idx / kRecFields, k = idx % kRecFields;
       if (c0 + cl < ncell && k < nk) {
 #pragma unroll
         for (int comp = 0; comp < NC; ++comp)
-          rec[((c0 + cl) * NC + comp) * nfp + f0 + k] = tile[comp][cl][k];
+          rec[rec_index(c0 + cl, f0 + k, comp, NC, nfp)] = tile[comp][cl][k];
       }
     }
     __syncthreads();
@@ -586,19 +597,20 @@ grad_c2l_rec_kernel(const GradTile* __restrict__ tiles, int ntiles, long long nc
 constexpr int kTileD = XGB_TILE_D;
 constexpr int kTileE = 12 * XGB_TILE_D;   // entries staged per tile (mean 1.6 per destination cell on configs[1]); more: generic loop
 
-struct __align__(16) TileEntry { double area, di, dj; long long cell; };
+struct __align__(16) TileEntry { double area, di, dj; long long off; };   // off: byte offset of the source cell's records
 
 // a source cell's record for this lane's two field-levels
 template <bool MISSING>
 struct RecPair {
   double2 v, gx, gy, gm;
-  __device__ __forceinline__ void load(const double* __restrict__ recf, long long cstride, int nfp, long long cell)
+  // recf: this lane's pair record of source cell 0; off: byte offset of the source cell
+  __device__ __forceinline__ void load(const char* __restrict__ recf, long long off)
   {
-    const double* rc = recf + cell * cstride;
-    v = *reinterpret_cast<const double2*>(rc);
-    gx = *reinterpret_cast<const double2*>(rc + nfp);
-    gy = *reinterpret_cast<const double2*>(rc + 2 * nfp);
-    if (MISSING) gm = *reinterpret_cast<const double2*>(rc + 3 * nfp);
+    const double2* rc = reinterpret_cast<const double2*>(recf + off);
+    v = __ldg(rc);
+    gx = __ldg(rc + kRecLane / 2);
+    gy = __ldg(rc + kRecLane);
+    if (MISSING) gm = __ldg(rc + 3 * kRecLane / 2);
   }
   __device__ __forceinline__ void add(double area, double di, double dj, double missing, double& acc0, double& acc1, double& as0,
                                       double& as1, bool& seen0, bool& seen1) const
@@ -625,17 +637,20 @@ struct RecPair {
 #ifndef XGB_APPLY_BLOCKS
 #define XGB_APPLY_BLOCKS 8
 #endif
+
 template <bool MISSING>
 __global__ void __launch_bounds__(128, XGB_APPLY_BLOCKS)
 apply_rec_kernel(ApplyCsr csr, long long ndst, int nf, int nfp, const double* __restrict__ rec, double missing, int sum_mode,
                  double* __restrict__ out)
 {
   constexpr int NC = MISSING ? 4 : 3;
-  __shared__ double res[4][64][kTileD + 1];                       // [warp][field][destination cell]
+  constexpr int kResRow = 64 + 4;                                 // row stride = 4 mod 16 doubles: the transposed reads below are conflict-free
+  __shared__ __align__(16) double res[4][kTileD][kResRow];        // [warp][destination cell][field]
   __shared__ uint32_t s_off[kTileD + 1];
   __shared__ TileEntry s_ent[kTileE];
   const long long d0 = (long long)blockIdx.x * kTileD;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long cbytes = (long long)NC * nfp * 8;                // bytes of one source cell's records
   const int nd = (ndst - d0 < kTileD) ? (int)(ndst - d0) : kTileD;
   if (threadIdx.x <= kTileD) s_off[threadIdx.x] = csr.off[d0 + (threadIdx.x < nd ? threadIdx.x : nd)];
   __syncthreads();
@@ -644,39 +659,17 @@ apply_rec_kernel(ApplyCsr csr, long long ndst, int nf, int nfp, const double* __
   const bool staged = ne <= kTileE;
   if (staged)
     for (int k = threadIdx.x; k < ne; k += 128)
-      s_ent[k] = TileEntry{csr.area[q0 + k], csr.di[q0 + k], csr.dj[q0 + k], (long long)csr.cell[q0 + k]};
+      s_ent[k] = TileEntry{csr.area[q0 + k], csr.di[q0 + k], csr.dj[q0 + k], (long long)csr.cell[q0 + k] * cbytes};
   __syncthreads();
   const int fw = blockIdx.y * 256 + wid * 64;                    // this warp's 64 field-levels
   if (fw >= nf) return;                                           // warp-uniform
   const int f = fw + 2 * lane;                                    // this lane's two: f, f + 1
   const bool l0 = f < nf;
-  const double* recf = rec + f;
-  const long long cstride = (long long)NC * nfp;
-  for (int dl = 0; dl < nd; ++dl) {
-    const int b = (int)(s_off[dl] - q0), e = (int)(s_off[dl + 1] - q0);
-    double acc0 = 0.0, acc1 = 0.0, as0 = 0.0, as1 = 0.0;
-    bool seen0 = false, seen1 = false;
-    if (l0) {
-      if (staged) {
-        // (tried: keeping the records of a destination cell's first two entries in registers while the next cells name the same
-        // source cells — two thirds of the record loads go away, L1 hit rate 49 -> 63 %, but the kernel got slower, 2.2 -> 2.9 ms)
-        for (int q = b; q < e; ++q) {
-          const double2 p0 = *reinterpret_cast<const double2*>(&s_ent[q].area);       // (area, di)
-          RecPair<MISSING> rr;
-          rr.load(recf, cstride, nfp, s_ent[q].cell);
-          rr.add(p0.x, p0.y, s_ent[q].dj, missing, acc0, acc1, as0, as1, seen0, seen1);
-        }
-      } else {
-        for (int q = b; q < e; ++q) {
-          RecPair<MISSING> rr;
-          rr.load(recf, cstride, nfp, (long long)csr.cell[q0 + q]);
-          rr.add(csr.area[q0 + q], csr.di[q0 + q], csr.dj[q0 + q], missing, acc0, acc1, as0, as1, seen0, seen1);
-        }
-      }
-    }
+  const char* recf = reinterpret_cast<const char*>(rec + (long long)(fw / kRecLane) * NC * kRecLane + 2 * lane);
+  // result of one destination cell from this lane's sums (conserve_interp.c:821-838)
+  auto finish = [&](bool any, double acc0, double acc1, double as0, double as1, bool seen0, bool seen1) {
     double r0, r1;
     if (!MISSING) {
-      const bool any = e > b;
       if (sum_mode) { r0 = (as0 == 0) ? (any ? 0.0 : missing) : acc0; r1 = (as0 == 0) ? (any ? 0.0 : missing) : acc1; }   // :821-830
       else if (as0 > 0) { r0 = acc0 / as0; r1 = acc1 / as0; }                                                             // :833-834
       else { r0 = r1 = any ? 0.0 : missing; }                                                                             // :835-838
@@ -686,7 +679,34 @@ apply_rec_kernel(ApplyCsr csr, long long ndst, int nf, int nfp, const double* __
       r0 = (as0 > 0) ? acc0 / as0 : (seen0 ? 0.0 : missing);
       r1 = (as1 > 0) ? acc1 / as1 : (seen1 ? 0.0 : missing);
     }
-    res[wid][2 * lane][dl] = r0; res[wid][2 * lane + 1][dl] = r1;
+    return make_double2(r0, r1);
+  };
+  // (tried, each slower than this plain per-cell loop at 1.87 ms, scripts/apply_variants.sh: the records of the two source
+  // cells used last kept in registers, 1.97 ms — a third of the loads, half as many more instructions; one flat loop over the
+  // tile's entries with the records of entry q + 1 requested before entry q is summed, 2.09 ms at 80 registers / 6 blocks,
+  // 2.31 ms with spills at 64 / 8: the kernel lives on resident warps, not on loads in flight per warp)
+  for (int dl = 0; dl < nd; ++dl) {
+    const int b = (int)(s_off[dl] - q0), e = (int)(s_off[dl + 1] - q0);
+    double acc0 = 0.0, acc1 = 0.0, as0 = 0.0, as1 = 0.0;
+    bool seen0 = false, seen1 = false;
+    if (l0) {
+      if (staged) {
+        for (int q = b; q < e; ++q) {
+          const double2 p0 = *reinterpret_cast<const double2*>(&s_ent[q].area);       // (area, di)
+          const double2 p1 = *reinterpret_cast<const double2*>(&s_ent[q].dj);         // (dj, offset)
+          RecPair<MISSING> rr;
+          rr.load(recf, __double_as_longlong(p1.y));
+          rr.add(p0.x, p0.y, p1.x, missing, acc0, acc1, as0, as1, seen0, seen1);
+        }
+      } else {
+        for (int q = b; q < e; ++q) {
+          RecPair<MISSING> rr;
+          rr.load(recf, (long long)csr.cell[q0 + q] * cbytes);
+          rr.add(csr.area[q0 + q], csr.di[q0 + q], csr.dj[q0 + q], missing, acc0, acc1, as0, as1, seen0, seen1);
+        }
+      }
+    }
+    *reinterpret_cast<double2*>(&res[wid][dl][2 * lane]) = finish(e > b, acc0, acc1, as0, as1, seen0, seen1);
   }
   __syncwarp();
   // field-major rows: kTileD destination cells are contiguous; 32 / kTileD rows per pass
@@ -696,10 +716,10 @@ apply_rec_kernel(ApplyCsr csr, long long ndst, int nf, int nfp, const double* __
   const long long ostep = (long long)kRowsPerPass * ndst;
   if (fw + 64 <= nf && nd == kTileD) {
 #pragma unroll 4
-    for (int fr = sub; fr < 64; fr += kRowsPerPass, o += ostep) *o = res[wid][fr][dl];
+    for (int fr = sub; fr < 64; fr += kRowsPerPass, o += ostep) *o = res[wid][dl][fr];
   } else {
     for (int fr = sub; fr < 64; fr += kRowsPerPass, o += ostep)
-      if (fw + fr < nf && dl < nd) *o = res[wid][fr][dl];
+      if (fw + fr < nf && dl < nd) *o = res[wid][dl][fr];
   }
 }
 
@@ -728,7 +748,7 @@ int shared_div_check(long long n, const double* a_host, const double* b_host, un
 
 size_t apply_rec_doubles(long long ncell, int nf, bool has_missing)
 {
-  const int nfp = (nf + 3) & ~3;
+  const int nfp = (nf + kRecLane - 1) / kRecLane * kRecLane;
   return (size_t)ncell * (has_missing ? 4 : 3) * nfp;
 }
 
@@ -737,7 +757,7 @@ void launch_regrid_rec(const GradTile* tiles, int ntiles, long long ncell, int n
                        double* out, cudaStream_t st)
 {
   if (ncell <= 0 || nf <= 0 || ndst <= 0) return;
-  const int nfp = (nf + 3) & ~3;
+  const int nfp = (nf + kRecLane - 1) / kRecLane * kRecLane;
   const dim3 gblk((unsigned)((ncell + 127) / 128), (unsigned)((nf + kRecChunk - 1) / kRecChunk));
   const long long atiles = (ndst + kTileD - 1) / kTileD;
   if (atiles >= (1ll << 31)) return;
