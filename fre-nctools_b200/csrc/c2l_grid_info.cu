@@ -7,6 +7,7 @@
 // 1e-15/excess, because both sides cancel 2*pi out of a sum of four angles); callers that need the reference's
 // exact metrics pass them in with xgb_plan_grad_set_metrics instead.
 #include "apply_internal.h"
+#include "gc_clip.cuh"
 
 namespace xgb {
 
@@ -48,7 +49,7 @@ __device__ __forceinline__ double sph_angle(const double* v1, const double* v2, 
   if (fabs(ddd - 1) < 1.e-30) ddd = 1;
   if (fabs(ddd + 1) < 1.e-30) ddd = -1;
   if (ddd > 1. || ddd < -1.) return (ddd < 0.) ? kPi : 0.;
-  return acos(ddd);
+  return gc::gc_acos(ddd);      // acosl rounded to double, as the reference computes it (gc_clip.cuh)
 }
 
 // mid_pt_sphere (gradient_c2l.c:315-337) -> (lon, lat)

@@ -22,6 +22,14 @@
 #include <math.h>
 #include "ref_trig.cuh"
 
+// The great-circle kernel is bound by instruction fetch (ncu r02v: 11 488 SASS instructions, "no instruction" the top stall by
+// 6x, 14 of 32 lanes active): the large routines are calls on the device, one copy each, instead of inlined at every site.
+#if defined(__CUDACC__)
+#define XGB_HD_CALL static __host__ __device__ __noinline__
+#else
+#define XGB_HD_CALL static inline
+#endif
+
 namespace xgb {
 namespace gc {
 
@@ -64,8 +72,88 @@ XGB_HD dd dd_div(dd a, dd b) {
 // a*b - c*d with doubles, exact products
 XGB_HD dd det2(double a, double b, double c, double d) { return dd_sub(two_prod(a, b), two_prod(c, d)); }
 
-// acosl(x) rounded to double, as spherical_angle (mosaic_util.c:834) produces it
-XGB_HD double gc_acos(double x) { return acos(x); }
+// ---- acosl(x) rounded to double, as spherical_angle (mosaic_util.c:834) produces it ------------------------------------
+// On x86-64 glibc's acosl is the x87 sequence fpatan(sqrt((1 - x)(1 + x)), x) (sysdeps/i386/fpu/e_acosl.c): the angle comes
+// out with a 64-bit mantissa and the assignment to `double angle` rounds it a second time.  great_circle_area subtracts
+// (n - 2) pi from the sum of the angles, so one unit in the last place of an angle is 1e-11 .. 1e-10 of a quarter-degree
+// cell's area: the device acos() (1-2 ulp) cannot meet the 1e-12 the areas are held to.  Here the same formula runs in
+// double-double (atan by a 65-row table of atan(k/64) and a Taylor tail, ~2^-100 relative), and the result is rounded twice
+// the way the hardware does it: to 64 bits, then to 53, ties to even.  That reproduces the reference bit for bit wherever
+// fpatan's own result is the correctly rounded one (Intel documents < 1 ulp of the 64-bit format; tests/test_gc_cpu.py counts
+// the differences against this machine's acosl over millions of arguments).
+#if defined(__CUDACC__)
+static __device__ const double kAtanTabDev[65][2] = {
+#include "atantab.inc"
+};
+#endif
+static const double kAtanTabHost[65][2] = {
+#include "atantab.inc"
+};
+XGB_HD dd atan_row(int k) {
+#if defined(__CUDA_ARCH__)
+  return dd{kAtanTabDev[k][0], kAtanTabDev[k][1]};
+#else
+  return dd{kAtanTabHost[k][0], kAtanTabHost[k][1]};
+#endif
+}
+XGB_HD dd dd_sqrt(dd a) {
+  if (!(a.hi > 0.0)) return dd{0.0, 0.0};
+  const double s = sqrt(a.hi);
+  const dd r = dd_sub(a, two_prod(s, s));                 // one Newton step from a 53-bit root
+  return dd_norm(s, r.hi / (2.0 * s));
+}
+// atan(t), 0 <= t <= 1: atan(c) + atan((t - c) / (1 + t c)), c = k / 64 next to t, the second angle below 1 / 128
+XGB_HD dd dd_atan01(dd t) {
+  const int k = (int)(t.hi * 64.0 + 0.5);
+  const double c = k * 0.015625;
+  const dd r = dd_div(dd_add(t, dd{-c, 0.0}), dd_add(dd_mul_d(t, c), dd{1.0, 0.0}));
+  const dd r2 = dd_mul(r, r);
+  const double z = r2.hi;
+  // atan(r) / r = 1 - z/3 + z^2 (1/5 - z/7 + z^2/9 - z^3/11 + z^4/13 - z^5/15), z <= 2^-14: the bracket in double is enough
+  double p = fma(z, -1.0 / 15.0, 1.0 / 13.0);
+  p = fma(z, p, -1.0 / 11.0);
+  p = fma(z, p, 1.0 / 9.0);
+  p = fma(z, p, -1.0 / 7.0);
+  p = fma(z, p, 1.0 / 5.0);
+  p = (z * z) * p;
+  const dd third{0x1.5555555555555p-2, 0x1.5555555555555p-56};
+  const dd w = dd_add(dd_neg(dd_mul(r2, third)), dd{p, 0.0});
+  return dd_add(atan_row(k), dd_add(r, dd_mul(r, w)));
+}
+// v = hi + lo, hi = fl(v): v rounded to a 64-bit mantissa, then to double (both to nearest even).  The second rounding
+// changes hi only when the first one lands exactly half way between hi and its neighbour on lo's side.
+XGB_HD double round_through_x87(dd v) {
+  const double hi = v.hi, lo = v.lo;
+  if (lo == 0.0 || hi == 0.0) return hi;
+#if defined(__CUDA_ARCH__)
+  const double nb = __longlong_as_double(__double_as_longlong(hi) + (((lo > 0.0) == (hi > 0.0)) ? 1 : -1));
+#else
+  const double nb = nextafter(hi, (lo > 0.0) ? INFINITY : -INFINITY);
+#endif
+  const double gap = fabs(nb - hi);                       // spacing of the doubles on that side, exact
+  const double half = 0.5 * gap, ulp64 = gap * (1.0 / 2048.0);
+  if (fabs(lo) > half - 0.5 * ulp64) {                    // rounds to the half-way point at 64 bits: tie for the double
+    const bool hi_even = (trig::bits(hi) & 1u) == 0u;
+    return hi_even ? hi : nb;
+  }
+  return hi;
+}
+XGB_HD double gc_acos(double x) {
+  const dd pi{0x1.921fb54442d18p+1, 0x1.1a62633145c07p-53}, half_pi{0x1.921fb54442d18p+0, 0x1.1a62633145c07p-54};
+  if (x >= 1.0) return 0.0;
+  if (x <= -1.0) return kPiD;
+  const double ax = fabs(x);
+  const dd s = dd_sqrt(dd_mul(two_sum(1.0, -x), two_sum(1.0, x)));     // sin of the angle; 1 -+ x are exact as double-doubles
+  dd a;
+  if (s.hi <= ax) {                                                    // within 45 degrees of a pole of the formula
+    a = dd_atan01(dd_div(s, dd{ax, 0.0}));
+    if (x < 0.0) a = dd_sub(pi, a);
+  } else {
+    a = dd_atan01(dd_div(dd{ax, 0.0}, s));
+    a = (x < 0.0) ? dd_add(half_pi, a) : dd_sub(half_pi, a);
+  }
+  return round_through_x87(a);
+}
 
 struct V3 { double x, y, z; };
 
@@ -75,8 +163,9 @@ XGB_HD bool same_point(double x1, double y1, double z1, double x2, double y2, do
 
 XGB_HD V3 cross(const V3& a, const V3& b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
 
-// spherical_angle (mosaic_util.c:800-838), plain double as an autotools build compiles it
-XGB_HD double spherical_angle(const V3& v1, const V3& v2, const V3& v3) {
+// spherical_angle (mosaic_util.c:800-838), plain double as an autotools build compiles it.  exact: the angle as the reference
+// rounds it (gc_acos); otherwise the toolchain's acos, within 2 ulp of it, for sums that are only compared with a tolerance.
+XGB_HD_CALL double spherical_angle_x(const V3& v1, const V3& v2, const V3& v3, bool exact) {
   const V3 p = cross(v1, v2), q = cross(v1, v3);
   double ddd = (p.x * p.x + p.y * p.y + p.z * p.z) * (q.x * q.x + q.y * q.y + q.z * q.z);
   if (ddd <= 0.0) return 0.;
@@ -84,8 +173,9 @@ XGB_HD double spherical_angle(const V3& v1, const V3& v2, const V3& v3) {
   if (fabs(ddd - 1) < kEps30) ddd = 1;
   if (fabs(ddd + 1) < kEps30) ddd = -1;
   if (ddd > 1. || ddd < -1.) return (ddd < 0.) ? kPiD : 0.;
-  return gc_acos(ddd);
+  return exact ? gc_acos(ddd) : acos(ddd);
 }
+XGB_HD double spherical_angle(const V3& v1, const V3& v2, const V3& v3) { return spherical_angle_x(v1, v2, v3, true); }
 
 // great_circle_area (mosaic_util.c:763-790) of n vertices v[0..n)
 template <class Get>
@@ -110,24 +200,48 @@ XGB_HD void ring_append_unique(Ring& l, double x, double y, double z) {         
   l.n[l.len++] = RNode{x, y, z, 0.0, 0, 0, -1};
 }
 
-XGB_HD bool inside_polygon(const RNode& q, const Ring& l) {                      // mosaic_util.c:1487-1530
-  double sum = 0;
+// insidePolygon (mosaic_util.c:1487-1530): |sum of the angles the sides subtend - 2 pi| < 1e-8.  The sum is taken with the
+// toolchain's acos first (a seventh of the instructions of gc_acos); it is within 2e-14 of the reference's, so only a sum
+// within 1e-12 of the threshold is taken again with the reference's own roundings.  Same decision in every case.
+XGB_HD_CALL bool inside_polygon(const RNode& q, const Ring& l) {
   const V3 p0{q.x, q.y, q.z};
-  for (int k = 0; k < l.len; ++k) {
-    const RNode& a = l.n[k];
-    const RNode& b = l.n[(k + 1 < l.len) ? k + 1 : 0];
-    if (same_point(p0.x, p0.y, p0.z, a.x, a.y, a.z)) return true;
-    sum += spherical_angle(p0, V3{b.x, b.y, b.z}, V3{a.x, a.y, a.z});
+  for (int pass = 0; pass < 2; ++pass) {
+    double sum = 0;
+    for (int k = 0; k < l.len; ++k) {
+      const RNode& a = l.n[k];
+      const RNode& b = l.n[(k + 1 < l.len) ? k + 1 : 0];
+      if (same_point(p0.x, p0.y, p0.z, a.x, a.y, a.z)) return true;
+      sum += spherical_angle_x(p0, V3{b.x, b.y, b.z}, V3{a.x, a.y, a.z}, pass == 1);
+    }
+    const double dev = fabs(sum - 2 * kPiD);
+    if (pass == 1 || fabs(dev - kEps8) > 1.e-12) return dev < kEps8;
   }
-  return fabs(sum - 2 * kPiD) < kEps8;
+  return false;
 }
 
 XGB_HD double ring_area(const Ring& l) {                                          // gridArea, mosaic_util.c:1364
   return great_circle_area(l.len, [&](int k) { return V3{l.n[k].x, l.n[k].y, l.n[k].z}; });
 }
 
+// gridArea(l) > 0 (mosaic_util.c:1364; the convexity test of create_xgrid.c:1575): sign of the spherical excess, settled by
+// the fast angles unless the excess is below 1e-12 rad
+XGB_HD bool ring_area_positive(const Ring& l) {
+  for (int pass = 0; pass < 2; ++pass) {
+    double sum = 0.0;
+    const int n = l.len;
+    for (int i = 0; i < n; ++i) {
+      const int i1 = (i + 1 < n) ? i + 1 : i + 1 - n;
+      const int i2 = (i + 2 < n) ? i + 2 : i + 2 - n;
+      sum += spherical_angle_x(V3{l.n[i1].x, l.n[i1].y, l.n[i1].z}, V3{l.n[i2].x, l.n[i2].y, l.n[i2].z}, V3{l.n[i].x, l.n[i].y, l.n[i].z}, pass == 1);
+    }
+    const double excess = sum - (n - 2.) * kPiD;
+    if (pass == 1 || fabs(excess) > 1.e-12) return excess * kR * kR > 0;
+  }
+  return false;
+}
+
 // insertIntersect (mosaic_util.c:1291-1362); false if vertex v is not in the ring (the reference aborts)
-XGB_HD bool ring_insert(Ring& l, const V3& p, double u1, double u2, int inbound, const V3& v) {
+XGB_HD_CALL bool ring_insert(Ring& l, const V3& p, double u1, double u2, int inbound, const V3& v) {
   int a = -1;
   for (int k = 0; k < l.len; ++k) if (l.n[k].x == v.x && l.n[k].y == v.y && l.n[k].z == v.z) { a = k; break; }
   if (a < 0) return false;
@@ -161,7 +275,7 @@ XGB_HD bool ring_insert(Ring& l, const V3& p, double u1, double u2, int inbound,
 
 // parameter t where the line l1 + t (l2 - l1) meets the plane through a, b and the origin
 // (intersect_tri_with_line, mosaic_util.c:967-1008: M = [l1-l2 | b-a | 0-a], x = M^-1 (l1-a), t = x[0]); double-double
-XGB_HD bool plane_line_param(const V3& a, const V3& b, const V3& l1, const V3& l2, double* t) {
+XGB_HD_CALL bool plane_line_param(const V3& a, const V3& b, const V3& l1, const V3& l2, double* t) {
   const double m0 = l1.x - l2.x, m1 = b.x - a.x, m2 = 0.0 - a.x;
   const double m3 = l1.y - l2.y, m4 = b.y - a.y, m5 = 0.0 - a.y;
   const double m6 = l1.z - l2.z, m7 = b.z - a.z, m8 = 0.0 - a.z;
@@ -263,7 +377,7 @@ XGB_HD int clip_great_circle(const V3* c1, int n1, const V3* c2, int n2, V3* out
   const int npts1 = g1.len, npts2 = g2.len;
   for (int k = 0; k < g1.len; ++k) g1.n[k].inside = inside_polygon(g1.n[k], g2) ? 1 : 0;     // :1549-1568
   for (int k = 0; k < g2.len; ++k) g2.n[k].inside = inside_polygon(g2.n[k], g1) ? 1 : 0;
-  if (ring_area(g1) <= 0 || ring_area(g2) <= 0) return kErrNotConvex;                       // :1575-1578
+  if (!ring_area_positive(g1) || !ring_area_positive(g2)) return kErrNotConvex;                       // :1575-1578
 
   V3 pt1[kMaxIn], pt2[kMaxIn];
   for (int k = 0; k < npts1; ++k) pt1[k] = V3{g1.n[k].x, g1.n[k].y, g1.n[k].z};

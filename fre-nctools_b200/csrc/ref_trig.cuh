@@ -41,13 +41,35 @@ static const double kSinCosTabHost[440] = {
 };
 
 namespace trig {
-constexpr double big = 0x1.8000000000000p+45;
-constexpr double hp0 = 0x1.921fb54442d18p+0;     // pi/2 high part
-constexpr double hp1 = 0x1.1a62633145c07p-54;    // pi/2 low part
-constexpr double s1 = -0x1.5555555555555p-3, s2 = 0x1.1111111110ecep-7, s3 = -0x1.a01a019db08b8p-13,
-                 s4 = 0x1.71de27b9a7ed9p-19, s5 = -0x1.addffc2fcdf59p-26;
-constexpr double sn3 = -0x1.5555555555515p-3, sn5 = 0x1.11110e829872fp-7;
-constexpr double cs2 = 0.5, cs4 = -0x1.5555555555535p-5, cs6 = 0x1.6c16bedd9e239p-10;
+// The constants of s_sin.c.  Device code reads them from constant memory (XGB_K): an FP64 instruction takes a constant-bank
+// operand for free, while a 64-bit literal costs two UMOV / IMAD.MOV to materialise each time it is used — a tenth of all
+// instructions of the moments kernel before this (ncu r02t: UMOV 10.4 %, IMAD 13.8 % of the warp instructions).
+#define XGB_TRIG_CONSTS(X)                                                                              \
+  X(big, 0x1.8000000000000p+45)                                                                         \
+  X(hp0, 0x1.921fb54442d18p+0)   /* pi/2 high part */                                                   \
+  X(hp1, 0x1.1a62633145c07p-54)  /* pi/2 low part */                                                    \
+  X(s1, -0x1.5555555555555p-3) X(s2, 0x1.1111111110ecep-7) X(s3, -0x1.a01a019db08b8p-13)                \
+  X(s4, 0x1.71de27b9a7ed9p-19) X(s5, -0x1.addffc2fcdf59p-26)                                            \
+  X(sn3, -0x1.5555555555515p-3) X(sn5, 0x1.11110e829872fp-7)                                            \
+  X(cs4, -0x1.5555555555535p-5) X(cs6, 0x1.6c16bedd9e239p-10)                                           \
+  X(hpinv, 0x1.45F306DC9C883p-1) X(toint, 0x1.8000000000000p52)                                         \
+  X(mp1, 0x1.921FB58000000p0) X(mp2, -0x1.DDE973C000000p-27)                                            \
+  X(pp3, -0x1.CB3B398000000p-55) X(pp4, -0x1.d747f23e32ed7p-83)                                         \
+  X(c126, 0.126) X(c01588, 0.01588)
+#define XGB_X_HOST(name, value) constexpr double name = value;
+XGB_TRIG_CONSTS(XGB_X_HOST)
+#undef XGB_X_HOST
+constexpr double cs2 = 0.5;
+#if defined(__CUDACC__)
+#define XGB_X_DEV(name, value) static __constant__ double dev_##name = value;
+XGB_TRIG_CONSTS(XGB_X_DEV)
+#undef XGB_X_DEV
+#endif
+#if defined(__CUDA_ARCH__) && !defined(XGB_LITERAL_CONSTS)
+#define XGB_K(name) (::xgb::trig::dev_##name)
+#else
+#define XGB_K(name) (::xgb::trig::name)
+#endif
 
 XGB_HD uint64_t bits(double x) {
 #if defined(__CUDA_ARCH__)
@@ -68,10 +90,10 @@ XGB_HD double mag_with_sign_of(double mag, double sgn) { return copysign(fabs(ma
 // TAYLOR_SIN(x*x, x, dx)
 XGB_HD double taylor_sin(double x, double dx) {
   const double xx = x * x;
-  double p = fma(xx, s5, s4);
-  p = fma(xx, p, s3);
-  p = fma(xx, p, s2);
-  p = fma(xx, p, s1);
+  double p = fma(xx, XGB_K(s5), XGB_K(s4));
+  p = fma(xx, p, XGB_K(s3));
+  p = fma(xx, p, XGB_K(s2));
+  p = fma(xx, p, XGB_K(s1));
   const double h = dx * 0.5;
   double w = fma(p, x, -h);
   w = fma(xx, w, dx);
@@ -81,17 +103,17 @@ XGB_HD double taylor_sin(double x, double dx) {
 struct Tab { double sn, ssn, cs, ccs; };
 // u = big + |x| puts round(|x|*128) in the low word; returns |x| - k/128 and loads row k
 XGB_HD double reduce(double ax, Tab* t) {
-  const double u = ax + big;
+  const double u = ax + XGB_K(big);
   const int k4 = (int)((uint32_t)bits(u) << 2);
   t->sn = tab(k4); t->ssn = tab(k4 + 1); t->cs = tab(k4 + 2); t->ccs = tab(k4 + 3);
-  return ax - (u - big);
+  return ax - (u - XGB_K(big));
 }
 
 XGB_HD double sin_core(double xr, double dx, const Tab& t) {       // do_sin after reduction
   const double xx = xr * xr;
-  const double p = fma(xx, sn5, sn3);
+  const double p = fma(xx, XGB_K(sn5), XGB_K(sn3));
   const double s = xr + fma(xr * xx, p, dx);
-  double q = fma(xx, cs6, cs4);
+  double q = fma(xx, XGB_K(cs6), XGB_K(cs4));
   q = fma(q, xx, cs2);
   const double c = fma(xr, dx, xx * q);
   double e = fma(s, t.ccs, t.ssn);
@@ -102,9 +124,9 @@ XGB_HD double sin_core(double xr, double dx, const Tab& t) {       // do_sin aft
 
 XGB_HD double cos_core(double xr, const Tab& t) {                  // do_cos after reduction (dx already added)
   const double xx = xr * xr;
-  const double p = fma(xx, sn5, sn3);
+  const double p = fma(xx, XGB_K(sn5), XGB_K(sn3));
   const double s = fma(xr * xx, p, xr);
-  double q = fma(xx, cs6, cs4);
+  double q = fma(xx, XGB_K(cs6), XGB_K(cs4));
   q = fma(q, xx, cs2);
   const double c = xx * q;
   double e = fma(-s, t.ssn, t.ccs);
@@ -115,7 +137,7 @@ XGB_HD double cos_core(double xr, const Tab& t) {                  // do_cos aft
 
 XGB_HD double do_sin(double x, double dx) {
   const double ax = fabs(x);
-  if (ax < 0.126) return taylor_sin(x, dx);
+  if (ax < XGB_K(c126)) return taylor_sin(x, dx);
   if (x <= 0) dx = -dx;
   Tab t;
   const double xr = reduce(ax, &t);
@@ -129,20 +151,17 @@ XGB_HD double do_cos(double x, double dx) {
   return cos_core(xr, t);
 }
 // reduce_sincos (s_sin.c): x = n*pi/2 + (a + da), |a| <= pi/4.  Only the y step is contracted in the FMA build
-// (checked against this image's libm on 4e8 arguments; contracting the pp4 step as well is indistinguishable).
-constexpr double hpinv = 0x1.45F306DC9C883p-1, toint = 0x1.8000000000000p52;
-constexpr double mp1 = 0x1.921FB58000000p0, mp2 = -0x1.DDE973C000000p-27;
-constexpr double pp3 = -0x1.CB3B398000000p-55, pp4 = -0x1.d747f23e32ed7p-83;
+// (checked against this image's libm on 4e8 arguments; contracting the XGB_K(pp4) step as well is indistinguishable).
 
 XGB_HD int reduce_sincos(double x, double* a, double* da) {
-  const double t = x * hpinv + toint;
-  const double xn = t - toint;
+  const double t = x * XGB_K(hpinv) + XGB_K(toint);
+  const double xn = t - XGB_K(toint);
   const int n = (int)(bits(t) & 3u);
-  const double y = fma(-xn, mp2, fma(-xn, mp1, x));
-  double t1 = xn * pp3;
+  const double y = fma(-xn, XGB_K(mp2), fma(-xn, XGB_K(mp1), x));
+  double t1 = xn * XGB_K(pp3);
   const double t2 = y - t1;
   double db = (y - t2) - t1;
-  t1 = xn * pp4;
+  t1 = xn * XGB_K(pp4);
   const double b = t2 - t1;
   db += (t2 - b) - t1;
   *a = b; *da = db;
@@ -154,7 +173,7 @@ XGB_HD double do_sincos(double a, double da, int n) {
   if (n & 1) r = do_cos(a, da);
   else {
     const double xx = a * a;
-    if (xx < 0.01588) r = taylor_sin(a, da);
+    if (xx < XGB_K(c01588)) r = taylor_sin(a, da);
     else r = mag_with_sign_of(do_sin(a, da), a);
   }
   return (n & 2) ? -r : r;
@@ -165,7 +184,7 @@ XGB_HD double ref_sin(double x) {
   const uint32_t k = (uint32_t)(trig::bits(x) >> 32) & 0x7fffffffu;
   if (k < 0x3e500000u) return x;
   if (k < 0x3feb6000u) return trig::do_sin(x, 0.0);
-  if (k < 0x400368fdu) return trig::mag_with_sign_of(trig::do_cos(trig::hp0 - fabs(x), trig::hp1), x);
+  if (k < 0x400368fdu) return trig::mag_with_sign_of(trig::do_cos(XGB_K(hp0) - fabs(x), XGB_K(hp1)), x);
   if (k < 0x419921FBu) { double a, da; const int n = trig::reduce_sincos(x, &a, &da); return trig::do_sincos(a, da, n); }
   return sin(x);
 }
@@ -175,9 +194,9 @@ XGB_HD double ref_cos(double x) {
   if (k < 0x3e400000u) return 1.0;
   if (k < 0x3feb6000u) return trig::do_cos(x, 0.0);
   if (k < 0x400368fdu) {
-    const double y = trig::hp0 - fabs(x);
-    const double a = y + trig::hp1;
-    const double da = (y - a) + trig::hp1;
+    const double y = XGB_K(hp0) - fabs(x);
+    const double a = y + XGB_K(hp1);
+    const double da = (y - a) + XGB_K(hp1);
     return trig::do_sin(a, da);
   }
   if (k < 0x419921FBu) { double a, da; const int n = trig::reduce_sincos(x, &a, &da); return trig::do_sincos(a, da, n + 1); }
@@ -192,20 +211,20 @@ XGB_HD void ref_sincos(double x, double* sn, double* cs) {
     trig::Tab t;
     const double xr0 = trig::reduce(ax, &t);
     // sin: do_sin(x, 0); cos: do_cos(x, 0) — both share one table row
-    if (ax < 0.126) *sn = trig::taylor_sin(x, 0.0);
+    if (ax < XGB_K(c126)) *sn = trig::taylor_sin(x, 0.0);
     else *sn = trig::mag_with_sign_of(trig::sin_core(xr0, (x > 0) ? 0.0 : -0.0, t), x);
     *cs = trig::cos_core(xr0 + ((x >= 0) ? 0.0 : -0.0), t);
     return;
   }
   if (k < 0x400368fdu) {
-    const double y = trig::hp0 - fabs(x);
-    const double a = y + trig::hp1;
-    const double da = (y - a) + trig::hp1;
+    const double y = XGB_K(hp0) - fabs(x);
+    const double a = y + XGB_K(hp1);
+    const double da = (y - a) + XGB_K(hp1);
     const double aa = fabs(a);
     trig::Tab t;
     const double xr0 = trig::reduce(aa, &t);
     *sn = trig::mag_with_sign_of(trig::cos_core(xr0 + ((a < 0) ? -da : da), t), x);
-    if (aa < 0.126) *cs = trig::taylor_sin(a, da);
+    if (aa < XGB_K(c126)) *cs = trig::taylor_sin(a, da);
     else *cs = trig::mag_with_sign_of(trig::sin_core(xr0, (a <= 0) ? -da : da, t), a);
     return;
   }
@@ -227,12 +246,12 @@ XGB_HD void ref_sincos(double x, double* sn, double* cs) {
 // Both table ranges reduce to "sin-type" and "cos-type" evaluations of one reduced argument (a, da):
 //   |x| < 0.855469        a = x, da = 0:                  sin = sin-type, cos = cos-type           (ref_sin == ref_sincos.sin)
 //   0.855469 <= |x| < 2.426265   y = pi/2 - |x|:          sin = +-cos-type, cos = sin-type, with
-//        ref_sincos: a = y + hp1, da = (y - a) + hp1;     ref_sin: a = y, da = hp1  (do_cos(y, hp1))
+//        ref_sincos: a = y + XGB_K(hp1), da = (y - a) + XGB_K(hp1);     ref_sin: a = y, da = XGB_K(hp1)  (do_cos(y, XGB_K(hp1)))
 // The operation order of every path is that of ref_sin / ref_sincos above; tests pin all three bit for bit against libm.
 // ---------------------------------------------------------------------------------------------
 namespace trig {
 XGB_HD double reduce_t(double ax, Tab* t, const double* T) {
-  const double u = ax + big;
+  const double u = ax + XGB_K(big);
   const int k4 = (int)((uint32_t)bits(u) << 2);
 #if defined(__CUDA_ARCH__)
   const double2 r0 = *reinterpret_cast<const double2*>(T + k4);       // rows are 32 bytes: two 16-byte loads
@@ -241,7 +260,7 @@ XGB_HD double reduce_t(double ax, Tab* t, const double* T) {
 #else
   t->sn = T[k4]; t->ssn = T[k4 + 1]; t->cs = T[k4 + 2]; t->ccs = T[k4 + 3];
 #endif
-  return ax - (u - big);
+  return ax - (u - XGB_K(big));
 }
 }  // namespace trig
 
@@ -264,16 +283,16 @@ XGB_HD void ref_trig_site(double x, bool sin_only, double* sn, double* cs, const
   const bool swap = (k >= 0x3feb6000u);
   double a = x, da = 0.0;
   if (swap) {
-    const double y = trig::hp0 - fabs(x);
-    if (sin_only) { a = y; da = trig::hp1; }
-    else { a = y + trig::hp1; da = (y - a) + trig::hp1; }
+    const double y = XGB_K(hp0) - fabs(x);
+    if (sin_only) { a = y; da = XGB_K(hp1); }
+    else { a = y + XGB_K(hp1); da = (y - a) + XGB_K(hp1); }
   }
   const double aa = fabs(a);
   trig::Tab t;
   const double xr0 = trig::reduce_t(aa, &t, T);
   double S = 0.0, Cc = 0.0;
   if (!(swap && sin_only)) {                    // sin-type of (a, da)
-    if (aa < 0.126) S = trig::taylor_sin(a, da);
+    if (aa < XGB_K(c126)) S = trig::taylor_sin(a, da);
     else S = trig::mag_with_sign_of(trig::sin_core(xr0, (a <= 0) ? -da : da, t), a);
   }
   if (swap || !sin_only)                        // cos-type of (a, da)
@@ -286,7 +305,7 @@ XGB_HD void ref_trig_site(double x, bool sin_only, double* sn, double* cs, const
 XGB_HD double ref_sin_small(double x) {
   const uint32_t k = (uint32_t)(trig::bits(x) >> 32) & 0x7fffffffu;
   if (k < 0x3e500000u) return x;
-  if (fabs(x) < 0.126) return trig::taylor_sin(x, 0.0);
+  if (fabs(x) < XGB_K(c126)) return trig::taylor_sin(x, 0.0);
 #if defined(__CUDA_ARCH__)
   return ref_sin_call(x);
 #else

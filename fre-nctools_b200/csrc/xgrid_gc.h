@@ -22,7 +22,7 @@ struct Pyramid3 { int nlev; Pyr3Level lev[kMaxLevels]; };
 
 void launch_gc_cell_precompute(const TileDesc& tile, const double* lon, const double* lat, GcCells cells, int* err, cudaStream_t st);
 void launch_gc_pyramid_level(const Pyr3Level& child, Box3* out, int nx, int ny, cudaStream_t st);
-void launch_gc_candidates(bool fill, const GcCells& src, long long s0, long long ns, const double* mask, const Pyramid3& pyr,
+void launch_gc_candidates(bool fill, const GcCells& src, const GcCells& dst, long long s0, long long ns, const double* mask, const Pyramid3& pyr,
                           const uint32_t* pair_off, uint32_t* cnt, int2* pairs, int* err, cudaStream_t st);
 void launch_gc_clip(const GcCells& src, const GcCells& dst, const double* mask, const int2* pairs, unsigned long long npairs,
                     long long s0, double* parea, uint32_t* cnt, int* err, cudaStream_t st);

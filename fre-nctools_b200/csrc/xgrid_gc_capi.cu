@@ -84,7 +84,7 @@ long long xgb_generate_great_circle(xgb_plan* p, int order)
       p->scan_tmp.reserve(scan_tmp_bytes(ns)))
     return -1;
   cudaEventRecord(p->ev[0], p->st);
-  launch_gc_candidates(false, p->gc_src, s0, ns, mask, p->gc_pyr, nullptr, (uint32_t*)p->pair_cnt.p, nullptr, p->err_dev, p->st);
+  launch_gc_candidates(false, p->gc_src, p->gc_dst, s0, ns, mask, p->gc_pyr, nullptr, (uint32_t*)p->pair_cnt.p, nullptr, p->err_dev, p->st);
   launch_exclusive_scan((const uint32_t*)p->pair_cnt.p, (uint32_t*)p->pair_off.p, ns, p->total_dev, p->scan_tmp.p, p->st);
   launch_publish(p->total_host, p->total_dev, 2, p->st);
   if (cudaStreamSynchronize(p->st) != cudaSuccess) {
@@ -96,7 +96,7 @@ long long xgb_generate_great_circle(xgb_plan* p, int order)
   p->npairs = npairs;
   cudaEventRecord(p->ev[1], p->st);
   if (p->pairs.reserve((size_t)npairs * sizeof(int2) + 16) || p->parea.reserve((size_t)npairs * 8 + 16)) return -1;
-  launch_gc_candidates(true, p->gc_src, s0, ns, mask, p->gc_pyr, (const uint32_t*)p->pair_off.p, (uint32_t*)p->pair_cnt.p,
+  launch_gc_candidates(true, p->gc_src, p->gc_dst, s0, ns, mask, p->gc_pyr, (const uint32_t*)p->pair_off.p, (uint32_t*)p->pair_cnt.p,
                        (int2*)p->pairs.p, p->err_dev, p->st);
   cudaMemsetAsync(p->cnt.p, 0, (size_t)(ns + 1) * 4, p->st);
   cudaEventRecord(p->ev[2], p->st);

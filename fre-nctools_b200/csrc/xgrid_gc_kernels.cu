@@ -121,9 +121,26 @@ __device__ __forceinline__ bool boxes_meet(const Box3& a, const Box3& b)
 
 constexpr int kGcStack = 3 * kMaxLevels + 8;
 
+__device__ __forceinline__ void load_cell(const GcCells& c, long long g, gc::V3* v)
+{
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    v[k] = gc::V3{c.v[(long long)(3 * k + 0) * c.ncell + g], c.v[(long long)(3 * k + 1) * c.ncell + g], c.v[(long long)(3 * k + 2) * c.ncell + g]};
+}
+
+// Leaf test of the candidate search: boxes that meet, and no side of either cell with the whole other cell beyond it
+// (gc::separated_by_side: such a pair cannot produce an exchange cell).  Almost half of the box candidates of configs[2] are
+// neighbours that merely touch the box; dropping them here instead of inside the clip kernel keeps that kernel's lanes busy.
+__device__ __forceinline__ bool gc_leaf(const GcCells& dst, long long q, const gc::V3* a)
+{
+  gc::V3 b[4];
+  load_cell(dst, q, b);
+  return !(gc::separated_by_side(a, b) || gc::separated_by_side(b, a));
+}
+
 template <bool FILL>
 __global__ void __launch_bounds__(128)
-gc_candidate_kernel(GcCells src, long long s0, long long ns, const double* __restrict__ mask, Pyramid3 pyr,
+gc_candidate_kernel(GcCells src, GcCells dst, long long s0, long long ns, const double* __restrict__ mask, Pyramid3 pyr,
                     const uint32_t* __restrict__ pair_off, uint32_t* __restrict__ cnt, int2* __restrict__ pairs, int* err)
 {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -133,6 +150,8 @@ gc_candidate_kernel(GcCells src, long long s0, long long ns, const double* __res
   const uint32_t base = FILL ? pair_off[t] : 0u;
   if (mask == nullptr || mask[s] > kMaskThresh) {                          // create_xgrid.c:1419
     const Box3 sb = load_box3(src.box + s);
+    gc::V3 a[4];
+    load_cell(src, s, a);
     unsigned long long stack[kGcStack];
     int sp = 0;
     const int top = pyr.nlev - 1;
@@ -142,7 +161,7 @@ gc_candidate_kernel(GcCells src, long long s0, long long ns, const double* __res
         for (int ix = 0; ix < L.nx; ++ix) {
           const long long q = (long long)iy * L.nx + ix;
           if (!boxes_meet(load_box3(L.box + q), sb)) continue;
-          if (top == 0) { if (FILL) pairs[base + n] = make_int2((int)t, (int)q); ++n; }
+          if (top == 0) { if (gc_leaf(dst, q, a)) { if (FILL) pairs[base + n] = make_int2((int)t, (int)q); ++n; } }
           else stack[sp++] = ((unsigned long long)top << 58) | ((unsigned long long)iy << 29) | (unsigned long long)ix;
         }
     }
@@ -159,7 +178,7 @@ gc_candidate_kernel(GcCells src, long long s0, long long ns, const double* __res
           if (cx >= L.nx) continue;
           const long long q = (long long)cy * L.nx + cx;
           if (!boxes_meet(load_box3(L.box + q), sb)) continue;
-          if (lev == 0) { if (FILL) pairs[base + n] = make_int2((int)t, (int)q); ++n; }
+          if (lev == 0) { if (gc_leaf(dst, q, a)) { if (FILL) pairs[base + n] = make_int2((int)t, (int)q); ++n; } }
           else if (sp < kGcStack) stack[sp++] = ((unsigned long long)lev << 58) | ((unsigned long long)cy << 29) | (unsigned long long)cx;
           else atomicOr(err, kErrStackOverflow);
         }
@@ -169,21 +188,14 @@ gc_candidate_kernel(GcCells src, long long s0, long long ns, const double* __res
   if (!FILL) cnt[t] = n;
 }
 
-void launch_gc_candidates(bool fill, const GcCells& src, long long s0, long long ns, const double* mask, const Pyramid3& pyr,
+void launch_gc_candidates(bool fill, const GcCells& src, const GcCells& dst, long long s0, long long ns, const double* mask, const Pyramid3& pyr,
                           const uint32_t* pair_off, uint32_t* cnt, int2* pairs, int* err, cudaStream_t st)
 {
   if (ns <= 0) return;
   const unsigned blocks = (unsigned)((ns + 127) / 128);
   ++g_launches;
-  if (fill) gc_candidate_kernel<true><<<blocks, 128, 0, st>>>(src, s0, ns, mask, pyr, pair_off, cnt, pairs, err);
-  else      gc_candidate_kernel<false><<<blocks, 128, 0, st>>>(src, s0, ns, mask, pyr, pair_off, cnt, pairs, err);
-}
-
-__device__ __forceinline__ void load_cell(const GcCells& c, long long g, gc::V3* v)
-{
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    v[k] = gc::V3{c.v[(long long)(3 * k + 0) * c.ncell + g], c.v[(long long)(3 * k + 1) * c.ncell + g], c.v[(long long)(3 * k + 2) * c.ncell + g]};
+  if (fill) gc_candidate_kernel<true><<<blocks, 128, 0, st>>>(src, dst, s0, ns, mask, pyr, pair_off, cnt, pairs, err);
+  else      gc_candidate_kernel<false><<<blocks, 128, 0, st>>>(src, dst, s0, ns, mask, pyr, pair_off, cnt, pairs, err);
 }
 
 __global__ void __launch_bounds__(64)
@@ -197,9 +209,7 @@ gc_clip_kernel(GcCells src, GcCells dst, const double* __restrict__ mask, const 
   gc::V3 a[4], b[4], out[gc::kPoly];
   load_cell(src, s, a);
   load_cell(dst, d, b);
-  // most rejected candidates are neighbours that merely touch the box: prove them disjoint with 32 dot products before
-  // paying for the eight inside-polygon angle sums of the full clip
-  const int n_out = (gc::separated_by_side(a, b) || gc::separated_by_side(b, a)) ? 0 : gc::clip_great_circle(a, 4, b, 4, out);
+  const int n_out = gc::clip_great_circle(a, 4, b, 4, out);      // (pairs separated by a side never get here: gc_leaf)
   double keep = 0.0;
   if (n_out < 0) {
     atomicOr(err, n_out == gc::kErrNotConvex ? kErrGcNotConvex : (n_out == gc::kErrPool ? kErrGcNodePool : kErrGcWalk));
@@ -238,4 +248,30 @@ extern "C" int xgb_gc_clip_host(const double* x1, const double* y1, const double
   for (int k = 0; k < n; ++k) { xo[k] = out[k].x; yo[k] = out[k].y; zo[k] = out[k].z; }
   if (area) *area = (n > 0) ? gc::great_circle_area(n, [&](int k) { return out[k]; }) : 0.0;
   return n;
+}
+
+// gc::gc_acos (acosl rounded to double, gc_clip.cuh) on n arguments: host build and device build, for the tests
+namespace xgb {
+__global__ void gc_acos_kernel(long long n, const double* __restrict__ x, double* __restrict__ out)
+{
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = gc::gc_acos(x[i]);
+}
+}  // namespace xgb
+
+extern "C" void xgb_gc_acos_host(long long n, const double* x, double* out)
+{
+  for (long long i = 0; i < n; ++i) out[i] = xgb::gc::gc_acos(x[i]);
+}
+
+extern "C" int xgb_gc_acos_device(long long n, const double* x_host, double* out_host)
+{
+  double *x = nullptr, *o = nullptr;
+  if (n <= 0) return 0;
+  if (cudaMalloc(&x, n * 8) != cudaSuccess || cudaMalloc(&o, n * 8) != cudaSuccess) { cudaFree(x); return 1; }
+  cudaMemcpy(x, x_host, n * 8, cudaMemcpyHostToDevice);
+  xgb::gc_acos_kernel<<<(unsigned)((n + 255) / 256), 256>>>(n, x, o);
+  const cudaError_t e = cudaMemcpy(out_host, o, n * 8, cudaMemcpyDeviceToHost);
+  cudaFree(x); cudaFree(o);
+  return e == cudaSuccess ? 0 : 1;
 }

@@ -20,6 +20,15 @@ constexpr double kSmall  = 1.e-10;             // mosaic_util.h:34 SMALL_VALUE
 constexpr double kPoleTol = 1.e-6;             // mosaic_util.c:35 TOLORENCE
 constexpr double kAreaRatioThresh = 1.e-6;     // create_xgrid.c:27
 constexpr double kMaskThresh = 0.5;            // create_xgrid.c:28
+// The same numbers in constant memory for the hot device code (xgrid_kernels.cu maps the names onto these after its includes):
+// an FP64 instruction takes a constant-bank operand for free, a 64-bit literal is two instructions to materialise (ref_trig.cuh).
+#if defined(__CUDACC__)
+static __constant__ double dev_kPi = 3.14159265358979323846, dev_kTwoPi = 2.0 * 3.14159265358979323846,
+                           dev_kHalfPi = 0.5 * 3.14159265358979323846, dev_kSmall = 1.e-10, dev_kAreaRatioThresh = 1.e-6,
+                           dev_kInsideTol = 1.e-12, dev_kEps30 = 1.0e-30;
+#endif
+constexpr double kInsideTol = 1.e-12;          // inside_edge, create_xgrid.c:2349
+constexpr double kEps30 = 1.0e-30;             // EPSLN30, create_xgrid.c:1314
 constexpr int    kMaxV = 8;                    // create_xgrid.c:627 MAX_V (vertices of a fix_lon'd cell)
 constexpr int    kMaxClip = 16;                // capacity of a clipped polygon (<= n1 + n2 for convex cells)
 

@@ -15,6 +15,17 @@
 #include "xgrid_internal.h"
 #include "xgrid_plan.h"
 
+// geometric constants of the hot kernels from constant memory (xgrid_geom.cuh); the literal versions stay for the host pass
+#if defined(__CUDA_ARCH__) && !defined(XGB_LITERAL_CONSTS)
+#define kPi (::xgb::dev_kPi)
+#define kTwoPi (::xgb::dev_kTwoPi)
+#define kHalfPi (::xgb::dev_kHalfPi)
+#define kSmall (::xgb::dev_kSmall)
+#define kAreaRatioThresh (::xgb::dev_kAreaRatioThresh)
+#define kInsideTol (::xgb::dev_kInsideTol)
+#define kEps30 (::xgb::dev_kEps30)
+#endif
+
 namespace xgb {
 
 long long g_launches = 0;
@@ -752,17 +763,17 @@ __device__ __forceinline__ int clip_cell(double* ax, double* ay, double* bx, dou
     const double ey1 = dst.vy[(long long)e * dst.ncell + d];
     const double edy = ey1 - ey0, endx = ex0 - ex1;            // (y1-y0), (x0-x1) of inside_edge
     double px = cx[(np - 1) * stride], py = cy[(np - 1) * stride];
-    bool was_in = ((px - ex0) * edy + endx * (py - ey0)) <= 1.e-12;
+    bool was_in = ((px - ex0) * edy + endx * (py - ey0)) <= kInsideTol;
     int no = 0;
     for (int k = 0; k < np; ++k) {
       const double qx = cx[k * stride], qy = cy[k * stride];
-      const bool is_in = ((qx - ex0) * edy + endx * (qy - ey0)) <= 1.e-12;
+      const bool is_in = ((qx - ex0) * edy + endx * (qy - ey0)) <= kInsideTol;
       if (is_in != was_in) {
         if (no >= CAP) return -1;
         const double dy1 = qy - py, dy2 = ey1 - ey0, dx1 = qx - px, dx2 = ex1 - ex0;
         const double ds1 = py * qx - qy * px, ds2 = ey0 * ex1 - ey1 * ex0;
         const double determ = dy2 * dx1 - dy1 * dx2;
-        if (fabs(determ) < 1.0e-30) atomicOr(err, kErrParallelEdges);
+        if (fabs(determ) < kEps30) atomicOr(err, kErrParallelEdges);
         ox[no * stride] = (dx2 * ds1 - dx1 * ds2) / determ;
         oy[no * stride] = (dy2 * ds1 - dy1 * ds2) / determ;
         ++no;
@@ -828,7 +839,7 @@ __device__ __forceinline__ int clip_cell_fast(double* sbase, const double (&ex)[
       unsigned in = 0;
       for (int k = 0; k < np; ++k) {
         const double qx = cx[k * S], qy = cy[k * S];
-        in |= (unsigned)(((qx - ex0) * edy + endx * (qy - ey0)) <= 1.e-12) << k;
+        in |= (unsigned)(((qx - ex0) * edy + endx * (qy - ey0)) <= kInsideTol) << k;
       }
       const unsigned full = (1u << np) - 1u;
       if (in == 0u) np = 0;
@@ -849,7 +860,7 @@ __device__ __forceinline__ int clip_cell_fast(double* sbase, const double (&ex)[
             const double dy1 = qy - py, dy2 = ey1 - ey0, dx1 = qx - px, dx2 = ex1 - ex0;
             const double ds1 = py * qx - qy * px, ds2 = ey0 * ex1 - ey1 * ex0;
             const double determ = dy2 * dx1 - dy1 * dx2;
-            if (fabs(determ) < 1.0e-30) atomicOr(err, kErrParallelEdges);
+            if (fabs(determ) < kEps30) atomicOr(err, kErrParallelEdges);
             const int pc = __popc(in & ((1u << k) - 1u)) + c;     // after the kept vertices before k (+ crossing 0)
             ox[pc * S] = (dx2 * ds1 - dx1 * ds2) / determ;
             oy[pc * S] = (dy2 * ds1 - dy1 * ds2) / determ;
@@ -1114,7 +1125,7 @@ constexpr int kIdxSlots = 12;      // 4 source vertices + 2 crossings per destin
 // inside_edge (create_xgrid.c:2342-2350) of point (x, y) against the edge (x0, y0) -> (x1, y1)
 __device__ __forceinline__ unsigned in_bit(double x0, double y0, double x1, double y1, double x, double y)
 {
-  return (unsigned)(((x - x0) * (y1 - y0) + (x0 - x1) * (y - y0)) <= 1.e-12);
+  return (unsigned)(((x - x0) * (y1 - y0) + (x0 - x1) * (y - y0)) <= kInsideTol);
 }
 
 // Sutherland-Hodgman (clip_2dx2d, create_xgrid.c:1292-1340) on an INDEXED polygon.  ncu on clip_cell_fast: the loop that
@@ -1179,7 +1190,7 @@ __device__ __forceinline__ int clip_cell_idx(double* sx, const double (&vx)[4], 
             const double dy1 = qy - py, dy2 = ey1 - ey0, dx1 = qx - px, dx2 = ex1 - ex0;
             const double ds1 = py * qx - qy * px, ds2 = ey0 * ex1 - ey1 * ex0;
             const double determ = dy2 * dx1 - dy1 * dx2;
-            if (fabs(determ) < 1.0e-30) atomicOr(err, kErrParallelEdges);
+            if (fabs(determ) < kEps30) atomicOr(err, kErrParallelEdges);
             cxv[c] = (dx2 * ds1 - dx1 * ds2) / determ;
             cyv[c] = (dy2 * ds1 - dy1 * ds2) / determ;
             sx[(ns + c) * S] = cxv[c]; sy[(ns + c) * S] = cyv[c];
@@ -1246,7 +1257,7 @@ __device__ __forceinline__ int clip_cell_idx(double* sx, const double (&vx)[4], 
             const double dy1 = qy - py, dy2 = ey1 - ey0, dx1 = qx - px, dx2 = ex1 - ex0;
             const double ds1 = py * qx - qy * px, ds2 = ey0 * ex1 - ey1 * ex0;
             const double determ = dy2 * dx1 - dy1 * dx2;
-            if (fabs(determ) < 1.0e-30) atomicOr(err, kErrParallelEdges);
+            if (fabs(determ) < kEps30) atomicOr(err, kErrParallelEdges);
             cxv[c] = (dx2 * ds1 - dx1 * ds2) / determ;
             cyv[c] = (dy2 * ds1 - dy1 * ds2) / determ;
             sx[(ns + c) * S] = cxv[c]; sy[(ns + c) * S] = cyv[c];
@@ -1289,8 +1300,8 @@ __device__ __forceinline__ void edge_terms(double xi, double yi, double xn, doub
   const double lat1 = yn, lat2 = yi;
   const double dx_raw = xn - xi;                       // x[ip]-x[i] == phi1-phi2
   double dxa = dx_raw;                                 // poly_area's wrapped dx (mosaic_util.c:429-432)
-  if (dxa > kPi)  dxa = dxa - 2.0 * kPi;
-  if (dxa < -kPi) dxa = dxa + 2.0 * kPi;
+  if (dxa > kPi)  dxa = dxa - kTwoPi;
+  if (dxa < -kPi) dxa = dxa + kTwoPi;
   const bool pole_edge = (fabs(dxa + kPi) < kSmall || fabs(dxa - kPi) < kSmall);
   const bool flat_area = (fabs(lat1 - lat2) < kSmall);
   const double avg = 0.5 * (lat1 + lat2);
@@ -1313,22 +1324,22 @@ __device__ __forceinline__ void edge_terms(double xi, double yi, double xn, doub
     if (moving) {
       // poly_ctrlat (create_xgrid.c:2100-2118)
       double dxl = dx_raw;
-      if (dxl > kPi)   dxl = dxl - 2.0 * kPi;
-      if (dxl <= -kPi) dxl = dxl + 2.0 * kPi;
+      if (dxl > kPi)   dxl = dxl - kTwoPi;
+      if (dxl <= -kPi) dxl = dxl + kTwoPi;
       if (flat_lat) tt = dxl * (2 * c_avg + lat2 * s_avg - cn);
       else          tt = dxl * (dat * (2 * c_avg + lat2 * s_avg) - cn);
       // poly_ctrlon (create_xgrid.c:2176-2215)
       const double f1 = 0.5 * (cn * sn + lat1);
       const double f2 = 0.5 * (ci * si + lat2);
       double dphi = dx_raw;
-      if (dphi > kPi)  dphi = dphi - 2.0 * kPi;
-      if (dphi < -kPi) dphi = dphi + 2.0 * kPi;
+      if (dphi > kPi)  dphi = dphi - kTwoPi;
+      if (dphi < -kPi) dphi = dphi + kTwoPi;
       double dphi1 = xn - clon;
-      if (dphi1 > kPi)  dphi1 -= 2.0 * kPi;
-      if (dphi1 < -kPi) dphi1 += 2.0 * kPi;
+      if (dphi1 > kPi)  dphi1 -= kTwoPi;
+      if (dphi1 < -kPi) dphi1 += kTwoPi;
       double dphi2 = xi - clon;
-      if (dphi2 > kPi)  dphi2 -= 2.0 * kPi;
-      if (dphi2 < -kPi) dphi2 += 2.0 * kPi;
+      if (dphi2 > kPi)  dphi2 -= kTwoPi;
+      if (dphi2 < -kPi) dphi2 += kTwoPi;
       if (fabs(dphi2 - dphi1) < kPi) {
         tl = dphi * (dphi1 * f1 + dphi2 * f2) / 2.0;
       } else {

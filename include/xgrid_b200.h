@@ -393,6 +393,11 @@ long long xgb_remap_size(const char *path);                /* read_mosaic_xgrid_
 int xgb_remap_read(const char *path, int order, long long cap, int *t_in, int *i_in, int *j_in, int *i_out, int *j_out,
                    double *area, double *di, double *dj);
 
+/* gc_acos: acosl(x) rounded to double as spherical_angle produces it (mosaic_util.c:834), host build / device build of
+ * csrc/gc_clip.cuh on n arguments (self-checks; the device version copies through temporary buffers) */
+void xgb_gc_acos_host(long long n, const double *x, double *out);
+int  xgb_gc_acos_device(long long n, const double *x_host, double *out_host);
+
 /* ============================================================================================
  * Part 5 — make_coupler_mosaic's exchange grids (tools/make_coupler_mosaic/make_coupler_mosaic.c)
  * ============================================================================================

@@ -7,6 +7,7 @@ import ctypes as C
 import os
 
 import numpy as np
+import pytest
 
 import xgtest
 
@@ -90,3 +91,25 @@ def test_oracle_gc_equals_compiled_reference(reflib, pkg):
         for k in ref:
             if k != "nxgrid":
                 assert np.array_equal(got[k], ref[k]), k
+
+
+def test_gc_acos_host_against_acosl(pkg):
+    """gc_acos (csrc/gc_clip.cuh) = acosl(x) rounded to double as spherical_angle leaves it (mosaic_util.c:834).  numpy's
+    longdouble arccos IS libm's acosl; the restatement must give its bits except where the x87 fpatan is not the correctly
+    rounded 64-bit result AND that result sits on a double rounding boundary (measured here: 3.5 per 100 000 arguments; plain
+    double acos differs on 5 %)."""
+    import ctypes as C
+    L = pkg.lib()
+    L.xgb_gc_acos_host.argtypes = [C.c_longlong, C.c_void_p, C.c_void_p]; L.xgb_gc_acos_host.restype = None
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-1, 1, 1_000_000), 1 - 10.0 ** rng.uniform(-16, 0, 300_000), -1 + 10.0 ** rng.uniform(-16, 0, 300_000),
+                        rng.uniform(-0.05, 0.05, 400_000), [1.0, -1.0, 0.0, 0.5, -0.5]])
+    out = np.empty_like(x)
+    L.xgb_gc_acos_host(x.size, x.ctypes.data, out.ctypes.data)
+    ref = np.arccos(x.astype(np.longdouble)).astype(np.float64)
+    if np.finfo(np.longdouble).nmant != 63:
+        pytest.skip("no 80-bit long double on this machine")
+    bad = out != ref
+    assert bad.mean() < 2e-4, bad.mean()
+    assert np.max(np.abs(out - ref)) <= 4.5e-16
+    assert (np.arccos(x) != ref).mean() > 0.01          # what the toolchain's acos would give
