@@ -24,6 +24,12 @@ void launch_gc_cell_precompute(const TileDesc& tile, const double* lon, const do
 void launch_gc_pyramid_level(const Pyr3Level& child, Box3* out, int nx, int ny, cudaStream_t st);
 void launch_gc_candidates(bool fill, const GcCells& src, const GcCells& dst, long long s0, long long ns, const double* mask, const Pyramid3& pyr,
                           const uint32_t* pair_off, uint32_t* cnt, int2* pairs, int* err, cudaStream_t st);
+// box candidates -> pairs no side separates: flag[p] per pair; then (after an exclusive scan of the flags into pos) the kept
+// pairs in order and the per-source-cell offsets / counts rewritten for them
+void launch_gc_filter(const GcCells& src, const GcCells& dst, const int2* pairs, unsigned long long npairs, long long s0, uint32_t* flag,
+                      cudaStream_t st);
+void launch_gc_compact(const int2* pairs, unsigned long long npairs, const uint32_t* flag, const uint32_t* pos, int2* kept, long long ns,
+                       uint32_t* pair_off, uint32_t* pair_cnt, cudaStream_t st);
 void launch_gc_clip(const GcCells& src, const GcCells& dst, const double* mask, const int2* pairs, unsigned long long npairs,
                     long long s0, double* parea, uint32_t* cnt, int* err, cudaStream_t st);
 

@@ -98,9 +98,27 @@ long long xgb_generate_great_circle(xgb_plan* p, int order)
   if (p->pairs.reserve((size_t)npairs * sizeof(int2) + 16) || p->parea.reserve((size_t)npairs * 8 + 16)) return -1;
   launch_gc_candidates(true, p->gc_src, p->gc_dst, s0, ns, mask, p->gc_pyr, (const uint32_t*)p->pair_off.p, (uint32_t*)p->pair_cnt.p,
                        (int2*)p->pairs.p, p->err_dev, p->st);
+  // second stage: drop the pairs a side separates (pclon / pclat are free on this path: flags, their scan; clip_vx: kept pairs)
+  const unsigned long long nbox = npairs;
+  unsigned long long nkept = nbox;
+  if (p->pclon.reserve((size_t)(nbox + 1) * 4 + 16) || p->pclat.reserve((size_t)(nbox + 1) * 4 + 16) ||
+      p->clip_vx.reserve((size_t)nbox * sizeof(int2) + 16) || p->scan_tmp.reserve(scan_tmp_bytes((long long)nbox > ns ? (long long)nbox : ns)))
+    return -1;
+  launch_gc_filter(p->gc_src, p->gc_dst, (const int2*)p->pairs.p, nbox, s0, (uint32_t*)p->pclon.p, p->st);
+  launch_exclusive_scan((const uint32_t*)p->pclon.p, (uint32_t*)p->pclat.p, (long long)nbox, p->total_dev, p->scan_tmp.p, p->st);
+  launch_gc_compact((const int2*)p->pairs.p, nbox, (const uint32_t*)p->pclon.p, (const uint32_t*)p->pclat.p, (int2*)p->clip_vx.p, ns,
+                    (uint32_t*)p->pair_off.p, (uint32_t*)p->pair_cnt.p, p->st);
+  launch_publish(p->total_host, p->total_dev, 2, p->st);
+  if (cudaStreamSynchronize(p->st) != cudaSuccess) {
+    xgb_set_error("great-circle candidate filter failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return -1;
+  }
+  nkept = p->total_host[0];
+  p->npairs = nkept;
+  const int2* kept = (const int2*)p->clip_vx.p;
   cudaMemsetAsync(p->cnt.p, 0, (size_t)(ns + 1) * 4, p->st);
   cudaEventRecord(p->ev[2], p->st);
-  launch_gc_clip(p->gc_src, p->gc_dst, mask, (const int2*)p->pairs.p, npairs, s0, (double*)p->parea.p, (uint32_t*)p->cnt.p,
+  launch_gc_clip(p->gc_src, p->gc_dst, mask, kept, nkept, s0, (double*)p->parea.p, (uint32_t*)p->cnt.p,
                  p->err_dev, p->st);
   cudaEventRecord(p->ev[3], p->st);
   launch_exclusive_scan((const uint32_t*)p->cnt.p, (uint32_t*)p->out_off.p, ns, p->total_dev + 1, p->scan_tmp.p, p->st);
@@ -117,7 +135,7 @@ long long xgb_generate_great_circle(xgb_plan* p, int order)
   if (p->t_in.reserve(ni) || p->i_in.reserve(ni) || p->j_in.reserve(ni) || p->i_out.reserve(ni) || p->j_out.reserve(ni) || p->area.reserve(nd))
     return -1;
   cudaEventRecord(p->ev[4], p->st);
-  launch_scatter(1, (const int2*)p->pairs.p, npairs, (const double*)p->parea.p, nullptr, nullptr, (const uint32_t*)p->pair_off.p,
+  launch_scatter(1, kept, nkept, (const double*)p->parea.p, nullptr, nullptr, (const uint32_t*)p->pair_off.p,
                  (const uint32_t*)p->pair_cnt.p, (const uint32_t*)p->out_off.p, (const TileDesc*)p->tiles_dev.p, (int)p->tiles.size(), sm, p->nx2,
                  (int*)p->t_in.p, (int*)p->i_in.p, (int*)p->j_in.p, (int*)p->i_out.p, (int*)p->j_out.p, (double*)p->area.p,
                  nullptr, nullptr, nullptr, p->st, nullptr, nullptr, nullptr);
