@@ -12,8 +12,8 @@ $CMD > $out/bench_${tag}.json 2> $out/bench_${tag}.err || { tail -5 $out/bench_$
 python bench.py --impl reference --steps 2 --warmup 1 > $out/bench_ref_${tag}.json 2> $out/bench_ref_${tag}.err
 SHORT="python bench.py --steps 2 --warmup 1 --no-cpu-baseline"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $out/launches_${tag}.csv $SHORT > $out/ncu_launches_${tag}.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"clip_kernel|candidate_single|scatter_kernel|scatter_long|order2_finalize" -s 5 -c 10 -o $out/${tag}_kernels $SHORT > $out/ncu_full_${tag}.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"clip_sh_kernel|clip_mom_kernel|candidate_single|scatter_kernel|scatter_long|order2_finalize" -s 6 -c 12 -o $out/${tag}_kernels $SHORT > $out/ncu_full_${tag}.log 2>&1
 tail -2 $out/ncu_full_${tag}.log
-ncu --set full --clock-control none -k regex:"apply_packed|grad_c2l" -s 2 -c 4 -o $out/${tag}_apply $SHORT > $out/ncu_apply_${tag}.log 2>&1
+ncu --set full --clock-control none -k regex:"apply_rec_kernel|grad_c2l_rec_kernel|gc_clip_kernel|gc_filter_kernel|gc_candidate_kernel" -s 2 -c 7 -o $out/${tag}_apply $SHORT > $out/ncu_apply_${tag}.log 2>&1
 tail -1 $out/ncu_apply_${tag}.log
 tail -c 400 $out/bench_${tag}.json
