@@ -160,6 +160,8 @@ static int rd_atts(Cur *c, int *natts, Att **atts)
     a->n = (long long)rd_nonneg(c);
     if (c->short_read) { *natts = (int)i; return 0; }
     if (!tsize(a->type)) return -2;
+    /* a CDF-5 count is 64 bits: refuse what cannot be an attribute before the multiplication can wrap */
+    if (a->n < 0 || a->n > (1LL << 31) / 8) return -5;
     bytes = (size_t)a->n * tsize(a->type);
     padded = (bytes + 3) & ~(size_t)3;
     if (c->at + padded > c->n) { c->short_read = 1; *natts = (int)i; return 0; }
@@ -248,7 +250,11 @@ static long long var_fixed_elems(const nc3_file *f, const Var *v)   /* elements 
 {
   long long n = 1;
   int k;
-  for (k = v->isrec ? 1 : 0; k < v->ndims; ++k) n *= f->dims[v->dimids[k]].len;
+  for (k = v->isrec ? 1 : 0; k < v->ndims; ++k) {
+    const long long len = f->dims[v->dimids[k]].len;
+    if (len < 0 || (len > 0 && n > (long long)(0x7fffffffffffffffLL / 16) / len)) return -1;   /* product would overflow */
+    n *= len;
+  }
   return n;
 }
 
@@ -301,7 +307,10 @@ nc3_file *nc3_open(const char *path, char *err, size_t errlen)
     }
   }
   if (rc < 0) { if (err) snprintf(err, errlen, "nc3_open: %s: malformed header (%d)", path, rc); goto bad; }
-  free(buf);
+  free(buf); buf = NULL;
+  { int i; for (i = 0; i < f->nvars; ++i) if (var_fixed_elems(f, &f->vars[i]) < 0) {
+      if (err) snprintf(err, errlen, "nc3_open: %s: variable %s: the product of its dimensions overflows", path, f->vars[i].name);
+      goto bad; } }
   compute_recsize(f);
   if (f->numrecs < 0) {                                    /* streaming numrecs: infer from the file size */
     long long first = -1; int i;

@@ -161,26 +161,34 @@ int xgb_remap_read(const char *path, int order, long long cap, int *t_in, int *i
   if (n > cap) { xgb_set_error("xgb_remap_read: %s holds %lld cells, the buffers %lld", path, n, cap); goto done; }
   ibuf = (int *)malloc((size_t)(n > 0 ? n : 1) * 2 * sizeof(int));
   if (!ibuf) { xgb_set_error("xgb_remap_read: out of memory"); goto done; }
-#define NEED_VAR(name) do { v = nc3_var_id(f, name); if (v < 0) { xgb_set_error("%s has no variable %s", path, name); goto done; } } while (0)
-  NEED_VAR("tile1_cell");
+  /* every variable is checked for the shape the buffers were sized for — (ncells) or (ncells, two = 2) — before it is read:
+     a file with another layout is refused instead of overrunning them */
+#define NEED_VAR(name, pairs) do { \
+    v = nc3_var_id(f, name); \
+    if (v < 0) { xgb_set_error("%s has no variable %s", path, name); goto done; } \
+    { const int nd_ = nc3_var_ndims(f, v); const int *di_ = nc3_var_dimids(f, v); \
+      if (nd_ != ((pairs) ? 2 : 1) || di_[0] != d || ((pairs) && nc3_dim_len(f, di_[1]) != 2) || nc3_var_type(f, v) == NC3_CHAR) { \
+        xgb_set_error("%s: variable %s is not a numeric (%s) array", path, name, (pairs) ? "ncells, 2" : "ncells"); goto done; } } \
+  } while (0)
+  NEED_VAR("tile1_cell", 1);
   if (nc3_get_var_int(f, v, ibuf)) goto io_error;
   for (i = 0; i < n; ++i) { i_in[i] = ibuf[2 * i] - 1; j_in[i] = ibuf[2 * i + 1] - 1; }
-  NEED_VAR("tile2_cell");
+  NEED_VAR("tile2_cell", 1);
   if (nc3_get_var_int(f, v, ibuf)) goto io_error;
   for (i = 0; i < n; ++i) { i_out[i] = ibuf[2 * i] - 1; j_out[i] = ibuf[2 * i + 1] - 1; }
-  NEED_VAR("xgrid_area");
+  NEED_VAR("xgrid_area", 0);
   if (nc3_get_var_double(f, v, area)) goto io_error;
   /* the reference scales to unit-sphere area on read (read_mosaic.c:437) and back in setup_conserve_interp
      (conserve_interp.c:86); the two roundings are kept so that READ reproduces its numbers */
   for (i = 0; i < n; ++i) { area[i] /= garea; area[i] *= garea; }
   if (order == 2) {
-    NEED_VAR("tile1_distance");
+    NEED_VAR("tile1_distance", 1);
     dbuf = (double *)malloc((size_t)(n > 0 ? n : 1) * 2 * sizeof(double));
     if (!dbuf) { xgb_set_error("xgb_remap_read: out of memory"); goto done; }
     if (nc3_get_var_double(f, v, dbuf)) goto io_error;
     for (i = 0; i < n; ++i) { di[i] = dbuf[2 * i]; dj[i] = dbuf[2 * i + 1]; }
   }
-  NEED_VAR("tile1");
+  NEED_VAR("tile1", 0);
   if (nc3_get_var_int(f, v, t_in)) goto io_error;
   for (i = 0; i < n; ++i) t_in[i] -= 1;                   /* conserve_interp.c:110 */
   rc = 0;

@@ -205,3 +205,43 @@ def test_golden_remap_files_round_trip(pkg, order):
     finally:
         if os.path.exists(out):
             os.remove(out)
+
+
+def test_remap_files_with_another_layout_are_refused(pkg, tmp_path):
+    """xgb_remap_read sizes its buffers from the `ncells` dimension; a file whose variables have another shape (three
+    columns, a missing `two`, a text variable) or whose header claims an absurd attribute length must be refused, not read
+    past the buffers"""
+    L = pkg.lib()
+    n = 5
+
+    def write(path, mutate):
+        g = netcdf_file(path, "w", version=2)
+        g.createDimension("string", 255); g.createDimension("ncells", n); g.createDimension("two", 2); g.createDimension("three", 3)
+        shapes = {"tile1": ("ncells",), "tile1_cell": ("ncells", "two"), "tile2_cell": ("ncells", "two"), "xgrid_area": ("ncells",)}
+        types = {"tile1": "i", "tile1_cell": "i", "tile2_cell": "i", "xgrid_area": "d"}
+        mutate(shapes, types)
+        for k, dims in shapes.items():
+            v = g.createVariable(k, types[k], dims)
+            v[:] = np.ones([{"ncells": n, "two": 2, "three": 3, "string": 255}[d] for d in dims], dtype=v.data.dtype) if types[k] != "c" else b"x"
+        g.close()
+
+    def read(path):
+        out = [np.zeros(n, np.int32) for _ in range(5)] + [np.zeros(n)]
+        return L.xgb_remap_read(path.encode(), 1, n, *[a.ctypes.data for a in out], None, None)
+
+    good = str(tmp_path / "good.nc"); write(good, lambda s, t: None)
+    assert read(good) == 0, L.xgb_last_error()
+    for tag, mut in (("three", lambda s, t: s.update(tile1_cell=("ncells", "three"))),
+                     ("flat", lambda s, t: s.update(tile2_cell=("ncells",))),
+                     ("pairs", lambda s, t: s.update(xgrid_area=("ncells", "two"))),
+                     ("other_dim", lambda s, t: s.update(tile1=("three",))),
+                     ("text", lambda s, t: (s.update(tile1=("ncells",)), t.update(tile1="c")))):
+        path = str(tmp_path / f"{tag}.nc"); write(path, mut)
+        assert read(path) != 0, tag
+        assert b"is not a numeric" in L.xgb_last_error(), (tag, L.xgb_last_error())
+    # a CDF-5 header whose one global attribute claims 2^60 doubles
+    import struct
+    hdr = b"CDF\x05" + struct.pack(">q", 0) + struct.pack(">iq", 0, 0) + struct.pack(">iq", 12, 1) + \
+        struct.pack(">q", 4) + b"name" + struct.pack(">iq", 6, 1 << 60) + bytes(64)
+    bad = str(tmp_path / "huge_att.nc"); open(bad, "wb").write(hdr)
+    assert L.xgb_remap_size(bad.encode()) < 0 and b"malformed header" in L.xgb_last_error(), L.xgb_last_error()
