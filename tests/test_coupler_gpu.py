@@ -198,6 +198,67 @@ def test_finer_grids_with_partly_wet_ocean_cells(pkg, tmp_path):
     g.close()
 
 
+def test_c48_one_degree_trio(pkg, tmp_path):
+    """the size the coupled models run at: C48 atmosphere, a land mosaic of its own (C32), one-degree 360 x 200 ocean with
+    partly wet cells, order 2: ~240 000 exchange cells in three families, every file of the reference tool bit for bit"""
+    tool = _ref_tool()
+    d = str(tmp_path)
+    atm = _write_mosaic(pkg, d, 48)
+    lnd = _write_mosaic(pkg, d, 32)
+    ocn = _write_ocean(d, 360, 200, -80.0, seed=1, frac_land=0.3, area_frac=True)
+    r = subprocess.run([tool, "--atmos_mosaic", "C48_mosaic.nc", "--land_mosaic", "C32_mosaic.nc", "--ocean_mosaic", "ocean_mosaic.nc",
+                        "--ocean_topog", "topog.nc", "--interp_order", "2", "--mosaic_name", "grid_spec"],
+                       cwd=d, capture_output=True, text=True, timeout=1800)
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])
+    x = pkg.make_coupler_xgrid(_tiles(atm), [(ocn["lon"], ocn["lat"])], [ocn["omask"]], lnd=_tiles(lnd), interp_order=2)
+    n = _compare_lists(d, x["atmxlnd"], "C48_mosaic", "C32_mosaic", 2)
+    n += _compare_lists(d, x["atmxocn"], "C48_mosaic", "ocean_mosaic", 2, ext2=1)
+    n += _compare_lists(d, x["lndxocn"], "C32_mosaic", "ocean_mosaic", 2, ext2=1)
+    assert n > 200000, n
+    g = netcdf_file(os.path.join(d, "ocean_mask.nc"), "r", mmap=False)
+    assert np.array_equal(np.array(g.variables["areaX"][:]), x["ocn_xarea"].reshape(201, 360)[1:])
+    g.close()
+    for t in range(6):
+        g = netcdf_file(os.path.join(d, f"land_mask_tile{t + 1}.nc"), "r", mmap=False)
+        assert np.array_equal(np.array(g.variables["l_area"][:]), x["lnd_xarea"].reshape(6, 32, 32)[t]), t
+        g.close()
+
+
+def test_all_three_models_on_one_mosaic(pkg, tmp_path):
+    """aquaplanet-style set-up: atmosphere, land and ocean on the same cubed-sphere mosaic, a six-tile topography file with
+    area_frac.  The tool then visits ocean tile n for atmosphere tile n only (make_coupler_mosaic.c:1332-1345), names its files
+    atm_..Xlnd_.. / atm_..Xocn_.. (:2151, :2278) and adds no southern row (:840, one-tile oceans only)"""
+    tool = _ref_tool()
+    d = str(tmp_path)
+    atm = _write_mosaic(pkg, d, 8)
+    rng = np.random.default_rng(21)
+    g = netcdf_file(os.path.join(d, "topog.nc"), "w", version=2)
+    g.createDimension("ntiles", 6)
+    omask = []
+    for t in range(6):
+        g.createDimension(f"nx_tile{t + 1}", 8); g.createDimension(f"ny_tile{t + 1}", 8)
+    for t in range(6):
+        u = rng.uniform(size=(8, 8))
+        frac = np.where(u < 0.3, 0.0, np.where(u < 0.6, 1.0, rng.uniform(0.0, 1.0, (8, 8))))
+        v = g.createVariable(f"depth_tile{t + 1}", "d", (f"ny_tile{t + 1}", f"nx_tile{t + 1}")); v[:] = 100.0 * frac
+        w = g.createVariable(f"area_frac_tile{t + 1}", "d", (f"ny_tile{t + 1}", f"nx_tile{t + 1}")); w[:] = frac
+        omask.append(frac)
+    g.close()
+    r = subprocess.run([tool, "--atmos_mosaic", "C8_mosaic.nc", "--land_mosaic", "C8_mosaic.nc", "--ocean_mosaic", "C8_mosaic.nc",
+                        "--ocean_topog", "topog.nc", "--interp_order", "2", "--mosaic_name", "grid_spec"],
+                       cwd=d, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])
+    x = pkg.make_coupler_xgrid(_tiles(atm), _tiles(atm), omask, lnd=None, interp_order=2, ocn_same_as_atm=True)
+    n = _compare_lists(d, x["atmxlnd"], "atm_C8_mosaic", "lnd_C8_mosaic", 2)
+    n += _compare_lists(d, x["atmxocn"], "atm_C8_mosaic", "ocn_C8_mosaic", 2)
+    assert n > 400 and x["lndxocn"]["area"].size == 0
+    assert np.array_equal(x["atmxocn"]["t1"], x["atmxocn"]["t2"])
+    for t in range(6):
+        g = netcdf_file(os.path.join(d, f"ocean_mask_tile{t + 1}.nc"), "r", mmap=False)
+        assert np.array_equal(np.array(g.variables["areaX"][:]), x["ocn_xarea"].reshape(6, 8, 8)[t]), t
+        g.close()
+
+
 def test_bad_arguments_are_refused(pkg):
     lon, lat = np.meshgrid(np.linspace(0, 1, 3), np.linspace(0, 1, 3))
     with pytest.raises(pkg.XgridError):
