@@ -684,7 +684,9 @@ apply_rec_kernel(ApplyCsr csr, long long ndst, int nf, int nfp, const double* __
   // (tried, each slower than this plain per-cell loop at 1.87 ms, scripts/apply_variants.sh: the records of the two source
   // cells used last kept in registers, 1.97 ms — a third of the loads, half as many more instructions; one flat loop over the
   // tile's entries with the records of entry q + 1 requested before entry q is summed, 2.09 ms at 80 registers / 6 blocks,
-  // 2.31 ms with spills at 64 / 8: the kernel lives on resident warps, not on loads in flight per warp)
+  // 2.31 ms with spills at 64 / 8: the kernel lives on resident warps, not on loads in flight per warp; writing the results
+  // out every 4 / 2 destination cells so that the staging shrinks and the L1 grows, 2.38 / 4.06 ms — the output rows want
+  // segments of at least 64 bytes; 16-cell tiles with 128-byte segments, 2.36 ms at the 5 blocks their staging leaves)
   for (int dl = 0; dl < nd; ++dl) {
     const int b = (int)(s_off[dl] - q0), e = (int)(s_off[dl + 1] - q0);
     double acc0 = 0.0, acc1 = 0.0, as0 = 0.0, as1 = 0.0;

@@ -1308,15 +1308,21 @@ __device__ __forceinline__ void edge_terms(double xi, double yi, double xn, doub
   const double dy = 0.5 * (lat1 - lat2);               // hdy of poly_ctrlat is -dy
   const bool moving = (ORDER == 2) && (dx_raw != 0.0); // poly_ctrlon / poly_ctrlat skip dx == 0 edges
   const bool flat_lat = (fabs(dy) < kSmall);           // fabs(hdy) < SMALL_VALUE (create_xgrid.c:2114)
+  // An edge along a meridian (dx == 0; against a lat-lon destination every polygon has one or two) adds dx * sin(avg) [* dat]
+  // = a zero whose sign is sign(dx) * sign(avg): sin keeps the sign of a latitude, dat = sin(dy)/dy is positive.  Writing that
+  // zero down directly is bit-identical and needs no trig, so a warp whose polygons lie below 49 degrees (where sin(avg) is
+  // the sine half of the sincos) never enters the separate sin() at all.
+  const bool meridian = (dx_raw == 0.0);
   double s_avg = 0.0, c_avg = 0.0;
   if (moving) C2_SINCOS(avg, &s_avg, &c_avg);
   double dat = 0.0;
-  if ((!pole_edge && !flat_area) || (moving && !flat_lat)) dat = C2_SIN_SMALL(dy) / dy;
+  if (!meridian && ((!pole_edge && !flat_area) || (moving && !flat_lat))) dat = C2_SIN_SMALL(dy) / dy;
   const uint32_t hi = (uint32_t)(trig::bits(avg) >> 32) & 0x7fffffffu;
-  const bool own_sin = !pole_edge && !(moving && hi < 0x3feb6000u);
+  const bool own_sin = !meridian && !pole_edge && !(moving && hi < 0x3feb6000u);
   double sin_avg = s_avg;
   if (own_sin) sin_avg = C2_SIN(avg);
-  if (pole_edge) *ta = -kPi;                           // mosaic_util.c:434-437
+  if (meridian) *ta = dxa * avg;
+  else if (pole_edge) *ta = -kPi;                      // mosaic_util.c:434-437
   else if (flat_area) *ta = dxa * sin_avg;
   else *ta = dxa * sin_avg * dat;
   if (ORDER == 2) {
