@@ -1,11 +1,12 @@
 // One-time grid metrics for the order-2 gradient: calc_c2l_grid_info / get_edge / mid_pt_sphere
 // (reference gradient_c2l.c:368-454, :198-313, :315-337) on the device.
 //
-// Unlike the exchange-grid kernels this routine is NOT bit-identical to the reference: it calls asin/acos/atan2,
-// for which CUDA's libm and glibc differ by an ulp, and the reference evaluates spherical_angle in x87 long double
-// (mosaic_util.c:803).  The metrics agree to rounding (relative 1e-15; the spherical-excess cell area to
-// 1e-15/excess, because both sides cancel 2*pi out of a sum of four angles); callers that need the reference's
-// exact metrics pass them in with xgb_plan_grad_set_metrics instead.
+// Round 2: the Cartesian vertices (latlon2xyz), the unit vectors (unit_vect_latlon), the edge normals and the spherical-excess
+// cell area are computed with the reference binary's own libm entry points and bits (ref_trig.cuh; acosl as the reference
+// rounds it, gc_clip.cuh) and come out bit-identical (area: but for the few angles per 100 000 where the x87 fpatan is not
+// correctly rounded).  dx, dy and the edge weights go through asin / atan2: gc_asin / gc_atan2 give the correctly rounded value,
+// which is glibc's on all but ~1 argument per 1000 (glibc 2.39's asin is not correctly rounded there; checked with mpmath), so
+// these agree to 1e-15 relative and are bit-identical in the vast majority of cells.  Callers that need the reference's exact metrics can still pass them in with xgb_plan_grad_set_metrics.
 #include "apply_internal.h"
 #include "gc_clip.cuh"
 
@@ -15,14 +16,16 @@ extern long long g_launches;
 
 __device__ __forceinline__ double gc_distance(double lon1, double lat1, double lon2, double lat2)
 {
-  const double a = sin((lat1 - lat2) / 2.), b = sin((lon1 - lon2) / 2.);       // mosaic_util.c:754-757
-  const double beta = 2. * asin(sqrt(a * a + cos(lat1) * cos(lat2) * (b * b)));
+  // mosaic_util.c:754-757; the reference binary calls sin, cos, cos, sin, asin (objdump of oracle/_ref)
+  const double a = ref_sin((lat1 - lat2) / 2.), b = ref_sin((lon1 - lon2) / 2.);
+  const double beta = 2. * gc::gc_asin(sqrt(a * a + ref_cos(lat1) * ref_cos(lat2) * (b * b)));
   return kRadius * beta;
 }
 
 __device__ __forceinline__ void ll2xyz(double lon, double lat, double* v)
 {
-  v[0] = cos(lat) * cos(lon); v[1] = cos(lat) * sin(lon); v[2] = sin(lat);      // mosaic_util.c:212-222
+  const gc::V3 r = gc::ll2xyz(lon, lat);      // mosaic_util.c:212-222 with the libm entry points and bits of the reference binary
+  v[0] = r.x; v[1] = r.y; v[2] = r.z;
 }
 
 __device__ __forceinline__ void cross3(const double* p1, const double* p2, double* e)
@@ -64,9 +67,9 @@ __device__ __forceinline__ void mid_pt(double lon1, double lat1, double lon2, do
   double xx = e[0], yy = e[1], zz = e[2];
   const double dist = sqrt(xx * xx + yy * yy + zz * zz);
   xx /= dist; yy /= dist; zz /= dist;
-  double lon = (fabs(xx) + fabs(yy) < 1.e-10) ? 0. : atan2(yy, xx);
+  double lon = (fabs(xx) + fabs(yy) < 1.e-10) ? 0. : gc::gc_atan2(yy, xx);
   if (lon < 0.) lon = 2. * kPi + lon;
-  pm[0] = lon; pm[1] = asin(zz);
+  pm[0] = lon; pm[1] = gc::gc_asin(zz);
 }
 
 // edge weight at a corner between the two neighbouring mid points (get_edge, gradient_c2l.c:243-309)
@@ -117,7 +120,8 @@ c2l_grid_info_kernel(int nx, int ny, const double* __restrict__ xt, const double
     const long long m = (long long)j * nx + i;
     area[m] = (a1 + a2 + a3 + a4 - 2. * kPi) * kRadius * kRadius;       // spherical_excess_area, mosaic_util.c:846-880
     const double lon = xt[(long long)(j + 1) * w + i + 1], lat = yt[(long long)(j + 1) * w + i + 1];
-    const double sl = sin(lon), cl = cos(lon), sa = sin(lat), ca = cos(lat);   // unit_vect_latlon, mosaic_util.c:937-957
+    double sl, cl, sa, ca;                                                     // unit_vect_latlon, mosaic_util.c:937-957:
+    ref_sincos(lon, &sl, &cl); ref_sincos(lat, &sa, &ca);                      // two sincos calls in the reference binary
     vlon[3 * m] = -sl; vlon[3 * m + 1] = cl; vlon[3 * m + 2] = 0.;
     vlat[3 * m] = -sa * cl; vlat[3 * m + 1] = -sa * sl; vlat[3 * m + 2] = ca;
   }

@@ -155,6 +155,34 @@ XGB_HD double gc_acos(double x) {
   return round_through_x87(a);
 }
 
+// asin and atan2 as glibc returns them.  The IBM Accurate Mathematical Library routines behind glibc's asin / atan2 aim at the
+// correctly rounded result (and reach it on all but a few arguments per million); the same double-double atan, rounded once,
+// therefore gives their bits.  Used by calc_c2l_grid_info's great_circle_distance and xyz2latlon (mosaic_util.c:228-252,
+// :754-757) so that the order-2 gradient metrics computed on the device equal the reference's.
+XGB_HD double gc_asin(double x) {
+  const dd half_pi{0x1.921fb54442d18p+0, 0x1.1a62633145c07p-54};
+  const double ax = fabs(x);
+  if (!(ax <= 1.0)) return asin(x);                                    // NaN / domain error: the toolchain's answer
+  if (ax < 0x1p-27) return x;                                          // x + x^3/6 rounds to x
+  if (ax == 1.0) return copysign(half_pi.hi, x);
+  const dd s = dd_sqrt(dd_mul(two_sum(1.0, -ax), two_sum(1.0, ax)));   // cos of the angle
+  dd a;
+  if (ax <= s.hi) a = dd_atan01(dd_div(dd{ax, 0.0}, s));
+  else a = dd_sub(half_pi, dd_atan01(dd_div(s, dd{ax, 0.0})));
+  return copysign(a.hi, x);
+}
+XGB_HD double gc_atan2(double y, double x) {
+  const dd pi{0x1.921fb54442d18p+1, 0x1.1a62633145c07p-53}, half_pi{0x1.921fb54442d18p+0, 0x1.1a62633145c07p-54};
+  const double ax = fabs(x), ay = fabs(y);
+  if (!(ax < INFINITY) || !(ay < INFINITY) || (ax == 0.0 && ay == 0.0) || ay < ax * 0x1p-60 || ax < ay * 0x1p-60)
+    return atan2(y, x);                                                // zeros, infinities, NaN, axis-hugging: the toolchain's answer
+  dd a;
+  if (ay <= ax) a = dd_atan01(dd_div(dd{ay, 0.0}, dd{ax, 0.0}));
+  else a = dd_sub(half_pi, dd_atan01(dd_div(dd{ax, 0.0}, dd{ay, 0.0})));
+  if (x < 0.0) a = dd_sub(pi, a);
+  return copysign(a.hi, y);
+}
+
 struct V3 { double x, y, z; };
 
 XGB_HD bool same_point(double x1, double y1, double z1, double x2, double y2, double z2) {   // mosaic_util.c:1193

@@ -291,28 +291,40 @@ extern "C" int xgb_gc_clip_host(const double* x1, const double* y1, const double
   return n;
 }
 
-// gc::gc_acos (acosl rounded to double, gc_clip.cuh) on n arguments: host build and device build, for the tests
+// gc::gc_acos / gc_asin / gc_atan2 (gc_clip.cuh) on n arguments: host build and device build, for the tests.
+// fn: 0 = acos (acosl rounded to double), 1 = asin, 2 = atan2(x[i], y[i])
 namespace xgb {
-__global__ void gc_acos_kernel(long long n, const double* __restrict__ x, double* __restrict__ out)
+__device__ __host__ inline double gc_math(int fn, double x, double y)
+{
+  return fn == 0 ? gc::gc_acos(x) : (fn == 1 ? gc::gc_asin(x) : gc::gc_atan2(x, y));
+}
+__global__ void gc_math_kernel(int fn, long long n, const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ out)
 {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i < n) out[i] = gc::gc_acos(x[i]);
+  if (i < n) out[i] = gc_math(fn, x[i], y ? y[i] : 0.0);
 }
 }  // namespace xgb
 
-extern "C" void xgb_gc_acos_host(long long n, const double* x, double* out)
+extern "C" void xgb_gc_math_host(int fn, long long n, const double* x, const double* y, double* out)
 {
-  for (long long i = 0; i < n; ++i) out[i] = xgb::gc::gc_acos(x[i]);
+  for (long long i = 0; i < n; ++i) out[i] = xgb::gc_math(fn, x[i], y ? y[i] : 0.0);
 }
 
-extern "C" int xgb_gc_acos_device(long long n, const double* x_host, double* out_host)
+extern "C" int xgb_gc_math_device(int fn, long long n, const double* x_host, const double* y_host, double* out_host)
 {
-  double *x = nullptr, *o = nullptr;
+  double *x = nullptr, *y = nullptr, *o = nullptr;
   if (n <= 0) return 0;
-  if (cudaMalloc(&x, n * 8) != cudaSuccess || cudaMalloc(&o, n * 8) != cudaSuccess) { cudaFree(x); return 1; }
+  if (cudaMalloc(&x, n * 8) != cudaSuccess || cudaMalloc(&o, n * 8) != cudaSuccess || (y_host && cudaMalloc(&y, n * 8) != cudaSuccess)) {
+    cudaFree(x); cudaFree(o); cudaFree(y);
+    return 1;
+  }
   cudaMemcpy(x, x_host, n * 8, cudaMemcpyHostToDevice);
-  xgb::gc_acos_kernel<<<(unsigned)((n + 255) / 256), 256>>>(n, x, o);
+  if (y_host) cudaMemcpy(y, y_host, n * 8, cudaMemcpyHostToDevice);
+  xgb::gc_math_kernel<<<(unsigned)((n + 255) / 256), 256>>>(fn, n, x, y, o);
   const cudaError_t e = cudaMemcpy(out_host, o, n * 8, cudaMemcpyDeviceToHost);
-  cudaFree(x); cudaFree(o);
+  cudaFree(x); cudaFree(y); cudaFree(o);
   return e == cudaSuccess ? 0 : 1;
 }
+
+extern "C" void xgb_gc_acos_host(long long n, const double* x, double* out) { xgb_gc_math_host(0, n, x, nullptr, out); }
+extern "C" int xgb_gc_acos_device(long long n, const double* x_host, double* out_host) { return xgb_gc_math_device(0, n, x_host, nullptr, out_host); }

@@ -397,6 +397,10 @@ int xgb_remap_read(const char *path, int order, long long cap, int *t_in, int *i
  * csrc/gc_clip.cuh on n arguments (self-checks; the device version copies through temporary buffers) */
 void xgb_gc_acos_host(long long n, const double *x, double *out);
 int  xgb_gc_acos_device(long long n, const double *x_host, double *out_host);
+/* the same for fn = 0 acos, 1 asin, 2 atan2(x[i], y[i]) as glibc returns them (calc_c2l_grid_info's great_circle_distance and
+ * xyz2latlon, mosaic_util.c:228-252, :754-757); y may be NULL for fn 0 and 1 */
+void xgb_gc_math_host(int fn, long long n, const double *x, const double *y, double *out);
+int  xgb_gc_math_device(int fn, long long n, const double *x_host, const double *y_host, double *out_host);
 
 /* ============================================================================================
  * Part 5 — make_coupler_mosaic's exchange grids (tools/make_coupler_mosaic/make_coupler_mosaic.c)

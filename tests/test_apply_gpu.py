@@ -74,9 +74,17 @@ def test_grad_c2l_and_metrics(pkg):
     for t, m in enumerate(c.oracle_metrics()):
         got = p.grad_get_metrics(t)
         for k in xgtest.METRICS:
-            tol = 1e-9 if k == "area" else 1e-13      # spherical excess: 2*pi cancels out of a sum of four angles
             scale = np.max(np.abs(m[k]))
-            assert np.max(np.abs(got[k] - m[k])) <= tol * scale, (t, k, np.max(np.abs(got[k] - m[k])) / scale)
+            if k in ("vlon", "vlat", "en_n", "en_e"):
+                assert np.array_equal(got[k], m[k]), (t, k)     # reference's own sin / cos / sincos bits
+            elif k == "area":
+                # spherical excess of four acosl() angles: bit-identical but where the x87 fpatan is not correctly rounded
+                assert np.mean(got[k] == m[k]) > 0.99 and np.max(np.abs(got[k] - m[k])) <= 1e-13 * scale, (t, np.mean(got[k] == m[k]))
+            else:
+                # dx, dy, edge weights: asin / atan2 in double-double, correctly rounded; glibc's own differ from that on about one
+                # argument per thousand
+                assert np.max(np.abs(got[k] - m[k])) <= 1e-15 * scale, (t, k, np.max(np.abs(got[k] - m[k])) / scale)
+                assert np.mean(got[k] == m[k]) > 0.9, (t, k, np.mean(got[k] == m[k]))
 
 
 @pytest.mark.parametrize("ni,nlon,nlat", [(8, 36, 18), (24, 144, 72)])

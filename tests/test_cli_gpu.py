@@ -223,7 +223,7 @@ def test_order2_fields_with_missing_values(pkg, dataset):
     for t in range(ds["nt"]):
         want = remap(ds["ps"][t], False, 0.0)
         got = g.variables["ps"][t].reshape(-1)
-        assert np.allclose(got, want, rtol=1e-11, atol=0), np.abs(got / want - 1).max()
+        assert np.allclose(got, want, rtol=1e-13, atol=0), np.abs(got / want - 1).max()
         for k in range(ds["nz"]):
             want = remap(ds["temp"][t, k].astype(np.float64), True, float(MISSING))
             got = g.variables["temp"][t, k].reshape(-1).astype(np.float64)
@@ -378,13 +378,14 @@ def test_fregrid_b200_against_the_unmodified_reference_fregrid(pkg, dataset):
     and field readers, mpp_io, conserve_interp, writers) compiled unmodified over the netCDF-C shim — and fregrid_b200 run with
     the same arguments on the same files.  Remap files: same cells, same order, bit-identical areas and distances (byte-
     identical when the container versions agree).  Output files: same variables, dimensions and attributes; order 1 values
-    identical; order 2 (the product computes the c2l metrics on the device) to 1e-11."""
+    identical; order 2 (the product computes the c2l metrics on the device: bit-identical but for asin / atan2 on about one
+    argument per thousand) to 1e-13."""
     ref = os.path.join(xgtest.ORACLE_DIR, "_ref", "fregrid_ref")
     xgtest.ref_lib()
     if not os.path.exists(ref):
         pytest.skip("oracle/_ref/fregrid_ref not built")
     ds = dataset
-    for method, order, tol in (("conserve_order1", 1, 0.0), ("conserve_order2", 2, 1e-11)):
+    for method, order, tol in (("conserve_order1", 1, 0.0), ("conserve_order2", 2, 1e-13)):
         common = ["--input_mosaic", f"C{ds['n']}_mosaic.nc", "--nlon", "48", "--nlat", "24", "--input_file", "atmos",
                   "--scalar_field", "temp,ps,orog", "--interp_method", method]
         r = subprocess.run([ref] + common + ["--output_file", f"cmp_ref_{order}.nc", "--remap_file", f"cmp_ref_remap_{order}.nc"],
