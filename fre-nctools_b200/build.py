@@ -25,8 +25,9 @@ def needs_build():
         return True
     t = os.path.getmtime(OUT)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    deps += [os.path.join(HERE, "..", "include", "xgrid_b200.h"), os.path.abspath(__file__), CLI_SRC]
-    if not os.path.exists(CLI_OUT):
+    deps += [os.path.join(HERE, "..", "include", "xgrid_b200.h"), os.path.abspath(__file__)]
+    deps += [os.path.join(HERE, "cli", f) for f in os.listdir(os.path.join(HERE, "cli"))]
+    if not all(os.path.exists(os.path.join(HERE, "bin", t)) for t in ("fregrid_b200", "make_coupler_mosaic_b200")):
         return True
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
@@ -50,15 +51,22 @@ def build(force=False, verbose=False, out=None, defines=()):
     return OUT
 
 
+CLI_TOOLS = ("fregrid_b200", "make_coupler_mosaic_b200")
+
+
 def build_cli():
-    """fregrid_b200: the host side of the fregrid command line in C, linked against libxgrid_b200.so next to it."""
+    """fregrid_b200, make_coupler_mosaic_b200: the host side of the reference command lines in C, linked against
+    libxgrid_b200.so next to them."""
     os.makedirs(os.path.dirname(CLI_OUT), exist_ok=True)
-    cmd = [os.environ.get("CC", "gcc"), "-O2", "-std=gnu99", "-Wall", "-o", CLI_OUT, CLI_SRC, "-L" + HERE, "-lxgrid_b200",
-           "-Wl,-rpath,$ORIGIN/..", "-Wl,--allow-shlib-undefined", "-lm"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("gcc failed building fregrid_b200")
+    for tool in CLI_TOOLS:
+        src = os.path.join(HERE, "cli", tool + ".c")
+        out = os.path.join(HERE, "bin", tool)
+        cmd = [os.environ.get("CC", "gcc"), "-O2", "-std=gnu99", "-Wall", "-o", out, src, "-L" + HERE, "-lxgrid_b200",
+               "-Wl,-rpath,$ORIGIN/..", "-Wl,--allow-shlib-undefined", "-lm"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("gcc failed building " + tool)
     return CLI_OUT
 
 

@@ -259,6 +259,80 @@ def test_all_three_models_on_one_mosaic(pkg, tmp_path):
         g.close()
 
 
+def _same_files(da, db, inputs):
+    """every output file of directory da exists in db with the same dimensions, variables, attributes and values; global
+    attributes only by name (they carry version, host, time and argv[0])"""
+    fa = sorted(f for f in os.listdir(da) if f.endswith(".nc") and f not in inputs)
+    fb = sorted(f for f in os.listdir(db) if f.endswith(".nc") and f not in inputs)
+    assert fa == fb, (set(fa) ^ set(fb))
+    for name in fa:
+        ga = netcdf_file(os.path.join(da, name), "r", mmap=False); gb = netcdf_file(os.path.join(db, name), "r", mmap=False)
+        assert dict(ga.dimensions) == dict(gb.dimensions), name
+        assert list(ga.variables) == list(gb.variables), (name, list(ga.variables), list(gb.variables))
+        assert set(ga._attributes) - {"great_circle_algorithm"} == set(gb._attributes), (name, set(ga._attributes) ^ set(gb._attributes))
+        assert ga._attributes["grid_version"] == gb._attributes["grid_version"]
+        for v, va in ga.variables.items():
+            vb = gb.variables[v]
+            assert va.dimensions == vb.dimensions and va.typecode() == vb.typecode(), (name, v)
+            assert va._attributes == vb._attributes, (name, v, va._attributes, vb._attributes)
+            xa, xb = np.array(va[:]), np.array(vb[:])
+            if name.startswith("land_mask") and v == "area_atm":
+                continue          # the reference indexes the atmosphere tile with the land cell number (make_coupler_mosaic.c:2083)
+            assert np.array_equal(xa, xb), (name, v)
+        ga.close(); gb.close()
+    return len(fa)
+
+
+@pytest.mark.parametrize("case", ["own_land_order2", "atm_land_order1", "one_mosaic"])
+def test_make_coupler_mosaic_b200_against_the_reference_tool(pkg, tmp_path, case):
+    """the command line: make_coupler_mosaic_b200 and the unmodified reference make_coupler_mosaic with the same arguments on
+    the same files -> the same files (exchange grids, land / ocean masks, the coupler mosaic file with its file lists)"""
+    tool = _ref_tool()
+    exe = os.path.join(os.path.dirname(pkg.__file__), "bin", "make_coupler_mosaic_b200")
+    assert os.path.exists(exe), "make_coupler_mosaic_b200 is not built (python __graft_entry__.py)"
+    dirs = [str(tmp_path / "ref"), str(tmp_path / "b200")]
+    for d in dirs:
+        os.makedirs(d)
+        _write_mosaic(pkg, d, 8)
+        if case == "own_land_order2":
+            _write_mosaic(pkg, d, 6)
+        if case == "one_mosaic":
+            rng = np.random.default_rng(33)
+            g = netcdf_file(os.path.join(d, "topog.nc"), "w", version=2)
+            g.createDimension("ntiles", 6)
+            for t in range(6):
+                g.createDimension(f"nx_tile{t + 1}", 8); g.createDimension(f"ny_tile{t + 1}", 8)
+            for t in range(6):
+                v = g.createVariable(f"depth_tile{t + 1}", "d", (f"ny_tile{t + 1}", f"nx_tile{t + 1}"))
+                v[:] = np.where(rng.uniform(size=(8, 8)) < 0.4, 0.0, 50.0)
+            g.close()
+        else:
+            _write_ocean(d, 30, 20, -78.0, seed=3, area_frac=(case == "atm_land_order1"))
+    args = {"own_land_order2": ["--atmos_mosaic", "C8_mosaic.nc", "--land_mosaic", "C6_mosaic.nc", "--ocean_mosaic", "ocean_mosaic.nc",
+                                "--ocean_topog", "topog.nc", "--interp_order", "2", "--mosaic_name", "grid_spec"],
+            "atm_land_order1": ["--atmos_mosaic", "C8_mosaic.nc", "--land_mosaic", "C8_mosaic.nc", "--ocean_mosaic", "ocean_mosaic.nc",
+                                "--ocean_topog", "topog.nc", "--interp_order", "1"],
+            "one_mosaic": ["--atmos_mosaic", "C8_mosaic.nc", "--land_mosaic", "C8_mosaic.nc", "--ocean_mosaic", "C8_mosaic.nc",
+                           "--ocean_topog", "topog.nc", "--sea_level", "10"]}[case]
+    inputs = set(os.listdir(dirs[0]))
+    for cmd, d in ((tool, dirs[0]), (exe, dirs[1])):
+        r = subprocess.run([cmd] + args, cwd=d, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, (cmd, r.stdout[-1500:], r.stderr[-1500:])
+    n = _same_files(dirs[0], dirs[1], inputs)
+    assert n >= (14 if case != "own_land_order2" else 30), n
+
+
+def test_make_coupler_mosaic_b200_messages(pkg, tmp_path):
+    exe = os.path.join(os.path.dirname(pkg.__file__), "bin", "make_coupler_mosaic_b200")
+    d = str(tmp_path)
+    _write_mosaic(pkg, d, 8)
+    r = subprocess.run([exe, "--atmos_mosaic", "C8_mosaic.nc"], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 1 and "ocean_mosaic is not specified" in r.stderr
+    r = subprocess.run([exe, "--atmos_mosaic", "C8_mosaic.nc", "--ocean_mosaic", "C8_mosaic.nc", "--ocean_topog", "t.nc", "--wave_mosaic", "w.nc"],
+                       cwd=d, capture_output=True, text=True)
+    assert r.returncode == 1 and "--wave_mosaic is not built" in r.stderr
+
+
 def test_bad_arguments_are_refused(pkg):
     lon, lat = np.meshgrid(np.linspace(0, 1, 3), np.linspace(0, 1, 3))
     with pytest.raises(pkg.XgridError):
