@@ -37,7 +37,7 @@ def build(force=False, verbose=False, out=None, defines=()):
     if out is None and not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", out or OUT] + [os.path.join(CSRC, s) for s in sources()] + ["-lcudart"]
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", out or OUT] + [os.path.join(CSRC, s) for s in sources()] + ["-lcudart", "-lz"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -14,7 +14,8 @@
  *   per time / level remapping loop                fregrid.c:1010-1085, get_input_data :2036, write_field_data :2339
  *   --check_conserve report                        conserve_interp.c:448-487
  * Not built (refused with a message): bilinear and vector remapping, --extrapolate / --dst_vgrid, --test_case,
- * cell_measures area files, MPI decomposition, netCDF-4 files (classic / 64-bit offset / CDF-5 only, csrc/nc3.c).
+ * cell_measures area files, MPI decomposition, netCDF-4 OUTPUT (input files may be classic, 64-bit offset, CDF-5 or
+ * netCDF-4/HDF5: csrc/nc3.c, csrc/h5r.c).
  * Unlike the reference, all levels of a time step go to the device as one batch; every level is still remapped exactly as
  * one reference call would remap it (include/xgrid_b200.h, Part 2b).
  */
@@ -713,7 +714,8 @@ int main(int argc, char **argv)
     if (ntiles_out > 1) snprintf(name_out[m], sizeof name_out[m], "%s.%s.nc", base_out, mout.gridtile[m]);
     else snprintf(name_out[m], sizeof name_out[m], "%s.nc", base_out);
   }
-  if (!format) { const int fmt = nc3_format(fin[0]); xgb_set_nc_format(fmt == 1 ? "classic" : fmt == 5 ? "cdf5" : "64bit_offset"); }  /* fregrid.c:896-903 */
+  if (!format) { const int fmt = nc3_format(fin[0]); xgb_set_nc_format(fmt == 1 ? "classic" : fmt == 5 ? "cdf5" : "64bit_offset"); }  /* fregrid.c:896-903; netCDF-4
+                                                   input (format 4): the output is 64-bit offset, HDF5 is read here but not written */
 
   Var var[MAXVAR];
   int nvar = 0;

@@ -8,7 +8,7 @@
  * xgb_make_coupler_xgrid (csrc/coupler.cu), instead of the loops of :1250-2017 and :2556-2808.
  *
  * Built: the tool's default clip method.  Refused by name: --wave_mosaic, great-circle grids (great_circle_algorithm = TRUE in a
- * grid file), nested atmosphere mosaics, --rotate_poly, netCDF-4 files.  --check, --verbose and --print_memory are accepted and
+ * grid file), nested atmosphere mosaics, --rotate_poly, netCDF-4 output.  --check, --verbose and --print_memory are accepted and
  * ignored (they only print).
  */
 #include <getopt.h>

@@ -21,6 +21,8 @@
 #include <sys/types.h>
 #include <unistd.h>
 
+#include "h5r.h"
+
 enum { TAG_DIM = 0x0A, TAG_VAR = 0x0B, TAG_ATT = 0x0C };
 #define NC3_MAX_LIST 65536u            /* dimensions / variables / attributes per list: a larger count is a corrupt header */
 
@@ -33,6 +35,7 @@ typedef struct {
 } Var;
 
 struct nc3_file {
+  struct h5r_file *h5; int *h5ds;                       /* a netCDF-4 file: the HDF5 reader and each variable's dataset */
   int fd, fmt, writing, defmode;
   long long numrecs;
   int ndims; Dim *dims;
@@ -42,6 +45,9 @@ struct nc3_file {
   long long recsize;
   char err[320];
 };
+
+static nc3_file *open_h5(const char *path, char *err, size_t errlen);
+static int h5_slab(nc3_file *f, int varid, const size_t *start, const size_t *count, void *host, int kind);
 
 static int tsize(int type)
 {
@@ -290,12 +296,18 @@ nc3_file *nc3_open(const char *path, char *err, size_t errlen)
     buf = (unsigned char *)realloc(buf, cap);
     got = pread(f->fd, buf, cap, 0);
     if (got < 4) { if (err) snprintf(err, errlen, "nc3_open: %s is not a netCDF file (too short)", path); goto bad; }
-    if (!memcmp(buf, "\211HDF", 4)) {
-      if (err) snprintf(err, errlen, "nc3_open: %s is a netCDF-4/HDF5 file; this build reads the classic formats only "
-                        "(convert with `nccopy -k classic` or `-k cdf5`)", path);
-      goto bad;
+    if (!memcmp(buf, "\211HDF", 4)) {                  /* netCDF-4: the reference's default format (mpp_io.c:52) */
+      free(buf); close(f->fd); free(f);
+      return open_h5(path, err, errlen);
     }
     if (memcmp(buf, "CDF", 3) || !(buf[3] == 1 || buf[3] == 2 || buf[3] == 5)) {
+      unsigned char sig[8];
+      long long off;
+      for (off = 512; off + 8 <= (long long)st.st_size; off *= 2)     /* an HDF5 superblock behind a user block */
+        if (pread(f->fd, sig, 8, off) == 8 && !memcmp(sig, "\211HDF\r\n\032\n", 8)) {
+          free(buf); close(f->fd); free(f);
+          return open_h5(path, err, errlen);
+        }
       if (err) snprintf(err, errlen, "nc3_open: %s is not a classic netCDF file", path);
       goto bad;
     }
@@ -464,6 +476,7 @@ static int slab_io(nc3_file *f, int varid, const size_t *start, const size_t *co
   const size_t WIN = (size_t)8 << 20;
   unsigned char *win;
   if (varid < 0 || varid >= f->nvars) return fail(f, "nc3: bad variable id %d", varid);
+  if (f->h5) return writing ? fail(f, "nc3: file is open read-only") : h5_slab(f, varid, start, count, host, kind);
   if (f->writing && f->defmode) return fail(f, "nc3: still in define mode");
   if (writing && !f->writing) return fail(f, "nc3: file is open read-only");
   v = &f->vars[varid];
@@ -780,8 +793,231 @@ int nc3_close(nc3_file *f)
       }
     }
   }
-  if (close(f->fd)) rc = -1;
+  if (f->h5) { h5r_close(f->h5); free(f->h5ds); }
+  else if (close(f->fd)) rc = -1;
   free_meta(f);
   free(f);
   return rc;
+}
+
+/* ------------------------------------------------------------------------------------------------------------- */
+/* netCDF-4 files.  The reference opens every file through libnetcdf and writes NC_FORMAT_NETCDF4_CLASSIC by default
+ * (tools/libfrencutils/mpp_io.c:52, :109-140, :163-169); h5r.c reads the HDF5 container, this part lays the netCDF-4
+ * conventions over it (netcdf-c libhdf5/hdf5open.c, nc4hdf.c): a dimension is a dimension-scale dataset (attribute CLASS =
+ * "DIMENSION_SCALE"; NAME starts with "This is a netCDF dimension but not a netCDF variable." when no coordinate variable
+ * goes with it; _Netcdf4Dimid holds its id), a variable's dimensions are the object references of DIMENSION_LIST, a variable
+ * that shares a dimension's name without being its coordinate variable is stored as "_nc4_non_coord_<name>", and the
+ * bookkeeping attributes (CLASS, NAME, DIMENSION_LIST, REFERENCE_LIST, _Netcdf4Dimid, _Netcdf4Coordinates, _nc3_strict,
+ * _NCProperties) are not netCDF attributes. */
+static const char NOT_A_VAR[] = "This is a netCDF dimension but not a netCDF variable.";
+static const char NON_COORD[] = "_nc4_non_coord_";
+
+static const h5r_att *h5_find_att(const h5r_dset *d, const char *name)
+{
+  int k;
+  for (k = 0; k < d->natts; ++k) if (!strcmp(d->atts[k].name, name)) return &d->atts[k];
+  return NULL;
+}
+static int h5_hidden_att(const char *n)
+{
+  static const char *const hidden[] = { "CLASS", "NAME", "DIMENSION_LIST", "REFERENCE_LIST", "_Netcdf4Dimid", "_Netcdf4Coordinates",
+                                        "_nc3_strict", "_NCProperties", "_Netcdf4Inq" };
+  size_t k;
+  for (k = 0; k < sizeof hidden / sizeof hidden[0]; ++k) if (!strcmp(n, hidden[k])) return 1;
+  return 0;
+}
+/* the classic type that holds every value of an HDF5 atomic type (int64 and the wide unsigned types: double) */
+static int h5_nc_type(const h5r_type *t)
+{
+  if (t->cls == H5R_STRING || t->cls == H5R_VLEN_STRING) return NC3_CHAR;
+  if (t->cls == H5R_FLOAT) return t->size == 4 ? NC3_FLOAT : t->size == 8 ? NC3_DOUBLE : 0;
+  if (t->cls == H5R_INT) {
+    if (t->size == 1) return t->is_signed ? NC3_BYTE : NC3_SHORT;
+    if (t->size == 2) return t->is_signed ? NC3_SHORT : NC3_INT;
+    if (t->size == 4) return t->is_signed ? NC3_INT : NC3_DOUBLE;
+    if (t->size == 8) return NC3_DOUBLE;
+  }
+  return 0;
+}
+/* one element in host byte order -> double */
+static double h5_elem(const unsigned char *p, const h5r_type *t)
+{
+  if (t->cls == H5R_FLOAT) {
+    if (t->size == 4) { float v; memcpy(&v, p, 4); return (double)v; }
+    { double v; memcpy(&v, p, 8); return v; }
+  }
+  switch (t->size) {
+    case 1: return t->is_signed ? (double)(signed char)p[0] : (double)p[0];
+    case 2: { uint16_t v; memcpy(&v, p, 2); return t->is_signed ? (double)(int16_t)v : (double)v; }
+    case 4: { uint32_t v; memcpy(&v, p, 4); return t->is_signed ? (double)(int32_t)v : (double)v; }
+    default: { uint64_t v; memcpy(&v, p, 8); return t->is_signed ? (double)(int64_t)v : (double)v; }
+  }
+}
+static void h5_swap_elems(unsigned char *p, size_t n, int es)   /* attribute bytes come as stored */
+{
+  size_t i; int b;
+  for (i = 0; i < n; ++i) for (b = 0; b < es / 2; ++b) { unsigned char t = p[i * es + b]; p[i * es + b] = p[i * es + es - 1 - b]; p[i * es + es - 1 - b] = t; }
+}
+
+static int h5_add_att(int *natts, Att **atts, const h5r_att *a)
+{
+  Att *o;
+  const int type = h5_nc_type(&a->type);
+  if (!type) return 0;                                   /* compound, enum, references ...: not a classic attribute */
+  *atts = (Att *)realloc(*atts, (size_t)(*natts + 1) * sizeof(Att));
+  if (!*atts) return -1;
+  o = &(*atts)[*natts];
+  o->name = strdup(a->name); o->type = type;
+  if (a->type.cls == H5R_STRING) {                       /* a text attribute is ONE fixed-length string (nc4hdf.c put_att_grpa) */
+    const size_t n = a->data_len;
+    o->n = (long long)n; o->raw = (unsigned char *)malloc(n + 1); memcpy(o->raw, a->data, n); o->raw[n] = 0;
+  } else if (a->type.cls == H5R_VLEN_STRING) {           /* NC_STRING: the first string, as text */
+    const size_t n = a->data_len ? strlen((const char *)a->data) : 0;
+    o->n = (long long)n; o->raw = (unsigned char *)malloc(n + 1); memcpy(o->raw, a->data, n); o->raw[n] = 0;
+  } else {
+    long long i;
+    const int ts = tsize(type), es = a->type.size;
+    unsigned char *tmp = (unsigned char *)malloc(a->data_len ? a->data_len : 1);
+    memcpy(tmp, a->data, a->data_len);
+    if (a->type.big_endian) h5_swap_elems(tmp, (size_t)a->nelem, es);      /* -> host order */
+    o->n = a->nelem; o->raw = (unsigned char *)malloc((size_t)(a->nelem > 0 ? a->nelem : 1) * (size_t)ts);
+    for (i = 0; i < a->nelem; ++i) double_to_disk(o->raw + i * ts, type, h5_elem(tmp + i * es, &a->type));
+    free(tmp);
+  }
+  ++*natts;
+  return 0;
+}
+
+static nc3_file *open_h5(const char *path, char *err, size_t errlen)
+{
+  nc3_file *f = (nc3_file *)calloc(1, sizeof(nc3_file));
+  int nds, i, k, *dim_of_ds = NULL, *is_var = NULL, ok = 0;
+  if (!f) { if (err) snprintf(err, errlen, "nc3_open: out of memory"); return NULL; }
+  f->fd = -1; f->unlim = -1; f->fmt = 4;
+  f->h5 = h5r_open(path, err, errlen);
+  if (!f->h5) { free(f); return NULL; }
+  nds = h5r_ndsets(f->h5);
+  dim_of_ds = (int *)malloc((size_t)(nds + 1) * sizeof(int));
+  is_var = (int *)calloc((size_t)(nds + 1), sizeof(int));
+  f->dims = (Dim *)calloc((size_t)(nds + 1) * (NC3_MAX_DIMS + 1), sizeof(Dim));     /* scales + phony dimensions */
+  f->vars = (Var *)calloc((size_t)(nds + 1), sizeof(Var));
+  f->h5ds = (int *)malloc((size_t)(nds + 1) * sizeof(int));
+  /* dimensions: the dimension scales, numbered by _Netcdf4Dimid where the file carries it, else in creation order */
+  {
+    int nscale = 0, have_ids = 1;
+    for (i = 0; i < nds; ++i) {
+      const h5r_dset *d = h5r_dset_at(f->h5, i);
+      const h5r_att *cls = h5_find_att(d, "CLASS");
+      dim_of_ds[i] = -1;
+      if (cls && cls->type.cls == H5R_STRING && cls->data_len >= 15 && !strncmp((const char *)cls->data, "DIMENSION_SCALE", 15) && d->rank >= 1) {
+        const h5r_att *id = h5_find_att(d, "_Netcdf4Dimid");
+        dim_of_ds[i] = nscale++;
+        if (!id || id->type.cls != H5R_INT || id->nelem < 1) have_ids = 0;
+      }
+    }
+    if (have_ids)
+      for (i = 0; i < nds; ++i) if (dim_of_ds[i] >= 0) {
+        const h5r_att *id = h5_find_att(h5r_dset_at(f->h5, i), "_Netcdf4Dimid");
+        unsigned char tmp[8] = {0};
+        memcpy(tmp, id->data, (size_t)(id->type.size <= 8 ? id->type.size : 8));
+        if (id->type.big_endian) h5_swap_elems(tmp, 1, id->type.size);
+        dim_of_ds[i] = (int)h5_elem(tmp, &id->type);
+        if (dim_of_ds[i] < 0 || dim_of_ds[i] >= nscale) { if (err) snprintf(err, errlen, "nc3_open: %s: _Netcdf4Dimid %d of %s is out of range", path, dim_of_ds[i], h5r_dset_at(f->h5, i)->name); goto done; }
+      }
+    f->ndims = nscale;
+    for (i = 0; i < nds; ++i) if (dim_of_ds[i] >= 0) {
+      const h5r_dset *d = h5r_dset_at(f->h5, i);
+      const h5r_att *nm = h5_find_att(d, "NAME");
+      Dim *dm = &f->dims[dim_of_ds[i]];
+      const char *name = d->name;
+      if (dm->name) { if (err) snprintf(err, errlen, "nc3_open: %s: two dimensions carry the id %d", path, dim_of_ds[i]); goto done; }
+      if (!strncmp(name, NON_COORD, sizeof NON_COORD - 1)) name += sizeof NON_COORD - 1;
+      dm->name = strdup(name); dm->len = d->dims[0];
+      if (d->maxdims[0] < 0 && f->unlim < 0) f->unlim = dim_of_ds[i];
+      is_var[i] = !(nm && nm->type.cls == H5R_STRING && nm->data_len >= sizeof NOT_A_VAR - 1 &&
+                    !strncmp((const char *)nm->data, NOT_A_VAR, sizeof NOT_A_VAR - 1));
+    } else is_var[i] = 1;
+  }
+  /* variables, in creation order (h5r sorts the links by it) */
+  for (i = 0; i < nds; ++i) {
+    const h5r_dset *d = h5r_dset_at(f->h5, i);
+    const h5r_att *dl = h5_find_att(d, "DIMENSION_LIST");
+    Var *v;
+    const char *name = d->name;
+    if (!is_var[i]) continue;
+    v = &f->vars[f->nvars];
+    v->type = h5_nc_type(&d->type);
+    if (!v->type || d->rank > NC3_MAX_DIMS) continue;      /* not expressible in the classic model: invisible, like a group */
+    if (!strncmp(name, NON_COORD, sizeof NON_COORD - 1)) name += sizeof NON_COORD - 1;
+    v->name = strdup(name); v->ndims = d->rank;
+    for (k = 0; k < d->rank; ++k) {
+      int dimid = -1, j;
+      if (dim_of_ds[i] >= 0 && d->rank == 1) dimid = dim_of_ds[i];                   /* a coordinate variable is its own scale */
+      else if (dl && k < dl->ndimrefs)
+        for (j = 0; j < nds; ++j) if (dim_of_ds[j] >= 0 && h5r_dset_at(f->h5, j)->addr == dl->dimrefs[k]) { dimid = dim_of_ds[j]; break; }
+      if (dimid < 0) {                                     /* no scale attached (a plain HDF5 file): a dimension per length */
+        char nm[48];
+        for (j = 0; j < f->ndims; ++j) if (!strncmp(f->dims[j].name, "phony_dim_", 10) && f->dims[j].len == d->dims[k]) { dimid = j; break; }
+        if (dimid < 0) { dimid = f->ndims++; snprintf(nm, sizeof nm, "phony_dim_%d", dimid); f->dims[dimid].name = strdup(nm); f->dims[dimid].len = d->dims[k]; }
+      }
+      v->dimids[k] = dimid;
+      if (dimid == f->unlim && d->dims[k] > f->dims[dimid].len) f->dims[dimid].len = d->dims[k];
+    }
+    v->isrec = (v->ndims > 0 && v->dimids[0] == f->unlim);
+    for (k = 0; k < d->natts; ++k) if (!h5_hidden_att(d->atts[k].name) && h5_add_att(&v->natts, &v->atts, &d->atts[k])) goto done;
+    f->h5ds[f->nvars++] = i;
+  }
+  for (k = 0; k < h5r_ngatts(f->h5); ++k) {
+    const h5r_att *a = h5r_gatt_at(f->h5, k);
+    if (!h5_hidden_att(a->name) && h5_add_att(&f->ngatts, &f->gatts, a)) goto done;
+  }
+  if (f->unlim >= 0) { f->numrecs = f->dims[f->unlim].len; f->dims[f->unlim].len = 0; }
+  ok = 1;
+done:
+  free(dim_of_ds); free(is_var);
+  if (!ok) { h5r_close(f->h5); free(f->h5ds); free_meta(f); free(f); return NULL; }
+  return f;
+}
+
+static int h5_slab(nc3_file *f, int varid, const size_t *start, const size_t *count, void *host, int kind)
+{
+  const Var *v = &f->vars[varid];
+  const h5r_dset *d = h5r_dset_at(f->h5, f->h5ds[varid]);
+  size_t total = 1, i, st[NC3_MAX_DIMS], ct[NC3_MAX_DIMS];
+  int k;
+  unsigned char *tmp;
+  if ((kind == K_TEXT) != (v->type == NC3_CHAR)) return fail(f, "nc3: %s: text/numeric access mismatch", v->name);
+  /* the request in terms of the netCDF dimensions (what the caller sized its buffer by); h5r_read checks it against the
+   * dataset's own extent */
+  for (k = 0; k < v->ndims; ++k) {
+    const long long len = (v->dimids[k] == f->unlim) ? f->numrecs : f->dims[v->dimids[k]].len;
+    st[k] = start ? start[k] : 0;
+    ct[k] = count ? count[k] : (size_t)len;
+    if ((long long)(st[k] + ct[k]) > len) return fail(f, "nc3: %s: start+count exceeds dimension %s", v->name, f->dims[v->dimids[k]].name);
+    total *= ct[k];
+  }
+  start = st; count = ct;
+  if (total == 0) return 0;
+  if (kind == K_TEXT) {
+    if (d->type.cls != H5R_STRING || d->type.size != 1) return fail(f, "nc3: %s: text stored as strings of %d bytes is not a classic char variable", v->name, d->type.size);
+    if (h5r_read(f->h5, f->h5ds[varid], start, count, host)) return fail(f, "%s", h5r_strerror(f->h5));
+    return 0;
+  }
+  if (kind == K_DOUBLE && d->type.cls == H5R_FLOAT && d->type.size == 8) {              /* the common case, in place */
+    if (h5r_read(f->h5, f->h5ds[varid], start, count, host)) return fail(f, "%s", h5r_strerror(f->h5));
+    return 0;
+  }
+  if (kind == K_INT && d->type.cls == H5R_INT && d->type.size == 4 && d->type.is_signed) {
+    if (h5r_read(f->h5, f->h5ds[varid], start, count, host)) return fail(f, "%s", h5r_strerror(f->h5));
+    return 0;
+  }
+  tmp = (unsigned char *)malloc(total * (size_t)d->type.size);
+  if (!tmp) return fail(f, "nc3: out of memory");
+  if (h5r_read(f->h5, f->h5ds[varid], start, count, tmp)) { free(tmp); return fail(f, "%s", h5r_strerror(f->h5)); }
+  for (i = 0; i < total; ++i) {
+    const double x = h5_elem(tmp + i * (size_t)d->type.size, &d->type);
+    if (kind == K_DOUBLE) ((double *)host)[i] = x; else ((int *)host)[i] = (int)x;
+  }
+  free(tmp);
+  return 0;
 }

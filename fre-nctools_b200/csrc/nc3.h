@@ -5,7 +5,9 @@
  * (mpp_io.c:163-175, 1526-1540).  This file implements exactly that on-disk format (the netCDF classic format
  * specification: big-endian header of dimension, attribute and variable lists, then the fixed-size variables in
  * definition order, then the records), so files written here are readable by libnetcdf and vice versa.  netCDF-4
- * (HDF5) files are recognised by their magic number and refused with a clear message.
+ * (HDF5) files — the reference's default (mpp_io.c:52) — are recognised by their magic number and READ through h5r.c behind
+ * these same calls (nc3_format() == 4; dimensions from the dimension scales, variables in creation order, int64 and wide
+ * unsigned data as NC3_DOUBLE); they are never written.
  *
  * Not thread-safe per file; all functions return 0 on success and a negative value on error with the message
  * available from nc3_strerror(f) (or the err buffer of nc3_open / nc3_create).
@@ -26,7 +28,7 @@ typedef struct nc3_file nc3_file;
 
 /* ---- reading ---- */
 nc3_file *nc3_open(const char *path, char *err, size_t errlen);
-int nc3_format(const nc3_file *f);                        /* 1, 2 or 5 */
+int nc3_format(const nc3_file *f);                        /* 1, 2 or 5; 4 for a netCDF-4 file */
 int nc3_ndims(const nc3_file *f);
 int nc3_nvars(const nc3_file *f);
 int nc3_dim_id(const nc3_file *f, const char *name);      /* -1 if absent */

@@ -97,8 +97,8 @@ int create_xgrid_2dx1d_order2_(const int *, const int *, const int *, const int 
  *   setup_conserve_interp (conserve_interp.c:42): the generate branch for all (output, input) tile pairs; interp[n].* are
  *     malloc'ed like the reference does (:238-258).  Order 2 with several output tiles sums the exchange cells of every
  *     output tile per source cell before the centroid correction, like :204-221 / :319-358.  READ (:62-125) and WRITE
- *     (:368-443) go through the classic-netCDF remap-file reader / writer of Part 4 (CDF-1/2/5; netCDF-4/HDF5 files are
- *     recognised and refused by name).
+ *     (:368-443) go through the classic-netCDF remap-file reader / writer of Part 4 (CDF-1/2/5 read and written; netCDF-4/HDF5
+ *     files are read through csrc/h5r.c, not written).
  *   do_scalar_conserve_interp (conserve_interp.c:507): order 1 / order 2 per variable (interp_method), missing values,
  *     MONOTONIC, any nz; weight fields, cell_methods sum, cell_measures and TARGET as in :535-539, :572-585, :841-865. */
 void setup_conserve_interp(int ntiles_in, const void *grid_in /* const Grid_config* */, int ntiles_out,
@@ -377,8 +377,8 @@ void xgb_poly_moments_site_host(int order, int n, const double *x, const double 
 /* ------------------------------------------------------------------------------------------
  * Part 4 — remap files (host side).  The file fregrid writes after weight generation and reads back with
  * --remap_file (conserve_interp.c:382-438; read_mosaic.c:330-560), in the classic netCDF formats fregrid's
- * --format option names (classic, 64bit_offset; mpp_io.c:1526-1540) plus CDF-5.  netCDF-4/HDF5 files are refused with a
- * message.  Layout: dims string=255, ncells, two=2; int tile1(ncells), int tile1_cell(ncells,two),
+ * --format option names (classic, 64bit_offset; mpp_io.c:1526-1540) plus CDF-5.  netCDF-4/HDF5 files (the reference's default,
+ * mpp_io.c:52) are read through csrc/h5r.c behind the same calls; writing them is refused with a message.  Layout: dims string=255, ncells, two=2; int tile1(ncells), int tile1_cell(ncells,two),
  * int tile2_cell(ncells,two), double xgrid_area(ncells) [m2], double tile1_distance(ncells,two) (order 2); 1-based on
  * disk, 0-based in memory.  setup_conserve_interp honours READ / WRITE through these.
  * ---------------------------------------------------------------------------------------- */

@@ -36,5 +36,11 @@ with torch.cuda.stream(st):
     e1.record()
 torch.cuda.synchronize()
 _, ph, ngen = plan.phase_ms()
-print(json.dumps({"rank": rank, "world": world, "wpr": WPR, "nxgrid": int(n), "ms_per_step": e0.elapsed_time(e1) / steps,
+import hashlib  # noqa: E402
+res = plan.result_host()
+h = hashlib.md5()
+for k in sorted(res):
+    h.update(res[k].tobytes())
+print(json.dumps({"rank": rank, "world": world, "wpr": WPR, "nxgrid": int(n), "ms_per_step": e0.elapsed_time(e1) / steps, "md5": h.hexdigest(),
+                  "heavy_stage": os.environ.get("XGB_HEAVY_STAGE", "1"),
                   "phase_ms": {k: round(v / max(ngen, 1), 4) for k, v in ph.items()}}))

@@ -418,3 +418,41 @@ def test_fregrid_b200_against_the_unmodified_reference_fregrid(pkg, dataset):
                 assert np.array_equal(xa == MISSING, xb == MISSING), name
                 assert np.max(np.abs(xa[m] - xb[m]) / np.maximum(np.abs(xa[m]), 1e-30), initial=0.0) <= tol, (order, name)
         ga.close(); gb.close()
+
+
+def test_netcdf4_inputs_give_the_same_output_files(pkg, dataset, tmp_path):
+    """The reference's default file format (NC_FORMAT_NETCDF4_CLASSIC, mpp_io.c:52): the mosaic, the six supergrids and the six
+    field files re-expressed as netCDF-4 by tests/h5_writer.py (both libnetcdf layouts, the field files chunked, shuffled and
+    deflated like FRE history files) -> output and remap files byte-identical to the run on the classic files; then the remap
+    file itself as netCDF-4 through the READ branch."""
+    import h5_writer
+    ds = dataset
+    n = ds["n"]
+    d4 = str(tmp_path)
+    names = [f"C{n}_mosaic.nc"] + [f"C{n}_grid.tile{t + 1}.nc" for t in range(6)] + [f"atmos.tile{t + 1}.nc" for t in range(6)]
+    for k, name in enumerate(names):
+        field = name.startswith("atmos")
+        h5_writer.from_classic(os.path.join(ds["dir"], name), os.path.join(d4, name), style=("v18", "earliest")[k % 2],
+                               chunk=16 if field else None, deflate=3 if field else 0, shuffle=field)
+        assert open(os.path.join(d4, name), "rb").read(4) == b"\x89HDF"
+    args = ["--input_mosaic", f"C{n}_mosaic.nc", "--nlon", "48", "--nlat", "24", "--input_file", "atmos", "--scalar_field", "temp,ps,orog",
+            "--interp_method", "conserve_order2", "--output_file", "o_h5.nc", "--remap_file", "r_h5.nc"]
+
+    def run(cwd, a):
+        r = subprocess.run([_exe(pkg)] + a, cwd=cwd, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+        return r.stdout
+    run(ds["dir"], args)
+    run(d4, args)
+    for name in ("o_h5.nc", "r_h5.nc"):
+        assert open(os.path.join(ds["dir"], name), "rb").read() == open(os.path.join(d4, name), "rb").read(), name
+    # READ branch: the same remap file as netCDF-4 against the classic one
+    h5_writer.from_classic(os.path.join(d4, "r_h5.nc"), os.path.join(d4, "r4.nc"), style="v18", chunk=4096, deflate=1)
+    a_read = args[:-3] + ["o_read3.nc", "--remap_file", "r_h5.nc"]
+    b_read = args[:-3] + ["o_read4.nc", "--remap_file", "r4.nc"]
+    assert "Finish reading index and weight" in run(d4, a_read)
+    assert "Finish reading index and weight" in run(d4, b_read)
+    g3 = netcdf_file(os.path.join(d4, "o_read3.nc"), "r", mmap=False); g4 = netcdf_file(os.path.join(d4, "o_read4.nc"), "r", mmap=False)
+    for v in ("temp", "ps", "orog"):
+        assert np.array_equal(g3.variables[v][:], g4.variables[v][:]), v
+    g3.close(); g4.close()

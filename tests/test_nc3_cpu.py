@@ -1,7 +1,7 @@
 """csrc/nc3.c (classic netCDF CDF-1 / CDF-2 / CDF-5 reader and writer) against scipy.io.netcdf_file, an independent implementation
 of the same on-disk format: files written by either side are read by the other; fixed and record variables, every classic type,
 strided hyperslabs ((n, 2) column writes like the reference's remap-file writer, conserve_interp.c:405-437), attributes, a
-byte-for-byte comparison where scipy keeps the definition order, and the netCDF-4/HDF5 refusal."""
+byte-for-byte comparison where scipy keeps the definition order, and the hand-over of HDF5 files to csrc/h5r.c."""
 import ctypes as C
 import os
 
@@ -138,13 +138,16 @@ def test_fixed_size_file_is_byte_identical_to_scipys(L, tmp_path):
     assert open(p1, 'rb').read() == open(p2, 'rb').read()
 
 
-def test_netcdf4_is_refused_by_name(L, tmp_path):
+def test_netcdf4_goes_to_the_hdf5_reader(L, tmp_path):
+    """an HDF5 signature hands the file to csrc/h5r.c (tests/test_h5_cpu.py); an empty shell is refused with its message"""
     d = str(tmp_path)
     err = C.create_string_buffer(256)
-    # HDF5 refusal
     open(os.path.join(d,'h.nc'),'wb').write(b'\x89HDF\r\n\x1a\n'+b'\0'*100)
     assert not L.nc3_open(os.path.join(d, 'h.nc').encode(), err, 256)
-    assert b'netCDF-4/HDF5' in err.value
+    assert b'h5r' in err.value
+    open(os.path.join(d,'x.nc'),'wb').write(b'GRIB'+b'\0'*100)
+    assert not L.nc3_open(os.path.join(d, 'x.nc').encode(), err, 256)
+    assert b'not a classic netCDF file' in err.value
 
 
 def test_corrupt_headers_are_refused(L, tmp_path):

@@ -174,12 +174,21 @@ def test_scipy_reads_what_the_product_writes_and_errors_are_loud(pkg, reflib, tm
     back = _read(pkg, path, 2)
     assert open(path, "rb").read(4) == b"CDF\x05" and np.array_equal(back["i_out"], ref["i_out"]) and np.array_equal(back["dj"], ref["dj"])
     L.xgb_set_nc_format(b"64bit_offset")
-    # netCDF-4 is refused by name, on write and on read
+    # netCDF-4 is refused by name on write; on read it goes through csrc/h5r.c (the reference's default format, mpp_io.c:52)
     assert L.xgb_set_nc_format(b"netcdf4") != 0 and b"HDF5" in L.xgb_last_error()
     assert L.xgb_set_nc_format(b"bogus") != 0 and b"not a valid option" in L.xgb_last_error()
     h5 = str(tmp_path / "h5.nc")
     open(h5, "wb").write(b"\x89HDF\r\n\x1a\n" + bytes(64))
-    assert L.xgb_remap_size(h5.encode()) < 0 and b"netCDF-4/HDF5" in L.xgb_last_error()
+    assert L.xgb_remap_size(h5.encode()) < 0 and b"h5r" in L.xgb_last_error()
+    import h5_writer
+    for style in ("v18", "earliest"):
+        for o in (1, 2):
+            classic = str(tmp_path / f"c{o}.nc")
+            _write(pkg, classic, o, ref)
+            h5_writer.from_classic(classic, h5, style=style, chunk=1000, deflate=1, shuffle=True)
+            assert open(h5, "rb").read(4) == b"\x89HDF"
+            a, b = _read(pkg, classic, o), _read(pkg, h5, o)
+            assert sorted(a) == sorted(b) and all(np.array_equal(a[k], b[k]) for k in a)
     assert L.xgb_remap_size(str(tmp_path / "missing.nc").encode()) < 0 and b"cannot open" in L.xgb_last_error()
 
 
