@@ -428,6 +428,38 @@ def run_gpu_arm(args):
     use_async = args.async_steps or (world > 1 and not args.sync_steps)
     plan.generate(opcode)                           # sizes the buffers for this rank's windows (untimed)
 
+    # ---- N > 1: cost-balanced windows (set-up, untimed).  Equal pair counts are not equal times: the ranks that own a pole spend
+    # longer per pair (pole-cap enumeration by one warp, the pole cell's sequential sums).  Every rank measures the device time
+    # of its share, the times are all-gathered, and the windows are re-cut with each rank's share of the pairs scaled by
+    # mean(t) / t_rank (distributed.rebalance_shares -> xgb_plan_partition_shares); a few rounds settle it.  The plan that
+    # results is static: the timed region below runs it unchanged, and the parity check after it covers the re-cut windows.
+    balance = None
+    if world > 1 and args.balance_rounds > 0:
+        from importlib import import_module
+        dmod = import_module(pkg.__name__ + ".distributed")
+        shares = [1.0 / (world * WPR)] * (world * WPR)
+        hist = []
+        for _ in range(args.balance_rounds):
+            plan.reset_phase_ms()
+            for _k in range(3):
+                plan.generate(opcode)
+            _, acc, ngen = plan.phase_ms()
+            tt = torch.tensor([sum(acc.values()) / max(ngen, 1)], dtype=torch.float64, device=dev)
+            allt = torch.empty(world, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(allt, tt)
+            rank_ms = [float(v) for v in allt.tolist()]
+            hist.append([round(v, 4) for v in rank_ms])
+            if max(rank_ms) <= 1.02 * min(rank_ms):
+                break
+            shares = dmod.rebalance_shares(shares, rank_ms, world)
+            bounds = plan.partition(world * WPR, shares)
+            my_windows = [(bounds[w], bounds[w + 1]) for w in range(rank, world * WPR, world)]
+            set_windows()
+            plan.generate(opcode)                   # sizes the buffers for the new windows
+        per_rank_share = [sum(shares[r::world]) for r in range(world)]
+        balance = {"rounds": len(hist), "rank_device_ms_per_round": hist, "pair_share_per_rank": [round(v, 4) for v in per_rank_share],
+                   "how": "windows re-cut by xgb_plan_partition_shares from the ranks' measured device time (set-up, untimed)"}
+
     def step():
         if use_async:
             plan.generate_async(opcode)
@@ -641,7 +673,7 @@ def run_gpu_arm(args):
                     "api": f"xgb_plan_set_dst_latlon + xgb_plan_set_src_sharded (pinned host source grid, each rank its own rows) + "
                            f"xgb_plan_generate_to_host in {args.e2e_chunks} pieces (pinned host result); bytes are whole-job sums over the ranks"},
             "roofline": roofline, "phase_ms": phases, "per_rank": per_rank, "cpu_baseline": cpu, "apply": apply,
-            "parity_checked_xcells": parity_checked, "multi_gpu_parity": multi_parity, "great_circle": gc}
+            "parity_checked_xcells": parity_checked, "multi_gpu_parity": multi_parity, "balance": balance, "great_circle": gc}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -658,6 +690,8 @@ def main():
     ap.add_argument("--async-steps", action="store_true",
                     help="xgb_plan_generate_async per step + one generate_finish after the timed region instead of the blocking call")
     ap.add_argument("--sync-steps", action="store_true", help="blocking xgb_plan_generate per step also for N > 1 (default there: asynchronous steps)")
+    ap.add_argument("--balance-rounds", type=int, default=3,
+                    help="N > 1: rounds of measured cost balancing of the source windows before the timed region (0: equal pair counts)")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="pieces of the end-to-end generate (download overlapped with compute)")
     ap.add_argument("--no-apply", action="store_true", help="skip the apply-GB/s leg (configs[1])")
     ap.add_argument("--no-gc", action="store_true", help="skip the great-circle leg (configs[2])")

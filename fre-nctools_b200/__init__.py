@@ -74,6 +74,7 @@ def lib():
     L.xgb_plan_set_src_window.argtypes = [vp, C.c_longlong, C.c_longlong]
     L.xgb_plan_set_src_sharded.argtypes = [vp, C.c_int, _ip, _ip, vp, vp, vp, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     L.xgb_plan_partition.argtypes = [vp, C.c_int, C.POINTER(C.c_longlong)]
+    L.xgb_plan_partition_shares.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     L.xgb_plan_set_src_windows.argtypes = [vp, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     L.xgb_plan_window_counts.argtypes = [vp, C.POINTER(C.c_longlong)]
     L.xgb_plan_generate_async.argtypes = [vp, C.c_uint]
@@ -309,9 +310,16 @@ class XgridPlan:
         self._ck(self._L.xgb_plan_window_counts(self._p, c))
         return [int(v) for v in c]
 
-    def partition(self, nparts):
+    def partition(self, nparts, shares=None):
+        """bounds of nparts contiguous source-cell windows: equal candidate-pair counts, or pair counts in the proportions `shares`"""
         b = (C.c_longlong * (nparts + 1))()
-        self._ck(self._L.xgb_plan_partition(self._p, nparts, b))
+        if shares is None:
+            self._ck(self._L.xgb_plan_partition(self._p, nparts, b))
+        else:
+            if len(shares) != nparts:
+                raise ValueError("partition: one share per window")
+            sh = (C.c_double * nparts)(*[float(v) for v in shares])
+            self._ck(self._L.xgb_plan_partition_shares(self._p, nparts, sh, b))
         return [int(v) for v in b]
 
     def generate(self, opcode):

@@ -487,18 +487,42 @@ static int count_candidates(xgb_plan* p, const SrcMap& sm, unsigned long long* t
   return 0;
 }
 
-extern "C" int xgb_plan_partition(xgb_plan* p, int nparts, long long* bounds)
+extern "C" int xgb_plan_partition_shares(xgb_plan* p, int nparts, const double* share, long long* bounds)
 {
   if (!p || !p->have_src || !p->have_dst || nparts <= 0 || !bounds) { xgb_set_error("xgb_plan_partition: bad arguments"); return 1; }
   CU_OK(cudaSetDevice(p->device));
   unsigned long long total = 0;
   const long long nc = p->src.ncell;
   if (count_candidates(p, single_window(0, nc), &total)) return 1;
-  if (p->bounds_dev.reserve((size_t)(nparts + 1) * sizeof(long long))) return 1;
-  launch_partition((const uint32_t*)p->pair_off.p, nc, total, nparts, (long long*)p->bounds_dev.p, p->st);
+  if (p->bounds_dev.reserve((size_t)(nparts + 1) * sizeof(long long) + (size_t)(nparts + 1) * sizeof(unsigned long long))) return 1;
+  unsigned long long* targets_dev = nullptr;
+  std::vector<unsigned long long> targets;
+  if (share) {                                   // window k ends where the running pair count reaches its cumulative share
+    double sum = 0.0, run = 0.0;
+    for (int k = 0; k < nparts; ++k) {
+      if (!(share[k] > 0.0) || !(share[k] < 1e300)) { xgb_set_error("xgb_plan_partition_shares: share[%d] is not a positive number", k); return 1; }
+      sum += share[k];
+    }
+    targets.assign((size_t)nparts + 1, 0ull);
+    for (int k = 1; k < nparts; ++k) {
+      run += share[k - 1];
+      targets[k] = (unsigned long long)((double)total * (run / sum));
+      if (targets[k] > total) targets[k] = total;
+      if (targets[k] < targets[k - 1]) targets[k] = targets[k - 1];
+    }
+    targets[nparts] = total;
+    targets_dev = (unsigned long long*)((long long*)p->bounds_dev.p + nparts + 1);
+    CU_OK(cudaMemcpyAsync(targets_dev, targets.data(), targets.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, p->st));
+  }
+  launch_partition((const uint32_t*)p->pair_off.p, nc, total, nparts, (long long*)p->bounds_dev.p, p->st, targets_dev);
   CU_OK(cudaMemcpyAsync(bounds, p->bounds_dev.p, (size_t)(nparts + 1) * sizeof(long long), cudaMemcpyDeviceToHost, p->st));
   CU_OK(cudaStreamSynchronize(p->st));
   return 0;
+}
+
+extern "C" int xgb_plan_partition(xgb_plan* p, int nparts, long long* bounds)
+{
+  return xgb_plan_partition_shares(p, nparts, nullptr, bounds);
 }
 
 // One window [s0, s0+ns) of source cells: candidate search, clip, ordered compaction, order-2 correction.

@@ -2445,13 +2445,14 @@ void launch_exclusive_scan(const uint32_t* in, uint32_t* out, long long n, unsig
 // =============================================================================================
 namespace xgb {
 __global__ void partition_kernel(const uint32_t* __restrict__ pair_off, long long ncell, unsigned long long total,
-                                 int nparts, long long* __restrict__ bounds)
+                                 int nparts, long long* __restrict__ bounds, const unsigned long long* __restrict__ targets)
 {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k > nparts) return;
   if (k == 0) { bounds[0] = 0; return; }
   if (k == nparts) { bounds[nparts] = ncell; return; }
-  const unsigned long long target = (total / (unsigned long long)nparts) * (unsigned long long)k;
+  // targets: the caller's cumulative shares of the pair total (xgb_plan_partition_shares); else equal parts
+  const unsigned long long target = targets ? targets[k] : (total / (unsigned long long)nparts) * (unsigned long long)k;
   long long lo = 0, hi = ncell;                 // first index with pair_off[idx] >= target
   while (lo < hi) {
     const long long mid = (lo + hi) >> 1;
@@ -2461,10 +2462,10 @@ __global__ void partition_kernel(const uint32_t* __restrict__ pair_off, long lon
 }
 
 void launch_partition(const uint32_t* pair_off, long long ncell, unsigned long long total, int nparts,
-                      long long* bounds, cudaStream_t st)
+                      long long* bounds, cudaStream_t st, const unsigned long long* targets)
 {
   ++g_launches;
-  partition_kernel<<<(nparts + 1 + 63) / 64, 64, 0, st>>>(pair_off, ncell, total, nparts, bounds);
+  partition_kernel<<<(nparts + 1 + 63) / 64, 64, 0, st>>>(pair_off, ncell, total, nparts, bounds, targets);
 }
 }  // namespace xgb
 

@@ -96,5 +96,5 @@ void xgb_apply_release(xgb_plan* p);                           // apply_capi.cu
 namespace xgb {
 extern long long g_launches;     // kernels launched by this library since load (xgrid_kernels.cu)
 void launch_partition(const uint32_t* pair_off, long long ncell, unsigned long long total, int nparts,
-                      long long* bounds, cudaStream_t st);
+                      long long* bounds, cudaStream_t st, const unsigned long long* targets = nullptr);
 }

@@ -60,15 +60,41 @@ def shard_field_levels(nfields, group=None):
     return list(range(rank, nfields, world))
 
 
-def window_bounds_from_counts(pair_counts, nparts):
+def window_bounds_from_counts(pair_counts, nparts, shares=None):
     """Host mirror of the device partition (csrc/xgrid_kernels.cu partition_kernel): bounds[k] = first source cell whose
-    exclusive candidate-pair offset reaches k * (total // nparts).  pair_counts: 1-D integer tensor/array."""
+    exclusive candidate-pair offset reaches k * (total // nparts) — or, with shares (xgb_plan_partition_shares), the
+    cumulative share of the total.  pair_counts: 1-D integer tensor/array."""
     c = torch.as_tensor(pair_counts, dtype=torch.int64)
     off = torch.cumsum(c, 0) - c
     total = int(c.sum())
     b = [0]
+    run, ssum, prev = 0.0, (float(sum(shares)) if shares is not None else 0.0), 0
     for k in range(1, nparts):
-        target = (total // nparts) * k
+        if shares is None:
+            target = (total // nparts) * k
+        else:
+            run += float(shares[k - 1])
+            target = max(prev, min(total, int(float(total) * (run / ssum))))
+            prev = target
         b.append(int(torch.searchsorted(off, torch.tensor(target), right=False)))
     b.append(int(c.numel()))
     return b
+
+
+def rebalance_shares(shares, rank_ms, world, damping=1.0, floor=0.25):
+    """Cost-balanced sharding.  Windows are dealt round-robin (window w belongs to rank w % world) and sized by
+    candidate-pair count, but a pair is not a fixed cost: the ranks that own a pole spend longer per pair (one warp
+    enumerates a pole cap's rows, the pole cell's thousands of exchange cells are summed sequentially to stay
+    bit-identical).  Given the device time every rank measured for its share, scale each rank's windows by
+    mean(t) / t_rank (damped, bounded below) and renormalise: the next partition gives a slow rank fewer pairs.
+    shares: one positive number per window; rank_ms: one time per rank.  Pure arithmetic, identical on every rank."""
+    t = [float(v) for v in rank_ms]
+    if len(t) != world or min(t) <= 0.0 or len(shares) % world:
+        return list(shares)
+    mean = sum(t) / world
+    out = []
+    for w, s in enumerate(shares):
+        f = (mean / t[w % world]) ** damping
+        out.append(max(float(s) * f, floor * float(s)))
+    tot = sum(out)
+    return [v / tot for v in out]

@@ -174,6 +174,11 @@ int xgb_plan_window_counts(xgb_plan *p, long long *counts);
 /* Split the source cells into nparts contiguous windows of (nearly) equal candidate-pair count.
  * bounds receives nparts+1 cell indices (bounds[0] = 0, bounds[nparts] = ncells). */
 int xgb_plan_partition(xgb_plan *p, int nparts, long long *bounds);
+/* The same with unequal parts: window k receives share[k] / sum(share) of the candidate pairs (share == NULL: equal parts).
+ * For cost-balanced sharding: a pair in a pole cap costs more than a mid-latitude pair (one warp enumerates the cap's rows,
+ * its exchange cells are summed sequentially), so the rank that owns a pole is given fewer pairs
+ * (fre-nctools_b200/distributed.py rebalance_shares; replaces the equal-rows decomposition of fregrid_util.c:489-492). */
+int xgb_plan_partition_shares(xgb_plan *p, int nparts, const double *share, long long *bounds);
 
 /* Generate the exchange grid of the current window.  opcode: XGB_CONSERVE_ORDER1 or
  * XGB_CONSERVE_ORDER2, optionally | XGB_GREAT_CIRCLE.  Returns nxgrid (>= 0) or -1.

@@ -5,6 +5,7 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -89,3 +90,32 @@ def test_single_process_defaults():
     assert D.exchange_offsets(5) == (0, 5, [5])
     assert D.shard_field_levels(3) == [0, 1, 2]
     assert D.window_bounds_from_counts(np.array([1, 1, 1, 1]), 2) == [0, 2, 4]
+
+
+def test_cost_balanced_shares():
+    """rebalance_shares: a rank that measured a longer device time gets a smaller share of the candidate pairs; the host mirror
+    of xgb_plan_partition_shares cuts the windows at the cumulative shares"""
+    xgtest.package()
+    from fre_nctools_b200 import distributed as D
+    world, wpr = 4, 2
+    shares = [1.0 / (world * wpr)] * (world * wpr)
+    assert D.rebalance_shares(shares, [1.0, 1.0, 1.0, 1.0], world) == pytest.approx(shares)
+    new = D.rebalance_shares(shares, [1.3, 1.0, 1.0, 1.2], world)
+    assert sum(new) == pytest.approx(1.0)
+    per_rank = [sum(new[r::world]) for r in range(world)]
+    assert per_rank[0] < per_rank[3] < per_rank[1] == pytest.approx(per_rank[2])
+    assert per_rank[0] / per_rank[1] == pytest.approx(1.0 / 1.3)
+    # a fixed cost plus a cost per pair: repeated rounds converge to equal times
+    fixed = [0.15, 0.0, 0.0, 0.1]
+    s = shares
+    for _ in range(6):
+        t = [fixed[r] + 2.0 * sum(s[r::world]) for r in range(world)]
+        s = D.rebalance_shares(s, t, world)
+    t = [fixed[r] + 2.0 * sum(s[r::world]) for r in range(world)]
+    assert max(t) / min(t) < 1.01
+    # malformed input leaves the shares alone
+    assert D.rebalance_shares(shares, [1.0, 0.0, 1.0, 1.0], world) == shares and D.rebalance_shares(shares, [1.0], world) == shares
+    counts = np.array([4, 4, 4, 4, 4, 4, 4, 4])
+    assert D.window_bounds_from_counts(counts, 2, [1.0, 1.0]) == D.window_bounds_from_counts(counts, 2) == [0, 4, 8]
+    assert D.window_bounds_from_counts(counts, 2, [1.0, 3.0]) == [0, 2, 8]
+    assert D.window_bounds_from_counts(counts, 4, [1.0, 1.0, 2.0, 4.0]) == [0, 1, 2, 4, 8]

@@ -403,6 +403,29 @@ def test_interleaved_windows_reassemble_to_serial_list(pkg):
     for key in full:
         cat = np.concatenate([pieces[w][key] for w in range(nparts)])
         assert np.array_equal(cat, full[key]), key
+    # cost-balanced windows (xgb_plan_partition_shares): equal shares are the plain partition, unequal shares move the cuts
+    # to the cumulative shares of the pair count, and the pieces still reassemble to the serial list
+    assert plan.partition(nparts, [1.0] * nparts) == b or max(abs(x - y) for x, y in zip(plan.partition(nparts, [1.0] * nparts), b)) <= 1
+    shares = [0.5 if w in (0, nparts - 1) else 1.0 for w in range(nparts)]
+    plan.set_src_window(0, plan.ncell_src)
+    plan.generate(2)
+    bs = plan.partition(nparts, shares)
+    assert bs[0] == 0 and bs[-1] == plan.ncell_src and all(x <= y for x, y in zip(bs, bs[1:])) and bs != b
+    pieces = {}
+    for rank in range(world):
+        plan.set_src_windows([(bs[w], bs[w + 1]) for w in range(rank, nparts, world)])
+        n = plan.generate(2)
+        r = plan.result_host()
+        counts = plan.window_counts()
+        off = 0
+        for k, w in enumerate(range(rank, nparts, world)):
+            pieces[w] = {key: v[off:off + counts[k]] for key, v in r.items()}
+            off += counts[k]
+    for key in full:
+        assert np.array_equal(np.concatenate([pieces[w][key] for w in range(nparts)]), full[key]), key
+    small = sum(len(pieces[w]["area"]) for w in (0, nparts - 1)) / 2.0
+    mid = sum(len(pieces[w]["area"]) for w in range(1, nparts - 1)) / (nparts - 2.0)
+    assert 0.35 < small / mid < 0.65
     # the host-download path works on several windows too
     wins = [(b[w], b[w + 1]) for w in range(0, nparts, 2)]
     plan.set_src_windows(wins)
