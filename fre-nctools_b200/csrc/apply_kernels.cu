@@ -499,28 +499,86 @@ __host__ __device__ __forceinline__ long long rec_index(long long cell, int f, i
 constexpr int kRecFields = 8;      // field-levels a gradient block transposes at a time
 constexpr int kRecChunk = 32;      // field-levels per gradient block
 
+#ifndef XGB_GRAD_UNROLL
+#define XGB_GRAD_UNROLL 1
+#endif
+#ifndef XGB_GRAD_BLOCKS
+#define XGB_GRAD_BLOCKS 0
+#endif
+#if XGB_GRAD_BLOCKS > 0
+#define XGB_GRAD_BOUNDS __launch_bounds__(128, XGB_GRAD_BLOCKS)
+#else
+#define XGB_GRAD_BOUNDS __launch_bounds__(128)
+#endif
+constexpr int kGradUnroll = XGB_GRAD_UNROLL;
+// XGB_GRAD_SPLIT: threads are dealt the INTERIOR cells of all tiles first (every corner of such a cell is the plain four-point
+// average, gradient_c2l.c:163-166: nine loads, no case analysis), then the cells on the tiles' rims (a2b_ord2's edge and corner
+// formulas).  With cells in storage order two of the three warps of a 96-cell row held one rim cell and ran both code paths
+// for every field-level; ncu: 373 instructions per (cell, field-level), FP64 pipe 22 %.
+#ifndef XGB_GRAD_SPLIT
+#define XGB_GRAD_SPLIT 1
+#endif
+
+// slot -> (tile, i, j): interior cells of tile 0, 1, ... then rim cells of tile 0, 1, ...; tiles narrower than 3 cells are all rim
+__device__ __forceinline__ bool grad_slot_cell(const GradTile* __restrict__ tiles, int ntiles, long long s, int* t_out, int* i_out, int* j_out)
+{
+  long long rem = s;
+  for (int t = 0; t < ntiles; ++t) {
+    const int nx = tiles[t].nx, ny = tiles[t].ny;
+    const long long cnt = (nx >= 3 && ny >= 3) ? (long long)(nx - 2) * (ny - 2) : 0;
+    if (rem < cnt) { *t_out = t; *i_out = 1 + (int)(rem % (nx - 2)); *j_out = 1 + (int)(rem / (nx - 2)); return true; }
+    rem -= cnt;
+  }
+  for (int t = 0; t < ntiles; ++t) {
+    const int nx = tiles[t].nx, ny = tiles[t].ny;
+    const bool thin = !(nx >= 3 && ny >= 3);
+    const long long cnt = thin ? (long long)nx * ny : 2ll * nx + 2ll * ny - 4;
+    if (rem < cnt) {
+      *t_out = t;
+      if (thin) { *i_out = (int)(rem % nx); *j_out = (int)(rem / nx); }
+      else if (rem < nx) { *i_out = (int)rem; *j_out = 0; }
+      else if (rem < 2ll * nx) { *i_out = (int)(rem - nx); *j_out = ny - 1; }
+      else { const long long k = rem - 2ll * nx; *j_out = 1 + (int)(k >> 1); *i_out = (k & 1) ? nx - 1 : 0; }
+      return false;
+    }
+    rem -= cnt;
+  }
+  *t_out = 0; *i_out = 0; *j_out = 0;
+  return false;
+}
+
 template <bool MISSING>
-__global__ void __launch_bounds__(128)
+__global__ void XGB_GRAD_BOUNDS
 grad_c2l_rec_kernel(const GradTile* __restrict__ tiles, int ntiles, long long ncell, int nf, int nfp,
                     const double* __restrict__ data, long long data_stride, double* __restrict__ rec, double missing)
 {
   constexpr int NC = MISSING ? 4 : 3;
   __shared__ double tile[NC][128][kRecFields + 1];
+  __shared__ long long s_cell[128];
   const long long c0 = (long long)blockIdx.x * 128;
-  const long long c = c0 + threadIdx.x;
+  long long c = c0 + threadIdx.x;                   // XGB_GRAD_SPLIT: a slot, turned into the cell it stands for below
   const bool live = c < ncell;
   GradTile g = tiles[0];
   int i = 0, j = 0, nx = 1, ny = 1, nxp = 2;
   long long lc = 0;
+  bool interior = false;
   double dx_s = 0, dx_n = 0, dy_w = 0, dy_e = 0, area = 1;
   double en_s[3], en_nn[3], ee_w[3], ee_e[3], vlon[3], vlat[3];
   if (live) {
     int t = 0;
+#if XGB_GRAD_SPLIT
+    interior = grad_slot_cell(tiles, ntiles, c, &t, &i, &j);
+    g = tiles[t];
+    nx = g.nx; ny = g.ny; nxp = nx + 1;
+    lc = (long long)j * nx + i;
+    c = g.cell_off + lc;
+#else
     while (t + 1 < ntiles && c >= tiles[t + 1].cell_off) ++t;
     g = tiles[t];
     nx = g.nx; ny = g.ny; nxp = nx + 1;
     lc = c - g.cell_off;
     i = (int)(lc % nx); j = (int)(lc / nx);
+#endif
     // metrics of this cell (gradient_c2l.c:58-118), read once for all field-levels
     dx_s = g.dx[(long long)j * nx + i]; dx_n = g.dx[(long long)(j + 1) * nx + i];
     dy_w = g.dy[(long long)j * nxp + i]; dy_e = g.dy[(long long)j * nxp + i + 1];
@@ -535,16 +593,27 @@ grad_c2l_rec_kernel(const GradTile* __restrict__ tiles, int ntiles, long long nc
     }
     area = g.area[lc];
   }
+  s_cell[threadIdx.x] = live ? c : -1;
   // blockIdx.y: a chunk of kRecChunk field-levels (the metrics above are read once per chunk)
   const int fbeg = blockIdx.y * kRecChunk, fend = (fbeg + kRecChunk < nf) ? fbeg + kRecChunk : nf;
   for (int f0 = fbeg; f0 < fend; f0 += kRecFields) {
     const int nk = (fend - f0 < kRecFields) ? fend - f0 : kRecFields;
     if (live) {
-#pragma unroll 1
+#pragma unroll kGradUnroll
       for (int k = 0; k < nk; ++k) {
         const double* q = data + (long long)(f0 + k) * data_stride + g.halo_off;
-        const double p00 = corner_value(q, nx, ny, i, j, g), p10 = corner_value(q, nx, ny, i + 1, j, g);
-        const double p01 = corner_value(q, nx, ny, i, j + 1, g), p11 = corner_value(q, nx, ny, i + 1, j + 1, g);
+        double p00, p10, p01, p11;
+        if (interior) {                            // corner (ci, cj) = 0.25 * (q[cj][ci] + q[cj][ci+1] + q[cj+1][ci] + q[cj+1][ci+1]), :163-166
+          const double* r0 = q + (long long)j * (nx + 2) + i;
+          const double* r1 = r0 + (nx + 2);
+          const double* r2 = r1 + (nx + 2);
+          const double a0 = r0[0], a1 = r0[1], a2 = r0[2], b0 = r1[0], b1 = r1[1], b2 = r1[2], d0 = r2[0], d1 = r2[1], d2 = r2[2];
+          p00 = 0.25 * (a0 + a1 + b0 + b1); p10 = 0.25 * (a1 + a2 + b1 + b2);
+          p01 = 0.25 * (b0 + b1 + d0 + d1); p11 = 0.25 * (b1 + b2 + d1 + d2);
+        } else {
+          p00 = corner_value(q, nx, ny, i, j, g); p10 = corner_value(q, nx, ny, i + 1, j, g);
+          p01 = corner_value(q, nx, ny, i, j + 1, g); p11 = corner_value(q, nx, ny, i + 1, j + 1, g);
+        }
         double g3[3];
 #pragma unroll
         for (int n = 0; n < 3; ++n) {
@@ -574,10 +643,11 @@ grad_c2l_rec_kernel(const GradTile* __restrict__ tiles, int ntiles, long long nc
     // transposed write-out: kRecFields consecutive field-levels of a cell and a component are 64 contiguous bytes
     for (int idx = threadIdx.x; idx < 128 * kRecFields; idx += 128) {
       const int cl = idx / kRecFields, k = idx % kRecFields;
-      if (c0 + cl < ncell && k < nk) {
+      const long long cc = s_cell[cl];
+      if (cc >= 0 && k < nk) {
 #pragma unroll
         for (int comp = 0; comp < NC; ++comp)
-          rec[rec_index(c0 + cl, f0 + k, comp, NC, nfp)] = tile[comp][cl][k];
+          rec[rec_index(cc, f0 + k, comp, NC, nfp)] = tile[comp][cl][k];
       }
     }
     __syncthreads();

@@ -26,4 +26,16 @@ d_out = torch.empty(B * nlon * nlat, dtype=torch.float64, device="cuda")
 for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
     plan.regrid(2, d_in, B, out=d_out)
 torch.cuda.synchronize(); plan.sync()
+if len(sys.argv) > 2 and sys.argv[2] == "time":      # CUDA-event time of the whole regrid + a hash of the result (variant runs)
+    import hashlib
+    st = torch.cuda.ExternalStream(plan.stream, device=torch.device("cuda", 0))
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(st):
+        e0.record()
+        for _ in range(20):
+            plan.regrid(2, d_in, B, out=d_out)
+        e1.record()
+    torch.cuda.synchronize(); plan.sync()
+    print({"lib": os.environ.get("XGRID_B200_LIB", ""), "regrid_ms": round(e0.elapsed_time(e1) / 20, 4),
+           "md5": hashlib.md5(d_out.cpu().numpy().tobytes()).hexdigest()})
 print("ok")

@@ -440,3 +440,40 @@ def test_shared_reciprocal_division_is_the_compilers_division(pkg):
             bad = C.c_longlong(-1)
             assert L.xgb_shared_div_check(a.size, a.ctypes.data, b.ctypes.data, C.byref(bad)) == 0
             assert bad.value == 0, bad.value
+
+
+def test_fused_regrid_on_tiles_of_any_shape_equals_the_two_step_path(pkg):
+    """grad_c2l_rec_kernel deals its threads the interior cells of every tile first and the rim cells after (the rim needs
+    a2b_ord2's edge formulas, gradient_c2l.c:169-196): a mosaic of a square, a wide, a two-row and a one-column tile — the thin
+    ones are all rim — must give exactly what the storage-order gradient kernel followed by the apply kernel gives."""
+    shapes = [(6, 6), (9, 4), (7, 2), (1, 5), (3, 3)]                  # (nx, ny)
+    lon0 = 20.0
+    lons, lats, xt, yt = [], [], [], []
+    for nx, ny in shapes:                                               # regional lat-lon tiles side by side
+        xe = np.deg2rad(lon0 + np.arange(nx + 1) * 1.5); ye = np.deg2rad(-10.0 + np.arange(ny + 1) * 1.25)
+        lo, la = np.meshgrid(xe, ye)
+        lons.append(lo); lats.append(la)
+        xc = np.deg2rad(lon0 + (np.arange(-1, nx + 1) + 0.5) * 1.5); yc = np.deg2rad(-10.0 + (np.arange(-1, ny + 1) + 0.5) * 1.25)
+        cx, cy = np.meshgrid(xc, yc)
+        xt.append(cx.reshape(-1)); yt.append(cy.reshape(-1))
+        lon0 += nx * 1.5 + 3.0
+    lon2, lat2 = pkg.latlon_grid(90, 45)
+    p = pkg.XgridPlan(0)
+    p.set_dst(lon2, lat2)
+    p.set_src(lons, lats)
+    assert p.generate(2) > 0
+    p.apply_setup()
+    p.grad_setup(np.concatenate(xt), np.concatenate(yt))
+    rng = np.random.default_rng(11)
+    nf = 70                                                             # two 64-field-level chunks, ragged
+    nh = sum((nx + 2) * (ny + 2) for nx, ny in shapes)
+    for hmiss in (False, True):
+        fh = rng.uniform(0.0, 1.0, (nf, nh))
+        if hmiss:
+            fh[rng.uniform(size=fh.shape) < 0.05] = -999.0
+        gx, gy, gm = p.grad_c2l(fh.reshape(-1), nf, has_missing=hmiss, missing=-999.0)
+        two_step = p.apply(2, fh.reshape(-1), nf, gx, gy, gm, has_missing=hmiss, missing=-999.0)
+        fused = p.regrid(2, fh.reshape(-1), nf, has_missing=hmiss, missing=-999.0)
+        assert np.array_equal(two_step, fused, equal_nan=True), hmiss
+        assert (fused != 0).any()
+    p.close()
