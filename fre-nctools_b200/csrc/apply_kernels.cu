@@ -503,7 +503,7 @@ constexpr int kRecChunk = 32;      // field-levels per gradient block
 #define XGB_GRAD_UNROLL 1
 #endif
 #ifndef XGB_GRAD_BLOCKS
-#define XGB_GRAD_BLOCKS 0
+#define XGB_GRAD_BLOCKS 4
 #endif
 #if XGB_GRAD_BLOCKS > 0
 #define XGB_GRAD_BOUNDS __launch_bounds__(128, XGB_GRAD_BLOCKS)
@@ -514,7 +514,10 @@ constexpr int kGradUnroll = XGB_GRAD_UNROLL;
 // XGB_GRAD_SPLIT: threads are dealt the INTERIOR cells of all tiles first (every corner of such a cell is the plain four-point
 // average, gradient_c2l.c:163-166: nine loads, no case analysis), then the cells on the tiles' rims (a2b_ord2's edge and corner
 // formulas).  With cells in storage order two of the three warps of a 96-cell row held one rim cell and ran both code paths
-// for every field-level; ncu: 373 instructions per (cell, field-level), FP64 pipe 22 %.
+// for every field-level; ncu: 373 instructions per (cell, field-level), FP64 pipe 22 %.  configs[1] regrid (gradient + apply),
+// results md5-identical: storage order 2.54 ms; interior first 2.40 ms (152 registers, 3 blocks / SM); interior first at
+// __launch_bounds__(128, 4) (128 registers, no spill) 2.32 ms = the default; the field-level loop unrolled by 2 on top: 2.34
+// (spills at 4 blocks) / 2.40 ms (168 registers, 3 blocks).
 #ifndef XGB_GRAD_SPLIT
 #define XGB_GRAD_SPLIT 1
 #endif
