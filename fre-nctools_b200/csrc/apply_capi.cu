@@ -495,7 +495,7 @@ extern "C" int xgb_plan_regrid(xgb_plan* p, unsigned int opcode, int nfields, co
       // field-levels of one destination cell (apply_kernels.cu: grad_c2l_rec_kernel, apply_rec_kernel)
       if (a->s_gx.reserve(apply_rec_doubles(a->ncell, nfields, has_missing != 0) * 8 + 64)) return 1;
       launch_regrid_rec((const GradTile*)a->gtiles_dev.p, (int)a->gtiles.size(), a->ncell, nfields, d_data, a->nhalo, (double*)a->s_gx.p,
-                        has_missing != 0, missing, csr, a->ndst, miss, a->cell_methods, d_out, p->st);
+                        has_missing != 0, missing, csr, a->ndst, miss, a->cell_methods, d_out, p->st, a->nx2);
     } else {
       // packed path (round 1): one 32-byte record (value, grad_x, grad_y, grad_mask) per source cell and field-level
       if (a->s_gx.reserve(ng * 32 + 32)) return 1;

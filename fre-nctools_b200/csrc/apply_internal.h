@@ -63,7 +63,7 @@ int shared_div_check(long long n, const double* a_host, const double* b_host, un
 size_t apply_rec_doubles(long long ncell, int nf, bool has_missing);
 void launch_regrid_rec(const GradTile* tiles, int ntiles, long long ncell, int nf, const double* data, long long data_stride, double* rec,
                        bool has_missing, double missing, const ApplyCsr& csr, long long ndst, double apply_missing, int sum_mode,
-                       double* out, cudaStream_t st);
+                       double* out, cudaStream_t st, int nx2 = 0);
 void launch_effective_area(const ApplyCsr& csr, long long n, const double* weight, const double* carea, const double* farea,
                            int sum_mode, double* eff, cudaStream_t st);
 void launch_measure_check(const ApplyCsr& csr, long long n, int order, const double* data, const double* farea, double missing,

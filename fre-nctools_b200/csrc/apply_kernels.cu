@@ -711,9 +711,19 @@ struct RecPair {
 #define XGB_APPLY_BLOCKS 8
 #endif
 
+// XGB_TILE_R > 1 (measured, off): a block walks kTileR consecutive destination ROWS of its kTileD columns, one after the
+// other — the source cells one row gathered from are the ones the next row asks for (a C96 cell spans four quarter-degree
+// rows), so their records could come from the L1 instead of the L2 again (ncu on the one-row version: L1 hit rate 25 %,
+// L2 75 %).  configs[1] regrid, results md5-identical: 1 row 2.32 ms, 2 rows 2.39, 4 rows 2.34, 8 rows 2.35, 16 rows 2.36 ms —
+// where the records come from is not what the kernel waits for; it stays at one row.
+#ifndef XGB_TILE_R
+#define XGB_TILE_R 1
+#endif
+constexpr int kTileR = XGB_TILE_R;
+
 template <bool MISSING>
 __global__ void __launch_bounds__(128, XGB_APPLY_BLOCKS)
-apply_rec_kernel(ApplyCsr csr, long long ndst, int nf, int nfp, const double* __restrict__ rec, double missing, int sum_mode,
+apply_rec_kernel(ApplyCsr csr, long long ndst, int nx2, int nf, int nfp, const double* __restrict__ rec, double missing, int sum_mode,
                  double* __restrict__ out)
 {
   constexpr int NC = MISSING ? 4 : 3;
@@ -721,10 +731,29 @@ apply_rec_kernel(ApplyCsr csr, long long ndst, int nf, int nfp, const double* __
   __shared__ __align__(16) double res[4][kTileD][kResRow];        // [warp][destination cell][field]
   __shared__ uint32_t s_off[kTileD + 1];
   __shared__ TileEntry s_ent[kTileE];
-  const long long d0 = (long long)blockIdx.x * kTileD;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const long long cbytes = (long long)NC * nfp * 8;                // bytes of one source cell's records
-  const int nd = (ndst - d0 < kTileD) ? (int)(ndst - d0) : kTileD;
+  const int fw = blockIdx.y * 256 + wid * 64;                    // this warp's 64 field-levels
+  const bool wactive = fw < nf;                                   // warp-uniform
+  const int f = fw + 2 * lane;                                    // this lane's two: f, f + 1
+  const bool l0 = wactive && f < nf;
+  const int tiles_per_row = (nx2 + kTileD - 1) / kTileD;
+  const long long ny2 = ndst / nx2;
+#pragma unroll 1
+  for (int row = 0; row < kTileR; ++row) {
+  long long d0;
+  int nd;
+  if (kTileR == 1) {                                              // flat tiles over the destination index (rows may be ragged)
+    d0 = (long long)blockIdx.x * kTileD;
+    nd = (ndst - d0 < kTileD) ? (int)(ndst - d0) : kTileD;
+  } else {
+    const long long j = (long long)(blockIdx.x / tiles_per_row) * kTileR + row;
+    const int i0 = (int)(blockIdx.x % tiles_per_row) * kTileD;
+    if (j >= ny2) break;                                          // block-uniform
+    d0 = j * nx2 + i0;
+    nd = (nx2 - i0 < kTileD) ? nx2 - i0 : kTileD;
+    __syncthreads();                                              // the previous row's staging is no longer read
+  }
   if (threadIdx.x <= kTileD) s_off[threadIdx.x] = csr.off[d0 + (threadIdx.x < nd ? threadIdx.x : nd)];
   __syncthreads();
   const uint32_t q0 = s_off[0];
@@ -734,10 +763,7 @@ apply_rec_kernel(ApplyCsr csr, long long ndst, int nf, int nfp, const double* __
     for (int k = threadIdx.x; k < ne; k += 128)
       s_ent[k] = TileEntry{csr.area[q0 + k], csr.di[q0 + k], csr.dj[q0 + k], (long long)csr.cell[q0 + k] * cbytes};
   __syncthreads();
-  const int fw = blockIdx.y * 256 + wid * 64;                    // this warp's 64 field-levels
-  if (fw >= nf) return;                                           // warp-uniform
-  const int f = fw + 2 * lane;                                    // this lane's two: f, f + 1
-  const bool l0 = f < nf;
+  if (!wactive) continue;                                         // (still takes part in the barriers of the next row)
   const char* recf = reinterpret_cast<const char*>(rec + (long long)(fw / kRecLane) * NC * kRecLane + 2 * lane);
   // result of one destination cell from this lane's sums (conserve_interp.c:821-838)
   auto finish = [&](bool any, double acc0, double acc1, double as0, double as1, bool seen0, bool seen1) {
@@ -796,6 +822,8 @@ apply_rec_kernel(ApplyCsr csr, long long ndst, int nf, int nfp, const double* __
     for (int fr = sub; fr < 64; fr += kRowsPerPass, o += ostep)
       if (fw + fr < nf && dl < nd) *o = res[wid][dl][fr];
   }
+  __syncwarp();                                                   // the next row overwrites this warp's staging
+  }
 }
 
 // self-check of shared_div.cuh: quotients of a[i] / b[i] by SharedDiv against the compiler's division, bit for bit
@@ -829,21 +857,23 @@ size_t apply_rec_doubles(long long ncell, int nf, bool has_missing)
 
 void launch_regrid_rec(const GradTile* tiles, int ntiles, long long ncell, int nf, const double* data, long long data_stride, double* rec,
                        bool has_missing, double missing, const ApplyCsr& csr, long long ndst, double apply_missing, int sum_mode,
-                       double* out, cudaStream_t st)
+                       double* out, cudaStream_t st, int nx2)
 {
   if (ncell <= 0 || nf <= 0 || ndst <= 0) return;
+  if (nx2 <= 0 || ndst % nx2) nx2 = (int)ndst;                     // no row structure known: one row
   const int nfp = (nf + kRecLane - 1) / kRecLane * kRecLane;
   const dim3 gblk((unsigned)((ncell + 127) / 128), (unsigned)((nf + kRecChunk - 1) / kRecChunk));
-  const long long atiles = (ndst + kTileD - 1) / kTileD;
+  const long long atiles = (kTileR == 1) ? (ndst + kTileD - 1) / kTileD
+                                         : (long long)((nx2 + kTileD - 1) / kTileD) * ((ndst / nx2 + kTileR - 1) / kTileR);
   if (atiles >= (1ll << 31)) return;
   const dim3 ablk((unsigned)atiles, (unsigned)((nf + 255) / 256));
   g_launches += 2;
   if (has_missing) {
     grad_c2l_rec_kernel<true><<<gblk, 128, 0, st>>>(tiles, ntiles, ncell, nf, nfp, data, data_stride, rec, missing);
-    apply_rec_kernel<true><<<ablk, 128, 0, st>>>(csr, ndst, nf, nfp, rec, apply_missing, sum_mode, out);
+    apply_rec_kernel<true><<<ablk, 128, 0, st>>>(csr, ndst, nx2, nf, nfp, rec, apply_missing, sum_mode, out);
   } else {
     grad_c2l_rec_kernel<false><<<gblk, 128, 0, st>>>(tiles, ntiles, ncell, nf, nfp, data, data_stride, rec, missing);
-    apply_rec_kernel<false><<<ablk, 128, 0, st>>>(csr, ndst, nf, nfp, rec, apply_missing, sum_mode, out);
+    apply_rec_kernel<false><<<ablk, 128, 0, st>>>(csr, ndst, nx2, nf, nfp, rec, apply_missing, sum_mode, out);
   }
 }
 
