@@ -239,7 +239,20 @@ void launch_gc_candidates(bool fill, const GcCells& src, const GcCells& dst, lon
   else      gc_candidate_kernel<false><<<blocks, 128, 0, st>>>(src, dst, s0, ns, mask, pyr, pair_off, cnt, pairs, err);
 }
 
-__global__ void __launch_bounds__(64)
+// Block size.  The kernel is 6 700 SASS instructions plus the double-double routines it calls, and ncu named "no instruction"
+// its top stall by a factor of six: warps of many small blocks, started at different times, sit at different places in that
+// code and evict each other's instruction-cache lines.  One large block per SM starts its warps together on consecutive pairs
+// (same source cell, neighbouring destination cells: the same path through the clip), and that alone is worth a third
+// (configs[2] clip phase, results md5-identical; threads x blocks/SM, registers):
+//    64 x 8, 122: 10.74 ms      64 x 16, 64:  9.82      128 x 8, 64: 9.56      256 x 4, 64: 8.91      512 x 2, 64: 8.26
+//   512 x 1, 124:  7.69        640 x 1, 96:  7.51      768 x 1, 80: 7.28      896 x 1, 72: 7.18     1024 x 1, 64: 7.43
+// Small launches (a few blocks per SM at most) keep 128-thread blocks so that every SM has work.
+#ifndef XGB_GC_THREADS
+#define XGB_GC_THREADS 896
+#endif
+constexpr int kGcBig = XGB_GC_THREADS, kGcSmall = 128;
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
 gc_clip_kernel(GcCells src, GcCells dst, const double* __restrict__ mask, const int2* __restrict__ pairs,
                unsigned long long npairs, long long s0, double* __restrict__ parea, uint32_t* __restrict__ cnt, int* err)
 {
@@ -270,7 +283,10 @@ void launch_gc_clip(const GcCells& src, const GcCells& dst, const double* mask, 
 {
   if (npairs == 0) return;
   ++g_launches;
-  gc_clip_kernel<<<(unsigned)((npairs + 63) / 64), 64, 0, st>>>(src, dst, mask, pairs, npairs, s0, parea, cnt, err);
+  if (npairs >= 4ull * 148 * kGcBig)
+    gc_clip_kernel<kGcBig><<<(unsigned)((npairs + kGcBig - 1) / kGcBig), kGcBig, 0, st>>>(src, dst, mask, pairs, npairs, s0, parea, cnt, err);
+  else
+    gc_clip_kernel<kGcSmall><<<(unsigned)((npairs + kGcSmall - 1) / kGcSmall), kGcSmall, 0, st>>>(src, dst, mask, pairs, npairs, s0, parea, cnt, err);
 }
 
 }  // namespace xgb

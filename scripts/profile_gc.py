@@ -16,4 +16,10 @@ op = pkg.CONSERVE_ORDER1 | pkg.GREAT_CIRCLE
 for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
     n = plan.generate(op)
 plan.sync()
-print("nxgrid", n, "pairs", plan.npairs, plan.phase_ms())
+import hashlib  # noqa: E402
+res = plan.result_host()
+h = hashlib.md5()
+for k in sorted(res):
+    h.update(res[k].tobytes())
+print("nxgrid", n, "pairs", plan.npairs, "lib", os.environ.get("XGRID_B200_LIB", ""), "md5", h.hexdigest(),
+      {k: round(v, 3) for k, v in plan.phase_ms()[0].items()})
