@@ -379,72 +379,63 @@ XGB_HD void poly_append_unique(Poly& l, double x, double y, double z) {
 // clip_2dx2d_great_circle: vertices of cell 1 (subject) and cell 2 (clip) in the reference's clockwise order.
 // Returns the vertex count of the overlap polygon written to out (capacity kPoly), 0 if none, < 0 where the
 // reference would abort.
-XGB_HD int clip_great_circle(const V3* c1, int n1, const V3* c2, int n2, V3* out) {
-  if (n1 > kMaxIn || n2 > kMaxIn) return kErrPool;
-  {                                                              // six range rejections (:1508-1528)
-    double lo1[3], hi1[3], lo2[3], hi2[3];
-    lo1[0] = hi1[0] = c1[0].x; lo1[1] = hi1[1] = c1[0].y; lo1[2] = hi1[2] = c1[0].z;
-    for (int k = 1; k < n1; ++k) {
-      lo1[0] = fmin(lo1[0], c1[k].x); hi1[0] = fmax(hi1[0], c1[k].x);
-      lo1[1] = fmin(lo1[1], c1[k].y); hi1[1] = fmax(hi1[1], c1[k].y);
-      lo1[2] = fmin(lo1[2], c1[k].z); hi1[2] = fmax(hi1[2], c1[k].z);
-    }
-    lo2[0] = hi2[0] = c2[0].x; lo2[1] = hi2[1] = c2[0].y; lo2[2] = hi2[2] = c2[0].z;
-    for (int k = 1; k < n2; ++k) {
-      lo2[0] = fmin(lo2[0], c2[k].x); hi2[0] = fmax(hi2[0], c2[k].x);
-      lo2[1] = fmin(lo2[1], c2[k].y); hi2[1] = fmax(hi2[1], c2[k].y);
-      lo2[2] = fmin(lo2[2], c2[k].z); hi2[2] = fmax(hi2[2], c2[k].z);
-    }
-    for (int a = 0; a < 3; ++a)
-      if (lo1[a] >= hi2[a] + kRange || lo2[a] >= hi1[a] + kRange) return 0;
-  }
+//
+// The routine is written as phases — ring construction, inside flags (angle sums), the (side of 1) x (side of 2) intersection
+// steps, the walk — so that a thread block can pass through them TOGETHER: with SYNC > 0 every thread of the block calls it
+// (live = false for padding threads) and meets the others at a barrier before each phase (SYNC >= 2: before each side of cell
+// 1, SYNC >= 3: before each pair of sides).  The kernel is bound by instruction fetch; warps that execute the same phase at
+// the same time share its cache lines instead of evicting each other's (xgrid_gc_kernels.cu, gc_clip_kernel).  SYNC = 0 is
+// the plain routine (host build, small launches); the arithmetic and its order are the same in every mode.
+struct ClipState {
   Ring g1, g2;
-  g1.len = g2.len = 0; g1.overflow = g2.overflow = false;
-  for (int k = 0; k < n1; ++k) ring_append_unique(g1, c1[k].x, c1[k].y, c1[k].z);
-  for (int k = 0; k < n2; ++k) ring_append_unique(g2, c2[k].x, c2[k].y, c2[k].z);
-  const int npts1 = g1.len, npts2 = g2.len;
-  for (int k = 0; k < g1.len; ++k) g1.n[k].inside = inside_polygon(g1.n[k], g2) ? 1 : 0;     // :1549-1568
-  for (int k = 0; k < g2.len; ++k) g2.n[k].inside = inside_polygon(g2.n[k], g1) ? 1 : 0;
-  if (!ring_area_positive(g1) || !ring_area_positive(g2)) return kErrNotConvex;                       // :1575-1578
-
   V3 pt1[kMaxIn], pt2[kMaxIn];
-  for (int k = 0; k < npts1; ++k) pt1[k] = V3{g1.n[k].x, g1.n[k].y, g1.n[k].z};
-  for (int k = 0; k < npts2; ++k) pt2[k] = V3{g2.n[k].x, g2.n[k].y, g2.n[k].z};
   INode inter[kInter];
-  int ninter = 0;
-  bool inter_overflow = false;
+  int ninter, npts1, npts2;
+  bool inter_overflow;
+};
 
-  for (int i1 = 0; i1 < npts1; ++i1) {                                                       // :1606-1670
-    const int i1p = (i1 + 1 < npts1) ? i1 + 1 : 0;
-    for (int i2 = 0; i2 < npts2; ++i2) {
-      const int i2p = (i2 + 1 < npts2) ? i2 + 1 : i2 + 1 - npts2;
-      const int i2p2 = (i2 + 2 < npts2) ? i2 + 2 : i2 + 2 - npts2;
-      V3 p;
-      double u1, u2;
-      int inbound;
-      if (!line_intersect(pt1[i1], pt1[i1p], pt2[i2], pt2[i2p], pt2[i2p2], &p, &u1, &u2, &inbound)) continue;
-      {                                                                                      // addIntersect :1133-1186
-        double u1c = u1, u2c = u2;
-        int s = i1, c = i2;
-        if (u1c == 1) { u1c = 0; s = i1p; }
-        if (u2c == 1) { u2c = 0; c = i2p; }
-        bool dup = false;
-        for (int k = 0; k < ninter; ++k)
-          if ((inter[k].u == u1c && inter[k].subj_index == s) || (inter[k].u_clip == u2c && inter[k].clip_index == c)) { dup = true; break; }
-        if (dup) continue;
-        if (ninter >= kInter) { inter_overflow = true; continue; }
-        inter[ninter++] = INode{p.x, p.y, p.z, u1c, u2c, inbound, s, c};
-      }
-      if (u1 == 1) { if (!ring_insert(g1, p, 0.0, u2, inbound, pt1[i1p])) return kErrWalk; }
-      else         { if (!ring_insert(g1, p, u1, u2, inbound, pt1[i1])) return kErrWalk; }
-      if (u1 == 1) pt1[i1p] = p; else if (u1 == 0) pt1[i1] = p;
-      if (u2 == 1) { if (!ring_insert(g2, p, 0.0, u1, 0, pt2[i2p])) return kErrWalk; }
-      else         { if (!ring_insert(g2, p, u2, u1, 0, pt2[i2])) return kErrWalk; }
-      if (u2 == 1) pt2[i2p] = p; else if (u2 == 0) pt2[i2] = p;
-    }
+// one (side i1 of cell 1, side i2 of cell 2) step of :1606-1670; false where the reference would abort
+XGB_HD bool clip_step(ClipState& S, int i1, int i2) {
+  Ring& g1 = S.g1; Ring& g2 = S.g2;
+  V3* pt1 = S.pt1; V3* pt2 = S.pt2;
+  INode* inter = S.inter;
+  int& ninter = S.ninter;
+  bool& inter_overflow = S.inter_overflow;
+  const int npts1 = S.npts1, npts2 = S.npts2;
+  const int i1p = (i1 + 1 < npts1) ? i1 + 1 : 0;
+  const int i2p = (i2 + 1 < npts2) ? i2 + 1 : i2 + 1 - npts2;
+  const int i2p2 = (i2 + 2 < npts2) ? i2 + 2 : i2 + 2 - npts2;
+  V3 p;
+  double u1, u2;
+  int inbound;
+  if (!line_intersect(pt1[i1], pt1[i1p], pt2[i2], pt2[i2p], pt2[i2p2], &p, &u1, &u2, &inbound)) return true;
+  {                                                                                      // addIntersect :1133-1186
+    double u1c = u1, u2c = u2;
+    int s = i1, c = i2;
+    if (u1c == 1) { u1c = 0; s = i1p; }
+    if (u2c == 1) { u2c = 0; c = i2p; }
+    bool dup = false;
+    for (int k = 0; k < ninter; ++k)
+      if ((inter[k].u == u1c && inter[k].subj_index == s) || (inter[k].u_clip == u2c && inter[k].clip_index == c)) { dup = true; break; }
+    if (dup) return true;
+    if (ninter >= kInter) { inter_overflow = true; return true; }
+    inter[ninter++] = INode{p.x, p.y, p.z, u1c, u2c, inbound, s, c};
   }
-  if (g1.overflow || g2.overflow || inter_overflow) return kErrPool;
+  if (u1 == 1) { if (!ring_insert(g1, p, 0.0, u2, inbound, pt1[i1p])) return false; }
+  else         { if (!ring_insert(g1, p, u1, u2, inbound, pt1[i1])) return false; }
+  if (u1 == 1) pt1[i1p] = p; else if (u1 == 0) pt1[i1] = p;
+  if (u2 == 1) { if (!ring_insert(g2, p, 0.0, u1, 0, pt2[i2p])) return false; }
+  else         { if (!ring_insert(g2, p, u2, u1, 0, pt2[i2])) return false; }
+  if (u2 == 1) pt2[i2p] = p; else if (u2 == 0) pt2[i2] = p;
 
+  return true;
+}
+
+// the walk over the two rings from the first inbound intersection (:1676-1904)
+XGB_HD int clip_walk(ClipState& S, V3* out) {
+  Ring& g1 = S.g1; Ring& g2 = S.g2;
+  INode* inter = S.inter;
+  const int ninter = S.ninter, npts1 = S.npts1, npts2 = S.npts2;
   int nint = ninter, first = -1;                                                             // :1676-1693
   if (nint > 1) for (int k = 0; k < ninter; ++k) if (inter[k].inbound == 2) { first = k; break; }
   if (first < 0 && nint > 1) {                                                               // setInbound :1437-1470
@@ -522,6 +513,70 @@ XGB_HD int clip_great_circle(const V3* c1, int n1, const V3* c2, int n2, V3* out
     }
   }
   return n_out;
+}
+
+#if defined(__CUDA_ARCH__)
+#define XGB_GC_BAR(level) do { if (SYNC >= (level)) __syncthreads(); } while (0)
+#else
+#define XGB_GC_BAR(level) do { } while (0)
+#endif
+
+template <int SYNC>
+XGB_HD int clip_great_circle_t(const V3* c1, int n1, const V3* c2, int n2, V3* out, bool live) {
+  int status = live ? 1 : 0;                                     // 1: still working; otherwise the value to return
+  if (status == 1 && (n1 > kMaxIn || n2 > kMaxIn)) status = kErrPool;
+  if (status == 1) {                                             // six range rejections (:1508-1528)
+    double lo1[3], hi1[3], lo2[3], hi2[3];
+    lo1[0] = hi1[0] = c1[0].x; lo1[1] = hi1[1] = c1[0].y; lo1[2] = hi1[2] = c1[0].z;
+    for (int k = 1; k < n1; ++k) {
+      lo1[0] = fmin(lo1[0], c1[k].x); hi1[0] = fmax(hi1[0], c1[k].x);
+      lo1[1] = fmin(lo1[1], c1[k].y); hi1[1] = fmax(hi1[1], c1[k].y);
+      lo1[2] = fmin(lo1[2], c1[k].z); hi1[2] = fmax(hi1[2], c1[k].z);
+    }
+    lo2[0] = hi2[0] = c2[0].x; lo2[1] = hi2[1] = c2[0].y; lo2[2] = hi2[2] = c2[0].z;
+    for (int k = 1; k < n2; ++k) {
+      lo2[0] = fmin(lo2[0], c2[k].x); hi2[0] = fmax(hi2[0], c2[k].x);
+      lo2[1] = fmin(lo2[1], c2[k].y); hi2[1] = fmax(hi2[1], c2[k].y);
+      lo2[2] = fmin(lo2[2], c2[k].z); hi2[2] = fmax(hi2[2], c2[k].z);
+    }
+    for (int a = 0; a < 3; ++a)
+      if (lo1[a] >= hi2[a] + kRange || lo2[a] >= hi1[a] + kRange) status = 0;
+  }
+  ClipState S;
+  Ring& g1 = S.g1; Ring& g2 = S.g2;
+  g1.len = g2.len = 0; g1.overflow = g2.overflow = false;
+  S.ninter = 0; S.inter_overflow = false; S.npts1 = S.npts2 = 0;
+  if (status == 1) {
+    for (int k = 0; k < n1; ++k) ring_append_unique(g1, c1[k].x, c1[k].y, c1[k].z);
+    for (int k = 0; k < n2; ++k) ring_append_unique(g2, c2[k].x, c2[k].y, c2[k].z);
+    S.npts1 = g1.len; S.npts2 = g2.len;
+  }
+  XGB_GC_BAR(1);
+  if (status == 1) {
+    for (int k = 0; k < g1.len; ++k) g1.n[k].inside = inside_polygon(g1.n[k], g2) ? 1 : 0;   // :1549-1568
+    for (int k = 0; k < g2.len; ++k) g2.n[k].inside = inside_polygon(g2.n[k], g1) ? 1 : 0;
+    if (!ring_area_positive(g1) || !ring_area_positive(g2)) status = kErrNotConvex;          // :1575-1578
+  }
+  if (status == 1) {
+    for (int k = 0; k < S.npts1; ++k) S.pt1[k] = V3{g1.n[k].x, g1.n[k].y, g1.n[k].z};
+    for (int k = 0; k < S.npts2; ++k) S.pt2[k] = V3{g2.n[k].x, g2.n[k].y, g2.n[k].z};
+  }
+  XGB_GC_BAR(1);
+  const int lim1 = SYNC ? kMaxIn : S.npts1, lim2 = SYNC ? kMaxIn : S.npts2;
+  for (int i1 = 0; i1 < lim1; ++i1) {                                                        // :1606-1670
+    XGB_GC_BAR(2);
+    for (int i2 = 0; i2 < lim2; ++i2) {
+      XGB_GC_BAR(3);
+      if (status == 1 && i1 < S.npts1 && i2 < S.npts2 && !clip_step(S, i1, i2)) status = kErrWalk;
+    }
+  }
+  if (status == 1 && (g1.overflow || g2.overflow || S.inter_overflow)) status = kErrPool;
+  XGB_GC_BAR(1);
+  return (status == 1) ? clip_walk(S, out) : status;
+}
+
+XGB_HD int clip_great_circle(const V3* c1, int n1, const V3* c2, int n2, V3* out) {
+  return clip_great_circle_t<0>(c1, n1, c2, n2, out, true);
 }
 
 // Cheap proof that two cells cannot produce an exchange cell: some side of one cell has every corner of the other on its

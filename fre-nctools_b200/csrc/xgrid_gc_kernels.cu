@@ -247,8 +247,18 @@ void launch_gc_candidates(bool fill, const GcCells& src, const GcCells& dst, lon
 //    64 x 8, 122: 10.74 ms      64 x 16, 64:  9.82      128 x 8, 64: 9.56      256 x 4, 64: 8.91      512 x 2, 64: 8.26
 //   512 x 1, 124:  7.69        640 x 1, 96:  7.51      768 x 1, 80: 7.28      896 x 1, 72: 7.18     1024 x 1, 64: 7.43
 // Small launches (a few blocks per SM at most) keep 128-thread blocks so that every SM has work.
+// Then, with 896-thread blocks: the clip routine written as phases (gc_clip.cuh, clip_great_circle_t; same arithmetic) 7.17 ->
+// 5.95 ms; one block barrier between the clip and the area code (XGB_GC_AREA_BAR: the warps enter the acos-heavy area routine
+// together) 5.83 ms = the default.  Barriers between the phases inside the clip as well (XGB_GC_SYNC = 1 / 2 / 3: per phase /
+// per side of cell 1 / per pair of sides) cost more in waiting than they save in fetches: 6.25 / 6.52 / 7.10 ms.
 #ifndef XGB_GC_THREADS
 #define XGB_GC_THREADS 896
+#endif
+#ifndef XGB_GC_SYNC
+#define XGB_GC_SYNC 0
+#endif
+#ifndef XGB_GC_AREA_BAR
+#define XGB_GC_AREA_BAR 1
 #endif
 constexpr int kGcBig = XGB_GC_THREADS, kGcSmall = 128;
 template <int THREADS>
@@ -257,13 +267,23 @@ gc_clip_kernel(GcCells src, GcCells dst, const double* __restrict__ mask, const 
                unsigned long long npairs, long long s0, double* __restrict__ parea, uint32_t* __restrict__ cnt, int* err)
 {
   const unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+#if XGB_GC_SYNC > 0 || XGB_GC_AREA_BAR
+  const bool live = p < npairs;
+  const int2 pr = pairs[live ? p : npairs - 1];
+#else
   if (p >= npairs) return;
+  const bool live = true;
   const int2 pr = pairs[p];
+#endif
   const long long s = s0 + pr.x, d = pr.y;
   gc::V3 a[4], b[4], out[gc::kPoly];
   load_cell(src, s, a);
   load_cell(dst, d, b);
-  const int n_out = gc::clip_great_circle(a, 4, b, 4, out);      // (pairs separated by a side never get here: gc_leaf)
+  const int n_out = gc::clip_great_circle_t<XGB_GC_SYNC>(a, 4, b, 4, out, live);   // (pairs separated by a side never get here: gc_leaf)
+#if XGB_GC_SYNC > 0 || XGB_GC_AREA_BAR
+  __syncthreads();                                                // the block's warps enter the area code together
+  if (!live) return;
+#endif
   double keep = 0.0;
   if (n_out < 0) {
     atomicOr(err, n_out == gc::kErrNotConvex ? kErrGcNotConvex : (n_out == gc::kErrPool ? kErrGcNodePool : kErrGcWalk));
