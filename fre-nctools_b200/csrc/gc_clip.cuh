@@ -39,7 +39,7 @@ constexpr double kPiD = 3.14159265358979323846;
 constexpr double kR = 6371000.0;
 constexpr int kRing = 12;           // vertices (<= 4) + inserted intersections (<= 8 between two convex quadrilaterals)
 constexpr int kInter = 12;
-constexpr int kPoly = 16;
+constexpr int kPoly = 12;           // the overlap of two convex quadrilaterals has at most 8 vertices
 constexpr int kMaxIn = 4;           // corners of an input cell
 constexpr int kErrNotConvex = -1, kErrWalk = -2, kErrPool = -3;
 
@@ -218,8 +218,8 @@ XGB_HD double great_circle_area(int n, Get get) {
 }
 
 // vertex ring node / intersection node
-struct RNode { double x, y, z, u; int intersect, inbound, inside; };
-struct INode { double x, y, z, u, u_clip; int inbound, subj_index, clip_index; };
+struct RNode { double x, y, z, u; signed char intersect, inbound, inside; };   // 40 bytes: the rings live in local memory
+struct INode { double x, y, z, u, u_clip; signed char inbound, subj_index, clip_index; };
 struct Ring { RNode n[kRing]; int len; bool overflow; };
 
 XGB_HD void ring_append_unique(Ring& l, double x, double y, double z) {          // addEnd(list, x, y, z, 0, 0, 0, -1)
@@ -297,7 +297,7 @@ XGB_HD_CALL bool ring_insert(Ring& l, const V3& p, double u1, double u2, int inb
   if (l.len >= kRing) { l.overflow = true; return true; }
   for (int k = l.len; k > a + 1; --k) l.n[k] = l.n[k - 1];
   ++l.len;
-  l.n[a + 1] = RNode{p.x, p.y, p.z, ucur, 1, inbound, 1};
+  l.n[a + 1] = RNode{p.x, p.y, p.z, ucur, 1, (signed char)inbound, 1};
   return true;
 }
 
@@ -369,7 +369,7 @@ XGB_HD int ring_find(const Ring& l, double x, double y, double z) {
   return -1;
 }
 
-struct Poly { V3 v[kPoly]; int len; bool overflow; };
+struct Poly { V3* v; int len; bool overflow; };      // a view of the caller's output array (capacity kPoly)
 XGB_HD void poly_append_unique(Poly& l, double x, double y, double z) {
   for (int k = 0; k < l.len; ++k) if (same_point(l.v[k].x, l.v[k].y, l.v[k].z, x, y, z)) return;
   if (l.len >= kPoly) { l.overflow = true; return; }
@@ -419,7 +419,7 @@ XGB_HD bool clip_step(ClipState& S, int i1, int i2) {
       if ((inter[k].u == u1c && inter[k].subj_index == s) || (inter[k].u_clip == u2c && inter[k].clip_index == c)) { dup = true; break; }
     if (dup) return true;
     if (ninter >= kInter) { inter_overflow = true; return true; }
-    inter[ninter++] = INode{p.x, p.y, p.z, u1c, u2c, inbound, s, c};
+    inter[ninter++] = INode{p.x, p.y, p.z, u1c, u2c, (signed char)inbound, (signed char)s, (signed char)c};
   }
   if (u1 == 1) { if (!ring_insert(g1, p, 0.0, u2, inbound, pt1[i1p])) return false; }
   else         { if (!ring_insert(g1, p, u1, u2, inbound, pt1[i1])) return false; }
@@ -453,7 +453,7 @@ XGB_HD int clip_walk(ClipState& S, V3* out) {
   int n_out = 0;
   if (first >= 0) {                                                                          // :1697-1838
     Poly poly;
-    poly.len = 0; poly.overflow = false;
+    poly.v = out; poly.len = 0; poly.overflow = false;
     const V3 f{inter[first].x, inter[first].y, inter[first].z};
     if (ring_find(g1, f.x, f.y, f.z) < 0) return kErrWalk;
     poly_append_unique(poly, f.x, f.y, f.z);
@@ -492,7 +492,6 @@ XGB_HD int clip_walk(ClipState& S, V3* out) {
     }
     if (!found1 || nint > 0) return kErrWalk;
     if (poly.overflow) return kErrPool;
-    for (int k = 0; k < poly.len; ++k) out[k] = poly.v[k];
     n_out = poly.len;
     if (n_out < 3) n_out = 0;
   }
