@@ -1980,6 +1980,9 @@ __device__ __forceinline__ int find_tile(const TileDesc* tiles, int ntiles, long
 
 constexpr uint32_t kLongPairs = 256;      // heavy cells with at most this many pairs stay with the per-pair rank loop
 
+#ifndef XGB_SCATTER_VARIANT
+#define XGB_SCATTER_VARIANT 1
+#endif
 template <int ORDER>
 __global__ void __launch_bounds__(256)
 scatter_kernel(const int2* __restrict__ pairs, unsigned long long npairs,
@@ -2006,9 +2009,21 @@ scatter_kernel(const int2* __restrict__ pairs, unsigned long long npairs,
   // the reference visits destination cells in ascending ij for each source cell (create_xgrid.c:769)
   uint32_t rank = 0;
   const uint32_t qb = pair_off[pr.x], qe = qb + pair_cnt[pr.x];
+  const size_t obase = out_off[pr.x];
+#if XGB_SCATTER_VARIANT
+  // both loads of an iteration are issued unconditionally and the loop is unrolled: with `parea[q] > 0 && pairs[q].y < ...` the
+  // second load waited for the first, five dependent round trips per pair (ncu: long scoreboard 21 warps per issue)
+#pragma unroll 4
+  for (uint32_t q = qb; q < qe; ++q) {
+    const double aq = parea[q];
+    const int yq = pairs[q].y;
+    rank += (aq > 0.0 && yq < pr.y) ? 1u : 0u;
+  }
+#else
   for (uint32_t q = qb; q < qe; ++q)
     if (parea[q] > 0.0 && pairs[q].y < pr.y) ++rank;
-  const size_t o = (size_t)out_off[pr.x] + rank;
+#endif
+  const size_t o = obase + rank;
   const long long s = sm.cell(pr.x);
   const int tl = find_tile(tiles, ntiles, s);
   const long long c = s - tiles[tl].cell_off;
@@ -2174,9 +2189,15 @@ order2_finalize_kernel(CellSet src, SrcMap sm, const uint32_t* __restrict__ out_
   if (b == e) return;
   if (e - b > kLongSegment) return;                              // order2_finalize_long_kernel (the cell is on the heavy list)
   double sa = 0.0, sx = 0.0, sy = 0.0;
+#if XGB_SCATTER_VARIANT
+#pragma unroll 4
+#endif
   for (uint32_t k = b; k < e; ++k) { sa += area[k]; sx += clon[k]; sy += clat[k]; }
   double cx, cy;
   cell_centroid(src, sm.cell(t), sa, sx, sy, &cx, &cy);
+#if XGB_SCATTER_VARIANT
+#pragma unroll 4
+#endif
   for (uint32_t k = b; k < e; ++k) {                             // :256-257 then :355-356
     const double a = area[k];
     double u = clon[k] / a, v = clat[k] / a;
