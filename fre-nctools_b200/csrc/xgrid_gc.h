@@ -22,8 +22,9 @@ struct Pyramid3 { int nlev; Pyr3Level lev[kMaxLevels]; };
 
 void launch_gc_cell_precompute(const TileDesc& tile, const double* lon, const double* lat, GcCells cells, int* err, cudaStream_t st);
 void launch_gc_pyramid_level(const Pyr3Level& child, Box3* out, int nx, int ny, cudaStream_t st);
+size_t gc_slot_bytes(long long ns);
 void launch_gc_candidates(bool fill, const GcCells& src, const GcCells& dst, long long s0, long long ns, const double* mask, const Pyramid3& pyr,
-                          const uint32_t* pair_off, uint32_t* cnt, int2* pairs, int* err, cudaStream_t st);
+                          const uint32_t* pair_off, uint32_t* cnt, int2* pairs, int* err, cudaStream_t st, int* slots = nullptr);
 // box candidates -> pairs no side separates: flag[p] per pair; then (after an exclusive scan of the flags into pos) the kept
 // pairs in order and the per-source-cell offsets / counts rewritten for them
 void launch_gc_filter(const GcCells& src, const GcCells& dst, const int2* pairs, unsigned long long npairs, long long s0, uint32_t* flag,

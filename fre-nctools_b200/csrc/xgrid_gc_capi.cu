@@ -81,10 +81,11 @@ long long xgb_generate_great_circle(xgb_plan* p, int order)
   const double* mask = p->has_mask ? (const double*)p->mask.p : nullptr;
   if (p->cnt.reserve((size_t)(ns + 1) * 4) || p->pair_off.reserve((size_t)(ns + 1) * 4) || p->pair_cnt.reserve((size_t)(ns + 1) * 4) ||
       p->out_off.reserve((size_t)(ns + 1) * 4) ||
-      p->scan_tmp.reserve(scan_tmp_bytes(ns)))
+      p->scan_tmp.reserve(scan_tmp_bytes(ns)) || p->clon.reserve(gc_slot_bytes(ns) + 16))       // clon: free on this path (order 1)
     return -1;
+  int* slots = (int*)p->clon.p;
   cudaEventRecord(p->ev[0], p->st);
-  launch_gc_candidates(false, p->gc_src, p->gc_dst, s0, ns, mask, p->gc_pyr, nullptr, (uint32_t*)p->pair_cnt.p, nullptr, p->err_dev, p->st);
+  launch_gc_candidates(false, p->gc_src, p->gc_dst, s0, ns, mask, p->gc_pyr, nullptr, (uint32_t*)p->pair_cnt.p, nullptr, p->err_dev, p->st, slots);
   launch_exclusive_scan((const uint32_t*)p->pair_cnt.p, (uint32_t*)p->pair_off.p, ns, p->total_dev, p->scan_tmp.p, p->st);
   launch_publish(p->total_host, p->total_dev, 2, p->st);
   if (cudaStreamSynchronize(p->st) != cudaSuccess) {
@@ -97,7 +98,7 @@ long long xgb_generate_great_circle(xgb_plan* p, int order)
   cudaEventRecord(p->ev[1], p->st);
   if (p->pairs.reserve((size_t)npairs * sizeof(int2) + 16) || p->parea.reserve((size_t)npairs * 8 + 16)) return -1;
   launch_gc_candidates(true, p->gc_src, p->gc_dst, s0, ns, mask, p->gc_pyr, (const uint32_t*)p->pair_off.p, (uint32_t*)p->pair_cnt.p,
-                       (int2*)p->pairs.p, p->err_dev, p->st);
+                       (int2*)p->pairs.p, p->err_dev, p->st, slots);
   // second stage: drop the pairs a side separates (pclon / pclat are free on this path: flags, their scan; clip_vx: kept pairs)
   const unsigned long long nbox = npairs;
   unsigned long long nkept = nbox;

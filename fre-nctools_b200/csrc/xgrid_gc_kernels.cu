@@ -181,16 +181,28 @@ void launch_gc_compact(const int2* pairs, unsigned long long npairs, const uint3
   gc_reoffset_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(ns, pair_off, pair_cnt, pos);
 }
 
+// The count pass leaves the first kGcSlots candidates of every source cell in `slots` (a 1/4 degree cell meets 1.7 one-degree
+// cells on average); the fill pass copies them instead of walking the pyramid a second time and walks only for the cells
+// that had more.  Same candidates in the same order.
+constexpr int kGcSlots = 8;
 template <bool FILL>
 __global__ void __launch_bounds__(128)
 gc_candidate_kernel(GcCells src, GcCells dst, long long s0, long long ns, const double* __restrict__ mask, Pyramid3 pyr,
-                    const uint32_t* __restrict__ pair_off, uint32_t* __restrict__ cnt, int2* __restrict__ pairs, int* err)
+                    const uint32_t* __restrict__ pair_off, uint32_t* __restrict__ cnt, int2* __restrict__ pairs,
+                    int* __restrict__ slots, int* err)
 {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= ns) return;
   const long long s = s0 + t;
   uint32_t n = 0;
   const uint32_t base = FILL ? pair_off[t] : 0u;
+  if (FILL && slots) {
+    const uint32_t have = cnt[t];
+    if (have <= (uint32_t)kGcSlots) {
+      for (uint32_t k = 0; k < have; ++k) pairs[base + k] = make_int2((int)t, slots[t * kGcSlots + k]);
+      return;
+    }
+  }
   if (mask == nullptr || mask[s] > kMaskThresh) {                          // create_xgrid.c:1419
     const Box3 sb = load_box3(src.box + s);
     unsigned long long stack[kGcStack];
@@ -202,7 +214,7 @@ gc_candidate_kernel(GcCells src, GcCells dst, long long s0, long long ns, const 
         for (int ix = 0; ix < L.nx; ++ix) {
           const long long q = (long long)iy * L.nx + ix;
           if (!boxes_meet(load_box3(L.box + q), sb)) continue;
-          if (top == 0) { if (FILL) pairs[base + n] = make_int2((int)t, (int)q); ++n; }
+          if (top == 0) { if (FILL) pairs[base + n] = make_int2((int)t, (int)q); else if (slots && n < (uint32_t)kGcSlots) slots[t * kGcSlots + n] = (int)q; ++n; }
           else stack[sp++] = ((unsigned long long)top << 58) | ((unsigned long long)iy << 29) | (unsigned long long)ix;
         }
     }
@@ -219,7 +231,7 @@ gc_candidate_kernel(GcCells src, GcCells dst, long long s0, long long ns, const 
           if (cx >= L.nx) continue;
           const long long q = (long long)cy * L.nx + cx;
           if (!boxes_meet(load_box3(L.box + q), sb)) continue;
-          if (lev == 0) { if (FILL) pairs[base + n] = make_int2((int)t, (int)q); ++n; }
+          if (lev == 0) { if (FILL) pairs[base + n] = make_int2((int)t, (int)q); else if (slots && n < (uint32_t)kGcSlots) slots[t * kGcSlots + n] = (int)q; ++n; }
           else if (sp < kGcStack) stack[sp++] = ((unsigned long long)lev << 58) | ((unsigned long long)cy << 29) | (unsigned long long)cx;
           else atomicOr(err, kErrStackOverflow);
         }
@@ -229,14 +241,16 @@ gc_candidate_kernel(GcCells src, GcCells dst, long long s0, long long ns, const 
   if (!FILL) cnt[t] = n;
 }
 
+size_t gc_slot_bytes(long long ns) { return (size_t)ns * kGcSlots * sizeof(int); }
+
 void launch_gc_candidates(bool fill, const GcCells& src, const GcCells& dst, long long s0, long long ns, const double* mask, const Pyramid3& pyr,
-                          const uint32_t* pair_off, uint32_t* cnt, int2* pairs, int* err, cudaStream_t st)
+                          const uint32_t* pair_off, uint32_t* cnt, int2* pairs, int* err, cudaStream_t st, int* slots)
 {
   if (ns <= 0) return;
   const unsigned blocks = (unsigned)((ns + 127) / 128);
   ++g_launches;
-  if (fill) gc_candidate_kernel<true><<<blocks, 128, 0, st>>>(src, dst, s0, ns, mask, pyr, pair_off, cnt, pairs, err);
-  else      gc_candidate_kernel<false><<<blocks, 128, 0, st>>>(src, dst, s0, ns, mask, pyr, pair_off, cnt, pairs, err);
+  if (fill) gc_candidate_kernel<true><<<blocks, 128, 0, st>>>(src, dst, s0, ns, mask, pyr, pair_off, cnt, pairs, slots, err);
+  else      gc_candidate_kernel<false><<<blocks, 128, 0, st>>>(src, dst, s0, ns, mask, pyr, pair_off, cnt, pairs, slots, err);
 }
 
 // Block size.  The kernel is 6 700 SASS instructions plus the double-double routines it calls, and ncu named "no instruction"
