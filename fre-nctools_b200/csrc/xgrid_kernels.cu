@@ -383,7 +383,7 @@ __device__ __forceinline__ bool rect_column_hit(const RectDst& R, int i, const S
 // more than kSingleMax candidates, or too many node expansions, take the heavy path exactly as in the count pass.
 // Writes are dropped when the pair buffer (cap entries) is too small; the host sees ctl->total > cap and retries.
 #ifndef XGB_SINGLE_MAX
-#define XGB_SINGLE_MAX 32
+#define XGB_SINGLE_MAX 64   // 24: 3.78 ms, 32: 3.72, 48: 3.71, 64: 3.70 (C768 step; a polar rank of 8: 0.723 -> 0.709 ms)
 #endif
 constexpr int kSingleMax = XGB_SINGLE_MAX;   // thread-local buffer; beyond it the cell goes to the heavy path
 
@@ -2159,6 +2159,10 @@ void launch_scatter(int order, const int2* pairs, unsigned long long npairs,
 // clon/clat hold xgrid_clon/xgrid_clat on entry; di/dj receive tile1_distance.
 // =============================================================================================
 constexpr uint32_t kLongSegment = 64;     // source cells with more exchange cells than this are summed by a whole warp
+// order2_finalize_long_kernel finds its cells on the heavy list, and a cell is on that list only if it has more than kSingleMax
+// candidates: a larger kSingleMax would leave cells with kLongSegment < n <= kSingleMax exchange cells to nobody (measured:
+// XGB_SINGLE_MAX = 96 changes tile1_distance)
+static_assert(kSingleMax <= (int)kLongSegment, "cells off the heavy list must fit order2_finalize_kernel's per-thread sum");
 
 // centroid of a source cell from the sums over its exchange cells (conserve_interp.c:326-348)
 __device__ __forceinline__ void cell_centroid(const CellSet& src, long long s, double sa, double sx, double sy, double* cx, double* cy)
