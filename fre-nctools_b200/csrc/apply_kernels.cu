@@ -497,7 +497,10 @@ __host__ __device__ __forceinline__ long long rec_index(long long cell, int f, i
   return ((cell * (nfp / kRecLane) + (f / kRecLane)) * nc + comp) * kRecLane + (f % kRecLane);
 }
 constexpr int kRecFields = 8;      // field-levels a gradient block transposes at a time
-constexpr int kRecChunk = 32;      // field-levels per gradient block
+#ifndef XGB_REC_CHUNK
+#define XGB_REC_CHUNK 16   // configs[1] regrid: 8: 2.288 ms, 16: 2.291, 32: 2.32, 64: 2.42, 128: 2.66
+#endif
+constexpr int kRecChunk = XGB_REC_CHUNK;      // field-levels per gradient block
 
 #ifndef XGB_GRAD_UNROLL
 #define XGB_GRAD_UNROLL 1
