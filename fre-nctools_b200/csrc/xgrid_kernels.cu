@@ -1665,7 +1665,7 @@ clip2_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const in
 #define XGB_CLIP_SPLIT 1
 #endif
 #ifndef XGB_SPLIT_BLOCKS1
-#define XGB_SPLIT_BLOCKS1 6
+#define XGB_SPLIT_BLOCKS1 7   // clip_sh at 72 registers: clip phase 2.72 -> 2.66 ms (5: 2.74, 6: 2.72, 7: 2.66, 8: 3.45 with spills)
 #endif
 #ifndef XGB_SPLIT_BLOCKS2
 #define XGB_SPLIT_BLOCKS2 7
