@@ -1671,9 +1671,9 @@ clip2_kernel(CellSet src, CellSet dst, const double* __restrict__ mask, const in
 #define XGB_SPLIT_BLOCKS2 7
 #endif
 #ifndef XGB_WARP_CAP
-#define XGB_WARP_CAP 192
+#define XGB_WARP_CAP 160   // clip phase: 128: 2.680 ms, 160: 2.645, 192: 2.661
 #endif
-constexpr int kWarpCap = XGB_WARP_CAP;    // vertices per warp region (6 per pair; the mean is 3.6)
+constexpr int kWarpCap = XGB_WARP_CAP;    // vertices per warp region (5 per pair; the mean is 3.6; what does not fit is finished in clip_sh)
 constexpr int kSplitCap = 4 * kWarpCap;   // per block of 4 warps
 
 // the tail every pair goes through once its polygon's sums are known (create_xgrid.c:805-820, :1091-1097)
