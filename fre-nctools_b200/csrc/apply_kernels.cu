@@ -724,7 +724,10 @@ struct RecPair {
 #endif
 constexpr int kTileR = XGB_TILE_R;
 
-template <bool MISSING>
+// WF: warps of the block along the field-levels (64 each).  With few field-levels (a rank's share of a batch on 8 GPUs: 50)
+// a block of four field-warps would have three of them idle; the block then takes 4 / WF destination tiles instead, one per
+// group of WF warps, each group staging its own tile.
+template <bool MISSING, int WF>
 __global__ void __launch_bounds__(128, XGB_APPLY_BLOCKS)
 apply_rec_kernel(ApplyCsr csr, long long ndst, int nx2, int nf, int nfp, const double* __restrict__ rec, double missing, int sum_mode,
                  double* __restrict__ out)
@@ -732,11 +735,17 @@ apply_rec_kernel(ApplyCsr csr, long long ndst, int nx2, int nf, int nfp, const d
   constexpr int NC = MISSING ? 4 : 3;
   constexpr int kResRow = 64 + 4;                                 // row stride = 4 mod 16 doubles: the transposed reads below are conflict-free
   __shared__ __align__(16) double res[4][kTileD][kResRow];        // [warp][destination cell][field]
-  __shared__ uint32_t s_off[kTileD + 1];
-  __shared__ TileEntry s_ent[kTileE];
+  constexpr int NT = 4 / WF;                                      // destination tiles per block
+  constexpr int G = WF * 32;                                      // threads of one tile's group
+  static_assert(kTileR == 1 || WF == 4, "row-walking patches take one tile per block");
+  __shared__ uint32_t s_off_all[NT][kTileD + 1];
+  __shared__ TileEntry s_ent_all[NT][kTileE];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int tsub = wid / WF, wf = wid % WF, lt = threadIdx.x - tsub * G;
+  uint32_t* s_off = s_off_all[tsub];
+  TileEntry* s_ent = s_ent_all[tsub];
   const long long cbytes = (long long)NC * nfp * 8;                // bytes of one source cell's records
-  const int fw = blockIdx.y * 256 + wid * 64;                    // this warp's 64 field-levels
+  const int fw = blockIdx.y * (WF * 64) + wf * 64;               // this warp's 64 field-levels
   const bool wactive = fw < nf;                                   // warp-uniform
   const int f = fw + 2 * lane;                                    // this lane's two: f, f + 1
   const bool l0 = wactive && f < nf;
@@ -747,8 +756,9 @@ apply_rec_kernel(ApplyCsr csr, long long ndst, int nx2, int nf, int nfp, const d
   long long d0;
   int nd;
   if (kTileR == 1) {                                              // flat tiles over the destination index (rows may be ragged)
-    d0 = (long long)blockIdx.x * kTileD;
+    d0 = ((long long)blockIdx.x * NT + tsub) * kTileD;
     nd = (ndst - d0 < kTileD) ? (int)(ndst - d0) : kTileD;
+    if (nd < 0) nd = 0;                                           // a tile past the end (the last block's spare groups)
   } else {
     const long long j = (long long)(blockIdx.x / tiles_per_row) * kTileR + row;
     const int i0 = (int)(blockIdx.x % tiles_per_row) * kTileD;
@@ -757,13 +767,13 @@ apply_rec_kernel(ApplyCsr csr, long long ndst, int nx2, int nf, int nfp, const d
     nd = (nx2 - i0 < kTileD) ? nx2 - i0 : kTileD;
     __syncthreads();                                              // the previous row's staging is no longer read
   }
-  if (threadIdx.x <= kTileD) s_off[threadIdx.x] = csr.off[d0 + (threadIdx.x < nd ? threadIdx.x : nd)];
+  if (lt <= kTileD) s_off[lt] = (nd > 0) ? csr.off[d0 + (lt < nd ? lt : nd)] : 0u;
   __syncthreads();
   const uint32_t q0 = s_off[0];
   const int ne = (int)(s_off[nd] - q0);
   const bool staged = ne <= kTileE;
   if (staged)
-    for (int k = threadIdx.x; k < ne; k += 128)
+    for (int k = lt; k < ne; k += G)
       s_ent[k] = TileEntry{csr.area[q0 + k], csr.di[q0 + k], csr.dj[q0 + k], (long long)csr.cell[q0 + k] * cbytes};
   __syncthreads();
   if (!wactive) continue;                                         // (still takes part in the barriers of the next row)
@@ -868,16 +878,17 @@ void launch_regrid_rec(const GradTile* tiles, int ntiles, long long ncell, int n
   const dim3 gblk((unsigned)((ncell + 127) / 128), (unsigned)((nf + kRecChunk - 1) / kRecChunk));
   const long long atiles = (kTileR == 1) ? (ndst + kTileD - 1) / kTileD
                                          : (long long)((nx2 + kTileD - 1) / kTileD) * ((ndst / nx2 + kTileR - 1) / kTileR);
-  if (atiles >= (1ll << 31)) return;
-  const dim3 ablk((unsigned)atiles, (unsigned)((nf + 255) / 256));
+  const int wf = (kTileR != 1 || nf > 128) ? 4 : (nf > 64 ? 2 : 1);     // warps along the field-levels
+  const long long ablocks = (atiles + 4 / wf - 1) / (4 / wf);
+  if (ablocks >= (1ll << 31)) return;
+  const dim3 ablk((unsigned)ablocks, (unsigned)((nf + wf * 64 - 1) / (wf * 64)));
   g_launches += 2;
-  if (has_missing) {
-    grad_c2l_rec_kernel<true><<<gblk, 128, 0, st>>>(tiles, ntiles, ncell, nf, nfp, data, data_stride, rec, missing);
-    apply_rec_kernel<true><<<ablk, 128, 0, st>>>(csr, ndst, nx2, nf, nfp, rec, apply_missing, sum_mode, out);
-  } else {
-    grad_c2l_rec_kernel<false><<<gblk, 128, 0, st>>>(tiles, ntiles, ncell, nf, nfp, data, data_stride, rec, missing);
-    apply_rec_kernel<false><<<ablk, 128, 0, st>>>(csr, ndst, nx2, nf, nfp, rec, apply_missing, sum_mode, out);
-  }
+  if (has_missing) grad_c2l_rec_kernel<true><<<gblk, 128, 0, st>>>(tiles, ntiles, ncell, nf, nfp, data, data_stride, rec, missing);
+  else             grad_c2l_rec_kernel<false><<<gblk, 128, 0, st>>>(tiles, ntiles, ncell, nf, nfp, data, data_stride, rec, missing);
+#define XGB_APPLY_REC(M, W) apply_rec_kernel<M, W><<<ablk, 128, 0, st>>>(csr, ndst, nx2, nf, nfp, rec, apply_missing, sum_mode, out)
+  if (has_missing) { if (wf == 4) XGB_APPLY_REC(true, 4); else if (wf == 2) XGB_APPLY_REC(true, 2); else XGB_APPLY_REC(true, 1); }
+  else             { if (wf == 4) XGB_APPLY_REC(false, 4); else if (wf == 2) XGB_APPLY_REC(false, 2); else XGB_APPLY_REC(false, 1); }
+#undef XGB_APPLY_REC
 }
 
 // =============================================================================================

@@ -11,7 +11,7 @@ import torch  # noqa: E402
 import xgtest  # noqa: E402
 
 pkg = xgtest.package()
-ni, nlon, nlat, B = 96, 1440, 720, 396
+ni, nlon, nlat, B = 96, 1440, 720, (int(sys.argv[3]) if len(sys.argv) > 3 else 396)
 lonc, latc, lont, latt = pkg.cubed_sphere_grid(ni, centers=True)
 lon2, lat2 = pkg.latlon_grid(nlon, nlat)
 hm = xgtest.cubed_sphere_halo_map(lonc, latc)
